@@ -1,0 +1,607 @@
+// C-ABI of libsina_b200.so (see include/sina_b200.h): index / session lifetime, stage drivers, host-buffer
+// wrappers. No torch types, no exceptions across the boundary, no CPU fallback.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace sg {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+template <typename T>
+static int dmalloc(T** p, uint64_t n) {
+    *p = nullptr;
+    SG_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
+    return SG_OK;
+}
+#define SG_TRY(x)                  \
+    do {                           \
+        int rc__ = (x);            \
+        if (rc__ != SG_OK) return rc__; \
+    } while (0)
+
+static uint64_t env_mb(const char* name, uint64_t dflt_mb) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt_mb;
+    return strtoull(v, nullptr, 10);
+}
+
+static void free_align(Session* s) {
+    void* ptrs[] = {s->d_afam, s->d_afam_n, s->d_contains, s->d_copy_src, s->d_tab, s->d_tabli, s->d_colof, s->d_colbase,
+                    s->d_item_node, s->d_slot, s->d_ncol, s->d_nmask, s->d_ncount, s->d_nweight, s->d_nsigma,
+                    s->d_slotbase, s->d_cursor, s->d_pred_off, s->d_preds, s->d_pdesc, s->d_spillrow, s->d_nflags,
+                    s->d_lastnodes, s->d_groups, s->d_lastcol, s->d_rowmin, s->d_rowarg, s->d_tb, s->d_spill,
+                    s->d_fam_ids, s->d_fam_scores};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s->d_afam = nullptr; s->d_afam_n = nullptr; s->d_contains = nullptr; s->d_copy_src = nullptr; s->d_tab = nullptr;
+    s->d_tabli = nullptr; s->d_colof = nullptr; s->d_colbase = nullptr; s->d_item_node = nullptr; s->d_slot = nullptr;
+    s->d_ncol = nullptr; s->d_nmask = nullptr; s->d_ncount = nullptr; s->d_nweight = nullptr; s->d_nsigma = nullptr;
+    s->d_slotbase = nullptr; s->d_cursor = nullptr; s->d_pred_off = nullptr; s->d_preds = nullptr; s->d_pdesc = nullptr;
+    s->d_spillrow = nullptr; s->d_nflags = nullptr; s->d_lastnodes = nullptr; s->d_groups = nullptr;
+    s->d_lastcol = nullptr; s->d_rowmin = nullptr; s->d_rowarg = nullptr; s->d_tb = nullptr; s->d_spill = nullptr;
+    s->d_fam_ids = nullptr; s->d_fam_scores = nullptr;
+    s->fam_cap = 0; s->icap = 0;
+}
+
+// (re)allocate everything whose size depends on the family capacity
+static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
+    if (fam_cap <= s->fam_cap) return SG_OK;
+    if (fam_cap > FAM_CAP_MAX) SG_FAIL(SG_ERR_LIMIT, "family size above 255 is not supported");
+    free_align(s);
+    Index* ix = s->ix;
+    const uint64_t Q = s->max_q;
+    s->fam_cap = fam_cap;
+    s->icap = fam_cap * ix->max_row_len;
+    s->ncap = ix->W < s->icap ? ix->W : s->icap;
+    s->gcap = s->icap / DP_THREADS + 1;
+    const uint64_t I = s->icap;
+    SG_TRY(dmalloc(&s->d_fam_ids, Q * fam_cap)); SG_TRY(dmalloc(&s->d_fam_scores, Q * fam_cap));
+    SG_TRY(dmalloc(&s->d_afam, Q * fam_cap)); SG_TRY(dmalloc(&s->d_afam_n, Q));
+    SG_TRY(dmalloc(&s->d_contains, Q * fam_cap)); SG_TRY(dmalloc(&s->d_copy_src, Q * 2));
+    SG_TRY(dmalloc(&s->d_tab, Q * s->ncap * fam_cap)); SG_TRY(dmalloc(&s->d_tabli, Q * s->ncap * fam_cap));
+    SG_TRY(dmalloc(&s->d_colof, Q * s->ncap)); SG_TRY(dmalloc(&s->d_colbase, Q * (s->ncap + 1)));
+    SG_TRY(dmalloc(&s->d_item_node, Q * I)); SG_TRY(dmalloc(&s->d_slot, Q * I));
+    SG_TRY(dmalloc(&s->d_ncol, Q * I)); SG_TRY(dmalloc(&s->d_nmask, Q * I)); SG_TRY(dmalloc(&s->d_ncount, Q * I));
+    SG_TRY(dmalloc(&s->d_nweight, Q * I)); SG_TRY(dmalloc(&s->d_nsigma, Q * I));
+    SG_TRY(dmalloc(&s->d_slotbase, Q * (I + 1))); SG_TRY(dmalloc(&s->d_cursor, Q * I));
+    SG_TRY(dmalloc(&s->d_pred_off, Q * (I + 1))); SG_TRY(dmalloc(&s->d_preds, Q * I));
+    SG_TRY(dmalloc(&s->d_pdesc, Q * I)); SG_TRY(dmalloc(&s->d_spillrow, Q * I)); SG_TRY(dmalloc(&s->d_nflags, Q * I));
+    SG_TRY(dmalloc(&s->d_lastnodes, Q * I)); SG_TRY(dmalloc(&s->d_groups, Q * s->gcap));
+    SG_TRY(dmalloc(&s->d_lastcol, Q * I)); SG_TRY(dmalloc(&s->d_rowmin, Q * I)); SG_TRY(dmalloc(&s->d_rowarg, Q * I));
+    // arenas: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
+    const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
+    uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, Q * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
+    uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, Q * (256 * max_qlen_guess * 8 / 1000000 + 1))));
+    s->tb_words = tb_mb * 1024 * 1024 / 4;
+    s->spill_elems = sp_mb * 1024 * 1024 / 8;
+    SG_TRY(dmalloc(&s->d_tb, s->tb_words)); SG_TRY(dmalloc(&s->d_spill, s->spill_elems));
+    return SG_OK;
+}
+
+static int stage_begin(Session* s, int st) { SG_CUDA(cudaEventRecord(s->ev[0], s->stream)); (void)st; return SG_OK; }
+static int stage_end(Session* s, float* acc) {
+    SG_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    SG_CUDA(cudaEventSynchronize(s->ev[1]));
+    float ms = 0.f;
+    SG_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+    *acc += ms;
+    return SG_OK;
+}
+
+static int validate_align_params(const sg_align_params* ap) {
+    if (!ap) SG_FAIL(SG_ERR_ARG, "align params missing");
+    if (ap->insertion == 1) SG_FAIL(SG_ERR_ARG, "--insertion forbid is not supported (reference transition_aspace_aware)");
+    if (ap->insertion < 0 || ap->insertion > 2 || ap->overhang < 0 || ap->overhang > 2 || ap->lowercase < 0 || ap->lowercase > 2)
+        SG_FAIL(SG_ERR_ARG, "align params: enum out of range");
+    return SG_OK;
+}
+static int validate_fam_params(const sg_fam_params* fp) {
+    if (!fp) SG_FAIL(SG_ERR_ARG, "family params missing");
+    if (fp->fs_msc_max < 1.0f) SG_FAIL(SG_ERR_ARG, "--fs-msc-max < 1 needs the identity filter: not supported");
+    if (fp->fs_max == 0) SG_FAIL(SG_ERR_ARG, "--fs-max must be > 0");
+    return SG_OK;
+}
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+
+const char* sg_last_error(void) { return g_err.c_str(); }
+
+int sg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+void sg_default_fam_params(sg_fam_params* p) {
+    p->fs_min = 40; p->fs_max = 40; p->fs_msc = 0.7f; p->fs_msc_max = 2.0f; p->fs_min_len = 150; p->fs_req_full = 1;
+    p->fs_full_len = 1400; p->fs_req_gaps = 10; p->fs_req = 1; p->leave_query_out = 0;
+}
+void sg_default_align_params(sg_align_params* p) {
+    p->match_score = 2.f; p->mismatch_score = -1.f; p->gap_penalty = 5.f; p->gap_ext_penalty = 2.f; p->fs_weight = 1.f;
+    p->overhang = 0; p->lowercase = 0; p->insertion = 0; p->realign = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ index
+int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* row_off, uint32_t N, uint32_t W,
+                    int k, int nofast, int device, sg_index** out) {
+    if (!masks || !cols || !row_off || !out) SG_FAIL(SG_ERR_ARG, "sg_index_create: null argument");
+    if (N == 0) SG_FAIL(SG_ERR_ARG, "sg_index_create: empty reference");
+    if (k < 1 || k > MAX_K) SG_FAIL(SG_ERR_ARG, "K must be in 1..16");  // src/kmer.h:57-62
+    if (W == 0 || W > 786432) SG_FAIL(SG_ERR_LIMIT, "alignment width must be in 1..786432 columns");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        SG_FAIL(SG_ERR_CUDA, "no CUDA device: sina_b200 has no CPU path");
+    if (device < 0 || device >= ndev) SG_FAIL(SG_ERR_ARG, "sg_index_create: bad device ordinal");
+    const uint64_t total = row_off[N];
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < N; i++) {
+        if (row_off[i + 1] < row_off[i]) SG_FAIL(SG_ERR_ARG, "row_off must be non-decreasing");
+        const uint64_t a = row_off[i], b = row_off[i + 1];
+        if (b - a > max_len) max_len = (uint32_t)(b - a);
+        for (uint64_t j = a; j < b; j++) {
+            if ((masks[j] & 15) == 0 || masks[j] > 31) SG_FAIL(SG_ERR_ARG, "reference base is not an IUPAC mask");
+            if (cols[j] >= W || (j > a && cols[j] <= cols[j - 1]))
+                SG_FAIL(SG_ERR_ARG, "reference columns must be < W and strictly increasing inside a row");
+        }
+    }
+    Index* ix = new Index;
+    ix->device = device; ix->N = N; ix->W = W; ix->k = k; ix->nofast = nofast ? 1 : 0;
+    ix->max_row_len = max_len ? max_len : 1; ix->total_bases = total;
+    if (N <= TILE_MAX) { ix->tile_size = N + (N & 1); ix->n_tiles = 1; }
+    else { ix->tile_size = TILE_MAX; ix->n_tiles = (N + TILE_MAX - 1) / TILE_MAX; }
+    ix->n_slots = 1ull << (2 * (nofast ? k : k - 1));
+    if ((uint64_t)ix->n_tiles * ix->n_slots > (1ull << 31)) {
+        delete ix;
+        SG_FAIL(SG_ERR_LIMIT, "k-mer table too large for this k and reference size");
+    }
+    auto fail = [&](int rc) { sg_index_destroy((sg_index*)ix); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(SG_ERR_CUDA); }
+    int rc;
+    if ((rc = dmalloc(&ix->d_masks, total + 16)) || (rc = dmalloc(&ix->d_cols, total + 4)) ||
+        (rc = dmalloc(&ix->d_row_off, (uint64_t)N + 1)))
+        return fail(rc);
+    if (cudaMemcpy(ix->d_masks, masks, total, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ix->d_cols, cols, total * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(ix->d_row_off, row_off, ((uint64_t)N + 1) * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("sg_index_create: upload failed");
+        return fail(SG_ERR_CUDA);
+    }
+    cudaStream_t st;
+    if (cudaStreamCreate(&st) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(SG_ERR_CUDA); }
+    rc = launch_index_build(ix, st);
+    cudaStreamDestroy(st);
+    if (rc) return fail(rc);
+    *out = (sg_index*)ix;
+    return SG_OK;
+}
+
+void sg_index_destroy(sg_index* h) {
+    Index* ix = (Index*)h;
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->d_masks); cudaFree(ix->d_cols); cudaFree(ix->d_row_off); cudaFree(ix->d_list_off);
+    cudaFree(ix->d_postings);
+    delete ix;
+}
+
+int sg_index_info(const sg_index* h, uint32_t* N, uint32_t* W, int* k, int* nofast, uint64_t* n_postings,
+                  uint32_t* n_tiles, uint32_t* tile_size) {
+    const Index* ix = (const Index*)h;
+    if (!ix) SG_FAIL(SG_ERR_ARG, "null index");
+    if (N) *N = ix->N;
+    if (W) *W = ix->W;
+    if (k) *k = ix->k;
+    if (nofast) *nofast = ix->nofast;
+    if (n_postings) *n_postings = ix->n_postings;
+    if (n_tiles) *n_tiles = ix->n_tiles;
+    if (tile_size) *tile_size = ix->tile_size;
+    return SG_OK;
+}
+
+int sg_index_list(const sg_index* h, uint32_t kmer, uint32_t* ids, uint64_t cap, uint64_t* n) {
+    const Index* ix = (const Index*)h;
+    if (!ix || !n) SG_FAIL(SG_ERR_ARG, "null argument");
+    *n = 0;
+    if (kmer >= ix->n_slots) return SG_OK;  // fast mode: k-mers not starting with A have no list
+    SG_CUDA(cudaSetDevice(ix->device));
+    std::vector<uint32_t> all;
+    for (uint32_t t = 0; t < ix->n_tiles; t++) {
+        uint64_t ab[2];
+        SG_CUDA(cudaMemcpy(ab, ix->d_list_off + (uint64_t)t * ix->n_slots + kmer, 16, cudaMemcpyDeviceToHost));
+        size_t o = all.size();
+        all.resize(o + (ab[1] - ab[0]));
+        if (ab[1] > ab[0])
+            SG_CUDA(cudaMemcpy(all.data() + o, ix->d_postings + ab[0], (ab[1] - ab[0]) * 4, cudaMemcpyDeviceToHost));
+    }
+    std::sort(all.begin(), all.end());
+    *n = all.size();
+    if (ids) memcpy(ids, all.data(), std::min<uint64_t>(cap, all.size()) * 4);
+    return SG_OK;
+}
+
+int sg_index_list_sizes(const sg_index* h, const uint32_t* kmers, uint32_t n, uint64_t* sizes) {
+    const Index* ix = (const Index*)h;
+    if (!ix || !kmers || !sizes) SG_FAIL(SG_ERR_ARG, "null argument");
+    SG_CUDA(cudaSetDevice(ix->device));
+    for (uint32_t i = 0; i < n; i++) {
+        sizes[i] = 0;
+        if (kmers[i] >= ix->n_slots) continue;
+        for (uint32_t t = 0; t < ix->n_tiles; t++) {
+            uint64_t ab[2];
+            SG_CUDA(cudaMemcpy(ab, ix->d_list_off + (uint64_t)t * ix->n_slots + kmers[i], 16, cudaMemcpyDeviceToHost));
+            sizes[i] += ab[1] - ab[0];
+        }
+    }
+    return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- session
+int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_session** out) {
+    Index* ix = (Index*)h;
+    if (!ix || !out || max_queries == 0) SG_FAIL(SG_ERR_ARG, "sg_session_create: bad argument");
+    SG_CUDA(cudaSetDevice(ix->device));
+    Session* s = new Session;
+    s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
+    *out = (sg_session*)s;
+    SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) SG_CUDA(cudaEventCreate(&e));
+    const uint64_t Q = max_queries;
+    SG_TRY(dmalloc(&s->d_qmasks, s->max_bases + 16)); SG_TRY(dmalloc(&s->d_qoff, Q + 1)); SG_TRY(dmalloc(&s->d_excl, Q));
+    SG_TRY(dmalloc(&s->d_cand_n, Q * ix->n_tiles)); SG_TRY(dmalloc(&s->d_nres, Q)); SG_TRY(dmalloc(&s->d_counters, 8));
+    SG_TRY(dmalloc(&s->d_fam_n, Q)); SG_TRY(dmalloc(&s->d_retry, 2)); SG_TRY(dmalloc(&s->d_hdr, Q));
+    SG_TRY(dmalloc(&s->d_out_cols, s->max_bases + 4)); SG_TRY(dmalloc(&s->d_out_masks, s->max_bases + 16));
+    SG_TRY(dmalloc(&s->d_results, Q));
+    SG_CUDA(cudaMemset(s->d_counters, 0, 64));
+    s->h_qoff = (uint64_t*)malloc((Q + 1) * 8);
+    return SG_OK;
+}
+
+void sg_session_destroy(sg_session* h) {
+    Session* s = (Session*)h;
+    if (!s) return;
+    cudaSetDevice(s->ix->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    free_align(s);
+    void* ptrs[] = {s->d_qmasks, s->d_qoff, s->d_excl, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
+                    s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    free(s->h_qoff);
+    delete s;
+}
+
+int sg_session_upload(sg_session* h, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
+                      const int64_t* exclude_ids) {
+    Session* s = (Session*)h;
+    if (!s || !qmasks || !qoff) SG_FAIL(SG_ERR_ARG, "sg_session_upload: null argument");
+    if (nq == 0 || nq > s->max_q) SG_FAIL(SG_ERR_ARG, "sg_session_upload: query count outside 1..max_queries");
+    const uint64_t base = qoff[0], total = qoff[nq] - base;
+    if (total > s->max_bases) SG_FAIL(SG_ERR_ARG, "sg_session_upload: more bases than the session holds");
+    for (uint32_t i = 0; i < nq; i++) {
+        if (qoff[i + 1] < qoff[i]) SG_FAIL(SG_ERR_ARG, "qoff must be non-decreasing");
+        const uint64_t l = qoff[i + 1] - qoff[i];
+        if (l < 2 || l > QLEN_MAX) SG_FAIL(SG_ERR_ARG, "query length must be in 2..65536 bases");
+        s->h_qoff[i] = qoff[i] - base;
+    }
+    s->h_qoff[nq] = total;
+    for (uint64_t j = 0; j < total; j++)
+        if ((qmasks[base + j] & 15) == 0 || qmasks[base + j] > 31) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    s->nq = nq;
+    SG_CUDA(cudaMemcpyAsync(s->d_qmasks, qmasks + base, total, cudaMemcpyHostToDevice, s->stream));
+    SG_CUDA(cudaMemcpyAsync(s->d_qoff, s->h_qoff, ((uint64_t)nq + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+    if (exclude_ids) SG_CUDA(cudaMemcpyAsync(s->d_excl, exclude_ids, (uint64_t)nq * 8, cudaMemcpyHostToDevice, s->stream));
+    else SG_CUDA(cudaMemsetAsync(s->d_excl, 0xff, (uint64_t)nq * 8, s->stream));
+    s->have_find = s->have_family = s->have_align = false;
+    return SG_OK;
+}
+
+int sg_session_find(sg_session* h, uint32_t max) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_find: no queries uploaded");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_TRY(stage_begin(s, 0));
+    SG_TRY(launch_find(s, max));
+    SG_TRY(stage_end(s, &s->stats.ms_find));
+    s->have_find = true;
+    return SG_OK;
+}
+
+int sg_session_family(sg_session* h, const sg_fam_params* fp) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_family: no queries uploaded");
+    SG_TRY(validate_fam_params(fp));
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_TRY(ensure_family_capacity(s, fp->fs_max + fp->fs_req_full + 1));
+    uint64_t window = (uint64_t)fp->fs_max + 1;  // famfinder.cpp:590
+    for (;;) {
+        const uint32_t w = (uint32_t)std::min<uint64_t>(window, s->ix->N);
+        SG_TRY(sg_session_find(h, w));
+        SG_TRY(stage_begin(s, 1));
+        SG_TRY(launch_family(s, *fp, s->find_max));
+        SG_TRY(stage_end(s, &s->stats.ms_family));
+        uint32_t retry = 0;
+        SG_CUDA(cudaMemcpyAsync(&retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        if (retry == 0 || w >= s->ix->N) break;
+        window *= 10;  // famfinder.cpp:607 (the whole batch is re-ranked with the wider window)
+    }
+    s->have_family = true;
+    return SG_OK;
+}
+
+int sg_session_set_family(sg_session* h, const uint32_t* fam_ids, const uint64_t* fam_off) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0 || !fam_ids || !fam_off) SG_FAIL(SG_ERR_ARG, "sg_session_set_family: bad argument");
+    uint32_t cap = 1;
+    for (uint32_t i = 0; i < s->nq; i++) {
+        if (fam_off[i + 1] < fam_off[i]) SG_FAIL(SG_ERR_ARG, "fam_off must be non-decreasing");
+        cap = std::max<uint32_t>(cap, (uint32_t)(fam_off[i + 1] - fam_off[i]));
+    }
+    for (uint64_t j = fam_off[0]; j < fam_off[s->nq]; j++)
+        if (fam_ids[j] >= s->ix->N) SG_FAIL(SG_ERR_ARG, "family id outside the index");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_TRY(ensure_family_capacity(s, cap));
+    std::vector<uint32_t> ids((uint64_t)s->nq * s->fam_cap, 0);
+    std::vector<int32_t> n(s->nq);
+    for (uint32_t i = 0; i < s->nq; i++) {
+        n[i] = (int32_t)(fam_off[i + 1] - fam_off[i]);
+        memcpy(&ids[(uint64_t)i * s->fam_cap], fam_ids + fam_off[i], (size_t)n[i] * 4);
+    }
+    SG_CUDA(cudaMemcpyAsync(s->d_fam_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    SG_CUDA(cudaMemcpyAsync(s->d_fam_n, n.data(), n.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    SG_CUDA(cudaMemsetAsync(s->d_fam_scores, 0, (uint64_t)s->nq * s->fam_cap * 4, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    s->have_family = true;
+    return SG_OK;
+}
+
+int sg_session_align(sg_session* h, const sg_align_params* ap) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_align: no queries uploaded");
+    if (!s->have_family) SG_FAIL(SG_ERR_ARG, "sg_session_align: run sg_session_family or sg_session_set_family first");
+    SG_TRY(validate_align_params(ap));
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_TRY(stage_begin(s, 2));
+    SG_TRY(launch_prealign(s, *ap));
+    SG_TRY(stage_end(s, &s->stats.ms_graph));
+    uint32_t prev_remaining = 0xffffffffu;
+    for (int pass = 0;; pass++) {
+        SG_CUDA(cudaMemsetAsync(s->d_counters + 2, 0, 16, s->stream));  // arena cursors
+        SG_CUDA(cudaMemsetAsync(s->d_retry + 1, 0, 4, s->stream));
+        SG_TRY(stage_begin(s, 2));
+        SG_TRY(launch_graph(s, *ap));
+        SG_TRY(stage_end(s, &s->stats.ms_graph));
+        SG_TRY(stage_begin(s, 3));
+        SG_TRY(launch_mesh(s, *ap));
+        SG_TRY(stage_end(s, &s->stats.ms_dp));
+        SG_TRY(stage_begin(s, 4));
+        SG_TRY(launch_backtrack(s, *ap));
+        SG_TRY(stage_end(s, &s->stats.ms_backtrack));
+        uint32_t remaining = 0;
+        SG_CUDA(cudaMemcpyAsync(&remaining, s->d_retry + 1, 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        if (remaining == 0) break;
+        if (remaining >= prev_remaining)
+            SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
+        prev_remaining = remaining;
+    }
+    unsigned long long cnt[2];
+    SG_CUDA(cudaMemcpyAsync(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    s->stats.postings = cnt[0];
+    s->stats.cells = cnt[1];
+    s->have_align = true;
+    return SG_OK;
+}
+
+int sg_session_sync(sg_session* h) {
+    Session* s = (Session*)h;
+    if (!s) SG_FAIL(SG_ERR_ARG, "null session");
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    return SG_OK;
+}
+
+int sg_session_download_find(sg_session* h, int16_t* scores, uint32_t* ids, uint32_t* nres) {
+    Session* s = (Session*)h;
+    if (!s || !s->have_find) SG_FAIL(SG_ERR_ARG, "sg_session_download_find: no find results");
+    std::vector<uint64_t> keys((uint64_t)s->nq * s->find_max);
+    SG_CUDA(cudaMemcpyAsync(keys.data(), s->d_ranked, keys.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+    std::vector<uint32_t> nr(s->nq);
+    SG_CUDA(cudaMemcpyAsync(nr.data(), s->d_nres, (uint64_t)s->nq * 4, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t q = 0; q < s->nq; q++) {
+        if (nres) nres[q] = nr[q];
+        for (uint32_t i = 0; i < nr[q]; i++) {
+            const uint64_t kx = keys[(uint64_t)q * s->find_max + i];
+            if (scores) scores[(uint64_t)q * s->find_max + i] = (int16_t)(uint16_t)(kx >> 32);
+            if (ids) ids[(uint64_t)q * s->find_max + i] = (uint32_t)kx;
+        }
+    }
+    return SG_OK;
+}
+
+int sg_session_download_family(sg_session* h, uint32_t fam_stride, uint32_t* fam_ids, float* fam_scores,
+                               int32_t* fam_n) {
+    Session* s = (Session*)h;
+    if (!s || !s->have_family) SG_FAIL(SG_ERR_ARG, "sg_session_download_family: no family");
+    std::vector<uint32_t> ids((uint64_t)s->nq * s->fam_cap);
+    std::vector<float> sc((uint64_t)s->nq * s->fam_cap);
+    std::vector<int32_t> n(s->nq);
+    SG_CUDA(cudaMemcpyAsync(ids.data(), s->d_fam_ids, ids.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaMemcpyAsync(sc.data(), s->d_fam_scores, sc.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaMemcpyAsync(n.data(), s->d_fam_n, n.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t q = 0; q < s->nq; q++) {
+        if (fam_n) fam_n[q] = n[q];
+        const uint32_t c = n[q] > 0 ? std::min<uint32_t>((uint32_t)n[q], fam_stride) : 0;
+        if (n[q] > 0 && (uint32_t)n[q] > fam_stride) SG_FAIL(SG_ERR_ARG, "fam_stride smaller than a family");
+        for (uint32_t i = 0; i < c; i++) {
+            if (fam_ids) fam_ids[(uint64_t)q * fam_stride + i] = ids[(uint64_t)q * s->fam_cap + i];
+            if (fam_scores) fam_scores[(uint64_t)q * fam_stride + i] = sc[(uint64_t)q * s->fam_cap + i];
+        }
+    }
+    return SG_OK;
+}
+
+int sg_session_download_align(sg_session* h, uint32_t* out_cols, uint8_t* out_masks, sg_align_result* results) {
+    Session* s = (Session*)h;
+    if (!s || !s->have_align) SG_FAIL(SG_ERR_ARG, "sg_session_download_align: no alignment");
+    const uint64_t total = s->h_qoff[s->nq];
+    if (out_cols) SG_CUDA(cudaMemcpyAsync(out_cols, s->d_out_cols, total * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (out_masks) SG_CUDA(cudaMemcpyAsync(out_masks, s->d_out_masks, total, cudaMemcpyDeviceToHost, s->stream));
+    std::vector<sg_align_result> tmp;
+    sg_align_result* r = results;
+    if (!r) { tmp.resize(s->nq); r = tmp.data(); }
+    SG_CUDA(cudaMemcpyAsync(r, s->d_results, (uint64_t)s->nq * sizeof(sg_align_result), cudaMemcpyDeviceToHost, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    for (uint32_t q = 0; q < s->nq; q++)
+        if (r[q].status >= 100) SG_FAIL(SG_ERR_LIMIT, "a query exceeded a device capacity limit (family graph too large)");
+    return SG_OK;
+}
+
+int sg_session_stats(sg_session* h, sg_stage_stats* st, int reset) {
+    Session* s = (Session*)h;
+    if (!s) SG_FAIL(SG_ERR_ARG, "null session");
+    if (st) *st = s->stats;
+    if (reset) {
+        s->stats = sg_stage_stats{};
+        SG_CUDA(cudaMemsetAsync(s->d_counters, 0, 16, s->stream));
+    }
+    return SG_OK;
+}
+
+int sg_session_dump_graph(sg_session* h, uint32_t q, uint32_t cap_nodes, uint32_t cap_edges, uint32_t* V, uint32_t* E,
+                          uint32_t* col, uint8_t* mask, float* weight, uint32_t* pred_off, uint32_t* preds) {
+    Session* s = (Session*)h;
+    if (!s || !s->have_align || q >= s->nq) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: bad argument");
+    GraphHdr hd;
+    SG_CUDA(cudaMemcpy(&hd, s->d_hdr + q, sizeof(hd), cudaMemcpyDeviceToHost));
+    if (V) *V = hd.V;
+    if (E) *E = hd.E;
+    if (hd.V > cap_nodes || hd.E > cap_edges) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: capacity too small");
+    const uint64_t io = (uint64_t)q * s->icap;
+    if (col) SG_CUDA(cudaMemcpy(col, s->d_ncol + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
+    if (mask) SG_CUDA(cudaMemcpy(mask, s->d_nmask + io, hd.V, cudaMemcpyDeviceToHost));
+    if (weight) SG_CUDA(cudaMemcpy(weight, s->d_nweight + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
+    if (pred_off) SG_CUDA(cudaMemcpy(pred_off, s->d_pred_off + (uint64_t)q * (s->icap + 1), ((uint64_t)hd.V + 1) * 4, cudaMemcpyDeviceToHost));
+    if (preds) SG_CUDA(cudaMemcpy(preds, s->d_preds + io, (uint64_t)hd.E * 4, cudaMemcpyDeviceToHost));
+    return SG_OK;
+}
+
+// ------------------------------------------------------------------------- host-buffer entry points
+namespace {
+struct Chunker {  // split a host batch into session-sized pieces
+    uint32_t max_q; uint64_t max_bases;
+    uint32_t next(const uint64_t* qoff, uint32_t nq, uint32_t from) const {
+        uint32_t to = from;
+        while (to < nq && to - from < max_q && qoff[to + 1] - qoff[from] <= max_bases) to++;
+        return to;
+    }
+};
+uint32_t default_batch() { return (uint32_t)env_mb("SG_BATCH", 1024); }
+
+int make_session(sg_index* ix, const uint64_t* qoff, uint32_t nq, sg_session** s, Chunker* ch) {
+    uint64_t maxlen = 2;
+    for (uint32_t i = 0; i < nq; i++) maxlen = std::max<uint64_t>(maxlen, qoff[i + 1] - qoff[i]);
+    ch->max_q = std::min<uint32_t>(nq, default_batch());
+    ch->max_bases = (uint64_t)ch->max_q * maxlen;
+    return sg_session_create(ix, ch->max_q, ch->max_bases, s);
+}
+}  // namespace
+
+int sg_find_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, uint32_t max,
+                  int16_t* scores, uint32_t* ids, uint32_t* nres) {
+    if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_find_batch: bad argument");
+    sg_session* s = nullptr;
+    Chunker ch;
+    int rc = make_session(ix, qoff, nq, &s, &ch);
+    const uint32_t N = ((Index*)ix)->N;
+    const uint32_t m = std::min(max, N);
+    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
+        uint32_t b = ch.next(qoff, nq, a);
+        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
+        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, nullptr))) break;
+        if ((rc = sg_session_find(s, max))) break;
+        rc = sg_session_download_find(s, scores ? scores + (uint64_t)a * m : nullptr, ids ? ids + (uint64_t)a * m : nullptr,
+                                      nres ? nres + a : nullptr);
+        a = b;
+    }
+    sg_session_destroy(s);
+    return rc;
+}
+
+int sg_family_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
+                    const int64_t* exclude_ids, const sg_fam_params* fp, uint32_t fam_stride, uint32_t* fam_ids,
+                    float* fam_scores, int32_t* fam_n) {
+    if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_family_batch: bad argument");
+    sg_session* s = nullptr;
+    Chunker ch;
+    int rc = make_session(ix, qoff, nq, &s, &ch);
+    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
+        uint32_t b = ch.next(qoff, nq, a);
+        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
+        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, exclude_ids ? exclude_ids + a : nullptr))) break;
+        if ((rc = sg_session_family(s, fp))) break;
+        rc = sg_session_download_family(s, fam_stride, fam_ids ? fam_ids + (uint64_t)a * fam_stride : nullptr,
+                                        fam_scores ? fam_scores + (uint64_t)a * fam_stride : nullptr,
+                                        fam_n ? fam_n + a : nullptr);
+        a = b;
+    }
+    sg_session_destroy(s);
+    return rc;
+}
+
+int sg_align_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const uint32_t* fam_ids,
+                   const uint64_t* fam_off, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
+                   sg_align_result* results) {
+    if (!ix || !qmasks || !qoff || nq == 0 || !fam_ids || !fam_off) SG_FAIL(SG_ERR_ARG, "sg_align_batch: bad argument");
+    sg_session* s = nullptr;
+    Chunker ch;
+    int rc = make_session(ix, qoff, nq, &s, &ch);
+    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
+        uint32_t b = ch.next(qoff, nq, a);
+        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
+        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, nullptr))) break;
+        if ((rc = sg_session_set_family(s, fam_ids, fam_off + a))) break;
+        if ((rc = sg_session_align(s, ap))) break;
+        const uint64_t o = qoff[a];
+        rc = sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
+                                       results ? results + a : nullptr);
+        a = b;
+    }
+    sg_session_destroy(s);
+    return rc;
+}
+
+int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const int64_t* exclude_ids,
+                 const sg_fam_params* fp, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
+                 sg_align_result* results) {
+    if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_run_batch: bad argument");
+    sg_session* s = nullptr;
+    Chunker ch;
+    int rc = make_session(ix, qoff, nq, &s, &ch);
+    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
+        uint32_t b = ch.next(qoff, nq, a);
+        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
+        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, exclude_ids ? exclude_ids + a : nullptr))) break;
+        if ((rc = sg_session_family(s, fp))) break;
+        if ((rc = sg_session_align(s, ap))) break;
+        const uint64_t o = qoff[a];
+        rc = sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
+                                       results ? results + a : nullptr);
+        a = b;
+    }
+    sg_session_destroy(s);
+    return rc;
+}
+
+}  // extern "C"

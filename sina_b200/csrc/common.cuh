@@ -1,0 +1,208 @@
+// Shared declarations for the sina_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/sina_b200.h"
+
+namespace sg {
+
+// ------------------------------------------------------------------ errors
+void set_error(const std::string& msg);
+#define SG_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            sg::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" + \
+                          std::to_string(__LINE__) + ")");                                              \
+            return SG_ERR_CUDA;                                                                         \
+        }                                                                                               \
+    } while (0)
+#define SG_FAIL(code, msg)      \
+    do {                        \
+        sg::set_error(msg);     \
+        return code;            \
+    } while (0)
+
+// ------------------------------------------------------------------ constants
+constexpr int MAX_K = 16;
+constexpr uint32_t TILE_MAX = 98304;         // references per search-histogram tile (u16 counters: 192 KB smem)
+constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts in shared memory
+constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
+constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
+constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
+constexpr int DP_THREADS = 512;              // node rows per DP group (one thread each)
+constexpr int DP_RING = 16;                  // ring depth (time slots) of the shared-memory row window
+constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
+
+// traceback byte / halfword layout (mesh.cu writes, backtrack.cu decodes)
+constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH = 3;
+// u8 : [1:0] src  [4:2] pred ordinal  [5] chosen deletion opened  [6] last pred's deletion opened  [7] insertion opened
+// u16: [1:0] src  [2] chosen-open [3] last-open [4] ins-open  [15:8] pred ordinal
+
+// ------------------------------------------------------------------ index
+struct Index {
+    int device = 0;
+    uint32_t N = 0, W = 0;
+    int k = 10, nofast = 0;
+    uint32_t max_row_len = 0;
+    uint64_t total_bases = 0;
+    uint8_t* d_masks = nullptr;    // [total_bases]
+    uint32_t* d_cols = nullptr;    // [total_bases]
+    uint64_t* d_row_off = nullptr; // [N+1]
+    uint32_t n_tiles = 1, tile_size = 0;
+    uint64_t n_slots = 0;          // k-mer slots per tile: 4^(k-1) in fast mode (first base A), else 4^k
+    uint64_t* d_list_off = nullptr; // [n_tiles*n_slots + 1], tile-major
+    uint32_t* d_postings = nullptr; // global reference ids, unordered inside a (tile,k-mer) list
+    uint64_t n_postings = 0;
+};
+
+// per-query graph header written by the graph kernel, read by DP / backtrack / host
+struct GraphHdr {
+    uint32_t V, E, n_cols, n_groups;
+    uint32_t n_last, n_spill, max_indeg, wide;  // wide: traceback uses u16 cells
+    uint64_t tb_off;     // offset (in 4-byte words) of this query's traceback in the arena
+    uint64_t spill_off;  // offset (in float2) of this query's spill rows in the arena
+    uint32_t status;     // 0 ok, else SG_Q_* / internal failure code (see GS_*)
+    uint32_t qlen;
+};
+constexpr uint32_t GS_OK = 0, GS_DONE = 50, GS_ARENA_FULL = 100, GS_LIMIT = 101;
+
+struct GroupInfo {
+    uint32_t sigma_lo, depth;  // first column rank of the group, number of column ranks it spans
+    uint64_t tb_off;           // word offset inside the query's traceback block
+};
+
+// All per-batch device state. Per-query arrays use a uniform stride (icap items / ncap columns).
+struct Session {
+    Index* ix = nullptr;
+    cudaStream_t stream = nullptr;
+    uint32_t max_q = 0, nq = 0;
+    uint64_t max_bases = 0;
+    // queries
+    uint8_t* d_qmasks = nullptr;
+    uint64_t* d_qoff = nullptr;
+    int64_t* d_excl = nullptr;
+    uint64_t* h_qoff = nullptr;  // host copy
+    // find
+    uint32_t find_max = 0, find_cap = 0;
+    uint64_t* d_cand = nullptr;    // [nq][n_tiles][find_max] keys (score<<32 | id), unordered
+    uint32_t* d_cand_n = nullptr;  // [nq][n_tiles]
+    uint64_t* d_ranked = nullptr;  // [nq][find_max] keys in rank order
+    uint32_t* d_nres = nullptr;    // [nq]
+    unsigned long long* d_counters = nullptr;  // [8]: 0 postings, 1 cells, 2 tb arena cursor, 3 spill arena cursor
+    // family
+    uint32_t fam_cap = 0;
+    uint32_t* d_fam_ids = nullptr;   // [nq][fam_cap] rank order
+    float* d_fam_scores = nullptr;   // [nq][fam_cap]
+    int32_t* d_fam_n = nullptr;      // [nq] (-1: too few, -2: window too small)
+    uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window, [1] queries left for another align pass
+    // align
+    uint32_t icap = 0, ncap = 0;     // per-query capacities: items (= nodes = edges), column ranks
+    uint32_t* d_afam = nullptr;      // [nq][fam_cap] family after the contains-query partition
+    uint32_t* d_afam_n = nullptr;    // [nq]
+    uint32_t* d_contains = nullptr;  // [nq][fam_cap] 1 + first offset of the query inside the relative, 0 = none
+    uint32_t* d_copy_src = nullptr;  // [nq][2] (ref id, offset) for SG_Q_COPIED
+    GraphHdr* d_hdr = nullptr;       // [nq]
+    uint8_t* d_tab = nullptr;        // [nq][ncap][fam_cap] base mask of family row j at column rank c
+    uint8_t* d_tabli = nullptr;      // [nq][ncap][fam_cap] local node index in that column
+    uint32_t* d_colof = nullptr;     // [nq][ncap] column of rank c
+    uint32_t* d_colbase = nullptr;   // [nq][ncap+1] first node id of column rank c
+    uint32_t* d_item_node = nullptr; // [nq][icap]
+    uint32_t* d_slot = nullptr;      // [nq][icap] predecessor candidates grouped by node
+    uint32_t* d_ncol = nullptr;      // [nq][icap] node column
+    uint8_t* d_nmask = nullptr;      // [nq][icap]
+    uint16_t* d_ncount = nullptr;    // [nq][icap] family rows through the node
+    float* d_nweight = nullptr;      // [nq][icap]
+    uint32_t* d_nsigma = nullptr;    // [nq][icap] column rank
+    uint32_t* d_slotbase = nullptr;  // [nq][icap+1]
+    uint32_t* d_cursor = nullptr;    // [nq][icap]
+    uint32_t* d_pred_off = nullptr;  // [nq][icap+1]
+    uint32_t* d_preds = nullptr;     // [nq][icap]
+    uint32_t* d_pdesc = nullptr;     // [nq][icap] near/far descriptor per edge
+    int32_t* d_spillrow = nullptr;   // [nq][icap] spill row of node or -1
+    uint8_t* d_nflags = nullptr;     // [nq][icap] bit0 has successor
+    uint32_t* d_lastnodes = nullptr; // [nq][icap]
+    GroupInfo* d_groups = nullptr;   // [nq][gcap]
+    uint32_t gcap = 0;
+    float* d_lastcol = nullptr;      // [nq][icap] value(m, Lq-1)
+    float* d_rowmin = nullptr;       // [nq][icap] min over s of value(m, s) (last nodes only)
+    uint32_t* d_rowarg = nullptr;    // [nq][icap] first s reaching it
+    uint32_t* d_tb = nullptr;        // traceback arena (words)
+    uint64_t tb_words = 0;
+    float2* d_spill = nullptr;       // spill arena
+    uint64_t spill_elems = 0;
+    // outputs
+    uint32_t* d_out_cols = nullptr;  // [max_bases]
+    uint8_t* d_out_masks = nullptr;  // [max_bases]
+    sg_align_result* d_results = nullptr;  // [nq]
+    // timing
+    cudaEvent_t ev[8] = {};
+    sg_stage_stats stats = {};
+    bool have_family = false, have_find = false, have_align = false;
+};
+
+// ------------------------------------------------------------------ kernel launchers (one per .cu)
+int launch_index_build(Index* ix, cudaStream_t st);
+int launch_find(Session* s, uint32_t max);
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window);
+int launch_prealign(Session* s, const sg_align_params& ap);
+int launch_graph(Session* s, const sg_align_params& ap);
+int launch_mesh(Session* s, const sg_align_params& ap);
+int launch_backtrack(Session* s, const sg_align_params& ap);
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+
+// Block-wide exclusive prefix sum of one value per thread (blockDim.x multiple of 32, <= 1024).
+// `red` is shared scratch of 33 uint32. Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* red, uint32_t* total) {
+    uint32_t lane = lane_id(), w = warp_id(), nw = (blockDim.x + 31) >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    __syncthreads();  // protect red[] from a previous call
+    if (lane == 31) red[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < nw ? red[lane] : 0, t = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= (uint32_t)o) t += y;
+        }
+        if (lane < nw) red[lane] = t - s;
+        if (lane == 31) red[32] = t;
+    }
+    __syncthreads();
+    if (total) *total = red[32];
+    return red[w] + x - v;
+}
+
+// 2-bit code of an unambiguous base mask (A0 G1 C2 U3), reference src/aligned_base.h:113-115
+__device__ __forceinline__ uint32_t base_code(uint32_t m) { return (uint32_t)__ffs((int)(m & 15u)) - 1u; }
+__device__ __forceinline__ bool base_ambig(uint32_t m) { return __popc(m & 15u) > 1; }
+
+// K-mer ending at position i of a sequence (window [i-k+1, i]); returns false if the window holds an
+// ambiguous base. Shared by index build and search.
+__device__ __forceinline__ bool kmer_at(const uint8_t* __restrict__ m, uint32_t i, int k, uint32_t& val) {
+    uint32_t v = 0;
+    bool ok = true;
+    for (int j = k - 1; j >= 0; j--) {
+        uint32_t b = m[i - j];
+        ok &= !base_ambig(b);
+        v = (v << 2) | (base_code(b) & 3u);
+    }
+    val = v;
+    return ok;
+}
+
+#endif
+
+}  // namespace sg

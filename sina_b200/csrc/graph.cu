@@ -1,0 +1,385 @@
+// Aligner pre-steps and family-graph construction on the device.
+//   contains_kernel / partition_kernel   aligner::operator() pre-steps (reference src/align.cpp:320-389)
+//   graph_kernel                         mseq::mseq column sweep + dag::link + sort + reduce_edges
+//                                        (src/mseq.cpp:47-118, src/graph.h:332-357,451-488, src/align.cpp:399-402)
+//                                        followed by the DP plan (groups, ring/spill classification, arenas)
+#include "common.cuh"
+
+namespace sg {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------------
+// One warp per (query, relative): does the relative's base string contain the query's, ignoring case?
+// (boost::algorithm::icontains on getBases(), src/align.cpp:329-332). Stores 1 + first offset, 0 = no.
+__global__ void __launch_bounds__(128) contains_kernel(const uint8_t* __restrict__ qmasks,
+                                                       const uint64_t* __restrict__ qoff, uint32_t nq,
+                                                       const uint8_t* __restrict__ masks,
+                                                       const uint64_t* __restrict__ row_off,
+                                                       const uint32_t* __restrict__ fam_ids,
+                                                       const int32_t* __restrict__ fam_n, uint32_t fam_cap,
+                                                       uint32_t* __restrict__ contains) {
+    const uint32_t pair = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    const uint32_t q = pair / fam_cap, j = pair % fam_cap;
+    if (q >= nq) return;
+    const int32_t F = fam_n[q];
+    if (F <= 0 || j >= (uint32_t)F) return;
+    const uint32_t id = fam_ids[(uint64_t)q * fam_cap + j];
+    const uint8_t* r = masks + row_off[id];
+    const uint32_t rl = (uint32_t)(row_off[id + 1] - row_off[id]);
+    const uint8_t* m = qmasks + qoff[q];
+    const uint32_t ql = (uint32_t)(qoff[q + 1] - qoff[q]);
+    uint32_t found = NONE;
+    if (ql <= rl) {
+        for (uint32_t base = 0; base + ql <= rl && found == NONE; base += 32) {
+            uint32_t p = base + lane_id();
+            bool ok = p + ql <= rl;
+            for (uint32_t t = 0; ok && t < ql; t++) ok = ((r[p + t] ^ m[t]) & 15u) == 0;
+            uint32_t b = __ballot_sync(0xffffffffu, ok);
+            if (b) found = base + (uint32_t)__ffs((int)b) - 1;
+        }
+    }
+    if (lane_id() == 0) contains[(uint64_t)q * fam_cap + j] = found == NONE ? 0u : found + 1u;
+}
+
+// One thread per query: std::partition(vc, !contains) exactly as libstdc++'s bidirectional __partition
+// permutes (bits/stl_algo.h:1472-1495; the reference's call is src/align.cpp:333), then --realign erase
+// (:337-348) or the alignment copy decision (:349-388).
+__global__ void partition_kernel(uint32_t nq, const uint32_t* __restrict__ fam_ids, const int32_t* __restrict__ fam_n,
+                                 uint32_t fam_cap, uint32_t* __restrict__ contains, const uint64_t* __restrict__ qoff,
+                                 const uint64_t* __restrict__ row_off, int realign, uint32_t* __restrict__ afam,
+                                 uint32_t* __restrict__ afam_n, uint32_t* __restrict__ copy_src,
+                                 GraphHdr* __restrict__ hdr) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    GraphHdr h = {};
+    h.qlen = (uint32_t)(qoff[q + 1] - qoff[q]);
+    const int32_t Fi = fam_n[q];
+    uint32_t* a = afam + (uint64_t)q * fam_cap;
+    uint32_t* c = contains + (uint64_t)q * fam_cap;
+    if (Fi < 0) { h.status = SG_Q_NOFAMILY; afam_n[q] = 0; hdr[q] = h; return; }
+    uint32_t F = (uint32_t)Fi;
+    for (uint32_t j = 0; j < F; j++) a[j] = fam_ids[(uint64_t)q * fam_cap + j];
+    uint32_t first = 0, last = F;
+    for (;;) {
+        for (;;) { if (first == last) goto done; else if (c[first] == 0) ++first; else break; }
+        --last;
+        for (;;) { if (first == last) goto done; else if (c[last] != 0) --last; else break; }
+        { uint32_t t = a[first]; a[first] = a[last]; a[last] = t; t = c[first]; c[first] = c[last]; c[last] = t; }
+        ++first;
+    }
+done:
+    if (first != F) {
+        if (realign) {
+            F = first;
+            if (F == 0) h.status = SG_Q_SKIPPED;
+        } else {
+            uint32_t src = first;
+            for (uint32_t j = first; j < F; j++) {  // iequals: a containing relative of the same length
+                uint32_t id = a[j];
+                if ((uint32_t)(row_off[id + 1] - row_off[id]) == h.qlen) { src = j; break; }
+            }
+            copy_src[2 * q] = a[src];
+            copy_src[2 * q + 1] = c[src] - 1;
+            h.status = SG_Q_COPIED;
+        }
+    }
+    afam_n[q] = F;
+    hdr[q] = h;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct GraphArgs {
+    const uint8_t* masks; const uint32_t* cols; const uint64_t* row_off; uint32_t W;
+    const uint32_t* afam; const uint32_t* afam_n; uint32_t fam_cap;
+    uint32_t icap, ncap, gcap;
+    GraphHdr* hdr;
+    uint8_t *tab, *tabli; uint32_t *colof, *colbase, *item_node, *slot;
+    uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
+    uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
+    uint32_t* lastnodes; GroupInfo* groups;
+    unsigned long long* counters; uint64_t tb_words, spill_elems;
+    float fs_weight;
+};
+
+// running-carry exclusive scan of arr[0..n) (u32, global or shared), in place -> exclusive; returns total
+template <typename T>
+__device__ uint32_t scan_array_inplace(T* arr, uint32_t n, uint32_t* red) {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? (uint32_t)arr[i] : 0, tot;
+        uint32_t ex = block_exscan(v, red, &tot);
+        if (i < n) arr[i] = (T)(carry + ex);
+        carry += tot;
+    }
+    __syncthreads();
+    return carry;
+}
+
+__global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t q = blockIdx.x;
+    GraphHdr* hdr = A.hdr + q;
+    if (hdr->status != GS_OK) return;
+    const uint32_t words = (A.W + 31) >> 5;
+    uint32_t* bitmap = sm;            // [words]   columns used by any family row
+    uint32_t* wrank = sm + words;     // [words]   exclusive popcount prefix
+    uint32_t* famoff = wrank + words; // [fam_cap+1] item offsets of the family rows
+    uint32_t* red = famoff + A.fam_cap + 1;  // [33]
+    uint32_t* shv = red + 33;         // [8] misc broadcast
+    const uint32_t F = A.afam_n[q];
+    const uint32_t* fam = A.afam + (uint64_t)q * A.fam_cap;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t Lq = hdr->qlen;
+
+    // per-query views
+    uint8_t* tab = A.tab + (uint64_t)q * A.ncap * A.fam_cap;
+    uint8_t* tabli = A.tabli + (uint64_t)q * A.ncap * A.fam_cap;
+    uint32_t* colof = A.colof + (uint64_t)q * A.ncap;
+    uint32_t* colbase = A.colbase + (uint64_t)q * (A.ncap + 1);
+    const uint64_t io = (uint64_t)q * A.icap;
+    uint32_t* item_node = A.item_node + io;
+    uint32_t* slot = A.slot + io;
+    uint32_t* ncol = A.ncol + io; uint8_t* nmask = A.nmask + io; uint16_t* ncount = A.ncount + io;
+    float* nweight = A.nweight + io; uint32_t* nsigma = A.nsigma + io;
+    uint32_t* slotbase = A.slotbase + (uint64_t)q * (A.icap + 1);
+    uint32_t* cursor = A.cursor + io;
+    uint32_t* pred_off = A.pred_off + (uint64_t)q * (A.icap + 1);
+    uint32_t* preds = A.preds + io; uint32_t* pdesc = A.pdesc + io;
+    int32_t* spillrow = A.spillrow + io; uint8_t* nflags = A.nflags + io;
+    uint32_t* lastnodes = A.lastnodes + io;
+    GroupInfo* groups = A.groups + (uint64_t)q * A.gcap;
+
+    // ---- 0. item offsets of the family rows
+    for (uint32_t i = tid; i < words; i += nt) bitmap[i] = 0;
+    if (tid == 0) {
+        uint32_t o = 0;
+        for (uint32_t j = 0; j < F; j++) { famoff[j] = o; o += (uint32_t)(A.row_off[fam[j] + 1] - A.row_off[fam[j]]); }
+        famoff[F] = o;
+    }
+    __syncthreads();
+    const uint32_t I = famoff[F];
+    if (I > A.icap || F == 0) { if (tid == 0) hdr->status = F == 0 ? (uint32_t)SG_Q_SKIPPED : GS_LIMIT; return; }
+
+    // ---- 1. used-column bitmap and column ranks (= the sweep's `min_next` column order, mseq.cpp:76-84)
+    for (uint32_t j = 0; j < F; j++) {
+        const uint64_t a = A.row_off[fam[j]];
+        const uint32_t len = famoff[j + 1] - famoff[j];
+        for (uint32_t i = tid; i < len; i += nt) {
+            uint32_t c = A.cols[a + i];
+            atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < words; i += nt) wrank[i] = __popc(bitmap[i]);
+    __syncthreads();
+    const uint32_t n_cols = scan_array_inplace(wrank, words, red);
+    if (n_cols > A.ncap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+    for (uint32_t w = tid; w < words; w += nt) {
+        uint32_t bits = bitmap[w], r = wrank[w];
+        while (bits) { uint32_t b = __ffs((int)bits) - 1; colof[r++] = (w << 5) + b; bits &= bits - 1; }
+    }
+    auto colrank = [&](uint32_t c) -> uint32_t { return wrank[c >> 5] + __popc(bitmap[c >> 5] & ((1u << (c & 31)) - 1u)); };
+
+    // ---- 2. column table: tab[c][j] = base mask of family row j in column rank c
+    for (uint32_t i = tid; i < n_cols * A.fam_cap; i += nt) tab[i] = 0;
+    __syncthreads();
+    for (uint32_t j = 0; j < F; j++) {
+        const uint64_t a = A.row_off[fam[j]];
+        const uint32_t len = famoff[j + 1] - famoff[j];
+        for (uint32_t i = tid; i < len; i += nt)
+            tab[(uint64_t)colrank(A.cols[a + i]) * A.fam_cap + j] = A.masks[a + i] & 31u;
+    }
+    __syncthreads();
+
+    // ---- 3. nodes: one per (column, IUPAC char incl. case), local order = first family row bringing it
+    //         (mseq.cpp:88-98). Pass A counts per column, pass B writes node arrays.
+    for (uint32_t c = tid; c < n_cols; c += nt) {
+        uint32_t seen = 0, nn = 0;
+        const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
+        for (uint32_t j = 0; j < F; j++) { uint32_t b = t[j]; if (b && !((seen >> b) & 1u)) { seen |= 1u << b; nn++; } }
+        colbase[c] = nn;
+    }
+    __syncthreads();
+    const uint32_t V = scan_array_inplace(colbase, n_cols, red);
+    if (tid == 0) colbase[n_cols] = V;
+    if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+    for (uint32_t c = tid; c < n_cols; c += nt) {
+        uint32_t seen = 0, nn = 0;
+        uint8_t li_of[32];
+        uint16_t cnt[32];
+        uint8_t nm[32];
+        const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
+        uint8_t* tl = tabli + (uint64_t)c * A.fam_cap;
+        for (uint32_t j = 0; j < F; j++) {
+            uint32_t b = t[j];
+            if (!b) continue;
+            if (!((seen >> b) & 1u)) { seen |= 1u << b; li_of[b] = (uint8_t)nn; cnt[nn] = 1; nm[nn] = (uint8_t)b; nn++; }
+            else cnt[li_of[b]]++;
+            tl[j] = li_of[b];
+        }
+        const uint32_t base = colbase[c], col = colof[c];
+        for (uint32_t k2 = 0; k2 < nn; k2++) {
+            const uint32_t m = base + k2;
+            ncol[m] = col; nmask[m] = nm[k2]; ncount[m] = cnt[k2]; nsigma[m] = c;
+            // node->weight = 1.0/(weight+1) + weight * (node->weight/num_seqs)   (mseq.cpp:111-116)
+            float fr = __fdiv_rn((float)cnt[k2], (float)F);
+            float b2 = __fmul_rn(A.fs_weight, fr);
+            nweight[m] = (float)(1.0 / (double)__fadd_rn(A.fs_weight, 1.0f) + (double)b2);
+            cursor[m] = 0; nflags[m] = 0; spillrow[m] = 0;
+            slotbase[m] = cnt[k2];
+        }
+    }
+    __syncthreads();
+
+    // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
+    scan_array_inplace(slotbase, V, red);
+    if (tid == 0) slotbase[V] = I;
+    for (uint32_t j = 0; j < F; j++) {
+        const uint64_t a = A.row_off[fam[j]];
+        const uint32_t len = famoff[j + 1] - famoff[j];
+        for (uint32_t i = tid; i < len; i += nt) {
+            uint32_t c = colrank(A.cols[a + i]);
+            item_node[famoff[j] + i] = colbase[c] + tabli[(uint64_t)c * A.fam_cap + j];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = 0; j < F; j++) {
+        const uint32_t len = famoff[j + 1] - famoff[j];
+        for (uint32_t i = tid; i < len; i += nt) {
+            uint32_t node = item_node[famoff[j] + i];
+            uint32_t from = i ? item_node[famoff[j] + i - 1] : NONE;
+            uint32_t p = atomicAdd(&cursor[node], 1u);
+            slot[slotbase[node] + p] = from;
+            if (from != NONE) nflags[from] = 1;  // has a successor (benign same-value race)
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. reduce_edges: sort predecessor ids, drop duplicates (graph.h:466-488); in-degree per node
+    uint32_t my_max = 0;
+    for (uint32_t m = tid; m < V; m += nt) {
+        uint32_t* sl = slot + slotbase[m];
+        const uint32_t n = slotbase[m + 1] - slotbase[m];
+        for (uint32_t x = 1; x < n; x++) {  // insertion sort (n <= family size)
+            uint32_t key = sl[x];
+            int y = (int)x - 1;
+            while (y >= 0 && sl[y] > key) { sl[y + 1] = sl[y]; y--; }
+            sl[y + 1] = key;
+        }
+        uint32_t deg = 0;
+        for (uint32_t x = 0; x < n; x++) if (sl[x] != NONE && (x == 0 || sl[x] != sl[x - 1])) sl[deg++] = sl[x];
+        pred_off[m] = deg;
+        my_max = max(my_max, deg);
+    }
+    __syncthreads();
+    const uint32_t E = scan_array_inplace(pred_off, V, red);
+    if (tid == 0) pred_off[V] = E;
+    __syncthreads();
+    for (uint32_t m = tid; m < V; m += nt) {
+        const uint32_t deg = pred_off[m + 1] - pred_off[m];
+        for (uint32_t x = 0; x < deg; x++) preds[pred_off[m] + x] = slot[slotbase[m] + x];
+    }
+    // block max of in-degree
+    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
+    __syncthreads();
+    if (lane_id() == 0) red[warp_id()] = my_max;
+    __syncthreads();
+    if (tid == 0) { uint32_t mx = 0; for (uint32_t w = 0; w < (nt >> 5); w++) mx = max(mx, red[w]); shv[0] = mx; }
+    __syncthreads();
+    const uint32_t max_indeg = shv[0];
+    const uint32_t wide = max_indeg > 8;
+
+    // ---- 6. DP plan. Group g = nodes [g*T, (g+1)*T); a node at column rank sigma runs query position
+    // s at step s + sigma - sigma_lo(g). An edge is "near" (served from the shared-memory ring) when both
+    // ends are in the same group and at most DP_RING-2 column ranks apart; otherwise the predecessor row
+    // is spilled to global memory.
+    const uint32_t T = DP_THREADS;
+    const uint32_t n_groups = (V + T - 1) / T;
+    if (n_groups > A.gcap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+    for (uint32_t m = tid; m < V; m += nt) {
+        const uint32_t g = m / T, sg_ = nsigma[m];
+        for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
+            const uint32_t p = preds[e], d = sg_ - nsigma[p];
+            if (p / T == g && d <= (uint32_t)DP_RING - 2) pdesc[e] = (d << 16) | (p - g * T);
+            else { pdesc[e] = FAR_BIT; spillrow[p] = 1; }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_spill = scan_array_inplace(spillrow, V, red);  // exclusive index for flagged rows
+    // rows not flagged must read -1: flagged iff next prefix differs
+    for (uint32_t m = tid; m < V; m += nt) {
+        uint32_t nxt = (m + 1 < V) ? (uint32_t)spillrow[m + 1] : n_spill;
+        cursor[m] = (nxt != (uint32_t)spillrow[m]) ? (uint32_t)spillrow[m] : NONE;
+    }
+    __syncthreads();
+    for (uint32_t m = tid; m < V; m += nt) spillrow[m] = (int32_t)cursor[m];
+    __syncthreads();
+    for (uint32_t e = tid; e < E; e += nt) if (pdesc[e] == FAR_BIT) pdesc[e] = FAR_BIT | (uint32_t)spillrow[preds[e]];
+    // last nodes (no successor), ascending id: sentinel's _previous list (graph.h:332-357)
+    for (uint32_t m = tid; m < V; m += nt) cursor[m] = nflags[m] ? 0u : 1u;
+    __syncthreads();
+    const uint32_t n_last = scan_array_inplace(cursor, V, red);
+    for (uint32_t m = tid; m < V; m += nt) if (!nflags[m]) lastnodes[cursor[m]] = m;
+    if (tid == 0) {
+        uint64_t words_total = 0;
+        for (uint32_t g = 0; g < n_groups; g++) {
+            const uint32_t lo = nsigma[g * T];
+            const uint32_t hi = nsigma[min(V, (g + 1) * T) - 1];
+            groups[g].sigma_lo = lo;
+            groups[g].depth = hi - lo + 1;
+            groups[g].tb_off = words_total;
+            const uint32_t steps = Lq + (hi - lo);
+            const uint32_t per_word = wide ? 2 : 4;
+            words_total += (uint64_t)((steps + per_word - 1) / per_word) * T;
+        }
+        const uint64_t spill_need = (uint64_t)n_spill * Lq;
+        const uint64_t tb_off = atomicAdd(&A.counters[2], (unsigned long long)words_total);
+        const uint64_t sp_off = atomicAdd(&A.counters[3], (unsigned long long)spill_need);
+        hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;
+        hdr->n_last = n_last; hdr->n_spill = n_spill; hdr->max_indeg = max_indeg; hdr->wide = wide;
+        hdr->tb_off = tb_off; hdr->spill_off = sp_off;
+        if (tb_off + words_total > A.tb_words || sp_off + spill_need > A.spill_elems) hdr->status = GS_ARENA_FULL;
+        else atomicAdd(&A.counters[1], (unsigned long long)V * Lq);
+    }
+}
+
+int launch_prealign(Session* s, const sg_align_params& ap) {
+    Index* ix = s->ix;
+    uint32_t pairs = s->nq * s->fam_cap;
+    contains_kernel<<<(pairs + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, s->nq, ix->d_masks, ix->d_row_off,
+                                                           s->d_fam_ids, s->d_fam_n, s->fam_cap,
+                                                           s->d_contains);
+    partition_kernel<<<(s->nq + 127) / 128, 128, 0, s->stream>>>(s->nq, s->d_fam_ids, s->d_fam_n, s->fam_cap,
+                                                                s->d_contains, s->d_qoff, ix->d_row_off,
+                                                                ap.realign, s->d_afam, s->d_afam_n, s->d_copy_src,
+                                                                s->d_hdr);
+    SG_CUDA(cudaGetLastError());
+    s->stats.kernel_launches += 2;
+    return SG_OK;
+}
+
+int launch_graph(Session* s, const sg_align_params& ap) {
+    Index* ix = s->ix;
+    GraphArgs A;
+    A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off; A.W = ix->W;
+    A.afam = s->d_afam; A.afam_n = s->d_afam_n; A.fam_cap = s->fam_cap;
+    A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap;
+    A.hdr = s->d_hdr; A.tab = s->d_tab; A.tabli = s->d_tabli; A.colof = s->d_colof; A.colbase = s->d_colbase;
+    A.item_node = s->d_item_node; A.slot = s->d_slot; A.ncol = s->d_ncol; A.nmask = s->d_nmask;
+    A.ncount = s->d_ncount; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.slotbase = s->d_slotbase;
+    A.cursor = s->d_cursor; A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.pdesc = s->d_pdesc;
+    A.spillrow = s->d_spillrow; A.nflags = s->d_nflags; A.lastnodes = s->d_lastnodes; A.groups = s->d_groups;
+    A.counters = s->d_counters; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
+    A.fs_weight = ap.fs_weight;
+    const uint32_t words = (ix->W + 31) >> 5;
+    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8) * 4;
+    SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_kernel<<<s->nq, 512, smem, s->stream>>>(A);
+    SG_CUDA(cudaGetLastError());
+    s->stats.kernel_launches += 1;
+    return SG_OK;
+}
+
+}  // namespace sg

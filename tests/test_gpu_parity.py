@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path through the C-ABI (sina_b200) against the oracle (oracle/sina_oracle.c) and
+the golden vectors produced by the reference's own code. Bit-exact for ids, columns, strings; the DP score
+(north star tolerance: 1e-5 relative) is asserted bit-exact as well."""
+import numpy as np
+import pytest
+
+import sina_b200
+from conftest import load_golden
+from oracle import oracle as O
+from sina_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def pack_queries(qs):
+    qoff = np.zeros(len(qs) + 1, np.uint64)
+    qoff[1:] = np.cumsum([len(q) for q in qs])
+    return np.concatenate(qs).astype(np.uint8), qoff
+
+
+def gpu_align_one(msa, fam, qm, ap_kw, k=4):
+    ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=k)
+    fam = np.asarray(fam, np.uint32)
+    oc, om, res = ix.align(qm, np.array([0, len(qm)], np.uint64), fam, np.array([0, len(fam)], np.uint64),
+                           sina_b200.AlignParams(**ap_kw))
+    ix.close()
+    return oc, om, res[0]
+
+
+def compare_result(r_gpu, oc, om, r_orc, c_orc, m_orc, W, ctx):
+    assert r_gpu["status"] == r_orc.status, ctx
+    if r_orc.status in (0, 1):
+        n = r_orc.n_out
+        assert r_gpu["n_out"] == n, ctx
+        assert (oc[:n] == c_orc).all(), ctx
+        assert (om[:n] == m_orc).all(), ctx
+    if r_orc.status == 0:
+        assert (r_gpu["head"], r_gpu["tail"], r_gpu["qual"], r_gpu["n_nodes"]) == (r_orc.head, r_orc.tail, r_orc.qual, r_orc.n_nodes), ctx
+        assert bits(r_gpu["score"]) == bits(r_orc.score), ctx
+        assert bits(r_gpu["raw"]) == bits(r_orc.raw) and bits(r_gpu["sum_weight"]) == bits(r_orc.sum_weight), ctx
+        assert (r_gpu["end_m"], r_gpu["end_s"]) == (r_orc.end_m, r_orc.end_s), ctx
+
+
+def test_align_golden_cases():
+    """every golden case (hand KATs + 120 random small families), one index per case"""
+    cases = load_golden("align_cases")
+    for i, e in enumerate(cases):
+        msa = O.MSA.from_rows(e["rows"])
+        qm = O.encode(e["query"])
+        oc, om, r = gpu_align_one(msa, np.arange(msa.N), qm, e["params"])
+        assert r["status"] == e["status"], i
+        if e["status"] in (0, 1):
+            assert O.render(om[:r["n_out"]], oc[:r["n_out"]], msa.W) == e["aligned"], i
+        if e["status"] == 0:
+            assert (r["head"], r["tail"], r["qual"], r["n_nodes"]) == (e["head"], e["tail"], e["qual"], e["n_nodes"]), i
+            assert int(bits(r["score"])) == e["score_bits"], i
+
+
+def test_graph_matches_oracle(orc):
+    rng = np.random.default_rng(42)
+    for it in range(25):
+        rows, q = synth.random_case(rng, lowercase=0.05 if it % 2 else 0.0)
+        msa = O.MSA.from_rows(rows)
+        fsw = [1.0, 0.0, 2.5][it % 3]
+        ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=4)
+        qm = O.encode(q)
+        s = sina_b200.Session(ix, 1, len(qm))
+        s.upload(qm, np.array([0, len(qm)], np.uint64))
+        s.set_family(np.arange(msa.N, dtype=np.uint32), np.array([0, msa.N], np.uint64))
+        s.align(sina_b200.AlignParams(fs_weight=fsw, realign=1))
+        _, _, res = s.download_align()
+        if res[0]["status"] != 2:
+            g = s.dump_graph(0)
+            go = orc.graph(msa, np.arange(msa.N), fsw)
+            assert (g["V"], g["E"]) == (go["V"], go["E"])
+            for k in ("col", "mask", "pred_off", "preds"):
+                assert (g[k] == go[k]).all(), (it, k)
+            assert (bits(g["weight"]) == bits(go["weight"])).all()
+        s.close()
+        ix.close()
+
+
+def test_align_batch_random_vs_oracle(orc):
+    """one MSA, many queries with different families in one batch (different graph sizes per CTA)"""
+    rng = np.random.default_rng(7)
+    tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
+    msa = O.MSA(m, c, o, 900)
+    qm, qo = synth.synth_queries(tree, 48, "full", seed=9)
+    ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=6)
+    fams, foff = [], [0]
+    for i in range(48):
+        F = int(rng.integers(1, 41))
+        fams.append(rng.choice(300, F, replace=False).astype(np.uint32))
+        foff.append(foff[-1] + F)
+    for ap_kw in (dict(), dict(overhang=2, lowercase=2), dict(overhang=1, match_score=1.7, mismatch_score=-0.9,
+                                                              gap_penalty=4.3, gap_ext_penalty=1.1, fs_weight=0.5)):
+        oc, om, res = ix.align(qm, qo, np.concatenate(fams), np.array(foff, np.uint64), sina_b200.AlignParams(**ap_kw))
+        for i in range(48):
+            a, b = int(qo[i]), int(qo[i + 1])
+            r1, c1, m1, _ = orc.align(msa, fams[i], qm[a:b], O.AlignParams(**ap_kw))
+            compare_result(res[i], oc[a:b], om[a:b], r1, c1, m1, msa.W, (ap_kw, i))
+    ix.close()
+
+
+def test_wide_indegree_and_far_edges(orc):
+    """in-degree > 8 switches the traceback to 16-bit cells; long gaps force predecessor rows through the
+    global spill path (column-rank distance > ring depth); Lq > W hits the reference's runtime_error."""
+    rng = np.random.default_rng(3)
+    L, W = 400, 1000
+    core = np.sort(rng.choice(W - 50, L, replace=False))
+    root = rng.integers(0, 4, L)
+    rows = []
+    for j in range(14):
+        s = ["-"] * W
+        a = 100 + j
+        gap = 5 + 4 * j
+        for i in range(L):
+            if a <= i < a + gap:
+                continue
+            s[core[i]] = "AGCU"[root[i] if (i % 37 != j) else (root[i] + 1) % 4]
+        rows.append("".join(s))
+    msa = O.MSA.from_rows(rows)
+    qm = O.encode("".join("AGCU"[x] for x in root[20:380]))
+    fam = np.arange(14, dtype=np.uint32)
+    g = orc.graph(msa, fam)
+    assert np.diff(g["pred_off"]).max() > 8
+    for ap_kw in (dict(), dict(overhang=2)):
+        oc, om, r = gpu_align_one(msa, fam, qm, ap_kw)
+        r1, c1, m1, _ = orc.align(msa, fam, qm, O.AlignParams(**ap_kw))
+        compare_result(r, oc, om, r1, c1, m1, W, ap_kw)
+    msa2 = O.MSA.from_rows(["AGCUAGCUAGGCU"] * 2)  # Lq > W
+    oc, om, r = gpu_align_one(msa2, np.arange(2), O.encode("AGCUAGCUAGGCUAGC"), {})
+    assert r["status"] == sina_b200.SG_Q_NOSPACE
+
+
+def test_index_and_find_vs_oracle(orc):
+    for (N, L, W, k, nofast) in [(300, 220, 500, 6, 0), (300, 220, 500, 6, 1), (500, 400, 900, 8, 0), (200, 300, 700, 10, 0)]:
+        tree, m, c, o = synth.synth_msa(N, W=W, L=L, seed=11 + N + k)
+        msa = O.MSA(m, c, o, W)
+        oix = orc.index_build(msa, k, nofast)
+        off, post = orc.index_lists(oix)
+        ix = sina_b200.Index(m, c, o, W, k=k, nofast=bool(nofast))
+        assert ix.info()["n_postings"] == off[-1]
+        rng = np.random.default_rng(k)
+        kmers = np.concatenate([rng.integers(0, 4 ** k, 300), np.nonzero(np.diff(off.astype(np.int64)) > 0)[0][:300]]).astype(np.uint32)
+        sizes = ix.list_sizes(kmers)
+        assert (sizes == (off[kmers + 1] - off[kmers])).all()
+        for km in kmers[-20:]:
+            assert (ix.posting_list(int(km)) == post[int(off[km]):int(off[km + 1])]).all()
+        qm, qo = synth.synth_queries(tree, 24, "full", seed=3)
+        for mx in (1, 16, 50, N + 7):
+            sc, ids, nres = ix.find(qm, qo, mx)
+            for i in range(24):
+                s1, i1, _ = orc.find(oix, qm[int(qo[i]):int(qo[i + 1])], mx)
+                assert nres[i] == len(s1)
+                assert (sc[i, :nres[i]] == s1).all() and (ids[i, :nres[i]] == i1).all(), (N, k, mx, i)
+        orc.index_free(oix)
+        ix.close()
+
+
+def test_find_golden():
+    for case in load_golden("kmer_cases")["find"]:
+        tree, m, c, o = synth.synth_msa(case["N"], W=case["W"], L=case["L"], seed=case["seed"])
+        ix = sina_b200.Index(m, c, o, case["W"], k=case["k"], nofast=bool(case["nofast"]))
+        qm, qo = pack_queries([O.encode(q["query"]) for q in case["queries"]])
+        sc, ids, nres = ix.find(qm, qo, 50)
+        fids, fsc, fn = ix.family(qm, qo, sina_b200.FamParams(**case["fam_params"]))
+        for i, qe in enumerate(case["queries"]):
+            assert sc[i, :nres[i]].tolist() == qe["scores"] and ids[i, :nres[i]].tolist() == qe["ids"]
+            assert fn[i] == qe["fam_n"]
+            assert fids[i, :max(fn[i], 0)].tolist() == qe["fam_ids"]
+            assert fsc[i, :max(fn[i], 0)].tolist() == qe["fam_scores"]
+        ix.close()
+
+
+def test_family_retry_window_and_quotas(orc):
+    """quota rules + the 10x retry loop (famfinder.cpp:591-608): short references force wider windows"""
+    tree, m, c, o = synth.synth_msa(600, W=700, L=300, seed=21)
+    msa = O.MSA(m, c, o, 700)
+    oix = orc.index_build(msa, 6, 0)
+    ix = sina_b200.Index(m, c, o, 700, k=6)
+    qm, qo = synth.synth_queries(tree, 16, "full", seed=2)
+    lens = np.diff(o.astype(np.int64))
+    for fp_kw in (dict(fs_min=5, fs_max=9, fs_min_len=int(np.percentile(lens, 70)), fs_full_len=int(lens.max()) - 2, fs_req_gaps=3),
+                  dict(fs_min=3, fs_max=20, fs_msc=30.0, fs_min_len=10, fs_full_len=int(lens.max()), fs_req_full=3, fs_req_gaps=0),
+                  dict(fs_min=40, fs_max=40, fs_min_len=10, fs_full_len=10 ** 6, fs_req_gaps=10, fs_req=2),
+                  dict(fs_min=2, fs_max=4, fs_min_len=10 ** 6, fs_full_len=10, fs_req_gaps=0)):
+        fids, fsc, fn = ix.family(qm, qo, sina_b200.FamParams(**fp_kw))
+        for i in range(16):
+            n1, f1, s1 = orc.family(oix, msa, qm[int(qo[i]):int(qo[i + 1])], O.FamParams(**fp_kw))
+            assert fn[i] == n1, (fp_kw, i)
+            assert (fids[i, :max(n1, 0)] == f1).all() and (fsc[i, :max(n1, 0)] == s1).all()
+    fp_kw = dict(fs_min=5, fs_max=9, fs_min_len=10, fs_full_len=250, fs_req_gaps=0, leave_query_out=1)
+    qs = [msa.row(r)[0] for r in (0, 17, 333)]
+    qm2, qo2 = pack_queries(qs)
+    fids, fsc, fn = ix.family(qm2, qo2, sina_b200.FamParams(**fp_kw), exclude_ids=[0, 17, 333])
+    for i, rid in enumerate((0, 17, 333)):
+        n1, f1, _ = orc.family(oix, msa, qs[i], O.FamParams(**fp_kw), exclude_id=rid)
+        assert fn[i] == n1 and (fids[i, :n1] == f1).all() and rid not in fids[i, :n1]
+    orc.index_free(oix)
+    ix.close()
+
+
+def test_pipeline_golden():
+    case = load_golden("pipeline_case")
+    tree, m, c, o = synth.synth_msa(case["N"], W=case["W"], L=case["L"], seed=case["seed"])
+    ix = sina_b200.Index(m, c, o, case["W"], k=case["k"])
+    qm, qo = pack_queries([O.encode(q["query"]) for q in case["queries"]])
+    oc, om, res = ix.run(qm, qo, sina_b200.FamParams(**case["fam_params"]), sina_b200.AlignParams())
+    for i, qe in enumerate(case["queries"]):
+        a, b = int(qo[i]), int(qo[i + 1])
+        assert res[i]["status"] == qe["status"]
+        assert oc[a:b].tolist() == qe["cols"], i
+        assert (res[i]["head"], res[i]["tail"], res[i]["qual"], res[i]["n_nodes"]) == (qe["head"], qe["tail"], qe["qual"], qe["n_nodes"])
+        assert int(bits(res[i]["score"])) == qe["score_bits"]
+    ix.close()
+
+
+def test_full_size_queries_vs_oracle(orc):
+    """full-length (~1500 nt) and V4 (~250 nt) queries against 40-member families on a 50 000-column MSA:
+    multi-group graphs (V ~ 3000), default parameters, whole path through sg_run_batch."""
+    tree, m, c, o = synth.synth_msa(3000, W=50000, L=1500, seed=20260117)
+    msa = O.MSA(m, c, o, 50000)
+    oix = orc.index_build(msa, 10, 0)
+    ix = sina_b200.Index(m, c, o, 50000, k=10)
+    for kind, nq in (("full", 24), ("v4", 40)):
+        qm, qo = synth.synth_queries(tree, nq, kind, seed=13)
+        oc, om, res = ix.run(qm, qo)
+        ores, occ, omm, cells, posts, nt = orc.run_batch(oix, msa, qm, qo)
+        for i in range(nq):
+            a, b = int(qo[i]), int(qo[i + 1])
+            compare_result(res[i], oc[a:b], om[a:b], ores[i], occ[a:a + ores[i].n_out], omm[a:a + ores[i].n_out], 50000, (kind, i))
+        assert all(r["status"] == 0 for r in res)
+    orc.index_free(oix)
+    ix.close()
