@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SINA hot path on B200.
+
+    python bench.py [--gpus N --steps K --warmup W]            our CUDA path
+    python bench.py --impl reference [--steps K --warmup W]    the reference's CPU code on the host cores
+
+Workload (BASELINE.json configs[1]): 10 000 full-length 16S queries (~1 500 nt) against a synthetic
+SILVA-like reference MSA of 50 000 sequences x 50 000 columns, reference defaults (k=10 fast, --fs-max 40).
+One "step" = the whole hot path (k-mer family finding -> family graph -> mesh DP -> backtrack -> gap
+placement) over the step's queries. `value` = sequences/s with the queries already resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call (sg_run_batch: H2D of the queries, D2H of the aligned
+columns inside the timed region). Under torchrun each rank owns one GPU, holds a replica of the index and
+aligns its own shard of queries (weak scaling, no collective on the data path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_REFS, W_COLS, L_REF, KMER = 50000, 50000, 1500, 10
+SEED = 20260117
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=10000, help="queries per step per GPU")
+    ap.add_argument("--refs", type=int, default=N_REFS)
+    ap.add_argument("--kind", default="full", choices=["full", "v4"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_data(args, rank):
+    from sina_b200 import synth
+    tree, m, c, o = synth.synth_msa(args.refs, W=W_COLS, L=L_REF, seed=SEED)
+    qm, qo = synth.synth_queries(tree, args.queries, args.kind, seed=1000 + rank)
+    return tree, m, c, o, qm, qo
+
+
+def cpu_baseline(args, m, c, o, qm, qo, nsample, nthreads=0):
+    """reference's own CPU code (oracle/_ref, kind 'reference') or the C port (kind 'port') on a bounded
+    sample of the same workload, all host cores. Returns dict(value seq/s, cores, kind, sample, mcells_s)."""
+    from oracle import oracle as O
+    nsample = min(nsample, len(qo) - 1)
+    sub_off = (qo[:nsample + 1] - qo[0]).astype(np.uint64)
+    sub_m = qm[int(qo[0]):int(qo[nsample])]
+    msa = O.MSA(m, c, o, W_COLS)
+    kind = "reference" if os.path.exists(O.REF_SO) else "port"
+    if kind == "reference":
+        ref = O.Ref()
+        db = ref.db(msa)
+        ix = ref.kidx_build(db, KMER, 0)
+        queries = [O.decode(sub_m[int(sub_off[i]):int(sub_off[i + 1])]) for i in range(nsample)]
+        t0 = time.perf_counter()
+        res, oc, qoff, cells, posts, nt = ref.run_batch(ix, queries, O.FamParams(), O.AlignParams(), nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        ref.kidx_free(ix)
+        ref.db_free(db)
+    else:
+        orc = O.Oracle()
+        ix = orc.index_build(msa, KMER, 0)
+        t0 = time.perf_counter()
+        res, oc, om, cells, posts, nt = orc.run_batch(ix, msa, sub_m, sub_off, O.FamParams(), O.AlignParams(), nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        orc.index_free(ix)
+    return {"value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": kind,
+            "sample": "%d of the step's %s queries vs the same %d-row index, whole path, %.1f s" % (nsample, args.kind, args.refs, dt),
+            "mcells_per_s": cells / dt / 1e6, "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation timed on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tree, m, c, o, qm, qo = make_data(args, 0)
+    ncores = os.cpu_count() or 1
+    nsample = args.cpu_sample or max(16, 4 * ncores)
+    times, last = [], None
+    for it in range(args.warmup + args.steps):
+        # each step = a bounded sample of the workload (different queries every step)
+        a = (it * nsample) % max(1, args.queries - nsample)
+        sub = cpu_baseline(args, m, c, o, qm, qo[a:], nsample)
+        if it >= args.warmup:
+            times.append(sub["seconds"])
+            last = sub
+    t = float(np.mean(times))
+    val = nsample / t
+    line = {"impl": "reference", "metric": "sequences aligned/sec", "value": val, "unit": "sequences/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, nsample),
+            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": last["cores"], "kind": last["kind"],
+                             "sample": last["sample"]},
+            "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, queries_per_step):
+    return {"workload": "%d %s 16S queries (~%d nt) per step per GPU vs synthetic %d-seq reference MSA (%d columns), "
+                        "k=%d fast, fs-max 40, reference defaults" % (queries_per_step, "full-length" if args.kind == "full" else "V4",
+                                                                     1500 if args.kind == "full" else 280, args.refs, W_COLS, KMER),
+            "queries_per_step_per_gpu": queries_per_step, "refs": args.refs, "columns": W_COLS, "k": KMER,
+            "l2": "inputs larger than L2 (index 0.4 GB + >10 GB traceback written per step)",
+            "parallelism": "queries sharded over GPUs, index replicated, no collective"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import sina_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or sina_b200.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: sina_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    tree, m, c, o, qm, qo = make_data(args, rank)
+    nq = args.queries
+    ix = sina_b200.Index(m, c, o, W_COLS, k=KMER, device=local)
+    fp, ap = sina_b200.FamParams(), sina_b200.AlignParams()
+    sess = sina_b200.Session(ix, nq, int(qo[-1]))
+    sess.upload(qm, qo)  # queries resident in HBM before the timed region
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        sess.family(fp)
+        sess.align(ap)
+        sess.sync()
+
+    def step_e2e():
+        return ix.run(qm, qo, fp, ap)
+
+    # ---- device-resident number
+    for _ in range(args.warmup):
+        step_device()
+    sess.stats(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+    barrier()
+    dt = time.perf_counter() - t0
+    st = sess.stats()
+    # ---- end-to-end through the host-buffer C-ABI call
+    for _ in range(min(args.warmup, 1) or 1):
+        oc, om, res = step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        oc, om, res = step_e2e()
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    n_ok = int((res["status"] == 0).sum())
+
+    if world > 1:
+        tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(tt[0]), float(tt[1])
+        cnt = torch.tensor([float(st["cells"]), float(st["postings"]), float(st["ms_dp"]), float(st["ms_find"])],
+                           device="cuda", dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        cells_all, posts_all = float(cnt[0]), float(cnt[1])
+    else:
+        cells_all, posts_all = float(st["cells"]), float(st["postings"])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        total_q = nq * args.steps * world
+        value = total_q / dt
+        # dominant kernel: mesh DP. Algorithmic bytes = 1 B packed traceback per cell, this rank.
+        dp_s = st["ms_dp"] / 1e3
+        cells = float(st["cells"])
+        gcups = cells / dp_s / 1e9 if dp_s > 0 else 0.0
+        sm_mhz = sampler.summary().get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        ops_per_cell = 3 + 7 * 1.65
+        issue_ceiling = 148 * 128 * sm_mhz * 1e6 / ops_per_cell / 1e9  # GCUPS at the measured clock
+        find_s = st["ms_find"] / 1e3
+        posts = float(st["postings"])
+        kmer_bytes = 4.0 * posts + (2.0 * args.refs + 8.0 * 41) * nq * args.steps
+        line = {
+            "metric": "sequences aligned/sec", "value": value, "unit": "sequences/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, nq),
+            "e2e": {"value": total_q / dt_e2e, "unit": "sequences/s", "h2d_bytes_per_step": int(len(qm) + qo.nbytes),
+                    "d2h_bytes_per_step": int(oc.nbytes + om.nbytes + res.nbytes)},
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": {"kernel": "mesh_kernel", "bound": "hbm", "achieved": cells * 1.0 / dp_s / 1e9 if dp_s > 0 else 0.0,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": (cells / dp_s / 1e9 / hbm_peak) if dp_s > 0 else 0.0,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "DP is issue/latency bound, not HBM bound: see gcups vs issue_ceiling_gcups",
+                         "gcups": gcups, "issue_ceiling_gcups": issue_ceiling,
+                         "frac_issue": gcups / issue_ceiling if issue_ceiling else None,
+                         "share_of_step": st["ms_dp"] / (dt * 1e3)},
+            "roofline_kmer": {"kernel": "find_tile_kernel", "bound": "hbm", "achieved": kmer_bytes / find_s / 1e9 if find_s > 0 else 0.0,
+                              "peak": hbm_peak, "unit": "GB/s", "frac": (kmer_bytes / find_s / 1e9 / hbm_peak) if find_s > 0 else 0.0,
+                              "bytes_per_query": "4*P + 2*N + 8*max", "postings_per_query": posts / (nq * args.steps)},
+            "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
+            "cells_per_query": cells / (nq * args.steps), "aligned_ok": n_ok,
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            ncores = os.cpu_count() or 1
+            nsample = args.cpu_sample or max(16, 4 * ncores)
+            cb = cpu_baseline(args, m, c, o, qm, qo, nsample)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s")}
+        print(json.dumps(line))
+    sess.close()
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

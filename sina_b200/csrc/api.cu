@@ -53,7 +53,8 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     if (fam_cap > FAM_CAP_MAX) SG_FAIL(SG_ERR_LIMIT, "family size above 255 is not supported");
     free_align(s);
     Index* ix = s->ix;
-    const uint64_t Q = s->max_q;
+    const uint64_t Q = s->max_q;   // per-query results of the whole batch
+    const uint64_t C = s->chunk;   // graph/DP workspace: one align pass handles `chunk` queries
     s->fam_cap = fam_cap;
     s->icap = fam_cap * ix->max_row_len;
     s->ncap = ix->W < s->icap ? ix->W : s->icap;
@@ -62,20 +63,20 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     SG_TRY(dmalloc(&s->d_fam_ids, Q * fam_cap)); SG_TRY(dmalloc(&s->d_fam_scores, Q * fam_cap));
     SG_TRY(dmalloc(&s->d_afam, Q * fam_cap)); SG_TRY(dmalloc(&s->d_afam_n, Q));
     SG_TRY(dmalloc(&s->d_contains, Q * fam_cap)); SG_TRY(dmalloc(&s->d_copy_src, Q * 2));
-    SG_TRY(dmalloc(&s->d_tab, Q * s->ncap * fam_cap)); SG_TRY(dmalloc(&s->d_tabli, Q * s->ncap * fam_cap));
-    SG_TRY(dmalloc(&s->d_colof, Q * s->ncap)); SG_TRY(dmalloc(&s->d_colbase, Q * (s->ncap + 1)));
-    SG_TRY(dmalloc(&s->d_item_node, Q * I)); SG_TRY(dmalloc(&s->d_slot, Q * I));
-    SG_TRY(dmalloc(&s->d_ncol, Q * I)); SG_TRY(dmalloc(&s->d_nmask, Q * I)); SG_TRY(dmalloc(&s->d_ncount, Q * I));
-    SG_TRY(dmalloc(&s->d_nweight, Q * I)); SG_TRY(dmalloc(&s->d_nsigma, Q * I));
-    SG_TRY(dmalloc(&s->d_slotbase, Q * (I + 1))); SG_TRY(dmalloc(&s->d_cursor, Q * I));
-    SG_TRY(dmalloc(&s->d_pred_off, Q * (I + 1))); SG_TRY(dmalloc(&s->d_preds, Q * I));
-    SG_TRY(dmalloc(&s->d_pdesc, Q * I)); SG_TRY(dmalloc(&s->d_spillrow, Q * I)); SG_TRY(dmalloc(&s->d_nflags, Q * I));
-    SG_TRY(dmalloc(&s->d_lastnodes, Q * I)); SG_TRY(dmalloc(&s->d_groups, Q * s->gcap));
-    SG_TRY(dmalloc(&s->d_lastcol, Q * I)); SG_TRY(dmalloc(&s->d_rowmin, Q * I)); SG_TRY(dmalloc(&s->d_rowarg, Q * I));
+    SG_TRY(dmalloc(&s->d_tab, C * s->ncap * fam_cap)); SG_TRY(dmalloc(&s->d_tabli, C * s->ncap * fam_cap));
+    SG_TRY(dmalloc(&s->d_colof, C * s->ncap)); SG_TRY(dmalloc(&s->d_colbase, C * (s->ncap + 1)));
+    SG_TRY(dmalloc(&s->d_item_node, C * I)); SG_TRY(dmalloc(&s->d_slot, C * I));
+    SG_TRY(dmalloc(&s->d_ncol, C * I)); SG_TRY(dmalloc(&s->d_nmask, C * I)); SG_TRY(dmalloc(&s->d_ncount, C * I));
+    SG_TRY(dmalloc(&s->d_nweight, C * I)); SG_TRY(dmalloc(&s->d_nsigma, C * I));
+    SG_TRY(dmalloc(&s->d_slotbase, C * (I + 1))); SG_TRY(dmalloc(&s->d_cursor, C * I));
+    SG_TRY(dmalloc(&s->d_pred_off, C * (I + 1))); SG_TRY(dmalloc(&s->d_preds, C * I));
+    SG_TRY(dmalloc(&s->d_pdesc, C * I)); SG_TRY(dmalloc(&s->d_spillrow, C * I)); SG_TRY(dmalloc(&s->d_nflags, C * I));
+    SG_TRY(dmalloc(&s->d_lastnodes, C * I)); SG_TRY(dmalloc(&s->d_groups, C * s->gcap));
+    SG_TRY(dmalloc(&s->d_lastcol, C * I)); SG_TRY(dmalloc(&s->d_rowmin, C * I)); SG_TRY(dmalloc(&s->d_rowarg, C * I));
     // arenas: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
     const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
-    uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, Q * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
-    uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, Q * (256 * max_qlen_guess * 8 / 1000000 + 1))));
+    uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
+    uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (256 * max_qlen_guess * 8 / 1000000 + 1))));
     s->tb_words = tb_mb * 1024 * 1024 / 4;
     s->spill_elems = sp_mb * 1024 * 1024 / 8;
     SG_TRY(dmalloc(&s->d_tb, s->tb_words)); SG_TRY(dmalloc(&s->d_spill, s->spill_elems));
@@ -186,6 +187,7 @@ void sg_index_destroy(sg_index* h) {
     Index* ix = (Index*)h;
     if (!ix) return;
     cudaSetDevice(ix->device);
+    if (ix->cached) { sg_session_destroy((sg_session*)ix->cached); ix->cached = nullptr; }
     cudaFree(ix->d_masks); cudaFree(ix->d_cols); cudaFree(ix->d_row_off); cudaFree(ix->d_list_off);
     cudaFree(ix->d_postings);
     delete ix;
@@ -249,6 +251,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     SG_CUDA(cudaSetDevice(ix->device));
     Session* s = new Session;
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
+    s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 1024)));
     *out = (sg_session*)s;
     SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) SG_CUDA(cudaEventCreate(&e));
@@ -373,26 +376,29 @@ int sg_session_align(sg_session* h, const sg_align_params* ap) {
     SG_TRY(stage_begin(s, 2));
     SG_TRY(launch_prealign(s, *ap));
     SG_TRY(stage_end(s, &s->stats.ms_graph));
-    uint32_t prev_remaining = 0xffffffffu;
-    for (int pass = 0;; pass++) {
-        SG_CUDA(cudaMemsetAsync(s->d_counters + 2, 0, 16, s->stream));  // arena cursors
-        SG_CUDA(cudaMemsetAsync(s->d_retry + 1, 0, 4, s->stream));
-        SG_TRY(stage_begin(s, 2));
-        SG_TRY(launch_graph(s, *ap));
-        SG_TRY(stage_end(s, &s->stats.ms_graph));
-        SG_TRY(stage_begin(s, 3));
-        SG_TRY(launch_mesh(s, *ap));
-        SG_TRY(stage_end(s, &s->stats.ms_dp));
-        SG_TRY(stage_begin(s, 4));
-        SG_TRY(launch_backtrack(s, *ap));
-        SG_TRY(stage_end(s, &s->stats.ms_backtrack));
-        uint32_t remaining = 0;
-        SG_CUDA(cudaMemcpyAsync(&remaining, s->d_retry + 1, 4, cudaMemcpyDeviceToHost, s->stream));
-        SG_CUDA(cudaStreamSynchronize(s->stream));
-        if (remaining == 0) break;
-        if (remaining >= prev_remaining)
-            SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
-        prev_remaining = remaining;
+    for (uint32_t q0 = 0; q0 < s->nq; q0 += s->chunk) {
+        const uint32_t n = std::min(s->chunk, s->nq - q0);
+        uint32_t prev_remaining = 0xffffffffu;
+        for (;;) {  // passes: queries that did not fit the traceback/spill arenas are redone with the arenas reset
+            SG_CUDA(cudaMemsetAsync(s->d_counters + 2, 0, 16, s->stream));  // arena cursors
+            SG_CUDA(cudaMemsetAsync(s->d_retry + 1, 0, 4, s->stream));
+            SG_TRY(stage_begin(s, 2));
+            SG_TRY(launch_graph(s, *ap, q0, n));
+            SG_TRY(stage_end(s, &s->stats.ms_graph));
+            SG_TRY(stage_begin(s, 3));
+            SG_TRY(launch_mesh(s, *ap, q0, n));
+            SG_TRY(stage_end(s, &s->stats.ms_dp));
+            SG_TRY(stage_begin(s, 4));
+            SG_TRY(launch_backtrack(s, *ap, q0, n));
+            SG_TRY(stage_end(s, &s->stats.ms_backtrack));
+            uint32_t remaining = 0;
+            SG_CUDA(cudaMemcpyAsync(&remaining, s->d_retry + 1, 4, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaStreamSynchronize(s->stream));
+            if (remaining == 0) break;
+            if (remaining >= prev_remaining)
+                SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
+            prev_remaining = remaining;
+        }
     }
     unsigned long long cnt[2];
     SG_CUDA(cudaMemcpyAsync(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost, s->stream));
@@ -498,110 +504,106 @@ int sg_session_dump_graph(sg_session* h, uint32_t q, uint32_t cap_nodes, uint32_
 }
 
 // ------------------------------------------------------------------------- host-buffer entry points
+// One call = upload + kernels + download. The session (device workspace) is cached in the index and reused
+// by later calls, so steady-state calls do no cudaMalloc. Calls on one index are serialised by its mutex.
 namespace {
-struct Chunker {  // split a host batch into session-sized pieces
-    uint32_t max_q; uint64_t max_bases;
-    uint32_t next(const uint64_t* qoff, uint32_t nq, uint32_t from) const {
-        uint32_t to = from;
-        while (to < nq && to - from < max_q && qoff[to + 1] - qoff[from] <= max_bases) to++;
-        return to;
-    }
-};
-uint32_t default_batch() { return (uint32_t)env_mb("SG_BATCH", 1024); }
+constexpr uint32_t HOST_CALL_MAX_Q = 65536;  // queries per internal session; larger batches are looped
 
-int make_session(sg_index* ix, const uint64_t* qoff, uint32_t nq, sg_session** s, Chunker* ch) {
-    uint64_t maxlen = 2;
-    for (uint32_t i = 0; i < nq; i++) maxlen = std::max<uint64_t>(maxlen, qoff[i + 1] - qoff[i]);
-    ch->max_q = std::min<uint32_t>(nq, default_batch());
-    ch->max_bases = (uint64_t)ch->max_q * maxlen;
-    return sg_session_create(ix, ch->max_q, ch->max_bases, s);
-}
+struct SessionLease {
+    Index* ix; Session* s = nullptr; int rc = SG_OK;
+    SessionLease(sg_index* h, const uint64_t* qoff, uint32_t nq) : ix((Index*)h) {
+        ix->mu.lock();
+        uint64_t maxlen = 2;
+        for (uint32_t i = 0; i < nq; i++) maxlen = std::max<uint64_t>(maxlen, qoff[i + 1] - qoff[i]);
+        const uint32_t want_q = std::min(nq, HOST_CALL_MAX_Q);
+        uint64_t want_bases = 0;
+        for (uint32_t a = 0; a < nq; a += want_q)
+            want_bases = std::max<uint64_t>(want_bases, qoff[std::min(nq, a + want_q)] - qoff[a]);
+        Session* c = (Session*)ix->cached;
+        if (c && c->max_q >= want_q && c->max_bases >= want_bases) { s = c; return; }
+        if (c) { sg_session_destroy((sg_session*)c); ix->cached = nullptr; }
+        sg_session* ns = nullptr;
+        rc = sg_session_create(h, want_q, want_bases, &ns);
+        if (rc != SG_OK) { if (ns) sg_session_destroy(ns); return; }
+        ix->cached = ns;
+        s = (Session*)ns;
+    }
+    ~SessionLease() { ix->mu.unlock(); }
+    uint32_t step() const { return s->max_q; }
+};
 }  // namespace
 
 int sg_find_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, uint32_t max,
                   int16_t* scores, uint32_t* ids, uint32_t* nres) {
     if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_find_batch: bad argument");
-    sg_session* s = nullptr;
-    Chunker ch;
-    int rc = make_session(ix, qoff, nq, &s, &ch);
-    const uint32_t N = ((Index*)ix)->N;
-    const uint32_t m = std::min(max, N);
-    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
-        uint32_t b = ch.next(qoff, nq, a);
-        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
-        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, nullptr))) break;
-        if ((rc = sg_session_find(s, max))) break;
-        rc = sg_session_download_find(s, scores ? scores + (uint64_t)a * m : nullptr, ids ? ids + (uint64_t)a * m : nullptr,
-                                      nres ? nres + a : nullptr);
-        a = b;
+    SessionLease L(ix, qoff, nq);
+    if (L.rc) return L.rc;
+    sg_session* s = (sg_session*)L.s;
+    const uint32_t m = std::min(max, ((Index*)ix)->N);
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, nullptr));
+        SG_TRY(sg_session_find(s, max));
+        SG_TRY(sg_session_download_find(s, scores ? scores + (uint64_t)a * m : nullptr, ids ? ids + (uint64_t)a * m : nullptr,
+                                        nres ? nres + a : nullptr));
     }
-    sg_session_destroy(s);
-    return rc;
+    return SG_OK;
 }
 
 int sg_family_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
                     const int64_t* exclude_ids, const sg_fam_params* fp, uint32_t fam_stride, uint32_t* fam_ids,
                     float* fam_scores, int32_t* fam_n) {
     if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_family_batch: bad argument");
-    sg_session* s = nullptr;
-    Chunker ch;
-    int rc = make_session(ix, qoff, nq, &s, &ch);
-    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
-        uint32_t b = ch.next(qoff, nq, a);
-        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
-        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, exclude_ids ? exclude_ids + a : nullptr))) break;
-        if ((rc = sg_session_family(s, fp))) break;
-        rc = sg_session_download_family(s, fam_stride, fam_ids ? fam_ids + (uint64_t)a * fam_stride : nullptr,
-                                        fam_scores ? fam_scores + (uint64_t)a * fam_stride : nullptr,
-                                        fam_n ? fam_n + a : nullptr);
-        a = b;
+    SessionLease L(ix, qoff, nq);
+    if (L.rc) return L.rc;
+    sg_session* s = (sg_session*)L.s;
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
+        SG_TRY(sg_session_family(s, fp));
+        SG_TRY(sg_session_download_family(s, fam_stride, fam_ids ? fam_ids + (uint64_t)a * fam_stride : nullptr,
+                                          fam_scores ? fam_scores + (uint64_t)a * fam_stride : nullptr,
+                                          fam_n ? fam_n + a : nullptr));
     }
-    sg_session_destroy(s);
-    return rc;
+    return SG_OK;
 }
 
 int sg_align_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const uint32_t* fam_ids,
                    const uint64_t* fam_off, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
                    sg_align_result* results) {
     if (!ix || !qmasks || !qoff || nq == 0 || !fam_ids || !fam_off) SG_FAIL(SG_ERR_ARG, "sg_align_batch: bad argument");
-    sg_session* s = nullptr;
-    Chunker ch;
-    int rc = make_session(ix, qoff, nq, &s, &ch);
-    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
-        uint32_t b = ch.next(qoff, nq, a);
-        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
-        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, nullptr))) break;
-        if ((rc = sg_session_set_family(s, fam_ids, fam_off + a))) break;
-        if ((rc = sg_session_align(s, ap))) break;
+    SessionLease L(ix, qoff, nq);
+    if (L.rc) return L.rc;
+    sg_session* s = (sg_session*)L.s;
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, nullptr));
+        SG_TRY(sg_session_set_family(s, fam_ids, fam_off + a));
+        SG_TRY(sg_session_align(s, ap));
         const uint64_t o = qoff[a];
-        rc = sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
-                                       results ? results + a : nullptr);
-        a = b;
+        SG_TRY(sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
+                                         results ? results + a : nullptr));
     }
-    sg_session_destroy(s);
-    return rc;
+    return SG_OK;
 }
 
 int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const int64_t* exclude_ids,
                  const sg_fam_params* fp, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
                  sg_align_result* results) {
     if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_run_batch: bad argument");
-    sg_session* s = nullptr;
-    Chunker ch;
-    int rc = make_session(ix, qoff, nq, &s, &ch);
-    for (uint32_t a = 0; rc == SG_OK && a < nq;) {
-        uint32_t b = ch.next(qoff, nq, a);
-        if (b == a) { set_error("query too long for a session"); rc = SG_ERR_LIMIT; break; }
-        if ((rc = sg_session_upload(s, qmasks, qoff + a, b - a, exclude_ids ? exclude_ids + a : nullptr))) break;
-        if ((rc = sg_session_family(s, fp))) break;
-        if ((rc = sg_session_align(s, ap))) break;
+    SessionLease L(ix, qoff, nq);
+    if (L.rc) return L.rc;
+    sg_session* s = (sg_session*)L.s;
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
+        SG_TRY(sg_session_family(s, fp));
+        SG_TRY(sg_session_align(s, ap));
         const uint64_t o = qoff[a];
-        rc = sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
-                                       results ? results + a : nullptr);
-        a = b;
+        SG_TRY(sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
+                                         results ? results + a : nullptr));
     }
-    sg_session_destroy(s);
-    return rc;
+    return SG_OK;
 }
 
 }  // extern "C"

@@ -11,7 +11,7 @@
 namespace sg {
 
 struct BtArgs {
-    uint32_t nq, W;
+    uint32_t nq, W, q0;  // nq queries of the chunk starting at q0
     const uint8_t* qmasks; const uint64_t* qoff;
     GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap; uint32_t* remaining;
     const uint32_t* ncol; const float* nweight; const uint32_t* nsigma; const uint32_t* pred_off;
@@ -93,8 +93,9 @@ __device__ int fix_duplicate_positions(uint32_t* pos, uint8_t* masks, uint32_t n
 }
 
 __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= A.nq) return;
+    const uint32_t ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= A.nq) return;
+    const uint32_t q = A.q0 + ql;
     const GraphHdr h = A.hdr[q];
     if (h.status == GS_DONE) return;  // finished in an earlier pass
     if (h.status == GS_ARENA_FULL) { atomicAdd(A.remaining, 1u); return; }  // host resets the arenas and re-runs
@@ -116,13 +117,13 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     }
     if (h.status != GS_OK) { r.status = (int32_t)h.status; A.results[q] = r; A.hdr[q].status = GS_DONE; return; }
 
-    const uint64_t io = (uint64_t)q * A.icap;
-    const uint32_t* pred_off = A.pred_off + (uint64_t)q * (A.icap + 1);
+    const uint64_t io = (uint64_t)ql * A.icap;
+    const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     const uint32_t* preds = A.preds + io;
     const uint32_t* nsigma = A.nsigma + io;
     const uint32_t* ncol = A.ncol + io;
     const float* nweight = A.nweight + io;
-    const GroupInfo* groups = A.groups + (uint64_t)q * A.gcap;
+    const GroupInfo* groups = A.groups + (uint64_t)ql * A.gcap;
     const uint32_t* tbq = A.tb + h.tb_off;
     const bool wide = h.wide != 0;
     const uint32_t V = h.V, W = A.W;
@@ -258,17 +259,17 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     A.hdr[q].status = GS_DONE;
 }
 
-int launch_backtrack(Session* s, const sg_align_params& ap) {
+int launch_backtrack(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
     BtArgs A;
-    A.nq = s->nq; A.W = ix->W; A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
+    A.nq = n; A.q0 = q0; A.W = ix->W; A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
     A.gcap = s->gcap; A.icap = s->icap; A.remaining = s->d_retry + 1; A.ncol = s->d_ncol; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma;
     A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.lastnodes = s->d_lastnodes; A.afam_n = s->d_afam_n;
     A.tb = s->d_tb; A.lastcol = s->d_lastcol; A.rowmin = s->d_rowmin; A.rowarg = s->d_rowarg;
     A.copy_src = s->d_copy_src; A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off;
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;
     A.ms = -ap.match_score; A.overhang = ap.overhang; A.lowercase = ap.lowercase;
-    backtrack_kernel<<<(s->nq + 63) / 64, 64, 0, s->stream>>>(A);
+    backtrack_kernel<<<(n + 63) / 64, 64, 0, s->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/sina_b200.h"
@@ -56,6 +57,8 @@ struct Index {
     uint64_t* d_list_off = nullptr; // [n_tiles*n_slots + 1], tile-major
     uint32_t* d_postings = nullptr; // global reference ids, unordered inside a (tile,k-mer) list
     uint64_t n_postings = 0;
+    void* cached = nullptr;  // Session reused by the host-buffer entry points
+    std::mutex mu;           // serialises host-buffer calls on this index
 };
 
 // per-query graph header written by the graph kernel, read by DP / backtrack / host
@@ -79,6 +82,7 @@ struct Session {
     Index* ix = nullptr;
     cudaStream_t stream = nullptr;
     uint32_t max_q = 0, nq = 0;
+    uint32_t chunk = 0;              // queries per align pass: the graph/DP workspace is sized for this many
     uint64_t max_bases = 0;
     // queries
     uint8_t* d_qmasks = nullptr;
@@ -148,9 +152,9 @@ int launch_index_build(Index* ix, cudaStream_t st);
 int launch_find(Session* s, uint32_t max);
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window);
 int launch_prealign(Session* s, const sg_align_params& ap);
-int launch_graph(Session* s, const sg_align_params& ap);
-int launch_mesh(Session* s, const sg_align_params& ap);
-int launch_backtrack(Session* s, const sg_align_params& ap);
+int launch_graph(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
+int launch_mesh(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
+int launch_backtrack(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -92,7 +92,7 @@ done:
 struct GraphArgs {
     const uint8_t* masks; const uint32_t* cols; const uint64_t* row_off; uint32_t W;
     const uint32_t* afam; const uint32_t* afam_n; uint32_t fam_cap;
-    uint32_t icap, ncap, gcap;
+    uint32_t icap, ncap, gcap, q0;  // q0: first query of the chunk (workspace arrays are chunk-local)
     GraphHdr* hdr;
     uint8_t *tab, *tabli; uint32_t *colof, *colbase, *item_node, *slot;
     uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
@@ -119,9 +119,12 @@ __device__ uint32_t scan_array_inplace(T* arr, uint32_t n, uint32_t* red) {
 
 __global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
     extern __shared__ uint32_t sm[];
-    const uint32_t q = blockIdx.x;
+    const uint32_t q = A.q0 + blockIdx.x;  // global query index (hdr, family); workspace uses the local index
+    const uint32_t ql = blockIdx.x;
     GraphHdr* hdr = A.hdr + q;
-    if (hdr->status != GS_OK) return;
+    if (hdr->status == GS_ARENA_FULL) { if (threadIdx.x == 0) hdr->status = GS_OK; }  // retry pass, arenas were reset
+    else if (hdr->status != GS_OK) return;
+    __syncthreads();
     const uint32_t words = (A.W + 31) >> 5;
     uint32_t* bitmap = sm;            // [words]   columns used by any family row
     uint32_t* wrank = sm + words;     // [words]   exclusive popcount prefix
@@ -134,22 +137,22 @@ __global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
     const uint32_t Lq = hdr->qlen;
 
     // per-query views
-    uint8_t* tab = A.tab + (uint64_t)q * A.ncap * A.fam_cap;
-    uint8_t* tabli = A.tabli + (uint64_t)q * A.ncap * A.fam_cap;
-    uint32_t* colof = A.colof + (uint64_t)q * A.ncap;
-    uint32_t* colbase = A.colbase + (uint64_t)q * (A.ncap + 1);
-    const uint64_t io = (uint64_t)q * A.icap;
+    uint8_t* tab = A.tab + (uint64_t)ql * A.ncap * A.fam_cap;
+    uint8_t* tabli = A.tabli + (uint64_t)ql * A.ncap * A.fam_cap;
+    uint32_t* colof = A.colof + (uint64_t)ql * A.ncap;
+    uint32_t* colbase = A.colbase + (uint64_t)ql * (A.ncap + 1);
+    const uint64_t io = (uint64_t)ql * A.icap;
     uint32_t* item_node = A.item_node + io;
     uint32_t* slot = A.slot + io;
     uint32_t* ncol = A.ncol + io; uint8_t* nmask = A.nmask + io; uint16_t* ncount = A.ncount + io;
     float* nweight = A.nweight + io; uint32_t* nsigma = A.nsigma + io;
-    uint32_t* slotbase = A.slotbase + (uint64_t)q * (A.icap + 1);
+    uint32_t* slotbase = A.slotbase + (uint64_t)ql * (A.icap + 1);
     uint32_t* cursor = A.cursor + io;
-    uint32_t* pred_off = A.pred_off + (uint64_t)q * (A.icap + 1);
+    uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     uint32_t* preds = A.preds + io; uint32_t* pdesc = A.pdesc + io;
     int32_t* spillrow = A.spillrow + io; uint8_t* nflags = A.nflags + io;
     uint32_t* lastnodes = A.lastnodes + io;
-    GroupInfo* groups = A.groups + (uint64_t)q * A.gcap;
+    GroupInfo* groups = A.groups + (uint64_t)ql * A.gcap;
 
     // ---- 0. item offsets of the family rows
     for (uint32_t i = tid; i < words; i += nt) bitmap[i] = 0;
@@ -360,12 +363,12 @@ int launch_prealign(Session* s, const sg_align_params& ap) {
     return SG_OK;
 }
 
-int launch_graph(Session* s, const sg_align_params& ap) {
+int launch_graph(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
     GraphArgs A;
     A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off; A.W = ix->W;
     A.afam = s->d_afam; A.afam_n = s->d_afam_n; A.fam_cap = s->fam_cap;
-    A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap;
+    A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap; A.q0 = q0;
     A.hdr = s->d_hdr; A.tab = s->d_tab; A.tabli = s->d_tabli; A.colof = s->d_colof; A.colbase = s->d_colbase;
     A.item_node = s->d_item_node; A.slot = s->d_slot; A.ncol = s->d_ncol; A.nmask = s->d_nmask;
     A.ncount = s->d_ncount; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.slotbase = s->d_slotbase;
@@ -376,7 +379,7 @@ int launch_graph(Session* s, const sg_align_params& ap) {
     const uint32_t words = (ix->W + 31) >> 5;
     size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8) * 4;
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_kernel<<<s->nq, 512, smem, s->stream>>>(A);
+    graph_kernel<<<n, 512, smem, s->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

@@ -19,7 +19,7 @@ namespace sg {
 
 struct MeshArgs {
     const uint8_t* qmasks; const uint64_t* qoff;
-    const GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap;
+    const GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap, q0;
     const uint8_t* nmask; const float* nweight; const uint32_t* nsigma;
     const uint32_t* pred_off; const uint32_t* pdesc; const int32_t* spillrow; const uint8_t* nflags;
     uint32_t* tb; float2* spill;
@@ -32,12 +32,12 @@ constexpr int R = DP_RING;
 constexpr int NPR = 4;  // predecessors cached in registers
 
 template <bool WIDE>
-__device__ __forceinline__ void mesh_query(const MeshArgs& A, const GraphHdr& h, uint32_t q, float2* ring,
+__device__ __forceinline__ void mesh_query(const MeshArgs& A, const GraphHdr& h, uint32_t ql, float2* ring,
                                            const uint8_t* qm) {
     const uint32_t tid = threadIdx.x;
     const uint32_t Lq = h.qlen, V = h.V;
-    const uint64_t io = (uint64_t)q * A.icap;
-    const uint32_t* pred_off = A.pred_off + (uint64_t)q * (A.icap + 1);
+    const uint64_t io = (uint64_t)ql * A.icap;
+    const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     const uint32_t* pdesc = A.pdesc + io;
     const float2* spill = A.spill + h.spill_off;
     float2* spill_w = A.spill + h.spill_off;
@@ -45,7 +45,7 @@ __device__ __forceinline__ void mesh_query(const MeshArgs& A, const GraphHdr& h,
     const float gp = A.gp, gpe = A.gpe;
 
     for (uint32_t g = 0; g < h.n_groups; g++) {
-        const GroupInfo gi = A.groups[(uint64_t)q * A.gcap + g];
+        const GroupInfo gi = A.groups[(uint64_t)ql * A.gcap + g];
         const uint32_t m = g * T + tid;
         const bool valid = m < V;
         uint32_t np = 0, pbase = 0, mask = 0;
@@ -168,33 +168,33 @@ __global__ void __launch_bounds__(DP_THREADS, 2) mesh_kernel(MeshArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* ring = reinterpret_cast<float2*>(smem);            // [R][T]
     uint8_t* qm = smem + sizeof(float2) * R * T;                // [Lq]
-    const uint32_t q = blockIdx.x;
+    const uint32_t q = A.q0 + blockIdx.x;
     const GraphHdr h = A.hdr[q];
     if (h.status != GS_OK) return;
     const uint8_t* src = A.qmasks + A.qoff[q];
     for (uint32_t i = threadIdx.x; i < h.qlen; i += blockDim.x) qm[i] = src[i];
     __syncthreads();
-    if (h.wide) mesh_query<true>(A, h, q, ring, qm);
-    else mesh_query<false>(A, h, q, ring, qm);
+    if (h.wide) mesh_query<true>(A, h, blockIdx.x, ring, qm);
+    else mesh_query<false>(A, h, blockIdx.x, ring, qm);
 }
 
-int launch_mesh(Session* s, const sg_align_params& ap) {
+int launch_mesh(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     MeshArgs A;
     A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
-    A.gcap = s->gcap; A.icap = s->icap;
+    A.gcap = s->gcap; A.icap = s->icap; A.q0 = q0;
     A.nmask = s->d_nmask; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.pred_off = s->d_pred_off;
     A.pdesc = s->d_pdesc; A.spillrow = s->d_spillrow; A.nflags = s->d_nflags;
     A.tb = s->d_tb; A.spill = s->d_spill; A.lastcol = s->d_lastcol; A.rowmin = s->d_rowmin; A.rowarg = s->d_rowarg;
     A.ms = -ap.match_score; A.mms = -ap.mismatch_score; A.gp = ap.gap_penalty; A.gpe = ap.gap_ext_penalty;
     uint32_t max_qlen = 0;
-    for (uint32_t i = 0; i < s->nq; i++) {
+    for (uint32_t i = q0; i < q0 + n; i++) {
         uint32_t l = (uint32_t)(s->h_qoff[i + 1] - s->h_qoff[i]);
         if (l > max_qlen) max_qlen = l;
     }
     size_t smem = sizeof(float2) * R * T + ((max_qlen + 15) & ~15u);
     if (smem > 220 * 1024) SG_FAIL(SG_ERR_LIMIT, "query too long for the DP kernel's shared memory");
     SG_CUDA(cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mesh_kernel<<<s->nq, DP_THREADS, smem, s->stream>>>(A);
+    mesh_kernel<<<n, DP_THREADS, smem, s->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

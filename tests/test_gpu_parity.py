@@ -56,7 +56,10 @@ def test_align_golden_cases():
         if e["status"] in (0, 1):
             assert O.render(om[:r["n_out"]], oc[:r["n_out"]], msa.W) == e["aligned"], i
         if e["status"] == 0:
-            assert (r["head"], r["tail"], r["qual"], r["n_nodes"]) == (e["head"], e["tail"], e["qual"], e["n_nodes"]), i
+            assert (r["head"], r["tail"], r["qual"]) == (e["head"], e["tail"], e["qual"]), i
+            if e["fam_used"] == msa.N:  # the golden graph size is that of the whole family
+                assert r["n_nodes"] == e["n_nodes"], i
+            assert r["fam_used"] == e["fam_used"], i
             assert int(bits(r["score"])) == e["score_bits"], i
 
 
@@ -116,10 +119,9 @@ def test_wide_indegree_and_far_edges(orc):
     rows = []
     for j in range(14):
         s = ["-"] * W
-        a = 100 + j
-        gap = 5 + 4 * j
+        gap = 5 + 4 * j  # every row's deletion ends at the same column: the next node collects 14 predecessors
         for i in range(L):
-            if a <= i < a + gap:
+            if 200 - gap <= i < 200:
                 continue
             s[core[i]] = "AGCU"[root[i] if (i % 37 != j) else (root[i] + 1) % 4]
         rows.append("".join(s))
