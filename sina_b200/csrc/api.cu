@@ -35,7 +35,8 @@ static void free_align(Session* s) {
                     s->d_item_node, s->d_slot, s->d_ncol, s->d_nmask, s->d_ncount, s->d_nweight, s->d_nsigma,
                     s->d_slotbase, s->d_cursor, s->d_pred_off, s->d_preds, s->d_pdesc, s->d_spillrow, s->d_nflags,
                     s->d_lastnodes, s->d_groups, s->d_lastcol, s->d_rowmin, s->d_rowarg, s->d_tb, s->d_spill,
-                    s->d_fam_ids, s->d_fam_scores};
+                    s->d_fam_ids, s->d_fam_scores, s->d_pdesc2, s->d_order, s->d_nthr, s->d_nshift, s->d_ghosts,
+                    s->d_writers};
     for (void* p : ptrs) if (p) cudaFree(p);
     s->d_afam = nullptr; s->d_afam_n = nullptr; s->d_contains = nullptr; s->d_copy_src = nullptr; s->d_tab = nullptr;
     s->d_tabli = nullptr; s->d_colof = nullptr; s->d_colbase = nullptr; s->d_item_node = nullptr; s->d_slot = nullptr;
@@ -43,7 +44,8 @@ static void free_align(Session* s) {
     s->d_slotbase = nullptr; s->d_cursor = nullptr; s->d_pred_off = nullptr; s->d_preds = nullptr; s->d_pdesc = nullptr;
     s->d_spillrow = nullptr; s->d_nflags = nullptr; s->d_lastnodes = nullptr; s->d_groups = nullptr;
     s->d_lastcol = nullptr; s->d_rowmin = nullptr; s->d_rowarg = nullptr; s->d_tb = nullptr; s->d_spill = nullptr;
-    s->d_fam_ids = nullptr; s->d_fam_scores = nullptr;
+    s->d_fam_ids = nullptr; s->d_fam_scores = nullptr; s->d_pdesc2 = nullptr; s->d_order = nullptr; s->d_nthr = nullptr;
+    s->d_nshift = nullptr; s->d_ghosts = nullptr; s->d_writers = nullptr;
     s->fam_cap = 0; s->icap = 0;
 }
 
@@ -58,7 +60,7 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     s->fam_cap = fam_cap;
     s->icap = fam_cap * ix->max_row_len;
     s->ncap = ix->W < s->icap ? ix->W : s->icap;
-    s->gcap = s->icap / DP_THREADS + 1;
+    s->gcap = s->icap / DP_T + 1;
     const uint64_t I = s->icap;
     SG_TRY(dmalloc(&s->d_fam_ids, Q * fam_cap)); SG_TRY(dmalloc(&s->d_fam_scores, Q * fam_cap));
     SG_TRY(dmalloc(&s->d_afam, Q * fam_cap)); SG_TRY(dmalloc(&s->d_afam_n, Q));
@@ -73,6 +75,9 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     SG_TRY(dmalloc(&s->d_pdesc, C * I)); SG_TRY(dmalloc(&s->d_spillrow, C * I)); SG_TRY(dmalloc(&s->d_nflags, C * I));
     SG_TRY(dmalloc(&s->d_lastnodes, C * I)); SG_TRY(dmalloc(&s->d_groups, C * s->gcap));
     SG_TRY(dmalloc(&s->d_lastcol, C * I)); SG_TRY(dmalloc(&s->d_rowmin, C * I)); SG_TRY(dmalloc(&s->d_rowarg, C * I));
+    SG_TRY(dmalloc(&s->d_pdesc2, C * I)); SG_TRY(dmalloc(&s->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&s->d_nthr, C * I));
+    SG_TRY(dmalloc(&s->d_nshift, C * I)); SG_TRY(dmalloc(&s->d_ghosts, C * s->gcap * DP_G));
+    SG_TRY(dmalloc(&s->d_writers, C * s->gcap * DP_G));
     // arenas: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
     const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
     uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
@@ -252,6 +257,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     Session* s = new Session;
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
     s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 1024)));
+    s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
     *out = (sg_session*)s;
     SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) SG_CUDA(cudaEventCreate(&e));

@@ -15,7 +15,7 @@ struct BtArgs {
     const uint8_t* qmasks; const uint64_t* qoff;
     GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap; uint32_t* remaining;
     const uint32_t* ncol; const float* nweight; const uint32_t* nsigma; const uint32_t* pred_off;
-    const uint32_t* preds; const uint32_t* lastnodes; const uint32_t* afam_n;
+    const uint32_t* preds; const uint32_t* lastnodes; const uint32_t* afam_n; const uint16_t* nthr; const uint8_t* nshift;
     const uint32_t* tb; const float* lastcol; const float* rowmin; const uint32_t* rowarg;
     const uint32_t* copy_src; const uint8_t* masks; const uint32_t* cols; const uint64_t* row_off;
     uint32_t* out_cols; uint8_t* out_masks; sg_align_result* results;
@@ -127,11 +127,14 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     const uint32_t* tbq = A.tb + h.tb_off;
     const bool wide = h.wide != 0;
     const uint32_t V = h.V, W = A.W;
-    const uint32_t T = DP_THREADS;
+    const uint32_t T = DP_T;
+    const uint16_t* nthr = A.nthr + io;
+    const uint8_t* nshift = A.nshift + io;
+    const bool sorted = h.mode == 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
 
     // decoded traceback cell: src | ord<<8 | chosen_open<<2 | last_open<<3 | ins_open<<4 (the wide layout)
     auto cell = [&](uint32_t m, uint32_t s) -> uint32_t {
-        const uint32_t g = m / T, tid = m - g * T;
+        const uint32_t g = m / T, tid = sorted ? (uint32_t)nthr[m] : m - g * T;
         const GroupInfo gi = groups[g];
         const uint32_t t = s + nsigma[m] - gi.sigma_lo;
         if (wide) {
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     };
     // (value_midx, value_sidx) of cell (m,s)
     auto follow = [&](uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
-        const uint32_t src = c & 3u, ord = c >> 8;
+        const uint32_t src = c & 3u, ord = (c >> 8) - nshift[m];
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
         else if (src == TB_SRC_MATCH) { nm = preds[pred_off[m] + ord]; ns = s - 1; }
         else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(m, s); }
@@ -265,6 +268,7 @@ int launch_backtrack(Session* s, const sg_align_params& ap, uint32_t q0, uint32_
     A.nq = n; A.q0 = q0; A.W = ix->W; A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
     A.gcap = s->gcap; A.icap = s->icap; A.remaining = s->d_retry + 1; A.ncol = s->d_ncol; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma;
     A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.lastnodes = s->d_lastnodes; A.afam_n = s->d_afam_n;
+    A.nthr = s->d_nthr; A.nshift = s->d_nshift;
     A.tb = s->d_tb; A.lastcol = s->d_lastcol; A.rowmin = s->d_rowmin; A.rowarg = s->d_rowarg;
     A.copy_src = s->d_copy_src; A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off;
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;

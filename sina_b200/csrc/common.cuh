@@ -33,8 +33,12 @@ constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts
 constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
-constexpr int DP_THREADS = 512;              // node rows per DP group (one thread each)
+constexpr int DP_BLOCK = 512;                // threads per DP CTA = columns of the shared-memory ring
+constexpr int DP_T = 448;                    // node rows per DP group (compute lanes, one row each)
+constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
 constexpr int DP_RING = 16;                  // ring depth (time slots) of the shared-memory row window
+constexpr int GHOST_LEAD = 3;                // a ghost trails its source row by >= this many column ranks
+constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan can hold
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
 
 // traceback byte / halfword layout (mesh.cu writes, backtrack.cu decodes)
@@ -65,6 +69,7 @@ struct Index {
 struct GraphHdr {
     uint32_t V, E, n_cols, n_groups;
     uint32_t n_last, n_spill, max_indeg, wide;  // wide: traceback uses u16 cells
+    uint32_t mode, pad0;  // DP kernel: 2 = sorted rows + ghost columns (mesh_v2), 1 = generic fallback (mesh_v1)
     uint64_t tb_off;     // offset (in 4-byte words) of this query's traceback in the arena
     uint64_t spill_off;  // offset (in float2) of this query's spill rows in the arena
     uint32_t status;     // 0 ok, else SG_Q_* / internal failure code (see GS_*)
@@ -75,6 +80,11 @@ constexpr uint32_t GS_OK = 0, GS_DONE = 50, GS_ARENA_FULL = 100, GS_LIMIT = 101;
 struct GroupInfo {
     uint32_t sigma_lo, depth;  // first column rank of the group, number of column ranks it spans
     uint64_t tb_off;           // word offset inside the query's traceback block
+    uint32_t n_ghost, n_writer;
+};
+struct GhostInfo {   // a ring column fed from a spilled row: far predecessors become near ones
+    uint32_t spillrow;
+    int32_t soff;    // column rank of the ghost minus the group's sigma_lo (>= -1)
 };
 
 // All per-batch device state. Per-query arrays use a uniform stride (icap items / ncap columns).
@@ -124,7 +134,13 @@ struct Session {
     uint32_t* d_cursor = nullptr;    // [nq][icap]
     uint32_t* d_pred_off = nullptr;  // [nq][icap+1]
     uint32_t* d_preds = nullptr;     // [nq][icap]
-    uint32_t* d_pdesc = nullptr;     // [nq][icap] near/far descriptor per edge
+    uint32_t* d_pdesc = nullptr;     // [nq][icap] near/far descriptor per edge (generic kernel)
+    uint32_t* d_pdesc2 = nullptr;    // [nq][icap] (delta<<16 | ring column) per edge (v2 kernel)
+    uint32_t* d_order = nullptr;     // [nq][gcap*DP_T] node handled by (group, thread) in the v2 kernel
+    uint16_t* d_nthr = nullptr;      // [nq][icap] thread (ring column) of a node inside its group
+    uint8_t* d_nshift = nullptr;     // [nq][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
+    GhostInfo* d_ghosts = nullptr;   // [nq][gcap][DP_G]
+    uint32_t* d_writers = nullptr;   // [nq][gcap][DP_G] node whose row a loader lane spills / min-tracks
     int32_t* d_spillrow = nullptr;   // [nq][icap] spill row of node or -1
     uint8_t* d_nflags = nullptr;     // [nq][icap] bit0 has successor
     uint32_t* d_lastnodes = nullptr; // [nq][icap]
@@ -145,6 +161,7 @@ struct Session {
     cudaEvent_t ev[8] = {};
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
+    int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

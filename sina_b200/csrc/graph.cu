@@ -98,6 +98,7 @@ struct GraphArgs {
     uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
     uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
     uint32_t* lastnodes; GroupInfo* groups;
+    uint32_t* order; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
     unsigned long long* counters; uint64_t tb_words, spill_elems;
     float fs_weight;
 };
@@ -117,7 +118,7 @@ __device__ uint32_t scan_array_inplace(T* arr, uint32_t n, uint32_t* red) {
     return carry;
 }
 
-__global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
+__global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     extern __shared__ uint32_t sm[];
     const uint32_t q = A.q0 + blockIdx.x;  // global query index (hdr, family); workspace uses the local index
     const uint32_t ql = blockIdx.x;
@@ -297,8 +298,8 @@ __global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
     // ---- 6. DP plan. Group g = nodes [g*T, (g+1)*T); a node at column rank sigma runs query position
     // s at step s + sigma - sigma_lo(g). An edge is "near" (served from the shared-memory ring) when both
     // ends are in the same group and at most DP_RING-2 column ranks apart; otherwise the predecessor row
-    // is spilled to global memory.
-    const uint32_t T = DP_THREADS;
+    // is spilled to global memory ("far").
+    const uint32_t T = DP_T;
     const uint32_t n_groups = (V + T - 1) / T;
     if (n_groups > A.gcap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
     for (uint32_t m = tid; m < V; m += nt) {
@@ -325,6 +326,98 @@ __global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
     __syncthreads();
     const uint32_t n_last = scan_array_inplace(cursor, V, red);
     for (uint32_t m = tid; m < V; m += nt) if (!nflags[m]) lastnodes[cursor[m]] = m;
+
+    // ---- 7. plan for the v2 kernel: inside a group rows are sorted by in-degree (warps become uniform),
+    // every far predecessor is served by a "ghost" ring column that a loader lane streams from the spill
+    // buffer, and rows that must be spilled (far successors) or min-tracked (last nodes) get a writer lane.
+    uint32_t* order = A.order + (uint64_t)ql * A.gcap * T;
+    uint16_t* nthr = A.nthr + io;
+    uint32_t* pdesc2 = A.pdesc2 + io;
+    GhostInfo* ghosts = A.ghosts + (uint64_t)ql * A.gcap * DP_G;
+    uint32_t* writers = A.writers + (uint64_t)ql * A.gcap * DP_G;
+    uint32_t* far_e = shv + 8;                   // [FARLIST_CAP] edge index
+    uint32_t* far_gi = far_e + FARLIST_CAP;      // [FARLIST_CAP] ghost index of the edge
+    uint32_t* gh_p = far_gi + FARLIST_CAP;       // [DP_G] ghost source node
+    uint32_t* gh_b = gh_p + DP_G;                // [DP_G] ghost bucket
+    if (tid == 0) shv[1] = 0;                    // overflow flag
+    __syncthreads();
+    for (uint32_t g = 0; g < n_groups; g++) {
+        const uint32_t lo = g * T, n = min(T, V - lo);
+        const uint32_t sigma_lo = nsigma[lo];
+        const bool valid = tid < n;
+        const uint32_t m = lo + tid;
+        uint32_t np = 0;
+        if (valid) np = pred_off[m + 1] - pred_off[m];
+        const uint32_t key = !valid ? 0u : (np == 0 ? 1u : min(np, 5u));
+        uint32_t base = 0;
+        for (uint32_t b = 1; b <= 5; b++) {  // stable counting sort by in-degree class
+            uint32_t tot;
+            const uint32_t ex = block_exscan(key == b ? 1u : 0u, red, &tot);
+            if (key == b) { nthr[m] = (uint16_t)(base + ex); order[(uint64_t)g * T + base + ex] = m; }
+            base += tot;
+        }
+        if (tid >= n && tid < T) order[(uint64_t)g * T + tid] = NONE;
+        if (tid == 0) { shv[2] = 0; shv[3] = 0; }  // far edges, ghosts
+        __syncthreads();
+        if (valid) {
+            const uint32_t sg_ = nsigma[m];
+            for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
+                const uint32_t p = preds[e], d = sg_ - nsigma[p];
+                if (p >= lo && d <= (uint32_t)DP_RING - 2) pdesc2[e] = (d << 16) | nthr[p];
+                else {
+                    const uint32_t i = atomicAdd(&shv[2], 1u);
+                    if (i < FARLIST_CAP) far_e[i] = e; else shv[1] = 1;
+                    pdesc2[e] = m;  // remember the consumer until the ghost is known
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nfar = min(shv[2], FARLIST_CAP);
+        if (tid == 0) {  // ghosts = distinct (source row, 14-rank bucket of the consumer)
+            uint32_t ng = 0;
+            for (uint32_t i = 0; i < nfar; i++) {
+                const uint32_t e = far_e[i], p = preds[e], mm = pdesc2[e];
+                const uint32_t bk = (nsigma[mm] - sigma_lo) / (DP_RING - 2);
+                uint32_t j = 0;
+                while (j < ng && !(gh_p[j] == p && gh_b[j] == bk)) j++;
+                if (j == ng) {
+                    if (ng == DP_G) { shv[1] = 1; j = 0; }
+                    else { gh_p[ng] = p; gh_b[ng] = bk; ng++; }
+                }
+                far_gi[i] = j;
+            }
+            shv[3] = ng;
+        }
+        __syncthreads();
+        const uint32_t ng = shv[3];
+        auto ghost_sigma = [&](uint32_t j) -> int {  // column rank the ghost pretends to sit at
+            int sgm = (int)sigma_lo + (int)(gh_b[j] * (DP_RING - 2)) - 1;
+            if (gh_p[j] >= lo) sgm = max(sgm, (int)nsigma[gh_p[j]] + GHOST_LEAD);  // source still being computed
+            return sgm;
+        };
+        for (uint32_t i = tid; i < nfar; i += nt) {
+            const uint32_t e = far_e[i], mm = pdesc2[e], j = far_gi[i];
+            const uint32_t d = (uint32_t)((int)nsigma[mm] - ghost_sigma(j));
+            pdesc2[e] = (d << 16) | (T + j);
+        }
+        if (tid < ng) {
+            GhostInfo gi;
+            gi.spillrow = (uint32_t)spillrow[gh_p[tid]];
+            gi.soff = ghost_sigma(tid) - (int)sigma_lo;
+            ghosts[(uint64_t)g * DP_G + tid] = gi;
+        }
+        // writer lanes: rows with a far successor (spill) or without successor (end-cell search needs the row min)
+        const uint32_t wflag = valid && (spillrow[m] >= 0 || nflags[m] == 0) ? 1u : 0u;
+        uint32_t nwr;
+        const uint32_t wex = block_exscan(wflag, red, &nwr);
+        if (wflag && wex < DP_G) writers[(uint64_t)g * DP_G + wex] = m;
+        if (tid == 0) {
+            if (nwr > DP_G) shv[1] = 1;
+            groups[g].n_ghost = ng;
+            groups[g].n_writer = min(nwr, (uint32_t)DP_G);
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         uint64_t words_total = 0;
         for (uint32_t g = 0; g < n_groups; g++) {
@@ -333,15 +426,16 @@ __global__ void __launch_bounds__(512) graph_kernel(GraphArgs A) {
             groups[g].sigma_lo = lo;
             groups[g].depth = hi - lo + 1;
             groups[g].tb_off = words_total;
-            const uint32_t steps = Lq + (hi - lo);
+            const uint32_t steps = (Lq + (hi - lo) + 3) & ~3u;  // the v2 kernel runs whole blocks of 4 steps
             const uint32_t per_word = wide ? 2 : 4;
-            words_total += (uint64_t)((steps + per_word - 1) / per_word) * T;
+            words_total += (uint64_t)(steps / per_word) * T;
         }
         const uint64_t spill_need = (uint64_t)n_spill * Lq;
         const uint64_t tb_off = atomicAdd(&A.counters[2], (unsigned long long)words_total);
         const uint64_t sp_off = atomicAdd(&A.counters[3], (unsigned long long)spill_need);
         hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;
         hdr->n_last = n_last; hdr->n_spill = n_spill; hdr->max_indeg = max_indeg; hdr->wide = wide;
+        hdr->mode = (shv[1] || A.force_generic) ? 1u : 2u;
         hdr->tb_off = tb_off; hdr->spill_off = sp_off;
         if (tb_off + words_total > A.tb_words || sp_off + spill_need > A.spill_elems) hdr->status = GS_ARENA_FULL;
         else atomicAdd(&A.counters[1], (unsigned long long)V * Lq);
@@ -374,12 +468,14 @@ int launch_graph(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n)
     A.ncount = s->d_ncount; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.slotbase = s->d_slotbase;
     A.cursor = s->d_cursor; A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.pdesc = s->d_pdesc;
     A.spillrow = s->d_spillrow; A.nflags = s->d_nflags; A.lastnodes = s->d_lastnodes; A.groups = s->d_groups;
+    A.order = s->d_order; A.nthr = s->d_nthr; A.pdesc2 = s->d_pdesc2; A.ghosts = s->d_ghosts; A.writers = s->d_writers;
+    A.force_generic = s->force_generic;
     A.counters = s->d_counters; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;
-    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8) * 4;
+    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G) * 4;
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_kernel<<<n, 512, smem, s->stream>>>(A);
+    graph_kernel<<<n, DP_BLOCK, smem, s->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

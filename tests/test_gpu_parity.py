@@ -87,7 +87,14 @@ def test_graph_matches_oracle(orc):
         ix.close()
 
 
-def test_align_batch_random_vs_oracle(orc):
+@pytest.fixture(params=["v2", "generic"])
+def dp_mode(request, monkeypatch):
+    """run the DP through the specialised kernel (mesh_v2) and through the generic fallback (mesh_v1)"""
+    monkeypatch.setenv("SG_DP_GENERIC", "1" if request.param == "generic" else "0")
+    return request.param
+
+
+def test_align_batch_random_vs_oracle(orc, dp_mode):
     """one MSA, many queries with different families in one batch (different graph sizes per CTA)"""
     rng = np.random.default_rng(7)
     tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
@@ -109,7 +116,7 @@ def test_align_batch_random_vs_oracle(orc):
     ix.close()
 
 
-def test_wide_indegree_and_far_edges(orc):
+def test_wide_indegree_and_far_edges(orc, dp_mode):
     """in-degree > 8 switches the traceback to 16-bit cells; long gaps force predecessor rows through the
     global spill path (column-rank distance > ring depth); Lq > W hits the reference's runtime_error."""
     rng = np.random.default_rng(3)
@@ -222,7 +229,7 @@ def test_pipeline_golden():
     ix.close()
 
 
-def test_full_size_queries_vs_oracle(orc):
+def test_full_size_queries_vs_oracle(orc, dp_mode):
     """full-length (~1500 nt) and V4 (~250 nt) queries against 40-member families on a 50 000-column MSA:
     multi-group graphs (V ~ 3000), default parameters, whole path through sg_run_batch."""
     tree, m, c, o = synth.synth_msa(3000, W=50000, L=1500, seed=20260117)
