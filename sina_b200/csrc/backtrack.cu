@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     };
     // (value_midx, value_sidx) of cell (m,s)
     auto follow = [&](uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
-        const uint32_t src = c & 3u, ord = (c >> 8) - nshift[m];
+        const uint32_t src = c & 3u, sl = c >> 8, sh = nshift[m];
+        const uint32_t ord = sl > sh ? sl - sh : 0u;  // v2 slots are right-aligned, leading slots repeat ordinal 0
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
         else if (src == TB_SRC_MATCH) { nm = preds[pred_off[m] + ord]; ns = s - 1; }
         else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(m, s); }

@@ -37,7 +37,7 @@ constexpr int DP_BLOCK = 512;                // threads per DP CTA = columns of 
 constexpr int DP_T = 448;                    // node rows per DP group (compute lanes, one row each)
 constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
 constexpr int DP_RING = 16;                  // ring depth (time slots) of the shared-memory row window
-constexpr int GHOST_LEAD = 3;                // a ghost trails its source row by >= this many column ranks
+constexpr int GHOST_LEAD = 6;                // a ghost trails its source row by >= this many column ranks (prefetch 4 + 2)
 constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan can hold
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
 

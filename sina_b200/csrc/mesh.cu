@@ -39,7 +39,8 @@ struct MeshArgs {
 constexpr int T = DP_T;        // rows per group
 constexpr int S = DP_BLOCK;    // ring columns (= CTA threads)
 constexpr int R = DP_RING;
-constexpr int NPR = 4;         // predecessors held in registers
+constexpr int NPR = 4;         // predecessors held in registers (generic kernel)
+constexpr int NPF = 8;         // largest in-degree the specialised v2 step is instantiated for
 constexpr int QPAD = 512;      // padding either side of the query in shared memory (s runs out of range)
 constexpr uint32_t RING_BYTES = sizeof(float2) * R * S;
 
@@ -50,12 +51,15 @@ __device__ __forceinline__ float2 lds_f2(uint32_t byte_off, const unsigned char*
     return *reinterpret_cast<const float2*>(smem + byte_off);
 }
 
-// One group for the lanes of a warp whose rows all have <= NPW predecessors (slots are right-aligned: a row
-// with np < NPW gets NPW-np leading dummy slots that read (inf, inf) and can never win or leave a trace).
+// One group for the lanes of a warp whose rows all have <= NPW predecessors. Slots are right-aligned: a row
+// with np < NPW repeats its first predecessor in the NPW-np leading slots (a repeated candidate ties with
+// its first copy and strict '<' keeps the first, so nothing changes; backtrack maps slot -> ordinal with
+// max(0, slot - shift)). Rows without predecessor get dgp = dgpe = msw = mmsw = +inf so that no deletion or
+// match candidate can win, and has_real = false keeps gapm_val at its edge value.
 template <int NPW, bool WIDE>
 __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qm, uint32_t Lq,
-                                              uint32_t steps4, const uint32_t* ck, const uint32_t* mk,
-                                              const uint32_t* hk, int soff, float initv, bool has_real, uint32_t mask,
+                                              uint32_t steps4, const uint32_t* ck, float dgp, float dgpe, int soff,
+                                              float initv, bool has_real, uint32_t mask,
                                               float msw, float mmsw, float* lastcol_ptr, uint32_t* tbg) {
     const float gp = A.gp, gpe = A.gpe;
     const float INF = __int_as_float(0x7f800000);
@@ -81,11 +85,11 @@ __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* 
             // ---- deletion over predecessor slots, ascending id (mesh.h:475-478 -> 305-330)
 #pragma unroll
             for (int k = 0; k < NPW; k++) {
-                const uint32_t a = ((x + ck[k]) & mk[k]) | hk[k];
+                const uint32_t a = (x + ck[k]) & RMASK;
                 const float2 c = lds_f2(a, smem);
                 cur[k] = c.x;
-                const float v = __fadd_rn(c.x, gp);
-                const float gv = __fadd_rn(c.y, gpe);
+                const float v = __fadd_rn(c.x, dgp);
+                const float gv = __fadd_rn(c.y, dgpe);
                 open = v < gv;
                 gm = open ? v : gv;                               // last predecessor wins
                 const bool win = gm < value;
@@ -231,27 +235,37 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
         if (is_ghost && col >= 0 && col < (int)Lq) return __ldcg(&gsrc[col]);
         return make_float2(0.f, 0.f);
     };
-    // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0)
-    float2 cur = gload(-1);
-    float2 nxt = gload(0);
-    if (is_ghost) ring[((uint32_t)(-1) & (R - 1)) * S + threadIdx.x] = cur;
-    __syncthreads();
-    for (uint32_t t = 0; t <= steps4; t++) {
-        if (t < steps4) {
-            cur = nxt;
-            nxt = gload((int)t + 1);
-            if (is_ghost) ring[(t & (R - 1)) * S + threadIdx.x] = cur;
-        }
-        if (is_writer && t >= 1) {  // drain what the row published at step t-1
-            const int sw = (int)t - 1 - wsoff;
-            if (sw >= 0 && sw < (int)Lq) {
-                const float2 c = ring[((t - 1) & (R - 1)) * S + wcol];
-                if (wsr >= 0) __stcg(&spill[(uint64_t)wsr * Lq + sw], c);
-                if (wlast && (sw == 0 || c.x < rmin)) { rmin = c.x; rarg = (uint32_t)sw; }
-            }
-        }
-        if (t < steps4) __syncthreads();
+    // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0); afterwards the
+    // data of step t+4 is requested at step t, so the L2 latency never sits between two barriers
+    // (GHOST_LEAD = 4 + 2 keeps that request behind the source row's spill store).
+    float2 pf[4];
+    {
+        const float2 c = gload(-1);
+        if (is_ghost) ring[((uint32_t)(-1) & (R - 1)) * S + threadIdx.x] = c;
     }
+#pragma unroll
+    for (int k = 0; k < 4; k++) pf[k] = gload(k);
+    __syncthreads();
+    auto drain = [&](uint32_t t) {  // what the writer's row published at step t-1
+        const int sw = (int)t - 1 - wsoff;
+        if (is_writer && sw >= 0 && sw < (int)Lq) {
+            const float2 c = ring[((t - 1) & (R - 1)) * S + wcol];
+            if (wsr >= 0) __stcg(&spill[(uint64_t)wsr * Lq + sw], c);
+            if (wlast && (sw == 0 || c.x < rmin)) { rmin = c.x; rarg = (uint32_t)sw; }
+        }
+    };
+    for (uint32_t t0 = 0; t0 < steps4; t0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t t = t0 + u;
+            const float2 c = pf[u];
+            pf[u] = gload((int)t + 4);
+            if (is_ghost) ring[(t & (R - 1)) * S + threadIdx.x] = c;
+            if (t >= 1) drain(t);
+            __syncthreads();
+        }
+    }
+    drain(steps4);
     if (is_writer && wlast) { A.rowmin[io + wnode] = rmin; A.rowarg[io + wnode] = rarg; }
 }
 
@@ -265,7 +279,6 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
     const uint32_t* pdesc2 = A.pdesc2 + io;
     uint32_t* tbq = A.tb + h.tb_off;
     const uint32_t RMASK = RING_BYTES - 1;
-    const uint32_t DUMMY = RING_BYTES;  // byte offset of the (inf, inf) cell right behind the ring
 
     for (uint32_t g = 0; g < h.n_groups; g++) {
         const GroupInfo gi = A.groups[(uint64_t)ql * A.gcap + g];
@@ -296,24 +309,29 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
             const float initv = np == 0 ? 1.0f : 1000000.0f;
             uint32_t* tbg = tbq + gi.tb_off + tid;
             __syncthreads();  // matches the loader's prologue barrier
-            if (npw <= (uint32_t)NPR) {
-                uint32_t ck[NPR], mk[NPR], hk[NPR];
+            if (npw <= (uint32_t)NPF) {
+                uint32_t ck[NPF];
+                const uint32_t shift = npw - np;
 #pragma unroll
-                for (int k = 0; k < NPR; k++) {
-                    const int ord = k - (int)(npw - np);          // predecessor ordinal of slot k (this lane)
-                    if (valid && k < (int)npw && ord >= 0) {
+                for (int k = 0; k < NPF; k++) {
+                    ck[k] = tid * 8u;  // rows without predecessor: any valid cell, its candidates are +inf
+                    if (np > 0 && k < (int)npw) {
+                        const uint32_t ord = (uint32_t)k > shift ? (uint32_t)k - shift : 0u;
                         const uint32_t d = pdesc2[pbase + ord];
                         // slot (t - delta) & 15, column c  ->  byte ((t - delta)*S + c)*8, wrapped by RMASK
                         ck[k] = ((d & 0xffffu) * 8u - (d >> 16) * (S * 8u)) & RMASK;
-                        mk[k] = RMASK; hk[k] = 0;
-                    } else { ck[k] = 0; mk[k] = 0; hk[k] = DUMMY; }
+                    }
                 }
+                const float INF = __int_as_float(0x7f800000);
+                const bool hr = np > 0;
+                const float dgp = hr ? A.gp : INF, dgpe = hr ? A.gpe : INF;
+                if (!hr) { msw = INF; mmsw = INF; }
+#define V2_CASE(N) case N: v2_fast_group<N, WIDE>(A, smem, qm, Lq, steps4, ck, dgp, dgpe, soff, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
                 switch (npw) {
-                    case 1: v2_fast_group<1, WIDE>(A, smem, qm, Lq, steps4, ck, mk, hk, soff, initv, np > 0, mask, msw, mmsw, lastcol_ptr, tbg); break;
-                    case 2: v2_fast_group<2, WIDE>(A, smem, qm, Lq, steps4, ck, mk, hk, soff, initv, np > 0, mask, msw, mmsw, lastcol_ptr, tbg); break;
-                    case 3: v2_fast_group<3, WIDE>(A, smem, qm, Lq, steps4, ck, mk, hk, soff, initv, np > 0, mask, msw, mmsw, lastcol_ptr, tbg); break;
-                    default: v2_fast_group<4, WIDE>(A, smem, qm, Lq, steps4, ck, mk, hk, soff, initv, np > 0, mask, msw, mmsw, lastcol_ptr, tbg); break;
+                    V2_CASE(1) V2_CASE(2) V2_CASE(3) V2_CASE(4) V2_CASE(5) V2_CASE(6) V2_CASE(7)
+                    default: v2_fast_group<8, WIDE>(A, smem, qm, Lq, steps4, ck, dgp, dgpe, soff, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
                 }
+#undef V2_CASE
             } else {
                 v2_generic_group<WIDE>(A, smem, qm, Lq, steps4, npw, np, pdesc2 + pbase, soff,
                                        initv, mask, msw, mmsw, lastcol_ptr, tbg);
@@ -334,8 +352,8 @@ __global__ void __launch_bounds__(DP_BLOCK, 2) mesh_v2_kernel(MeshArgs A) {
         const int s = (int)i - QPAD;
         qm[s] = (s >= 0 && s < (int)h.qlen) ? (src[s] & 15u) : 0;
     }
-    if (threadIdx.x == 0)
-        *reinterpret_cast<float2*>(smem + RING_BYTES) = make_float2(__int_as_float(0x7f800000), __int_as_float(0x7f800000));
+    for (uint32_t i = threadIdx.x; i < RING_BYTES / 8; i += blockDim.x)  // no NaN bit patterns in unwritten cells
+        reinterpret_cast<float2*>(smem)[i] = make_float2(0.f, 0.f);
     __syncthreads();
     if (h.wide) v2_query<true>(A, h, blockIdx.x, smem, qm);
     else v2_query<false>(A, h, blockIdx.x, smem, qm);
