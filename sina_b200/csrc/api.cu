@@ -30,23 +30,52 @@ static uint64_t env_mb(const char* name, uint64_t dflt_mb) {
     return strtoull(v, nullptr, 10);
 }
 
-static void free_align(Session* s) {
-    void* ptrs[] = {s->d_afam, s->d_afam_n, s->d_contains, s->d_copy_src, s->d_tab, s->d_tabli, s->d_colof, s->d_colbase,
-                    s->d_item_node, s->d_slot, s->d_ncol, s->d_nmask, s->d_ncount, s->d_nweight, s->d_nsigma,
-                    s->d_slotbase, s->d_cursor, s->d_pred_off, s->d_preds, s->d_pdesc, s->d_spillrow, s->d_nflags,
-                    s->d_lastnodes, s->d_groups, s->d_lastcol, s->d_rowmin, s->d_rowarg, s->d_tb, s->d_spill,
-                    s->d_fam_ids, s->d_fam_scores, s->d_pdesc2, s->d_order, s->d_nthr, s->d_nshift, s->d_ghosts,
-                    s->d_writers};
+static void free_workspace(Workspace* w) {
+    void* ptrs[] = {w->d_cursors, w->d_remaining, w->d_tab, w->d_tabli, w->d_colof, w->d_colbase, w->d_item_node, w->d_slot,
+                    w->d_ncol, w->d_nmask, w->d_ncount, w->d_nweight, w->d_nsigma, w->d_slotbase, w->d_cursor,
+                    w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_nthr, w->d_nshift, w->d_ghosts,
+                    w->d_writers, w->d_spillrow, w->d_nflags, w->d_lastnodes, w->d_groups, w->d_lastcol, w->d_rowmin,
+                    w->d_rowarg, w->d_tb, w->d_spill};
     for (void* p : ptrs) if (p) cudaFree(p);
-    s->d_afam = nullptr; s->d_afam_n = nullptr; s->d_contains = nullptr; s->d_copy_src = nullptr; s->d_tab = nullptr;
-    s->d_tabli = nullptr; s->d_colof = nullptr; s->d_colbase = nullptr; s->d_item_node = nullptr; s->d_slot = nullptr;
-    s->d_ncol = nullptr; s->d_nmask = nullptr; s->d_ncount = nullptr; s->d_nweight = nullptr; s->d_nsigma = nullptr;
-    s->d_slotbase = nullptr; s->d_cursor = nullptr; s->d_pred_off = nullptr; s->d_preds = nullptr; s->d_pdesc = nullptr;
-    s->d_spillrow = nullptr; s->d_nflags = nullptr; s->d_lastnodes = nullptr; s->d_groups = nullptr;
-    s->d_lastcol = nullptr; s->d_rowmin = nullptr; s->d_rowarg = nullptr; s->d_tb = nullptr; s->d_spill = nullptr;
-    s->d_fam_ids = nullptr; s->d_fam_scores = nullptr; s->d_pdesc2 = nullptr; s->d_order = nullptr; s->d_nthr = nullptr;
-    s->d_nshift = nullptr; s->d_ghosts = nullptr; s->d_writers = nullptr;
+    if (w->h_remaining) cudaFreeHost(w->h_remaining);
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->done) cudaEventDestroy(w->done);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    *w = Workspace{};
+}
+
+static void free_align(Session* s) {
+    for (int i = 0; i < MAX_WS; i++) free_workspace(&s->ws[i]);
+    s->n_ws = 0;
+    void* ptrs[] = {s->d_afam, s->d_afam_n, s->d_contains, s->d_copy_src, s->d_fam_ids, s->d_fam_scores};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s->d_afam = nullptr; s->d_afam_n = nullptr; s->d_contains = nullptr; s->d_copy_src = nullptr;
+    s->d_fam_ids = nullptr; s->d_fam_scores = nullptr;
     s->fam_cap = 0; s->icap = 0;
+}
+
+static int alloc_workspace(Session* s, Workspace* w) {
+    const uint64_t C = s->chunk, I = s->icap;
+    SG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    for (auto& e : w->ev) SG_CUDA(cudaEventCreate(&e));
+    SG_CUDA(cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming));
+    SG_CUDA(cudaHostAlloc((void**)&w->h_remaining, sizeof(uint32_t), cudaHostAllocDefault));
+    SG_TRY(dmalloc(&w->d_cursors, 2)); SG_TRY(dmalloc(&w->d_remaining, 1));
+    SG_TRY(dmalloc(&w->d_tab, C * s->ncap * s->fam_cap)); SG_TRY(dmalloc(&w->d_tabli, C * s->ncap * s->fam_cap));
+    SG_TRY(dmalloc(&w->d_colof, C * s->ncap)); SG_TRY(dmalloc(&w->d_colbase, C * (s->ncap + 1)));
+    SG_TRY(dmalloc(&w->d_item_node, C * I)); SG_TRY(dmalloc(&w->d_slot, C * I));
+    SG_TRY(dmalloc(&w->d_ncol, C * I)); SG_TRY(dmalloc(&w->d_nmask, C * I)); SG_TRY(dmalloc(&w->d_ncount, C * I));
+    SG_TRY(dmalloc(&w->d_nweight, C * I)); SG_TRY(dmalloc(&w->d_nsigma, C * I));
+    SG_TRY(dmalloc(&w->d_slotbase, C * (I + 1))); SG_TRY(dmalloc(&w->d_cursor, C * I));
+    SG_TRY(dmalloc(&w->d_pred_off, C * (I + 1))); SG_TRY(dmalloc(&w->d_preds, C * I));
+    SG_TRY(dmalloc(&w->d_pdesc, C * I)); SG_TRY(dmalloc(&w->d_spillrow, C * I)); SG_TRY(dmalloc(&w->d_nflags, C * I));
+    SG_TRY(dmalloc(&w->d_lastnodes, C * I)); SG_TRY(dmalloc(&w->d_groups, C * s->gcap));
+    SG_TRY(dmalloc(&w->d_lastcol, C * I)); SG_TRY(dmalloc(&w->d_rowmin, C * I)); SG_TRY(dmalloc(&w->d_rowarg, C * I));
+    SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
+    SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
+    SG_TRY(dmalloc(&w->d_writers, C * s->gcap * DP_G));
+    SG_TRY(dmalloc(&w->d_tb, s->tb_words)); SG_TRY(dmalloc(&w->d_spill, s->spill_elems));
+    return SG_OK;
 }
 
 // (re)allocate everything whose size depends on the family capacity
@@ -61,30 +90,23 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     s->icap = fam_cap * ix->max_row_len;
     s->ncap = ix->W < s->icap ? ix->W : s->icap;
     s->gcap = s->icap / DP_T + 1;
-    const uint64_t I = s->icap;
     SG_TRY(dmalloc(&s->d_fam_ids, Q * fam_cap)); SG_TRY(dmalloc(&s->d_fam_scores, Q * fam_cap));
     SG_TRY(dmalloc(&s->d_afam, Q * fam_cap)); SG_TRY(dmalloc(&s->d_afam_n, Q));
     SG_TRY(dmalloc(&s->d_contains, Q * fam_cap)); SG_TRY(dmalloc(&s->d_copy_src, Q * 2));
-    SG_TRY(dmalloc(&s->d_tab, C * s->ncap * fam_cap)); SG_TRY(dmalloc(&s->d_tabli, C * s->ncap * fam_cap));
-    SG_TRY(dmalloc(&s->d_colof, C * s->ncap)); SG_TRY(dmalloc(&s->d_colbase, C * (s->ncap + 1)));
-    SG_TRY(dmalloc(&s->d_item_node, C * I)); SG_TRY(dmalloc(&s->d_slot, C * I));
-    SG_TRY(dmalloc(&s->d_ncol, C * I)); SG_TRY(dmalloc(&s->d_nmask, C * I)); SG_TRY(dmalloc(&s->d_ncount, C * I));
-    SG_TRY(dmalloc(&s->d_nweight, C * I)); SG_TRY(dmalloc(&s->d_nsigma, C * I));
-    SG_TRY(dmalloc(&s->d_slotbase, C * (I + 1))); SG_TRY(dmalloc(&s->d_cursor, C * I));
-    SG_TRY(dmalloc(&s->d_pred_off, C * (I + 1))); SG_TRY(dmalloc(&s->d_preds, C * I));
-    SG_TRY(dmalloc(&s->d_pdesc, C * I)); SG_TRY(dmalloc(&s->d_spillrow, C * I)); SG_TRY(dmalloc(&s->d_nflags, C * I));
-    SG_TRY(dmalloc(&s->d_lastnodes, C * I)); SG_TRY(dmalloc(&s->d_groups, C * s->gcap));
-    SG_TRY(dmalloc(&s->d_lastcol, C * I)); SG_TRY(dmalloc(&s->d_rowmin, C * I)); SG_TRY(dmalloc(&s->d_rowarg, C * I));
-    SG_TRY(dmalloc(&s->d_pdesc2, C * I)); SG_TRY(dmalloc(&s->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&s->d_nthr, C * I));
-    SG_TRY(dmalloc(&s->d_nshift, C * I)); SG_TRY(dmalloc(&s->d_ghosts, C * s->gcap * DP_G));
-    SG_TRY(dmalloc(&s->d_writers, C * s->gcap * DP_G));
-    // arenas: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
+    // arenas per workspace: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
     const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
     uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
     uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (256 * max_qlen_guess * 8 / 1000000 + 1))));
     s->tb_words = tb_mb * 1024 * 1024 / 4;
     s->spill_elems = sp_mb * 1024 * 1024 / 8;
-    SG_TRY(dmalloc(&s->d_tb, s->tb_words)); SG_TRY(dmalloc(&s->d_spill, s->spill_elems));
+    // one workspace when the batch is a single chunk, else SG_STREAMS (default 2) so that chunks overlap
+    const uint64_t n_chunks = (Q + C - 1) / C;
+    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 2)), MAX_WS);
+    if ((uint64_t)want > n_chunks) want = (int)n_chunks;
+    for (int i = 0; i < want; i++) {
+        SG_TRY(alloc_workspace(s, &s->ws[i]));
+        s->n_ws = i + 1;
+    }
     return SG_OK;
 }
 
@@ -373,6 +395,44 @@ int sg_session_set_family(sg_session* h, const uint32_t* fam_ids, const uint64_t
     return SG_OK;
 }
 
+// Retire the chunk in flight on a workspace: wait for it, add its stage times, and if some of its queries
+// did not fit the traceback/spill arenas re-run those (arenas reset) until none is left.
+static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap);
+
+static int enqueue_chunk(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
+    w->q0 = q0; w->n = n; w->busy = true;
+    SG_CUDA(cudaMemsetAsync(w->d_cursors, 0, 16, w->stream));  // arena cursors
+    SG_CUDA(cudaMemsetAsync(w->d_remaining, 0, 4, w->stream));
+    SG_CUDA(cudaEventRecord(w->ev[0], w->stream));
+    SG_TRY(launch_graph(s, w, ap, q0, n));
+    SG_CUDA(cudaEventRecord(w->ev[1], w->stream));
+    SG_TRY(launch_mesh(s, w, ap, q0, n));
+    SG_CUDA(cudaEventRecord(w->ev[2], w->stream));
+    SG_TRY(launch_backtrack(s, w, ap, q0, n));
+    SG_CUDA(cudaEventRecord(w->ev[3], w->stream));
+    SG_CUDA(cudaMemcpyAsync(w->h_remaining, w->d_remaining, 4, cudaMemcpyDeviceToHost, w->stream));
+    SG_CUDA(cudaEventRecord(w->done, w->stream));
+    return SG_OK;
+}
+
+static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
+    while (w->busy) {
+        SG_CUDA(cudaEventSynchronize(w->done));
+        float ms = 0.f;
+        SG_CUDA(cudaEventElapsedTime(&ms, w->ev[0], w->ev[1])); s->stats.ms_graph += ms;
+        SG_CUDA(cudaEventElapsedTime(&ms, w->ev[1], w->ev[2])); s->stats.ms_dp += ms;
+        SG_CUDA(cudaEventElapsedTime(&ms, w->ev[2], w->ev[3])); s->stats.ms_backtrack += ms;
+        w->busy = false;
+        const uint32_t remaining = *w->h_remaining;
+        if (remaining == 0) { w->prev_remaining = 0xffffffffu; break; }
+        if (remaining >= w->prev_remaining)
+            SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
+        w->prev_remaining = remaining;
+        SG_TRY(enqueue_chunk(s, w, ap, w->q0, w->n));  // finished queries are skipped (GS_DONE), the rest redone
+    }
+    return SG_OK;
+}
+
 int sg_session_align(sg_session* h, const sg_align_params* ap) {
     Session* s = (Session*)h;
     if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_align: no queries uploaded");
@@ -381,31 +441,14 @@ int sg_session_align(sg_session* h, const sg_align_params* ap) {
     SG_CUDA(cudaSetDevice(s->ix->device));
     SG_TRY(stage_begin(s, 2));
     SG_TRY(launch_prealign(s, *ap));
-    SG_TRY(stage_end(s, &s->stats.ms_graph));
-    for (uint32_t q0 = 0; q0 < s->nq; q0 += s->chunk) {
-        const uint32_t n = std::min(s->chunk, s->nq - q0);
-        uint32_t prev_remaining = 0xffffffffu;
-        for (;;) {  // passes: queries that did not fit the traceback/spill arenas are redone with the arenas reset
-            SG_CUDA(cudaMemsetAsync(s->d_counters + 2, 0, 16, s->stream));  // arena cursors
-            SG_CUDA(cudaMemsetAsync(s->d_retry + 1, 0, 4, s->stream));
-            SG_TRY(stage_begin(s, 2));
-            SG_TRY(launch_graph(s, *ap, q0, n));
-            SG_TRY(stage_end(s, &s->stats.ms_graph));
-            SG_TRY(stage_begin(s, 3));
-            SG_TRY(launch_mesh(s, *ap, q0, n));
-            SG_TRY(stage_end(s, &s->stats.ms_dp));
-            SG_TRY(stage_begin(s, 4));
-            SG_TRY(launch_backtrack(s, *ap, q0, n));
-            SG_TRY(stage_end(s, &s->stats.ms_backtrack));
-            uint32_t remaining = 0;
-            SG_CUDA(cudaMemcpyAsync(&remaining, s->d_retry + 1, 4, cudaMemcpyDeviceToHost, s->stream));
-            SG_CUDA(cudaStreamSynchronize(s->stream));
-            if (remaining == 0) break;
-            if (remaining >= prev_remaining)
-                SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
-            prev_remaining = remaining;
-        }
+    SG_TRY(stage_end(s, &s->stats.ms_graph));   // synchronises: the workspace streams may start
+    int k = 0;
+    for (uint32_t q0 = 0; q0 < s->nq; q0 += s->chunk, k++) {
+        Workspace* w = &s->ws[k % s->n_ws];
+        SG_TRY(retire_chunk(s, w, *ap));
+        SG_TRY(enqueue_chunk(s, w, *ap, q0, std::min(s->chunk, s->nq - q0)));
     }
+    for (int i = 0; i < s->n_ws; i++) SG_TRY(retire_chunk(s, &s->ws[i], *ap));
     unsigned long long cnt[2];
     SG_CUDA(cudaMemcpyAsync(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost, s->stream));
     SG_CUDA(cudaStreamSynchronize(s->stream));
@@ -500,12 +543,16 @@ int sg_session_dump_graph(sg_session* h, uint32_t q, uint32_t cap_nodes, uint32_
     if (V) *V = hd.V;
     if (E) *E = hd.E;
     if (hd.V > cap_nodes || hd.E > cap_edges) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: capacity too small");
-    const uint64_t io = (uint64_t)q * s->icap;
-    if (col) SG_CUDA(cudaMemcpy(col, s->d_ncol + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
-    if (mask) SG_CUDA(cudaMemcpy(mask, s->d_nmask + io, hd.V, cudaMemcpyDeviceToHost));
-    if (weight) SG_CUDA(cudaMemcpy(weight, s->d_nweight + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
-    if (pred_off) SG_CUDA(cudaMemcpy(pred_off, s->d_pred_off + (uint64_t)q * (s->icap + 1), ((uint64_t)hd.V + 1) * 4, cudaMemcpyDeviceToHost));
-    if (preds) SG_CUDA(cudaMemcpy(preds, s->d_preds + io, (uint64_t)hd.E * 4, cudaMemcpyDeviceToHost));
+    // the workspace that handled q's chunk; its arrays are only still there if no later chunk reused it
+    const uint32_t c = q / s->chunk, n_chunks = (s->nq + s->chunk - 1) / s->chunk;
+    if (c + (uint32_t)s->n_ws < n_chunks) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: the query's workspace has been reused");
+    const Workspace* w = &s->ws[c % s->n_ws];
+    const uint64_t ql = q - c * s->chunk, io = ql * s->icap;
+    if (col) SG_CUDA(cudaMemcpy(col, w->d_ncol + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
+    if (mask) SG_CUDA(cudaMemcpy(mask, w->d_nmask + io, hd.V, cudaMemcpyDeviceToHost));
+    if (weight) SG_CUDA(cudaMemcpy(weight, w->d_nweight + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
+    if (pred_off) SG_CUDA(cudaMemcpy(pred_off, w->d_pred_off + ql * (s->icap + 1), ((uint64_t)hd.V + 1) * 4, cudaMemcpyDeviceToHost));
+    if (preds) SG_CUDA(cudaMemcpy(preds, w->d_preds + io, (uint64_t)hd.E * 4, cudaMemcpyDeviceToHost));
     return SG_OK;
 }
 

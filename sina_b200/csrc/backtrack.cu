@@ -263,18 +263,18 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     A.hdr[q].status = GS_DONE;
 }
 
-int launch_backtrack(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
+int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
     BtArgs A;
-    A.nq = n; A.q0 = q0; A.W = ix->W; A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
-    A.gcap = s->gcap; A.icap = s->icap; A.remaining = s->d_retry + 1; A.ncol = s->d_ncol; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma;
-    A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.lastnodes = s->d_lastnodes; A.afam_n = s->d_afam_n;
-    A.nthr = s->d_nthr; A.nshift = s->d_nshift;
-    A.tb = s->d_tb; A.lastcol = s->d_lastcol; A.rowmin = s->d_rowmin; A.rowarg = s->d_rowarg;
+    A.nq = n; A.q0 = q0; A.W = ix->W; A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = w->d_groups;
+    A.gcap = s->gcap; A.icap = s->icap; A.remaining = w->d_remaining; A.ncol = w->d_ncol; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma;
+    A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.lastnodes = w->d_lastnodes; A.afam_n = s->d_afam_n;
+    A.nthr = w->d_nthr; A.nshift = w->d_nshift;
+    A.tb = w->d_tb; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.copy_src = s->d_copy_src; A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off;
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;
     A.ms = -ap.match_score; A.overhang = ap.overhang; A.lowercase = ap.lowercase;
-    backtrack_kernel<<<(n + 63) / 64, 64, 0, s->stream>>>(A);
+    backtrack_kernel<<<(n + 63) / 64, 64, 0, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

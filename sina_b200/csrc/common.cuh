@@ -87,12 +87,60 @@ struct GhostInfo {   // a ring column fed from a spilled row: far predecessors b
     int32_t soff;    // column rank of the ghost minus the group's sigma_lo (>= -1)
 };
 
-// All per-batch device state. Per-query arrays use a uniform stride (icap items / ncap columns).
+// Chunk-local device workspace of the aligner stage (graph arrays, DP plan, traceback/spill arenas). A
+// session owns several and deals the batch's chunks to them round-robin; each workspace has its own stream,
+// so the graph kernel of one chunk, the DP of another and the (latency-bound) backtrack of a third overlap.
+// Per-query arrays use a uniform stride (icap items / ncap columns).
+constexpr int MAX_WS = 4;
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {};          // stage boundaries: graph | dp | backtrack | end
+    cudaEvent_t done = nullptr;
+    bool busy = false;               // a chunk is in flight (retire() has not run yet)
+    uint32_t q0 = 0, n = 0;          // the chunk in flight
+    uint32_t prev_remaining = 0xffffffffu;
+    unsigned long long* d_cursors = nullptr;  // [0] traceback arena cursor, [1] spill arena cursor
+    uint32_t* d_remaining = nullptr; // queries of the chunk that did not fit the arenas in this pass
+    uint32_t* h_remaining = nullptr; // pinned host copy
+    uint8_t* d_tab = nullptr;        // [n][ncap][fam_cap] base mask of family row j at column rank c
+    uint8_t* d_tabli = nullptr;      // [n][ncap][fam_cap] local node index in that column
+    uint32_t* d_colof = nullptr;     // [n][ncap] column of rank c
+    uint32_t* d_colbase = nullptr;   // [n][ncap+1] first node id of column rank c
+    uint32_t* d_item_node = nullptr; // [n][icap]
+    uint32_t* d_slot = nullptr;      // [n][icap] predecessor candidates grouped by node
+    uint32_t* d_ncol = nullptr;      // [n][icap] node column
+    uint8_t* d_nmask = nullptr;      // [n][icap]
+    uint16_t* d_ncount = nullptr;    // [n][icap] family rows through the node
+    float* d_nweight = nullptr;      // [n][icap]
+    uint32_t* d_nsigma = nullptr;    // [n][icap] column rank
+    uint32_t* d_slotbase = nullptr;  // [n][icap+1]
+    uint32_t* d_cursor = nullptr;    // [n][icap]
+    uint32_t* d_pred_off = nullptr;  // [n][icap+1]
+    uint32_t* d_preds = nullptr;     // [n][icap]
+    uint32_t* d_pdesc = nullptr;     // [n][icap] near/far descriptor per edge (generic kernel)
+    uint32_t* d_pdesc2 = nullptr;    // [n][icap] (delta<<16 | ring column) per edge (v2 kernel)
+    uint32_t* d_order = nullptr;     // [n][gcap*DP_T] node handled by (group, thread) in the v2 kernel
+    uint16_t* d_nthr = nullptr;      // [n][icap] thread (ring column) of a node inside its group
+    uint8_t* d_nshift = nullptr;     // [n][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
+    GhostInfo* d_ghosts = nullptr;   // [n][gcap][DP_G]
+    uint32_t* d_writers = nullptr;   // [n][gcap][DP_G] node whose row a loader lane spills / min-tracks
+    int32_t* d_spillrow = nullptr;   // [n][icap] spill row of node or -1
+    uint8_t* d_nflags = nullptr;     // [n][icap] bit0 has successor
+    uint32_t* d_lastnodes = nullptr; // [n][icap]
+    GroupInfo* d_groups = nullptr;   // [n][gcap]
+    float* d_lastcol = nullptr;      // [n][icap] value(m, Lq-1)
+    float* d_rowmin = nullptr;       // [n][icap] min over s of value(m, s) (last nodes only)
+    uint32_t* d_rowarg = nullptr;    // [n][icap] first s reaching it
+    uint32_t* d_tb = nullptr;        // traceback arena (words)
+    float2* d_spill = nullptr;       // spill arena
+};
+
+// All per-batch device state.
 struct Session {
     Index* ix = nullptr;
     cudaStream_t stream = nullptr;
     uint32_t max_q = 0, nq = 0;
-    uint32_t chunk = 0;              // queries per align pass: the graph/DP workspace is sized for this many
+    uint32_t chunk = 0;              // queries per align pass: one workspace handles `chunk` queries at a time
     uint64_t max_bases = 0;
     // queries
     uint8_t* d_qmasks = nullptr;
@@ -105,54 +153,25 @@ struct Session {
     uint32_t* d_cand_n = nullptr;  // [nq][n_tiles]
     uint64_t* d_ranked = nullptr;  // [nq][find_max] keys in rank order
     uint32_t* d_nres = nullptr;    // [nq]
-    unsigned long long* d_counters = nullptr;  // [8]: 0 postings, 1 cells, 2 tb arena cursor, 3 spill arena cursor
+    unsigned long long* d_counters = nullptr;  // [8]: 0 postings, 1 cells
     // family
     uint32_t fam_cap = 0;
     uint32_t* d_fam_ids = nullptr;   // [nq][fam_cap] rank order
     float* d_fam_scores = nullptr;   // [nq][fam_cap]
     int32_t* d_fam_n = nullptr;      // [nq] (-1: too few, -2: window too small)
-    uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window, [1] queries left for another align pass
-    // align
-    uint32_t icap = 0, ncap = 0;     // per-query capacities: items (= nodes = edges), column ranks
+    uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window
+    // align (whole batch)
+    uint32_t icap = 0, ncap = 0, gcap = 0;  // per-query capacities: items (= nodes = edges), column ranks, DP groups
     uint32_t* d_afam = nullptr;      // [nq][fam_cap] family after the contains-query partition
     uint32_t* d_afam_n = nullptr;    // [nq]
     uint32_t* d_contains = nullptr;  // [nq][fam_cap] 1 + first offset of the query inside the relative, 0 = none
     uint32_t* d_copy_src = nullptr;  // [nq][2] (ref id, offset) for SG_Q_COPIED
     GraphHdr* d_hdr = nullptr;       // [nq]
-    uint8_t* d_tab = nullptr;        // [nq][ncap][fam_cap] base mask of family row j at column rank c
-    uint8_t* d_tabli = nullptr;      // [nq][ncap][fam_cap] local node index in that column
-    uint32_t* d_colof = nullptr;     // [nq][ncap] column of rank c
-    uint32_t* d_colbase = nullptr;   // [nq][ncap+1] first node id of column rank c
-    uint32_t* d_item_node = nullptr; // [nq][icap]
-    uint32_t* d_slot = nullptr;      // [nq][icap] predecessor candidates grouped by node
-    uint32_t* d_ncol = nullptr;      // [nq][icap] node column
-    uint8_t* d_nmask = nullptr;      // [nq][icap]
-    uint16_t* d_ncount = nullptr;    // [nq][icap] family rows through the node
-    float* d_nweight = nullptr;      // [nq][icap]
-    uint32_t* d_nsigma = nullptr;    // [nq][icap] column rank
-    uint32_t* d_slotbase = nullptr;  // [nq][icap+1]
-    uint32_t* d_cursor = nullptr;    // [nq][icap]
-    uint32_t* d_pred_off = nullptr;  // [nq][icap+1]
-    uint32_t* d_preds = nullptr;     // [nq][icap]
-    uint32_t* d_pdesc = nullptr;     // [nq][icap] near/far descriptor per edge (generic kernel)
-    uint32_t* d_pdesc2 = nullptr;    // [nq][icap] (delta<<16 | ring column) per edge (v2 kernel)
-    uint32_t* d_order = nullptr;     // [nq][gcap*DP_T] node handled by (group, thread) in the v2 kernel
-    uint16_t* d_nthr = nullptr;      // [nq][icap] thread (ring column) of a node inside its group
-    uint8_t* d_nshift = nullptr;     // [nq][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
-    GhostInfo* d_ghosts = nullptr;   // [nq][gcap][DP_G]
-    uint32_t* d_writers = nullptr;   // [nq][gcap][DP_G] node whose row a loader lane spills / min-tracks
-    int32_t* d_spillrow = nullptr;   // [nq][icap] spill row of node or -1
-    uint8_t* d_nflags = nullptr;     // [nq][icap] bit0 has successor
-    uint32_t* d_lastnodes = nullptr; // [nq][icap]
-    GroupInfo* d_groups = nullptr;   // [nq][gcap]
-    uint32_t gcap = 0;
-    float* d_lastcol = nullptr;      // [nq][icap] value(m, Lq-1)
-    float* d_rowmin = nullptr;       // [nq][icap] min over s of value(m, s) (last nodes only)
-    uint32_t* d_rowarg = nullptr;    // [nq][icap] first s reaching it
-    uint32_t* d_tb = nullptr;        // traceback arena (words)
-    uint64_t tb_words = 0;
-    float2* d_spill = nullptr;       // spill arena
-    uint64_t spill_elems = 0;
+    // align (chunk workspaces)
+    int n_ws = 0;
+    Workspace ws[MAX_WS];
+    uint64_t tb_words = 0, spill_elems = 0;  // arena sizes per workspace
+    cudaEvent_t ev_pre = nullptr;    // prealign finished on `stream`
     // outputs
     uint32_t* d_out_cols = nullptr;  // [max_bases]
     uint8_t* d_out_masks = nullptr;  // [max_bases]
@@ -169,9 +188,9 @@ int launch_index_build(Index* ix, cudaStream_t st);
 int launch_find(Session* s, uint32_t max);
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window);
 int launch_prealign(Session* s, const sg_align_params& ap);
-int launch_graph(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
-int launch_mesh(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
-int launch_backtrack(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n);
+int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
+int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
+int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
 
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -99,7 +99,7 @@ struct GraphArgs {
     uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
     uint32_t* lastnodes; GroupInfo* groups;
     uint32_t* order; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
-    unsigned long long* counters; uint64_t tb_words, spill_elems;
+    unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
 };
 
@@ -431,14 +431,14 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             words_total += (uint64_t)(steps / per_word) * T;
         }
         const uint64_t spill_need = (uint64_t)n_spill * Lq;
-        const uint64_t tb_off = atomicAdd(&A.counters[2], (unsigned long long)words_total);
-        const uint64_t sp_off = atomicAdd(&A.counters[3], (unsigned long long)spill_need);
+        const uint64_t tb_off = atomicAdd(&A.cursors[0], (unsigned long long)words_total);
+        const uint64_t sp_off = atomicAdd(&A.cursors[1], (unsigned long long)spill_need);
         hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;
         hdr->n_last = n_last; hdr->n_spill = n_spill; hdr->max_indeg = max_indeg; hdr->wide = wide;
         hdr->mode = (shv[1] || A.force_generic) ? 1u : 2u;
         hdr->tb_off = tb_off; hdr->spill_off = sp_off;
         if (tb_off + words_total > A.tb_words || sp_off + spill_need > A.spill_elems) hdr->status = GS_ARENA_FULL;
-        else atomicAdd(&A.counters[1], (unsigned long long)V * Lq);
+        else atomicAdd(A.cells, (unsigned long long)V * Lq);
     }
 }
 
@@ -457,25 +457,25 @@ int launch_prealign(Session* s, const sg_align_params& ap) {
     return SG_OK;
 }
 
-int launch_graph(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
+int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
     GraphArgs A;
     A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off; A.W = ix->W;
     A.afam = s->d_afam; A.afam_n = s->d_afam_n; A.fam_cap = s->fam_cap;
     A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap; A.q0 = q0;
-    A.hdr = s->d_hdr; A.tab = s->d_tab; A.tabli = s->d_tabli; A.colof = s->d_colof; A.colbase = s->d_colbase;
-    A.item_node = s->d_item_node; A.slot = s->d_slot; A.ncol = s->d_ncol; A.nmask = s->d_nmask;
-    A.ncount = s->d_ncount; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.slotbase = s->d_slotbase;
-    A.cursor = s->d_cursor; A.pred_off = s->d_pred_off; A.preds = s->d_preds; A.pdesc = s->d_pdesc;
-    A.spillrow = s->d_spillrow; A.nflags = s->d_nflags; A.lastnodes = s->d_lastnodes; A.groups = s->d_groups;
-    A.order = s->d_order; A.nthr = s->d_nthr; A.pdesc2 = s->d_pdesc2; A.ghosts = s->d_ghosts; A.writers = s->d_writers;
+    A.hdr = s->d_hdr; A.tab = w->d_tab; A.tabli = w->d_tabli; A.colof = w->d_colof; A.colbase = w->d_colbase;
+    A.item_node = w->d_item_node; A.slot = w->d_slot; A.ncol = w->d_ncol; A.nmask = w->d_nmask;
+    A.ncount = w->d_ncount; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma; A.slotbase = w->d_slotbase;
+    A.cursor = w->d_cursor; A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.pdesc = w->d_pdesc;
+    A.spillrow = w->d_spillrow; A.nflags = w->d_nflags; A.lastnodes = w->d_lastnodes; A.groups = w->d_groups;
+    A.order = w->d_order; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
     A.force_generic = s->force_generic;
-    A.counters = s->d_counters; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
+    A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;
     size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G) * 4;
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_kernel<<<n, DP_BLOCK, smem, s->stream>>>(A);
+    graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

@@ -509,15 +509,15 @@ __global__ void __launch_bounds__(DP_BLOCK, 2) mesh_v1_kernel(MeshArgs A) {
     else v1_query<false>(A, h, blockIdx.x, ring, qm);
 }
 
-int launch_mesh(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
+int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     MeshArgs A;
-    A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = s->d_groups;
+    A.qmasks = s->d_qmasks; A.qoff = s->d_qoff; A.hdr = s->d_hdr; A.groups = w->d_groups;
     A.gcap = s->gcap; A.icap = s->icap; A.q0 = q0;
-    A.nmask = s->d_nmask; A.nweight = s->d_nweight; A.nsigma = s->d_nsigma; A.pred_off = s->d_pred_off;
-    A.pdesc = s->d_pdesc; A.spillrow = s->d_spillrow; A.nflags = s->d_nflags;
-    A.pdesc2 = s->d_pdesc2; A.order = s->d_order; A.nthr = s->d_nthr; A.nshift = s->d_nshift;
-    A.ghosts = s->d_ghosts; A.writers = s->d_writers;
-    A.tb = s->d_tb; A.spill = s->d_spill; A.lastcol = s->d_lastcol; A.rowmin = s->d_rowmin; A.rowarg = s->d_rowarg;
+    A.nmask = w->d_nmask; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma; A.pred_off = w->d_pred_off;
+    A.pdesc = w->d_pdesc; A.spillrow = w->d_spillrow; A.nflags = w->d_nflags;
+    A.pdesc2 = w->d_pdesc2; A.order = w->d_order; A.nthr = w->d_nthr; A.nshift = w->d_nshift;
+    A.ghosts = w->d_ghosts; A.writers = w->d_writers;
+    A.tb = w->d_tb; A.spill = w->d_spill; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.ms = -ap.match_score; A.mms = -ap.mismatch_score; A.gp = ap.gap_penalty; A.gpe = ap.gap_ext_penalty;
     uint32_t max_qlen = 0;
     for (uint32_t i = q0; i < q0 + n; i++) {
@@ -528,8 +528,8 @@ int launch_mesh(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) 
     if (smem > 220 * 1024) SG_FAIL(SG_ERR_LIMIT, "query too long for the DP kernel's shared memory");
     SG_CUDA(cudaFuncSetAttribute(mesh_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SG_CUDA(cudaFuncSetAttribute(mesh_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mesh_v2_kernel<<<n, DP_BLOCK, smem, s->stream>>>(A);
-    mesh_v1_kernel<<<n, DP_BLOCK, smem, s->stream>>>(A);
+    mesh_v2_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
+    mesh_v1_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 2;
     return SG_OK;

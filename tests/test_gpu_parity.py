@@ -246,3 +246,30 @@ def test_full_size_queries_vs_oracle(orc, dp_mode):
         assert all(r["status"] == 0 for r in res)
     orc.index_free(oix)
     ix.close()
+
+
+def test_chunk_pipeline_and_arena_retry(orc, monkeypatch):
+    """the batch is cut into chunks dealt to several workspaces/streams (SG_BATCH, SG_STREAMS); queries that do
+    not fit the traceback arena are redone in further passes (SG_TB_ARENA_MB): results must not depend on any of it"""
+    tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
+    msa = O.MSA(m, c, o, 900)
+    oix = orc.index_build(msa, 6, 0)
+    nq = 61
+    qm, qo = synth.synth_queries(tree, nq, "full", seed=19)
+    fp_kw = dict(fs_min=20, fs_max=20, fs_min_len=100, fs_full_len=240, fs_req_gaps=5)
+    ores, occ, omm, cells, posts, nt = orc.run_batch(oix, msa, qm, qo, O.FamParams(**fp_kw), O.AlignParams())
+    for batch, streams, tb_mb in ((7, 3, None), (16, 2, 1), (5, 4, 1), (64, 1, None)):
+        monkeypatch.setenv("SG_BATCH", str(batch))
+        monkeypatch.setenv("SG_STREAMS", str(streams))
+        if tb_mb is None:
+            monkeypatch.delenv("SG_TB_ARENA_MB", raising=False)
+        else:
+            monkeypatch.setenv("SG_TB_ARENA_MB", str(tb_mb))
+        ix = sina_b200.Index(m, c, o, 900, k=6)
+        oc, om, res = ix.run(qm, qo, sina_b200.FamParams(**fp_kw), sina_b200.AlignParams())
+        for i in range(nq):
+            a, b = int(qo[i]), int(qo[i + 1])
+            compare_result(res[i], oc[a:b], om[a:b], ores[i], occ[a:a + ores[i].n_out], omm[a:a + ores[i].n_out], 900,
+                           (batch, streams, tb_mb, i))
+        ix.close()
+    orc.index_free(oix)
