@@ -33,10 +33,11 @@ constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts
 constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
-constexpr int DP_BLOCK = 512;                // threads per DP CTA = columns of the shared-memory ring
-constexpr int DP_T = 448;                    // node rows per DP group (compute lanes, one row each)
+constexpr int DP_BLOCK = 256;                // threads per DP CTA = columns of the shared-memory ring
+constexpr int DP_CTAS_PER_SM = 4;            // resident DP CTAs per SM the kernels are compiled for (register cap)
+constexpr int DP_T = 224;                    // node rows per DP group (compute lanes, one row each)
 constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
-constexpr int DP_RING = 16;                  // ring depth (time slots) of the shared-memory row window
+constexpr int DP_RING = 8;                   // ring depth (time slots) of the shared-memory row window
 constexpr int GHOST_LEAD = 6;                // a ghost trails its source row by >= this many column ranks (prefetch 4 + 2)
 constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan can hold
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer

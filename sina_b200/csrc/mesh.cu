@@ -41,14 +41,36 @@ constexpr int S = DP_BLOCK;    // ring columns (= CTA threads)
 constexpr int R = DP_RING;
 constexpr int NPR = 4;         // predecessors held in registers (generic kernel)
 constexpr int NPF = 8;         // largest in-degree the specialised v2 step is instantiated for
-constexpr int QPAD = 512;      // padding either side of the query in shared memory (s runs out of range)
-constexpr uint32_t RING_BYTES = sizeof(float2) * R * S;
+constexpr int QPAD = 256;      // padding either side of the query in shared memory (s runs out of range by < T + 4)
+static_assert(QPAD >= DP_T + 8, "query padding must cover the group skew");
+constexpr uint32_t SLOT_BYTES = sizeof(float2) * S;       // one time slot of the ring
+constexpr uint32_t RB = SLOT_BYTES * R;                   // one copy of the ring
+constexpr uint32_t RING_BYTES = 2 * RB;                   // the ring is stored twice back to back (see below)
 
 // ====================================================================================================
 // v2: branch-free specialised step
+//
+// Ring addressing. A row publishes the cell of step t into time slot t & (R-1), column = its thread, of BOTH
+// copies of the ring. A consumer reads predecessor p (delta = difference of column ranks, 1..R-2) at byte
+//     slot(t) + ck,   slot(t) = (t & (R-1)) * SLOT_BYTES  (uniform),  ck = col(p)*8 + ((R - delta) & (R-1)) * SLOT_BYTES
+// which lands on time slot (t - delta) & (R-1) of copy A when it does not wrap and on the same slot of copy B
+// when it does, so the per-lane address needs no add-and-mask: it is register + uniform register in the LDS itself.
 // ====================================================================================================
-__device__ __forceinline__ float2 lds_f2(uint32_t byte_off, const unsigned char* smem) {
-    return *reinterpret_cast<const float2*>(smem + byte_off);
+// explicit shared-window accesses: address = per-lane register + uniform slot offset, which ptxas folds into
+// the LDS/STS operand ([R + UR + imm]) so that no per-lane integer op is spent on addressing
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y), "n"(OFF) : "memory");
 }
 
 // One group for the lanes of a warp whose rows all have <= NPW predecessors. Slots are right-aligned: a row
@@ -56,28 +78,42 @@ __device__ __forceinline__ float2 lds_f2(uint32_t byte_off, const unsigned char*
 // its first copy and strict '<' keeps the first, so nothing changes; backtrack maps slot -> ordinal with
 // max(0, slot - shift)). Rows without predecessor get dgp = dgpe = msw = mmsw = +inf so that no deletion or
 // match candidate can win, and has_real = false keeps gapm_val at its edge value.
+// The row computes query position s = t - t_first at step t (t_first = its column rank offset in the group);
+// qrow = query - t_first, so qrow[t] is the query base of that position. Lanes without a row have
+// t_first = t_last = ~0: whatever they compute is never read.
 template <int NPW, bool WIDE>
-__device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qm, uint32_t Lq,
-                                              uint32_t steps4, const uint32_t* ck, float dgp, float dgpe, int soff,
-                                              float initv, bool has_real, uint32_t mask,
-                                              float msw, float mmsw, float* lastcol_ptr, uint32_t* tbg) {
+__device__ __forceinline__ void v2_fast_group(const MeshArgs& A, uint32_t sring, uint32_t qrow,
+                                              uint32_t steps4, const uint32_t* ck, float dgp, float dgpe,
+                                              uint32_t t_first, uint32_t t_last, uint32_t w_first, uint32_t w_last,
+                                              float initv, bool has_real,
+                                              uint32_t mask, float msw, float mmsw, float* lastcol_ptr, uint32_t* tbg) {
     const float gp = A.gp, gpe = A.gpe;
     const float INF = __int_as_float(0x7f800000);
+    const float gcap = has_real ? INF : 1.0f;
     float pvp[NPW];
+    uint32_t pk[NPW];                      // shared-window byte address of predecessor slot k at time slot 0
 #pragma unroll
-    for (int k = 0; k < NPW; k++) pvp[k] = 0.f;
+    for (int k = 0; k < NPW; k++) { pvp[k] = 0.f; pk[k] = sring + ck[k]; }
     float Ep = 1.0f, Hp = 1.0f;
-    uint32_t x = 0;                       // t * S * 8: byte offset of time slot t before wrapping
-    int s = -soff;
-    const uint32_t wofs = threadIdx.x * 8u;
-    const uint32_t RMASK = RING_BYTES - 1;
+    const uint32_t wadr = sring + threadIdx.x * 8u;
     for (uint32_t t0 = 0; t0 < steps4; t0 += 4) {
+        // [w_first, w_last] = steps at which some row of this warp is inside the query; outside of it the warp
+        // only keeps the barriers (nothing it would publish is read: a consumer's window starts after its
+        // predecessors' and ends after theirs)
+        if (t0 + 3 < w_first || t0 > w_last) {
+            __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
+            continue;
+        }
         uint32_t tbw = 0, tbw2 = 0;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
+            const uint32_t t = t0 + u;
+            const uint32_t xs = (t & (R - 1)) * SLOT_BYTES;      // uniform
             const uint32_t SH = WIDE ? 16u * (u & 1) : 8u * u;   // compile-time shift of this step's cell
-            const bool s0 = (s == 0);
-            float value = s0 ? 1.0f : initv;                     // init_edge / init (mesh.h:294-301,469-473)
+            const bool s0 = (t == t_first);
+            // init (mesh.h:294-301,469-473): 1000000, or 1 for rows without predecessor. The s == 0 column is an
+            // edge too (init 1): there the forced insertion candidate E = 1 below supplies that 1.
+            float value = initv;
             float gm = 1.0f;
             uint32_t code = 0;
             bool open = false;
@@ -85,8 +121,7 @@ __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* 
             // ---- deletion over predecessor slots, ascending id (mesh.h:475-478 -> 305-330)
 #pragma unroll
             for (int k = 0; k < NPW; k++) {
-                const uint32_t a = (x + ck[k]) & RMASK;
-                const float2 c = lds_f2(a, smem);
+                const float2 c = lds_f2(pk[k] + xs);
                 cur[k] = c.x;
                 const float v = __fadd_rn(c.x, dgp);
                 const float gv = __fadd_rn(c.y, dgpe);
@@ -98,16 +133,18 @@ __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* 
                 const uint32_t co = WIDE ? (cd | (4u << SH)) : (cd | (32u << SH));
                 code = win ? (open ? co : cd) : code;
             }
-            const float gapm = has_real ? gm : 1.0f;
-            // ---- insertion from (m, s-1) (mesh.h:486-490 -> 332-358)
+            const float gapm = fminf(gm, gcap);                   // gcap = +inf, or 1 for rows without predecessor
+            // ---- insertion from (m, s-1) (mesh.h:486-490 -> 332-358). At s == 0 the reference evaluates no
+            // insertion, gaps_val stays 1 and value starts from 1: E is forced to 1, so value = min(1, deletions)
+            // exactly as there (the traceback of an s == 0 cell is never followed).
             const bool ext = (Ep == Hp);
             float E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
             E = s0 ? 1.0f : E;
-            const bool iwin = (E <= value) && !s0;
+            const bool iwin = (E <= value);
             value = iwin ? E : value;
             code = iwin ? (TB_SRC_INS << SH) : code;
             // ---- match from (p, s-1) (mesh.h:492-500 -> 360-374)
-            float sc = (mask & qm[s]) ? msw : mmsw;
+            float sc = (mask & lds_u8(qrow + t)) ? msw : mmsw;
             sc = s0 ? INF : sc;
 #pragma unroll
             for (int k = 0; k < NPW; k++) {
@@ -118,16 +155,16 @@ __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* 
             }
             const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
             const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
-            code |= (open ? f_open : 0u) | ((!ext && !s0) ? f_ins : 0u);
+            code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
             if (WIDE && u >= 2) tbw2 |= code; else tbw |= code;
 #pragma unroll
             for (int k = 0; k < NPW; k++) pvp[k] = cur[k];
             Ep = E;
             Hp = value;
-            *reinterpret_cast<float2*>(smem + ((x + wofs) & RMASK)) = make_float2(value, gapm);
-            if (s == (int)Lq - 1) *lastcol_ptr = value;
-            x += S * 8u;
-            s++;
+            const float2 out = make_float2(value, gapm);
+            sts_f2<0>(wadr + xs, out);
+            sts_f2<RB>(wadr + xs, out);
+            if (t == t_last) *lastcol_ptr = value;
             __syncthreads();
         }
         if (WIDE) {
@@ -139,7 +176,7 @@ __device__ __forceinline__ void v2_fast_group(const MeshArgs& A, unsigned char* 
     }
 }
 
-// Warps holding a row with more than NPR predecessors: slots are looped over.
+// Warps holding a row with more than NPF predecessors: slots are looped over.
 template <bool WIDE>
 __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qm, uint32_t Lq,
                                                  uint32_t steps4, uint32_t npw, uint32_t np, const uint32_t* pd,
@@ -186,7 +223,9 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                 }
                 code |= WIDE ? ((open_last << 3) | (ins_open << 4)) : ((open_last << 6) | (ins_open << 7));
                 Ep = E; Hp = value;
-                ringw[(t & (R - 1)) * S + threadIdx.x] = make_float2(value, gapm);
+                const float2 out = make_float2(value, gapm);
+                ringw[(t & (R - 1)) * S + threadIdx.x] = out;
+                ringw[(R + (t & (R - 1))) * S + threadIdx.x] = out;   // second copy, read by the specialised warps
                 if (s == (int)Lq - 1) *lastcol_ptr = value;
             }
             if (WIDE) { if (u >= 2) tbw2 |= code << (16 * (u & 1)); else tbw |= code << (16 * (u & 1)); }
@@ -235,13 +274,17 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
         if (is_ghost && col >= 0 && col < (int)Lq) return __ldcg(&gsrc[col]);
         return make_float2(0.f, 0.f);
     };
+    auto gstore = [&](uint32_t t, float2 c) {
+        ring[(t & (R - 1)) * S + threadIdx.x] = c;
+        ring[(R + (t & (R - 1))) * S + threadIdx.x] = c;
+    };
     // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0); afterwards the
     // data of step t+4 is requested at step t, so the L2 latency never sits between two barriers
     // (GHOST_LEAD = 4 + 2 keeps that request behind the source row's spill store).
     float2 pf[4];
     {
         const float2 c = gload(-1);
-        if (is_ghost) ring[((uint32_t)(-1) & (R - 1)) * S + threadIdx.x] = c;
+        if (is_ghost) gstore((uint32_t)(-1), c);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) pf[k] = gload(k);
@@ -260,7 +303,7 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
             const uint32_t t = t0 + u;
             const float2 c = pf[u];
             pf[u] = gload((int)t + 4);
-            if (is_ghost) ring[(t & (R - 1)) * S + threadIdx.x] = c;
+            if (is_ghost) gstore(t, c);
             if (t >= 1) drain(t);
             __syncthreads();
         }
@@ -278,7 +321,6 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
     const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     const uint32_t* pdesc2 = A.pdesc2 + io;
     uint32_t* tbq = A.tb + h.tb_off;
-    const uint32_t RMASK = RING_BYTES - 1;
 
     for (uint32_t g = 0; g < h.n_groups; g++) {
         const GroupInfo gi = A.groups[(uint64_t)ql * A.gcap + g];
@@ -291,7 +333,7 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
             uint32_t np = 0, pbase = 0, mask = 0;
             int soff = 0;
             float msw = 0.f, mmsw = 0.f;
-            float* lastcol_ptr = A.lastcol + io;  // never stored through for invalid lanes (s stays out of range)
+            float* lastcol_ptr = A.lastcol + io;  // never stored through for lanes without a row
             if (valid) {
                 pbase = pred_off[m];
                 np = pred_off[m + 1] - pbase;
@@ -301,15 +343,16 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
                 mmsw = __fmul_rn(A.mms, w);
                 soff = (int)(A.nsigma[io + m] - gi.sigma_lo);
                 lastcol_ptr = A.lastcol + io + m;
-            } else {
-                soff = (int)(steps4 + 8);    // idle lane: s stays negative, nothing it computes is ever read
             }
             const uint32_t npw = max(1u, __reduce_max_sync(0xffffffffu, np));
+            const bool warp_has_rows = __any_sync(0xffffffffu, valid);
             if (valid) A.nshift[io + m] = (uint8_t)(npw - np);
             const float initv = np == 0 ? 1.0f : 1000000.0f;
             uint32_t* tbg = tbq + gi.tb_off + tid;
             __syncthreads();  // matches the loader's prologue barrier
-            if (npw <= (uint32_t)NPF) {
+            if (!warp_has_rows) {
+                for (uint32_t t = 0; t < steps4; t++) __syncthreads();   // a warp without rows only keeps the barriers
+            } else if (npw <= (uint32_t)NPF) {
                 uint32_t ck[NPF];
                 const uint32_t shift = npw - np;
 #pragma unroll
@@ -318,21 +361,27 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
                     if (np > 0 && k < (int)npw) {
                         const uint32_t ord = (uint32_t)k > shift ? (uint32_t)k - shift : 0u;
                         const uint32_t d = pdesc2[pbase + ord];
-                        // slot (t - delta) & 15, column c  ->  byte ((t - delta)*S + c)*8, wrapped by RMASK
-                        ck[k] = ((d & 0xffffu) * 8u - (d >> 16) * (S * 8u)) & RMASK;
+                        ck[k] = (d & 0xffffu) * 8u + (((uint32_t)R - (d >> 16)) & (R - 1)) * SLOT_BYTES;
                     }
                 }
                 const float INF = __int_as_float(0x7f800000);
                 const bool hr = np > 0;
                 const float dgp = hr ? A.gp : INF, dgpe = hr ? A.gpe : INF;
                 if (!hr) { msw = INF; mmsw = INF; }
-#define V2_CASE(N) case N: v2_fast_group<N, WIDE>(A, smem, qm, Lq, steps4, ck, dgp, dgpe, soff, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
+                const uint32_t t_first = valid ? (uint32_t)soff : 0xFFFFFFFFu;
+                const uint32_t t_last = valid ? (uint32_t)soff + Lq - 1 : 0xFFFFFFFFu;
+                const uint32_t w_first = __reduce_min_sync(0xffffffffu, t_first);
+                const uint32_t w_last = __reduce_max_sync(0xffffffffu, valid ? t_last : 0u);
+                const uint32_t sring = (uint32_t)__cvta_generic_to_shared(smem);
+                const uint32_t qrow = (uint32_t)__cvta_generic_to_shared(qm) - (valid ? (uint32_t)soff : 0u);
+#define V2_CASE(N) case N: v2_fast_group<N, WIDE>(A, sring, qrow, steps4, ck, dgp, dgpe, t_first, t_last, w_first, w_last, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
                 switch (npw) {
                     V2_CASE(1) V2_CASE(2) V2_CASE(3) V2_CASE(4) V2_CASE(5) V2_CASE(6) V2_CASE(7)
-                    default: v2_fast_group<8, WIDE>(A, smem, qm, Lq, steps4, ck, dgp, dgpe, soff, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
+                    default: v2_fast_group<8, WIDE>(A, sring, qrow, steps4, ck, dgp, dgpe, t_first, t_last, w_first, w_last, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
                 }
 #undef V2_CASE
             } else {
+                if (!valid) soff = (int)(steps4 + 8);    // lane without a row: s stays negative
                 v2_generic_group<WIDE>(A, smem, qm, Lq, steps4, npw, np, pdesc2 + pbase, soff,
                                        initv, mask, msw, mmsw, lastcol_ptr, tbg);
             }
@@ -341,7 +390,7 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
     }
 }
 
-__global__ void __launch_bounds__(DP_BLOCK, 2) mesh_v2_kernel(MeshArgs A) {
+__global__ void __launch_bounds__(DP_BLOCK, DP_CTAS_PER_SM) mesh_v2_kernel(MeshArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t q = A.q0 + blockIdx.x;
     const GraphHdr h = A.hdr[q];
@@ -495,7 +544,7 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
     }
 }
 
-__global__ void __launch_bounds__(DP_BLOCK, 2) mesh_v1_kernel(MeshArgs A) {
+__global__ void __launch_bounds__(DP_BLOCK, DP_CTAS_PER_SM) mesh_v1_kernel(MeshArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2* ring = reinterpret_cast<float2*>(smem);            // [R][S]
     uint8_t* qm = smem + RING_BYTES + 16 + QPAD;
