@@ -1,0 +1,174 @@
+// Unit checks of the host-side mirror (no GPU needed). Vectors are the reference's own:
+// src/unit_tests/cseq_test.cpp:49-52 (strings), :99-131 (append), :133-183 (setWidth), :185-203 (dna),
+// :226-243 (case); FASTA reader/writer behaviour follows src/rw_fasta.cpp:229-315,438-528.
+#include <algorithm>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "align.h"
+#include "famfinder.h"
+#include "rw_fasta.h"
+
+using namespace sina;
+static int n_checks = 0, n_fail = 0;
+#define CHECK(cond) do { n_checks++; if (!(cond)) { n_fail++; std::cerr << "FAIL " << __FILE__ << ":" << __LINE__ << ": " #cond << std::endl; } } while (0)
+#define EQUAL(a, b) do { n_checks++; if (!((a) == (b))) { n_fail++; std::cerr << "FAIL " << __FILE__ << ":" << __LINE__ << ": " #a " == " #b " [" << (a) << " vs " << (b) << "]" << std::endl; } } while (0)
+#define THROWS(stmt, ex) do { n_checks++; bool t_ = false; try { stmt; } catch (ex&) { t_ = true; } if (!t_) { n_fail++; std::cerr << "FAIL " << __FILE__ << ":" << __LINE__ << ": no " #ex << std::endl; } } while (0)
+
+static const std::string rna = "AGCURYKMSWBDHVN";
+static const std::string rna_aligned = "--A-G---CUR-YKM-S---WBD-HVN---";
+static const std::string rna_aligned_dots = "..A-G---CUR-YKM-S---WBD-HVN...";
+
+static std::string strip(std::string s) { s.erase(std::remove(s.begin(), s.end(), '-'), s.end()); return s; }
+static std::string lower(std::string s) { for (auto& c : s) c = (char)tolower(c); return s; }
+static void test_data(const cseq& c, const std::string& name, const std::string& aligned) {
+    EQUAL(c.size(), strip(aligned).size());
+    EQUAL(c.getWidth(), aligned.size());
+    EQUAL(c.getBases(), strip(aligned));
+    EQUAL(c.getAligned(true), aligned);
+    EQUAL(c.getName(), name);
+}
+
+static void test_cseq() {
+    { cseq c; test_data(c, "", ""); }
+    { cseq c("thename", rna.c_str()); test_data(c, "thename", rna); cseq d = c; test_data(d, "thename", rna); }
+    {
+        cseq c;
+        c.append(rna); test_data(c, "", rna);
+        c.append(""); test_data(c, "", rna);
+        c.append(rna); test_data(c, "", rna + rna);
+        c.clearSequence(); test_data(c, "", "");
+        c.append(rna_aligned); test_data(c, "", rna_aligned);
+        c.append(rna); test_data(c, "", rna_aligned + rna);
+        c.append(rna_aligned); test_data(c, "", rna_aligned + rna + rna_aligned);
+        c.append(aligned_base(0, base_iupac::from_char('A')));  // wrong order: forced to the current width
+        EQUAL(c.getAligned(true), rna_aligned + rna + rna_aligned + "A");
+        EQUAL(c.getWidth(), 75u);  // the reference's known off-by-one (expected failure in its own test)
+    }
+    {
+        cseq c;
+        const std::string g20(20, '-');
+        c.setWidth(20); test_data(c, "", g20);
+        c.setWidth(40); test_data(c, "", g20 + g20);
+        c.setWidth(20); test_data(c, "", g20);
+        c.setWidth(0); test_data(c, "", "");
+        c.append(rna_aligned);
+        c.setWidth(rna_aligned.size() + 20); test_data(c, "", rna_aligned + g20);
+        c.setWidth(rna_aligned.size()); test_data(c, "", rna_aligned);
+        const char* steps[] = {"--A-G---CUR-YKM-S---WBD-HVN", "--A-G---CUR-YKM-S---WBDHVN", "--A-G---CUR-YKM-S--WBDHVN", nullptr,
+                               "--A-G---CUR-YKM-SWBDHVN", "--A-G---CUR-YKMSWBDHVN", "--A-G---CURYKMSWBDHVN", "--A-G--CURYKMSWBDHVN",
+                               "--A-G-CURYKMSWBDHVN", "--A-GCURYKMSWBDHVN", "--AGCURYKMSWBDHVN", "-AGCURYKMSWBDHVN", "AGCURYKMSWBDHVN"};
+        for (int w = 27, i = 0; w >= 15; w--, i++) {
+            if (!steps[i]) continue;  // the reference's test skips width 24
+            c.setWidth(w);
+            test_data(c, "", steps[i]);
+        }
+        cseq d("", rna_aligned.c_str());
+        THROWS(d.setWidth(14), std::runtime_error);
+    }
+    {
+        std::string r = lower(rna_aligned), d = r, D = rna_aligned;
+        std::replace(d.begin(), d.end(), 'u', 't');
+        std::replace(D.begin(), D.end(), 'U', 'T');
+        cseq c("", r.c_str()), e("", d.c_str());
+        EQUAL(c.getAligned(true, true), d); EQUAL(c.getAligned(true, false), r);
+        EQUAL(e.getAligned(true, true), d); EQUAL(e.getAligned(true, false), r);
+        c.upperCaseAll(); e.upperCaseAll();
+        EQUAL(c.getAligned(true, true), D); EQUAL(c.getAligned(true, false), rna_aligned);
+        EQUAL(e.getAligned(true, false), rna_aligned);
+    }
+    { cseq c("", rna_aligned.c_str()); EQUAL(c.getAligned(false), rna_aligned_dots); }
+    { cseq c("", lower(rna).c_str()); EQUAL(c.getAligned(true), lower(rna)); c.upperCaseAll(); EQUAL(c.getAligned(true), rna); }
+    THROWS(cseq("", "AGCX"), base_iupac::bad_character_exception);
+    { cseq c("x", " A G\tC\r\nU . - N"); EQUAL(c.getAligned(true), "AGCU--N"); }
+}
+
+static void test_options() {
+    po::options_description main_od("m"), adv("a");
+    rw_fasta::get_options_description(main_od, adv);
+    famfinder::get_options_description(main_od, adv);
+    aligner::get_options_description(main_od, adv);
+    po::options_description all;
+    all.add(main_od).add(adv);
+    {   // reference defaults (src/famfinder.cpp:155-195, src/align.cpp:232-259)
+        EQUAL(famfinder::opts.fs_kmer_len, 10u); EQUAL(famfinder::opts.fs_min, 40u); EQUAL(famfinder::opts.fs_max, 40u);
+        EQUAL(famfinder::opts.fs_req, 1u); EQUAL(famfinder::opts.fs_req_full, 1u); EQUAL(famfinder::opts.fs_full_len, 1400u);
+        EQUAL(famfinder::opts.fs_req_gaps, 10u); EQUAL(famfinder::opts.fs_min_len, 150u);
+        CHECK(famfinder::opts.fs_msc == 0.7f); CHECK(famfinder::opts.fs_msc_max == 2.f);
+        CHECK(aligner::opts->match_score == 2.f); CHECK(aligner::opts->mismatch_score == -1.f);
+        CHECK(aligner::opts->gap_penalty == 5.f); CHECK(aligner::opts->gap_ext_penalty == 2.f); CHECK(aligner::opts->fs_weight == 1.f);
+        EQUAL((int)aligner::opts->overhang, (int)OVERHANG_ATTACH); EQUAL((int)aligner::opts->lowercase, (int)LOWERCASE_NONE);
+        EQUAL((int)aligner::opts->insertion, (int)INSERTION_SHIFT);
+    }
+    {
+        const char* argv[] = {"sina", "--db", "ref.fa", "--fs-engine", "internal", "--fs-kmer-len=8", "--fs-min", "15", "--fs-max", "20",
+                              "--fs-msc", "0.5", "--fs-req", "2", "--pen-gap", "4.5", "--pen-gapext", "1.5", "--match-score", "3",
+                              "--mismatch-score", "-2", "--overhang", "edge", "--lowercase", "unaligned", "--insertion", "remove",
+                              "--realign", "--fs-kmer-no-fast", "--fs-kmer-mm", "1", "--fs-kmer-norel", "-t", "none"};
+        po::variables_map vm;
+        po::store(sizeof(argv) / sizeof(*argv), argv, all, vm);
+        famfinder::validate_vm(vm, all);
+        EQUAL(famfinder::opts.database, std::string("ref.fa")); EQUAL(famfinder::opts.fs_kmer_len, 8u);
+        EQUAL(famfinder::opts.fs_min, 15u); EQUAL(famfinder::opts.fs_max, 20u); CHECK(famfinder::opts.fs_msc == 0.5f);
+        EQUAL(famfinder::opts.fs_req, 2u); CHECK(famfinder::opts.fs_no_fast); EQUAL(famfinder::opts.fs_kmer_mm, 1u);
+        CHECK(aligner::opts->gap_penalty == 4.5f); CHECK(aligner::opts->gap_ext_penalty == 1.5f);
+        CHECK(aligner::opts->match_score == 3.f); CHECK(aligner::opts->mismatch_score == -2.f);
+        EQUAL((int)aligner::opts->overhang, (int)OVERHANG_EDGE); EQUAL((int)aligner::opts->lowercase, (int)LOWERCASE_UNALIGNED);
+        EQUAL((int)aligner::opts->insertion, (int)INSERTION_REMOVE); CHECK(aligner::opts->realign);
+        EQUAL(vm.count("db"), 1u); EQUAL(vm.count("fs-min-len"), 0u);
+    }
+    auto rejects = [&](std::vector<const char*> extra) {
+        std::vector<const char*> argv{"sina"};
+        argv.insert(argv.end(), extra.begin(), extra.end());
+        po::variables_map vm;
+        try { po::store((int)argv.size(), argv.data(), all, vm); } catch (std::logic_error&) { return true; }
+        return false;
+    };
+    CHECK(rejects({"--fs-engine", "pt-server"})); CHECK(rejects({"--fs-no-graph"})); CHECK(rejects({"--use-subst-matrix"}));
+    CHECK(rejects({"--filter", "x"})); CHECK(rejects({"--insertion", "forbid"})); CHECK(rejects({"--overhang", "bogus"}));
+    CHECK(rejects({"--no-such-option"})); CHECK(rejects({"--fs-min"})); CHECK(rejects({"--fs-min", "abc"}));
+    CHECK(rejects({"--turn", "all"})); CHECK(rejects({"stray"}));
+    CHECK(!rejects({"--fs-min", "7"}));
+    { po::variables_map vm; THROWS(famfinder::validate_vm(vm, all), std::logic_error); }  // --db is mandatory
+}
+
+static void test_fasta(const std::string& tmpdir) {
+    const std::string in = tmpdir + "/host_unit_in.fasta", out = tmpdir + "/host_unit_out.fasta";
+    {
+        std::ofstream f(in);
+        f << "junk before the first record\n>seq1 first sequence\n; key = value\nAGCU\nagcu\n>bad\nAGXU\n>seq2\r\nAC-GU.N\r\n";
+    }
+    rw_fasta::reader rd(in);
+    tray t1, t2, t3;
+    CHECK(rd(t1)); CHECK(rd(t2)); CHECK(!rd(t3));
+    EQUAL(t1.seqno, 1u); EQUAL(t1.input_sequence->getName(), std::string("seq1"));
+    EQUAL(t1.input_sequence->get_attr_string(fn_fullname), std::string("first sequence"));
+    EQUAL(t1.input_sequence->get_attr_string("key"), std::string("value"));
+    EQUAL(t1.input_sequence->getBases(), std::string("AGCUagcu"));
+    EQUAL(t2.seqno, 3u);  // the skipped record consumed number 2
+    EQUAL(t2.input_sequence->getName(), std::string("seq2")); EQUAL(t2.input_sequence->getAligned(true), std::string("AC-GU-N"));
+    EQUAL(rd.skipped(), 1u);
+    {
+        rw_fasta::writer wr(out);
+        t1.aligned_sequence = new cseq("seq1", "--AG-CU");
+        t1.aligned_sequence->set_attr<std::string>(fn_fullname, "first sequence");
+        wr(t1);
+        wr(t2);  // not aligned: excluded
+        EQUAL(wr.written(), 1u); EQUAL(wr.excluded(), 1u);
+    }
+    std::ifstream f(out);
+    std::stringstream ss; ss << f.rdbuf();
+    EQUAL(ss.str(), std::string(">seq1 first sequence\n--AG-CU\n"));
+    t1.destroy(); t2.destroy();
+    remove(in.c_str()); remove(out.c_str());
+}
+
+int main(int argc, char** argv) {
+    test_cseq();
+    test_options();
+    test_fasta(argc > 1 ? argv[1] : "/tmp");
+    std::cout << (n_fail ? "FAILED " : "ok ") << n_checks << " checks, " << n_fail << " failures" << std::endl;
+    return n_fail ? 1 : 0;
+}

@@ -1,0 +1,98 @@
+#include "reference_db.h"
+
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+
+namespace sina {
+
+namespace {
+std::mutex g_mu;
+std::map<std::string, std::unique_ptr<reference_db>> g_dbs;
+}  // namespace
+
+void reference_db::pack() {
+    row_off.assign(1, 0);
+    uint64_t total = 0;
+    for (const auto& s : seqs) total += s.size();
+    packed_masks.reserve(total);
+    packed_cols.reserve(total);
+    by_name.clear();
+    for (uint32_t i = 0; i < seqs.size(); i++) {
+        if (seqs[i].getWidth() > width) width = seqs[i].getWidth();
+        for (const auto& b : seqs[i].getAlignedBases()) {
+            packed_masks.push_back(b.getBase());
+            packed_cols.push_back(b.getPosition());
+        }
+        row_off.push_back(packed_masks.size());
+        by_name.emplace(seqs[i].getName(), i);
+    }
+    // mseq requires all rows to have the alignment's width (src/mseq.cpp:56-65)
+    for (auto& s : seqs) s.setWidth(width);
+}
+
+reference_db* reference_db::fromSequences(const std::string& key, std::vector<cseq>&& v) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::unique_ptr<reference_db> db(new reference_db());
+    db->filename = key;
+    db->seqs = std::move(v);
+    db->pack();
+    reference_db* p = db.get();
+    g_dbs[key] = std::move(db);
+    return p;
+}
+
+reference_db* reference_db::getDB(const std::string& path) {
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_dbs.find(path);
+        if (it != g_dbs.end()) return it->second.get();
+    }
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Unable to open reference database '" + path + "'");
+    std::vector<cseq> v;
+    std::string line;
+    cseq* cur = nullptr;
+    size_t lineno = 0;
+    while (std::getline(in, line)) {
+        lineno++;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty() || line[0] == ';') continue;
+        if (line[0] == '>') {
+            const auto blank = line.find_first_of(" \t");
+            v.emplace_back(line.substr(1, blank == std::string::npos ? std::string::npos : blank - 1).c_str());
+            cur = &v.back();
+            if (blank != std::string::npos) cur->set_attr<std::string>(fn_fullname, line.substr(blank + 1));
+        } else if (cur) {
+            try {
+                cur->append(line);
+            } catch (base_iupac::bad_character_exception& e) {
+                throw std::runtime_error("reference database '" + path + "' line " + std::to_string(lineno) +
+                                         ": character '" + std::string(1, (char)e.character) + "' is not IUPAC");
+            }
+        }
+    }
+    if (v.empty()) throw std::runtime_error("reference database '" + path + "' holds no sequences");
+    return fromSequences(path, std::move(v));
+}
+
+std::vector<std::string> reference_db::getSequenceNames() const {
+    std::vector<std::string> n;
+    n.reserve(seqs.size());
+    for (const auto& s : seqs) n.push_back(s.getName());
+    return n;
+}
+
+const cseq& reference_db::getCseq(const std::string& name) const {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) throw std::runtime_error("sequence '" + name + "' not in reference database");
+    return seqs[it->second];
+}
+
+int64_t reference_db::indexOf(const std::string& name) const {
+    auto it = by_name.find(name);
+    return it == by_name.end() ? -1 : (int64_t)it->second;
+}
+
+}  // namespace sina

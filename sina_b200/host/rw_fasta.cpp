@@ -1,0 +1,155 @@
+#include "rw_fasta.h"
+
+#include <fstream>
+#include <iostream>
+
+namespace sina {
+
+rw_fasta::options* rw_fasta::opts = nullptr;
+
+void rw_fasta::get_options_description(po::options_description& main, po::options_description& adv) {
+    if (!opts) opts = new options();
+    main.custom("meta-fmt", "none", "meta data in (*none*|header|comment)", [](const std::string& v) {
+        if (v == "none") opts->fastameta = FASTA_META_NONE;
+        else if (v == "header") opts->fastameta = FASTA_META_HEADER;
+        else if (v == "comment") opts->fastameta = FASTA_META_COMMENT;
+        else if (v == "csv") throw std::logic_error("--meta-fmt csv is not supported by sina_b200");
+        else throw std::logic_error("Illegal value for meta-fmt");
+    });
+    po::options_description od("FASTA I/O");
+    od.value<int>("line-length", &opts->line_length, 0, "wrap output sequence (unlimited)");
+    od.unsupported("min-idty", true, "identity computation (cseq_comparator)");
+    od.flag("fasta-write-dna", &opts->out_dna, "Write DNA sequences (default: RNA)");
+    od.flag("fasta-write-dots", &opts->out_dots, "Use dots instead of dashes to distinguish unknown sequence data from indels");
+    od.unsupported("fasta-idx", true, "block-wise input");
+    od.unsupported("fasta-block", true, "block-wise input");
+    adv.add(od);
+}
+void rw_fasta::validate_vm(po::variables_map&, po::options_description&) {}
+
+// ------------------------------------------------------------------------------------------------ reader
+struct rw_fasta::reader::priv_data {
+    std::ifstream file;
+    std::istream* in = nullptr;
+    std::string filename;
+    unsigned int seqno = 0, lineno = 0, skipped = 0;
+};
+
+rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
+    if (!opts) opts = new options();
+    data->filename = infile;
+    if (infile == "-") data->in = &std::cin;
+    else {
+        data->file.open(infile);
+        if (!data->file) throw std::runtime_error("Unable to open file " + infile + " for reading.");
+        data->in = &data->file;
+    }
+}
+rw_fasta::reader::~reader() = default;
+unsigned int rw_fasta::reader::skipped() const { return data->skipped; }
+
+bool rw_fasta::reader::operator()(tray& t) {
+    std::istream& in = *data->in;
+    std::string line;
+    for (;;) {
+        if (in.fail()) return false;
+        while (in.peek() != '>' && std::getline(in, line).good()) data->lineno++;  // skip to the next title
+        data->lineno++;
+        if (!std::getline(in, line).good()) return false;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        t.seqno = ++data->seqno;
+        t.input_sequence = new cseq();
+        cseq& c = *t.input_sequence;
+        size_t blank = line.find_first_of(" \t");
+        if (blank == 0 || blank == std::string::npos) blank = line.size();
+        c.setName(line.substr(1, blank - 1));
+        if (blank < line.size()) c.set_attr<std::string>(fn_fullname, line.substr(blank + 1));
+        while (in.peek() == ';' && std::getline(in, line).good()) {  // comment lines may carry key=value attributes
+            data->lineno++;
+            const size_t eq = line.find('=');
+            if (eq != std::string::npos) {
+                auto trim = [](std::string s) {
+                    const size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+                    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+                };
+                c.set_attr<std::string>(trim(line.substr(1, eq - 1)), trim(line.substr(eq + 1)));
+            }
+        }
+        try {
+            while (in.peek() != '>' && in.good()) {
+                std::getline(in, line);
+                data->lineno++;
+                c.append(line);
+            }
+            return true;
+        } catch (base_iupac::bad_character_exception& e) {  // src/rw_fasta.cpp:294-304: skip the sequence, keep going
+            std::cerr << "Skipping sequence " << data->seqno << " (>" << c.getName() << ") at " << data->filename << ":"
+                      << data->lineno << " (contains character '" << (char)e.character << "')" << std::endl;
+            data->skipped++;
+            delete t.input_sequence;
+            t.input_sequence = nullptr;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ writer
+struct rw_fasta::writer::priv_data {
+    std::ofstream file;
+    std::ostream* out = nullptr;
+    unsigned int count = 0, excluded = 0;
+    void write(const cseq& c);
+};
+
+rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
+    if (!opts) opts = new options();
+    if (outfile == "-") data->out = &std::cout;
+    else {
+        data->file.open(outfile);
+        if (!data->file) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
+        data->out = &data->file;
+    }
+}
+rw_fasta::writer::~writer() = default;
+unsigned int rw_fasta::writer::written() const { return data->count; }
+unsigned int rw_fasta::writer::excluded() const { return data->excluded; }
+
+void rw_fasta::writer::priv_data::write(const cseq& c) {  // src/rw_fasta.cpp:438-528
+    std::ostream& o = *out;
+    o << ">" << c.getName();
+    const std::string fname = c.get_attr_string(fn_fullname);
+    if (!fname.empty()) o << " " << fname;
+    if (opts->fastameta == FASTA_META_HEADER) {
+        for (const auto& ap : c.get_attrs()) {
+            if (ap.first == fn_family || ap.first == fn_fullname || ap.second.empty()) continue;
+            o << " [" << ap.first << "=" << ap.second << "]";
+        }
+        o << "\n";
+    } else if (opts->fastameta == FASTA_META_COMMENT) {
+        o << "\n";
+        for (const auto& ap : c.get_attrs()) {
+            if (ap.first == fn_family || ap.first == fn_fullname) continue;
+            o << "; " << ap.first << "=" << ap.second << "\n";
+        }
+    } else {
+        o << "\n";
+    }
+    const std::string seq = c.getAligned(!opts->out_dots, opts->out_dna);
+    if (opts->line_length > 0) {
+        for (size_t i = 0; i < seq.size(); i += opts->line_length) o << seq.substr(i, opts->line_length) << "\n";
+    } else {
+        o << seq << "\n";
+    }
+    count++;
+}
+
+tray rw_fasta::writer::operator()(tray t) {
+    if (t.input_sequence == nullptr) throw std::runtime_error("Received broken tray in rw_fasta writer");
+    if (t.aligned_sequence == nullptr) {  // src/rw_fasta.cpp:399-404
+        ++data->excluded;
+        return t;
+    }
+    data->write(*t.aligned_sequence);
+    return t;
+}
+
+}  // namespace sina

@@ -1,0 +1,51 @@
+// FASTA source and sink of the pipeline (src/rw_fasta.h:46-105, src/rw_fasta.cpp:229-315,394-528).
+#ifndef SINA_B200_HOST_RW_FASTA_H
+#define SINA_B200_HOST_RW_FASTA_H
+#include <istream>
+#include <memory>
+#include <ostream>
+#include <string>
+
+#include "options.h"
+#include "tray.h"
+
+namespace sina {
+
+enum FASTA_META_TYPE { FASTA_META_NONE = 0, FASTA_META_HEADER = 1, FASTA_META_COMMENT = 2 };
+
+class rw_fasta {
+public:
+    struct options {
+        FASTA_META_TYPE fastameta = FASTA_META_NONE;
+        int line_length = 0;
+        bool out_dots = false, out_dna = false;
+    };
+    static options* opts;
+    static void get_options_description(po::options_description& main, po::options_description& adv);
+    static void validate_vm(po::variables_map& vm, po::options_description& desc);
+
+    class reader {
+    public:
+        explicit reader(const std::string& infile);  // "-" = stdin; throws std::runtime_error if unreadable
+        ~reader();
+        bool operator()(tray& t);                    // false at end of input; bad sequences are skipped with a message
+        unsigned int skipped() const;
+    private:
+        struct priv_data;
+        std::shared_ptr<priv_data> data;
+    };
+    class writer {
+    public:
+        explicit writer(const std::string& outfile);  // "-" = stdout
+        ~writer();
+        tray operator()(tray t);
+        unsigned int written() const;
+        unsigned int excluded() const;
+    private:
+        struct priv_data;
+        std::shared_ptr<priv_data> data;
+    };
+};
+
+}  // namespace sina
+#endif

@@ -1,0 +1,137 @@
+"""GPU: the `sina` command line and the per-tray stage functors of sina_b200/host against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sina_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "sina_b200", "bin")
+FAM = dict(fs_min=20, fs_max=20, fs_min_len=100, fs_full_len=240, fs_req_gaps=5)
+FAM_ARGS = ["--fs-kmer-len", "6", "--fs-min", "20", "--fs-max", "20", "--fs-min-len", "100", "--fs-full-len", "240", "--fs-req-gaps", "5"]
+
+
+def write_fasta(path, names, seqs, width=0):
+    with open(path, "w") as f:
+        for n, s in zip(names, seqs):
+            f.write(">%s\n" % n)
+            if width:
+                for i in range(0, len(s), width):
+                    f.write(s[i:i + width] + "\n")
+            else:
+                f.write(s + "\n")
+
+
+def read_fasta(path):
+    out, name = {}, None
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            out[name] = ""
+        elif name:
+            out[name] += line
+    return out
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
+    msa = O.MSA(m, c, o, 900)
+    nq = 37
+    qm, qo = synth.synth_queries(tree, nq, "full", seed=23)
+    write_fasta(d / "ref.fasta", ["ref%d" % i for i in range(msa.N)], [msa.row_string(i) for i in range(msa.N)], width=70)
+    qs = [O.decode(qm[int(qo[i]):int(qo[i + 1])]) for i in range(nq)]
+    qs[3] = qs[3].lower()          # case is ignored unless --lowercase original
+    qs[5] = qs[5][:40] + "n" + qs[5][41:]
+    write_fasta(d / "q.fasta", ["q%d" % i for i in range(nq)], qs, width=60)
+    qmasks = [O.encode(s) for s in qs]
+    return d, msa, qmasks
+
+
+def oracle_strings(orc, msa, qmasks, ap_kw, fp_kw=FAM, k=6):
+    oix = orc.index_build(msa, k, 0)
+    qoff = np.zeros(len(qmasks) + 1, np.uint64)
+    qoff[1:] = np.cumsum([len(q) for q in qmasks])
+    qm = np.concatenate(qmasks)
+    res, oc, om, cells, posts, nt = orc.run_batch(oix, msa, qm, qoff, O.FamParams(**fp_kw), O.AlignParams(**ap_kw))
+    out = []
+    for i in range(len(qmasks)):
+        a, n = int(qoff[i]), res[i].n_out
+        out.append(O.render(om[a:a + n], oc[a:a + n], msa.W) if res[i].status in (0, 1) else None)
+    orc.index_free(oix)
+    return out, res
+
+
+@pytest.mark.parametrize("cli,ap_kw", [
+    ([], {}),
+    (["--overhang", "edge", "--lowercase", "unaligned", "--batch-size", "8"], dict(overhang=2, lowercase=2)),
+    (["--lowercase", "original", "--pen-gap", "4.3", "--pen-gapext", "1.1", "--match-score", "1.7", "--mismatch-score", "-0.9",
+      "--fs-weight", "0.5", "--line-length", "100"],
+     dict(lowercase=1, gap_penalty=4.3, gap_ext_penalty=1.1, match_score=1.7, mismatch_score=-0.9, fs_weight=0.5)),
+])
+def test_cli_matches_oracle(orc, data, cli, ap_kw):
+    d, msa, qmasks = data
+    out = d / "out.fasta"
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
+                        "--fs-engine", "internal", "--gpus", "1"] + FAM_ARGS + cli, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "sequences/s" in r.stderr
+    got = read_fasta(out)
+    want, res = oracle_strings(orc, msa, qmasks, ap_kw)
+    assert list(got) == ["q%d" % i for i in range(len(qmasks)) if want[i] is not None]  # input order kept
+    for i, w in enumerate(want):
+        if w is not None:
+            assert got["q%d" % i] == w, i
+
+
+def test_stage_functors_per_tray(orc, data):
+    """famfinder::operator()(tray) / aligner::operator()(tray) / kmer_search::find one query at a time"""
+    d, msa, qmasks = data
+    r = subprocess.run([os.path.join(BIN, "stage_dump"), str(d / "ref.fasta"), str(d / "q.fasta")] + FAM_ARGS,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert lines[0] == "size %d" % msa.N
+    want, res = oracle_strings(orc, msa, qmasks, {})
+    oix = orc.index_build(msa, 6, 0)
+    blocks = [lines[i:i + 6] for i in range(1, len(lines), 6)]
+    assert len(blocks) == len(qmasks)
+    for i, b in enumerate(blocks):
+        assert b[0] == "query q%d" % i
+        sc, ids, _ = orc.find(oix, qmasks[i], 5)
+        assert b[1] == "find" + "".join(" ref%d:%d" % (j, s) for j, s in zip(ids, sc))
+        n, fids, fsc = orc.family(oix, msa, qmasks[i], O.FamParams(**FAM))
+        assert b[2] == "family" + "".join(" ref%d:%d" % (j, s) for j, s in zip(fids, fsc))
+        assert b[3] == "aligned " + want[i]
+        assert b[4] == "attrs %d %d %d" % (res[i].qual, res[i].head, res[i].tail)
+        assert b[5].startswith("log scoring: raw=")
+    orc.index_free(oix)
+
+
+def test_cli_soft_failures_and_copy(orc, data, tmp_path):
+    """too few relatives => not written (src/famfinder.cpp:486-491); query contained in a reference => alignment copied
+    (src/align.cpp:349-388); with --realign that reference is dropped instead"""
+    d, msa, qmasks = data
+    m5, c5 = msa.row(5)
+    sub = O.decode(m5[10:200])
+    write_fasta(tmp_path / "q.fasta", ["contained", "tiny", "normal"], [sub, "A", O.decode(qmasks[0])])
+    out = tmp_path / "out.fasta"
+    base = [os.path.join(BIN, "sina"), "-i", str(tmp_path / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta")] + FAM_ARGS
+    r = subprocess.run(base + ["--show-log"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = read_fasta(out)
+    assert list(got) == ["contained", "normal"]
+    assert "too few relatives" in r.stderr and "1 sequences were not aligned" in r.stderr
+    w1, res1 = oracle_strings(orc, msa, [O.encode(sub)], {})
+    assert res1[0].status == 1 and got["contained"] == w1[0]
+    assert "copied alignment" in r.stderr
+    r = subprocess.run(base + ["--realign"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0
+    w2, res2 = oracle_strings(orc, msa, [O.encode(sub)], dict(realign=1))
+    assert res2[0].status == 0 and read_fasta(out)["contained"] == w2[0]

@@ -1,0 +1,75 @@
+"""Host-side mirror of the reference's stage interfaces (sina_b200/host): unit checks with the reference's own
+cseq vectors, the option surface, and the loud failure without a GPU. No device needed."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "sina_b200", "bin")
+
+
+def have_gpu():
+    import sina_b200
+    try:
+        return sina_b200.device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    if not os.path.exists(os.path.join(BIN, "sina")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "sina_b200", "host"), "-j", "4"], check=True, capture_output=True)
+
+
+def run(args, **kw):
+    return subprocess.run([os.path.join(BIN, args[0])] + args[1:], capture_output=True, text=True, timeout=120, **kw)
+
+
+def test_host_unit(tmp_path):
+    r = run(["host_unit", str(tmp_path)])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("ok ")
+
+
+def test_cli_help_and_version():
+    r = run(["sina", "--help"])
+    assert r.returncode == 0
+    for name in ("--db", "--fs-engine", "--fs-kmer-len", "--fs-min", "--fs-max", "--fs-msc", "--fs-req", "-i [ --in ]", "-o [ --out ]"):
+        assert name in r.stderr, name
+    r = run(["sina", "--help-all"])
+    for name in ("--pen-gap", "--pen-gapext", "--match-score", "--mismatch-score", "--overhang", "--lowercase", "--insertion",
+                 "--fs-kmer-no-fast", "--fs-kmer-mm", "--fs-msc-max", "--fs-leave-query-out", "--realign", "--fs-weight",
+                 "--preserve-order", "--max-in-flight"):
+        assert name in r.stderr, name
+    assert run(["sina", "--version"]).returncode == 0
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["--fs-engine", "pt-server", "--db", "x"], "pt-server is not supported"),
+    (["--db", "x", "--fs-no-graph"], "not supported"),
+    (["--db", "x", "--use-subst-matrix"], "not supported"),
+    (["--db", "x", "--filter", "f"], "not supported"),
+    (["--db", "x", "--insertion", "forbid"], "forbid is not supported"),
+    (["--db", "x", "--search"], "not supported"),
+    (["--db", "x", "--fs-msc-max", "0.9"], "identity filter"),
+    (["--db", "x", "--bogus"], "unrecognised option"),
+    (["-i", "q"], "Must have reference database"),
+])
+def test_cli_rejects(args, msg):
+    """unsupported reference options are rejected (exit 1, like a reference configuration error), never ignored"""
+    r = run(["sina"] + args)
+    assert r.returncode == 1
+    assert msg in r.stderr, r.stderr
+
+
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    if have_gpu():
+        pytest.skip("a CUDA device is present")
+    q, d = tmp_path / "q.fa", tmp_path / "r.fa"
+    q.write_text(">q\nAGCU\n")
+    d.write_text(">r\nAG-CU\n")
+    r = run(["sina", "-i", str(q), "--db", str(d)])
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+    assert r.stdout == ""  # nothing was "aligned" by some fallback
