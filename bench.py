@@ -84,35 +84,58 @@ def make_data(args, rank):
     return tree, m, c, o, qm, qo
 
 
-def cpu_baseline(args, m, c, o, qm, qo, nsample, nthreads=0):
-    """reference's own CPU code (oracle/_ref, kind 'reference') or the C port (kind 'port') on a bounded
-    sample of the same workload, all host cores. Returns dict(value seq/s, cores, kind, sample, mcells_s)."""
-    from oracle import oracle as O
-    nsample = min(nsample, len(qo) - 1)
-    sub_off = (qo[:nsample + 1] - qo[0]).astype(np.uint64)
-    sub_m = qm[int(qo[0]):int(qo[nsample])]
-    msa = O.MSA(m, c, o, W_COLS)
-    kind = "reference" if os.path.exists(O.REF_SO) else "port"
-    if kind == "reference":
-        ref = O.Ref()
-        db = ref.db(msa)
-        ix = ref.kidx_build(db, KMER, 0)
-        queries = [O.decode(sub_m[int(sub_off[i]):int(sub_off[i + 1])]) for i in range(nsample)]
-        t0 = time.perf_counter()
-        res, oc, qoff, cells, posts, nt = ref.run_batch(ix, queries, O.FamParams(), O.AlignParams(), nthreads=nthreads)
-        dt = time.perf_counter() - t0
-        ref.kidx_free(ix)
-        ref.db_free(db)
-    else:
-        orc = O.Oracle()
-        ix = orc.index_build(msa, KMER, 0)
-        t0 = time.perf_counter()
-        res, oc, om, cells, posts, nt = orc.run_batch(ix, msa, sub_m, sub_off, O.FamParams(), O.AlignParams(), nthreads=nthreads)
-        dt = time.perf_counter() - t0
-        orc.index_free(ix)
-    return {"value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": kind,
-            "sample": "%d of the step's %s queries vs the same %d-row index, whole path, %.1f s" % (nsample, args.kind, args.refs, dt),
-            "mcells_per_s": cells / dt / 1e6, "seconds": dt}
+class CpuPath:
+    """The reference's own CPU code (oracle/_ref, kind 'reference') or, where that binary is absent, the C port
+    (kind 'port'), with its database and k-mer index built once. run() times the whole path (family finding +
+    graph + DP + backtrack + gap placement) over a bounded sample of queries on all host cores."""
+
+    def __init__(self, args, m, c, o):
+        from oracle import oracle as O
+        self.O, self.args = O, args
+        self.msa = O.MSA(m, c, o, W_COLS)
+        self.kind = "reference" if os.path.exists(O.REF_SO) else "port"
+        if self.kind == "reference":
+            self.ref = O.Ref()
+            self.db = self.ref.db(self.msa)
+            self.ix = self.ref.kidx_build(self.db, KMER, 0)
+        else:
+            self.orc = O.Oracle()
+            self.ix = self.orc.index_build(self.msa, KMER, 0)
+
+    def run(self, qm, qo, nsample, nthreads=0):
+        O = self.O
+        nsample = min(nsample, len(qo) - 1)
+        sub_off = (qo[:nsample + 1] - qo[0]).astype(np.uint64)
+        sub_m = qm[int(qo[0]):int(qo[nsample])]
+        if self.kind == "reference":
+            queries = [O.decode(sub_m[int(sub_off[i]):int(sub_off[i + 1])]) for i in range(nsample)]
+            t0 = time.perf_counter()
+            res, oc, qoff, cells, posts, nt = self.ref.run_batch(self.ix, queries, O.FamParams(), O.AlignParams(), nthreads=nthreads)
+            dt = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            res, oc, om, cells, posts, nt = self.orc.run_batch(self.ix, self.msa, sub_m, sub_off, O.FamParams(), O.AlignParams(), nthreads=nthreads)
+            dt = time.perf_counter() - t0
+        return {"value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": self.kind,
+                "sample": "%d of the step's %s queries vs the same %d-row index, whole path, %.1f s on %d threads"
+                          % (nsample, self.args.kind, self.args.refs, dt, int(nt)),
+                "mcells_per_s": cells / dt / 1e6, "seconds": dt}
+
+    def close(self):
+        if self.kind == "reference":
+            self.ref.kidx_free(self.ix)
+            self.ref.db_free(self.db)
+        else:
+            self.orc.index_free(self.ix)
+
+
+def cpu_sample_size(args):
+    """bounded sample: about 10-30 s of CPU work for the bench's own arm, a few seconds per step for --impl reference"""
+    if args.cpu_sample:
+        return args.cpu_sample
+    per_core = 6.0 if args.kind == "full" else 60.0   # measured order of magnitude, sequences/s per host core
+    target_s = 12.0 if args.impl == "ours" else 4.0
+    return int(max(16, min(args.queries, per_core * (os.cpu_count() or 1) * target_s)))
 
 
 def run_reference(args):
@@ -121,16 +144,17 @@ def run_reference(args):
     if rank != 0:
         return
     tree, m, c, o, qm, qo = make_data(args, 0)
-    ncores = os.cpu_count() or 1
-    nsample = args.cpu_sample or max(16, 4 * ncores)
+    nsample = cpu_sample_size(args)
+    cpu = CpuPath(args, m, c, o)
     times, last = [], None
     for it in range(args.warmup + args.steps):
         # each step = a bounded sample of the workload (different queries every step)
         a = (it * nsample) % max(1, args.queries - nsample)
-        sub = cpu_baseline(args, m, c, o, qm, qo[a:], nsample)
+        sub = cpu.run(qm, qo[a:], nsample)
         if it >= args.warmup:
             times.append(sub["seconds"])
             last = sub
+    cpu.close()
     t = float(np.mean(times))
     val = nsample / t
     line = {"impl": "reference", "metric": "sequences aligned/sec", "value": val, "unit": "sequences/s",
@@ -144,11 +168,13 @@ def run_reference(args):
 
 
 def workload_config(args, queries_per_step):
-    return {"workload": "%d %s 16S queries (~%d nt) per step per GPU vs synthetic %d-seq reference MSA (%d columns), "
+    return {"workload": "BASELINE configs[1]: %d %s 16S queries (~%d nt) per step per GPU vs synthetic %d-seq reference MSA (%d columns), "
                         "k=%d fast, fs-max 40, reference defaults" % (queries_per_step, "full-length" if args.kind == "full" else "V4",
                                                                      1500 if args.kind == "full" else 280, args.refs, W_COLS, KMER),
             "queries_per_step_per_gpu": queries_per_step, "refs": args.refs, "columns": W_COLS, "k": KMER,
-            "l2": "inputs larger than L2 (index 0.4 GB + >10 GB traceback written per step)",
+            "l2": "inputs larger than L2 (index 0.4 GB + >30 GB traceback written per step)",
+            "timing": "host clock between device-wide synchronisations (the library runs on its own streams); per-stage "
+                      "times are CUDA events on the launching streams and overlap across the chunk pipeline",
             "parallelism": "queries sharded over GPUs, index replicated, no collective"}
 
 
@@ -216,6 +242,25 @@ def main():
     sampler.join(timeout=2)
     n_ok = int((res["status"] == 0).sum())
 
+    # ---- kernel-only pass: one workspace / one stream, so that the CUDA events bracket every kernel alone
+    # (in the timed region above the chunks of two workspaces overlap and the per-stage event times include
+    # whatever ran beside them)
+    sess.close()
+    os.environ["SG_STREAMS"] = "1"
+    nq_iso = min(nq, 4096)
+    iso = sina_b200.Session(ix, nq_iso, int(qo[nq_iso]))
+    iso.upload(qm[:int(qo[nq_iso])], qo[:nq_iso + 1])
+    iso.family(fp)
+    iso.align(ap)
+    iso.sync()
+    iso.stats(reset=True)
+    iso.family(fp)
+    iso.align(ap)
+    iso.sync()
+    st_iso = iso.stats()
+    iso.close()
+    os.environ.pop("SG_STREAMS", None)
+
     if world > 1:
         tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -237,16 +282,26 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         total_q = nq * args.steps * world
         value = total_q / dt
-        # dominant kernel: mesh DP. Algorithmic bytes = 1 B packed traceback per cell, this rank.
-        dp_s = st["ms_dp"] / 1e3
+        # dominant kernel: mesh DP (mesh_v2_kernel). Algorithmic bytes = 1 B packed traceback per cell;
+        # duration = CUDA events around the kernel on its stream in the kernel-only pass, this rank.
+        dp_s = st_iso["ms_dp"] / 1e3
+        cells_iso = float(st_iso["cells"])
+        gcups = cells_iso / dp_s / 1e9 if dp_s > 0 else 0.0
+        dp_live_s = st["ms_dp"] / 1e3
         cells = float(st["cells"])
-        gcups = cells / dp_s / 1e9 if dp_s > 0 else 0.0
         sm_mhz = sampler.summary().get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
         ops_per_cell = 3 + 7 * 1.65
-        issue_ceiling = 148 * 128 * sm_mhz * 1e6 / ops_per_cell / 1e9  # GCUPS at the measured clock
-        find_s = st["ms_find"] / 1e3
-        posts = float(st["postings"])
-        kmer_bytes = 4.0 * posts + (2.0 * args.refs + 8.0 * 41) * nq * args.steps
+        issue_ceiling = 148 * 128 * sm_mhz * 1e6 / ops_per_cell / 1e9  # GCUPS at the measured clock (SURVEY §8d)
+        find_s = st_iso["ms_find"] / 1e3
+        posts = float(st_iso["postings"])
+        kmer_bytes = 4.0 * posts + (2.0 * args.refs + 8.0 * 41) * nq_iso
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["mesh_v2_kernel"]
+            traffic = tj["dram_bytes_per_query"] * min(1024, nq_iso) / 1e9   # GB per launch of one 1024-query chunk
+        except Exception:
+            pass
+        launches_iso = max(1, -(-nq_iso // 1024))
         line = {
             "metric": "sequences aligned/sec", "value": value, "unit": "sequences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -255,27 +310,33 @@ def main():
             "e2e": {"value": total_q / dt_e2e, "unit": "sequences/s", "h2d_bytes_per_step": int(len(qm) + qo.nbytes),
                     "d2h_bytes_per_step": int(oc.nbytes + om.nbytes + res.nbytes)},
             "gpu_launches": int(st["kernel_launches"]),
-            "roofline": {"kernel": "mesh_kernel", "bound": "hbm", "achieved": cells * 1.0 / dp_s / 1e9 if dp_s > 0 else 0.0,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": (cells / dp_s / 1e9 / hbm_peak) if dp_s > 0 else 0.0,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "DP is issue/latency bound, not HBM bound: see gcups vs issue_ceiling_gcups",
-                         "gcups": gcups, "issue_ceiling_gcups": issue_ceiling,
+            "roofline": {"kernel": "mesh_v2_kernel", "bound": "hbm", "achieved": gcups * 1.0,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": gcups / hbm_peak,
+                         "traffic": traffic, "traffic_unit": "GB per launch (1024-query chunk), ncu dram read+write",
+                         "algorithmic_gb_per_launch": cells_iso / launches_iso / 1e9,
+                         "peak_source": peak_src,
+                         "note": "1 B of traceback per cell is the only mandatory HBM traffic, so the HBM fraction is low by "
+                                 "construction: the kernel is bound by the ALU pipe (fp32 compare/select) and barrier latency; "
+                                 "see gcups vs issue_ceiling_gcups and profiles/",
+                         "gcups": gcups, "gcups_in_pipeline": cells / dp_live_s / 1e9 if dp_live_s > 0 else 0.0,
+                         "issue_ceiling_gcups": issue_ceiling,
                          "frac_issue": gcups / issue_ceiling if issue_ceiling else None,
+                         "duration_ms_per_launch": st_iso["ms_dp"] / launches_iso,
                          "share_of_step": st["ms_dp"] / (dt * 1e3)},
             "roofline_kmer": {"kernel": "find_tile_kernel", "bound": "hbm", "achieved": kmer_bytes / find_s / 1e9 if find_s > 0 else 0.0,
                               "peak": hbm_peak, "unit": "GB/s", "frac": (kmer_bytes / find_s / 1e9 / hbm_peak) if find_s > 0 else 0.0,
-                              "bytes_per_query": "4*P + 2*N + 8*max", "postings_per_query": posts / (nq * args.steps)},
+                              "bytes_per_query": "4*P + 2*N + 8*max", "postings_per_query": posts / nq_iso},
+            "stages_ms_per_step_isolated": {k: st_iso[k] * (nq / nq_iso) for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
             "cells_per_query": cells / (nq * args.steps), "aligned_ok": n_ok,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
-            ncores = os.cpu_count() or 1
-            nsample = args.cpu_sample or max(16, 4 * ncores)
-            cb = cpu_baseline(args, m, c, o, qm, qo, nsample)
+            cpu = CpuPath(args, m, c, o)
+            cb = cpu.run(qm, qo, cpu_sample_size(args))
+            cpu.close()
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s")}
         print(json.dumps(line))
-    sess.close()
     ix.close()
     if world > 1:
         dist.destroy_process_group()
