@@ -157,23 +157,38 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
 
     // ---- 0. item offsets of the family rows
     for (uint32_t i = tid; i < words; i += nt) bitmap[i] = 0;
-    if (tid == 0) {
-        uint32_t o = 0;
-        for (uint32_t j = 0; j < F; j++) { famoff[j] = o; o += (uint32_t)(A.row_off[fam[j] + 1] - A.row_off[fam[j]]); }
-        famoff[F] = o;
+    uint32_t* rb32 = shv + 8 + 2 * FARLIST_CAP + 2 * DP_G;
+    if (reinterpret_cast<uintptr_t>(rb32) & 7u) rb32++;
+    uint64_t* rowbase = reinterpret_cast<uint64_t*>(rb32);  // [fam_cap] first item of family row j in the index
+    for (uint32_t j = tid; j < F; j += nt) {
+        const uint64_t a = A.row_off[fam[j]];
+        rowbase[j] = a;
+        famoff[j] = (uint32_t)(A.row_off[fam[j] + 1] - a);
     }
     __syncthreads();
-    const uint32_t I = famoff[F];
+    const uint32_t I = scan_array_inplace(famoff, F, red);
+    if (tid == 0) famoff[F] = I;
+    __syncthreads();
     if (I > A.icap || F == 0) { if (tid == 0) hdr->status = F == 0 ? (uint32_t)SG_Q_SKIPPED : GS_LIMIT; return; }
+    // flat iteration over the family's items, 4 per thread and round so that the global loads of a round are all in
+    // flight together: item x of the concatenation belongs to row j = upper_bound(famoff, x) - 1
+    auto row_of = [&](uint32_t x) -> uint32_t {
+        uint32_t lo = 0, hi = F;   // famoff[lo] <= x < famoff[hi]
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (famoff[mid] <= x) lo = mid; else hi = mid; }
+        return lo;
+    };
 
     // ---- 1. used-column bitmap and column ranks (= the sweep's `min_next` column order, mseq.cpp:76-84)
-    for (uint32_t j = 0; j < F; j++) {
-        const uint64_t a = A.row_off[fam[j]];
-        const uint32_t len = famoff[j + 1] - famoff[j];
-        for (uint32_t i = tid; i < len; i += nt) {
-            uint32_t c = A.cols[a + i];
-            atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
+        uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t x = x0 + u * nt;
+            c[u] = NONE;
+            if (x < I) { const uint32_t j = row_of(x); c[u] = A.cols[rowbase[j] + (x - famoff[j])]; }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (c[u] != NONE) atomicOr(&bitmap[c[u] >> 5], 1u << (c[u] & 31));
     }
     __syncthreads();
     for (uint32_t i = tid; i < words; i += nt) wrank[i] = __popc(bitmap[i]);
@@ -189,11 +204,28 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     // ---- 2. column table: tab[c][j] = base mask of family row j in column rank c
     for (uint32_t i = tid; i < n_cols * A.fam_cap; i += nt) tab[i] = 0;
     __syncthreads();
-    for (uint32_t j = 0; j < F; j++) {
-        const uint64_t a = A.row_off[fam[j]];
-        const uint32_t len = famoff[j + 1] - famoff[j];
-        for (uint32_t i = tid; i < len; i += nt)
-            tab[(uint64_t)colrank(A.cols[a + i]) * A.fam_cap + j] = A.masks[a + i] & 31u;
+    // (the column rank of every item is kept in item_node until the nodes exist)
+    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
+        uint32_t c[4], j[4];
+        uint8_t mk[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t x = x0 + u * nt;
+            c[u] = NONE;
+            if (x < I) {
+                j[u] = row_of(x);
+                const uint64_t at = rowbase[j[u]] + (x - famoff[j[u]]);
+                c[u] = A.cols[at];
+                mk[u] = A.masks[at];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (c[u] == NONE) continue;
+            const uint32_t r = colrank(c[u]);
+            tab[(uint64_t)r * A.fam_cap + j[u]] = mk[u] & 31u;
+            item_node[x0 + u * nt] = r;
+        }
     }
     __syncthreads();
 
@@ -240,23 +272,40 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
     scan_array_inplace(slotbase, V, red);
     if (tid == 0) slotbase[V] = I;
-    for (uint32_t j = 0; j < F; j++) {
-        const uint64_t a = A.row_off[fam[j]];
-        const uint32_t len = famoff[j + 1] - famoff[j];
-        for (uint32_t i = tid; i < len; i += nt) {
-            uint32_t c = colrank(A.cols[a + i]);
-            item_node[famoff[j] + i] = colbase[c] + tabli[(uint64_t)c * A.fam_cap + j];
+    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
+        uint32_t r[4], j[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t x = x0 + u * nt;
+            r[u] = NONE;
+            if (x < I) { j[u] = row_of(x); r[u] = item_node[x]; }
         }
+        uint32_t cb[4], li[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (r[u] != NONE) { cb[u] = colbase[r[u]]; li[u] = tabli[(uint64_t)r[u] * A.fam_cap + j[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (r[u] != NONE) item_node[x0 + u * nt] = cb[u] + li[u];
     }
     __syncthreads();
-    for (uint32_t j = 0; j < F; j++) {
-        const uint32_t len = famoff[j + 1] - famoff[j];
-        for (uint32_t i = tid; i < len; i += nt) {
-            uint32_t node = item_node[famoff[j] + i];
-            uint32_t from = i ? item_node[famoff[j] + i - 1] : NONE;
-            uint32_t p = atomicAdd(&cursor[node], 1u);
-            slot[slotbase[node] + p] = from;
-            if (from != NONE) nflags[from] = 1;  // has a successor (benign same-value race)
+    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
+        uint32_t node[4], from[4], pos[4], sb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t x = x0 + u * nt;
+            node[u] = NONE;
+            if (x < I) {
+                const uint32_t j = row_of(x);
+                node[u] = item_node[x];
+                from[u] = x > famoff[j] ? item_node[x - 1] : NONE;   // previous item of the same family row
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (node[u] != NONE) { pos[u] = atomicAdd(&cursor[node[u]], 1u); sb[u] = slotbase[node[u]]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (node[u] == NONE) continue;
+            slot[sb[u] + pos[u]] = from[u];
+            if (from[u] != NONE) nflags[from[u]] = 1;  // has a successor (benign same-value race)
         }
     }
     __syncthreads();
@@ -266,14 +315,26 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     for (uint32_t m = tid; m < V; m += nt) {
         uint32_t* sl = slot + slotbase[m];
         const uint32_t n = slotbase[m + 1] - slotbase[m];
-        for (uint32_t x = 1; x < n; x++) {  // insertion sort (n <= family size)
-            uint32_t key = sl[x];
-            int y = (int)x - 1;
-            while (y >= 0 && sl[y] > key) { sl[y + 1] = sl[y]; y--; }
-            sl[y + 1] = key;
-        }
+        // sorted list of the distinct predecessors, built in thread-local memory (n <= family size, and most of the
+        // n candidates repeat one of a handful of nodes)
+        uint32_t u[FAM_CAP_MAX + 1];
         uint32_t deg = 0;
-        for (uint32_t x = 0; x < n; x++) if (sl[x] != NONE && (x == 0 || sl[x] != sl[x - 1])) sl[deg++] = sl[x];
+        for (uint32_t x0 = 0; x0 < n; x0 += 4) {
+            uint32_t key[4];
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) key[k2] = x0 + k2 < n ? sl[x0 + k2] : NONE;
+#pragma unroll
+            for (int k2 = 0; k2 < 4; k2++) {
+                if (key[k2] == NONE) continue;
+                uint32_t y = deg;
+                while (y > 0 && u[y - 1] > key[k2]) y--;
+                if (y > 0 && u[y - 1] == key[k2]) continue;
+                for (uint32_t z = deg; z > y; z--) u[z] = u[z - 1];
+                u[y] = key[k2];
+                deg++;
+            }
+        }
+        for (uint32_t x = 0; x < deg; x++) sl[x] = u[x];
         pred_off[m] = deg;
         my_max = max(my_max, deg);
     }
@@ -473,7 +534,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;
-    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G) * 4;
+    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + 1 + 2 * s->fam_cap) * 4;
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
