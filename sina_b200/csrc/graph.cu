@@ -170,25 +170,21 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     if (tid == 0) famoff[F] = I;
     __syncthreads();
     if (I > A.icap || F == 0) { if (tid == 0) hdr->status = F == 0 ? (uint32_t)SG_Q_SKIPPED : GS_LIMIT; return; }
-    // flat iteration over the family's items, 4 per thread and round so that the global loads of a round are all in
-    // flight together: item x of the concatenation belongs to row j = upper_bound(famoff, x) - 1
-    auto row_of = [&](uint32_t x) -> uint32_t {
-        uint32_t lo = 0, hi = F;   // famoff[lo] <= x < famoff[hi]
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (famoff[mid] <= x) lo = mid; else hi = mid; }
-        return lo;
-    };
-
+    // item passes: one warp per family row at a time, 4 items per lane and round so that the global loads of a
+    // round are all in flight together. ROW_ITEMS(body) runs body(x, at, u) for item x (flat index over the family),
+    // `at` = its position in the index arrays.
+    const uint32_t wid = warp_id(), nwarp = nt >> 5, lane = lane_id();
     // ---- 1. used-column bitmap and column ranks (= the sweep's `min_next` column order, mseq.cpp:76-84)
-    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
-        uint32_t c[4];
+    for (uint32_t j = wid; j < F; j += nwarp) {
+        const uint64_t a = rowbase[j];
+        const uint32_t len = famoff[j + 1] - famoff[j];
+        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+            uint32_t c[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t x = x0 + u * nt;
-            c[u] = NONE;
-            if (x < I) { const uint32_t j = row_of(x); c[u] = A.cols[rowbase[j] + (x - famoff[j])]; }
+            for (int u = 0; u < 4; u++) c[u] = i0 + 32 * u < len ? A.cols[a + i0 + 32 * u] : NONE;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (c[u] != NONE) atomicOr(&bitmap[c[u] >> 5], 1u << (c[u] & 31));
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (c[u] != NONE) atomicOr(&bitmap[c[u] >> 5], 1u << (c[u] & 31));
     }
     __syncthreads();
     for (uint32_t i = tid; i < words; i += nt) wrank[i] = __popc(bitmap[i]);
@@ -205,26 +201,24 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     for (uint32_t i = tid; i < n_cols * A.fam_cap; i += nt) tab[i] = 0;
     __syncthreads();
     // (the column rank of every item is kept in item_node until the nodes exist)
-    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
-        uint32_t c[4], j[4];
-        uint8_t mk[4];
+    for (uint32_t j = wid; j < F; j += nwarp) {
+        const uint64_t a = rowbase[j];
+        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+            uint32_t c[4];
+            uint8_t mk[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t x = x0 + u * nt;
-            c[u] = NONE;
-            if (x < I) {
-                j[u] = row_of(x);
-                const uint64_t at = rowbase[j[u]] + (x - famoff[j[u]]);
-                c[u] = A.cols[at];
-                mk[u] = A.masks[at];
+            for (int u = 0; u < 4; u++) {
+                c[u] = NONE;
+                if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (c[u] == NONE) continue;
-            const uint32_t r = colrank(c[u]);
-            tab[(uint64_t)r * A.fam_cap + j[u]] = mk[u] & 31u;
-            item_node[x0 + u * nt] = r;
+            for (int u = 0; u < 4; u++) {
+                if (c[u] == NONE) continue;
+                const uint32_t r = colrank(c[u]);
+                tab[(uint64_t)r * A.fam_cap + j] = mk[u] & 31u;
+                item_node[fo + i0 + 32 * u] = r;
+            }
         }
     }
     __syncthreads();
@@ -272,40 +266,40 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
     scan_array_inplace(slotbase, V, red);
     if (tid == 0) slotbase[V] = I;
-    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
-        uint32_t r[4], j[4];
+    for (uint32_t j = wid; j < F; j += nwarp) {
+        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+            uint32_t r[4], cb[4], li[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t x = x0 + u * nt;
-            r[u] = NONE;
-            if (x < I) { j[u] = row_of(x); r[u] = item_node[x]; }
+            for (int u = 0; u < 4; u++) r[u] = i0 + 32 * u < len ? item_node[fo + i0 + 32 * u] : NONE;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (r[u] != NONE) { cb[u] = colbase[r[u]]; li[u] = tabli[(uint64_t)r[u] * A.fam_cap + j]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (r[u] != NONE) item_node[fo + i0 + 32 * u] = cb[u] + li[u];
         }
-        uint32_t cb[4], li[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (r[u] != NONE) { cb[u] = colbase[r[u]]; li[u] = tabli[(uint64_t)r[u] * A.fam_cap + j[u]]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (r[u] != NONE) item_node[x0 + u * nt] = cb[u] + li[u];
     }
     __syncthreads();
-    for (uint32_t x0 = tid; x0 < I; x0 += 4 * nt) {
-        uint32_t node[4], from[4], pos[4], sb[4];
+    for (uint32_t j = wid; j < F; j += nwarp) {
+        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+            uint32_t node[4], from[4], pos[4], sb[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t x = x0 + u * nt;
-            node[u] = NONE;
-            if (x < I) {
-                const uint32_t j = row_of(x);
-                node[u] = item_node[x];
-                from[u] = x > famoff[j] ? item_node[x - 1] : NONE;   // previous item of the same family row
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = i0 + 32 * u;
+                node[u] = NONE;
+                if (i < len) {
+                    node[u] = item_node[fo + i];
+                    from[u] = i ? item_node[fo + i - 1] : NONE;   // previous item of the same family row
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (node[u] != NONE) { pos[u] = atomicAdd(&cursor[node[u]], 1u); sb[u] = slotbase[node[u]]; }
+            for (int u = 0; u < 4; u++) if (node[u] != NONE) { pos[u] = atomicAdd(&cursor[node[u]], 1u); sb[u] = slotbase[node[u]]; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (node[u] == NONE) continue;
-            slot[sb[u] + pos[u]] = from[u];
-            if (from[u] != NONE) nflags[from[u]] = 1;  // has a successor (benign same-value race)
+            for (int u = 0; u < 4; u++) {
+                if (node[u] == NONE) continue;
+                slot[sb[u] + pos[u]] = from[u];
+                if (from[u] != NONE) nflags[from[u]] = 1;  // has a successor (benign same-value race)
+            }
         }
     }
     __syncthreads();
