@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     const uint32_t T = DP_T;
     const uint16_t* nthr = A.nthr + io;
     const uint8_t* nshift = A.nshift + io;
-    const bool sorted = h.mode == 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
+    const bool sorted = h.mode >= 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
 
     // decoded traceback cell: src | ord<<8 | chosen_open<<2 | last_open<<3 | ins_open<<4 (the wide layout)
     auto cell = [&](uint32_t m, uint32_t s) -> uint32_t {
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
             const uint32_t w = tbq[gi.tb_off + (uint64_t)(t >> 1) * T + tid];
             return (w >> (16 * (t & 1))) & 0xffffu;
         }
-        const uint32_t w = tbq[gi.tb_off + (uint64_t)(t >> 2) * T + tid];
-        const uint32_t c = (w >> (8 * (t & 3))) & 0xffu;
+        const uint16_t* tb16 = reinterpret_cast<const uint16_t*>(tbq + gi.tb_off);
+        const uint32_t c = ((uint32_t)tb16[(uint64_t)(t >> 1) * T + tid] >> (8 * (t & 1))) & 0xffu;
         return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2) | (((c >> 6) & 1u) << 3) | (((c >> 7) & 1u) << 4);
     };
     auto gaps_idx = [&](uint32_t m, uint32_t s) -> uint32_t {
@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
         else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(m, s); }
         else {
             const uint32_t p = preds[pred_off[m] + ord];
-            nm = (c & 4u) ? p : gapm_idx(p, s);
+            // deletion opened at p? For the last predecessor that is the cell's last-opened bit (the specialised
+            // DP step does not set the chosen-opened bit for its last slot)
+            const bool opened = (c & 4u) || (ord + 1 == pred_off[m + 1] - pred_off[m] && (c & 8u));
+            nm = opened ? p : gapm_idx(p, s);
             ns = s;
         }
     };

@@ -42,7 +42,8 @@ constexpr int GHOST_LEAD = 6;                // a ghost trails its source row by
 constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan can hold
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
 
-// traceback byte / halfword layout (mesh.cu writes, backtrack.cu decodes)
+// traceback cell layout (mesh.cu writes, backtrack.cu decodes); cells of two consecutive steps share one store:
+// tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells
 constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH = 3;
 // u8 : [1:0] src  [4:2] pred ordinal  [5] chosen deletion opened  [6] last pred's deletion opened  [7] insertion opened
 // u16: [1:0] src  [2] chosen-open [3] last-open [4] ins-open  [15:8] pred ordinal
@@ -70,7 +71,8 @@ struct Index {
 struct GraphHdr {
     uint32_t V, E, n_cols, n_groups;
     uint32_t n_last, n_spill, max_indeg, wide;  // wide: traceback uses u16 cells
-    uint32_t mode, pad0;  // DP kernel: 2 = sorted rows + ghost columns (mesh_v2), 1 = generic fallback (mesh_v1)
+    uint32_t mode;       // DP kernel: 2 / 3 = sorted rows + ghost columns (mesh_v2 with 8 / 16 query-table planes), 1 = generic fallback (mesh_v1)
+    uint32_t maskset;    // bit b set iff some node has IUPAC mask b (1..15); the v2 kernel keeps one query-table plane per mask
     uint64_t tb_off;     // offset (in 4-byte words) of this query's traceback in the arena
     uint64_t spill_off;  // offset (in float2) of this query's spill rows in the arena
     uint32_t status;     // 0 ok, else SG_Q_* / internal failure code (see GS_*)

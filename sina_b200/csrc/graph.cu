@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     const uint32_t V = scan_array_inplace(colbase, n_cols, red);
     if (tid == 0) colbase[n_cols] = V;
     if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+    uint32_t my_masks = 0;   // IUPAC masks (case ignored) of the nodes this thread creates
+    if (tid == 0) shv[4] = 0;
     for (uint32_t c = tid; c < n_cols; c += nt) {
         uint32_t seen = 0, nn = 0;
         uint8_t li_of[32];
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         const uint32_t base = colbase[c], col = colof[c];
         for (uint32_t k2 = 0; k2 < nn; k2++) {
             const uint32_t m = base + k2;
+            my_masks |= 1u << (nm[k2] & 15u);
             ncol[m] = col; nmask[m] = nm[k2]; ncount[m] = cnt[k2]; nsigma[m] = c;
             // node->weight = 1.0/(weight+1) + weight * (node->weight/num_seqs)   (mseq.cpp:111-116)
             float fr = __fdiv_rn((float)cnt[k2], (float)F);
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         }
     }
     __syncthreads();
+    if (my_masks) atomicOr(&shv[4], my_masks);
 
     // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
     scan_array_inplace(slotbase, V, red);
@@ -436,7 +440,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
                 uint32_t j = 0;
                 while (j < ng && !(gh_p[j] == p && gh_b[j] == bk)) j++;
                 if (j == ng) {
-                    if (ng == DP_G) { shv[1] = 1; j = 0; }
+                    if (ng == DP_G - 1) { shv[1] = 1; j = 0; }   // the last loader column is the DP's constant edge column
                     else { gh_p[ng] = p; gh_b[ng] = bk; ng++; }
                 }
                 far_gi[i] = j;
@@ -490,7 +494,8 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         const uint64_t sp_off = atomicAdd(&A.cursors[1], (unsigned long long)spill_need);
         hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;
         hdr->n_last = n_last; hdr->n_spill = n_spill; hdr->max_indeg = max_indeg; hdr->wide = wide;
-        hdr->mode = (shv[1] || A.force_generic) ? 1u : 2u;
+        hdr->maskset = shv[4];
+        hdr->mode = (shv[1] || A.force_generic) ? 1u : (__popc(shv[4]) > 8 ? 3u : 2u);
         hdr->tb_off = tb_off; hdr->spill_off = sp_off;
         if (tb_off + words_total > A.tb_words || sp_off + spill_need > A.spill_elems) hdr->status = GS_ARENA_FULL;
         else atomicAdd(A.cells, (unsigned long long)V * Lq);

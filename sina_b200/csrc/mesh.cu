@@ -68,119 +68,175 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
     return r;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+    return r;
+}
 template <uint32_t OFF>
 __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
     asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y), "n"(OFF) : "memory");
 }
 
-// One group for the lanes of a warp whose rows all have <= NPW predecessors. Slots are right-aligned: a row
-// with np < NPW repeats its first predecessor in the NPW-np leading slots (a repeated candidate ties with
-// its first copy and strict '<' keeps the first, so nothing changes; backtrack maps slot -> ordinal with
-// max(0, slot - shift)). Rows without predecessor get dgp = dgpe = msw = mmsw = +inf so that no deletion or
-// match candidate can win, and has_real = false keeps gapm_val at its edge value.
-// The row computes query position s = t - t_first at step t (t_first = its column rank offset in the group);
-// qrow = query - t_first, so qrow[t] is the query base of that position. Lanes without a row have
-// t_first = t_last = ~0: whatever they compute is never read.
-template <int NPW, bool WIDE>
-__device__ __forceinline__ void v2_fast_group(const MeshArgs& A, uint32_t sring, uint32_t qrow,
-                                              uint32_t steps4, const uint32_t* ck, float dgp, float dgpe,
-                                              uint32_t t_first, uint32_t t_last, uint32_t w_first, uint32_t w_last,
-                                              float initv, bool has_real,
-                                              uint32_t mask, float msw, float mmsw, float* lastcol_ptr, uint32_t* tbg) {
-    const float gp = A.gp, gpe = A.gpe;
+// Per-lane constants of the specialised step.
+template <int NPW>
+struct V2Lane {
+    uint32_t pk[NPW];        // shared-window byte address of predecessor slot k at time slot 0
+    uint32_t wadr;           // own ring column
+    uint32_t qrow;           // query-table address of (position 0, plane of the node's mask) minus 8*t_first
+    uint32_t mmsw_bits, dsc; // PLANES > 1: bits of mismatch*weight, and bits(match*weight) - bits(mismatch*weight)
+    float msw, mmsw;         // PLANES == 1: (mis)match score * weight (+inf for rows without predecessor)
+    uint32_t mask;           // PLANES == 1: the node's IUPAC mask
+    float dgp, dgpe;         // gap penalties (0 for rows without predecessor, see below)
+    float initv;
+    uint32_t t_first, t_last;
+    float* lastcol_ptr;
+};
+
+// Two steps t0, t0+1 of one group for the lanes of a warp whose rows all have <= NPW predecessors.
+// Slots are right-aligned: a row with np < NPW repeats its first predecessor in the NPW-np leading slots (a
+// repeated candidate ties with its first copy and strict '<' keeps the first, so nothing changes; backtrack maps
+// slot -> ordinal with max(0, slot - shift)).
+// Rows without predecessor read the constant ring column (value 1, gapm +inf) with dgp = dgpe = 0: the deletion
+// candidate is exactly 1, never below the initial 1, and leaves gapm_val = 1 (init_edge, mesh.h:294-301); their match
+// score is +inf (mmsw_bits = +inf, dsc = 0), so no match candidate can win either.
+// The match score is read from the query table as a 0/1 byte and turned into the float's bits with integer
+// arithmetic (exact, and off the ALU pipe that bounds this kernel).
+// EDGES: some lane may be at s == 0 or s == Lq-1 in these steps; the other (vast majority of) steps skip those tests.
+template <int NPW, bool WIDE, bool EDGES, int PLANES>
+__device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
+                                          float (&pvp)[NPW], float& Ep, float& Hp, uint32_t& tbw) {
     const float INF = __int_as_float(0x7f800000);
-    const float gcap = has_real ? INF : 1.0f;
-    float pvp[NPW];
-    uint32_t pk[NPW];                      // shared-window byte address of predecessor slot k at time slot 0
 #pragma unroll
-    for (int k = 0; k < NPW; k++) { pvp[k] = 0.f; pk[k] = sring + ck[k]; }
-    float Ep = 1.0f, Hp = 1.0f;
-    const uint32_t wadr = sring + threadIdx.x * 8u;
-    for (uint32_t t0 = 0; t0 < steps4; t0 += 4) {
-        // [w_first, w_last] = steps at which some row of this warp is inside the query; outside of it the warp
-        // only keeps the barriers (nothing it would publish is read: a consumer's window starts after its
-        // predecessors' and ends after theirs)
-        if (t0 + 3 < w_first || t0 > w_last) {
-            __syncthreads(); __syncthreads(); __syncthreads(); __syncthreads();
-            continue;
+    for (int u = 0; u < 2; u++) {
+        const uint32_t t = t0 + u;
+        const uint32_t xs = (t & (R - 1)) * SLOT_BYTES;      // uniform
+        const uint32_t SH = (WIDE ? 16u : 8u) * u;           // compile-time shift of this step's cell
+        const bool s0 = EDGES && (t == L.t_first);
+        // init (mesh.h:294-301,469-473): 1000000, or 1 for rows without predecessor. The s == 0 column is an
+        // edge too (init 1): there the forced insertion candidate E = 1 below supplies that 1.
+        float value = L.initv;
+        float gm = 1.0f;
+        uint32_t code = 0;
+        bool open = false;
+        float cur[NPW];
+        // ---- deletion over predecessor slots, ascending id (mesh.h:475-478 -> 305-330)
+#pragma unroll
+        for (int k = 0; k < NPW; k++) {
+            const float2 c = lds_f2(L.pk[k] + xs);
+            cur[k] = c.x;
+            const float v = __fadd_rn(c.x, L.dgp);
+            const float gv = __fadd_rn(c.y, L.dgpe);
+            // min() and the compare feed different consumers: the running value only depends on the FMNMX chain
+            // (this step's critical path to the ring store), the predicates only feed the traceback code.
+            // min(a, b) == (a < b ? a : b) here: no NaN, and a -0 cannot arise from these sums.
+            open = v < gv;
+            gm = fminf(v, gv);                                // last predecessor wins
+            const bool win = gm < value;
+            value = fminf(value, gm);
+            const uint32_t cd = WIDE ? ((TB_SRC_DEL | (k << 8)) << SH) : ((TB_SRC_DEL | (k << 2)) << SH);
+            const uint32_t co = WIDE ? (cd | (4u << SH)) : (cd | (32u << SH));
+            // the chosen-deletion-opened bit of the LAST slot is the cell's last-opened bit (set below): backtrack
+            // reads that one when the chosen predecessor is the last
+            code = win ? ((k < NPW - 1 && open) ? co : cd) : code;
         }
-        uint32_t tbw = 0, tbw2 = 0;
+        // ---- insertion from (m, s-1) (mesh.h:486-490 -> 332-358). At s == 0 the reference evaluates no
+        // insertion, gaps_val stays 1 and value starts from 1: E is forced to 1, so value = min(1, deletions)
+        // exactly as there (the traceback of an s == 0 cell is never followed).
+        const bool ext = (Ep == Hp);
+        float E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
+        if (EDGES) E = s0 ? 1.0f : E;
+        const bool iwin = (E <= value);
+        value = fminf(value, E);
+        code = iwin ? (TB_SRC_INS << SH) : code;
+        // ---- match from (p, s-1) (mesh.h:492-500 -> 360-374)
+        float sc;
+        if (PLANES == 1) sc = (L.mask & lds_u8(L.qrow + t)) ? L.msw : L.mmsw;   // comp(): the IUPAC masks intersect
+        else sc = __uint_as_float(lds_u8(L.qrow + (uint32_t)PLANES * t) * L.dsc + L.mmsw_bits);
+        if (EDGES) sc = s0 ? INF : sc;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t t = t0 + u;
-            const uint32_t xs = (t & (R - 1)) * SLOT_BYTES;      // uniform
-            const uint32_t SH = WIDE ? 16u * (u & 1) : 8u * u;   // compile-time shift of this step's cell
-            const bool s0 = (t == t_first);
-            // init (mesh.h:294-301,469-473): 1000000, or 1 for rows without predecessor. The s == 0 column is an
-            // edge too (init 1): there the forced insertion candidate E = 1 below supplies that 1.
-            float value = initv;
-            float gm = 1.0f;
-            uint32_t code = 0;
-            bool open = false;
-            float cur[NPW];
-            // ---- deletion over predecessor slots, ascending id (mesh.h:475-478 -> 305-330)
-#pragma unroll
-            for (int k = 0; k < NPW; k++) {
-                const float2 c = lds_f2(pk[k] + xs);
-                cur[k] = c.x;
-                const float v = __fadd_rn(c.x, dgp);
-                const float gv = __fadd_rn(c.y, dgpe);
-                open = v < gv;
-                gm = open ? v : gv;                               // last predecessor wins
-                const bool win = gm < value;
-                value = win ? gm : value;
-                const uint32_t cd = WIDE ? ((TB_SRC_DEL | (k << 8)) << SH) : ((TB_SRC_DEL | (k << 2)) << SH);
-                const uint32_t co = WIDE ? (cd | (4u << SH)) : (cd | (32u << SH));
-                code = win ? (open ? co : cd) : code;
-            }
-            const float gapm = fminf(gm, gcap);                   // gcap = +inf, or 1 for rows without predecessor
-            // ---- insertion from (m, s-1) (mesh.h:486-490 -> 332-358). At s == 0 the reference evaluates no
-            // insertion, gaps_val stays 1 and value starts from 1: E is forced to 1, so value = min(1, deletions)
-            // exactly as there (the traceback of an s == 0 cell is never followed).
-            const bool ext = (Ep == Hp);
-            float E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
-            E = s0 ? 1.0f : E;
-            const bool iwin = (E <= value);
-            value = iwin ? E : value;
-            code = iwin ? (TB_SRC_INS << SH) : code;
-            // ---- match from (p, s-1) (mesh.h:492-500 -> 360-374)
-            float sc = (mask & lds_u8(qrow + t)) ? msw : mmsw;
-            sc = s0 ? INF : sc;
-#pragma unroll
-            for (int k = 0; k < NPW; k++) {
-                const float v = __fadd_rn(pvp[k], sc);
-                const bool win = v < value;
-                value = win ? v : value;
-                code = win ? (WIDE ? ((TB_SRC_MATCH | (k << 8)) << SH) : ((TB_SRC_MATCH | (k << 2)) << SH)) : code;
-            }
-            const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
-            const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
-            code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
-            if (WIDE && u >= 2) tbw2 |= code; else tbw |= code;
-#pragma unroll
-            for (int k = 0; k < NPW; k++) pvp[k] = cur[k];
-            Ep = E;
-            Hp = value;
-            const float2 out = make_float2(value, gapm);
-            sts_f2<0>(wadr + xs, out);
-            sts_f2<RB>(wadr + xs, out);
-            if (t == t_last) *lastcol_ptr = value;
-            __syncthreads();
+        for (int k = 0; k < NPW; k++) {
+            const float v = __fadd_rn(pvp[k], sc);
+            const bool win = v < value;
+            value = fminf(value, v);
+            code = win ? (WIDE ? ((TB_SRC_MATCH | (k << 8)) << SH) : ((TB_SRC_MATCH | (k << 2)) << SH)) : code;
         }
-        if (WIDE) {
-            tbg[(uint64_t)(t0 >> 1) * T] = tbw;
-            tbg[(uint64_t)((t0 >> 1) + 1) * T] = tbw2;
-        } else {
-            tbg[(uint64_t)(t0 >> 2) * T] = tbw;
-        }
+        const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
+        const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
+        code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
+        tbw |= code;
+#pragma unroll
+        for (int k = 0; k < NPW; k++) pvp[k] = cur[k];
+        Ep = E;
+        Hp = value;
+        const float2 out = make_float2(value, gm);
+        sts_f2<0>(L.wadr + xs, out);
+        sts_f2<RB>(L.wadr + xs, out);
+        if (EDGES && t == L.t_last) *L.lastcol_ptr = value;
+        __syncthreads();
     }
 }
 
+// [w_first, w_last] = steps at which some row of this warp is inside the query; outside of it the warp only keeps
+// the barriers (nothing it would publish is read: a consumer's window starts after its predecessors' and ends after
+// theirs). [b_first, b_last] = steps at which every row of the warp is strictly inside (0 < s < Lq-1).
+template <int NPW, bool WIDE, int PLANES>
+__device__ __forceinline__ void v2_fast_group(const V2Lane<NPW>& L, const float gp, const float gpe, uint32_t steps4,
+                                              uint32_t w_first, uint32_t w_last, uint32_t b_first, uint32_t b_last,
+                                              uint32_t* tbg) {
+    float pvp[NPW];
+#pragma unroll
+    for (int k = 0; k < NPW; k++) pvp[k] = 0.f;
+    float Ep = 1.0f, Hp = 1.0f;
+    uint16_t* tbg16 = reinterpret_cast<uint16_t*>(tbg);   // u8 cells: this lane's halfword of step pair 0
+    for (uint32_t t0 = 0; t0 < steps4; t0 += 2) {
+        if (t0 + 1 < w_first || t0 > w_last) {
+            __syncthreads(); __syncthreads();
+            continue;
+        }
+        uint32_t tbw = 0;
+        if (t0 >= b_first && t0 + 1 <= b_last) v2_steps2<NPW, WIDE, false, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+        else v2_steps2<NPW, WIDE, true, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+        if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
+        else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
+    }
+}
+
+template <int NPW, bool WIDE, int PLANES>
+__device__ __forceinline__ void v2_fast_dispatch(const MeshArgs& A, uint32_t sring, uint32_t sq, const uint32_t* ck,
+                                                 bool valid, uint32_t np, int soff, uint32_t Lq, uint32_t plane, uint32_t mask, float w,
+                                                 uint32_t steps4, float* lastcol_ptr, uint32_t* tbg) {
+    V2Lane<NPW> L;
+#pragma unroll
+    for (int k = 0; k < NPW; k++) L.pk[k] = sring + ck[k];
+    L.wadr = sring + threadIdx.x * 8u;
+    const bool hr = np > 0;
+    const float msw = __fmul_rn(A.ms, w);    // (comp ? match : mismatch) * weight  (scoring_schemes.h:150-156)
+    const float mmsw = __fmul_rn(A.mms, w);
+    L.dgp = hr ? A.gp : 0.0f;
+    L.dgpe = hr ? A.gpe : 0.0f;
+    L.initv = hr ? 1000000.0f : 1.0f;
+    L.mmsw_bits = hr ? __float_as_uint(mmsw) : 0x7f800000u;
+    L.dsc = hr ? __float_as_uint(msw) - __float_as_uint(mmsw) : 0u;
+    L.msw = hr ? msw : __int_as_float(0x7f800000);
+    L.mmsw = hr ? mmsw : __int_as_float(0x7f800000);
+    L.mask = mask;
+    L.t_first = valid ? (uint32_t)soff : 0xFFFFFFFFu;
+    L.t_last = valid ? (uint32_t)soff + Lq - 1 : 0xFFFFFFFFu;
+    L.lastcol_ptr = lastcol_ptr;
+    L.qrow = sq + (valid ? (PLANES == 1 ? 0u : plane) - (uint32_t)PLANES * (uint32_t)soff : 0u);
+    const uint32_t w_first = __reduce_min_sync(0xffffffffu, L.t_first);
+    const uint32_t w_last = __reduce_max_sync(0xffffffffu, valid ? L.t_last : 0u);
+    const uint32_t b_first = __reduce_max_sync(0xffffffffu, valid ? L.t_first : 0u) + 1u;
+    const uint32_t b_last = __reduce_min_sync(0xffffffffu, L.t_last) - 1u;
+    v2_fast_group<NPW, WIDE, PLANES>(L, A.gp, A.gpe, steps4, w_first, w_last, b_first, b_last, tbg);
+}
+
 // Warps holding a row with more than NPF predecessors: slots are looped over.
-template <bool WIDE>
-__device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qm, uint32_t Lq,
+template <bool WIDE, int PLANES>
+__device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qt, uint32_t Lq,
                                                  uint32_t steps4, uint32_t npw, uint32_t np, const uint32_t* pd,
-                                                 int soff, float initv, uint32_t mask, float msw, float mmsw,
+                                                 int soff, float initv, uint32_t plane, uint32_t mask, float msw, float mmsw,
                                                  float* lastcol_ptr, uint32_t* tbg) {
     // slot k of this lane is real iff k >= npw - np; real slot k is predecessor ordinal k - (npw - np)
     const float gp = A.gp, gpe = A.gpe;
@@ -188,9 +244,10 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
     float Ep = 1.0f, Hp = 1.0f;
     const float2* ring = reinterpret_cast<const float2*>(smem);
     float2* ringw = reinterpret_cast<float2*>(smem);
-    for (uint32_t t0 = 0; t0 < steps4; t0 += 4) {
-        uint32_t tbw = 0, tbw2 = 0;
-        for (uint32_t u = 0; u < 4; u++) {
+    uint16_t* tbg16 = reinterpret_cast<uint16_t*>(tbg);
+    for (uint32_t t0 = 0; t0 < steps4; t0 += 2) {
+        uint32_t tbw = 0;
+        for (uint32_t u = 0; u < 2; u++) {
             const uint32_t t = t0 + u;
             const int s = (int)t - soff;
             uint32_t code = 0;
@@ -214,7 +271,7 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                     E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
                     ins_open = !ext;
                     if (E <= value) { value = E; code = TB_SRC_INS; }
-                    const float sc = (mask & qm[s]) ? msw : mmsw;
+                    const float sc = (PLANES == 1 ? (mask & qt[s]) : qt[s * PLANES + (int)plane]) ? msw : mmsw;
                     for (uint32_t k = shift; k < npw; k++) {
                         const uint32_t d = __ldg(&pd[k - shift]);
                         const float v = __fadd_rn(ring[((t - 1 - (d >> 16)) & (R - 1)) * S + (d & 0xffffu)].x, sc);
@@ -228,12 +285,11 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                 ringw[(R + (t & (R - 1))) * S + threadIdx.x] = out;   // second copy, read by the specialised warps
                 if (s == (int)Lq - 1) *lastcol_ptr = value;
             }
-            if (WIDE) { if (u >= 2) tbw2 |= code << (16 * (u & 1)); else tbw |= code << (16 * (u & 1)); }
-            else tbw |= code << (8 * u);
+            tbw |= code << ((WIDE ? 16 : 8) * u);
             __syncthreads();
         }
-        if (WIDE) { tbg[(uint64_t)(t0 >> 1) * T] = tbw; tbg[(uint64_t)((t0 >> 1) + 1) * T] = tbw2; }
-        else tbg[(uint64_t)(t0 >> 2) * T] = tbw;
+        if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
+        else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
     }
 }
 
@@ -278,6 +334,9 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
         ring[(t & (R - 1)) * S + threadIdx.x] = c;
         ring[(R + (t & (R - 1))) * S + threadIdx.x] = c;
     };
+    // the last loader lane owns the constant edge column (value 1, gapm +inf) read by rows without predecessor
+    if (threadIdx.x == S - 1)
+        for (uint32_t r = 0; r < 2 * R; r++) ring[r * S + threadIdx.x] = make_float2(1.0f, __int_as_float(0x7f800000));
     // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0); afterwards the
     // data of step t+4 is requested at step t, so the L2 latency never sits between two barriers
     // (GHOST_LEAD = 4 + 2 keeps that request behind the source row's spill store).
@@ -312,15 +371,17 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
     if (is_writer && wlast) { A.rowmin[io + wnode] = rmin; A.rowarg[io + wnode] = rarg; }
 }
 
-template <bool WIDE>
+template <bool WIDE, int PLANES>
 __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, uint32_t ql, unsigned char* smem,
-                                         const uint8_t* qm) {
+                                         const uint8_t* qt) {
     const uint32_t tid = threadIdx.x;
     const uint32_t Lq = h.qlen;
     const uint64_t io = (uint64_t)ql * A.icap;
     const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     const uint32_t* pdesc2 = A.pdesc2 + io;
     uint32_t* tbq = A.tb + h.tb_off;
+    const uint32_t sring = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t sq = (uint32_t)__cvta_generic_to_shared(qt);
 
     for (uint32_t g = 0; g < h.n_groups; g++) {
         const GroupInfo gi = A.groups[(uint64_t)ql * A.gcap + g];
@@ -330,25 +391,23 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
         } else {
             const uint32_t m = A.order[((uint64_t)ql * A.gcap + g) * T + tid];
             const bool valid = m != 0xFFFFFFFFu;
-            uint32_t np = 0, pbase = 0, mask = 0;
+            uint32_t np = 0, pbase = 0, plane = 0, mask = 0;
             int soff = 0;
-            float msw = 0.f, mmsw = 0.f;
+            float w = 0.f;
             float* lastcol_ptr = A.lastcol + io;  // never stored through for lanes without a row
             if (valid) {
                 pbase = pred_off[m];
                 np = pred_off[m + 1] - pbase;
                 mask = A.nmask[io + m] & 15u;
-                const float w = A.nweight[io + m];
-                msw = __fmul_rn(A.ms, w);    // (comp ? match : mismatch) * weight  (scoring_schemes.h:150-156)
-                mmsw = __fmul_rn(A.mms, w);
+                plane = __popc(h.maskset & ((1u << mask) - 1u));   // rank of the node's mask among the graph's
+                w = A.nweight[io + m];
                 soff = (int)(A.nsigma[io + m] - gi.sigma_lo);
                 lastcol_ptr = A.lastcol + io + m;
             }
             const uint32_t npw = max(1u, __reduce_max_sync(0xffffffffu, np));
             const bool warp_has_rows = __any_sync(0xffffffffu, valid);
             if (valid) A.nshift[io + m] = (uint8_t)(npw - np);
-            const float initv = np == 0 ? 1.0f : 1000000.0f;
-            uint32_t* tbg = tbq + gi.tb_off + tid;
+            uint32_t* tbg = tbq + gi.tb_off;
             __syncthreads();  // matches the loader's prologue barrier
             if (!warp_has_rows) {
                 for (uint32_t t = 0; t < steps4; t++) __syncthreads();   // a warp without rows only keeps the barriers
@@ -357,55 +416,73 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
                 const uint32_t shift = npw - np;
 #pragma unroll
                 for (int k = 0; k < NPF; k++) {
-                    ck[k] = tid * 8u;  // rows without predecessor: any valid cell, its candidates are +inf
+                    ck[k] = (S - 1) * 8u;  // rows without predecessor: the constant edge column
                     if (np > 0 && k < (int)npw) {
                         const uint32_t ord = (uint32_t)k > shift ? (uint32_t)k - shift : 0u;
                         const uint32_t d = pdesc2[pbase + ord];
                         ck[k] = (d & 0xffffu) * 8u + (((uint32_t)R - (d >> 16)) & (R - 1)) * SLOT_BYTES;
                     }
                 }
-                const float INF = __int_as_float(0x7f800000);
-                const bool hr = np > 0;
-                const float dgp = hr ? A.gp : INF, dgpe = hr ? A.gpe : INF;
-                if (!hr) { msw = INF; mmsw = INF; }
-                const uint32_t t_first = valid ? (uint32_t)soff : 0xFFFFFFFFu;
-                const uint32_t t_last = valid ? (uint32_t)soff + Lq - 1 : 0xFFFFFFFFu;
-                const uint32_t w_first = __reduce_min_sync(0xffffffffu, t_first);
-                const uint32_t w_last = __reduce_max_sync(0xffffffffu, valid ? t_last : 0u);
-                const uint32_t sring = (uint32_t)__cvta_generic_to_shared(smem);
-                const uint32_t qrow = (uint32_t)__cvta_generic_to_shared(qm) - (valid ? (uint32_t)soff : 0u);
-#define V2_CASE(N) case N: v2_fast_group<N, WIDE>(A, sring, qrow, steps4, ck, dgp, dgpe, t_first, t_last, w_first, w_last, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
+                // lane's cell of step pair 0: halfword (u8 cells) or word (u16 cells) number tid
+                uint32_t* tbl = WIDE ? tbg + tid : reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(tbg) + tid);
+#define V2_CASE(N) case N: v2_fast_dispatch<N, WIDE, PLANES>(A, sring, sq, ck, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
                 switch (npw) {
                     V2_CASE(1) V2_CASE(2) V2_CASE(3) V2_CASE(4) V2_CASE(5) V2_CASE(6) V2_CASE(7)
-                    default: v2_fast_group<8, WIDE>(A, sring, qrow, steps4, ck, dgp, dgpe, t_first, t_last, w_first, w_last, initv, hr, mask, msw, mmsw, lastcol_ptr, tbg); break;
+                    default: v2_fast_dispatch<8, WIDE, PLANES>(A, sring, sq, ck, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
                 }
 #undef V2_CASE
             } else {
                 if (!valid) soff = (int)(steps4 + 8);    // lane without a row: s stays negative
-                v2_generic_group<WIDE>(A, smem, qm, Lq, steps4, npw, np, pdesc2 + pbase, soff,
-                                       initv, mask, msw, mmsw, lastcol_ptr, tbg);
+                const float initv = np == 0 ? 1.0f : 1000000.0f;
+                uint32_t* tbl = WIDE ? tbg + tid : reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(tbg) + tid);
+                v2_generic_group<WIDE, PLANES>(A, smem, qt, Lq, steps4, npw, np, pdesc2 + pbase, soff,
+                                       initv, plane, mask, __fmul_rn(A.ms, w), __fmul_rn(A.mms, w), lastcol_ptr, tbl);
             }
         }
         __syncthreads();  // ring and spill rows of this group are complete before the next group starts
     }
 }
 
+// Query table in shared memory.
+// PLANES == 8 (hdr.mode 2, graphs with at most 8 distinct node masks: the four bases and a few ambiguity codes):
+//   8 bytes per query position, byte p = 1 iff the query base matches the p-th IUPAC mask occurring among the
+//   graph's nodes (comp(): the masks intersect, src/aligned_base.h:153-156); a row reads its match/mismatch selector
+//   as one byte and turns it into the score's float bits with one integer multiply-add.
+// PLANES == 1 (hdr.mode 3, more distinct masks): one byte per position = the query base's mask; rows test
+//   `mask & byte`.
+// Positions outside the query read 0.
+template <int PLANES>
 __global__ void __launch_bounds__(DP_BLOCK, DP_CTAS_PER_SM) mesh_v2_kernel(MeshArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t q = A.q0 + blockIdx.x;
     const GraphHdr h = A.hdr[q];
-    if (h.status != GS_OK || h.mode != 2) return;
-    uint8_t* qm = smem + RING_BYTES + 16 + QPAD;   // valid for s in [-QPAD, Lq + QPAD)
+    if (h.status != GS_OK || h.mode != (PLANES == 8 ? 2u : 3u)) return;
+    uint8_t* qt = smem + RING_BYTES + 16 + PLANES * QPAD;   // valid for s in [-QPAD, Lq + QPAD)
     const uint8_t* src = A.qmasks + A.qoff[q];
-    for (uint32_t i = threadIdx.x; i < h.qlen + 2 * QPAD; i += blockDim.x) {
-        const int s = (int)i - QPAD;
-        qm[s] = (s >= 0 && s < (int)h.qlen) ? (src[s] & 15u) : 0;
+    if (PLANES == 1) {
+        for (uint32_t i = threadIdx.x; i < h.qlen + 2 * QPAD; i += blockDim.x) {
+            const int s = (int)i - QPAD;
+            qt[s] = (s >= 0 && s < (int)h.qlen) ? (src[s] & 15u) : 0;
+        }
+    } else {
+        uint32_t pm[8];   // mask of plane p
+        uint32_t ms = h.maskset;
+#pragma unroll
+        for (int p2 = 0; p2 < 8; p2++) { pm[p2] = ms ? (uint32_t)__ffs((int)ms) - 1u : 0u; ms &= ms - 1u; }
+        for (uint32_t i = threadIdx.x; i < h.qlen + 2 * QPAD; i += blockDim.x) {
+            const int s = (int)i - QPAD;
+            const uint32_t b = (s >= 0 && s < (int)h.qlen) ? (src[s] & 15u) : 0u;
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int p2 = 0; p2 < 4; p2++) { lo |= ((pm[p2] & b) ? 1u : 0u) << (8 * p2); hi |= ((pm[p2 + 4] & b) ? 1u : 0u) << (8 * p2); }
+            *reinterpret_cast<uint2*>(qt + (int64_t)s * 8) = make_uint2(lo, hi);
+        }
     }
     for (uint32_t i = threadIdx.x; i < RING_BYTES / 8; i += blockDim.x)  // no NaN bit patterns in unwritten cells
         reinterpret_cast<float2*>(smem)[i] = make_float2(0.f, 0.f);
     __syncthreads();
-    if (h.wide) v2_query<true>(A, h, blockIdx.x, smem, qm);
-    else v2_query<false>(A, h, blockIdx.x, smem, qm);
+    if (h.wide) v2_query<true, PLANES>(A, h, blockIdx.x, smem, qt);
+    else v2_query<false, PLANES>(A, h, blockIdx.x, smem, qt);
 }
 
 // ====================================================================================================
@@ -528,13 +605,12 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                 if (s == (int)Lq - 1) A.lastcol[io + m] = value;
                 if (is_last && (s == 0 || value < rmin)) { rmin = value; rarg = (uint32_t)s; }
             }
-            if (tid < (uint32_t)T) {
-                if (WIDE) {
-                    tbw |= code << (16 * (t & 1));
-                    if ((t & 1) == 1) { tbg[(uint64_t)(t >> 1) * T + tid] = tbw; tbw = 0; }
-                } else {
-                    tbw |= code << (8 * (t & 3));
-                    if ((t & 3) == 3) { tbg[(uint64_t)(t >> 2) * T + tid] = tbw; tbw = 0; }
+            if (tid < (uint32_t)T) {   // cells of two consecutive steps share one store (see common.cuh)
+                tbw |= code << ((WIDE ? 16 : 8) * (t & 1));
+                if ((t & 1) == 1) {
+                    if (WIDE) tbg[(uint64_t)(t >> 1) * T + tid] = tbw;
+                    else reinterpret_cast<uint16_t*>(tbg)[(uint64_t)(t >> 1) * T + tid] = (uint16_t)tbw;
+                    tbw = 0;
                 }
             }
             __syncthreads();
@@ -573,14 +649,17 @@ int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0
         uint32_t l = (uint32_t)(s->h_qoff[i + 1] - s->h_qoff[i]);
         if (l > max_qlen) max_qlen = l;
     }
-    size_t smem = RING_BYTES + 16 + 2 * QPAD + ((max_qlen + 15) & ~15u);
-    if (smem > 220 * 1024) SG_FAIL(SG_ERR_LIMIT, "query too long for the DP kernel's shared memory");
-    SG_CUDA(cudaFuncSetAttribute(mesh_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CUDA(cudaFuncSetAttribute(mesh_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mesh_v2_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
-    mesh_v1_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
+    const size_t qpos = 2 * QPAD + ((max_qlen + 15) & ~15u);
+    const size_t smem8 = RING_BYTES + 16 + 8 * qpos, smem1 = RING_BYTES + 16 + qpos;  // ring + query table
+    if (smem8 > 220 * 1024) SG_FAIL(SG_ERR_LIMIT, "query too long for the DP kernel's shared memory");
+    SG_CUDA(cudaFuncSetAttribute(mesh_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+    SG_CUDA(cudaFuncSetAttribute(mesh_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    SG_CUDA(cudaFuncSetAttribute(mesh_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+    mesh_v2_kernel<8><<<n, DP_BLOCK, smem8, w->stream>>>(A);
+    mesh_v2_kernel<1><<<n, DP_BLOCK, smem1, w->stream>>>(A);
+    mesh_v1_kernel<<<n, DP_BLOCK, smem8, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
-    s->stats.kernel_launches += 2;
+    s->stats.kernel_launches += 3;
     return SG_OK;
 }
 
