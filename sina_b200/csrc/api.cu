@@ -35,7 +35,7 @@ static void free_workspace(Workspace* w) {
                     w->d_ncol, w->d_nmask, w->d_ncount, w->d_nweight, w->d_nsigma, w->d_slotbase, w->d_cursor,
                     w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_nthr, w->d_nshift, w->d_ghosts,
                     w->d_writers, w->d_spillrow, w->d_nflags, w->d_lastnodes, w->d_groups, w->d_lastcol, w->d_rowmin,
-                    w->d_rowarg, w->d_tb, w->d_spill};
+                    w->d_rowarg, w->d_rec, w->d_tb, w->d_spill};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (w->h_remaining) cudaFreeHost(w->h_remaining);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -74,6 +74,7 @@ static int alloc_workspace(Session* s, Workspace* w) {
     SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
     SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
     SG_TRY(dmalloc(&w->d_writers, C * s->gcap * DP_G));
+    { uint8_t* p = nullptr; SG_TRY(dmalloc(&p, C * I * 32)); w->d_rec = p; }
     SG_TRY(dmalloc(&w->d_tb, s->tb_words)); SG_TRY(dmalloc(&w->d_spill, s->spill_elems));
     return SG_OK;
 }

@@ -1,4 +1,4 @@
-// Backtrack + gap placement on the device, one thread per query.
+// Backtrack + gap placement on the device, one warp per query.
 // Replaces backtrack() (reference src/mesh.h:534-739) and cseq::fix_duplicate_positions
 // (src/cseq.cpp:456-594), decoding the packed traceback written by mesh.cu instead of the reference's
 // 28-byte cells:
@@ -6,9 +6,30 @@
 //                                  | DEL via pred i: opened ? (pred_i, s) : (gapm_idx(pred_i, s), s)
 //   gaps_idx(m,s) = ins-open(m,s) ? s-1 : gaps_idx(m,s-1), gaps_idx(m,0) = 0            (mesh.h:340-349)
 //   gapm_idx(x,s) = no preds ? 0 : last-open(x,s) ? lastpred(x) : gapm_idx(lastpred(x), s)  (mesh.h:315-323)
+//
+// The walk is a pointer chase through HBM (one traceback byte per step, 3-4 MB per query), so the kernel is
+// organised around the length of the dependent-load chain:
+//   * prologue: the warp packs everything the walk needs to know about a node into one 32-byte record
+//     (traceback row base, step offset, predecessor-slot shift, in-degree, column, first four predecessors);
+//   * walk: all lanes run the same chase. As soon as a node's record is there the records of its (<= 4 inline)
+//     predecessors are requested, so that when the node's traceback cell arrives and names the predecessor, that
+//     record is already in registers and the next cell can be requested at once: one memory latency per step.
+//     The walk only records which node every query position landed on;
+//   * epilogue (lane-parallel): columns of the overhangs and the aligned part in closed form, cseq::append's
+//     running width as a prefix maximum, sum_weight added in the reference's order, reverse + setWidth, and the
+//     serial gap placement only for queries that actually have bases sharing a column.
 #include "common.cuh"
 
 namespace sg {
+
+struct __align__(16) NodeRec {
+    uint32_t tbbase;    // index of the row's first cell pair inside the query's traceback block (u16 or u32 units)
+    uint32_t meta;      // [15:0] sigma - sigma_lo(group)  [23:16] predecessor-slot shift  [31:24] in-degree
+    uint32_t ncol;
+    uint32_t pred_off;
+    uint32_t pred[4];   // predecessors 0..3 (ascending id)
+};
+static_assert(sizeof(NodeRec) == 32, "NodeRec is read as two 16-byte loads");
 
 struct BtArgs {
     uint32_t nq, W, q0;  // nq queries of the chunk starting at q0
@@ -18,17 +39,13 @@ struct BtArgs {
     const uint32_t* preds; const uint32_t* lastnodes; const uint32_t* afam_n; const uint16_t* nthr; const uint8_t* nshift;
     const uint32_t* tb; const float* lastcol; const float* rowmin; const uint32_t* rowarg;
     const uint32_t* copy_src; const uint8_t* masks; const uint32_t* cols; const uint64_t* row_off;
+    NodeRec* rec;
     uint32_t* out_cols; uint8_t* out_masks; sg_align_result* results;
     float ms; int overhang, lowercase;
 };
 
-struct Out {  // cseq under construction: append() semantics of src/cseq.cpp:79-95
-    uint32_t* pos; uint8_t* mask; uint32_t n, width;
-    __device__ void append(uint32_t p, uint8_t b) {
-        if (p >= width) { pos[n] = p; mask[n] = b; n++; width = p; }
-        else { pos[n] = width; mask[n] = b; n++; }
-    }
-};
+constexpr int BT_WARPS = 2;   // queries per CTA
+constexpr uint32_t FULL = 0xffffffffu;
 
 // cseq_base::fix_duplicate_positions (src/cseq.cpp:456-594); returns 1 for its runtime_error
 __device__ int fix_duplicate_positions(uint32_t* pos, uint8_t* masks, uint32_t n, uint32_t width, int lowercase) {
@@ -92,13 +109,25 @@ __device__ int fix_duplicate_positions(uint32_t* pos, uint8_t* masks, uint32_t n
     return 0;
 }
 
-__global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
-    const uint32_t ql = blockIdx.x * blockDim.x + threadIdx.x;
+// strict-'<' argmin in ascending index order (the reference's scan): (value, first index reaching it) over the
+// lanes' partial results
+__device__ __forceinline__ void warp_argmin(float& v, uint32_t& i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(FULL, v, o);
+        const uint32_t i2 = __shfl_xor_sync(FULL, i, o);
+        if (v2 < v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+    }
+}
+
+__global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
+    const uint32_t ql = blockIdx.x * BT_WARPS + warp_id();
     if (ql >= A.nq) return;
+    const uint32_t lane = lane_id();
     const uint32_t q = A.q0 + ql;
     const GraphHdr h = A.hdr[q];
     if (h.status == GS_DONE) return;  // finished in an earlier pass
-    if (h.status == GS_ARENA_FULL) { atomicAdd(A.remaining, 1u); return; }  // host resets the arenas and re-runs
+    if (h.status == GS_ARENA_FULL) { if (lane == 0) atomicAdd(A.remaining, 1u); return; }  // host resets the arenas and re-runs
     sg_align_result r = {};
     const uint64_t qo = A.qoff[q];
     const uint32_t L = h.qlen;
@@ -109,161 +138,280 @@ __global__ void __launch_bounds__(64) backtrack_kernel(BtArgs A) {
     if (h.status == SG_Q_COPIED) {  // setAlignedBases from the containing relative (src/align.cpp:349-388)
         const uint32_t id = A.copy_src[2 * q], at = A.copy_src[2 * q + 1];
         const uint64_t ro = A.row_off[id] + at;
-        for (uint32_t i = 0; i < L; i++) { ocols[i] = A.cols[ro + i]; omasks[i] = A.masks[ro + i]; }
+        for (uint32_t i = lane; i < L; i += 32) { ocols[i] = A.cols[ro + i]; omasks[i] = A.masks[ro + i]; }
         r.status = SG_Q_COPIED; r.score = 1.f; r.qual = 100; r.n_out = L;
-        A.results[q] = r;
-        A.hdr[q].status = GS_DONE;
+        if (lane == 0) { A.results[q] = r; A.hdr[q].status = GS_DONE; }
         return;
     }
-    if (h.status != GS_OK) { r.status = (int32_t)h.status; A.results[q] = r; A.hdr[q].status = GS_DONE; return; }
+    if (h.status != GS_OK) {
+        r.status = (int32_t)h.status;
+        if (lane == 0) { A.results[q] = r; A.hdr[q].status = GS_DONE; }
+        return;
+    }
 
     const uint64_t io = (uint64_t)ql * A.icap;
     const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
     const uint32_t* preds = A.preds + io;
-    const uint32_t* nsigma = A.nsigma + io;
-    const uint32_t* ncol = A.ncol + io;
     const float* nweight = A.nweight + io;
-    const GroupInfo* groups = A.groups + (uint64_t)ql * A.gcap;
     const uint32_t* tbq = A.tb + h.tb_off;
+    const uint16_t* tbq16 = reinterpret_cast<const uint16_t*>(tbq);
     const bool wide = h.wide != 0;
     const uint32_t V = h.V, W = A.W;
     const uint32_t T = DP_T;
-    const uint16_t* nthr = A.nthr + io;
-    const uint8_t* nshift = A.nshift + io;
-    const bool sorted = h.mode >= 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
+    NodeRec* rec = A.rec + io;
 
-    // decoded traceback cell: src | ord<<8 | chosen_open<<2 | last_open<<3 | ins_open<<4 (the wide layout)
-    auto cell = [&](uint32_t m, uint32_t s) -> uint32_t {
-        const uint32_t g = m / T, tid = sorted ? (uint32_t)nthr[m] : m - g * T;
-        const GroupInfo gi = groups[g];
-        const uint32_t t = s + nsigma[m] - gi.sigma_lo;
-        if (wide) {
-            const uint32_t w = tbq[gi.tb_off + (uint64_t)(t >> 1) * T + tid];
-            return (w >> (16 * (t & 1))) & 0xffffu;
+    // ---- prologue: node records
+    {
+        const uint32_t* nsigma = A.nsigma + io;
+        const uint32_t* ncol = A.ncol + io;
+        const GroupInfo* groups = A.groups + (uint64_t)ql * A.gcap;
+        const uint16_t* nthr = A.nthr + io;
+        const uint8_t* nshift = A.nshift + io;
+        const bool sorted = h.mode >= 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
+        for (uint32_t m = lane; m < V; m += 32) {
+            const uint32_t g = m / T, tid = sorted ? (uint32_t)nthr[m] : m - g * T;
+            const GroupInfo gi = groups[g];
+            const uint32_t po = pred_off[m], np = pred_off[m + 1] - po;
+            uint4 a, b;
+            a.x = (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
+            a.y = (nsigma[m] - gi.sigma_lo) | ((uint32_t)nshift[m] << 16) | (min(np, 255u) << 24);
+            a.z = ncol[m];
+            a.w = po;
+            b.x = np > 0 ? preds[po] : 0u;
+            b.y = np > 1 ? preds[po + 1] : 0u;
+            b.z = np > 2 ? preds[po + 2] : 0u;
+            b.w = np > 3 ? preds[po + 3] : 0u;
+            uint4* dst = reinterpret_cast<uint4*>(rec + m);
+            __stcg(dst, a);
+            __stcg(dst + 1, b);
         }
-        const uint16_t* tb16 = reinterpret_cast<const uint16_t*>(tbq + gi.tb_off);
-        const uint32_t c = ((uint32_t)tb16[(uint64_t)(t >> 1) * T + tid] >> (8 * (t & 1))) & 0xffu;
+    }
+    __syncwarp();
+
+    auto ldrec = [&](uint32_t x, uint4& a, uint4& b) {
+        const uint4* p = reinterpret_cast<const uint4*>(rec + x);
+        a = __ldcg(p);
+        b = __ldcg(p + 1);
+    };
+    // decoded traceback cell: src | ord<<8 | chosen_open<<2 | last_open<<3 | ins_open<<4 (the wide layout)
+    auto cell = [&](const uint4& a, uint32_t s) -> uint32_t {
+        const uint32_t t = s + (a.y & 0xffffu);
+        const uint32_t idx = a.x + (t >> 1) * T;
+        if (wide) return (__ldcg(&tbq[idx]) >> (16 * (t & 1))) & 0xffffu;
+        const uint32_t c = ((uint32_t)__ldcg(&tbq16[idx]) >> (8 * (t & 1))) & 0xffu;
         return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2) | (((c >> 6) & 1u) << 3) | (((c >> 7) & 1u) << 4);
     };
-    auto gaps_idx = [&](uint32_t m, uint32_t s) -> uint32_t {
-        for (uint32_t cur = s; cur > 0; cur--) if (cell(m, cur) & 16u) return cur - 1;
+    auto np_of = [](const uint4& a) -> uint32_t { return a.y >> 24; };
+    auto pred_of = [&](const uint4& a, const uint4& b, uint32_t ord) -> uint32_t {
+        if (ord == 0) return b.x;
+        if (ord == 1) return b.y;
+        if (ord == 2) return b.z;
+        if (ord == 3) return b.w;
+        return __ldcg(&preds[a.w + ord]);
+    };
+    // first query position of the insertion run ending at (m, s): lanes look at 32 cells of the row at a time
+    auto gaps_idx = [&](const uint4& a, uint32_t s, uint32_t c_s) -> uint32_t {
+        if (c_s & 16u) return s - 1;
+        uint32_t top = s - 1;                       // cells top, top-1, ... (cur > 0)
+        while (top > 0) {
+            const bool in = lane < top;             // cur = top - lane >= 1
+            const uint32_t cc = in ? cell(a, top - lane) : 0u;
+            const uint32_t hit = __ballot_sync(FULL, in && (cc & 16u));
+            if (hit) return top - ((uint32_t)__ffs((int)hit) - 1u) - 1u;
+            top = top > 32 ? top - 32 : 0;
+        }
         return 0;
     };
     auto gapm_idx = [&](uint32_t x, uint32_t s) -> uint32_t {
         for (;;) {
-            if (pred_off[x + 1] == pred_off[x]) return 0;
-            const uint32_t lp = preds[pred_off[x + 1] - 1];
-            if (cell(x, s) & 8u) return lp;
+            uint4 a, b;
+            ldrec(x, a, b);
+            const uint32_t np = np_of(a);
+            if (np == 0) return 0;
+            const uint32_t lp = pred_of(a, b, np - 1);
+            if (cell(a, s) & 8u) return lp;
             x = lp;
         }
     };
-    // (value_midx, value_sidx) of cell (m,s)
-    auto follow = [&](uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
-        const uint32_t src = c & 3u, sl = c >> 8, sh = nshift[m];
+    // (value_midx, value_sidx) of cell (m,s) = c
+    auto follow = [&](const uint4& a, const uint4& b, uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
+        const uint32_t src = c & 3u, sl = c >> 8, sh = (a.y >> 16) & 0xffu;
         const uint32_t ord = sl > sh ? sl - sh : 0u;  // v2 slots are right-aligned, leading slots repeat ordinal 0
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
-        else if (src == TB_SRC_MATCH) { nm = preds[pred_off[m] + ord]; ns = s - 1; }
-        else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(m, s); }
+        else if (src == TB_SRC_MATCH) { nm = pred_of(a, b, ord); ns = s - 1; }
+        else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(a, s, c); }
         else {
-            const uint32_t p = preds[pred_off[m] + ord];
+            const uint32_t p = pred_of(a, b, ord);
             // deletion opened at p? For the last predecessor that is the cell's last-opened bit (the specialised
             // DP step does not set the chosen-opened bit for its last slot)
-            const bool opened = (c & 4u) || (ord + 1 == pred_off[m + 1] - pred_off[m] && (c & 8u));
+            const bool opened = (c & 4u) || (ord + 1 == np_of(a) && (c & 8u));
             nm = opened ? p : gapm_idx(p, s);
             ns = s;
         }
     };
 
-    // ---- starting point (mesh.h:567-592)
+    // ---- starting point (mesh.h:567-592): strict-'<' scans in id order, starting from the first last-node
     const uint32_t send = L - 1;
     const float* lastcol = A.lastcol + io;
     const uint32_t* lastnodes = A.lastnodes + io;
     uint32_t m = lastnodes[0];
     float best = lastcol[m];
-    for (uint32_t t = 0; t < V; t++) { const float v = lastcol[t]; if (v < best) { best = v; m = t; } }
+    {
+        float bv = __int_as_float(0x7f800000);
+        uint32_t bi = 0xffffffffu;
+        for (uint32_t t = lane; t < V; t += 32) { const float v = lastcol[t]; if (v < bv) { bv = v; bi = t; } }
+        warp_argmin(bv, bi);
+        if (bv < best) { best = bv; m = bi; }
+    }
     uint32_t s = send;
-    for (uint32_t i = 0; i < h.n_last; i++) {
-        const uint32_t mt = lastnodes[i];
-        const float v = A.rowmin[io + mt];
-        if (v < best) { best = v; m = mt; s = A.rowarg[io + mt]; }
+    {
+        float bv = __int_as_float(0x7f800000);
+        uint32_t bi = 0xffffffffu;
+        for (uint32_t i = lane; i < h.n_last; i += 32) {
+            const float v = A.rowmin[io + lastnodes[i]];
+            if (v < bv) { bv = v; bi = i; }
+        }
+        warp_argmin(bv, bi);
+        if (bv < best) { best = bv; m = lastnodes[bi]; s = A.rowarg[io + m]; }
     }
     r.end_m = m; r.end_s = s;
-    const bool keep_case = A.lowercase == 1;
-    const bool lc_unaligned = A.lowercase == 2;
-    auto qbase = [&](uint32_t i) -> uint8_t { return keep_case ? qm[i] : (uint8_t)(qm[i] & 15u); };
+    const uint32_t m_end = m, s_end = s;
 
-    Out o = { ocols, omasks, 0, 0 };
-    // ---- right overhang (mesh.h:594-615)
-    const int cutoff_tail = (int)(send - s);
-    if (cutoff_tail && A.overhang != 1) {
-        int pos = (A.overhang == 0) ? (int)W - 1 - (int)ncol[m] - cutoff_tail : 0;
-        for (int i = 0; i < cutoff_tail; i++) {
-            uint8_t b = qbase(L - 1 - i);
-            if (lc_unaligned) b |= 16;
-            const int pp = pos++;
-            o.append((uint32_t)(pp > 0 ? pp : 0), b);
-        }
-    }
-    const float rval = best;
-    uint32_t pos = W - 1 - ncol[m];
-    float sum_weight = 0.f;
-    o.append(pos, qbase(s));
-    sum_weight = __fadd_rn(sum_weight, __fmul_rn(A.ms, nweight[m]));
-    // ---- walk back (mesh.h:642-685)
-    while (s != 0 && pred_off[m + 1] != pred_off[m]) {
+    // ---- walk back (mesh.h:642-685): ocols[s] = node the query position s is aligned to
+    uint4 ra, rb;
+    ldrec(m, ra, rb);
+    uint32_t c = cell(ra, s);
+    if (lane == 0) ocols[s] = m;
+    while (s != 0 && np_of(ra) != 0) {
+        // records of the inline predecessors, requested before the cell is looked at
+        const uint32_t np = np_of(ra);
+        uint4 qa0 = ra, qb0 = rb, qa1 = ra, qb1 = rb, qa2 = ra, qb2 = rb, qa3 = ra, qb3 = rb;
+        ldrec(rb.x, qa0, qb0);
+        if (np > 1) ldrec(rb.y, qa1, qb1);
+        if (np > 2) ldrec(rb.z, qa2, qb2);
+        if (np > 3) ldrec(rb.w, qa3, qb3);
         uint32_t nm, snew;
-        follow(m, s, cell(m, s), nm, snew);
-        m = nm;
+        follow(ra, rb, m, s, c, nm, snew);
+        uint4 na, nb;
+        if (nm == m) { na = ra; nb = rb; }
+        else if (nm == rb.x) { na = qa0; nb = qb0; }
+        else if (np > 1 && nm == rb.y) { na = qa1; nb = qb1; }
+        else if (np > 2 && nm == rb.z) { na = qa2; nb = qb2; }
+        else if (np > 3 && nm == rb.w) { na = qa3; nb = qb3; }
+        else ldrec(nm, na, nb);
+        m = nm; ra = na; rb = nb;
+        uint32_t c2 = 0;
         if (snew != 0) {  // landing on a cell reached by deletion (its value_sidx == snew): skip it (mesh.h:653-655)
-            const uint32_t c2 = cell(m, snew);
+            c2 = cell(ra, snew);
             if ((c2 & 3u) == TB_SRC_DEL) {
                 uint32_t m2, s2;
-                follow(m, snew, c2, m2, s2);
+                follow(ra, rb, m, snew, c2, m2, s2);
                 m = m2;
+                ldrec(m, ra, rb);
+                c2 = cell(ra, snew);
             }
         }
-        pos = W - 1 - ncol[m];
-        while (s != snew) {
-            --s;
-            o.append(pos, qbase(s));
-            sum_weight = __fadd_rn(sum_weight, __fmul_rn(A.ms, nweight[m]));
+        for (int ss = (int)s - 1 - (int)lane; ss >= (int)snew; ss -= 32) ocols[ss] = m;
+        s = snew;
+        c = c2;
+    }
+    const uint32_t m_fin = m, s_fin = s;
+    __syncwarp();
+
+    // ---- epilogue. Elements are appended for s descending: right overhang (mesh.h:594-615), aligned part,
+    // left overhang (mesh.h:690-721); cseq::append (src/cseq.cpp:79-95) places element j at the running maximum of
+    // the requested positions, i.e. a prefix maximum.
+    const bool keep_case = A.lowercase == 1;
+    const bool lc_unaligned = A.lowercase == 2;
+    const int cutoff_tail = (int)(send - s_end);
+    const bool right_oh = cutoff_tail != 0 && A.overhang != 1;
+    const bool left_oh = s_fin != 0 && A.overhang != 1;
+    const uint32_t top_s = right_oh ? send : s_end;
+    const uint32_t bottom_s = left_oh ? 0u : s_fin;
+    const uint32_t n = top_s - bottom_s + 1;
+    const int rbase = (A.overhang == 0) ? (int)W - 1 - (int)A.ncol[io + m_end] - cutoff_tail : 0;
+    const uint32_t lpos = W - 1 - A.ncol[io + m_fin];   // `pos` when the walk ended
+    // sum_weight: the aligned elements' match scores added in append order (mesh.h:640,683)
+    float sum_weight = 0.f;
+    for (uint32_t j0 = 0; j0 <= s_end - s_fin; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool in = j <= s_end - s_fin;
+        const float pw = in ? __fmul_rn(A.ms, nweight[ocols[s_end - j]]) : 0.f;
+        const uint32_t cnt = min(32u, s_end - s_fin + 1 - j0);
+        for (uint32_t l = 0; l < cnt; l++) sum_weight = __fadd_rn(sum_weight, __shfl_sync(FULL, pw, l));
+    }
+    uint32_t width = 0;
+    for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool in = j < n;
+        const uint32_t sx = top_s - (in ? j : 0u);
+        uint32_t p = 0;
+        bool unal = false;
+        if (in) {
+            if (sx > s_end) {            // right overhang, element i = send - sx: position max(rbase + i, 0)
+                const int pp = rbase + (int)(send - sx);
+                p = (uint32_t)(pp > 0 ? pp : 0);
+                unal = true;
+            } else if (sx >= s_fin) {
+                p = W - 1 - A.ncol[io + ocols[sx]];
+            } else if (A.overhang == 0) {  // attach: ++pos per base, clamped to the last column
+                const uint32_t pp = lpos + (s_fin - sx);
+                p = pp < W - 1 ? pp : W - 1;
+                unal = true;
+            } else {                       // edge
+                p = W - sx - 1;
+                unal = true;
+            }
+        }
+        uint32_t x = in ? p : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, x, o);
+            if (lane >= (uint32_t)o) x = max(x, y);
+        }
+        x = max(x, width);
+        width = __shfl_sync(FULL, x, 31);
+        if (in) {
+            // setWidth + reverse (mesh.h:723-724; cseq.cpp:283-289): column W-1-position, ascending s
+            ocols[sx] = W - 1 - x;
+            uint8_t b = keep_case ? qm[sx] : (uint8_t)(qm[sx] & 15u);
+            if (unal && lc_unaligned) b |= 16;
+            omasks[sx] = b;
         }
     }
-    // ---- left overhang (mesh.h:690-721)
-    if (s != 0) {
-        r.head = (int)s;
-        if (A.overhang == 0) {
-            while (s-- != 0) {
-                uint8_t b = qbase(s);
-                ++pos;
-                if (lc_unaligned) b |= 16;
-                o.append(pos < W - 1 ? pos : W - 1, b);
-            }
-        } else if (A.overhang == 2) {
-            int n = (int)s;
-            while (n--) {
-                uint8_t b = qbase((uint32_t)n);
-                if (lc_unaligned) b |= 16;
-                o.append(W - (uint32_t)n - 1, b);
-            }
+    __syncwarp();
+    if (bottom_s != 0) {  // --overhang remove dropped the head: the output starts at its first base
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t cv = 0; uint8_t mv = 0;
+            if (i < n) { cv = ocols[bottom_s + i]; mv = omasks[bottom_s + i]; }
+            __syncwarp();
+            if (i < n) { ocols[i] = cv; omasks[i] = mv; }
+            __syncwarp();
         }
     }
+    // bases sharing a column (insertions) need the serial gap placement
+    uint32_t dup = 0;
+    for (uint32_t i0 = 0; i0 + 1 < n; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        dup |= (i + 1 < n && ocols[i] == ocols[i + 1]) ? 1u : 0u;
+    }
+    dup = __any_sync(FULL, dup);
+    int nospace = 0;
+    if (dup) {
+        if (lane == 0) nospace = fix_duplicate_positions(ocols, omasks, n, W, lc_unaligned);
+        nospace = __shfl_sync(FULL, nospace, 0);
+    }
+    if (s_fin != 0) r.head = (int)s_fin;
     r.tail = cutoff_tail;
-    // ---- setWidth + reverse (mesh.h:723-724; cseq.cpp:283-289)
-    for (uint32_t i = 0; i < o.n / 2; i++) {
-        const uint32_t tp = o.pos[i]; o.pos[i] = o.pos[o.n - 1 - i]; o.pos[o.n - 1 - i] = tp;
-        const uint8_t tm = o.mask[i]; o.mask[i] = o.mask[o.n - 1 - i]; o.mask[o.n - 1 - i] = tm;
-    }
-    for (uint32_t i = 0; i < o.n; i++) o.pos[i] = W - 1 - o.pos[i];
-    r.n_out = o.n;
-    r.raw = rval; r.sum_weight = sum_weight;
-    r.score = __fdiv_rn(rval, sum_weight);
+    r.n_out = n;
+    r.raw = best; r.sum_weight = sum_weight;
+    r.score = __fdiv_rn(best, sum_weight);
     const float q100 = __fmul_rn(100.f, r.score);  // src/align.cpp:509
     r.qual = (int)(q100 < 0.f ? 0.f : (q100 > 100.f ? 100.f : q100));
     r.n_nodes = V;
-    r.status = fix_duplicate_positions(o.pos, o.mask, o.n, W, lc_unaligned) ? SG_Q_NOSPACE : SG_Q_ALIGNED;
-    A.results[q] = r;
-    A.hdr[q].status = GS_DONE;
+    r.status = nospace ? SG_Q_NOSPACE : SG_Q_ALIGNED;
+    if (lane == 0) { A.results[q] = r; A.hdr[q].status = GS_DONE; }
 }
 
 int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
@@ -275,9 +423,10 @@ int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32
     A.nthr = w->d_nthr; A.nshift = w->d_nshift;
     A.tb = w->d_tb; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.copy_src = s->d_copy_src; A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off;
+    A.rec = reinterpret_cast<NodeRec*>(w->d_rec);
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;
     A.ms = -ap.match_score; A.overhang = ap.overhang; A.lowercase = ap.lowercase;
-    backtrack_kernel<<<(n + 63) / 64, 64, 0, w->stream>>>(A);
+    backtrack_kernel<<<(n + BT_WARPS - 1) / BT_WARPS, 32 * BT_WARPS, 0, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;
