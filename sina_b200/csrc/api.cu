@@ -183,13 +183,23 @@ int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* 
     Index* ix = new Index;
     ix->device = device; ix->N = N; ix->W = W; ix->k = k; ix->nofast = nofast ? 1 : 0;
     ix->max_row_len = max_len ? max_len : 1; ix->total_bases = total;
-    if (N <= TILE_MAX) { ix->tile_size = N + (N & 1); ix->n_tiles = 1; }
-    else { ix->tile_size = TILE_MAX; ix->n_tiles = (N + TILE_MAX - 1) / TILE_MAX; }
     ix->n_slots = 1ull << (2 * (nofast ? k : k - 1));
-    if ((uint64_t)ix->n_tiles * ix->n_slots > (1ull << 31)) {
+    // sub-tile size: SG_SUBTILE (power of two, 32..65536; tests use small ones to reach the multi-tile paths),
+    // doubled until the (k-mer, sub-tile) offset table stays below 2^32 entries
+    uint64_t sub = env_mb("SG_SUBTILE", SUB_DEFAULT);
+    if (sub < 32 || sub > 65536 || (sub & (sub - 1))) { delete ix; SG_FAIL(SG_ERR_ARG, "SG_SUBTILE must be a power of two in 32..65536"); }
+    while (sub < 65536 && ix->n_slots * (((uint64_t)N + sub - 1) / sub) >= (1ull << 32)) sub <<= 1;
+    ix->sub_size = (uint32_t)sub;
+    ix->n_sub = (uint32_t)(((uint64_t)N + sub - 1) / sub);
+    if (ix->n_slots * ix->n_sub >= (1ull << 32)) {
         delete ix;
         SG_FAIL(SG_ERR_LIMIT, "k-mer table too large for this k and reference size");
     }
+    uint64_t tw = env_mb("SG_TILE_WARPS", TILE_WARPS_MAX);
+    tw = std::max<uint64_t>(1, std::min<uint64_t>(tw, std::min<uint64_t>(TILE_WARPS_MAX, (uint64_t)TILE_WARPS_MAX * SUB_DEFAULT / sub)));
+    ix->tile_warps = (uint32_t)std::min<uint64_t>(tw, ix->n_sub);
+    ix->tile_size = ix->tile_warps * ix->sub_size;
+    ix->n_tiles = (ix->n_sub + ix->tile_warps - 1) / ix->tile_warps;
     auto fail = [&](int rc) { sg_index_destroy((sg_index*)ix); return rc; };
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return fail(SG_ERR_CUDA); }
     int rc;
@@ -241,15 +251,14 @@ int sg_index_list(const sg_index* h, uint32_t kmer, uint32_t* ids, uint64_t cap,
     *n = 0;
     if (kmer >= ix->n_slots) return SG_OK;  // fast mode: k-mers not starting with A have no list
     SG_CUDA(cudaSetDevice(ix->device));
-    std::vector<uint32_t> all;
-    for (uint32_t t = 0; t < ix->n_tiles; t++) {
-        uint64_t ab[2];
-        SG_CUDA(cudaMemcpy(ab, ix->d_list_off + (uint64_t)t * ix->n_slots + kmer, 16, cudaMemcpyDeviceToHost));
-        size_t o = all.size();
-        all.resize(o + (ab[1] - ab[0]));
-        if (ab[1] > ab[0])
-            SG_CUDA(cudaMemcpy(all.data() + o, ix->d_postings + ab[0], (ab[1] - ab[0]) * 4, cudaMemcpyDeviceToHost));
-    }
+    std::vector<uint32_t> offs(ix->n_sub + 1);
+    SG_CUDA(cudaMemcpy(offs.data(), ix->d_list_off + (uint64_t)kmer * ix->n_sub, ((size_t)ix->n_sub + 1) * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> loc(offs[ix->n_sub] - offs[0]);
+    if (!loc.empty())
+        SG_CUDA(cudaMemcpy(loc.data(), ix->d_postings + offs[0], loc.size() * 2, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> all(loc.size());
+    for (uint32_t j = 0; j < ix->n_sub; j++)
+        for (uint32_t e = offs[j]; e < offs[j + 1]; e++) all[e - offs[0]] = j * ix->sub_size + loc[e - offs[0]];
     std::sort(all.begin(), all.end());
     *n = all.size();
     if (ids) memcpy(ids, all.data(), std::min<uint64_t>(cap, all.size()) * 4);
@@ -263,11 +272,10 @@ int sg_index_list_sizes(const sg_index* h, const uint32_t* kmers, uint32_t n, ui
     for (uint32_t i = 0; i < n; i++) {
         sizes[i] = 0;
         if (kmers[i] >= ix->n_slots) continue;
-        for (uint32_t t = 0; t < ix->n_tiles; t++) {
-            uint64_t ab[2];
-            SG_CUDA(cudaMemcpy(ab, ix->d_list_off + (uint64_t)t * ix->n_slots + kmers[i], 16, cudaMemcpyDeviceToHost));
-            sizes[i] += ab[1] - ab[0];
-        }
+        uint32_t a = 0, b = 0;
+        SG_CUDA(cudaMemcpy(&a, ix->d_list_off + (uint64_t)kmers[i] * ix->n_sub, 4, cudaMemcpyDeviceToHost));
+        SG_CUDA(cudaMemcpy(&b, ix->d_list_off + ((uint64_t)kmers[i] + 1) * ix->n_sub, 4, cudaMemcpyDeviceToHost));
+        sizes[i] = b - a;
     }
     return SG_OK;
 }
@@ -286,6 +294,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     for (auto& e : s->ev) SG_CUDA(cudaEventCreate(&e));
     const uint64_t Q = max_queries;
     SG_TRY(dmalloc(&s->d_qmasks, s->max_bases + 16)); SG_TRY(dmalloc(&s->d_qoff, Q + 1)); SG_TRY(dmalloc(&s->d_excl, Q));
+    SG_TRY(dmalloc(&s->d_kmers, s->max_bases + 32)); SG_TRY(dmalloc(&s->d_nk, Q));
     SG_TRY(dmalloc(&s->d_cand_n, Q * ix->n_tiles)); SG_TRY(dmalloc(&s->d_nres, Q)); SG_TRY(dmalloc(&s->d_counters, 8));
     SG_TRY(dmalloc(&s->d_fam_n, Q)); SG_TRY(dmalloc(&s->d_retry, 2)); SG_TRY(dmalloc(&s->d_hdr, Q));
     SG_TRY(dmalloc(&s->d_out_cols, s->max_bases + 4)); SG_TRY(dmalloc(&s->d_out_masks, s->max_bases + 16));
@@ -301,7 +310,7 @@ void sg_session_destroy(sg_session* h) {
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     free_align(s);
-    void* ptrs[] = {s->d_qmasks, s->d_qoff, s->d_excl, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
+    void* ptrs[] = {s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);

@@ -28,7 +28,8 @@ void set_error(const std::string& msg);
 
 // ------------------------------------------------------------------ constants
 constexpr int MAX_K = 16;
-constexpr uint32_t TILE_MAX = 98304;         // references per search-histogram tile (u16 counters: 192 KB smem)
+constexpr uint32_t SUB_DEFAULT = 4096;       // references per search sub-tile: one warp owns its u16 score counters (8 KB)
+constexpr uint32_t TILE_WARPS_MAX = 24;      // sub-tiles (= warps) per search CTA: 24 x 8 KB = 192 KB of counters
 constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts in shared memory
 constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
@@ -58,10 +59,11 @@ struct Index {
     uint8_t* d_masks = nullptr;    // [total_bases]
     uint32_t* d_cols = nullptr;    // [total_bases]
     uint64_t* d_row_off = nullptr; // [N+1]
-    uint32_t n_tiles = 1, tile_size = 0;
-    uint64_t n_slots = 0;          // k-mer slots per tile: 4^(k-1) in fast mode (first base A), else 4^k
-    uint64_t* d_list_off = nullptr; // [n_tiles*n_slots + 1], tile-major
-    uint32_t* d_postings = nullptr; // global reference ids, unordered inside a (tile,k-mer) list
+    uint32_t n_tiles = 1, tile_size = 0;   // search CTA tile = tile_warps sub-tiles
+    uint32_t sub_size = SUB_DEFAULT, n_sub = 1, tile_warps = 1;  // sub-tile j = references [j*sub_size, (j+1)*sub_size)
+    uint64_t n_slots = 0;          // k-mer slots: 4^(k-1) in fast mode (first base A), else 4^k
+    uint32_t* d_list_off = nullptr; // [n_slots*n_sub + 1], k-mer-major: list (v, j) = postings[off[v*n_sub+j] .. off[v*n_sub+j+1])
+    uint16_t* d_postings = nullptr; // reference id minus the sub-tile's first id, unordered inside a list
     uint64_t n_postings = 0;
     void* cached = nullptr;  // Session reused by the host-buffer entry points
     std::mutex mu;           // serialises host-buffer calls on this index
@@ -157,6 +159,8 @@ struct Session {
     uint32_t* d_cand_n = nullptr;  // [nq][n_tiles]
     uint64_t* d_ranked = nullptr;  // [nq][find_max] keys in rank order
     uint32_t* d_nres = nullptr;    // [nq]
+    uint32_t* d_kmers = nullptr;   // [max_bases] valid (fast: A-prefixed) k-mers of query q at qoff[q].., duplicates kept
+    uint32_t* d_nk = nullptr;      // [nq] how many
     unsigned long long* d_counters = nullptr;  // [8]: 0 postings, 1 cells
     // family
     uint32_t fam_cap = 0;

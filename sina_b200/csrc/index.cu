@@ -1,4 +1,6 @@
-// K-mer index build on the device: CSR posting lists per (reference tile, k-mer), resident in HBM.
+// K-mer index build on the device: CSR posting lists per (k-mer, reference sub-tile), resident in HBM.
+// A k-mer's lists for consecutive sub-tiles are consecutive, so the whole posting list of a k-mer is one
+// contiguous run partitioned by sub-tile; ids are stored relative to the sub-tile (u16).
 // Replaces kmer_search::impl::build + IndexBuilder (reference src/kmer_search.cpp:152-276):
 //   * every reference row contributes each of its k-mers ONCE (unique_kmers / unique_prefix_kmers, :164-177)
 //   * fast mode keeps only k-mers whose first base is A (prefix_kmers(...,1,BASE_A), src/kmer.h:110-125)
@@ -10,13 +12,13 @@
 
 namespace sg {
 
-// One CTA per reference row. Pass 0 counts unique k-mers per (tile, k-mer) slot, pass 1 writes ids.
+// One CTA per reference row. Pass 0 counts unique k-mers per (k-mer, sub-tile) slot, pass 1 writes ids.
 __global__ void __launch_bounds__(128) idx_rows_kernel(const uint8_t* __restrict__ masks,
                                                         const uint64_t* __restrict__ row_off, uint32_t N, int k,
-                                                        int nofast, uint32_t tile_size, uint64_t n_slots,
+                                                        int nofast, uint32_t sub_size, uint32_t n_sub,
                                                         uint32_t hash_size, unsigned int* __restrict__ counts,
-                                                        const uint64_t* __restrict__ list_off,
-                                                        uint32_t* __restrict__ postings, int pass) {
+                                                        const uint32_t* __restrict__ list_off,
+                                                        uint16_t* __restrict__ postings, int pass) {
     extern __shared__ uint32_t hset[];  // open addressing, key+1, 0 = empty
     for (uint32_t row = blockIdx.x; row < N; row += gridDim.x) {
         const uint64_t a = row_off[row];
@@ -24,7 +26,8 @@ __global__ void __launch_bounds__(128) idx_rows_kernel(const uint8_t* __restrict
         const uint8_t* m = masks + a;
         for (uint32_t i = threadIdx.x; i < hash_size; i += blockDim.x) hset[i] = 0;
         __syncthreads();
-        const uint64_t tile_base = (uint64_t)(row / tile_size) * n_slots;
+        const uint32_t sub = row / sub_size;
+        const uint16_t local = (uint16_t)(row - sub * sub_size);
         if (n > (uint32_t)k) {
             for (uint32_t i = (uint32_t)k - 1 + threadIdx.x; i + 1 < n; i += blockDim.x) {
                 uint32_t v;
@@ -39,9 +42,9 @@ __global__ void __launch_bounds__(128) idx_rows_kernel(const uint8_t* __restrict
                     h = (h + 1) & (hash_size - 1);
                 }
                 if (fresh) {
-                    uint64_t slot = tile_base + v;
+                    uint64_t slot = (uint64_t)v * n_sub + sub;
                     unsigned int c = atomicAdd(&counts[slot], 1u);
-                    if (pass == 1) postings[list_off[slot] + c] = row;
+                    if (pass == 1) postings[list_off[slot] + c] = local;
                 }
             }
         }
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(128) idx_rows_kernel(const uint8_t* __restrict
     }
 }
 
-// ---- exclusive scan of u32 counts into u64 offsets (three small kernels; n can be hundreds of millions)
+// ---- exclusive scan of u32 counts into u32 offsets (three small kernels; n can be hundreds of millions)
 constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 1024, SCAN_BLOCK = SCAN_ITEMS * SCAN_THREADS;
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_partial_kernel(const unsigned int* __restrict__ in, uint64_t n,
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(unsigned long long* __r
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(unsigned int* __restrict__ counts, uint64_t n,
                                                                    const unsigned long long* __restrict__ block_sums,
-                                                                   uint64_t* __restrict__ off) {
+                                                                   uint32_t* __restrict__ off) {
     __shared__ uint32_t red[33];
     uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS], s = 0;
@@ -113,13 +116,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(unsigned int* 
     uint64_t run = block_sums[blockIdx.x] + ex;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; j++) {
-        if (base + j < n) { off[base + j] = run; counts[base + j] = 0; }  // counts become the fill cursors
+        if (base + j < n) { off[base + j] = (uint32_t)run; counts[base + j] = 0; }  // counts become the fill cursors
         run += v[j];
     }
 }
 
 int launch_index_build(Index* ix, cudaStream_t st) {
-    const uint64_t n = (uint64_t)ix->n_tiles * ix->n_slots;
+    const uint64_t n = ix->n_slots * ix->n_sub;
     uint32_t hash_size = 1024;
     while (hash_size < 2 * ix->max_row_len + 2) hash_size <<= 1;
     if (hash_size > 32768) SG_FAIL(SG_ERR_LIMIT, "reference row longer than 16383 bases: not supported by the index builder");
@@ -131,11 +134,11 @@ int launch_index_build(Index* ix, cudaStream_t st) {
     SG_CUDA(cudaMalloc(&counts, n * sizeof(unsigned int)));
     SG_CUDA(cudaMalloc(&block_sums, (nb + 1) * sizeof(unsigned long long)));
     SG_CUDA(cudaMalloc(&total, sizeof(unsigned long long)));
-    SG_CUDA(cudaMalloc(&ix->d_list_off, (n + 1) * sizeof(uint64_t)));
+    SG_CUDA(cudaMalloc(&ix->d_list_off, (n + 1) * sizeof(uint32_t)));
     SG_CUDA(cudaMemsetAsync(counts, 0, n * sizeof(unsigned int), st));
     uint32_t grid = ix->N < 148u * 16u ? (ix->N ? ix->N : 1) : 148u * 16u;
-    idx_rows_kernel<<<grid, 128, smem, st>>>(ix->d_masks, ix->d_row_off, ix->N, ix->k, ix->nofast, ix->tile_size,
-                                            ix->n_slots, hash_size, counts, nullptr, nullptr, 0);
+    idx_rows_kernel<<<grid, 128, smem, st>>>(ix->d_masks, ix->d_row_off, ix->N, ix->k, ix->nofast, ix->sub_size,
+                                            ix->n_sub, hash_size, counts, nullptr, nullptr, 0);
     scan_partial_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(counts, n, block_sums);
     scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, nb, total);
     scan_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(counts, n, block_sums, ix->d_list_off);
@@ -143,10 +146,15 @@ int launch_index_build(Index* ix, cudaStream_t st) {
     SG_CUDA(cudaMemcpyAsync(&h_total, total, sizeof(h_total), cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     ix->n_postings = h_total;
-    SG_CUDA(cudaMemcpyAsync(ix->d_list_off + n, &ix->n_postings, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    SG_CUDA(cudaMalloc(&ix->d_postings, (ix->n_postings + 4) * sizeof(uint32_t)));
-    idx_rows_kernel<<<grid, 128, smem, st>>>(ix->d_masks, ix->d_row_off, ix->N, ix->k, ix->nofast, ix->tile_size,
-                                            ix->n_slots, hash_size, counts, ix->d_list_off, ix->d_postings, 1);
+    if (h_total >= (1ull << 32)) {
+        cudaFree(counts); cudaFree(block_sums); cudaFree(total);
+        SG_FAIL(SG_ERR_LIMIT, "more than 2^32 posting entries: not supported (32-bit list offsets)");
+    }
+    const uint32_t total32 = (uint32_t)h_total;
+    SG_CUDA(cudaMemcpyAsync(ix->d_list_off + n, &total32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMalloc(&ix->d_postings, (ix->n_postings + 64) * sizeof(uint16_t)));
+    idx_rows_kernel<<<grid, 128, smem, st>>>(ix->d_masks, ix->d_row_off, ix->N, ix->k, ix->nofast, ix->sub_size,
+                                            ix->n_sub, hash_size, counts, ix->d_list_off, ix->d_postings, 1);
     SG_CUDA(cudaStreamSynchronize(st));
     SG_CUDA(cudaGetLastError());
     cudaFree(counts); cudaFree(block_sums); cudaFree(total);

@@ -7,110 +7,222 @@
 namespace sg {
 
 // ---------------------------------------------------------------------------------------------------
-// One CTA per (query, reference tile). The tile's scores live in shared memory as packed u16 counters;
-// each warp takes one query k-mer at a time and streams its posting list with coalesced 4-byte loads,
-// one shared-memory atomic per posting. A query k-mer occurring twice is counted twice (all_kmers /
-// prefix_kmers, not the unique_ variants, :391,397). Then the tile's top-`max` (score desc, id desc) is
-// selected with a two-level radix select over the 16-bit scores and emitted unordered.
-__global__ void __launch_bounds__(1024) find_tile_kernel(
-    const uint8_t* __restrict__ qmasks, const uint64_t* __restrict__ qoff, uint32_t N, int k, int nofast,
-    uint32_t tile_size, uint64_t n_slots, const uint64_t* __restrict__ list_off,
-    const uint32_t* __restrict__ postings, uint32_t max, uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_n,
-    unsigned long long* __restrict__ counters) {
-    extern __shared__ uint32_t hist[];  // (tile_n+1)/2 words of two u16 counters
-    __shared__ uint32_t h256[256];
-    __shared__ uint32_t red[33];
-    __shared__ uint32_t sh_sel[4];      // 0: threshold T, 1: count_gt, 2: need_eq, 3: emitted
-    const uint32_t q = blockIdx.x, tile = blockIdx.y, n_tiles = gridDim.y;
-    const uint32_t tile_lo = tile * tile_size;
-    const uint32_t tile_n = min(tile_size, N - tile_lo);
-    const uint32_t words = (tile_n + 1) >> 1;
-    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) hist[i] = 0;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) h256[i] = 0;
-    __syncthreads();
-
+// Valid k-mers of every query (one warp per query), compacted: ambiguous windows dropped, fast mode keeps
+// A-prefixed ones, the last k-mer is never produced (src/kmer.h:69-78,110-125,179-201). A query k-mer occurring
+// twice is listed twice (all_kmers / prefix_kmers, not the unique_ variants, src/kmer_search.cpp:391,397).
+__global__ void __launch_bounds__(128) query_kmers_kernel(const uint8_t* __restrict__ qmasks,
+                                                          const uint64_t* __restrict__ qoff, uint32_t nq, int k,
+                                                          int nofast, uint32_t* __restrict__ kmers,
+                                                          uint32_t* __restrict__ nk) {
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (q >= nq) return;
     const uint8_t* m = qmasks + qoff[q];
     const uint32_t n = (uint32_t)(qoff[q + 1] - qoff[q]);
-    const uint32_t lane = lane_id(), nw = blockDim.x >> 5;
-    unsigned long long my_post = 0;
+    uint32_t* out = kmers + qoff[q];
+    const uint32_t lane = lane_id();
+    uint32_t cnt = 0;
     if (n > (uint32_t)k) {
-        for (uint32_t i = (uint32_t)k - 1 + warp_id(); i + 1 < n; i += nw) {  // last k-mer never produced
-            uint32_t v;
-            if (!kmer_at(m, i, k, v)) continue;                               // warp-uniform
-            if (!nofast && (v >> (2 * (k - 1))) != 0) continue;               // fast: first base A
-            const uint64_t slot = (uint64_t)tile * n_slots + v;
-            const uint64_t a = list_off[slot], b = list_off[slot + 1];
-            uint64_t e = a + lane;
-            for (; e + 96 < b; e += 128) {                                    // 4 independent loads in flight
-                uint32_t i0 = postings[e], i1 = postings[e + 32], i2 = postings[e + 64], i3 = postings[e + 96];
-                i0 -= tile_lo; i1 -= tile_lo; i2 -= tile_lo; i3 -= tile_lo;
-                atomicAdd(&hist[i0 >> 1], 1u << ((i0 & 1) * 16));
-                atomicAdd(&hist[i1 >> 1], 1u << ((i1 & 1) * 16));
-                atomicAdd(&hist[i2 >> 1], 1u << ((i2 & 1) * 16));
-                atomicAdd(&hist[i3 >> 1], 1u << ((i3 & 1) * 16));
-            }
-            for (; e < b; e += 32) {
-                uint32_t i0 = postings[e] - tile_lo;
-                atomicAdd(&hist[i0 >> 1], 1u << ((i0 & 1) * 16));
-            }
-            if (lane == 0) my_post += b - a;
+        for (uint32_t i0 = (uint32_t)k - 1; i0 + 1 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint32_t v = 0;
+            bool ok = i + 1 < n && kmer_at(m, i, k, v);
+            ok = ok && (nofast || (v >> (2 * (k - 1))) == 0);
+            const uint32_t b = __ballot_sync(0xffffffffu, ok);
+            if (ok) out[cnt + __popc(b & ((1u << lane) - 1u))] = v;
+            cnt += __popc(b);
         }
     }
-    if (lane == 0 && my_post) atomicAdd(&counters[0], my_post);
+    if (lane == 0) nk[q] = cnt;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Counting part of find(): one CTA per (query, tile); a tile is up to 24 sub-tiles and every warp OWNS the
+// u16 score counters of one sub-tile in shared memory. The warp walks the query's k-mers and, for each, streams
+// the k-mer's posting list for its own sub-tile: ids inside one list are distinct, so the 32 lanes of one load
+// update 32 different counters with a plain LDS / add / STS and no atomic is needed (shared-memory atomics run
+// at 2 cycles per lane and were the bound of the first version); lists are applied one after the other, in
+// program order. The first 32 postings of FIND_G lists are requested before any of them is applied.
+// Selection: the tile's top-`need` in rank order (score desc, id desc) are those above a threshold score T plus
+// the highest ids among the ties at T. T is found on a histogram of the high scores only ((M/2, M], then
+// (M/4, M/2], ... below the tile's maximum M), so the many low counters cost one compare each.
+constexpr int FIND_G = 8;
+constexpr uint32_t SEL_BINS = 1024;    // widest score window histogrammed at once
+constexpr uint32_t TIE_CAP = 1024;     // ties at the threshold ranked in shared memory (more: id-ordered walk)
+
+struct FindArgs {
+    const uint32_t* kmers; const uint32_t* nk; const uint64_t* qoff;
+    uint32_t N, sub_size, n_sub, tile_warps;
+    const uint32_t* list_off; const uint16_t* postings;
+    uint32_t max; uint64_t* cand; uint32_t* cand_n; unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs A) {
+    extern __shared__ uint32_t hist32[];  // tile_warps * sub_size u16 counters
+    __shared__ uint32_t hist2[SEL_BINS];
+    __shared__ uint32_t tie[TIE_CAP];
+    __shared__ uint32_t red[33];
+    __shared__ uint32_t sh_sel[8];      // 0: T, 1: count_gt, 2: need_eq, 3: emitted, 4: found, 5: ties gathered, 6: count_eq
+    uint16_t* hist = reinterpret_cast<uint16_t*>(hist32);
+    const uint32_t q = blockIdx.x, tile = blockIdx.y, n_tiles = gridDim.y;
+    const uint32_t B = A.sub_size;
+    const uint32_t tile_lo = tile * A.tile_warps * B;
+    const uint32_t tile_n = min(A.tile_warps * B, A.N - tile_lo);
+    const uint32_t words = (tile_n + 1) >> 1;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x, lane = lane_id(), w = warp_id();
+    for (uint32_t i = tid; i < words; i += nt) hist32[i] = 0;
     __syncthreads();
 
-    // ---- top-`need` of the tile in rank order (score desc, id desc) via radix select on the score
-    const uint32_t need = min(max, tile_n);
-    auto score_of = [&](uint32_t i) -> uint32_t { return (hist[i >> 1] >> ((i & 1) * 16)) & 0xffffu; };
-    for (uint32_t i = threadIdx.x; i < tile_n; i += blockDim.x) atomicAdd(&h256[score_of(i) >> 8], 1u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t cum = 0;
-        int b1 = 255;
-        for (; b1 > 0; b1--) { if (cum + h256[b1] >= need) break; cum += h256[b1]; }
-        sh_sel[0] = (uint32_t)b1; sh_sel[1] = cum;
+    // ---- counting
+    const uint32_t sub = tile * A.tile_warps + w;
+    if (sub < A.n_sub) {
+        uint16_t* hw = hist + (size_t)w * B;
+        const uint32_t* kl = A.kmers + A.qoff[q];
+        const uint32_t nk = A.nk[q];
+        const uint16_t* __restrict__ post = A.postings;
+        unsigned long long my_post = 0;
+        for (uint32_t base = 0; base < nk; base += 32) {
+            uint32_t a = 0, len = 0;
+            if (base + lane < nk) {
+                const uint32_t* o = A.list_off + (uint64_t)kl[base + lane] * A.n_sub + sub;
+                a = __ldg(o);
+                len = __ldg(o + 1) - a;
+            }
+            my_post += len;
+            if (!__any_sync(0xffffffffu, len != 0)) continue;
+            for (uint32_t i0 = 0; i0 < 32; i0 += FIND_G) {
+                uint32_t al[FIND_G], ll[FIND_G], x[FIND_G];
+#pragma unroll
+                for (int g = 0; g < FIND_G; g++) {
+                    al[g] = __shfl_sync(0xffffffffu, a, i0 + g);
+                    ll[g] = __shfl_sync(0xffffffffu, len, i0 + g);
+                    x[g] = lane < ll[g] ? (uint32_t)__ldg(post + al[g] + lane) : 0u;
+                }
+#pragma unroll
+                for (int g = 0; g < FIND_G; g++) {
+                    if (ll[g] == 0) continue;                       // warp-uniform
+                    if (lane < ll[g]) hw[x[g]] = (uint16_t)(hw[x[g]] + 1);
+                    __syncwarp();
+                    for (uint32_t e0 = 32; e0 < ll[g]; e0 += 128) {  // long lists: four more loads at a time
+                        uint32_t y[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t e = e0 + 32 * u + lane;
+                            y[u] = e < ll[g] ? (uint32_t)__ldg(post + al[g] + e) : 0xffffffffu;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (y[u] != 0xffffffffu) hw[y[u]] = (uint16_t)(hw[y[u]] + 1);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) my_post += __shfl_xor_sync(0xffffffffu, my_post, o);
+        if (lane == 0 && my_post) atomicAdd(&A.counters[0], my_post);
     }
     __syncthreads();
-    const uint32_t b1 = sh_sel[0];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) h256[i] = 0;
+
+    // ---- selection
+    const uint32_t need = min(A.max, tile_n);
+    uint64_t* out = A.cand + ((uint64_t)q * n_tiles + tile) * A.max;
+    auto score_of = [&](uint32_t i) -> uint32_t { return hist[i]; };
+    // tile maximum
+    uint32_t mx = 0;
+    for (uint32_t i = tid; i < words; i += nt) { const uint32_t v = hist32[i]; mx = max(mx, max(v & 0xffffu, v >> 16)); }
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[w] = mx;
+    if (tid == 0) { sh_sel[3] = 0; sh_sel[4] = 0; sh_sel[5] = 0; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < tile_n; i += blockDim.x) {
-        uint32_t sc = score_of(i);
-        if ((sc >> 8) == b1) atomicAdd(&h256[sc & 255u], 1u);
-    }
+    if (tid == 0) { uint32_t m2 = 0; for (uint32_t i = 0; i < (nt >> 5); i++) m2 = max(m2, red[i]); red[32] = m2; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t cum = sh_sel[1];
-        int b2 = 255;
-        for (; b2 > 0; b2--) { if (cum + h256[b2] >= need) break; cum += h256[b2]; }
-        sh_sel[0] = (b1 << 8) | (uint32_t)b2;  // threshold score T
-        sh_sel[1] = cum;                        // entries with score > T
-        sh_sel[2] = need - cum;                 // entries to take among score == T (highest ids first)
-        sh_sel[3] = 0;
-    }
-    __syncthreads();
-    const uint32_t T = sh_sel[0], count_gt = sh_sel[1];
-    uint64_t* out = cand + ((uint64_t)q * n_tiles + tile) * max;
-    for (uint32_t i = threadIdx.x; i < tile_n; i += blockDim.x) {
-        uint32_t sc = score_of(i);
-        if (sc > T) {
-            uint32_t p = atomicAdd(&sh_sel[3], 1u);
-            out[p] = ((uint64_t)sc << 32) | (tile_lo + i);
+    const uint32_t M = red[32];
+    uint32_t T = 0, count_gt = 0, need_eq = 0, count_eq = 0;
+    {
+        // windows (lo, hi] of scores, highest first; entries above the current window are already counted in cum
+        uint32_t hi = M, cum = 0;
+        for (;;) {
+            uint32_t lo = hi / 2;
+            if (hi - lo > SEL_BINS) lo = hi - SEL_BINS;
+            for (uint32_t i = tid; i < SEL_BINS; i += nt) hist2[i] = 0;
+            __syncthreads();
+            if (hi > 0) {
+                for (uint32_t i = tid; i < words; i += nt) {
+                    const uint32_t v = hist32[i];
+                    const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
+                    if (s0 > lo && s0 <= hi) atomicAdd(&hist2[s0 - lo - 1], 1u);
+                    if (s1 > lo && s1 <= hi && 2 * i + 1 < tile_n) atomicAdd(&hist2[s1 - lo - 1], 1u);
+                }
+            }
+            __syncthreads();
+            if (w == 0) {   // lane L owns bins [32L, 32L+32); find the highest bin where cum + suffix count >= need
+                uint32_t part = 0;
+                for (uint32_t b = 0; b < 32; b++) part += hist2[32 * lane + b];
+                // above = entries in the bins of higher lanes, suffix = entries in the whole window
+                uint32_t above = 0, suffix = 0;
+                for (int l = 31; l >= 0; l--) {
+                    const uint32_t pl = __shfl_sync(0xffffffffu, part, l);
+                    if ((int)lane == l) above = suffix;
+                    suffix += pl;
+                }
+                const bool mine = cum + above < need && cum + above + part >= need;
+                const uint32_t who = __ballot_sync(0xffffffffu, mine);
+                if (who) {
+                    if (mine) {
+                        uint32_t c2 = cum + above;
+                        for (int b = 31; b >= 0; b--) {
+                            const uint32_t hb = hist2[32 * lane + b];
+                            if (c2 + hb >= need) { sh_sel[0] = lo + 1 + 32 * lane + b; sh_sel[1] = c2; sh_sel[2] = need - c2; sh_sel[6] = hb; break; }
+                            c2 += hb;
+                        }
+                        sh_sel[4] = 1;
+                    }
+                } else if (lane == 0) {
+                    sh_sel[1] = cum + suffix;   // everything in this window ranks above the threshold
+                }
+            }
+            __syncthreads();
+            if (sh_sel[4]) { T = sh_sel[0]; count_gt = sh_sel[1]; need_eq = sh_sel[2]; count_eq = sh_sel[6]; break; }
+            cum = sh_sel[1];
+            if (lo == 0) { T = 0; count_gt = cum; need_eq = need - cum; count_eq = tile_n - cum; break; }  // ties at score 0
+            hi = lo;
+            __syncthreads();
         }
     }
-    // ties: walk ids downwards in chunks of blockDim, thread 0 <-> highest id of the chunk
-    uint32_t remaining = sh_sel[2], emitted_eq = 0;
-    for (uint32_t top = tile_n; top > 0 && remaining > 0;) {
-        uint32_t chunk = min(top, (uint32_t)blockDim.x);
-        uint32_t flag = 0, i = 0;
-        if (threadIdx.x < chunk) { i = top - 1 - threadIdx.x; flag = score_of(i) == T; }
-        uint32_t tot, ex = block_exscan(flag, red, &tot);
-        if (flag && ex < remaining) out[count_gt + emitted_eq + ex] = ((uint64_t)T << 32) | (tile_lo + i);
-        uint32_t took = min(tot, remaining);
-        emitted_eq += took; remaining -= took;
-        top -= chunk;
+    // entries above the threshold, and the ties at it
+    const bool rank_ties = T > 0 && count_eq <= TIE_CAP;
+    for (uint32_t i = tid; i < words; i += nt) {
+        const uint32_t v = hist32[i];
+        const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
+        if (s0 > T) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s0 << 32) | (tile_lo + 2 * i);
+        if (s1 > T && 2 * i + 1 < tile_n) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s1 << 32) | (tile_lo + 2 * i + 1);
+        if (rank_ties) {
+            if (s0 == T) tie[atomicAdd(&sh_sel[5], 1u)] = 2 * i;
+            if (s1 == T && 2 * i + 1 < tile_n) tie[atomicAdd(&sh_sel[5], 1u)] = 2 * i + 1;
+        }
     }
-    if (threadIdx.x == 0) cand_n[q * n_tiles + tile] = need;
+    __syncthreads();
+    if (rank_ties) {   // highest ids first: rank = number of tied ids above this one
+        const uint32_t ne = sh_sel[5];
+        for (uint32_t i = tid; i < ne; i += nt) {
+            const uint32_t id = tie[i];
+            uint32_t rk = 0;
+            for (uint32_t j = 0; j < ne; j++) rk += tie[j] > id ? 1u : 0u;
+            if (rk < need_eq) out[count_gt + rk] = ((uint64_t)T << 32) | (tile_lo + id);
+        }
+    } else {
+        // walk ids downwards in chunks of blockDim, thread 0 <-> highest id of the chunk
+        uint32_t remaining = need_eq, emitted_eq = 0;
+        for (uint32_t top = tile_n; top > 0 && remaining > 0;) {
+            uint32_t chunk = min(top, nt);
+            uint32_t flag = 0, i = 0;
+            if (tid < chunk) { i = top - 1 - tid; flag = score_of(i) == T; }
+            uint32_t tot, ex = block_exscan(flag, red, &tot);
+            if (flag && ex < remaining) out[count_gt + emitted_eq + ex] = ((uint64_t)T << 32) | (tile_lo + i);
+            uint32_t took = min(tot, remaining);
+            emitted_eq += took; remaining -= took;
+            top -= chunk;
+        }
+    }
+    if (tid == 0) A.cand_n[q * n_tiles + tile] = need;
 }
 
 // One CTA per query: gather the tiles' candidates, bitonic-sort the 64-bit keys descending in shared
@@ -165,18 +277,21 @@ int launch_find(Session* s, uint32_t max) {
         s->find_cap = max;
     }
     s->find_max = max;
-    const uint32_t tile_n = ix->tile_size < ix->N ? ix->tile_size : ix->N;
-    size_t smem = (size_t)((tile_n + 1) / 2) * 4;
+    const size_t smem = (size_t)ix->tile_warps * ix->sub_size * 2;
     SG_CUDA(cudaFuncSetAttribute(find_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SG_CUDA(cudaFuncSetAttribute(find_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p2 * 8)));
+    query_kmers_kernel<<<(s->nq + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, s->nq, ix->k, ix->nofast,
+                                                              s->d_kmers, s->d_nk);
+    FindArgs A;
+    A.kmers = s->d_kmers; A.nk = s->d_nk; A.qoff = s->d_qoff; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
+    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max;
+    A.cand = s->d_cand; A.cand_n = s->d_cand_n; A.counters = s->d_counters;
     dim3 grid(s->nq, ix->n_tiles);
-    find_tile_kernel<<<grid, 1024, smem, s->stream>>>(s->d_qmasks, s->d_qoff, ix->N, ix->k, ix->nofast, ix->tile_size,
-                                                     ix->n_slots, ix->d_list_off, ix->d_postings, max, s->d_cand,
-                                                     s->d_cand_n, s->d_counters);
+    find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
     find_merge_kernel<<<s->nq, p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
         s->d_cand, s->d_cand_n, ix->n_tiles, max, ix->N, p2, s->d_ranked, s->d_nres);
     SG_CUDA(cudaGetLastError());
-    s->stats.kernel_launches += 2;
+    s->stats.kernel_launches += 3;
     return SG_OK;
 }
 

@@ -146,7 +146,13 @@ def test_wide_indegree_and_far_edges(orc, dp_mode):
     assert r["status"] == sina_b200.SG_Q_NOSPACE
 
 
-def test_index_and_find_vs_oracle(orc):
+@pytest.mark.parametrize("layout", [None, (64, 3), (32, 24), (128, 1)])
+def test_index_and_find_vs_oracle(orc, layout, monkeypatch):
+    """index lists and find() ranks; `layout` = (sub-tile size, warps per search CTA) forces several sub-tiles per
+    CTA and several CTA tiles per query on these small references (production: 4096 x 24)"""
+    if layout:
+        monkeypatch.setenv("SG_SUBTILE", str(layout[0]))
+        monkeypatch.setenv("SG_TILE_WARPS", str(layout[1]))
     for (N, L, W, k, nofast) in [(300, 220, 500, 6, 0), (300, 220, 500, 6, 1), (500, 400, 900, 8, 0), (200, 300, 700, 10, 0)]:
         tree, m, c, o = synth.synth_msa(N, W=W, L=L, seed=11 + N + k)
         msa = O.MSA(m, c, o, W)
