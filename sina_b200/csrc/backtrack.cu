@@ -199,6 +199,20 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         const uint32_t idx = a.x + (t >> 1) * T;
         if (wide) return (__ldcg(&tbq[idx]) >> (16 * (t & 1))) & 0xffffu;
         const uint32_t c = ((uint32_t)__ldcg(&tbq16[idx]) >> (8 * (t & 1))) & 0xffu;
+        const uint32_t sh = (a.y >> 16) & 0xffu;
+        if (sh & TBR_FLAG) {
+            // raw cell (common.cuh): the last winner in evaluation order is the source. The insertion-opened bit
+            // is not stored for these rows (gaps_idx below derives it from the neighbouring cell's source).
+            const uint32_t npw = (a.y >> 24) + (sh & 0x7fu);
+            uint32_t out = 0;
+            if (c & (3u * TBR_MATCH)) out = TB_SRC_MATCH | (((c >> 4) & 1u) << 8);
+            else if (c & TBR_INS) out = TB_SRC_INS;
+            else if (c & (3u * TBR_DEL)) {
+                const uint32_t slot = (c >> 1) & 1u;
+                out = TB_SRC_DEL | (slot << 8) | (((c >> (5 + slot)) & 1u) << 2);
+            }
+            return out | (((c >> (4 + npw)) & 1u) << 3);
+        }
         return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2) | (((c >> 6) & 1u) << 3) | (((c >> 7) & 1u) << 4);
     };
     auto np_of = [](const uint4& a) -> uint32_t { return a.y >> 24; };
@@ -211,6 +225,20 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     };
     // first query position of the insertion run ending at (m, s): lanes look at 32 cells of the row at a time
     auto gaps_idx = [&](const uint4& a, uint32_t s, uint32_t c_s) -> uint32_t {
+        if (!wide && ((a.y >> 16) & TBR_FLAG)) {
+            // raw rows: the insertion at (m, s') extends (E == H at s'-1) iff the source of (m, s'-1) is an
+            // insertion, so ins-open(m, s') == "source of (m, s'-1) is not an insertion" and the run starts at the
+            // first cell left of s whose source is something else
+            uint32_t top = s;                       // cells top-1, top-2, ...
+            while (top > 0) {
+                const bool in = lane < top;
+                const uint32_t cc = in ? cell(a, top - 1 - lane) : TB_SRC_INS;
+                const uint32_t hit = __ballot_sync(FULL, in && (cc & 3u) != TB_SRC_INS);
+                if (hit) return top - 1u - ((uint32_t)__ffs((int)hit) - 1u);
+                top = top > 32 ? top - 32 : 0;
+            }
+            return 0;
+        }
         if (c_s & 16u) return s - 1;
         uint32_t top = s - 1;                       // cells top, top-1, ... (cur > 0)
         while (top > 0) {
@@ -235,7 +263,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     };
     // (value_midx, value_sidx) of cell (m,s) = c
     auto follow = [&](const uint4& a, const uint4& b, uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
-        const uint32_t src = c & 3u, sl = c >> 8, sh = (a.y >> 16) & 0xffu;
+        const uint32_t src = c & 3u, sl = c >> 8, sh = (a.y >> 16) & (wide ? 0xffu : 0x7fu);
         const uint32_t ord = sl > sh ? sl - sh : 0u;  // v2 slots are right-aligned, leading slots repeat ordinal 0
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
         else if (src == TB_SRC_MATCH) { nm = pred_of(a, b, ord); ns = s - 1; }

@@ -48,6 +48,14 @@ constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row live
 constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH = 3;
 // u8 : [1:0] src  [4:2] pred ordinal  [5] chosen deletion opened  [6] last pred's deletion opened  [7] insertion opened
 // u16: [1:0] src  [2] chosen-open [3] last-open [4] ins-open  [15:8] pred ordinal
+// raw u8 (rows of v2 warps specialised on <= 2 predecessor slots, u8 cells): the comparison outcomes as they fall,
+// undecoded. The last winner in evaluation order (deletion slots, insertion, match slots) is the source; the
+// insertion-opened flag is not stored: it is "the source of (m, s-1) is not an insertion" (see backtrack.cu).
+//   [0] deletion via slot 0 won  [1] via slot 1  [2] insertion won  [3] match via slot 0 won  [4] via slot 1
+//   [5] slot 0's deletion opened  [6] slot 1's
+constexpr uint32_t TBR_DEL = 1, TBR_INS = 4, TBR_MATCH = 8, TBR_OPEN = 32;
+constexpr uint32_t TBR_FLAG = 0x80;          // in nshift[]: the row's cells are raw
+__host__ __device__ constexpr bool v2_raw_cells(int npw, bool wide) { return !wide && npw <= 2; }
 
 // ------------------------------------------------------------------ index
 struct Index {

@@ -73,6 +73,17 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
     return r;
 }
+// compare into a float 0/1 (FSET.BF): the raw traceback bits are accumulated with FFMA, off the ALU pipe
+__device__ __forceinline__ float fset_lt(float a, float b) {
+    float r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float fset_le(float a, float b) {
+    float r;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 template <uint32_t OFF>
 __device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
     asm volatile("st.shared.v2.f32 [%0+%3], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y), "n"(OFF) : "memory");
@@ -107,6 +118,8 @@ template <int NPW, bool WIDE, bool EDGES, int PLANES>
 __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
                                           float (&pvp)[NPW], float& Ep, float& Hp, uint32_t& tbw) {
     const float INF = __int_as_float(0x7f800000);
+    constexpr bool RAW = v2_raw_cells(NPW, WIDE);
+    float acc = 0.f;   // RAW: the two cells' bits as a small integer held in a float
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         const uint32_t t = t0 + u;
@@ -130,6 +143,15 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
             // min() and the compare feed different consumers: the running value only depends on the FMNMX chain
             // (this step's critical path to the ring store), the predicates only feed the traceback code.
             // min(a, b) == (a < b ? a : b) here: no NaN, and a -0 cannot arise from these sums.
+            if (RAW) {
+                const float of = fset_lt(v, gv);
+                gm = fminf(v, gv);
+                const float wf = fset_lt(gm, value);
+                value = fminf(value, gm);
+                acc = fmaf(wf, (float)((TBR_DEL << k) << (8 * u)), acc);
+                acc = fmaf(of, (float)((TBR_OPEN << k) << (8 * u)), acc);
+                continue;
+            }
             open = v < gv;
             gm = fminf(v, gv);                                // last predecessor wins
             const bool win = gm < value;
@@ -146,9 +168,14 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
         const bool ext = (Ep == Hp);
         float E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
         if (EDGES) E = s0 ? 1.0f : E;
-        const bool iwin = (E <= value);
-        value = fminf(value, E);
-        code = iwin ? (TB_SRC_INS << SH) : code;
+        if (RAW) {
+            acc = fmaf(fset_le(E, value), (float)(TBR_INS << (8 * u)), acc);
+            value = fminf(value, E);
+        } else {
+            const bool iwin = (E <= value);
+            value = fminf(value, E);
+            code = iwin ? (TB_SRC_INS << SH) : code;
+        }
         // ---- match from (p, s-1) (mesh.h:492-500 -> 360-374)
         float sc;
         if (PLANES == 1) sc = (L.mask & lds_u8(L.qrow + t)) ? L.msw : L.mmsw;   // comp(): the IUPAC masks intersect
@@ -157,14 +184,21 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
 #pragma unroll
         for (int k = 0; k < NPW; k++) {
             const float v = __fadd_rn(pvp[k], sc);
+            if (RAW) {
+                acc = fmaf(fset_lt(v, value), (float)((TBR_MATCH << k) << (8 * u)), acc);
+                value = fminf(value, v);
+                continue;
+            }
             const bool win = v < value;
             value = fminf(value, v);
             code = win ? (WIDE ? ((TB_SRC_MATCH | (k << 8)) << SH) : ((TB_SRC_MATCH | (k << 2)) << SH)) : code;
         }
-        const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
-        const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
-        code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
-        tbw |= code;
+        if (!RAW) {
+            const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
+            const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
+            code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
+            tbw |= code;
+        }
 #pragma unroll
         for (int k = 0; k < NPW; k++) pvp[k] = cur[k];
         Ep = E;
@@ -175,6 +209,8 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
         if (EDGES && t == L.t_last) *L.lastcol_ptr = value;
         __syncthreads();
     }
+    // the integer sits in the low mantissa bits of acc + 2^23 (acc < 2^16, exact)
+    if (RAW) tbw = __float_as_uint(__fadd_rn(acc, 8388608.0f));
 }
 
 // [w_first, w_last] = steps at which some row of this warp is inside the query; outside of it the warp only keeps
@@ -189,17 +225,32 @@ __device__ __forceinline__ void v2_fast_group(const V2Lane<NPW>& L, const float 
     for (int k = 0; k < NPW; k++) pvp[k] = 0.f;
     float Ep = 1.0f, Hp = 1.0f;
     uint16_t* tbg16 = reinterpret_cast<uint16_t*>(tbg);   // u8 cells: this lane's halfword of step pair 0
-    for (uint32_t t0 = 0; t0 < steps4; t0 += 2) {
-        if (t0 + 1 < w_first || t0 > w_last) {
-            __syncthreads(); __syncthreads();
-            continue;
+    // Step pairs [0, e0) and [e1, steps4): the warp only keeps the barriers. [e0, c0) and [c1, e1): some row is at
+    // an edge of the query (EDGES variant). [c0, c1): every row strictly inside; that loop carries no window tests.
+    const uint32_t e0 = min(w_first & ~1u, steps4);
+    const uint32_t e1 = min((w_last & ~1u) + 2u, steps4);
+    uint32_t c0 = (b_first + 1u) & ~1u, c1 = (b_last + 1u) & ~1u;   // bulk pairs: t0 >= b_first && t0 + 1 <= b_last
+    if (b_last == 0xFFFFFFFFu || b_last < b_first || c0 >= c1 || c0 < e0 || c1 > e1) c0 = c1 = e1;
+    for (uint32_t t0 = 0; t0 < e0; t0 += 2) { __syncthreads(); __syncthreads(); }
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ph++) {
+        const uint32_t a = ph ? c1 : e0, b = ph ? e1 : c0;
+        for (uint32_t t0 = a; t0 < b; t0 += 2) {
+            uint32_t tbw = 0;
+            v2_steps2<NPW, WIDE, true, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+            if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
+            else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
         }
-        uint32_t tbw = 0;
-        if (t0 >= b_first && t0 + 1 <= b_last) v2_steps2<NPW, WIDE, false, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
-        else v2_steps2<NPW, WIDE, true, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
-        if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
-        else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
+        if (ph == 0) {
+            for (uint32_t t0 = c0; t0 < c1; t0 += 2) {
+                uint32_t tbw = 0;
+                v2_steps2<NPW, WIDE, false, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+                if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
+                else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
+            }
+        }
     }
+    for (uint32_t t0 = e1; t0 < steps4; t0 += 2) { __syncthreads(); __syncthreads(); }
 }
 
 template <int NPW, bool WIDE, int PLANES>
@@ -406,7 +457,7 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
             }
             const uint32_t npw = max(1u, __reduce_max_sync(0xffffffffu, np));
             const bool warp_has_rows = __any_sync(0xffffffffu, valid);
-            if (valid) A.nshift[io + m] = (uint8_t)(npw - np);
+            if (valid) A.nshift[io + m] = (uint8_t)((npw - np) | (v2_raw_cells((int)npw, WIDE) ? TBR_FLAG : 0u));
             uint32_t* tbg = tbq + gi.tb_off;
             __syncthreads();  // matches the loader's prologue barrier
             if (!warp_has_rows) {
