@@ -173,7 +173,8 @@ def workload_config(args, queries_per_step):
                                                                      1500 if args.kind == "full" else 280, args.refs, W_COLS, KMER),
             "queries_per_step_per_gpu": queries_per_step, "refs": args.refs, "columns": W_COLS, "k": KMER,
             "l2": "inputs larger than L2 (index 0.4 GB + >30 GB traceback written per step)",
-            "timing": "host clock between device-wide synchronisations (the library runs on its own streams); per-stage "
+            "timing": "value: CUDA events on the library's own stream around the K steps (sg_session_timer), max over "
+                      "ranks; e2e: host clock between device-wide synchronisations (host copies are part of it); per-stage "
                       "times are CUDA events on the launching streams and overlap across the chunk pipeline",
             "parallelism": "queries sharded over GPUs, index replicated, no collective"}
 
@@ -224,10 +225,12 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
+    sess.timer_start()          # CUDA event on the library's stream (torch.cuda.Event only sees torch's streams)
     for _ in range(args.steps):
         step_device()
+    dt = sess.timer_stop() / 1e3  # device clock between the two events: every kernel of the K steps lies inside
     barrier()
-    dt = time.perf_counter() - t0
+    dt_host = time.perf_counter() - t0
     st = sess.stats()
     # ---- end-to-end through the host-buffer C-ABI call
     for _ in range(min(args.warmup, 1) or 1):
@@ -328,7 +331,7 @@ def main():
                               "bytes_per_query": "4*P + 2*N + 8*max", "postings_per_query": posts / nq_iso},
             "stages_ms_per_step_isolated": {k: st_iso[k] * (nq / nq_iso) for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
             "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
-            "cells_per_query": cells / (nq * args.steps), "aligned_ok": n_ok,
+            "cells_per_query": cells / (nq * args.steps), "aligned_ok": n_ok, "ms_per_step_host_clock": dt_host / args.steps * 1e3,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

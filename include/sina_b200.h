@@ -151,6 +151,9 @@ typedef struct sg_stage_stats {
     uint64_t kernel_launches;
 } sg_stage_stats;
 int sg_session_stats(sg_session* s, sg_stage_stats* st, int reset);
+/* device clock over a run of stage calls: stop=0 records the start event on the session's stream, stop=1 records the
+ * end event, waits for it and returns the elapsed milliseconds between the two (cudaEventElapsedTime) */
+int sg_session_timer(sg_session* s, int stop, float* ms);
 
 /* test hooks: device graph / traceback dumps for one query of the session after sg_session_align */
 int sg_session_dump_graph(sg_session* s, uint32_t q, uint32_t cap_nodes, uint32_t cap_edges, uint32_t* V,

@@ -21,7 +21,7 @@ EXPORTS = [
     "sg_find_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
     "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_family",
     "sg_session_set_family", "sg_session_align", "sg_session_sync", "sg_session_download_find",
-    "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_dump_graph",
+    "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
 ]
 
 SG_Q_ALIGNED, SG_Q_COPIED, SG_Q_SKIPPED, SG_Q_NOSPACE, SG_Q_NOFAMILY = 0, 1, 2, 3, 4
@@ -119,6 +119,7 @@ def lib():
     L.sg_session_download_family.argtypes = [C.c_void_p, C.c_uint32, u32p, f32p, i32p]
     L.sg_session_download_align.argtypes = [C.c_void_p, u32p, u8p, C.c_void_p]
     L.sg_session_stats.argtypes = [C.c_void_p, C.POINTER(StageStats), C.c_int]
+    L.sg_session_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
     L.sg_session_dump_graph.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32),
                                         C.POINTER(C.c_uint32), u32p, u8p, f32p, u32p, u32p]
     _lib = L
@@ -300,6 +301,15 @@ class Session:
         st = StageStats()
         _check(lib().sg_session_stats(self.h, C.byref(st), int(reset)))
         return {f: getattr(st, f) for f, _ in StageStats._fields_}
+
+    def timer_start(self):
+        """CUDA event on the session's stream; timer_stop() returns the device milliseconds since."""
+        _check(lib().sg_session_timer(self.h, 0, None))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(lib().sg_session_timer(self.h, 1, C.byref(ms)))
+        return float(ms.value)
 
     def dump_graph(self, q, cap_nodes=1 << 17, cap_edges=1 << 19):
         V, E = C.c_uint32(), C.c_uint32()

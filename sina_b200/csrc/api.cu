@@ -544,6 +544,20 @@ int sg_session_stats(sg_session* h, sg_stage_stats* st, int reset) {
     return SG_OK;
 }
 
+// Device clock around a run of stage calls: CUDA events on the session's stream. Every stage call returns with the
+// session's streams drained, so the two events bracket all the kernels launched between them.
+int sg_session_timer(sg_session* h, int stop, float* ms) {
+    Session* s = (Session*)h;
+    if (!s || (stop && !ms)) SG_FAIL(SG_ERR_ARG, "sg_session_timer: bad argument");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_CUDA(cudaEventRecord(s->ev[stop ? 7 : 6], s->stream));
+    if (stop) {
+        SG_CUDA(cudaEventSynchronize(s->ev[7]));
+        SG_CUDA(cudaEventElapsedTime(ms, s->ev[6], s->ev[7]));
+    }
+    return SG_OK;
+}
+
 int sg_session_dump_graph(sg_session* h, uint32_t q, uint32_t cap_nodes, uint32_t cap_edges, uint32_t* V, uint32_t* E,
                           uint32_t* col, uint8_t* mask, float* weight, uint32_t* pred_off, uint32_t* preds) {
     Session* s = (Session*)h;

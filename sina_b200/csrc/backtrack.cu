@@ -3,9 +3,10 @@
 // (src/cseq.cpp:456-594), decoding the packed traceback written by mesh.cu instead of the reference's
 // 28-byte cells:
 //   value_(midx,sidx) of a cell  = NONE: (0,0) | MATCH via pred i: (pred_i, s-1) | INS: (m, gaps_idx(m,s))
-//                                  | DEL via pred i: opened ? (pred_i, s) : (gapm_idx(pred_i, s), s)
+//                                  | DEL via pred i: ob(pred_i, s) ? (pred_i, s) : (gapm_idx(pred_i, s), s)
 //   gaps_idx(m,s) = ins-open(m,s) ? s-1 : gaps_idx(m,s-1), gaps_idx(m,0) = 0            (mesh.h:340-349)
-//   gapm_idx(x,s) = no preds ? 0 : last-open(x,s) ? lastpred(x) : gapm_idx(lastpred(x), s)  (mesh.h:315-323)
+//   gapm_idx(x,s) = no preds ? 0 : ob(lastpred(x), s) ? lastpred(x) : gapm_idx(lastpred(x), s)  (mesh.h:315-323)
+//   ob(x,s) = "a deletion leaving (x,s) opens the gap", stored in (x,s)'s own traceback cell (common.cuh)
 //
 // The walk is a pointer chase through HBM (one traceback byte per step, 3-4 MB per query), so the kernel is
 // organised around the length of the dependent-load chain:
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         a = __ldcg(p);
         b = __ldcg(p + 1);
     };
-    // decoded traceback cell: src | ord<<8 | chosen_open<<2 | last_open<<3 | ins_open<<4 (the wide layout)
+    // decoded traceback cell: src | slot<<8 | ob<<2 (the wide layout; ob = a deletion leaving the cell opens, common.cuh)
     auto cell = [&](const uint4& a, uint32_t s) -> uint32_t {
         const uint32_t t = s + (a.y & 0xffffu);
         const uint32_t idx = a.x + (t >> 1) * T;
@@ -201,19 +202,15 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         const uint32_t c = ((uint32_t)__ldcg(&tbq16[idx]) >> (8 * (t & 1))) & 0xffu;
         const uint32_t sh = (a.y >> 16) & 0xffu;
         if (sh & TBR_FLAG) {
-            // raw cell (common.cuh): the last winner in evaluation order is the source. The insertion-opened bit
-            // is not stored for these rows (gaps_idx below derives it from the neighbouring cell's source).
-            const uint32_t npw = (a.y >> 24) + (sh & 0x7fu);
+            // raw cell (common.cuh): the last winner in evaluation order is the source
+            const uint32_t mt = (c >> 4) & 7u, dl = c & 7u;
             uint32_t out = 0;
-            if (c & (3u * TBR_MATCH)) out = TB_SRC_MATCH | (((c >> 4) & 1u) << 8);
+            if (mt) out = TB_SRC_MATCH | ((31u - (uint32_t)__clz((int)mt)) << 8);
             else if (c & TBR_INS) out = TB_SRC_INS;
-            else if (c & (3u * TBR_DEL)) {
-                const uint32_t slot = (c >> 1) & 1u;
-                out = TB_SRC_DEL | (slot << 8) | (((c >> (5 + slot)) & 1u) << 2);
-            }
-            return out | (((c >> (4 + npw)) & 1u) << 3);
+            else if (dl) out = TB_SRC_DEL | ((31u - (uint32_t)__clz((int)dl)) << 8);
+            return out | ((c >> 7) << 2);
         }
-        return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2) | (((c >> 6) & 1u) << 3) | (((c >> 7) & 1u) << 4);
+        return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
     };
     auto np_of = [](const uint4& a) -> uint32_t { return a.y >> 24; };
     auto pred_of = [&](const uint4& a, const uint4& b, uint32_t ord) -> uint32_t {
@@ -223,43 +220,21 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         if (ord == 3) return b.w;
         return __ldcg(&preds[a.w + ord]);
     };
-    // first query position of the insertion run ending at (m, s): lanes look at 32 cells of the row at a time
-    auto gaps_idx = [&](const uint4& a, uint32_t s, uint32_t c_s) -> uint32_t {
-        if (!wide && ((a.y >> 16) & TBR_FLAG)) {
-            // raw rows: the insertion at (m, s') extends (E == H at s'-1) iff the source of (m, s'-1) is an
-            // insertion, so ins-open(m, s') == "source of (m, s'-1) is not an insertion" and the run starts at the
-            // first cell left of s whose source is something else
-            uint32_t top = s;                       // cells top-1, top-2, ...
-            while (top > 0) {
-                const bool in = lane < top;
-                const uint32_t cc = in ? cell(a, top - 1 - lane) : TB_SRC_INS;
-                const uint32_t hit = __ballot_sync(FULL, in && (cc & 3u) != TB_SRC_INS);
-                if (hit) return top - 1u - ((uint32_t)__ffs((int)hit) - 1u);
-                top = top > 32 ? top - 32 : 0;
-            }
-            return 0;
-        }
-        if (c_s & 16u) return s - 1;
-        uint32_t top = s - 1;                       // cells top, top-1, ... (cur > 0)
+    // gaps_idx(m, s): first query position of the insertion run ending at (m, s). The insertion at (m, s') extends
+    // iff gaps_val == value at (m, s'-1) (mesh.h:340-349), i.e. iff the source of (m, s'-1) is an insertion (the
+    // insertion candidate wins ties against everything evaluated before it and loses only to a strictly smaller
+    // match), so the run starts at the first cell left of s whose source is something else. Lanes look at 32 cells
+    // of the row at a time.
+    auto gaps_idx = [&](const uint4& a, uint32_t s) -> uint32_t {
+        uint32_t top = s;                       // cells top-1, top-2, ...
         while (top > 0) {
-            const bool in = lane < top;             // cur = top - lane >= 1
-            const uint32_t cc = in ? cell(a, top - lane) : 0u;
-            const uint32_t hit = __ballot_sync(FULL, in && (cc & 16u));
-            if (hit) return top - ((uint32_t)__ffs((int)hit) - 1u) - 1u;
+            const bool in = lane < top;
+            const uint32_t cc = in ? cell(a, top - 1 - lane) : TB_SRC_INS;
+            const uint32_t hit = __ballot_sync(FULL, in && (cc & 3u) != TB_SRC_INS);
+            if (hit) return top - 1u - ((uint32_t)__ffs((int)hit) - 1u);
             top = top > 32 ? top - 32 : 0;
         }
         return 0;
-    };
-    auto gapm_idx = [&](uint32_t x, uint32_t s) -> uint32_t {
-        for (;;) {
-            uint4 a, b;
-            ldrec(x, a, b);
-            const uint32_t np = np_of(a);
-            if (np == 0) return 0;
-            const uint32_t lp = pred_of(a, b, np - 1);
-            if (cell(a, s) & 8u) return lp;
-            x = lp;
-        }
     };
     // (value_midx, value_sidx) of cell (m,s) = c
     auto follow = [&](const uint4& a, const uint4& b, uint32_t m, uint32_t s, uint32_t c, uint32_t& nm, uint32_t& ns) {
@@ -267,13 +242,21 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         const uint32_t ord = sl > sh ? sl - sh : 0u;  // v2 slots are right-aligned, leading slots repeat ordinal 0
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
         else if (src == TB_SRC_MATCH) { nm = pred_of(a, b, ord); ns = s - 1; }
-        else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(a, s, c); }
+        else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(a, s); }
         else {
-            const uint32_t p = pred_of(a, b, ord);
-            // deletion opened at p? For the last predecessor that is the cell's last-opened bit (the specialised
-            // DP step does not set the chosen-opened bit for its last slot)
-            const bool opened = (c & 4u) || (ord + 1 == np_of(a) && (c & 8u));
-            nm = opened ? p : gapm_idx(p, s);
+            // deletion via predecessor p: (p, s) if it opened there, else gapm_idx(p, s): down the chain of last
+            // predecessors to the first cell whose deletion opens; a row without predecessor ends it at node 0
+            // (init_edge, mesh.h:294-297)
+            uint32_t x = pred_of(a, b, ord);
+            for (;;) {
+                uint4 xa, xb;
+                ldrec(x, xa, xb);
+                if (cell(xa, s) & 4u) break;
+                const uint32_t np = np_of(xa);
+                if (np == 0) { x = 0; break; }
+                x = pred_of(xa, xb, np - 1);
+            }
+            nm = x;
             ns = s;
         }
     };

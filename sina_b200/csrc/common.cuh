@@ -44,18 +44,22 @@ constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan 
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
 
 // traceback cell layout (mesh.cu writes, backtrack.cu decodes); cells of two consecutive steps share one store:
-// tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells
+// tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells.
+// Deletion candidates are computed once, by the row they leave from: a row publishes (value, dm) with
+//   dm(x,s) = min(value(x,s) + gap, gapm_val(x,s) + gapext)            (deletion(), src/mesh.h:305-330, seen from src)
+// and records in ITS OWN cell the bit ob(x,s) = value(x,s) + gap < gapm_val(x,s) + gapext ("a deletion leaving this
+// cell opens the gap"). The reference's per-edge facts follow from it: the deletion via predecessor p opened iff
+// ob(p,s); gapm_idx(x,s) = ob(lastpred(x), s) ? lastpred(x) : gapm_idx(lastpred(x), s).
 constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH = 3;
-// u8 : [1:0] src  [4:2] pred ordinal  [5] chosen deletion opened  [6] last pred's deletion opened  [7] insertion opened
-// u16: [1:0] src  [2] chosen-open [3] last-open [4] ins-open  [15:8] pred ordinal
-// raw u8 (rows of v2 warps specialised on <= 2 predecessor slots, u8 cells): the comparison outcomes as they fall,
+// u8 : [1:0] src  [4:2] pred slot  [5] ob  [7] insertion opened
+// u16: [1:0] src  [2] ob  [4] ins-open  [15:8] pred slot
+// raw u8 (rows of v2 warps specialised on <= 3 predecessor slots, u8 cells): the comparison outcomes as they fall,
 // undecoded. The last winner in evaluation order (deletion slots, insertion, match slots) is the source; the
 // insertion-opened flag is not stored: it is "the source of (m, s-1) is not an insertion" (see backtrack.cu).
-//   [0] deletion via slot 0 won  [1] via slot 1  [2] insertion won  [3] match via slot 0 won  [4] via slot 1
-//   [5] slot 0's deletion opened  [6] slot 1's
-constexpr uint32_t TBR_DEL = 1, TBR_INS = 4, TBR_MATCH = 8, TBR_OPEN = 32;
+//   [2:0] deletion via slot k won  [3] insertion won  [6:4] match via slot k won  [7] ob
+constexpr uint32_t TBR_DEL = 1, TBR_INS = 8, TBR_MATCH = 16, TBR_OB = 128;
 constexpr uint32_t TBR_FLAG = 0x80;          // in nshift[]: the row's cells are raw
-__host__ __device__ constexpr bool v2_raw_cells(int npw, bool wide) { return !wide && npw <= 2; }
+__host__ __device__ constexpr bool v2_raw_cells(int npw, bool wide) { return !wide && npw <= 3; }
 
 // ------------------------------------------------------------------ index
 struct Index {

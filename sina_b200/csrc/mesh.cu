@@ -98,7 +98,6 @@ struct V2Lane {
     uint32_t mmsw_bits, dsc; // PLANES > 1: bits of mismatch*weight, and bits(match*weight) - bits(mismatch*weight)
     float msw, mmsw;         // PLANES == 1: (mis)match score * weight (+inf for rows without predecessor)
     uint32_t mask;           // PLANES == 1: the node's IUPAC mask
-    float dgp, dgpe;         // gap penalties (0 for rows without predecessor, see below)
     float initv;
     uint32_t t_first, t_last;
     float* lastcol_ptr;
@@ -108,15 +107,19 @@ struct V2Lane {
 // Slots are right-aligned: a row with np < NPW repeats its first predecessor in the NPW-np leading slots (a
 // repeated candidate ties with its first copy and strict '<' keeps the first, so nothing changes; backtrack maps
 // slot -> ordinal with max(0, slot - shift)).
-// Rows without predecessor read the constant ring column (value 1, gapm +inf) with dgp = dgpe = 0: the deletion
-// candidate is exactly 1, never below the initial 1, and leaves gapm_val = 1 (init_edge, mesh.h:294-301); their match
-// score is +inf (mmsw_bits = +inf, dsc = 0), so no match candidate can win either.
+// A ring cell is (value, dm): dm = min(value + gap, gapm_val + gapext) is the deletion candidate this cell offers
+// to every successor row (deletion(), mesh.h:305-330, evaluated once by the row it leaves from instead of once per
+// edge); the row's own gapm_val is the dm of its last predecessor ("last predecessor wins").
+// Rows without predecessor read the constant ring column (value 1, dm 1): the deletion candidate 1 is never below
+// the initial 1 and leaves gapm_val = 1 (init_edge, mesh.h:294-301); their match score is +inf (mmsw_bits = +inf,
+// dsc = 0), so no match candidate can win either.
 // The match score is read from the query table as a 0/1 byte and turned into the float's bits with integer
 // arithmetic (exact, and off the ALU pipe that bounds this kernel).
+// En carries gaps_val of the next cell of the row: (m,s)'s insertion candidate is fixed when (m,s-1) is finished.
 // EDGES: some lane may be at s == 0 or s == Lq-1 in these steps; the other (vast majority of) steps skip those tests.
 template <int NPW, bool WIDE, bool EDGES, int PLANES>
 __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
-                                          float (&pvp)[NPW], float& Ep, float& Hp, uint32_t& tbw) {
+                                          float (&pvp)[NPW], float& En, uint32_t& tbw) {
     const float INF = __int_as_float(0x7f800000);
     constexpr bool RAW = v2_raw_cells(NPW, WIDE);
     float acc = 0.f;   // RAW: the two cells' bits as a small integer held in a float
@@ -129,44 +132,31 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
         // init (mesh.h:294-301,469-473): 1000000, or 1 for rows without predecessor. The s == 0 column is an
         // edge too (init 1): there the forced insertion candidate E = 1 below supplies that 1.
         float value = L.initv;
-        float gm = 1.0f;
+        float gmin = 1.0f;
         uint32_t code = 0;
-        bool open = false;
         float cur[NPW];
         // ---- deletion over predecessor slots, ascending id (mesh.h:475-478 -> 305-330)
 #pragma unroll
         for (int k = 0; k < NPW; k++) {
             const float2 c = lds_f2(L.pk[k] + xs);
             cur[k] = c.x;
-            const float v = __fadd_rn(c.x, L.dgp);
-            const float gv = __fadd_rn(c.y, L.dgpe);
+            gmin = c.y;                                       // last predecessor wins
             // min() and the compare feed different consumers: the running value only depends on the FMNMX chain
             // (this step's critical path to the ring store), the predicates only feed the traceback code.
             // min(a, b) == (a < b ? a : b) here: no NaN, and a -0 cannot arise from these sums.
             if (RAW) {
-                const float of = fset_lt(v, gv);
-                gm = fminf(v, gv);
-                const float wf = fset_lt(gm, value);
-                value = fminf(value, gm);
-                acc = fmaf(wf, (float)((TBR_DEL << k) << (8 * u)), acc);
-                acc = fmaf(of, (float)((TBR_OPEN << k) << (8 * u)), acc);
-                continue;
+                acc = fmaf(fset_lt(c.y, value), (float)((TBR_DEL << k) << (8 * u)), acc);
+                value = fminf(value, c.y);
+            } else {
+                const bool win = c.y < value;
+                value = fminf(value, c.y);
+                code = win ? (WIDE ? ((TB_SRC_DEL | (k << 8)) << SH) : ((TB_SRC_DEL | (k << 2)) << SH)) : code;
             }
-            open = v < gv;
-            gm = fminf(v, gv);                                // last predecessor wins
-            const bool win = gm < value;
-            value = fminf(value, gm);
-            const uint32_t cd = WIDE ? ((TB_SRC_DEL | (k << 8)) << SH) : ((TB_SRC_DEL | (k << 2)) << SH);
-            const uint32_t co = WIDE ? (cd | (4u << SH)) : (cd | (32u << SH));
-            // the chosen-deletion-opened bit of the LAST slot is the cell's last-opened bit (set below): backtrack
-            // reads that one when the chosen predecessor is the last
-            code = win ? ((k < NPW - 1 && open) ? co : cd) : code;
         }
         // ---- insertion from (m, s-1) (mesh.h:486-490 -> 332-358). At s == 0 the reference evaluates no
         // insertion, gaps_val stays 1 and value starts from 1: E is forced to 1, so value = min(1, deletions)
         // exactly as there (the traceback of an s == 0 cell is never followed).
-        const bool ext = (Ep == Hp);
-        float E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
+        float E = En;
         if (EDGES) E = s0 ? 1.0f : E;
         if (RAW) {
             acc = fmaf(fset_le(E, value), (float)(TBR_INS << (8 * u)), acc);
@@ -187,23 +177,22 @@ __device__ __forceinline__ void v2_steps2(const V2Lane<NPW>& L, const float gp, 
             if (RAW) {
                 acc = fmaf(fset_lt(v, value), (float)((TBR_MATCH << k) << (8 * u)), acc);
                 value = fminf(value, v);
-                continue;
+            } else {
+                const bool win = v < value;
+                value = fminf(value, v);
+                code = win ? (WIDE ? ((TB_SRC_MATCH | (k << 8)) << SH) : ((TB_SRC_MATCH | (k << 2)) << SH)) : code;
             }
-            const bool win = v < value;
-            value = fminf(value, v);
-            code = win ? (WIDE ? ((TB_SRC_MATCH | (k << 8)) << SH) : ((TB_SRC_MATCH | (k << 2)) << SH)) : code;
         }
-        if (!RAW) {
-            const uint32_t f_open = WIDE ? (8u << SH) : (64u << SH);
-            const uint32_t f_ins = WIDE ? (16u << SH) : (128u << SH);
-            code |= (open ? f_open : 0u) | (ext ? 0u : f_ins);    // the insertion flag of an s == 0 cell is never read
-            tbw |= code;
-        }
+        // ---- what this cell offers: the deletion candidate of its successors and the row's next insertion
+        const float vgp = __fadd_rn(value, gp);
+        const float ggpe = __fadd_rn(gmin, gpe);
+        const float dm = fminf(vgp, ggpe);
+        if (RAW) acc = fmaf(fset_lt(vgp, ggpe), (float)(TBR_OB << (8 * u)), acc);
+        else tbw |= code | ((vgp < ggpe) ? (WIDE ? (4u << SH) : (32u << SH)) : 0u);
+        En = (E == value) ? __fadd_rn(E, gpe) : vgp;          // extension iff gaps_val == value (mesh.h:340-349)
 #pragma unroll
         for (int k = 0; k < NPW; k++) pvp[k] = cur[k];
-        Ep = E;
-        Hp = value;
-        const float2 out = make_float2(value, gm);
+        const float2 out = make_float2(value, dm);
         sts_f2<0>(L.wadr + xs, out);
         sts_f2<RB>(L.wadr + xs, out);
         if (EDGES && t == L.t_last) *L.lastcol_ptr = value;
@@ -223,7 +212,7 @@ __device__ __forceinline__ void v2_fast_group(const V2Lane<NPW>& L, const float 
     float pvp[NPW];
 #pragma unroll
     for (int k = 0; k < NPW; k++) pvp[k] = 0.f;
-    float Ep = 1.0f, Hp = 1.0f;
+    float En = 1.0f;
     uint16_t* tbg16 = reinterpret_cast<uint16_t*>(tbg);   // u8 cells: this lane's halfword of step pair 0
     // Step pairs [0, e0) and [e1, steps4): the warp only keeps the barriers. [e0, c0) and [c1, e1): some row is at
     // an edge of the query (EDGES variant). [c0, c1): every row strictly inside; that loop carries no window tests.
@@ -237,14 +226,14 @@ __device__ __forceinline__ void v2_fast_group(const V2Lane<NPW>& L, const float 
         const uint32_t a = ph ? c1 : e0, b = ph ? e1 : c0;
         for (uint32_t t0 = a; t0 < b; t0 += 2) {
             uint32_t tbw = 0;
-            v2_steps2<NPW, WIDE, true, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+            v2_steps2<NPW, WIDE, true, PLANES>(L, gp, gpe, t0, pvp, En, tbw);
             if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
             else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
         }
         if (ph == 0) {
             for (uint32_t t0 = c0; t0 < c1; t0 += 2) {
                 uint32_t tbw = 0;
-                v2_steps2<NPW, WIDE, false, PLANES>(L, gp, gpe, t0, pvp, Ep, Hp, tbw);
+                v2_steps2<NPW, WIDE, false, PLANES>(L, gp, gpe, t0, pvp, En, tbw);
                 if (WIDE) tbg[(uint64_t)(t0 >> 1) * T] = tbw;
                 else tbg16[(uint64_t)(t0 >> 1) * T] = (uint16_t)tbw;
             }
@@ -264,8 +253,6 @@ __device__ __forceinline__ void v2_fast_dispatch(const MeshArgs& A, uint32_t sri
     const bool hr = np > 0;
     const float msw = __fmul_rn(A.ms, w);    // (comp ? match : mismatch) * weight  (scoring_schemes.h:150-156)
     const float mmsw = __fmul_rn(A.mms, w);
-    L.dgp = hr ? A.gp : 0.0f;
-    L.dgpe = hr ? A.gpe : 0.0f;
     L.initv = hr ? 1000000.0f : 1.0f;
     L.mmsw_bits = hr ? __float_as_uint(mmsw) : 0x7f800000u;
     L.dsc = hr ? __float_as_uint(msw) - __float_as_uint(mmsw) : 0u;
@@ -292,7 +279,7 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
     // slot k of this lane is real iff k >= npw - np; real slot k is predecessor ordinal k - (npw - np)
     const float gp = A.gp, gpe = A.gpe;
     const uint32_t shift = npw - np;
-    float Ep = 1.0f, Hp = 1.0f;
+    float En = 1.0f;
     const float2* ring = reinterpret_cast<const float2*>(smem);
     float2* ringw = reinterpret_cast<float2*>(smem);
     uint16_t* tbg16 = reinterpret_cast<uint16_t*>(tbg);
@@ -305,22 +292,15 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
             if (s >= 0 && s < (int)Lq) {
                 const bool s0 = s == 0;
                 float value = s0 ? 1.0f : initv, gapm = value;
-                uint32_t open_last = 0;
                 for (uint32_t k = shift; k < npw; k++) {
                     const uint32_t d = __ldg(&pd[k - shift]);
-                    const float2 c = ring[((t - (d >> 16)) & (R - 1)) * S + (d & 0xffffu)];
-                    const float v = __fadd_rn(c.x, gp), gv = __fadd_rn(c.y, gpe);
-                    const bool open = v < gv;
-                    const float gm = open ? v : gv;
-                    gapm = gm; open_last = open;
-                    if (gm < value) { value = gm; code = WIDE ? (TB_SRC_DEL | ((uint32_t)open << 2) | (k << 8)) : (TB_SRC_DEL | (k << 2) | ((uint32_t)open << 5)); }
+                    const float gm = ring[((t - (d >> 16)) & (R - 1)) * S + (d & 0xffffu)].y;   // the predecessor's dm
+                    gapm = gm;
+                    if (gm < value) { value = gm; code = WIDE ? (TB_SRC_DEL | (k << 8)) : (TB_SRC_DEL | (k << 2)); }
                 }
                 float E = 1.0f;
-                uint32_t ins_open = 0;
                 if (!s0) {
-                    const bool ext = (Ep == Hp);
-                    E = ext ? __fadd_rn(Ep, gpe) : __fadd_rn(Hp, gp);
-                    ins_open = !ext;
+                    E = En;
                     if (E <= value) { value = E; code = TB_SRC_INS; }
                     const float sc = (PLANES == 1 ? (mask & qt[s]) : qt[s * PLANES + (int)plane]) ? msw : mmsw;
                     for (uint32_t k = shift; k < npw; k++) {
@@ -329,9 +309,10 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                         if (v < value) { value = v; code = WIDE ? (TB_SRC_MATCH | (k << 8)) : (TB_SRC_MATCH | (k << 2)); }
                     }
                 }
-                code |= WIDE ? ((open_last << 3) | (ins_open << 4)) : ((open_last << 6) | (ins_open << 7));
-                Ep = E; Hp = value;
-                const float2 out = make_float2(value, gapm);
+                const float vgp = __fadd_rn(value, gp), ggpe = __fadd_rn(gapm, gpe);
+                if (vgp < ggpe) code |= WIDE ? 4u : 32u;
+                En = (E == value) ? __fadd_rn(E, gpe) : vgp;
+                const float2 out = make_float2(value, fminf(vgp, ggpe));
                 ringw[(t & (R - 1)) * S + threadIdx.x] = out;
                 ringw[(R + (t & (R - 1))) * S + threadIdx.x] = out;   // second copy, read by the specialised warps
                 if (s == (int)Lq - 1) *lastcol_ptr = value;
@@ -385,9 +366,9 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
         ring[(t & (R - 1)) * S + threadIdx.x] = c;
         ring[(R + (t & (R - 1))) * S + threadIdx.x] = c;
     };
-    // the last loader lane owns the constant edge column (value 1, gapm +inf) read by rows without predecessor
+    // the last loader lane owns the constant edge column (value 1, dm 1) read by rows without predecessor
     if (threadIdx.x == S - 1)
-        for (uint32_t r = 0; r < 2 * R; r++) ring[r * S + threadIdx.x] = make_float2(1.0f, __int_as_float(0x7f800000));
+        for (uint32_t r = 0; r < 2 * R; r++) ring[r * S + threadIdx.x] = make_float2(1.0f, 1.0f);
     // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0); afterwards the
     // data of step t+4 is requested at step t, so the L2 latency never sits between two barriers
     // (GHOST_LEAD = 4 + 2 keeps that request behind the source row's spill store).
@@ -579,7 +560,7 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
 #pragma unroll
             for (int i = 0; i < NPR; i++) if ((uint32_t)i < np) pd[i] = pdesc[pbase + i];
         }
-        float E_prev = 1.0f, H_prev = 1.0f;  // gaps_val / value of (m, s-1)
+        float E_next = 1.0f;  // gaps_val of the row's next cell
         float rmin = 0.f;
         uint32_t rarg = 0;
         const uint32_t steps = (Lq + gi.depth - 1 + 3) & ~3u;
@@ -593,19 +574,12 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                 const bool edge = (np == 0) || (s == 0);                 // init_edge / init (mesh.h:294-301,469-473)
                 float value = edge ? 1.0f : 1000000.0f;
                 float gapm = value;
-                uint32_t open_last = 0;
                 float pv_cur[NPR];
-                auto del_step = [&](uint32_t i, float2 c) {              // mesh.h:305-330
-                    const float v = __fadd_rn(c.x, gp);
-                    const float gv = __fadd_rn(c.y, gpe);
-                    const bool open = v < gv;
-                    const float gm = open ? v : gv;
-                    gapm = gm;                 // last predecessor wins
-                    open_last = open;
-                    if (gm < value) {
-                        value = gm;
-                        code = WIDE ? (TB_SRC_DEL | ((uint32_t)open << 2) | (i << 8))
-                                    : (TB_SRC_DEL | (i << 2) | ((uint32_t)open << 5));
+                auto del_step = [&](uint32_t i, float2 c) {              // mesh.h:305-330; c.y = the predecessor's dm
+                    gapm = c.y;                // last predecessor wins
+                    if (c.y < value) {
+                        value = c.y;
+                        code = WIDE ? (TB_SRC_DEL | (i << 8)) : (TB_SRC_DEL | (i << 2));
                     }
                 };
                 auto load_cell = [&](uint32_t d, int ss, uint32_t tt) -> float2 {
@@ -625,11 +599,8 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                     del_step(i, load_cell(d, s, t));
                 }
                 float E = 1.0f;
-                uint32_t ins_open = 0;
                 if (s > 0) {
-                    const bool ext = (E_prev == H_prev);                 // mesh.h:332-358
-                    E = ext ? __fadd_rn(E_prev, gpe) : __fadd_rn(H_prev, gp);
-                    ins_open = !ext;
+                    E = E_next;                                          // mesh.h:332-358
                     if (E <= value) { value = E; code = TB_SRC_INS; }
                     const float sc = (mask & qm[s] & 15u) ? msw : mmsw;  // mesh.h:360-374
 #pragma unroll
@@ -645,12 +616,12 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                         if (v < value) { value = v; code = WIDE ? (TB_SRC_MATCH | (i << 8)) : (TB_SRC_MATCH | (i << 2)); }
                     }
                 }
-                code |= WIDE ? ((open_last << 3) | (ins_open << 4)) : ((open_last << 6) | (ins_open << 7));
+                const float vgp = __fadd_rn(value, gp), ggpe = __fadd_rn(gapm, gpe);
+                if (vgp < ggpe) code |= WIDE ? 4u : 32u;                 // ob: a deletion leaving this cell opens
+                E_next = (E == value) ? __fadd_rn(E, gpe) : vgp;         // extension iff gaps_val == value
 #pragma unroll
                 for (int i = 0; i < NPR; i++) pv_prev[i] = pv_cur[i];
-                E_prev = E;
-                H_prev = value;
-                const float2 out = make_float2(value, gapm);
+                const float2 out = make_float2(value, fminf(vgp, ggpe));
                 ring[(t & (R - 1)) * S + tid] = out;
                 if (sr >= 0) __stcg(&spill_w[(uint64_t)sr * Lq + s], out);
                 if (s == (int)Lq - 1) A.lastcol[io + m] = value;
