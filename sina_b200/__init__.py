@@ -218,13 +218,20 @@ class Index:
                                     fam_off, C.byref(ap), oc, om, res.ctypes.data_as(C.c_void_p)))
         return oc, om, res
 
-    def run(self, qmasks, qoff, fp=None, ap=None, exclude_ids=None):
-        """famfinder + aligner for a batch, host buffers in and out."""
+    def run(self, qmasks, qoff, fp=None, ap=None, exclude_ids=None, out=None):
+        """famfinder + aligner for a batch, host buffers in and out. `out` = (cols u32[len(qmasks)], masks
+        u8[len(qmasks)], results[nq]) lets a caller reuse its output buffers from call to call, as a C++ host does."""
         fp, ap = fp or FamParams(), ap or AlignParams()
         qmasks, qoff = np.ascontiguousarray(qmasks, np.uint8), np.ascontiguousarray(qoff, np.uint64)
         nq = len(qoff) - 1
-        oc, om = np.zeros(max(1, len(qmasks)), np.uint32), np.zeros(max(1, len(qmasks)), np.uint8)
-        res = np.zeros(nq, RESULT_DTYPE)
+        if out is not None:
+            oc, om, res = out
+            assert oc.dtype == np.uint32 and om.dtype == np.uint8 and res.dtype == RESULT_DTYPE
+            assert len(oc) >= len(qmasks) and len(om) >= len(qmasks) and len(res) >= nq
+            assert oc.flags.c_contiguous and om.flags.c_contiguous and res.flags.c_contiguous
+        else:
+            oc, om = np.zeros(max(1, len(qmasks)), np.uint32), np.zeros(max(1, len(qmasks)), np.uint8)
+            res = np.zeros(nq, RESULT_DTYPE)
         keep, ex = _excl_ptr(exclude_ids)
         _check(lib().sg_run_batch(self.h, qmasks, qoff, nq, ex, C.byref(fp), C.byref(ap), oc, om,
                                   res.ctypes.data_as(C.c_void_p)))

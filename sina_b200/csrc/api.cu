@@ -314,6 +314,9 @@ void sg_session_destroy(sg_session* h) {
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s->cev) if (e) cudaEventDestroy(e);
+    for (auto& p : s->stage) if (p) cudaFreeHost(p);
+    if (s->cstream) cudaStreamDestroy(s->cstream);
     if (s->stream) cudaStreamDestroy(s->stream);
     free(s->h_qoff);
     delete s;
@@ -333,8 +336,12 @@ int sg_session_upload(sg_session* h, const uint8_t* qmasks, const uint64_t* qoff
         s->h_qoff[i] = qoff[i] - base;
     }
     s->h_qoff[nq] = total;
-    for (uint64_t j = 0; j < total; j++)
-        if ((qmasks[base + j] & 15) == 0 || qmasks[base + j] > 31) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    {
+        unsigned bad = 0;   // branch-free so that the compiler vectorises the scan
+        const uint8_t* qb = qmasks + base;
+        for (uint64_t j = 0; j < total; j++) bad |= (unsigned)((qb[j] & 15) == 0) | (unsigned)(qb[j] > 31);
+        if (bad) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    }
     SG_CUDA(cudaSetDevice(s->ix->device));
     s->nq = nq;
     SG_CUDA(cudaMemcpyAsync(s->d_qmasks, qmasks + base, total, cudaMemcpyHostToDevice, s->stream));
@@ -405,6 +412,43 @@ int sg_session_set_family(sg_session* h, const uint32_t* fam_ids, const uint64_t
     return SG_OK;
 }
 
+// Streaming download: copy slot `slot` of the staging area into the caller's buffers once its D2H has landed.
+static int flush_stage(Session* s, int slot) {
+    auto& si = s->stage_info[slot];
+    if (!si.pending) return SG_OK;
+    SG_CUDA(cudaEventSynchronize(s->cev[slot]));
+    if (s->host_cols) memcpy(s->host_cols + si.off, s->stage[slot], si.nb * 4);
+    if (s->host_masks) memcpy(s->host_masks + si.off, s->stage[slot] + s->stage_cap * 4, si.nb);
+    si.pending = false;
+    return SG_OK;
+}
+
+// Queue the D2H of a finished chunk's output (queries q0 .. q0+n) into the next staging slot.
+static int stage_chunk(Session* s, uint32_t q0, uint32_t n) {
+    if (!s->host_cols && !s->host_masks) return SG_OK;
+    const uint64_t off = s->h_qoff[q0], nb = s->h_qoff[q0 + n] - off;
+    if (nb == 0) return SG_OK;
+    if (!s->cstream) {
+        SG_CUDA(cudaStreamCreateWithFlags(&s->cstream, cudaStreamNonBlocking));
+        for (auto& e : s->cev) SG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (nb > s->stage_cap) {
+        for (int i = 0; i < 2; i++) {
+            SG_TRY(flush_stage(s, i));
+            if (s->stage[i]) { cudaFreeHost(s->stage[i]); s->stage[i] = nullptr; }
+        }
+        s->stage_cap = nb + nb / 4 + 1024;
+        for (int i = 0; i < 2; i++) SG_CUDA(cudaMallocHost((void**)&s->stage[i], s->stage_cap * 5));
+    }
+    const int slot = (int)(s->stage_next++ & 1u);
+    SG_TRY(flush_stage(s, slot));
+    if (s->host_cols) SG_CUDA(cudaMemcpyAsync(s->stage[slot], s->d_out_cols + off, nb * 4, cudaMemcpyDeviceToHost, s->cstream));
+    if (s->host_masks) SG_CUDA(cudaMemcpyAsync(s->stage[slot] + s->stage_cap * 4, s->d_out_masks + off, nb, cudaMemcpyDeviceToHost, s->cstream));
+    SG_CUDA(cudaEventRecord(s->cev[slot], s->cstream));
+    s->stage_info[slot].pending = true; s->stage_info[slot].off = off; s->stage_info[slot].nb = nb;
+    return SG_OK;
+}
+
 // Retire the chunk in flight on a workspace: wait for it, add its stage times, and if some of its queries
 // did not fit the traceback/spill arenas re-run those (arenas reset) until none is left.
 static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap);
@@ -434,7 +478,7 @@ static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
         SG_CUDA(cudaEventElapsedTime(&ms, w->ev[2], w->ev[3])); s->stats.ms_backtrack += ms;
         w->busy = false;
         const uint32_t remaining = *w->h_remaining;
-        if (remaining == 0) { w->prev_remaining = 0xffffffffu; break; }
+        if (remaining == 0) { w->prev_remaining = 0xffffffffu; SG_TRY(stage_chunk(s, w->q0, w->n)); break; }
         if (remaining >= w->prev_remaining)
             SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
         w->prev_remaining = remaining;
@@ -457,8 +501,14 @@ int sg_session_align(sg_session* h, const sg_align_params* ap) {
         Workspace* w = &s->ws[k % s->n_ws];
         SG_TRY(retire_chunk(s, w, *ap));
         SG_TRY(enqueue_chunk(s, w, *ap, q0, std::min(s->chunk, s->nq - q0)));
+        // the retired chunk's output goes to the caller's buffers while the GPU runs the chunks just queued
+        for (int i = 0; i < 2; i++) SG_TRY(flush_stage(s, i));
     }
-    for (int i = 0; i < s->n_ws; i++) SG_TRY(retire_chunk(s, &s->ws[i], *ap));
+    for (int i = 0; i < s->n_ws; i++) {
+        SG_TRY(retire_chunk(s, &s->ws[(k + i) % s->n_ws], *ap));   // oldest chunk first
+        if (i + 1 < s->n_ws) for (int j = 0; j < 2; j++) SG_TRY(flush_stage(s, j));
+    }
+    for (int i = 0; i < 2; i++) SG_TRY(flush_stage(s, i));
     unsigned long long cnt[2];
     SG_CUDA(cudaMemcpyAsync(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost, s->stream));
     SG_CUDA(cudaStreamSynchronize(s->stream));
@@ -536,6 +586,14 @@ int sg_session_download_align(sg_session* h, uint32_t* out_cols, uint8_t* out_ma
 int sg_session_stats(sg_session* h, sg_stage_stats* st, int reset) {
     Session* s = (Session*)h;
     if (!s) SG_FAIL(SG_ERR_ARG, "null session");
+    {   // the device-side counters (postings scanned, DP cells) as of now
+        unsigned long long cnt[2];
+        SG_CUDA(cudaSetDevice(s->ix->device));
+        SG_CUDA(cudaMemcpyAsync(cnt, s->d_counters, 16, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        s->stats.postings = cnt[0];
+        s->stats.cells = cnt[1];
+    }
     if (st) *st = s->stats;
     if (reset) {
         s->stats = sg_stage_stats{};
@@ -608,6 +666,14 @@ struct SessionLease {
     ~SessionLease() { ix->mu.unlock(); }
     uint32_t step() const { return s->max_q; }
 };
+// aligner stage whose output columns/bases stream into the caller's buffers chunk by chunk (stage_chunk above)
+static int align_streaming(Session* s, const sg_align_params* ap, uint32_t* cols, uint8_t* masks) {
+    s->host_cols = cols; s->host_masks = masks; s->stage_next = 0;
+    const int rc = sg_session_align((sg_session*)s, ap);
+    s->host_cols = nullptr; s->host_masks = nullptr;
+    s->stage_info[0].pending = s->stage_info[1].pending = false;
+    return rc;
+}
 }  // namespace
 
 int sg_find_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, uint32_t max,
@@ -656,10 +722,8 @@ int sg_align_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, ui
         const uint32_t n = std::min(L.step(), nq - a);
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, nullptr));
         SG_TRY(sg_session_set_family(s, fam_ids, fam_off + a));
-        SG_TRY(sg_session_align(s, ap));
-        const uint64_t o = qoff[a];
-        SG_TRY(sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
-                                         results ? results + a : nullptr));
+        SG_TRY(align_streaming(L.s, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
+        SG_TRY(sg_session_download_align(s, nullptr, nullptr, results ? results + a : nullptr));
     }
     return SG_OK;
 }
@@ -675,10 +739,8 @@ int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint
         const uint32_t n = std::min(L.step(), nq - a);
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
         SG_TRY(sg_session_family(s, fp));
-        SG_TRY(sg_session_align(s, ap));
-        const uint64_t o = qoff[a];
-        SG_TRY(sg_session_download_align(s, out_cols ? out_cols + o : nullptr, out_masks ? out_masks + o : nullptr,
-                                         results ? results + a : nullptr));
+        SG_TRY(align_streaming(L.s, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
+        SG_TRY(sg_session_download_align(s, nullptr, nullptr, results ? results + a : nullptr));
     }
     return SG_OK;
 }

@@ -196,6 +196,16 @@ struct Session {
     uint32_t* d_out_cols = nullptr;  // [max_bases]
     uint8_t* d_out_masks = nullptr;  // [max_bases]
     sg_align_result* d_results = nullptr;  // [nq]
+    // streaming download (host-buffer entry points): a finished chunk's columns/bases go to a pinned staging slot on
+    // `cstream` and from there to the caller's buffers while the following chunks compute
+    uint32_t* host_cols = nullptr;   // destination of query 0's bases for the align call in flight (null: no streaming)
+    uint8_t* host_masks = nullptr;
+    cudaStream_t cstream = nullptr;
+    cudaEvent_t cev[2] = {};
+    uint8_t* stage[2] = {};
+    uint64_t stage_cap = 0;          // bases a staging slot holds (5 bytes each: u32 column + u8 base)
+    struct { bool pending; uint64_t off, nb; } stage_info[2] = {};
+    uint32_t stage_next = 0;
     // timing
     cudaEvent_t ev[8] = {};
     sg_stage_stats stats = {};

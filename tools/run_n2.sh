@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r01h_bench_n2.json 2> gpurun_out/r01h_bench_n2.err; echo "n2 rc=$?"
+tail -3 gpurun_out/r01h_bench_n2.err
+cat gpurun_out/r01h_bench_n2.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r01h_ref_n2.json 2> gpurun_out/r01h_ref_n2.err; echo "ref rc=$?"
+cat gpurun_out/r01h_ref_n2.json
