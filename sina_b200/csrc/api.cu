@@ -33,7 +33,7 @@ static uint64_t env_mb(const char* name, uint64_t dflt_mb) {
 static void free_workspace(Workspace* w) {
     void* ptrs[] = {w->d_cursors, w->d_remaining, w->d_tab, w->d_tabli, w->d_colof, w->d_colbase, w->d_item_node, w->d_slot,
                     w->d_ncol, w->d_nmask, w->d_ncount, w->d_nweight, w->d_nsigma, w->d_slotbase, w->d_cursor,
-                    w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_nthr, w->d_nshift, w->d_ghosts,
+                    w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_rcol, w->d_nthr, w->d_nshift, w->d_ghosts,
                     w->d_writers, w->d_spillrow, w->d_nflags, w->d_lastnodes, w->d_groups, w->d_lastcol, w->d_rowmin,
                     w->d_rowarg, w->d_rec, w->d_tb, w->d_spill};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -71,7 +71,7 @@ static int alloc_workspace(Session* s, Workspace* w) {
     SG_TRY(dmalloc(&w->d_pdesc, C * I)); SG_TRY(dmalloc(&w->d_spillrow, C * I)); SG_TRY(dmalloc(&w->d_nflags, C * I));
     SG_TRY(dmalloc(&w->d_lastnodes, C * I)); SG_TRY(dmalloc(&w->d_groups, C * s->gcap));
     SG_TRY(dmalloc(&w->d_lastcol, C * I)); SG_TRY(dmalloc(&w->d_rowmin, C * I)); SG_TRY(dmalloc(&w->d_rowarg, C * I));
-    SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
+    SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_rcol, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
     SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
     SG_TRY(dmalloc(&w->d_writers, C * s->gcap * DP_G));
     { uint8_t* p = nullptr; SG_TRY(dmalloc(&p, C * I * 32)); w->d_rec = p; }
@@ -289,6 +289,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
     s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 1184)));
     s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
+    s->bankplan = (int)env_mb("SG_BANKPLAN", 0);
     *out = (sg_session*)s;
     SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) SG_CUDA(cudaEventCreate(&e));

@@ -137,6 +137,7 @@ struct Workspace {
     uint32_t* d_pdesc = nullptr;     // [n][icap] near/far descriptor per edge (generic kernel)
     uint32_t* d_pdesc2 = nullptr;    // [n][icap] (delta<<16 | ring column) per edge (v2 kernel)
     uint32_t* d_order = nullptr;     // [n][gcap*DP_T] node handled by (group, thread) in the v2 kernel
+    uint8_t* d_rcol = nullptr;       // [n][gcap*DP_T] ring column (group, thread) publishes to: a permutation inside every 16-thread block
     uint16_t* d_nthr = nullptr;      // [n][icap] thread (ring column) of a node inside its group
     uint8_t* d_nshift = nullptr;     // [n][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
     GhostInfo* d_ghosts = nullptr;   // [n][gcap][DP_G]
@@ -211,6 +212,7 @@ struct Session {
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
+    int bankplan = 0;                // SG_BANKPLAN=1: bank-aware ring columns (bankplan_kernel). Measured on B200: shared-load bank conflicts 735M -> 395M per chunk, DP 80.2 -> 78.6 ms per 10k queries, but the plan costs 5.2 ms: off by default
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

@@ -98,7 +98,7 @@ struct GraphArgs {
     uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
     uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
     uint32_t* lastnodes; GroupInfo* groups;
-    uint32_t* order; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
+    uint32_t* order; uint8_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
     unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
 };
@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             base += tot;
         }
         if (tid >= n && tid < T) order[(uint64_t)g * T + tid] = NONE;
+        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (uint8_t)tid;   // bankplan_kernel permutes these
         if (tid == 0) { shv[2] = 0; shv[3] = 0; }  // far edges, ghosts
         __syncthreads();
         if (valid) {
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
                 uint32_t j = 0;
                 while (j < ng && !(gh_p[j] == p && gh_b[j] == bk)) j++;
                 if (j == ng) {
-                    if (ng == DP_G - 1) { shv[1] = 1; j = 0; }   // the last loader column is the DP's constant edge column
+                    if (ng == DP_G - 2) { shv[1] = 1; j = 0; }   // the last two loader columns are the DP's constant columns
                     else { gh_p[ng] = p; gh_b[ng] = bk; ng++; }
                 }
                 far_gi[i] = j;
@@ -502,6 +503,160 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Ring-column plan of the v2 DP kernel, one warp per (query, group).
+// A row publishes its cells into one column of the shared-memory ring and every successor row reads them from
+// there with one LDS.64 per step. The 16 lanes of a half-warp are served in one wavefront only if their columns
+// fall into 16 different 8-byte bank pairs; with columns = thread ids the predecessor columns of a half-warp are
+// close to random and the loads cost 5.3 wavefronts instead of 2 (ncu: the LSU data pipe is what bounds the DP
+// kernel). Here every row gets its ring column: the column stays inside the row's 16-thread block (so a warp's
+// stores still cover whole 128-byte lines without conflict) and its bank is chosen greedily, block by block, as
+// the one that collides least with the predecessors already placed in the load instructions that will read it.
+// Bank pair of (column c, column-rank distance d) = (c + 3 * (8 - d)) mod 16: the ring's time-slot stride is
+// 3 cells more than a multiple of 16 (mesh.cu, RS).
+constexpr int BP_WARPS = 4;
+constexpr uint32_t BP_ENT = 640;        // near in-group edges per group the plan looks at
+constexpr uint32_t BP_INST = (DP_T / 16) * 8;   // load instructions per group: (half-warp, predecessor slot < 8)
+struct BankPlanArgs {
+    const GraphHdr* hdr; uint32_t q0, gcap, icap;
+    const uint32_t* order; const uint16_t* nthr; const uint32_t* pred_off; const uint32_t* preds; const uint32_t* nsigma;
+    uint32_t* pdesc2; uint8_t* rcol;
+};
+
+__global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A) {
+    __shared__ uint32_t occ_s[BP_WARPS][BP_INST * 16 / 4];   // u8 counters: addresses per (instruction, bank pair)
+    __shared__ uint32_t off_s[BP_WARPS][DP_T + 1];           // reads of the row at a position: CSR offsets
+    __shared__ uint32_t cur_s[BP_WARPS][DP_T];
+    __shared__ uint16_t ent_s[BP_WARPS][BP_ENT];             // instruction | distance << 7
+    __shared__ uint8_t np_s[BP_WARPS][DP_T];
+    __shared__ uint8_t rho_s[BP_WARPS][DP_T];
+    const uint32_t FULLM = 0xffffffffu;
+    const uint32_t w = warp_id(), lane = lane_id(), ql = blockIdx.x;
+    const GraphHdr h = A.hdr[A.q0 + ql];
+    if (h.status != GS_OK || h.mode < 2) return;
+    const uint32_t T = DP_T;
+    const uint64_t io = (uint64_t)ql * A.icap;
+    const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
+    const uint32_t* preds = A.preds + io;
+    const uint32_t* nsigma = A.nsigma + io;
+    const uint16_t* nthr = A.nthr + io;
+    uint32_t* pdesc2 = A.pdesc2 + io;
+    uint32_t* occ32 = occ_s[w];
+    const uint8_t* occ = reinterpret_cast<const uint8_t*>(occ32);
+    uint32_t* off = off_s[w];
+    uint32_t* cur = cur_s[w];
+    uint16_t* ent = ent_s[w];
+    uint8_t* npl = np_s[w];
+    uint8_t* rho = rho_s[w];
+    for (uint32_t g = w; g < h.n_groups; g += BP_WARPS) {
+        const uint32_t lo = g * T, n = min(T, h.V - lo);
+        const uint32_t* order = A.order + ((uint64_t)ql * A.gcap + g) * T;
+        uint8_t* rcol = A.rcol + ((uint64_t)ql * A.gcap + g) * T;
+        // in-degree of the row at every position; lane i keeps the specialisation width of DP warp i
+        uint32_t npw_mine = 1;
+        for (uint32_t wi = 0; wi < T / 32; wi++) {
+            const uint32_t pos = wi * 32 + lane;
+            uint32_t np = 0;
+            if (pos < n) { const uint32_t m = order[pos]; np = pred_off[m + 1] - pred_off[m]; }
+            npl[pos] = (uint8_t)min(np, 255u);
+            const uint32_t mx = max(1u, __reduce_max_sync(FULLM, np));
+            if (lane == wi) npw_mine = mx;
+        }
+        for (uint32_t i = lane; i <= T; i += 32) off[i] = 0;
+        for (uint32_t i = lane; i < BP_INST * 16 / 4; i += 32) occ32[i] = 0;
+        __syncwarp();
+        // reads of every producer position: pass 0 counts, pass 1 fills. Far predecessors sit in ghost columns that
+        // are already fixed: they go straight into the occupancy table.
+        uint32_t total = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            for (uint32_t wi = 0; wi < T / 32; wi++) {
+                const uint32_t pos = wi * 32 + lane;
+                const uint32_t npw = __shfl_sync(FULLM, npw_mine, wi);
+                if (pos < n && npw <= 8) {
+                    const uint32_t m = order[pos], po = pred_off[m], np = npl[pos], shift = npw - np, sg_ = nsigma[m];
+                    for (uint32_t o = 0; o < np; o++) {
+                        const uint32_t p = preds[po + o], d = sg_ - nsigma[p];
+                        const uint32_t inst = (pos >> 4) * 8 + o + shift;
+                        if (p >= lo && d <= (uint32_t)DP_RING - 2) {
+                            const uint32_t pp = nthr[p];
+                            if (pass == 0) atomicAdd(&off[pp], 1u);
+                            else {
+                                const uint32_t at = atomicAdd(&cur[pp], 1u);
+                                if (at < BP_ENT) ent[at] = (uint16_t)(inst | (d << 7));
+                            }
+                        } else if (pass == 1) {
+                            const uint32_t dd = pdesc2[po + o];   // (distance << 16) | ghost column
+                            const uint32_t idx = inst * 16 + (((dd & 0xffffu) + 3u * (8u - (dd >> 16))) & 15u);
+                            atomicAdd(&occ32[idx >> 2], 1u << (8 * (idx & 3)));
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (pass == 0) {   // exclusive scan of the counts
+                uint32_t carry = 0;
+                for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                    const uint32_t v = off[i0 + lane];
+                    uint32_t x = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, x, o); if (lane >= (uint32_t)o) x += y; }
+                    off[i0 + lane] = carry + x - v;
+                    cur[i0 + lane] = carry + x - v;
+                    carry += __shfl_sync(FULLM, x, 31);
+                }
+                total = carry;
+                if (lane == 0) off[T] = total;
+                __syncwarp();
+            }
+        }
+        if (total > BP_ENT) continue;   // an unusually dense group keeps the identity columns written by graph_kernel
+        // greedy choice, position by position; lane b < 16 prices bank pair b, lane i < 14 keeps the free banks of block i
+        uint32_t fm = 0xffffu;
+        for (uint32_t pos = 0; pos < T; pos++) {
+            const uint32_t blk = pos >> 4;
+            const uint32_t fmask = __shfl_sync(FULLM, fm, blk);
+            uint32_t b;
+            const uint32_t a = off[pos], e = off[pos + 1];
+            if (pos < n && e > a) {
+                uint32_t key = 0xffffffffu;
+                if (lane < 16 && ((fmask >> lane) & 1u)) {
+                    uint32_t cost = 0;
+                    for (uint32_t j = a; j < e; j++) {
+                        const uint32_t en = ent[j];
+                        cost += occ[(en & 127u) * 16 + ((lane + 3u * (8u - (en >> 7))) & 15u)];
+                    }
+                    key = (cost << 4) | ((lane - pos) & 15u);   // ties: the bank nearest above the thread's own
+                }
+                key = __reduce_min_sync(FULLM, key);
+                b = ((key & 15u) + pos) & 15u;
+                for (uint32_t j = a + lane; j < e; j += 32) {
+                    const uint32_t en = ent[j];
+                    const uint32_t idx = (en & 127u) * 16 + ((b + 3u * (8u - (en >> 7))) & 15u);
+                    atomicAdd(&occ32[idx >> 2], 1u << (8 * (idx & 3)));
+                }
+            } else {
+                // nobody reads this position through the ring: the free bank nearest above the thread's own
+                const uint32_t rot = (fmask >> (pos & 15u)) | (fmask << (16u - (pos & 15u)));
+                b = ((uint32_t)__ffs((int)(rot & 0xffffu)) - 1u + pos) & 15u;
+            }
+            if (lane == blk) fm &= ~(1u << b);
+            if (lane == 0) rho[pos] = (uint8_t)(blk * 16 + b);
+            __syncwarp();
+        }
+        // publish: ring column per thread, and the column field of every near edge
+        for (uint32_t pos = lane; pos < T; pos += 32) rcol[pos] = rho[pos];
+        for (uint32_t pos = lane; pos < n; pos += 32) {
+            const uint32_t m = order[pos], po = pred_off[m], np = pred_off[m + 1] - po, sg_ = nsigma[m];
+            for (uint32_t o = 0; o < np; o++) {
+                const uint32_t p = preds[po + o], d = sg_ - nsigma[p];
+                if (p >= lo && d <= (uint32_t)DP_RING - 2) pdesc2[po + o] = (d << 16) | rho[nthr[p]];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 int launch_prealign(Session* s, const sg_align_params& ap) {
     Index* ix = s->ix;
     uint32_t pairs = s->nq * s->fam_cap;
@@ -528,7 +683,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.ncount = w->d_ncount; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma; A.slotbase = w->d_slotbase;
     A.cursor = w->d_cursor; A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.pdesc = w->d_pdesc;
     A.spillrow = w->d_spillrow; A.nflags = w->d_nflags; A.lastnodes = w->d_lastnodes; A.groups = w->d_groups;
-    A.order = w->d_order; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
+    A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
     A.force_generic = s->force_generic;
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
@@ -536,8 +691,16 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + 1 + 2 * s->fam_cap) * 4;
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
-    SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
+    if (s->bankplan) {
+        BankPlanArgs B;
+        B.hdr = s->d_hdr; B.q0 = q0; B.gcap = s->gcap; B.icap = s->icap;
+        B.order = w->d_order; B.nthr = w->d_nthr; B.pred_off = w->d_pred_off; B.preds = w->d_preds; B.nsigma = w->d_nsigma;
+        B.pdesc2 = w->d_pdesc2; B.rcol = w->d_rcol;
+        bankplan_kernel<<<n, 32 * BP_WARPS, 0, w->stream>>>(B);
+        s->stats.kernel_launches += 1;
+    }
+    SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
 

@@ -29,7 +29,7 @@ struct MeshArgs {
     const GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap, q0;
     const uint8_t* nmask; const float* nweight; const uint32_t* nsigma;
     const uint32_t* pred_off; const uint32_t* pdesc; const int32_t* spillrow; const uint8_t* nflags;
-    const uint32_t* pdesc2; const uint32_t* order; const uint16_t* nthr; uint8_t* nshift;
+    const uint32_t* pdesc2; const uint32_t* order; const uint8_t* rcol; const uint16_t* nthr; uint8_t* nshift;
     const GhostInfo* ghosts; const uint32_t* writers;
     uint32_t* tb; float2* spill;
     float* lastcol; float* rowmin; uint32_t* rowarg;
@@ -43,7 +43,10 @@ constexpr int NPR = 4;         // predecessors held in registers (generic kernel
 constexpr int NPF = 8;         // largest in-degree the specialised v2 step is instantiated for
 constexpr int QPAD = 256;      // padding either side of the query in shared memory (s runs out of range by < T + 4)
 static_assert(QPAD >= DP_T + 8, "query padding must cover the group skew");
-constexpr uint32_t SLOT_BYTES = sizeof(float2) * S;       // one time slot of the ring
+constexpr int RS = S + 3;      // cells per time slot of the v2 ring: the odd stride rotates the banks by three cells from one
+                               // time slot to the next, so that readers of the same column at different column-rank
+                               // distances (a very common pattern: a row skipping a column) do not collide
+constexpr uint32_t SLOT_BYTES = sizeof(float2) * RS;      // one time slot of the ring
 constexpr uint32_t RB = SLOT_BYTES * R;                   // one copy of the ring
 constexpr uint32_t RING_BYTES = 2 * RB;                   // the ring is stored twice back to back (see below)
 
@@ -104,9 +107,8 @@ struct V2Lane {
 };
 
 // Two steps t0, t0+1 of one group for the lanes of a warp whose rows all have <= NPW predecessors.
-// Slots are right-aligned: a row with np < NPW repeats its first predecessor in the NPW-np leading slots (a
-// repeated candidate ties with its first copy and strict '<' keeps the first, so nothing changes; backtrack maps
-// slot -> ordinal with max(0, slot - shift)).
+// Slots are right-aligned: the NPW-np leading slots of a row with np < NPW read a constant (+inf, +inf) ring column,
+// a candidate that never wins (backtrack maps slot -> ordinal with slot - shift).
 // A ring cell is (value, dm): dm = min(value + gap, gapm_val + gapext) is the deletion candidate this cell offers
 // to every successor row (deletion(), mesh.h:305-330, evaluated once by the row it leaves from instead of once per
 // edge); the row's own gapm_val is the dm of its last predecessor ("last predecessor wins").
@@ -243,13 +245,13 @@ __device__ __forceinline__ void v2_fast_group(const V2Lane<NPW>& L, const float 
 }
 
 template <int NPW, bool WIDE, int PLANES>
-__device__ __forceinline__ void v2_fast_dispatch(const MeshArgs& A, uint32_t sring, uint32_t sq, const uint32_t* ck,
+__device__ __forceinline__ void v2_fast_dispatch(const MeshArgs& A, uint32_t sring, uint32_t sq, const uint32_t* ck, uint32_t rcol,
                                                  bool valid, uint32_t np, int soff, uint32_t Lq, uint32_t plane, uint32_t mask, float w,
                                                  uint32_t steps4, float* lastcol_ptr, uint32_t* tbg) {
     V2Lane<NPW> L;
 #pragma unroll
     for (int k = 0; k < NPW; k++) L.pk[k] = sring + ck[k];
-    L.wadr = sring + threadIdx.x * 8u;
+    L.wadr = sring + rcol * 8u;
     const bool hr = np > 0;
     const float msw = __fmul_rn(A.ms, w);    // (comp ? match : mismatch) * weight  (scoring_schemes.h:150-156)
     const float mmsw = __fmul_rn(A.mms, w);
@@ -273,7 +275,7 @@ __device__ __forceinline__ void v2_fast_dispatch(const MeshArgs& A, uint32_t sri
 // Warps holding a row with more than NPF predecessors: slots are looped over.
 template <bool WIDE, int PLANES>
 __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned char* smem, const uint8_t* qt, uint32_t Lq,
-                                                 uint32_t steps4, uint32_t npw, uint32_t np, const uint32_t* pd,
+                                                 uint32_t steps4, uint32_t npw, uint32_t np, const uint32_t* pd, uint32_t rcol,
                                                  int soff, float initv, uint32_t plane, uint32_t mask, float msw, float mmsw,
                                                  float* lastcol_ptr, uint32_t* tbg) {
     // slot k of this lane is real iff k >= npw - np; real slot k is predecessor ordinal k - (npw - np)
@@ -294,7 +296,7 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                 float value = s0 ? 1.0f : initv, gapm = value;
                 for (uint32_t k = shift; k < npw; k++) {
                     const uint32_t d = __ldg(&pd[k - shift]);
-                    const float gm = ring[((t - (d >> 16)) & (R - 1)) * S + (d & 0xffffu)].y;   // the predecessor's dm
+                    const float gm = ring[((t - (d >> 16)) & (R - 1)) * RS + (d & 0xffffu)].y;   // the predecessor's dm
                     gapm = gm;
                     if (gm < value) { value = gm; code = WIDE ? (TB_SRC_DEL | (k << 8)) : (TB_SRC_DEL | (k << 2)); }
                 }
@@ -305,7 +307,7 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                     const float sc = (PLANES == 1 ? (mask & qt[s]) : qt[s * PLANES + (int)plane]) ? msw : mmsw;
                     for (uint32_t k = shift; k < npw; k++) {
                         const uint32_t d = __ldg(&pd[k - shift]);
-                        const float v = __fadd_rn(ring[((t - 1 - (d >> 16)) & (R - 1)) * S + (d & 0xffffu)].x, sc);
+                        const float v = __fadd_rn(ring[((t - 1 - (d >> 16)) & (R - 1)) * RS + (d & 0xffffu)].x, sc);
                         if (v < value) { value = v; code = WIDE ? (TB_SRC_MATCH | (k << 8)) : (TB_SRC_MATCH | (k << 2)); }
                     }
                 }
@@ -313,8 +315,8 @@ __device__ __forceinline__ void v2_generic_group(const MeshArgs& A, unsigned cha
                 if (vgp < ggpe) code |= WIDE ? 4u : 32u;
                 En = (E == value) ? __fadd_rn(E, gpe) : vgp;
                 const float2 out = make_float2(value, fminf(vgp, ggpe));
-                ringw[(t & (R - 1)) * S + threadIdx.x] = out;
-                ringw[(R + (t & (R - 1))) * S + threadIdx.x] = out;   // second copy, read by the specialised warps
+                ringw[(t & (R - 1)) * RS + rcol] = out;
+                ringw[(R + (t & (R - 1))) * RS + rcol] = out;   // second copy, read by the specialised warps
                 if (s == (int)Lq - 1) *lastcol_ptr = value;
             }
             tbw |= code << ((WIDE ? 16 : 8) * u);
@@ -350,7 +352,7 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
     bool wlast = false;
     if (is_writer) {
         wnode = A.writers[((uint64_t)ql * A.gcap + g) * DP_G + j];
-        wcol = A.nthr[io + wnode];
+        wcol = A.rcol[((uint64_t)ql * A.gcap + g) * T + A.nthr[io + wnode]];   // ring column of the row's thread
         wsoff = (int)(A.nsigma[io + wnode] - gi.sigma_lo);
         wsr = A.spillrow[io + wnode];
         wlast = A.nflags[io + wnode] == 0;
@@ -363,12 +365,16 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
         return make_float2(0.f, 0.f);
     };
     auto gstore = [&](uint32_t t, float2 c) {
-        ring[(t & (R - 1)) * S + threadIdx.x] = c;
-        ring[(R + (t & (R - 1))) * S + threadIdx.x] = c;
+        ring[(t & (R - 1)) * RS + threadIdx.x] = c;
+        ring[(R + (t & (R - 1))) * RS + threadIdx.x] = c;
     };
-    // the last loader lane owns the constant edge column (value 1, dm 1) read by rows without predecessor
-    if (threadIdx.x == S - 1)
-        for (uint32_t r = 0; r < 2 * R; r++) ring[r * S + threadIdx.x] = make_float2(1.0f, 1.0f);
+    // the last loader lane owns the constant edge column (value 1, dm 1) read by rows without predecessor, the one
+    // before it the constant column (+inf, +inf) read by the padding slots of rows with fewer predecessors than
+    // their warp is specialised on: a candidate that can never win, and one shared address for all of them
+    if (threadIdx.x >= S - 2) {
+        const float cv = threadIdx.x == S - 1 ? 1.0f : __int_as_float(0x7f800000);
+        for (uint32_t r = 0; r < 2 * R; r++) ring[r * RS + threadIdx.x] = make_float2(cv, cv);
+    }
     // prologue = step -1 (a ghost with soff -1 must have position 0 in slot -1 before step 0); afterwards the
     // data of step t+4 is requested at step t, so the L2 latency never sits between two barriers
     // (GHOST_LEAD = 4 + 2 keeps that request behind the source row's spill store).
@@ -383,7 +389,7 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
     auto drain = [&](uint32_t t) {  // what the writer's row published at step t-1
         const int sw = (int)t - 1 - wsoff;
         if (is_writer && sw >= 0 && sw < (int)Lq) {
-            const float2 c = ring[((t - 1) & (R - 1)) * S + wcol];
+            const float2 c = ring[((t - 1) & (R - 1)) * RS + wcol];
             if (wsr >= 0) __stcg(&spill[(uint64_t)wsr * Lq + sw], c);
             if (wlast && (sw == 0 || c.x < rmin)) { rmin = c.x; rarg = (uint32_t)sw; }
         }
@@ -422,6 +428,7 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
             v2_loader_group(A, smem, ql, h, gi, g, steps4);
         } else {
             const uint32_t m = A.order[((uint64_t)ql * A.gcap + g) * T + tid];
+            const uint32_t rc = A.rcol[((uint64_t)ql * A.gcap + g) * T + tid];   // ring column this thread publishes to
             const bool valid = m != 0xFFFFFFFFu;
             uint32_t np = 0, pbase = 0, plane = 0, mask = 0;
             int soff = 0;
@@ -448,26 +455,28 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
                 const uint32_t shift = npw - np;
 #pragma unroll
                 for (int k = 0; k < NPF; k++) {
-                    ck[k] = (S - 1) * 8u;  // rows without predecessor: the constant edge column
+                    ck[k] = (S - 1) * 8u;  // rows without predecessor: the constant edge column (1, 1)
                     if (np > 0 && k < (int)npw) {
-                        const uint32_t ord = (uint32_t)k > shift ? (uint32_t)k - shift : 0u;
-                        const uint32_t d = pdesc2[pbase + ord];
-                        ck[k] = (d & 0xffffu) * 8u + (((uint32_t)R - (d >> 16)) & (R - 1)) * SLOT_BYTES;
+                        ck[k] = (S - 2) * 8u;   // padding slot: the constant (+inf, +inf) column, never a winner
+                        if ((uint32_t)k >= shift) {
+                            const uint32_t d = pdesc2[pbase + (uint32_t)k - shift];
+                            ck[k] = (d & 0xffffu) * 8u + (((uint32_t)R - (d >> 16)) & (R - 1)) * SLOT_BYTES;
+                        }
                     }
                 }
                 // lane's cell of step pair 0: halfword (u8 cells) or word (u16 cells) number tid
                 uint32_t* tbl = WIDE ? tbg + tid : reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(tbg) + tid);
-#define V2_CASE(N) case N: v2_fast_dispatch<N, WIDE, PLANES>(A, sring, sq, ck, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
+#define V2_CASE(N) case N: v2_fast_dispatch<N, WIDE, PLANES>(A, sring, sq, ck, rc, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
                 switch (npw) {
                     V2_CASE(1) V2_CASE(2) V2_CASE(3) V2_CASE(4) V2_CASE(5) V2_CASE(6) V2_CASE(7)
-                    default: v2_fast_dispatch<8, WIDE, PLANES>(A, sring, sq, ck, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
+                    default: v2_fast_dispatch<8, WIDE, PLANES>(A, sring, sq, ck, rc, valid, np, soff, Lq, plane, mask, w, steps4, lastcol_ptr, tbl); break;
                 }
 #undef V2_CASE
             } else {
                 if (!valid) soff = (int)(steps4 + 8);    // lane without a row: s stays negative
                 const float initv = np == 0 ? 1.0f : 1000000.0f;
                 uint32_t* tbl = WIDE ? tbg + tid : reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(tbg) + tid);
-                v2_generic_group<WIDE, PLANES>(A, smem, qt, Lq, steps4, npw, np, pdesc2 + pbase, soff,
+                v2_generic_group<WIDE, PLANES>(A, smem, qt, Lq, steps4, npw, np, pdesc2 + pbase, rc, soff,
                                        initv, plane, mask, __fmul_rn(A.ms, w), __fmul_rn(A.mms, w), lastcol_ptr, tbl);
             }
         }
@@ -662,7 +671,7 @@ int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0
     A.gcap = s->gcap; A.icap = s->icap; A.q0 = q0;
     A.nmask = w->d_nmask; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma; A.pred_off = w->d_pred_off;
     A.pdesc = w->d_pdesc; A.spillrow = w->d_spillrow; A.nflags = w->d_nflags;
-    A.pdesc2 = w->d_pdesc2; A.order = w->d_order; A.nthr = w->d_nthr; A.nshift = w->d_nshift;
+    A.pdesc2 = w->d_pdesc2; A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.nshift = w->d_nshift;
     A.ghosts = w->d_ghosts; A.writers = w->d_writers;
     A.tb = w->d_tb; A.spill = w->d_spill; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.ms = -ap.match_score; A.mms = -ap.mismatch_score; A.gp = ap.gap_penalty; A.gpe = ap.gap_ext_penalty;
