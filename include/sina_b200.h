@@ -15,6 +15,7 @@
  *                        cseq::fix_duplicate_positions                src/align.cpp:307-521, src/mseq.cpp:47-118,
  *                                                                     src/mesh.h:453-739, src/cseq.cpp:456-594
  *   sg_run_batch         the famfinder -> aligner node pair           src/sina.cpp:511,516
+ *   sg_turn_batch        famfinder::impl::turn_check (--turn)          src/famfinder.cpp:344-378
  *
  * Data layout: bases are SINA's IUPAC bit masks, one byte each (A=1 G=2 C=4 T/U=8, +16 lowercase;
  * src/aligned_base.h:38-52). A set of sequences is (masks[], off[n+1]); aligned rows add cols[] (alignment
@@ -107,6 +108,11 @@ int sg_index_list(const sg_index* ix, uint32_t kmer, uint32_t* ids, uint64_t cap
  * nres[q] = min(max, N). */
 int sg_find_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, uint32_t max,
                   int16_t* scores, uint32_t* ids, uint32_t* nres);
+/* --turn orientation check (famfinder::turn_check, src/famfinder.cpp:344-378): find(max = 1) on the query, its
+ * reverse, its complement and its reverse complement (mode 2 = "all"; mode 1 = "revcomp" skips the middle two).
+ * turn[q] = 0 none, 1 reversed, 2 complemented, 3 reversed and complemented: the first orientation with the strictly
+ * largest top score. The caller applies it to its sequence (cseq::reverse / complement) before family finding. */
+int sg_turn_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, int mode, int32_t* turn);
 /* famfinder stage: family per query in rank order. fam_ids/fam_scores: nq rows of fam_stride entries;
  * fam_n[q] = family size, or -1 when fewer than fs_req relatives remain. exclude_ids (optional): id of the
  * reference carrying the query's name (for --fs-leave-query-out), -1 for none. */
@@ -130,6 +136,8 @@ void sg_session_destroy(sg_session* s);
 int sg_session_upload(sg_session* s, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
                       const int64_t* exclude_ids);
 int sg_session_find(sg_session* s, uint32_t max);
+/* orientation check on the resident batch; the queries are left in the chosen orientation (turn may be null) */
+int sg_session_turn(sg_session* s, int mode, int32_t* turn);
 int sg_session_family(sg_session* s, const sg_fam_params* fp);
 int sg_session_set_family(sg_session* s, const uint32_t* fam_ids, const uint64_t* fam_off);
 int sg_session_align(sg_session* s, const sg_align_params* ap);

@@ -22,6 +22,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
 u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
 i16p = np.ctypeslib.ndpointer(np.int16, flags="C")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
 i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
 
@@ -176,6 +177,8 @@ class Oracle:
         L.so_index_build.restype = C.POINTER(_Index)
         L.so_index_build.argtypes = [C.c_uint32, u8p, u64p, C.c_int, C.c_int]
         L.so_index_free.argtypes = [C.POINTER(_Index)]
+        L.so_turn_check.restype = C.c_int
+        L.so_turn_check.argtypes = [C.POINTER(_Index), u8p, C.c_uint32, C.c_int, i32p]
         L.so_find.restype = C.c_uint32
         L.so_find.argtypes = [C.POINTER(_Index), u8p, C.c_uint32, C.c_uint32, i16p, u32p, C.POINTER(C.c_uint64)]
         L.so_family.restype = C.c_int
@@ -238,6 +241,12 @@ class Oracle:
         P = C.c_uint64()
         r = self.L.so_find(ix, q, len(q), max_results, sc, ids, C.byref(P))
         return sc[:r].copy(), ids[:r].copy(), P.value
+
+    def turn_check(self, ix, q, all_frames=True):
+        """famfinder::turn_check: (best orientation 0..3, the four top scores)"""
+        q = np.ascontiguousarray(q, np.uint8)
+        sc = np.zeros(4, np.int32)
+        return self.L.so_turn_check(ix, q, len(q), int(all_frames), sc), sc
 
     def family(self, ix, msa, q, fp=None, exclude_id=-1):
         fp = fp or FamParams()
@@ -349,6 +358,8 @@ class Ref:
         L.ref_kidx_list_size.argtypes = [C.c_void_p, C.c_uint32]
         L.ref_kidx_find.restype = C.c_uint32
         L.ref_kidx_find.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, i16p, u32p, C.POINTER(C.c_uint64)]
+        L.ref_turn_check.restype = C.c_int
+        L.ref_turn_check.argtypes = [C.c_void_p, C.c_char_p, C.c_int, i32p]
         L.ref_family.restype = C.c_int
         L.ref_family.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(FamParams), u32p, f32p, C.c_uint32]
         L.ref_graph.restype = C.c_int
@@ -417,6 +428,10 @@ class Ref:
         P = C.c_uint64()
         n = self.L.ref_kidx_find(ix, query.encode(), max_results, sc, ids, C.byref(P))
         return sc[:n].copy(), ids[:n].copy(), P.value
+
+    def turn_check(self, ix, query, all_frames=True):
+        sc = np.zeros(4, np.int32)
+        return self.L.ref_turn_check(ix, query.encode(), int(all_frames), sc), sc
 
     def family(self, ix, query, fp=None, qname=""):
         fp = fp or FamParams()

@@ -240,6 +240,43 @@ uint32_t ref_kidx_find(ref_kidx* ix, const char* query, uint32_t max, int16_t* s
     return max;
 }
 
+// famfinder::impl::turn_check (famfinder.cpp:344-378) on the reference's own cseq::reverse / complement
+// (cseq.cpp:284-296, aligned_base.h:117-124) and the restated find above. scores4 (optional) = the four top scores.
+int ref_turn_check(ref_kidx* ix, const char* query, int all, int32_t* scores4) {
+    const uint32_t N = ix->db->seqs.size();
+    auto top = [&](const cseq& c) -> double {
+        if (N == 0) return 0;
+        std::vector<rank_pair> ranks;
+        kidx_rank(ix, c, ranks, nullptr);
+        std::partial_sort(ranks.begin(), ranks.begin() + 1, ranks.end(), std::greater<rank_pair>());
+        return (float)ranks[0].first;
+    };
+    cseq q("q", query);
+    double score[4];
+    score[0] = top(q);
+    cseq turn(q);
+    turn.reverse();
+    if (all) {
+        score[1] = top(turn);
+        cseq comp(q);
+        comp.complement();
+        score[2] = top(comp);
+    } else {
+        score[1] = score[2] = 0;
+    }
+    turn.complement();
+    score[3] = top(turn);
+    double max = 0;
+    int best = 0;
+    for (int i = 0; i < 4; i++) {
+        if (max < score[i]) {
+            max = score[i], best = i;
+        }
+    }
+    if (scores4) for (int i = 0; i < 4; i++) scores4[i] = (int32_t)score[i];
+    return best;
+}
+
 // ---------------------------------------------------------------- family selection (restated)
 struct fam_item { float score; uint32_t id; };
 

@@ -232,6 +232,38 @@ uint32_t so_find(const so_index* ix, const uint8_t* q, uint32_t qlen, uint32_t m
     return max;
 }
 
+/* famfinder::impl::turn_check src/famfinder.cpp:344-378: top find() score of the query as is, reversed
+ * (cseq_base::reverse, src/cseq.cpp:284-289), complemented (base_iupac::complement, src/aligned_base.h:117-124)
+ * and reverse-complemented; the first orientation whose score is strictly above the running maximum (from 0) wins.
+ * all == 0 ("revcomp") leaves scores 1 and 2 at 0. scores4 (optional) receives the four scores. */
+static uint8_t mask_complement(uint8_t m) {
+    return (uint8_t)(((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 1u) << 3) | ((m & 8u) >> 3) | (m & 16u));
+}
+int so_turn_check(const so_index* ix, const uint8_t* q, uint32_t qlen, int all, int32_t* scores4) {
+    uint8_t* t = (uint8_t*)malloc(qlen ? qlen : 1);
+    int32_t score[4] = {0, 0, 0, 0};
+    int16_t sc;
+    uint32_t id;
+    if (so_find(ix, q, qlen, 1, &sc, &id, NULL)) score[0] = sc;
+    for (uint32_t i = 0; i < qlen; i++) t[i] = q[qlen - 1 - i];                      /* turn.reverse() */
+    if (all) {
+        if (so_find(ix, t, qlen, 1, &sc, &id, NULL)) score[1] = sc;
+        uint8_t* c = (uint8_t*)malloc(qlen ? qlen : 1);
+        for (uint32_t i = 0; i < qlen; i++) c[i] = mask_complement(q[i]);            /* comp.complement() */
+        if (so_find(ix, c, qlen, 1, &sc, &id, NULL)) score[2] = sc;
+        free(c);
+    }
+    for (uint32_t i = 0; i < qlen; i++) t[i] = mask_complement(t[i]);                /* turn.complement() */
+    if (so_find(ix, t, qlen, 1, &sc, &id, NULL)) score[3] = sc;
+    free(t);
+    int32_t max = 0;
+    int best = 0;
+    for (int i = 0; i < 4; i++)
+        if (max < score[i]) { max = score[i]; best = i; }
+    if (scores4) memcpy(scores4, score, sizeof(score));
+    return best;
+}
+
 /* ------------------------------------------------------------------ family selection */
 typedef struct {
     const so_fam_params* p;

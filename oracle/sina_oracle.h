@@ -51,6 +51,8 @@ typedef struct so_fam_params {
     int leave_query_out;
 } so_fam_params;
 /* exclude_id: reference with the query's name (-1: none). returns family size, -1 if < fs_req */
+/* famfinder::impl::turn_check (--turn): 0 none, 1 reversed, 2 complemented, 3 reversed + complemented */
+int so_turn_check(const so_index* ix, const uint8_t* q, uint32_t qlen, int all, int32_t* scores4);
 int so_family(const so_index* ix, const uint64_t* off, const uint32_t* cols, const uint8_t* q, uint32_t qlen,
               int64_t exclude_id, const so_fam_params* p, uint32_t* ids, float* scores, uint32_t cap,
               uint64_t* postings);

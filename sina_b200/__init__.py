@@ -18,13 +18,14 @@ LIB_PATH = os.path.join(HERE, "libsina_b200.so")
 EXPORTS = [
     "sg_default_fam_params", "sg_default_align_params", "sg_last_error", "sg_device_count",
     "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list",
-    "sg_find_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
-    "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_family",
+    "sg_find_batch", "sg_turn_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
+    "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_turn", "sg_session_family",
     "sg_session_set_family", "sg_session_align", "sg_session_sync", "sg_session_download_find",
     "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
 ]
 
 SG_Q_ALIGNED, SG_Q_COPIED, SG_Q_SKIPPED, SG_Q_NOSPACE, SG_Q_NOFAMILY = 0, 1, 2, 3, 4
+TURN_MODES = {"none": 0, "revcomp": 1, "all": 2}
 
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
@@ -100,6 +101,7 @@ def lib():
     L.sg_index_list.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.sg_index_list_sizes.argtypes = [C.c_void_p, u32p, C.c_uint32, u64p]
     L.sg_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_uint32, i16p, u32p, u32p]
+    L.sg_turn_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_int, i32p]
     L.sg_family_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_void_p, C.POINTER(FamParams), C.c_uint32,
                                   u32p, f32p, i32p]
     L.sg_align_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, u32p, u64p, C.POINTER(AlignParams), u32p, u8p,
@@ -111,6 +113,7 @@ def lib():
     L.sg_session_destroy.restype = None
     L.sg_session_upload.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_void_p]
     L.sg_session_find.argtypes = [C.c_void_p, C.c_uint32]
+    L.sg_session_turn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.sg_session_family.argtypes = [C.c_void_p, C.POINTER(FamParams)]
     L.sg_session_set_family.argtypes = [C.c_void_p, u32p, u64p]
     L.sg_session_align.argtypes = [C.c_void_p, C.POINTER(AlignParams)]
@@ -197,6 +200,14 @@ class Index:
         _check(lib().sg_find_batch(self.h, qmasks, qoff, nq, max_results, sc, ids, nres))
         return sc, ids, nres
 
+    def turn(self, qmasks, qoff, mode="all"):
+        """--turn orientation check (famfinder::turn_check): 0 none, 1 reversed, 2 complemented, 3 both, per query."""
+        qmasks, qoff = np.ascontiguousarray(qmasks, np.uint8), np.ascontiguousarray(qoff, np.uint64)
+        nq = len(qoff) - 1
+        out = np.zeros(nq, np.int32)
+        _check(lib().sg_turn_batch(self.h, qmasks, qoff, nq, TURN_MODES[mode], out))
+        return out
+
     def family(self, qmasks, qoff, fp=None, exclude_ids=None):
         fp = fp or FamParams()
         qmasks, qoff = np.ascontiguousarray(qmasks, np.uint8), np.ascontiguousarray(qoff, np.uint64)
@@ -268,6 +279,12 @@ class Session:
     def find(self, max_results):
         _check(lib().sg_session_find(self.h, max_results))
         self.find_max = min(max_results, self.index.N)
+
+    def turn(self, mode="all"):
+        """orientation check on the resident batch; leaves the queries in the chosen orientation"""
+        out = np.zeros(self.nq, np.int32)
+        _check(lib().sg_session_turn(self.h, TURN_MODES[mode], out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def family(self, fp=None):
         self.fp = fp or FamParams()

@@ -18,11 +18,6 @@ static int dmalloc(T** p, uint64_t n) {
     SG_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)));
     return SG_OK;
 }
-#define SG_TRY(x)                  \
-    do {                           \
-        int rc__ = (x);            \
-        if (rc__ != SG_OK) return rc__; \
-    } while (0)
 
 static uint64_t env_mb(const char* name, uint64_t dflt_mb) {
     const char* v = getenv(name);
@@ -298,6 +293,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     SG_TRY(dmalloc(&s->d_kmers, s->max_bases + 32)); SG_TRY(dmalloc(&s->d_nk, Q));
     SG_TRY(dmalloc(&s->d_cand_n, Q * ix->n_tiles)); SG_TRY(dmalloc(&s->d_nres, Q)); SG_TRY(dmalloc(&s->d_counters, 8));
     SG_TRY(dmalloc(&s->d_fam_n, Q)); SG_TRY(dmalloc(&s->d_retry, 2)); SG_TRY(dmalloc(&s->d_hdr, Q));
+    SG_TRY(dmalloc(&s->d_turn_scores, 4 * Q)); SG_TRY(dmalloc(&s->d_turn, Q)); SG_TRY(dmalloc(&s->d_turn_ops, Q));
     SG_TRY(dmalloc(&s->d_out_cols, s->max_bases + 4)); SG_TRY(dmalloc(&s->d_out_masks, s->max_bases + 16));
     SG_TRY(dmalloc(&s->d_results, Q));
     SG_CUDA(cudaMemset(s->d_counters, 0, 64));
@@ -312,7 +308,8 @@ void sg_session_destroy(sg_session* h) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     free_align(s);
     void* ptrs[] = {s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
-                    s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results};
+                    s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results,
+                    s->d_turn_scores, s->d_turn, s->d_turn_ops};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->cev) if (e) cudaEventDestroy(e);
@@ -361,6 +358,26 @@ int sg_session_find(sg_session* h, uint32_t max) {
     SG_TRY(launch_find(s, max));
     SG_TRY(stage_end(s, &s->stats.ms_find));
     s->have_find = true;
+    return SG_OK;
+}
+
+int sg_session_turn(sg_session* h, int mode, int32_t* turn) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_turn: no queries uploaded");
+    if (mode < 0 || mode > 2) SG_FAIL(SG_ERR_ARG, "sg_session_turn: mode must be 0 (none), 1 (revcomp) or 2 (all)");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    if (mode == 0) {
+        if (turn) memset(turn, 0, (size_t)s->nq * 4);
+        return SG_OK;
+    }
+    SG_TRY(stage_begin(s, 0));
+    SG_TRY(launch_turn(s, mode == 2));
+    SG_TRY(stage_end(s, &s->stats.ms_find));
+    if (turn) {
+        SG_CUDA(cudaMemcpyAsync(turn, s->d_turn, (uint64_t)s->nq * 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    s->have_find = s->have_family = s->have_align = false;   // the query buffer changed
     return SG_OK;
 }
 
@@ -690,6 +707,19 @@ int sg_find_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uin
         SG_TRY(sg_session_find(s, max));
         SG_TRY(sg_session_download_find(s, scores ? scores + (uint64_t)a * m : nullptr, ids ? ids + (uint64_t)a * m : nullptr,
                                         nres ? nres + a : nullptr));
+    }
+    return SG_OK;
+}
+
+int sg_turn_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, int mode, int32_t* turn) {
+    if (!ix || !qmasks || !qoff || nq == 0 || !turn) SG_FAIL(SG_ERR_ARG, "sg_turn_batch: bad argument");
+    SessionLease L(ix, qoff, nq);
+    if (L.rc) return L.rc;
+    sg_session* s = (sg_session*)L.s;
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, nullptr));
+        SG_TRY(sg_session_turn(s, mode, turn + a));
     }
     return SG_OK;
 }

@@ -26,6 +26,12 @@ void set_error(const std::string& msg);
         return code;            \
     } while (0)
 
+#define SG_TRY(x)                       \
+    do {                                \
+        int rc__ = (x);                 \
+        if (rc__ != SG_OK) return rc__; \
+    } while (0)
+
 // ------------------------------------------------------------------ constants
 constexpr int MAX_K = 16;
 constexpr uint32_t SUB_DEFAULT = 4096;       // references per search sub-tile: one warp owns its u16 score counters (8 KB)
@@ -181,6 +187,10 @@ struct Session {
     float* d_fam_scores = nullptr;   // [nq][fam_cap]
     int32_t* d_fam_n = nullptr;      // [nq] (-1: too few, -2: window too small)
     uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window
+    // orientation check (--turn)
+    int32_t* d_turn_scores = nullptr; // [4][nq] top k-mer score of the query as is / reversed / complemented / both
+    int32_t* d_turn = nullptr;        // [nq] chosen orientation 0..3
+    uint8_t* d_turn_ops = nullptr;    // [nq]
     // align (whole batch)
     uint32_t icap = 0, ncap = 0, gcap = 0;  // per-query capacities: items (= nodes = edges), column ranks, DP groups
     uint32_t* d_afam = nullptr;      // [nq][fam_cap] family after the contains-query partition
@@ -219,6 +229,7 @@ struct Session {
 int launch_index_build(Index* ix, cudaStream_t st);
 int launch_find(Session* s, uint32_t max);
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window);
+int launch_turn(Session* s, int all);
 int launch_prealign(Session* s, const sg_align_params& ap);
 int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
 int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);

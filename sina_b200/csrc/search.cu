@@ -296,6 +296,88 @@ int launch_find(Session* s, uint32_t max) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Orientation check (--turn): famfinder::impl::turn_check + do_turn_check (reference src/famfinder.cpp:311-378).
+// The reference runs find(max = 1) on the query, its reverse, its complement and its reverse complement and keeps
+// the first orientation with the strictly largest top score. Here the query buffer is transformed in place between
+// the searches (orig -> reversed -> complemented -> reverse-complemented) and finally brought to the chosen one.
+// op bit 0 = reverse (cseq_base::reverse, src/cseq.cpp:284-289), bit 1 = complement (base_iupac::complement,
+// src/aligned_base.h:117-124: A<->T/U, G<->C on the IUPAC bits, case kept).
+__device__ __forceinline__ uint8_t mask_complement(uint8_t m) {
+    return (uint8_t)(((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 1u) << 3) | ((m & 8u) >> 3) | (m & 16u));
+}
+
+// one warp per query; ops: per-query op code, or null for the uniform code `op_all`
+__global__ void __launch_bounds__(128) orient_kernel(uint8_t* __restrict__ qmasks, const uint64_t* __restrict__ qoff,
+                                                     uint32_t nq, const uint8_t* __restrict__ ops, uint32_t op_all) {
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (q >= nq) return;
+    const uint32_t op = ops ? ops[q] : op_all;
+    if (op == 0) return;
+    uint8_t* m = qmasks + qoff[q];
+    const uint32_t n = (uint32_t)(qoff[q + 1] - qoff[q]);
+    const bool rev = op & 1u, comp = op & 2u;
+    if (rev) {
+        for (uint32_t i = lane_id(); i < (n + 1) / 2; i += 32) {
+            const uint32_t j = n - 1 - i;
+            uint8_t a = m[i], b = m[j];
+            if (comp) { a = mask_complement(a); b = mask_complement(b); }
+            m[i] = b;
+            m[j] = a;   // i == j (middle base): written twice with the same value
+        }
+    } else {
+        for (uint32_t i = lane_id(); i < n; i += 32) m[i] = mask_complement(m[i]);
+    }
+}
+
+// top score of every query after find(max = 1) into column `which` of scores[4][nq]
+__global__ void turn_score_kernel(const uint64_t* __restrict__ ranked, const uint32_t* __restrict__ nres, uint32_t max,
+                                  uint32_t nq, int32_t* __restrict__ scores, uint32_t which) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    scores[(uint64_t)which * nq + q] = nres[q] ? (int32_t)(ranked[(uint64_t)q * max] >> 32) : 0;
+}
+
+// best orientation (strict '>' from 0 in the order none, reversed, complemented, both; src/famfinder.cpp:369-377) and
+// the op that takes the buffer from its current state `state` to it
+__global__ void turn_pick_kernel(const int32_t* __restrict__ scores, uint32_t nq, uint32_t state,
+                                 int32_t* __restrict__ turn, uint8_t* __restrict__ ops) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int32_t mx = 0, best = 0;
+    for (int i = 0; i < 4; i++) {
+        const int32_t sc = scores[(uint64_t)i * nq + q];
+        if (mx < sc) { mx = sc; best = i; }
+    }
+    turn[q] = best;
+    ops[q] = (uint8_t)((uint32_t)best ^ state);   // orientations are the group {1, rev, comp, rev*comp}: codes xor
+}
+
+int launch_turn(Session* s, int all) {
+    const uint32_t nq = s->nq, gw = (nq + 3) / 4, gt = (nq + 127) / 128;
+    SG_CUDA(cudaMemsetAsync(s->d_turn_scores, 0, (uint64_t)4 * nq * 4, s->stream));
+    auto search = [&](uint32_t which) -> int {
+        SG_TRY(launch_find(s, 1));
+        turn_score_kernel<<<gt, 128, 0, s->stream>>>(s->d_ranked, s->d_nres, s->find_max, nq, s->d_turn_scores, which);
+        return SG_OK;
+    };
+    auto orient = [&](uint32_t op) { orient_kernel<<<gw, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, nq, nullptr, op); };
+    uint32_t state = 0;                      // orientation code of the buffer: bit 0 reversed, bit 1 complemented
+    SG_TRY(search(0));
+    if (all) {
+        orient(1); state = 1; SG_TRY(search(1));
+        orient(3); state = 2; SG_TRY(search(2));   // reversed -> complemented
+        orient(1); state = 3; SG_TRY(search(3));
+    } else {
+        orient(3); state = 3; SG_TRY(search(3));
+    }
+    turn_pick_kernel<<<gt, 128, 0, s->stream>>>(s->d_turn_scores, nq, state, s->d_turn, s->d_turn_ops);
+    orient_kernel<<<gw, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, nq, s->d_turn_ops, 0);
+    SG_CUDA(cudaGetLastError());
+    s->stats.kernel_launches += (all ? 4 : 2) * 1 + (all ? 3 : 1) + 2;
+    return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // One thread per query walks its ranked candidates with the reference's quota rules. The outcome only
 // depends on earlier items, and once both quotas are met every later item is removed, so scanning a
 // window that reaches that point equals the reference's retry loop (:591-608); if the window ends first

@@ -1,5 +1,7 @@
 #include "cseq.h"
 
+#include <algorithm>
+
 #include <cstring>
 
 namespace sina {
@@ -11,6 +13,7 @@ const char* const fn_qual = "align_quality_slv";
 const char* const fn_head = "align_cutoff_head_slv";
 const char* const fn_tail = "align_cutoff_tail_slv";
 const char* const fn_date = "aligned_slv";
+const char* const fn_turn = "turn";
 const char* const fn_family = "align_family_slv";
 const char* const fn_filter = "align_filter_slv";
 const char* const fn_used_rels = "used_rels";
@@ -107,6 +110,18 @@ std::string cseq::getAligned(bool nodots, bool dna) const {
         aligned.append(alignment_width - cursor, dot);
     }
     return aligned;
+}
+
+void cseq::reverse() {
+    std::reverse(bases.begin(), bases.end());
+    for (auto& b : bases) b.setPosition(alignment_width - 1 - b.getPosition());
+}
+
+void cseq::complement() {
+    for (auto& b : bases) {
+        const uint8_t m = b.getBase();   // A<->T/U, G<->C on the IUPAC bits, case kept
+        b = aligned_base(b.getPosition(), (uint8_t)(((m & 2u) << 1) | ((m & 4u) >> 1) | ((m & 1u) << 3) | ((m & 8u) >> 3) | (m & 16u)));
+    }
 }
 
 void cseq::upperCaseAll() {

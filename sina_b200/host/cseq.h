@@ -61,6 +61,8 @@ public:
     std::string getBases() const;                          // unaligned RNA string (src/cseq.cpp:176-188)
     std::string getAligned(bool nodots = false, bool dna = false) const;  // src/cseq.cpp:135-174
     void upperCaseAll();
+    void reverse();                                        // src/cseq.cpp:284-289: order and positions mirrored
+    void complement();                                     // src/cseq.cpp:292-296, src/aligned_base.h:117-124
     bool operator<(const cseq& o) const { return name < o.name; }
 
     // attributes (the reference keeps a boost::variant map, src/cseq.h:236-262; strings are enough here)
@@ -93,6 +95,7 @@ private:
 };
 
 // attribute names (src/query_arb.cpp:107-126)
+extern const char* const fn_turn;
 extern const char* const fn_acc;
 extern const char* const fn_start;
 extern const char* const fn_fullname;

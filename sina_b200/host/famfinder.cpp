@@ -14,8 +14,8 @@ void famfinder::get_options_description(po::options_description& main, po::optio
     main.value<std::string>("db,r", &opts.database, "", "reference database (aligned FASTA)");
     main.custom("turn,t", "none", "check other strand as well ('all' checks all four frames)", [](const std::string& v) {
         if (v == "none") opts.turn_which = TURN_NONE;
-        else if (v == "revcomp" || v == "all")
-            throw std::logic_error("--turn " + v + " is not supported by sina_b200 (only 'none')");
+        else if (v == "revcomp") opts.turn_which = TURN_REVCOMP;
+        else if (v == "all") opts.turn_which = TURN_ALL;
         else throw std::logic_error("Turn type must be one of 'none', 'revcomp' or 'all'");
     });
     po::options_description mid("Reference Selection");
@@ -79,7 +79,35 @@ famfinder::famfinder(const famfinder& o) = default;
 famfinder& famfinder::operator=(const famfinder& o) = default;
 famfinder::~famfinder() = default;
 
-int famfinder::turn_check(const cseq& /*query*/, bool /*all*/) { return 0; }
+int famfinder::turn_check(const cseq& query, bool all) {
+    if (query.size() < 2) return 0;
+    std::vector<const cseq*> qs{&query};
+    std::vector<uint8_t> masks;
+    std::vector<uint64_t> off;
+    pack_queries(qs, masks, off);
+    int32_t turn = 0;
+    check_sg(sg_turn_batch(pimpl->index->handle(), masks.data(), off.data(), 1, all ? 2 : 1, &turn), "orientation check");
+    return turn;
+}
+
+// famfinder::impl::do_turn_check (src/famfinder.cpp:311-341) for a batch of trays
+static void do_turn_check(sg_index* handle, std::vector<tray*>& live, const std::vector<uint8_t>& masks,
+                          const std::vector<uint64_t>& off, TURN_TYPE which) {
+    if (which == TURN_NONE) {
+        for (tray* t : live) t->input_sequence->set_attr<std::string>(fn_turn, "turn-check disabled");
+        return;
+    }
+    std::vector<int32_t> turn(live.size());
+    check_sg(sg_turn_batch(handle, masks.data(), off.data(), (uint32_t)live.size(), which == TURN_ALL ? 2 : 1, turn.data()),
+             "orientation check");
+    static const char* const what[4] = {"none", "reversed", "complemented", "reversed and complemented"};
+    for (size_t i = 0; i < live.size(); i++) {
+        cseq& c = *live[i]->input_sequence;
+        c.set_attr<std::string>(fn_turn, what[turn[i] & 3]);
+        if (turn[i] & 1) c.reverse();
+        if (turn[i] & 2) c.complement();
+    }
+}
 
 void famfinder::impl::run(std::vector<tray*>& trays) {
     if (trays.empty()) return;
@@ -101,6 +129,8 @@ void famfinder::impl::run(std::vector<tray*>& trays) {
     std::vector<uint8_t> masks;
     std::vector<uint64_t> off;
     pack_queries(qs, masks, off);
+    do_turn_check(index->handle(), live, masks, off, opts.turn_which);
+    if (opts.turn_which != TURN_NONE) pack_queries(qs, masks, off);   // the sequences may have been turned
     sg_fam_params fp;
     sg_default_fam_params(&fp);
     fp.fs_min = opts.fs_min; fp.fs_max = opts.fs_max; fp.fs_msc = opts.fs_msc; fp.fs_msc_max = opts.fs_msc_max;

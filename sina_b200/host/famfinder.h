@@ -24,7 +24,7 @@ public:
     tray operator()(const tray& t);
     void run(std::vector<tray>& trays);
 
-    int turn_check(const cseq& query, bool all);  // only TURN_NONE is supported: always 0
+    int turn_check(const cseq& query, bool all);  // src/famfinder.cpp:344-378: 0 none, 1 reversed, 2 complemented, 3 both
 
     static void get_options_description(po::options_description& main, po::options_description& adv);
     static void validate_vm(po::variables_map& vm, po::options_description& desc);

@@ -129,7 +129,19 @@ static void test_options() {
     CHECK(rejects({"--fs-engine", "pt-server"})); CHECK(rejects({"--fs-no-graph"})); CHECK(rejects({"--use-subst-matrix"}));
     CHECK(rejects({"--filter", "x"})); CHECK(rejects({"--insertion", "forbid"})); CHECK(rejects({"--overhang", "bogus"}));
     CHECK(rejects({"--no-such-option"})); CHECK(rejects({"--fs-min"})); CHECK(rejects({"--fs-min", "abc"}));
-    CHECK(rejects({"--turn", "all"})); CHECK(rejects({"stray"}));
+    CHECK(rejects({"--turn", "sideways"})); CHECK(rejects({"stray"}));
+    CHECK(!rejects({"--turn", "all"})); CHECK(famfinder::opts.turn_which == TURN_ALL);
+    CHECK(!rejects({"--turn", "revcomp"})); CHECK(famfinder::opts.turn_which == TURN_REVCOMP);
+    CHECK(!rejects({"--turn", "none"})); CHECK(famfinder::opts.turn_which == TURN_NONE);
+    {   // cseq::reverse / complement (src/cseq.cpp:284-296; src/unit_tests/cseq_test.cpp has reverse on aligned data)
+        cseq c("", "-AG--CUR-n");
+        c.reverse();
+        EQUAL(c.getAligned(true, false), std::string("n-RUC--GA-"));
+        c.complement();
+        EQUAL(c.getAligned(true, false), std::string("n-YAG--CU-"));
+        c.reverse(); c.complement();
+        EQUAL(c.getAligned(true, false), std::string("-AG--CUR-n"));
+    }
     CHECK(!rejects({"--fs-min", "7"}));
     { po::variables_map vm; THROWS(famfinder::validate_vm(vm, all), std::logic_error); }  // --db is mandatory
 }

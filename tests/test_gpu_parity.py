@@ -279,3 +279,48 @@ def test_chunk_pipeline_and_arena_retry(orc, monkeypatch):
                            (batch, streams, tb_mb, i))
         ix.close()
     orc.index_free(oix)
+
+
+def test_turn_check_vs_oracle(orc):
+    """--turn (sg_turn_batch / sg_session_turn, famfinder::turn_check src/famfinder.cpp:344-378): orientation per
+    query against the oracle in both modes; the session leaves the batch in the chosen orientation, so family finding
+    and alignment afterwards equal the oracle's on the turned queries"""
+    tree, m, c, o = synth.synth_msa(600, W=3000, L=600, seed=5)
+    msa = O.MSA(m, c, o, 3000)
+    qm, qo = synth.synth_queries(tree, 40, "full", seed=3)
+    comp = lambda a: (((a & 2) << 1) | ((a & 4) >> 1) | ((a & 1) << 3) | ((a & 8) >> 3) | (a & 16)).astype(np.uint8)
+    turned = lambda q, t: comp(q[::-1].copy() if t & 1 else q) if t & 2 else (q[::-1].copy() if t & 1 else q.copy())
+    qs = []
+    for i in range(40):
+        q = qm[int(qo[i]):int(qo[i + 1])]
+        if i % 7 == 0:
+            q = q[:-1]                       # odd / even lengths
+        qs.append(turned(q, i % 4))
+    qs.append(O.encode("ACGUAC"))            # no k-mer at all: stays as it is
+    qmask, qoff = pack_queries(qs)
+    oix = orc.index_build(msa, 8, 0)
+    ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=8)
+    fp_kw = dict(fs_min=15, fs_max=15, fs_min_len=100, fs_full_len=560, fs_req_gaps=5)
+    for mode in ("all", "revcomp"):
+        want = np.array([orc.turn_check(oix, q, mode == "all")[0] for q in qs], np.int32)
+        got = ix.turn(qmask, qoff, mode)
+        assert (got == want).all(), (mode, got, want)
+        if mode == "all":
+            assert (want[:40] == np.arange(40) % 4).all() and want[40] == 0
+        s = sina_b200.Session(ix, len(qs), len(qmask))
+        s.upload(qmask, qoff)
+        assert (s.turn(mode) == want).all()
+        s.family(sina_b200.FamParams(**fp_kw))
+        s.align(sina_b200.AlignParams())
+        oc, om, res = s.download_align()
+        s.close()
+        tq, toff = pack_queries([turned(q, int(t)) for q, t in zip(qs, want)])
+        ores, occ, omm, cells, posts, nt = orc.run_batch(oix, msa, tq, toff, O.FamParams(**fp_kw), O.AlignParams())
+        for i in range(len(qs)):
+            a, n = int(qoff[i]), ores[i].n_out
+            assert res[i]["status"] == ores[i].status, (mode, i)
+            if ores[i].status in (0, 1):
+                assert (oc[a:a + n] == occ[a:a + n]).all() and (om[a:a + n] == omm[a:a + n]).all(), (mode, i)
+                assert bits(res[i]["score"]) == bits(ores[i].score), (mode, i)
+    orc.index_free(oix)
+    ix.close()

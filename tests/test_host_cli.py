@@ -135,3 +135,43 @@ def test_cli_soft_failures_and_copy(orc, data, tmp_path):
     assert r.returncode == 0
     w2, res2 = oracle_strings(orc, msa, [O.encode(sub)], dict(realign=1))
     assert res2[0].status == 0 and read_fasta(out)["contained"] == w2[0]
+
+
+def test_cli_turn(orc, data, tmp_path):
+    """--turn all / revcomp (src/famfinder.cpp:311-378): queries given in any of the four orientations come out aligned
+    like their forward form; without --turn the reference-side semantics keep them as they are"""
+    d, msa, qmasks = data
+    comp = str.maketrans("ACGUacgu", "UGCAugca")
+    fwd = [O.decode(q) for q in qmasks[:12]]
+    given = []
+    for i, s in enumerate(fwd):
+        t = i % 4
+        s2 = s[::-1] if t & 1 else s
+        given.append(s2.translate(comp) if t & 2 else s2)
+    write_fasta(tmp_path / "q.fasta", ["q%d" % i for i in range(12)], given)
+    out = tmp_path / "out.fasta"
+    base = [os.path.join(BIN, "sina"), "-i", str(tmp_path / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta")] + FAM_ARGS
+    r = subprocess.run(base + ["--turn", "all"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = read_fasta(out)
+    oix = orc.index_build(msa, 6, 0)
+    turns = [orc.turn_check(oix, O.encode(g), True)[0] for g in given]
+    orc.index_free(oix)
+
+    def apply(s, t):
+        s2 = s[::-1] if t & 1 else s
+        return s2.translate(comp) if t & 2 else s2
+    want, res = oracle_strings(orc, msa, [O.encode(apply(g, t)) for g, t in zip(given, turns)], {})
+    for i, w in enumerate(want):
+        if w is not None:
+            assert got["q%d" % i] == w, i
+    r = subprocess.run(base + ["--turn", "revcomp"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = read_fasta(out)
+    oix = orc.index_build(msa, 6, 0)
+    turns = [orc.turn_check(oix, O.encode(g), False)[0] for g in given]
+    orc.index_free(oix)
+    want, res = oracle_strings(orc, msa, [O.encode(apply(g, t)) for g, t in zip(given, turns)], {})
+    for i, w in enumerate(want):
+        if w is not None:
+            assert got["q%d" % i] == w, i

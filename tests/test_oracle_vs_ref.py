@@ -164,3 +164,35 @@ def test_fix_duplicate_positions_random(orc, ref):
         if st2 == 0:
             assert (p1 == po).all() and O.decode(m1) == co.tobytes().decode()
     assert nerr > 0
+
+
+def test_turn_check_oracle_vs_ref(orc, ref):
+    """--turn: famfinder::impl::turn_check (src/famfinder.cpp:344-378) restated in C vs the harness running the
+    reference's own cseq::reverse / complement; queries in all four orientations, odd and even lengths, 'all' and
+    'revcomp' modes, and a query without any k-mer hit (best stays 0)"""
+    tree, m, c, o = synth.synth_msa(500, W=2500, L=500, seed=11)
+    msa = O.MSA(m, c, o, 2500)
+    qm, qo = synth.synth_queries(tree, 24, "full", seed=9)
+    comp = lambda a: (((a & 2) << 1) | ((a & 4) >> 1) | ((a & 1) << 3) | ((a & 8) >> 3) | (a & 16)).astype(np.uint8)
+    oix = orc.index_build(msa, 8, 0)
+    db = ref.db(msa)
+    rix = ref.kidx_build(db, 8, 0)
+    seen = set()
+    for i in range(24):
+        q = qm[int(qo[i]):int(qo[i + 1])]
+        if i % 5 == 0:
+            q = q[:-1]
+        var = [q, q[::-1].copy(), comp(q), comp(q[::-1].copy())][i % 4]
+        for allf in (True, False):
+            a, asc = orc.turn_check(oix, var, allf)
+            b, bsc = ref.turn_check(rix, O.decode(var), allf)
+            assert a == b and (asc == bsc).all(), (i, allf, asc, bsc)
+            if allf:
+                seen.add(a)
+                assert a == [0, 1, 2, 3][i % 4]      # turning it back is what scores best
+    assert seen == {0, 1, 2, 3}
+    none = O.encode("ACGU")                          # shorter than k: no k-mer, all scores 0
+    assert orc.turn_check(oix, none, True)[0] == 0 and ref.turn_check(rix, "ACGU", True)[0] == 0
+    orc.index_free(oix)
+    ref.kidx_free(rix)
+    ref.db_free(db)
