@@ -26,6 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_REFS, W_COLS, L_REF, KMER = 50000, 50000, 1500, 10
+CHUNK = int(os.environ.get("SG_BATCH", "888"))   # queries per graph/DP/backtrack launch (the library's default)
 SEED = 20260117
 
 
@@ -304,10 +305,10 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["mesh_v2_kernel"]
-            traffic = tj["dram_bytes_per_query"] * min(1184, nq_iso) / 1e9   # GB per launch of one 1184-query chunk
+            traffic = tj["dram_bytes_per_query"] * min(CHUNK, nq_iso) / 1e9   # GB per launch of one full chunk
         except Exception:
             pass
-        launches_iso = max(1, -(-nq_iso // 1184))
+        launches_iso = max(1, -(-nq_iso // CHUNK))
         line = {
             "metric": "sequences aligned/sec", "value": value, "unit": "sequences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -318,7 +319,7 @@ def main():
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"kernel": "mesh_v2_kernel", "bound": "hbm", "achieved": gcups * 1.0,
                          "peak": hbm_peak, "unit": "GB/s", "frac": gcups / hbm_peak,
-                         "traffic": traffic, "traffic_unit": "GB per launch (1184-query chunk), ncu dram read+write",
+                         "traffic": traffic, "traffic_unit": "GB per launch (%d-query chunk), ncu dram read+write" % CHUNK,
                          "algorithmic_gb_per_launch": cells_iso / launches_iso / 1e9,
                          "peak_source": peak_src,
                          "note": "1 B of traceback per cell is the only mandatory HBM traffic, so the HBM fraction is low by "

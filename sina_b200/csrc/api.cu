@@ -91,13 +91,14 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     SG_TRY(dmalloc(&s->d_contains, Q * fam_cap)); SG_TRY(dmalloc(&s->d_copy_src, Q * 2));
     // arenas per workspace: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
     const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
-    uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (4 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));
+    uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (2 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));   // V <= ~1.5 row lengths in practice; a chunk that does not fit is re-run (retire_chunk)
     uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (256 * max_qlen_guess * 8 / 1000000 + 1))));
     s->tb_words = tb_mb * 1024 * 1024 / 4;
     s->spill_elems = sp_mb * 1024 * 1024 / 8;
-    // one workspace when the batch is a single chunk, else SG_STREAMS (default 2) so that chunks overlap
+    // one workspace when the batch is a single chunk, else SG_STREAMS (default 4) so that chunks overlap: measured on
+    // B200 (10k full-length queries): 1184 x 2: 91.3k seq/s, 1184 x 3: 99.7k, 888 x 3: 97.3k, 888 x 4: 99.8k, 592 x 4: 98.7k
     const uint64_t n_chunks = (Q + C - 1) / C;
-    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 2)), MAX_WS);
+    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 4)), MAX_WS);
     if ((uint64_t)want > n_chunks) want = (int)n_chunks;
     for (int i = 0; i < want; i++) {
         SG_TRY(alloc_workspace(s, &s->ws[i]));
@@ -282,7 +283,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     SG_CUDA(cudaSetDevice(ix->device));
     Session* s = new Session;
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
-    s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 1184)));
+    s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 888)));
     s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
     s->bankplan = (int)env_mb("SG_BANKPLAN", 0);
     *out = (sg_session*)s;

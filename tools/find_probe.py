@@ -11,9 +11,10 @@ ap.add_argument("--queries", type=int, default=2048)
 ap.add_argument("--k", type=int, default=10)
 ap.add_argument("--nofast", action="store_true")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--kind", default="full")
 a = ap.parse_args()
 tree, m, c, o = synth.synth_msa(a.refs, W=50000, L=1500, seed=20260117)
-qm, qo = synth.synth_queries(tree, a.queries, "full", seed=1000)
+qm, qo = synth.synth_queries(tree, a.queries, a.kind, seed=1000)
 ix = sina_b200.Index(m, c, o, 50000, k=a.k, nofast=a.nofast)
 s = sina_b200.Session(ix, a.queries, int(qo[-1]))
 s.upload(qm, qo)
