@@ -66,7 +66,8 @@ typedef struct sg_align_params {
     float fs_weight;       /* --fs-weight 1 */
     int32_t overhang;      /* --overhang: 0 attach, 1 remove, 2 edge */
     int32_t lowercase;     /* --lowercase: 0 none, 1 original, 2 unaligned */
-    int32_t insertion;     /* --insertion: 0 shift, 2 remove (= shift, as in the reference); 1 forbid: SG_ERR_ARG */
+    int32_t insertion;     /* --insertion: 0 shift, 1 forbid (transition_aspace_aware, src/mesh.h:377-438; runs in the
+                            * generic DP kernel), 2 remove (= shift, as in the reference) */
     int32_t realign;       /* --realign */
 } sg_align_params;
 

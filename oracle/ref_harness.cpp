@@ -414,6 +414,46 @@ static bool iequals(const std::string& a, const std::string& b) {
 
 struct align_item { float score; const cseq* sequence; };
 
+// do_align (align.cpp:475-521) for one transition type: transition_simple, or transition_aspace_aware for
+// --insertion forbid (choose_transition, align.cpp:462-473)
+extern "C++" {
+template <typename TR>
+static bool run_dp(mseq& m, cseq& c, const scoring_scheme_simple& s, const ref_align_params& P, ref_align_result& R,
+                   std::stringstream& log, std::string* logstr, uint32_t* cells, uint64_t cells_cap_words) {
+    using cell_t = typename TR::data_type;
+    TR tr(s);
+    compute_node_simple<TR> cns(tr);
+    mesh<mseq, cseq, cell_t> A(m, c);
+    compute(A, cns);
+    if (cells) {
+        uint64_t n = (uint64_t)m.size() * c.size();
+        if (n * 7 <= cells_cap_words) {
+            for (uint64_t i = 0; i < n; i++) {
+                cell_t& d = A(i);
+                uint32_t* o = cells + i * 7;
+                o[0] = d.value_midx; o[1] = d.value_sidx; o[2] = d.gapm_idx; o[3] = d.gaps_idx;
+                memcpy(o + 4, &d.value, 4); memcpy(o + 5, &d.gapm_val, 4); memcpy(o + 6, &d.gaps_val, 4);
+            }
+        }
+    }
+    c.clearSequence();
+    int oh_head = 0, oh_tail = 0;
+    try {
+        float score = backtrack(A, c, tr, (OVERHANG_TYPE)P.overhang, (LOWERCASE_TYPE)P.lowercase,
+                                (INSERTION_TYPE)P.insertion, oh_head, oh_tail, log);
+        R.score = score;
+        R.head = oh_head; R.tail = oh_tail;
+        R.qual = (int)std::min(100.f, std::max(0.f, 100.f * score));  // align.cpp:509
+        R.status = 0;
+    } catch (std::runtime_error& e) {
+        R.status = 3;
+        if (logstr) *logstr = log.str() + e.what();
+        return false;
+    }
+    return true;
+}
+}  // extern "C++"
+
 // aligner::operator() (align.cpp:307-460) + do_align (:475-521) for the graph/simple-scheme path.
 // `cells` (optional) receives the full mesh, 7 x u32/f32 per cell in data_type field order
 // {value_midx, value_sidx, gapm_idx, gaps_idx, value, gapm_val, gaps_val}; must hold n_nodes*qlen*7 words.
@@ -462,35 +502,10 @@ static void align_one(ref_db* db, std::vector<align_item>& vc, const cseq& input
         m.reduce_edges();
         R.n_nodes = m.size();
         scoring_scheme_simple s(-P.match_score, -P.mismatch_score, P.gap_penalty, P.gap_ext_penalty);
-        mesh_tr tr(s);
-        compute_node_simple<mesh_tr> cns(tr);
-        mesh<mseq, cseq, mesh_cell> A(m, c);
-        compute(A, cns);
-        if (cells) {
-            uint64_t n = (uint64_t)m.size() * c.size();
-            if (n * 7 <= cells_cap_words) {
-                for (uint64_t i = 0; i < n; i++) {
-                    mesh_cell& d = A(i);
-                    uint32_t* o = cells + i * 7;
-                    o[0] = d.value_midx; o[1] = d.value_sidx; o[2] = d.gapm_idx; o[3] = d.gaps_idx;
-                    memcpy(o + 4, &d.value, 4); memcpy(o + 5, &d.gapm_val, 4); memcpy(o + 6, &d.gaps_val, 4);
-                }
-            }
-        }
-        c.clearSequence();
-        int oh_head = 0, oh_tail = 0;
-        try {
-            float score = backtrack(A, c, tr, (OVERHANG_TYPE)P.overhang, (LOWERCASE_TYPE)P.lowercase,
-                                    (INSERTION_TYPE)P.insertion, oh_head, oh_tail, log);
-            R.score = score;
-            R.head = oh_head; R.tail = oh_tail;
-            R.qual = (int)std::min(100.f, std::max(0.f, 100.f * score));  // align.cpp:509
-            R.status = 0;
-        } catch (std::runtime_error& e) {
-            R.status = 3;
-            if (logstr) *logstr = log.str() + e.what();
-            return;
-        }
+        const bool ok = P.insertion == INSERTION_FORBID
+            ? run_dp<transition_aspace_aware<scoring_scheme_simple, mseq, cseq>>(m, c, s, P, R, log, logstr, cells, cells_cap_words)
+            : run_dp<mesh_tr>(m, c, s, P, R, log, logstr, cells, cells_cap_words);
+        if (!ok) return;
     }
     aligned = c.getAligned(true, false);  // rw_fasta.cpp:520
     if (out_cols) {

@@ -461,9 +461,22 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
     M->gapm_idx = (uint32_t*)malloc((n + 1) * 4);   M->gaps_idx = (uint32_t*)malloc((n + 1) * 4);
     M->value = (float*)malloc((n + 1) * 4); M->gapm_val = (float*)malloc((n + 1) * 4);
     M->gaps_val = (float*)malloc((n + 1) * 4);
+    /* --insertion forbid: transition_aspace_aware (src/mesh.h:377-438, chosen in src/align.cpp:466-468): a cell also
+     * carries gaps_max, the number of insertions still accommodated by the free columns between the node and its
+     * nearest successor (max_insert, compute_node_simple::calc src/mesh.h:480-484) */
+    const int forbid = p->insertion == 1;
+    uint32_t* gaps_max = forbid ? (uint32_t*)calloc(n + 1, 4) : NULL;
+    uint32_t* min_mpos = forbid ? (uint32_t*)malloc(((size_t)g->V + 1) * 4) : NULL;
+    if (forbid) {
+        for (uint32_t m = 0; m < g->V; m++) min_mpos[m] = 1000000u;
+        for (uint32_t m = 0; m < g->V; m++)
+            for (uint32_t e = g->pred_off[m]; e < g->pred_off[m + 1]; e++)
+                if (g->col[m] < min_mpos[g->preds[e]]) min_mpos[g->preds[e]] = g->col[m];
+    }
     for (uint32_t m = 0; m < g->V; m++) {
         uint32_t pb = g->pred_off[m], pe = g->pred_off[m + 1];
         float w = g->weight[m];
+        const uint32_t smax = forbid ? (uint32_t)(int)(min_mpos[m] - g->col[m] - 1) : 0;
         for (uint32_t s = 0; s < L; s++) {
             uint64_t o = (uint64_t)m * L + s;
             float value, gapm_val, gaps_val;
@@ -482,9 +495,20 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
             }
             if (s > 0) { /* insertion :486-490 -> :332-358 */
                 uint64_t so = o - 1;
-                if (M->gaps_val[so] != M->value[so]) { gaps_val = M->value[so] + gp; gaps_idx = s - 1; }
-                else { gaps_val = M->gaps_val[so] + gpe; gaps_idx = M->gaps_idx[so]; }
-                if (gaps_val <= value) { value = gaps_val; value_sidx = gaps_idx; value_midx = m; }
+                int evaluated = 1;
+                if (!forbid) {
+                    if (M->gaps_val[so] != M->value[so]) { gaps_val = M->value[so] + gp; gaps_idx = s - 1; }
+                    else { gaps_val = M->gaps_val[so] + gpe; gaps_idx = M->gaps_idx[so]; }
+                } else if (smax < 1) {
+                    evaluated = 0;                                        /* can't insert :412-414 */
+                } else if (M->gaps_val[so] != M->value[so]) {              /* opening gap :416-420 */
+                    gaps_val = M->value[so] + gp; gaps_idx = s - 1; gaps_max[o] = smax - 1;
+                } else if (gaps_max[so] > 0) {                             /* extending gap :421-426 */
+                    gaps_val = M->gaps_val[so] + gpe; gaps_idx = M->gaps_idx[so]; gaps_max[o] = gaps_max[so] - 1;
+                } else {
+                    evaluated = 0;                                        /* :427-429 */
+                }
+                if (evaluated && gaps_val <= value) { value = gaps_val; value_sidx = gaps_idx; value_midx = m; }
                 for (uint32_t e = pb; e < pe; e++) { /* match :492-500 -> :360-374 */
                     uint32_t mi = g->preds[e];
                     uint64_t po = (uint64_t)mi * L + (s - 1);
@@ -498,6 +522,7 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
             M->gapm_idx[o] = gapm_idx; M->gaps_idx[o] = gaps_idx;
         }
     }
+    free(gaps_max); free(min_mpos);
     return M;
 }
 

@@ -82,7 +82,7 @@ typedef struct so_align_params {
     float match_score, mismatch_score, gap_penalty, gap_ext_penalty, fs_weight;
     int overhang;  /* 0 attach 1 remove 2 edge */
     int lowercase; /* 0 none 1 original 2 unaligned */
-    int insertion; /* 0 shift (1 forbid: not restated) 2 remove(=shift) */
+    int insertion; /* 0 shift, 1 forbid (transition_aspace_aware), 2 remove (= shift, src/cseq.cpp:462-464) */
     int realign;
 } so_align_params;
 

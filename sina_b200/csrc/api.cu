@@ -28,7 +28,7 @@ static uint64_t env_mb(const char* name, uint64_t dflt_mb) {
 static void free_workspace(Workspace* w) {
     void* ptrs[] = {w->d_cursors, w->d_remaining, w->d_tab, w->d_tabli, w->d_colof, w->d_colbase, w->d_item_node, w->d_slot,
                     w->d_ncol, w->d_nmask, w->d_ncount, w->d_nweight, w->d_nsigma, w->d_slotbase, w->d_cursor,
-                    w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_rcol, w->d_nthr, w->d_nshift, w->d_ghosts,
+                    w->d_pred_off, w->d_preds, w->d_pdesc, w->d_pdesc2, w->d_order, w->d_rcol, w->d_nthr, w->d_nshift, w->d_nmaxins, w->d_ghosts,
                     w->d_writers, w->d_spillrow, w->d_nflags, w->d_lastnodes, w->d_groups, w->d_lastcol, w->d_rowmin,
                     w->d_rowarg, w->d_rec, w->d_tb, w->d_spill};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -67,7 +67,7 @@ static int alloc_workspace(Session* s, Workspace* w) {
     SG_TRY(dmalloc(&w->d_lastnodes, C * I)); SG_TRY(dmalloc(&w->d_groups, C * s->gcap));
     SG_TRY(dmalloc(&w->d_lastcol, C * I)); SG_TRY(dmalloc(&w->d_rowmin, C * I)); SG_TRY(dmalloc(&w->d_rowarg, C * I));
     SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_rcol, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
-    SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
+    SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_nmaxins, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
     SG_TRY(dmalloc(&w->d_writers, C * s->gcap * DP_G));
     { uint8_t* p = nullptr; SG_TRY(dmalloc(&p, C * I * 32)); w->d_rec = p; }
     SG_TRY(dmalloc(&w->d_tb, s->tb_words)); SG_TRY(dmalloc(&w->d_spill, s->spill_elems));
@@ -119,7 +119,6 @@ static int stage_end(Session* s, float* acc) {
 
 static int validate_align_params(const sg_align_params* ap) {
     if (!ap) SG_FAIL(SG_ERR_ARG, "align params missing");
-    if (ap->insertion == 1) SG_FAIL(SG_ERR_ARG, "--insertion forbid is not supported (reference transition_aspace_aware)");
     if (ap->insertion < 0 || ap->insertion > 2 || ap->overhang < 0 || ap->overhang > 2 || ap->lowercase < 0 || ap->lowercase > 2)
         SG_FAIL(SG_ERR_ARG, "align params: enum out of range");
     return SG_OK;

@@ -146,6 +146,7 @@ struct Workspace {
     uint8_t* d_rcol = nullptr;       // [n][gcap*DP_T] ring column (group, thread) publishes to: a permutation inside every 16-thread block
     uint16_t* d_nthr = nullptr;      // [n][icap] thread (ring column) of a node inside its group
     uint8_t* d_nshift = nullptr;     // [n][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
+    uint32_t* d_nmaxins = nullptr;   // [n][icap] --insertion forbid: free columns between a node and its nearest successor
     GhostInfo* d_ghosts = nullptr;   // [n][gcap][DP_G]
     uint32_t* d_writers = nullptr;   // [n][gcap][DP_G] node whose row a loader lane spills / min-tracks
     int32_t* d_spillrow = nullptr;   // [n][icap] spill row of node or -1

@@ -98,6 +98,7 @@ struct GraphArgs {
     uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
     uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
     uint32_t* lastnodes; GroupInfo* groups;
+    uint32_t* nmaxins; int forbid;   // --insertion forbid
     uint32_t* order; uint8_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
     unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
@@ -343,6 +344,19 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     for (uint32_t m = tid; m < V; m += nt) {
         const uint32_t deg = pred_off[m + 1] - pred_off[m];
         for (uint32_t x = 0; x < deg; x++) preds[pred_off[m] + x] = slot[slotbase[m] + x];
+    }
+    if (A.forbid) {
+        // --insertion forbid: max_insert of a node = columns free before its nearest successor
+        // (compute_node_simple::calc, src/mesh.h:480-484: min over next nodes of their position, 1000000 without one)
+        uint32_t* nmaxins = A.nmaxins + io;
+        for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = 1000000u;
+        __syncthreads();
+        for (uint32_t m = tid; m < V; m += nt) {
+            const uint32_t deg = pred_off[m + 1] - pred_off[m], cm = ncol[m];
+            for (uint32_t x = 0; x < deg; x++) atomicMin(&nmaxins[slot[slotbase[m] + x]], cm);
+        }
+        __syncthreads();
+        for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = nmaxins[m] - ncol[m] - 1u;
     }
     // block max of in-degree
     for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
@@ -684,7 +698,8 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cursor = w->d_cursor; A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.pdesc = w->d_pdesc;
     A.spillrow = w->d_spillrow; A.nflags = w->d_nflags; A.lastnodes = w->d_lastnodes; A.groups = w->d_groups;
     A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
-    A.force_generic = s->force_generic;
+    A.force_generic = s->force_generic || ap.insertion == 1;   // the aspace-aware transition lives in the generic kernel
+    A.nmaxins = w->d_nmaxins; A.forbid = ap.insertion == 1;
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;

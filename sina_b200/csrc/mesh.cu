@@ -31,6 +31,7 @@ struct MeshArgs {
     const uint32_t* pred_off; const uint32_t* pdesc; const int32_t* spillrow; const uint8_t* nflags;
     const uint32_t* pdesc2; const uint32_t* order; const uint8_t* rcol; const uint16_t* nthr; uint8_t* nshift;
     const GhostInfo* ghosts; const uint32_t* writers;
+    const uint32_t* nmaxins; int forbid;   // --insertion forbid (generic kernel only): free columns after each node
     uint32_t* tb; float2* spill;
     float* lastcol; float* rowmin; uint32_t* rowarg;
     float ms, mms, gp, gpe;  // -match_score, -mismatch_score, gap_penalty, gap_ext_penalty (align.cpp:406-407)
@@ -569,7 +570,9 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
 #pragma unroll
             for (int i = 0; i < NPR; i++) if ((uint32_t)i < np) pd[i] = pdesc[pbase + i];
         }
-        float E_next = 1.0f;  // gaps_val of the row's next cell
+        float E_prev = 1.0f, H_prev = 1.0f;  // gaps_val / value of (m, s-1)
+        uint32_t gmax_prev = 0;              // --insertion forbid: insertions the run at (m, s-1) may still take
+        const uint32_t maxins = (valid && A.forbid) ? A.nmaxins[io + m] : 0u;
         float rmin = 0.f;
         uint32_t rarg = 0;
         const uint32_t steps = (Lq + gi.depth - 1 + 3) & ~3u;
@@ -607,10 +610,22 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                     const uint32_t d = __ldg(&pdesc[pbase + i]);
                     del_step(i, load_cell(d, s, t));
                 }
-                float E = 1.0f;
+                float E = edge ? 1.0f : 1000000.0f;                      // gaps_val as initialised (mesh.h:294-301)
+                uint32_t gmax = 0;
                 if (s > 0) {
-                    E = E_next;                                          // mesh.h:332-358
-                    if (E <= value) { value = E; code = TB_SRC_INS; }
+                    bool evaluated = true;
+                    if (!A.forbid) {                                     // transition_simple::insertion, mesh.h:332-358
+                        E = (E_prev != H_prev) ? __fadd_rn(H_prev, gp) : __fadd_rn(E_prev, gpe);
+                    } else if (maxins < 1) {                             // transition_aspace_aware, mesh.h:403-438
+                        evaluated = false;
+                    } else if (E_prev != H_prev) {
+                        E = __fadd_rn(H_prev, gp); gmax = maxins - 1;
+                    } else if (gmax_prev > 0) {
+                        E = __fadd_rn(E_prev, gpe); gmax = gmax_prev - 1;
+                    } else {
+                        evaluated = false;
+                    }
+                    if (evaluated && E <= value) { value = E; code = TB_SRC_INS; }
                     const float sc = (mask & qm[s] & 15u) ? msw : mmsw;  // mesh.h:360-374
 #pragma unroll
                     for (int i = 0; i < NPR; i++) {
@@ -627,7 +642,7 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                 }
                 const float vgp = __fadd_rn(value, gp), ggpe = __fadd_rn(gapm, gpe);
                 if (vgp < ggpe) code |= WIDE ? 4u : 32u;                 // ob: a deletion leaving this cell opens
-                E_next = (E == value) ? __fadd_rn(E, gpe) : vgp;         // extension iff gaps_val == value
+                E_prev = E; H_prev = value; gmax_prev = gmax;
 #pragma unroll
                 for (int i = 0; i < NPR; i++) pv_prev[i] = pv_cur[i];
                 const float2 out = make_float2(value, fminf(vgp, ggpe));
@@ -673,6 +688,7 @@ int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0
     A.pdesc = w->d_pdesc; A.spillrow = w->d_spillrow; A.nflags = w->d_nflags;
     A.pdesc2 = w->d_pdesc2; A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.nshift = w->d_nshift;
     A.ghosts = w->d_ghosts; A.writers = w->d_writers;
+    A.nmaxins = w->d_nmaxins; A.forbid = ap.insertion == 1;
     A.tb = w->d_tb; A.spill = w->d_spill; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.ms = -ap.match_score; A.mms = -ap.mismatch_score; A.gp = ap.gap_penalty; A.gpe = ap.gap_ext_penalty;
     uint32_t max_qlen = 0;

@@ -32,7 +32,7 @@ void aligner::get_options_description(po::options_description& /*main*/, po::opt
               [](const std::string& v) {
                   if (v == "shift") opts->insertion = INSERTION_SHIFT;
                   else if (v == "remove") opts->insertion = INSERTION_REMOVE;  // "using shift" in the reference too (src/cseq.cpp:462-464)
-                  else if (v == "forbid") throw std::logic_error("--insertion forbid is not supported by sina_b200");
+                  else if (v == "forbid") opts->insertion = INSERTION_FORBID;  // transition_aspace_aware (src/align.cpp:466-468)
                   else throw std::logic_error("insertion type must be one of 'shift', 'forbid' or 'remove'");
               });
     od.unsupported("fs-no-graph", false, "profile-vector alignment (pseq) is a test-only path of the reference");

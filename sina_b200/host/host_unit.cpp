@@ -127,7 +127,7 @@ static void test_options() {
         return false;
     };
     CHECK(rejects({"--fs-engine", "pt-server"})); CHECK(rejects({"--fs-no-graph"})); CHECK(rejects({"--use-subst-matrix"}));
-    CHECK(rejects({"--filter", "x"})); CHECK(rejects({"--insertion", "forbid"})); CHECK(rejects({"--overhang", "bogus"}));
+    CHECK(rejects({"--filter", "x"})); CHECK(rejects({"--insertion", "bogus"})); CHECK(!rejects({"--insertion", "forbid"})); CHECK(!rejects({"--insertion", "shift"})); CHECK(rejects({"--overhang", "bogus"}));
     CHECK(rejects({"--no-such-option"})); CHECK(rejects({"--fs-min"})); CHECK(rejects({"--fs-min", "abc"}));
     CHECK(rejects({"--turn", "sideways"})); CHECK(rejects({"stray"}));
     CHECK(!rejects({"--turn", "all"})); CHECK(famfinder::opts.turn_which == TURN_ALL);

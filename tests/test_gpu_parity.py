@@ -324,3 +324,52 @@ def test_turn_check_vs_oracle(orc):
                 assert bits(res[i]["score"]) == bits(ores[i].score), (mode, i)
     orc.index_free(oix)
     ix.close()
+
+
+def test_insertion_forbid_vs_oracle(orc):
+    """--insertion forbid (transition_aspace_aware, src/mesh.h:377-438; generic DP kernel): dense alignments where the
+    budget of free columns changes the result, all overhang / lowercase / scoring variants, one batch per setting"""
+    rng = np.random.default_rng(99)
+    differ = 0
+    for it in range(24):
+        rows, _ = synth.random_case(rng, F=int(rng.integers(2, 10)), wfac=[1.0, 1.2, 1.5, 2.5][it % 4], indel=[0.05, 0.1, 0.2][it % 3])
+        msa = O.MSA.from_rows(rows)
+        qs = []
+        for j in range(6):
+            _, q = synth.random_case(rng, F=2, L=int(msa.off[1] - msa.off[0]) if j % 2 else None)
+            qs.append(O.encode(q))
+        # queries related to the MSA: mutated copies of its rows
+        for j in range(6):
+            m, _ = msa.row(int(rng.integers(0, msa.N)))
+            q = m.copy()
+            flip = rng.random(len(q)) < 0.08
+            q[flip] = (1 << rng.integers(0, 4, int(flip.sum()))).astype(np.uint8)
+            keep = rng.random(len(q)) >= 0.05
+            extra = rng.random(len(q)) < 0.08
+            out = []
+            for b, k, e in zip(q, keep, extra):
+                if k:
+                    out.append(b)
+                if e:
+                    out.append(np.uint8(1 << int(rng.integers(0, 4))))
+            if len(out) >= 4:
+                qs.append(np.array(out, np.uint8))
+        qmask, qoff = pack_queries(qs)
+        fam = np.tile(np.arange(msa.N, dtype=np.uint32), len(qs))
+        foff = (np.arange(len(qs) + 1) * msa.N).astype(np.uint64)
+        ap_kw = dict(insertion=1, overhang=it % 3, lowercase=[0, 2, 1][(it // 3) % 3], fs_weight=[1.0, 0.0, 2.5][(it // 9) % 3],
+                     realign=1)
+        if it % 5 == 4:
+            ap_kw.update(match_score=1.7, mismatch_score=-0.9, gap_penalty=4.3, gap_ext_penalty=1.1)
+        ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=4)
+        oc, om, res = ix.align(qmask, qoff, fam, foff, sina_b200.AlignParams(**ap_kw))
+        ix.close()
+        for i, q in enumerate(qs):
+            r1, c1, m1, _ = orc.align(msa, np.arange(msa.N, dtype=np.uint32), q, O.AlignParams(**ap_kw))
+            a = int(qoff[i])
+            compare_result(res[i], oc[a:], om[a:], r1, c1, m1, msa.W, (it, i))
+            if r1.status == 0:
+                kw0 = dict(ap_kw, insertion=0)
+                r0, c0, m0, _ = orc.align(msa, np.arange(msa.N, dtype=np.uint32), q, O.AlignParams(**kw0))
+                differ += int(len(c0) != len(c1) or (c0 != c1).any())
+    assert differ >= 10, differ

@@ -74,6 +74,7 @@ def oracle_strings(orc, msa, qmasks, ap_kw, fp_kw=FAM, k=6):
     (["--lowercase", "original", "--pen-gap", "4.3", "--pen-gapext", "1.1", "--match-score", "1.7", "--mismatch-score", "-0.9",
       "--fs-weight", "0.5", "--line-length", "100"],
      dict(lowercase=1, gap_penalty=4.3, gap_ext_penalty=1.1, match_score=1.7, mismatch_score=-0.9, fs_weight=0.5)),
+    (["--insertion", "forbid", "--overhang", "remove"], dict(insertion=1, overhang=1)),
 ])
 def test_cli_matches_oracle(orc, data, cli, ap_kw):
     d, msa, qmasks = data

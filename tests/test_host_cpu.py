@@ -51,7 +51,8 @@ def test_cli_help_and_version():
     (["--db", "x", "--fs-no-graph"], "not supported"),
     (["--db", "x", "--use-subst-matrix"], "not supported"),
     (["--db", "x", "--filter", "f"], "not supported"),
-    (["--db", "x", "--insertion", "forbid"], "forbid is not supported"),
+    (["--db", "x", "--insertion", "sideways"], "insertion type must be one of"),
+    (["--db", "x", "--turn", "sideways"], "Turn type must be one of"),
     (["--db", "x", "--search"], "not supported"),
     (["--db", "x", "--fs-msc-max", "0.9"], "identity filter"),
     (["--db", "x", "--bogus"], "unrecognised option"),

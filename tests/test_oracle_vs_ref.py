@@ -196,3 +196,39 @@ def test_turn_check_oracle_vs_ref(orc, ref):
     orc.index_free(oix)
     ref.kidx_free(rix)
     ref.db_free(db)
+
+
+def test_insertion_forbid_random(orc, ref):
+    """--insertion forbid: transition_aspace_aware (src/mesh.h:377-438) through the reference's own compute / backtrack
+    against the C restatement: all seven mesh cell fields, strings, columns, score bits. The cases are dense
+    alignments (few free columns), so the gaps_max budget changes many results with respect to --insertion shift."""
+    rng = np.random.default_rng(4242)
+    ncells, differ = 0, 0
+    for it in range(90):
+        rows, q = synth.random_case(rng, wfac=[1.0, 1.15, 1.4, 2.0][it % 4], indel=[0.05, 0.1, 0.2][it % 3])
+        msa = O.MSA.from_rows(rows)
+        db = ref.db(msa)
+        fam = np.arange(msa.N, dtype=np.uint32)
+        ap = params_for(it)
+        ap.insertion = 1
+        qm = O.encode(q)
+        rr, s2, c2, log, cells = ref.align(db, fam, q, msa.W, ap, want_cells=True)
+        r1, c1, m1, famp = orc.align(msa, fam, qm, ap)
+        assert rr.status == r1.status, it
+        if rr.status == 0:
+            mesh = orc.mesh(msa, famp[:r1.fam_used], (qm & 15) if ap.lowercase != 1 else qm, ap)
+            for k in mesh:
+                a, b = mesh[k], cells[k]
+                if a.dtype == np.float32:
+                    a, b = bits(a), bits(b)
+                assert (a == b).all(), (it, k)
+            ncells += mesh["value"].size
+            assert O.render(m1, c1, msa.W) == s2, it
+            assert (c1 == c2).all()
+            assert (r1.head, r1.tail, r1.qual) == (rr.head, rr.tail, rr.qual)
+            assert bits(r1.score) == bits(rr.score)
+            ap.insertion = 0
+            r0, c0, m0, _ = orc.align(msa, fam, qm, ap)
+            differ += int(r0.status != 0 or len(c0) != len(c1) or (c0 != c1).any())
+        ref.db_free(db)
+    assert ncells > 300000 and differ >= 10, (ncells, differ)
