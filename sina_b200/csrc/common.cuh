@@ -114,7 +114,7 @@ struct GhostInfo {   // a ring column fed from a spilled row: far predecessors b
 // session owns several and deals the batch's chunks to them round-robin; each workspace has its own stream,
 // so the graph kernel of one chunk, the DP of another and the (latency-bound) backtrack of a third overlap.
 // Per-query arrays use a uniform stride (icap items / ncap columns).
-constexpr int MAX_WS = 4;
+constexpr int MAX_WS = 8;
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {};          // stage boundaries: graph | dp | backtrack | end
