@@ -194,12 +194,17 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         a = __ldcg(p);
         b = __ldcg(p + 1);
     };
-    // decoded traceback cell: src | slot<<8 | ob<<2 (the wide layout; ob = a deletion leaving the cell opens, common.cuh)
-    auto cell = [&](const uint4& a, uint32_t s) -> uint32_t {
+    // traceback cell: the load (cell_raw) and its decoding (cell_dec) are separate so that a speculative load can stay
+    // in flight; decoded = src | slot<<8 | ob<<2 (the wide layout; ob = a deletion leaving the cell opens, common.cuh)
+    auto cell_raw = [&](const uint4& a, uint32_t s) -> uint32_t {
         const uint32_t t = s + (a.y & 0xffffu);
         const uint32_t idx = a.x + (t >> 1) * T;
-        if (wide) return (__ldcg(&tbq[idx]) >> (16 * (t & 1))) & 0xffffu;
-        const uint32_t c = ((uint32_t)__ldcg(&tbq16[idx]) >> (8 * (t & 1))) & 0xffu;
+        return wide ? __ldcg(&tbq[idx]) : (uint32_t)__ldcg(&tbq16[idx]);
+    };
+    auto cell_dec = [&](const uint4& a, uint32_t s, uint32_t raw) -> uint32_t {
+        const uint32_t t = s + (a.y & 0xffffu);
+        if (wide) return (raw >> (16 * (t & 1))) & 0xffffu;
+        const uint32_t c = (raw >> (8 * (t & 1))) & 0xffu;
         const uint32_t sh = (a.y >> 16) & 0xffu;
         if (sh & TBR_FLAG) {
             // raw cell (common.cuh): the last winner in evaluation order is the source
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         }
         return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
     };
+    auto cell = [&](const uint4& a, uint32_t s) -> uint32_t { return cell_dec(a, s, cell_raw(a, s)); };
     auto np_of = [](const uint4& a) -> uint32_t { return a.y >> 24; };
     auto pred_of = [&](const uint4& a, const uint4& b, uint32_t ord) -> uint32_t {
         if (ord == 0) return b.x;
@@ -301,6 +307,18 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         if (np > 1) ldrec(rb.y, qa1, qb1);
         if (np > 2) ldrec(rb.z, qa2, qb2);
         if (np > 3) ldrec(rb.w, qa3, qb3);
+        // speculation: the most common step is a match through one of the inline predecessors; its cell (p_k, s-1) is
+        // requested by lane k as soon as p_k's record is there, i.e. while this node's own cell is still on its way
+        uint32_t spec_raw = 0;
+        if (lane < min(np, 4u)) {
+            const uint4 pa = lane == 0 ? qa0 : (lane == 1 ? qa1 : (lane == 2 ? qa2 : qa3));
+            spec_raw = cell_raw(pa, s - 1);
+        }
+        uint32_t spec_k = 4;   // inline predecessor the match goes through, if it does
+        if ((c & 3u) == TB_SRC_MATCH) {
+            const uint32_t sl = c >> 8, sh = (ra.y >> 16) & (wide ? 0xffu : 0x7fu);
+            spec_k = sl > sh ? sl - sh : 0u;
+        }
         uint32_t nm, snew;
         follow(ra, rb, m, s, c, nm, snew);
         uint4 na, nb;
@@ -313,7 +331,8 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         m = nm; ra = na; rb = nb;
         uint32_t c2 = 0;
         if (snew != 0) {  // landing on a cell reached by deletion (its value_sidx == snew): skip it (mesh.h:653-655)
-            c2 = cell(ra, snew);
+            if (spec_k < 4) c2 = cell_dec(ra, snew, __shfl_sync(FULL, spec_raw, spec_k));   // (p_k, s-1), already loaded
+            else c2 = cell(ra, snew);
             if ((c2 & 3u) == TB_SRC_DEL) {
                 uint32_t m2, s2;
                 follow(ra, rb, m, snew, c2, m2, s2);

@@ -112,14 +112,13 @@ void aligner::run(std::vector<tray*>& trays, bool rethrow) {
             t.log << "ERROR: no space to left and right?? sequence longer than alignment?!;";
             continue;
         }
-        cseq* c = new cseq(*t.input_sequence);  // working copy: name and attributes
-        c->clearSequence();
+        cseq* c = new cseq(cseq::withoutBases(*t.input_sequence));  // working copy: name and attributes
         std::vector<aligned_base> v;
         v.reserve(r.n_out);
         for (uint32_t i = 0; i < r.n_out; i++) v.emplace_back(out_cols[off[q] + i], out_masks[off[q] + i]);
-        c->setAlignedBases(v);
         uint32_t W = db.getAlignmentWidth();
         if (!v.empty() && v.back().getPosition() + 1 > W) W = v.back().getPosition() + 1;  // the reference's right-edge quirk
+        c->setAlignedBases(std::move(v));
         c->setWidth(W);
         if (r.status == SG_Q_COPIED) {  // src/align.cpp:349-388
             t.log << "copied alignment from template sequence; ";

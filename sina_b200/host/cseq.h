@@ -53,6 +53,10 @@ public:
     cseq& append(const aligned_base& ab);
     void clearSequence() { bases.clear(); alignment_width = 0; }
     void setAlignedBases(const std::vector<aligned_base>& v) { bases = v; }
+    void setAlignedBases(std::vector<aligned_base>&& v) { bases = std::move(v); }
+    // name and attributes of `o` without its bases (the aligner's working copy, src/align.cpp:320-323, starts from
+    // the input sequence and replaces the bases)
+    static cseq withoutBases(const cseq& o) { cseq c; c.name = o.name; c.attributes = o.attributes; return c; }
     const std::vector<aligned_base>& getAlignedBases() const { return bases; }
     std::vector<aligned_base>& getAlignedBasesMutable() { return bases; }
     uint32_t size() const { return (uint32_t)bases.size(); }
@@ -72,6 +76,8 @@ public:
         o << val;
         attributes[key] = o.str();
     }
+    void set_attr(const std::string& key, const std::string& val) { attributes[key] = val; }
+    void set_attr(const std::string& key, int val) { attributes[key] = std::to_string(val); }
     template <typename T>
     T get_attr(const std::string& key, const T& dflt = T()) const {
         auto it = attributes.find(key);

@@ -158,13 +158,26 @@ void famfinder::impl::run(std::vector<tray*>& trays) {
         t.alignment_reference = new search::result_vector();
         t.alignment_reference->reserve(fam_n[q]);
         std::string famstr;
+        famstr.reserve((size_t)fam_n[q] * 24);
         char buf[64];
         for (int32_t i = 0; i < fam_n[q]; i++) {
-            const cseq& r = db.getCseq(ids[(size_t)q * stride + i]);
-            t.alignment_reference->emplace_back(scores[(size_t)q * stride + i], &r);
-            // "{acc}.{start}:{score:.2f} " (src/famfinder.cpp:458-470); FASTA references have no acc/start fields
-            snprintf(buf, sizeof(buf), ":%.2f ", scores[(size_t)q * stride + i]);
-            famstr += r.get_attr_string(fn_acc, r.getName()) + "." + r.get_attr_string(fn_start, "0") + buf;
+            const uint32_t id = ids[(size_t)q * stride + i];
+            const float sc = scores[(size_t)q * stride + i];
+            t.alignment_reference->emplace_back(sc, &db.getCseq(id));
+            // "{acc}.{start}:{score:.2f} " (src/famfinder.cpp:458-470); FASTA references have no acc/start fields.
+            // The internal engine's scores are k-mer counts: integral, so ".00" needs no float formatting.
+            famstr += db.familyLabel(id);
+            if (sc >= 0.f && sc < 1e9f && sc == (float)(uint32_t)sc) {
+                char* p = buf + sizeof(buf);
+                *--p = 0; *--p = ' '; *--p = '0'; *--p = '0'; *--p = '.';
+                uint32_t v = (uint32_t)sc;
+                do { *--p = (char)('0' + v % 10); v /= 10; } while (v);
+                *--p = ':';
+                famstr += p;
+            } else {
+                snprintf(buf, sizeof(buf), ":%.2f ", sc);
+                famstr += buf;
+            }
         }
         t.input_sequence->set_attr<std::string>(fn_family, famstr);
     }

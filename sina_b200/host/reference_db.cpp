@@ -30,6 +30,9 @@ void reference_db::pack() {
     }
     // mseq requires all rows to have the alignment's width (src/mseq.cpp:56-65)
     for (auto& s : seqs) s.setWidth(width);
+    labels.clear();
+    labels.reserve(seqs.size());
+    for (const auto& r : seqs) labels.push_back(r.get_attr_string(fn_acc, r.getName()) + "." + r.get_attr_string(fn_start, "0"));
 }
 
 reference_db* reference_db::fromSequences(const std::string& key, std::vector<cseq>&& v) {

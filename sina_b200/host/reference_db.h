@@ -29,6 +29,8 @@ public:
     int64_t indexOf(const std::string& name) const;         // -1 if unknown
     uint32_t indexOf(const cseq* s) const { return (uint32_t)(s - seqs.data()); }
     const std::string& getFileName() const { return filename; }
+    // "{acc}.{start}" of a reference as the family attribute prints it (src/famfinder.cpp:458-470), built once
+    const std::string& familyLabel(uint32_t index) const { return labels[index]; }
 
     // packed form handed to sg_index_create
     const std::vector<uint8_t>& masks() const { return packed_masks; }
@@ -41,6 +43,7 @@ private:
     std::string filename;
     uint32_t width = 0;
     std::vector<cseq> seqs;
+    std::vector<std::string> labels;
     std::unordered_map<std::string, uint32_t> by_name;
     std::vector<uint8_t> packed_masks;
     std::vector<uint32_t> packed_cols;

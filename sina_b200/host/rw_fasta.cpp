@@ -1,5 +1,10 @@
 #include "rw_fasta.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+#include <cerrno>
+#include <cstring>
+
 #include <fstream>
 #include <iostream>
 
@@ -94,52 +99,95 @@ bool rw_fasta::reader::operator()(tray& t) {
 
 // ------------------------------------------------------------------------------------------------ writer
 struct rw_fasta::writer::priv_data {
-    std::ofstream file;
-    std::ostream* out = nullptr;
+    int fd = -1;                 // regular file: positional writes
+    uint64_t offset = 0;         // next free byte of the file
+    std::ostream* out = nullptr; // stdout
     unsigned int count = 0, excluded = 0;
     void write(const cseq& c);
+    void put(const char* p, size_t n);
+    ~priv_data() { if (fd >= 0) ::close(fd); }
 };
+
+static void pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
+    while (n > 0) {
+        const ssize_t w = ::pwrite(fd, p, n, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw std::runtime_error(std::string("write failed: ") + strerror(errno));
+        }
+        p += w; n -= (size_t)w; off += (uint64_t)w;
+    }
+}
+
+void rw_fasta::writer::priv_data::put(const char* p, size_t n) {
+    if (fd >= 0) { pwrite_all(fd, p, n, offset); offset += n; }
+    else out->write(p, (std::streamsize)n);
+}
 
 rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
     if (!opts) opts = new options();
     if (outfile == "-") data->out = &std::cout;
     else {
-        data->file.open(outfile);
-        if (!data->file) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
-        data->out = &data->file;
+        data->fd = ::open(outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (data->fd < 0) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
     }
 }
+bool rw_fasta::writer::positional() const { return data->fd >= 0; }
+uint64_t rw_fasta::writer::reserve(uint64_t nbytes, unsigned int n_records, unsigned int n_excluded) {
+    const uint64_t at = data->offset;
+    data->offset += nbytes;
+    data->count += n_records;
+    data->excluded += n_excluded;
+    return at;
+}
+void rw_fasta::writer::write_at(uint64_t offset, const char* p, size_t n) const { pwrite_all(data->fd, p, n, offset); }
 rw_fasta::writer::~writer() = default;
 unsigned int rw_fasta::writer::written() const { return data->count; }
 unsigned int rw_fasta::writer::excluded() const { return data->excluded; }
 
-void rw_fasta::writer::priv_data::write(const cseq& c) {  // src/rw_fasta.cpp:438-528
-    std::ostream& o = *out;
-    o << ">" << c.getName();
+std::string rw_fasta::writer::format(const cseq& c) {  // src/rw_fasta.cpp:438-528
+    if (!opts) opts = new options();
+    std::string o;
+    const std::string seq = c.getAligned(!opts->out_dots, opts->out_dna);
+    o.reserve(seq.size() + seq.size() / (opts->line_length ? opts->line_length : seq.size() + 1) + 256);
+    o += ">";
+    o += c.getName();
     const std::string fname = c.get_attr_string(fn_fullname);
-    if (!fname.empty()) o << " " << fname;
+    if (!fname.empty()) { o += " "; o += fname; }
     if (opts->fastameta == FASTA_META_HEADER) {
         for (const auto& ap : c.get_attrs()) {
             if (ap.first == fn_family || ap.first == fn_fullname || ap.second.empty()) continue;
-            o << " [" << ap.first << "=" << ap.second << "]";
+            o += " ["; o += ap.first; o += "="; o += ap.second; o += "]";
         }
-        o << "\n";
+        o += "\n";
     } else if (opts->fastameta == FASTA_META_COMMENT) {
-        o << "\n";
+        o += "\n";
         for (const auto& ap : c.get_attrs()) {
             if (ap.first == fn_family || ap.first == fn_fullname) continue;
-            o << "; " << ap.first << "=" << ap.second << "\n";
+            o += "; "; o += ap.first; o += "="; o += ap.second; o += "\n";
         }
     } else {
-        o << "\n";
+        o += "\n";
     }
-    const std::string seq = c.getAligned(!opts->out_dots, opts->out_dna);
     if (opts->line_length > 0) {
-        for (size_t i = 0; i < seq.size(); i += opts->line_length) o << seq.substr(i, opts->line_length) << "\n";
+        for (size_t i = 0; i < seq.size(); i += opts->line_length) { o.append(seq, i, opts->line_length); o += "\n"; }
     } else {
-        o << seq << "\n";
+        o += seq;
+        o += "\n";
     }
+    return o;
+}
+
+void rw_fasta::writer::priv_data::write(const cseq& c) {
+    const std::string rec = format(c);
+    put(rec.data(), rec.size());
     count++;
+}
+
+void rw_fasta::writer::write_formatted(const std::string* record) {
+    if (record == nullptr) { ++data->excluded; return; }  // src/rw_fasta.cpp:399-404
+    data->put(record->data(), record->size());
+    data->count++;
 }
 
 tray rw_fasta::writer::operator()(tray t) {

@@ -39,6 +39,15 @@ public:
         explicit writer(const std::string& outfile);  // "-" = stdout
         ~writer();
         tray operator()(tray t);
+        // the record operator() would write for this sequence (header + sequence lines), so that the rendering of the
+        // alignment_width-long lines can run on several threads; write_formatted() then emits it (null: sequence excluded)
+        static std::string format(const cseq& c);
+        void write_formatted(const std::string* record);
+        // positional output (regular files): the caller reserves byte ranges in record order and any thread fills them
+        // with pwrite, so that writing 50 kB records is not bound to one thread. Not available on stdout.
+        bool positional() const;
+        uint64_t reserve(uint64_t nbytes, unsigned int n_records, unsigned int n_excluded);
+        void write_at(uint64_t offset, const char* p, size_t n) const;
         unsigned int written() const;
         unsigned int excluded() const;
     private:

@@ -2,11 +2,14 @@
 // (src/sina.cpp:224-264,379-440) and its pipeline reader -> famfinder -> aligner -> writer (src/sina.cpp:443-593),
 // with the TBB flow graph replaced by batches: a reader thread cuts the input into batches, one worker thread per
 // GPU runs famfinder + aligner on whole batches against its replica of the index, and the writer emits the
-// batches in input order (the reference's sequencer_node, src/sina.cpp:529-538).
+// batches in input order (the reference's sequencer_node, src/sina.cpp:529-538). The alignment_width-long output lines
+// are rendered by a small pool of threads between the GPU workers and the writer (at 10^5
+// sequences/s x 50 000 columns a single rendering + writing thread is the bottleneck).
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <map>
 #include <mutex>
@@ -32,6 +35,9 @@ cli_options opts;
 struct batch_t {
     uint64_t no = 0;
     std::vector<tray> trays;
+    std::vector<std::string> records;   // FASTA record of every tray, rendered off the writer thread
+    std::vector<char> has_record;
+    uint64_t file_offset = 0;           // where the batch's records start in the output file (positional writer)
 };
 
 template <typename T>
@@ -129,8 +135,8 @@ int real_main(int argc, const char* const* argv) {
     std::cerr << "Aligner ready. Processing sequences" << std::endl;  // src/sina.cpp:581
     const auto before = std::chrono::steady_clock::now();
 
-    const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 4 * std::max(1u, ngpu);
-    bounded_queue<batch_t> todo(inflight);
+    const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 6 * std::max(1u, ngpu);
+    bounded_queue<batch_t> todo(inflight), torender(inflight), towrite(inflight);
     std::mutex done_mu;
     std::condition_variable done_cv;
     std::map<uint64_t, batch_t> done;
@@ -139,12 +145,20 @@ int real_main(int argc, const char* const* argv) {
     uint64_t n_batches = 0;
     bool reading_done = false;
 
+    // busy seconds of every pipeline role, printed with SINA_B200_TIMING=1 (where does a file-to-file run spend its time)
+    std::atomic<uint64_t> us_read(0), us_family(0), us_align(0), us_render(0), us_write(0);
+    auto usec = [](std::chrono::steady_clock::time_point a) {
+        return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - a).count();
+    };
     std::thread rd([&] {
         try {
             batch_t b;
             for (;;) {
                 tray t;
-                if (!reader(t)) break;
+                const auto t0 = std::chrono::steady_clock::now();
+                const bool more = reader(t);
+                us_read += usec(t0);
+                if (!more) break;
                 b.trays.push_back(t);
                 if (b.trays.size() == opts.batch) {
                     b.no = n_batches++;
@@ -170,21 +184,76 @@ int real_main(int argc, const char* const* argv) {
         while (todo.pop(b)) {
             try {
                 if (do_align && !failed) {
+                    auto t0 = std::chrono::steady_clock::now();
                     ff[d]->run(b.trays);
+                    us_family += usec(t0);
+                    t0 = std::chrono::steady_clock::now();
                     al[d]->run(b.trays);
+                    us_align += usec(t0);
                 }
             } catch (std::exception& e) {
                 std::lock_guard<std::mutex> l(done_mu);
                 if (!failed) failure = e.what();
                 failed = true;
             }
+            torender.push(std::move(b));
+        }
+    };
+    auto render = [&] {
+        batch_t b;
+        while (torender.pop(b)) {
+            const auto t0r = std::chrono::steady_clock::now();
+            try {
+                b.records.resize(b.trays.size());
+                b.has_record.assign(b.trays.size(), 0);
+                if (!failed) {
+                    for (size_t i = 0; i < b.trays.size(); i++) {
+                        tray& t = b.trays[i];
+                        if (!do_align && t.input_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
+                        if (t.input_sequence == nullptr) throw std::runtime_error("Received broken tray in rw_fasta writer");
+                        if (t.aligned_sequence) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
+                    }
+                }
+            } catch (std::exception& e) {
+                std::lock_guard<std::mutex> l(done_mu);
+                if (!failed) failure = e.what();
+                failed = true;
+            }
+            us_render += usec(t0r);
             std::lock_guard<std::mutex> l(done_mu);
             done.emplace(b.no, std::move(b));
             done_cv.notify_all();
         }
     };
-    std::vector<std::thread> workers;
-    for (unsigned int d = 0; d < std::max(1u, ngpu); d++) workers.emplace_back(work, d);
+    std::atomic<uint64_t> us_pwrite(0);
+    auto write_pool = [&] {
+        batch_t b;
+        while (towrite.pop(b)) {
+            const auto t0 = std::chrono::steady_clock::now();
+            try {
+                uint64_t at = b.file_offset;
+                for (size_t i = 0; i < b.trays.size(); i++) {
+                    if (b.has_record[i] && !failed) { writer.write_at(at, b.records[i].data(), b.records[i].size()); at += b.records[i].size(); }
+                    b.trays[i].destroy();  // src/sina.cpp:573-579
+                }
+            } catch (std::exception& e) {
+                std::lock_guard<std::mutex> l(done_mu);
+                if (!failed) failure = e.what();
+                failed = true;
+            }
+            us_pwrite += usec(t0);
+        }
+    };
+    std::vector<std::thread> workers, renderers, writers;
+    for (unsigned int r = 0; r < 4; r++) writers.emplace_back(write_pool);
+    // several host threads per GPU: the library serialises the device calls of one index, so while one thread's batch
+    // is on the GPU the others pack queries / build the result sequences of theirs
+    unsigned int wpg = do_align ? (ngpu <= 2 ? 6u : 3u) : 1u;   // B200 box, 1 GPU, 160k queries: 3 threads 44.8k seq/s, 6 threads 49.1k
+    if (do_align && getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
+    for (unsigned int d = 0; d < std::max(1u, ngpu); d++)
+        for (unsigned int k = 0; k < wpg; k++) workers.emplace_back(work, d);
+    const unsigned int n_render = std::max(2u, std::min(16u, std::max(1u, std::thread::hardware_concurrency()) / 2));
+    for (unsigned int r = 0; r < n_render; r++) renderers.emplace_back(render);
 
     uint64_t count = 0, next = 0;
     for (;;) {  // sink: batches in input order
@@ -197,25 +266,51 @@ int real_main(int argc, const char* const* argv) {
             done.erase(next);
         }
         next++;
-        for (auto& t : b.trays) {
+        const auto t0w = std::chrono::steady_clock::now();
+        if (writer.positional() && !failed) {
+            // byte ranges are handed out here, in input order; the write pool fills them and frees the trays
+            uint64_t total = 0;
+            unsigned int nrec = 0, nexc = 0;
+            for (size_t i = 0; i < b.trays.size(); i++) {
+                if (b.has_record[i]) { total += b.records[i].size(); nrec++; } else nexc++;
+                if (opts.show_log) std::cerr << "sequence_number: " << b.trays[i].seqno << " sequence_identifier: "
+                                             << b.trays[i].input_sequence->getName() << " " << b.trays[i].log.str() << std::endl;
+            }
+            count += b.trays.size();
+            b.file_offset = writer.reserve(total, nrec, nexc);
+            towrite.push(std::move(b));
+            us_write += usec(t0w);
+            continue;
+        }
+        for (size_t i = 0; i < b.trays.size(); i++) {
+            tray& t = b.trays[i];
             if (!failed) {
-                if (!do_align && t.input_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
-                writer(t);
+                writer.write_formatted(b.has_record[i] ? &b.records[i] : nullptr);
                 if (opts.show_log) std::cerr << "sequence_number: " << t.seqno << " sequence_identifier: "
                                              << t.input_sequence->getName() << " " << t.log.str() << std::endl;
             }
             count++;
             t.destroy();  // src/sina.cpp:573-579
         }
+        us_write += usec(t0w);
     }
+    towrite.close();
+    for (auto& w : writers) w.join();
     rd.join();
     for (auto& w : workers) w.join();
+    torender.close();
+    for (auto& r : renderers) r.join();
     if (failed) throw std::runtime_error(failure);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - before).count();
     char buf[256];
     snprintf(buf, sizeof(buf), "Took %.3fs to align %llu sequences (%.1f sequences/s)", secs, (unsigned long long)count,
              secs > 0 ? count / secs : 0.0);  // src/sina.cpp:588-589
     std::cerr << buf << std::endl;
+    if (getenv("SINA_B200_TIMING")) {
+        snprintf(buf, sizeof(buf), "busy seconds: read %.3f | family %.3f + align %.3f over %u worker threads | render %.3f over %u threads | sink %.3f | pwrite %.3f over 4 threads",
+                 us_read / 1e6, us_family / 1e6, us_align / 1e6, wpg * std::max(1u, ngpu), us_render / 1e6, n_render, us_write / 1e6, us_pwrite / 1e6);
+        std::cerr << buf << std::endl;
+    }
     if (writer.excluded()) std::cerr << writer.excluded() << " sequences were not aligned and not written" << std::endl;
     std::cerr << "SINA finished." << std::endl;
     return 0;

@@ -74,3 +74,32 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     r = run(["sina", "-i", str(q), "--db", str(d)])
     assert r.returncode == 1 and "no CUDA device" in r.stderr
     assert r.stdout == ""  # nothing was "aligned" by some fallback
+
+
+def test_cli_prealigned_passthrough_keeps_order(tmp_path):
+    """--prealigned (no device needed): reader -> render pool -> writer over many small batches keeps the input order
+    (the reference's sequencer_node, src/sina.cpp:529-538) and re-emits the aligned rows, wrapped by --line-length"""
+    import random
+    rnd = random.Random(5)
+    names, rows = [], []
+    for i in range(57):
+        names.append("s%03d" % i)
+        rows.append("".join(rnd.choice("ACGU-----") for _ in range(200)))
+    with open(tmp_path / "in.fasta", "w") as f:
+        for n, r in zip(names, rows):
+            f.write(">%s\n%s\n" % (n, r))
+    out = tmp_path / "out.fasta"
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "in.fasta"), "-o", str(out), "--batch-size", "3", "--line-length", "70"])
+    assert r.returncode == 0, r.stderr
+    got_names, got = [], {}
+    for line in open(out):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            got_names.append(line[1:].split()[0])
+            got[got_names[-1]] = []
+        else:
+            got[got_names[-1]].append(line)
+    assert got_names == names
+    for n, row in zip(names, rows):
+        assert all(len(x) <= 70 for x in got[n])
+        assert "".join(got[n]) == row
