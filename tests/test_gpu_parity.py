@@ -373,3 +373,90 @@ def test_insertion_forbid_vs_oracle(orc):
                 r0, c0, m0, _ = orc.align(msa, np.arange(msa.N, dtype=np.uint32), q, O.AlignParams(**kw0))
                 differ += int(len(c0) != len(c1) or (c0 != c1).any())
     assert differ >= 10, differ
+
+
+def test_host_buffer_streaming_matches_session(orc, monkeypatch):
+    """sg_run_batch streams each finished chunk's output through pinned staging into the caller's buffers: the result
+    must equal the session path's bulk download for several chunk / stream settings, for caller-owned buffers reused
+    across calls of different sizes (staging growth, cached-session reuse) and for calls without output buffers"""
+    tree, m, c, o = synth.synth_msa(500, W=1500, L=350, seed=21)
+    qm, qo = synth.synth_queries(tree, 75, "full", seed=8)
+    fp = sina_b200.FamParams(fs_min=12, fs_max=12, fs_min_len=100, fs_full_len=330, fs_req_gaps=5)
+    ap = sina_b200.AlignParams()
+    for batch, streams in ((7, 3), (16, 1), (1000, 4)):
+        monkeypatch.setenv("SG_BATCH", str(batch))
+        monkeypatch.setenv("SG_STREAMS", str(streams))
+        ix = sina_b200.Index(m, c, o, 1500, k=8)
+        s = sina_b200.Session(ix, 75, len(qm))
+        s.upload(qm, qo)
+        s.family(fp)
+        s.align(ap)
+        want_c, want_m, want_r = s.download_align()
+        s.close()
+        out = (np.full(len(qm), 0xFFFFFFFF, np.uint32), np.full(len(qm), 0xFF, np.uint8), np.zeros(75, sina_b200.RESULT_DTYPE))
+        for nq in (75, 20, 61):        # big, small, medium: the cached session and the staging slots are reused
+            n = int(qo[nq])
+            oc, om, res = ix.run(qm[:n], qo[:nq + 1], fp, ap, out=out)
+            assert oc is out[0] and om is out[1]
+            for q in range(nq):
+                a, k = int(qo[q]), int(want_r[q]["n_out"])
+                assert res[q]["status"] == want_r[q]["status"], (batch, streams, nq, q)
+                if want_r[q]["status"] in (0, 1):
+                    assert (oc[a:a + k] == want_c[a:a + k]).all() and (om[a:a + k] == want_m[a:a + k]).all(), (batch, streams, nq, q)
+                    assert bits(res[q]["score"]) == bits(want_r[q]["score"])
+        oc2, om2, res2 = ix.run(qm, qo, fp, ap)            # library-allocated outputs
+        assert (res2["status"] == want_r["status"]).all()
+        ix.close()
+
+
+def test_edge_case_queries_vs_oracle(orc):
+    """corner inputs through the whole path (sg_run_batch) against the oracle: queries of 2..12 bases (shorter than k:
+    no k-mer at all), all-ambiguous queries, a query much longer than every reference, a query equal to a reference
+    (copy path) and one contained in it, in one batch; then a one-row reference with --fs-req-full 0"""
+    tree, m, c, o = synth.synth_msa(120, W=900, L=220, seed=31)
+    msa = O.MSA(m, c, o, 900)
+    rng = np.random.default_rng(17)
+    qs = [np.array([1 << int(x) for x in rng.integers(0, 4, n)], np.uint8) for n in (2, 3, 5, 7, 8, 9, 12)]
+    qs.append(np.full(40, 15, np.uint8))                                   # NNNN...
+    qs.append(np.array([1 << int(x) for x in rng.integers(0, 4, 700)], np.uint8))   # random, 3x longer than the refs
+    r5, _ = msa.row(5)
+    qs.append(r5.copy())                                                   # identical to a reference
+    qs.append(r5[20:150].copy())                                           # contained in it
+    fqm, fqo = synth.synth_queries(tree, 6, "full", seed=77)
+    for i in range(6):
+        q = fqm[int(fqo[i]):int(fqo[i + 1])].copy()
+        if i % 2:
+            q[::17] = 15                                                   # sprinkle N
+        qs.append(q)
+    qmask, qoff = pack_queries(qs)
+    for fp_kw in (dict(fs_min=10, fs_max=10, fs_min_len=50, fs_full_len=200, fs_req_gaps=5),
+                  dict(fs_min=1, fs_max=1, fs_min_len=10, fs_full_len=200, fs_req_gaps=0, fs_req=1)):
+        for ap_kw in (dict(), dict(realign=1, overhang=1)):
+            ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=8)
+            oc, om, res = ix.run(qmask, qoff, sina_b200.FamParams(**fp_kw), sina_b200.AlignParams(**ap_kw))
+            ix.close()
+            oix = orc.index_build(msa, 8, 0)
+            ores, occ, omm, cells, posts, nt = orc.run_batch(oix, msa, qmask, qoff, O.FamParams(**fp_kw), O.AlignParams(**ap_kw))
+            orc.index_free(oix)
+            for i in range(len(qs)):
+                a, n = int(qoff[i]), ores[i].n_out
+                assert res[i]["status"] == ores[i].status, (fp_kw, ap_kw, i, res[i]["status"], ores[i].status)
+                if ores[i].status in (0, 1):
+                    assert res[i]["n_out"] == n
+                    assert (oc[a:a + n] == occ[a:a + n]).all() and (om[a:a + n] == omm[a:a + n]).all(), (fp_kw, ap_kw, i)
+                if ores[i].status == 0:
+                    assert bits(res[i]["score"]) == bits(ores[i].score), (fp_kw, ap_kw, i)
+    # a reference of one row
+    one = O.MSA(*[x for x in (msa.masks[:int(msa.off[1])], msa.cols[:int(msa.off[1])], msa.off[:2])], 900)
+    fp_kw = dict(fs_min=1, fs_max=5, fs_min_len=10, fs_full_len=100, fs_req_gaps=0, fs_req_full=0)
+    ix = sina_b200.Index(one.masks, one.cols, one.off, 900, k=8)
+    oc, om, res = ix.run(qmask, qoff, sina_b200.FamParams(**fp_kw), sina_b200.AlignParams(realign=1))
+    ix.close()
+    oix = orc.index_build(one, 8, 0)
+    ores, occ, omm, cells, posts, nt = orc.run_batch(oix, one, qmask, qoff, O.FamParams(**fp_kw), O.AlignParams(realign=1))
+    orc.index_free(oix)
+    for i in range(len(qs)):
+        a, n = int(qoff[i]), ores[i].n_out
+        assert res[i]["status"] == ores[i].status, ("one", i)
+        if ores[i].status in (0, 1):
+            assert (oc[a:a + n] == occ[a:a + n]).all() and (om[a:a + n] == omm[a:a + n]).all(), ("one", i)
