@@ -118,7 +118,25 @@ class CpuPath:
             t0 = time.perf_counter()
             res, oc, om, cells, posts, nt = self.orc.run_batch(self.ix, self.msa, sub_m, sub_off, O.FamParams(), O.AlignParams(), nthreads=nthreads)
             dt = time.perf_counter() - t0
-        return {"value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": self.kind,
+        # k-mer search alone on one core (the reference's find() is serial per query), same algorithmic-bytes formula
+        # as roofline_kmer: 4*P + 2*N + 8*max per query
+        kfind = None
+        try:
+            nf = min(64, nsample)
+            t1 = time.perf_counter()
+            P = 0
+            for i in range(nf):
+                q = sub_m[int(sub_off[i]):int(sub_off[i + 1])]
+                if self.kind == "reference":
+                    P += self.ref.find(self.ix, O.decode(q), 41)[2]
+                else:
+                    P += self.orc.find(self.ix, q, 41)[2]
+            dtf = time.perf_counter() - t1
+            kfind = {"gbs": (4.0 * P + (2.0 * self.args.refs + 8 * 41) * nf) / dtf / 1e9, "queries_per_s": nf / dtf,
+                     "cores": 1, "sample": "%d queries, find(max=41) only" % nf}
+        except Exception:
+            pass
+        return {"kmer_search": kfind, "value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": self.kind,
                 "sample": "%d of the step's %s queries vs the same %d-row index, whole path, %.1f s on %d threads"
                           % (nsample, self.args.kind, self.args.refs, dt, int(nt)),
                 "mcells_per_s": cells / dt / 1e6, "seconds": dt}
@@ -349,7 +367,7 @@ def main():
             cpu = CpuPath(args, m, c, o)
             cb = cpu.run(qm, qo, cpu_sample_size(args))
             cpu.close()
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s", "kmer_search")}
         print(json.dumps(line))
     ix.close()
     if world > 1:
