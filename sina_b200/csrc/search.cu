@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
 
     // ---- counting
     const uint32_t sub = tile * A.tile_warps + w;
+    uint32_t lmax = 0;   // highest counter value this lane wrote: the tile maximum needs no pass of its own
     if (sub < A.n_sub) {
         uint16_t* hw = hist + (size_t)w * B;
         const uint32_t* kl = A.kmers + A.qoff[q];
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
 #pragma unroll
                 for (int g = 0; g < FIND_G; g++) {
                     if (ll[g] == 0) continue;                       // warp-uniform
-                    if (lane < ll[g]) hw[x[g]] = (uint16_t)(hw[x[g]] + 1);
+                    if (lane < ll[g]) { const uint32_t nv = hw[x[g]] + 1u; hw[x[g]] = (uint16_t)nv; lmax = max(lmax, nv); }
                     __syncwarp();
                     for (uint32_t e0 = 32; e0 < ll[g]; e0 += 128) {  // long lists: four more loads at a time
                         uint32_t y[4];
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
                             y[u] = e < ll[g] ? (uint32_t)__ldg(post + al[g] + e) : 0xffffffffu;
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; u++) if (y[u] != 0xffffffffu) hw[y[u]] = (uint16_t)(hw[y[u]] + 1);
+                        for (int u = 0; u < 4; u++)
+                            if (y[u] != 0xffffffffu) { const uint32_t nv = hw[y[u]] + 1u; hw[y[u]] = (uint16_t)nv; lmax = max(lmax, nv); }
                         __syncwarp();
                     }
                 }
@@ -126,8 +128,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
     uint64_t* out = A.cand + ((uint64_t)q * n_tiles + tile) * A.max;
     auto score_of = [&](uint32_t i) -> uint32_t { return hist[i]; };
     // tile maximum
-    uint32_t mx = 0;
-    for (uint32_t i = tid; i < words; i += nt) { const uint32_t v = hist32[i]; mx = max(mx, max(v & 0xffffu, v >> 16)); }
+    uint32_t mx = lmax;   // tracked while counting (a counter's last write is its final value)
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[w] = mx;
     if (tid == 0) { sh_sel[3] = 0; sh_sel[4] = 0; sh_sel[5] = 0; }
