@@ -230,8 +230,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        sess.family(fp)
-        sess.align(ap)
+        sess.run(fp, ap)   # famfinder + aligner in one call (sg_session_run), as sg_run_batch runs them
         sess.sync()
 
     # the caller's output buffers, allocated once as a C++ host keeps them (plain pageable memory)

@@ -142,6 +142,8 @@ int sg_session_turn(sg_session* s, int mode, int32_t* turn);
 int sg_session_family(sg_session* s, const sg_fam_params* fp);
 int sg_session_set_family(sg_session* s, const uint32_t* fam_ids, const uint64_t* fam_off);
 int sg_session_align(sg_session* s, const sg_align_params* ap);
+/* sg_session_family + sg_session_align in one call (what sg_run_batch runs) */
+int sg_session_run(sg_session* s, const sg_fam_params* fp, const sg_align_params* ap);
 int sg_session_sync(sg_session* s);
 int sg_session_download_find(sg_session* s, int16_t* scores, uint32_t* ids, uint32_t* nres);
 int sg_session_download_family(sg_session* s, uint32_t fam_stride, uint32_t* fam_ids, float* fam_scores,

@@ -20,7 +20,7 @@ EXPORTS = [
     "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list",
     "sg_find_batch", "sg_turn_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
     "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_turn", "sg_session_family",
-    "sg_session_set_family", "sg_session_align", "sg_session_sync", "sg_session_download_find",
+    "sg_session_set_family", "sg_session_align", "sg_session_run", "sg_session_sync", "sg_session_download_find",
     "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
 ]
 
@@ -116,6 +116,7 @@ def lib():
     L.sg_session_turn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.sg_session_family.argtypes = [C.c_void_p, C.POINTER(FamParams)]
     L.sg_session_set_family.argtypes = [C.c_void_p, u32p, u64p]
+    L.sg_session_run.argtypes = [C.c_void_p, C.POINTER(FamParams), C.POINTER(AlignParams)]
     L.sg_session_align.argtypes = [C.c_void_p, C.POINTER(AlignParams)]
     L.sg_session_sync.argtypes = [C.c_void_p]
     L.sg_session_download_find.argtypes = [C.c_void_p, i16p, u32p, u32p]
@@ -297,6 +298,12 @@ class Session:
     def align(self, ap=None):
         ap = ap or AlignParams()
         _check(lib().sg_session_align(self.h, C.byref(ap)))
+
+    def run(self, fp=None, ap=None):
+        """family finding + alignment in one call (sg_session_run)"""
+        self.fp = fp or FamParams()
+        ap = ap or AlignParams()
+        _check(lib().sg_session_run(self.h, C.byref(self.fp), C.byref(ap)))
 
     def sync(self):
         _check(lib().sg_session_sync(self.h))

@@ -381,25 +381,35 @@ int sg_session_turn(sg_session* h, int mode, int32_t* turn) {
     return SG_OK;
 }
 
+// Family finding for queries [q0, q0 + n) of the batch (n == 0: all of it): k-mer search + selection, the candidate
+// window widened x10 until no query of the range asks for more (famfinder.cpp:590-608).
+static int family_range(Session* s, const sg_fam_params* fp, uint32_t q0, uint32_t n) {
+    uint64_t window = (uint64_t)fp->fs_max + 1;  // famfinder.cpp:590
+    for (;;) {
+        const uint32_t w = (uint32_t)std::min<uint64_t>(window, s->ix->N);
+        SG_TRY(stage_begin(s, 0));
+        SG_TRY(launch_find(s, w, q0, n));
+        SG_TRY(stage_end(s, &s->stats.ms_find));
+        SG_TRY(stage_begin(s, 1));
+        SG_TRY(launch_family(s, *fp, s->find_max, q0, n));
+        SG_TRY(stage_end(s, &s->stats.ms_family));
+        uint32_t retry = 0;
+        SG_CUDA(cudaMemcpyAsync(&retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        if (retry == 0 || w >= s->ix->N) break;
+        window *= 10;  // famfinder.cpp:607 (the whole range is re-ranked with the wider window)
+    }
+    return SG_OK;
+}
+
 int sg_session_family(sg_session* h, const sg_fam_params* fp) {
     Session* s = (Session*)h;
     if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_family: no queries uploaded");
     SG_TRY(validate_fam_params(fp));
     SG_CUDA(cudaSetDevice(s->ix->device));
     SG_TRY(ensure_family_capacity(s, fp->fs_max + fp->fs_req_full + 1));
-    uint64_t window = (uint64_t)fp->fs_max + 1;  // famfinder.cpp:590
-    for (;;) {
-        const uint32_t w = (uint32_t)std::min<uint64_t>(window, s->ix->N);
-        SG_TRY(sg_session_find(h, w));
-        SG_TRY(stage_begin(s, 1));
-        SG_TRY(launch_family(s, *fp, s->find_max));
-        SG_TRY(stage_end(s, &s->stats.ms_family));
-        uint32_t retry = 0;
-        SG_CUDA(cudaMemcpyAsync(&retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
-        SG_CUDA(cudaStreamSynchronize(s->stream));
-        if (retry == 0 || w >= s->ix->N) break;
-        window *= 10;  // famfinder.cpp:607 (the whole batch is re-ranked with the wider window)
-    }
+    SG_TRY(family_range(s, fp, 0, 0));
+    s->have_find = true;
     s->have_family = true;
     return SG_OK;
 }
@@ -505,17 +515,10 @@ static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
     return SG_OK;
 }
 
-int sg_session_align(sg_session* h, const sg_align_params* ap) {
-    Session* s = (Session*)h;
-    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_align: no queries uploaded");
-    if (!s->have_family) SG_FAIL(SG_ERR_ARG, "sg_session_align: run sg_session_family or sg_session_set_family first");
-    SG_TRY(validate_align_params(ap));
-    SG_CUDA(cudaSetDevice(s->ix->device));
-    SG_TRY(stage_begin(s, 2));
-    SG_TRY(launch_prealign(s, *ap));
-    SG_TRY(stage_end(s, &s->stats.ms_graph));   // synchronises: the workspace streams may start
-    int k = 0;
-    for (uint32_t q0 = 0; q0 < s->nq; q0 += s->chunk, k++) {
+// Chunk pipeline of the aligner stage from query q_start on: chunk k goes to workspace k % n_ws (k_start = chunks
+// already queued), then everything in flight is retired.
+static int align_chunks(Session* s, const sg_align_params* ap, uint32_t q_start, int k) {
+    for (uint32_t q0 = q_start; q0 < s->nq; q0 += s->chunk, k++) {
         Workspace* w = &s->ws[k % s->n_ws];
         SG_TRY(retire_chunk(s, w, *ap));
         SG_TRY(enqueue_chunk(s, w, *ap, q0, std::min(s->chunk, s->nq - q0)));
@@ -534,6 +537,31 @@ int sg_session_align(sg_session* h, const sg_align_params* ap) {
     s->stats.cells = cnt[1];
     s->have_align = true;
     return SG_OK;
+}
+
+int sg_session_align(sg_session* h, const sg_align_params* ap) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_align: no queries uploaded");
+    if (!s->have_family) SG_FAIL(SG_ERR_ARG, "sg_session_align: run sg_session_family or sg_session_set_family first");
+    SG_TRY(validate_align_params(ap));
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    SG_TRY(stage_begin(s, 2));
+    SG_TRY(launch_prealign(s, *ap));
+    SG_TRY(stage_end(s, &s->stats.ms_graph));   // synchronises: the workspace streams may start
+    return align_chunks(s, ap, 0, 0);
+}
+
+// famfinder + aligner on the resident batch in one call (what sg_run_batch runs). The family finding of the whole batch
+// runs first: overlapping it with the first chunks' graph / DP kernels was measured and loses (B200, 10 k queries: the
+// k-mer search CTAs, 96 KB of shared memory each, starve behind the resident DP CTAs, 3.6 -> 9.5 .. 26.7 ms, and the
+// later chunks start late: 99.2 k -> 97.4 k / 96.8 k sequences/s).
+int sg_session_run(sg_session* h, const sg_fam_params* fp, const sg_align_params* ap) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_run: no queries uploaded");
+    SG_TRY(validate_fam_params(fp));
+    SG_TRY(validate_align_params(ap));
+    SG_TRY(sg_session_family(h, fp));
+    return sg_session_align(h, ap);
 }
 
 int sg_session_sync(sg_session* h) {
@@ -684,10 +712,11 @@ struct SessionLease {
     ~SessionLease() { ix->mu.unlock(); }
     uint32_t step() const { return s->max_q; }
 };
-// aligner stage whose output columns/bases stream into the caller's buffers chunk by chunk (stage_chunk above)
-static int align_streaming(Session* s, const sg_align_params* ap, uint32_t* cols, uint8_t* masks) {
+// aligner stage (fp == null) or famfinder + aligner pipeline whose output columns/bases stream into the caller's
+// buffers chunk by chunk (stage_chunk above)
+static int align_streaming(Session* s, const sg_fam_params* fp, const sg_align_params* ap, uint32_t* cols, uint8_t* masks) {
     s->host_cols = cols; s->host_masks = masks; s->stage_next = 0;
-    const int rc = sg_session_align((sg_session*)s, ap);
+    const int rc = fp ? sg_session_run((sg_session*)s, fp, ap) : sg_session_align((sg_session*)s, ap);
     s->host_cols = nullptr; s->host_masks = nullptr;
     s->stage_info[0].pending = s->stage_info[1].pending = false;
     return rc;
@@ -753,7 +782,7 @@ int sg_align_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, ui
         const uint32_t n = std::min(L.step(), nq - a);
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, nullptr));
         SG_TRY(sg_session_set_family(s, fam_ids, fam_off + a));
-        SG_TRY(align_streaming(L.s, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
+        SG_TRY(align_streaming(L.s, nullptr, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
         SG_TRY(sg_session_download_align(s, nullptr, nullptr, results ? results + a : nullptr));
     }
     return SG_OK;
@@ -769,8 +798,7 @@ int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint
     for (uint32_t a = 0; a < nq; a += L.step()) {
         const uint32_t n = std::min(L.step(), nq - a);
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
-        SG_TRY(sg_session_family(s, fp));
-        SG_TRY(align_streaming(L.s, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
+        SG_TRY(align_streaming(L.s, fp, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
         SG_TRY(sg_session_download_align(s, nullptr, nullptr, results ? results + a : nullptr));
     }
     return SG_OK;

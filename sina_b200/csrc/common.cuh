@@ -228,10 +228,11 @@ struct Session {
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)
 int launch_index_build(Index* ix, cudaStream_t st);
-int launch_find(Session* s, uint32_t max);
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window);
+// q0 / n: query range of the batch (n == 0: all of it)
+int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0);
 int launch_turn(Session* s, int all);
-int launch_prealign(Session* s, const sg_align_params& ap);
+int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0 = 0, uint32_t n = 0);
 int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
 int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);
 int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);

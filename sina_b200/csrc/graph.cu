@@ -671,16 +671,18 @@ __global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A)
     }
 }
 
-int launch_prealign(Session* s, const sg_align_params& ap) {
+int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
-    uint32_t pairs = s->nq * s->fam_cap;
-    contains_kernel<<<(pairs + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, s->nq, ix->d_masks, ix->d_row_off,
-                                                           s->d_fam_ids, s->d_fam_n, s->fam_cap,
-                                                           s->d_contains);
-    partition_kernel<<<(s->nq + 127) / 128, 128, 0, s->stream>>>(s->nq, s->d_fam_ids, s->d_fam_n, s->fam_cap,
-                                                                s->d_contains, s->d_qoff, ix->d_row_off,
-                                                                ap.realign, s->d_afam, s->d_afam_n, s->d_copy_src,
-                                                                s->d_hdr);
+    if (n == 0) { q0 = 0; n = s->nq; }
+    const uint64_t fo = (uint64_t)q0 * s->fam_cap;
+    uint32_t pairs = n * s->fam_cap;
+    contains_kernel<<<(pairs + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff + q0, n, ix->d_masks, ix->d_row_off,
+                                                           s->d_fam_ids + fo, s->d_fam_n + q0, s->fam_cap,
+                                                           s->d_contains + fo);
+    partition_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(n, s->d_fam_ids + fo, s->d_fam_n + q0, s->fam_cap,
+                                                            s->d_contains + fo, s->d_qoff + q0, ix->d_row_off,
+                                                            ap.realign, s->d_afam + fo, s->d_afam_n + q0, s->d_copy_src + 2 * (uint64_t)q0,
+                                                            s->d_hdr + q0);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 2;
     return SG_OK;

@@ -262,8 +262,9 @@ __global__ void __launch_bounds__(1024) find_merge_kernel(const uint64_t* __rest
     if (threadIdx.x == 0) nres[q] = r;
 }
 
-int launch_find(Session* s, uint32_t max) {
+int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
+    if (n == 0) { q0 = 0; n = s->nq; }
     if (max == 0) SG_FAIL(SG_ERR_ARG, "find: max must be > 0");
     if (max > ix->N) max = ix->N;
     uint32_t p2 = 1;
@@ -281,16 +282,16 @@ int launch_find(Session* s, uint32_t max) {
     const size_t smem = (size_t)ix->tile_warps * ix->sub_size * 2;
     SG_CUDA(cudaFuncSetAttribute(find_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SG_CUDA(cudaFuncSetAttribute(find_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p2 * 8)));
-    query_kmers_kernel<<<(s->nq + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff, s->nq, ix->k, ix->nofast,
-                                                              s->d_kmers, s->d_nk);
+    query_kmers_kernel<<<(n + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff + q0, n, ix->k, ix->nofast,
+                                                          s->d_kmers, s->d_nk + q0);
     FindArgs A;
-    A.kmers = s->d_kmers; A.nk = s->d_nk; A.qoff = s->d_qoff; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
+    A.kmers = s->d_kmers; A.nk = s->d_nk + q0; A.qoff = s->d_qoff + q0; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
     A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max;
-    A.cand = s->d_cand; A.cand_n = s->d_cand_n; A.counters = s->d_counters;
-    dim3 grid(s->nq, ix->n_tiles);
+    A.cand = s->d_cand + (uint64_t)q0 * ix->n_tiles * max; A.cand_n = s->d_cand_n + (uint64_t)q0 * ix->n_tiles; A.counters = s->d_counters;
+    dim3 grid(n, ix->n_tiles);
     find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
-    find_merge_kernel<<<s->nq, p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
-        s->d_cand, s->d_cand_n, ix->n_tiles, max, ix->N, p2, s->d_ranked, s->d_nres);
+    find_merge_kernel<<<n, p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
+        A.cand, A.cand_n, ix->n_tiles, max, ix->N, p2, s->d_ranked + (uint64_t)q0 * max, s->d_nres + q0);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 3;
     return SG_OK;
@@ -430,12 +431,14 @@ __global__ void family_kernel(const uint64_t* __restrict__ ranked, const uint32_
     fam_n[q] = n < p.fs_req ? -1 : (int32_t)n;  // :486-491
 }
 
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window) {
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
+    if (n == 0) { q0 = 0; n = s->nq; }
     SG_CUDA(cudaMemsetAsync(s->d_retry, 0, sizeof(uint32_t), s->stream));
-    family_kernel<<<(s->nq + 127) / 128, 128, 0, s->stream>>>(s->d_ranked, s->d_nres, s->nq, window, ix->N,
-                                                             ix->d_row_off, ix->d_cols, s->d_excl, fp, s->fam_cap,
-                                                             s->d_fam_ids, s->d_fam_scores, s->d_fam_n, s->d_retry);
+    family_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d_ranked + (uint64_t)q0 * window, s->d_nres + q0, n, window, ix->N,
+                                                         ix->d_row_off, ix->d_cols, s->d_excl + q0, fp, s->fam_cap,
+                                                         s->d_fam_ids + (uint64_t)q0 * s->fam_cap,
+                                                         s->d_fam_scores + (uint64_t)q0 * s->fam_cap, s->d_fam_n + q0, s->d_retry);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;
