@@ -392,6 +392,10 @@ def test_host_buffer_streaming_matches_session(orc, monkeypatch):
         s.family(fp)
         s.align(ap)
         want_c, want_m, want_r = s.download_align()
+        s.run(fp, ap)                                       # sg_session_run = the same two stages in one call
+        run_c, run_m, run_r = s.download_align()
+        assert (run_r["status"] == want_r["status"]).all() and (bits(run_r["score"]) == bits(want_r["score"])).all()
+        assert (run_c == want_c).all() and (run_m == want_m).all()
         s.close()
         out = (np.full(len(qm), 0xFFFFFFFF, np.uint32), np.full(len(qm), 0xFF, np.uint8), np.zeros(75, sina_b200.RESULT_DTYPE))
         for nq in (75, 20, 61):        # big, small, medium: the cached session and the staging slots are reused
