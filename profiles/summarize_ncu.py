@@ -16,10 +16,14 @@ WANT = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads per instruction"),
-    ("sm__inst_executed_pipe_alu.sum", "pipe alu"),
-    ("sm__inst_executed_pipe_fma.sum", "pipe fma"),
-    ("sm__inst_executed_pipe_fmaheavy.sum", "pipe fmaheavy"),
-    ("sm__inst_executed_pipe_lsu.sum", "pipe lsu"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "pipe alu % (int / compare / select / min-max)"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "pipe fma % (fp32 add / fma, imad)"),
+    ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "pipe fmaheavy %"),
+    ("sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active", "pipe fmalite %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "pipe lsu %"),
+    ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "pipe uniform %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu data pipe wavefronts % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short scoreboard / issue"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long scoreboard / issue"),
