@@ -188,8 +188,16 @@ def run_reference(args):
 
 
 def workload_config(args, queries_per_step):
-    return {"workload": "BASELINE configs[1]: %d %s 16S queries (~%d nt) per step per GPU vs synthetic %d-seq reference MSA (%d columns), "
-                        "k=%d fast, fs-max 40, reference defaults" % (queries_per_step, "full-length" if args.kind == "full" else "V4",
+    if args.refs == N_REFS and args.kind == "full":
+        which = "BASELINE configs[1]"
+    elif args.refs == 500000 and args.kind == "v4":
+        which = "BASELINE configs[2] (one GPU's share)"
+    elif args.refs == 500000 and args.kind == "full":
+        which = "BASELINE configs[3] (one GPU's share)"
+    else:
+        which = "variant of BASELINE configs[1]"
+    return {"workload": "%s: %d %s 16S queries (~%d nt) per step per GPU vs synthetic %d-seq reference MSA (%d columns), "
+                        "k=%d fast, fs-max 40, reference defaults" % (which, queries_per_step, "full-length" if args.kind == "full" else "V4",
                                                                      1500 if args.kind == "full" else 280, args.refs, W_COLS, KMER),
             "queries_per_step_per_gpu": queries_per_step, "refs": args.refs, "columns": W_COLS, "k": KMER,
             "l2": "inputs larger than L2 (index 0.4 GB + >30 GB traceback written per step)",
