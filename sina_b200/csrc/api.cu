@@ -518,10 +518,14 @@ static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
 // Chunk pipeline of the aligner stage from query q_start on: chunk k goes to workspace k % n_ws (k_start = chunks
 // already queued), then everything in flight is retired.
 static int align_chunks(Session* s, const sg_align_params* ap, uint32_t q_start, int k) {
-    for (uint32_t q0 = q_start; q0 < s->nq; q0 += s->chunk, k++) {
+    // the first chunk is a third of the others: its graph kernel is all the GPU has to do until the first DP kernel can
+    // start, so a short one shortens the pipeline's fill
+    for (uint32_t q0 = q_start, n; q0 < s->nq; q0 += n, k++) {
         Workspace* w = &s->ws[k % s->n_ws];
+        static const uint32_t first_div = (uint32_t)std::max<uint64_t>(1, env_mb("SG_FIRST_DIV", 3));
+        n = std::min((k == 0 && s->n_ws > 1) ? std::max(1u, s->chunk / first_div) : s->chunk, s->nq - q0);
         SG_TRY(retire_chunk(s, w, *ap));
-        SG_TRY(enqueue_chunk(s, w, *ap, q0, std::min(s->chunk, s->nq - q0)));
+        SG_TRY(enqueue_chunk(s, w, *ap, q0, n));
         // the retired chunk's output goes to the caller's buffers while the GPU runs the chunks just queued
         for (int i = 0; i < 2; i++) SG_TRY(flush_stage(s, i));
     }
