@@ -6,6 +6,8 @@
 #include <mutex>
 #include <vector>
 
+#include <future>
+
 #include "common.cuh"
 
 namespace sg {
@@ -334,15 +336,23 @@ int sg_session_upload(sg_session* h, const uint8_t* qmasks, const uint64_t* qoff
         s->h_qoff[i] = qoff[i] - base;
     }
     s->h_qoff[nq] = total;
-    {
+    // the bases are validated on a second host thread while this one copies them to the device (a pageable source makes
+    // cudaMemcpyAsync a blocking staged copy); nothing is launched on them before the verdict is in
+    const uint8_t* qb = qmasks + base;
+    auto scan = [qb, total]() -> unsigned {
         unsigned bad = 0;   // branch-free so that the compiler vectorises the scan
-        const uint8_t* qb = qmasks + base;
         for (uint64_t j = 0; j < total; j++) bad |= (unsigned)((qb[j] & 15) == 0) | (unsigned)(qb[j] > 31);
-        if (bad) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
-    }
+        return bad;
+    };
+    std::future<unsigned> verdict;
+    const bool threaded = total > (1u << 20);
+    if (threaded) verdict = std::async(std::launch::async, scan);
+    else if (scan()) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
     SG_CUDA(cudaSetDevice(s->ix->device));
-    s->nq = nq;
+    s->nq = 0;
     SG_CUDA(cudaMemcpyAsync(s->d_qmasks, qmasks + base, total, cudaMemcpyHostToDevice, s->stream));
+    if (threaded && verdict.get()) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    s->nq = nq;
     SG_CUDA(cudaMemcpyAsync(s->d_qoff, s->h_qoff, ((uint64_t)nq + 1) * 8, cudaMemcpyHostToDevice, s->stream));
     if (exclude_ids) SG_CUDA(cudaMemcpyAsync(s->d_excl, exclude_ids, (uint64_t)nq * 8, cudaMemcpyHostToDevice, s->stream));
     else SG_CUDA(cudaMemsetAsync(s->d_excl, 0xff, (uint64_t)nq * 8, s->stream));
