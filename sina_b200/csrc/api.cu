@@ -345,13 +345,19 @@ int sg_session_upload(sg_session* h, const uint8_t* qmasks, const uint64_t* qoff
         return bad;
     };
     std::future<unsigned> verdict;
-    const bool threaded = total > (1u << 20);
-    if (threaded) verdict = std::async(std::launch::async, scan);
-    else if (scan()) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    bool threaded = total > (1u << 20);
+    if (threaded) {
+        try { verdict = std::async(std::launch::async, scan); } catch (...) { threaded = false; }   // no thread: scan here
+    }
+    if (!threaded && scan()) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
     SG_CUDA(cudaSetDevice(s->ix->device));
     s->nq = 0;
     SG_CUDA(cudaMemcpyAsync(s->d_qmasks, qmasks + base, total, cudaMemcpyHostToDevice, s->stream));
-    if (threaded && verdict.get()) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    if (threaded) {
+        unsigned bad = 1;
+        try { bad = verdict.get(); } catch (...) { bad = scan(); }
+        if (bad) SG_FAIL(SG_ERR_ARG, "query base is not an IUPAC mask");
+    }
     s->nq = nq;
     SG_CUDA(cudaMemcpyAsync(s->d_qoff, s->h_qoff, ((uint64_t)nq + 1) * 8, cudaMemcpyHostToDevice, s->stream));
     if (exclude_ids) SG_CUDA(cudaMemcpyAsync(s->d_excl, exclude_ids, (uint64_t)nq * 8, cudaMemcpyHostToDevice, s->stream));
