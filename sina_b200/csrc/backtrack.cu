@@ -24,7 +24,8 @@
 namespace sg {
 
 struct __align__(16) NodeRec {
-    uint32_t tbbase;    // index of the row's first cell pair inside the query's traceback block (u16 or u32 units)
+    uint32_t tbbase;    // generic kernel: index of the row's first cell pair inside the query's traceback block (u16 or u32
+                        // units); v2 kernel: byte offset of the row's first 16-byte record
     uint32_t meta;      // [15:0] sigma - sigma_lo(group)  [23:16] predecessor-slot shift  [31:24] in-degree
     uint32_t ncol;
     uint32_t pred_off;
@@ -156,7 +157,9 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     const float* nweight = A.nweight + io;
     const uint32_t* tbq = A.tb + h.tb_off;
     const uint16_t* tbq16 = reinterpret_cast<const uint16_t*>(tbq);
+    const uint8_t* tbq8 = reinterpret_cast<const uint8_t*>(tbq);
     const bool wide = h.wide != 0;
+    const bool v2 = h.mode == 2;   // cells written by the v2 DP kernel: two query positions per step (common.cuh)
     const uint32_t V = h.V, W = A.W;
     const uint32_t T = DP_T;
     NodeRec* rec = A.rec + io;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
             const GroupInfo gi = groups[g];
             const uint32_t po = pred_off[m], np = pred_off[m + 1] - po;
             uint4 a, b;
-            a.x = (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
+            a.x = v2 ? (uint32_t)(4 * gi.tb_off) + 16u * tid : (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
             a.y = (nsigma[m] - gi.sigma_lo) | ((uint32_t)nshift[m] << 16) | (min(np, 255u) << 24);
             a.z = ncol[m];
             a.w = po;
@@ -197,24 +200,37 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     // traceback cell: the load (cell_raw) and its decoding (cell_dec) are separate so that a speculative load can stay
     // in flight; decoded = src | slot<<8 | ob<<2 (the wide layout; ob = a deletion leaving the cell opens, common.cuh)
     auto cell_raw = [&](const uint4& a, uint32_t s) -> uint32_t {
+        if (v2) {
+            const uint32_t t = (s >> 1) + (a.y & 0xffffu);
+            return (uint32_t)__ldcg(&tbq8[a.x + (t >> 3) * (T * 16u) + 2u * (t & 7u) + (s & 1u)]);
+        }
         const uint32_t t = s + (a.y & 0xffffu);
         const uint32_t idx = a.x + (t >> 1) * T;
         return wide ? __ldcg(&tbq[idx]) : (uint32_t)__ldcg(&tbq16[idx]);
     };
     auto cell_dec = [&](const uint4& a, uint32_t s, uint32_t raw) -> uint32_t {
+        const uint32_t sh = (a.y >> 16) & 0xffu, np = a.y >> 24;
+        if (v2) {
+            const uint32_t c = raw & 0xffu;
+            if (sh & TBR_FLAG) {
+                // raw cell (common.cuh): the first flag in the order insertion, deletion slots, match slots names the
+                // source; no flag = the last match slot; a row without predecessor has no deletion / match source
+                const uint32_t mt = (c >> 4) & 3u, dl = c & 7u;
+                uint32_t out = 0;
+                if (c & TBR_INS) out = TB_SRC_INS;
+                else if (np == 0) out = TB_SRC_NONE;
+                else if (dl) out = TB_SRC_DEL | (((uint32_t)__ffs((int)dl) - 1u) << 8);
+                else if (mt) out = TB_SRC_MATCH | (((uint32_t)__ffs((int)mt) - 1u) << 8);
+                else out = TB_SRC_MATCH | (((sh & 0x7fu) + np - 1u) << 8);
+                return out | ((c >> 7) << 2);
+            }
+            uint32_t src = c & 3u;
+            if (np == 0 && src != TB_SRC_INS) src = TB_SRC_NONE;
+            return src | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
+        }
         const uint32_t t = s + (a.y & 0xffffu);
         if (wide) return (raw >> (16 * (t & 1))) & 0xffffu;
         const uint32_t c = (raw >> (8 * (t & 1))) & 0xffu;
-        const uint32_t sh = (a.y >> 16) & 0xffu;
-        if (sh & TBR_FLAG) {
-            // raw cell (common.cuh): the last winner in evaluation order is the source
-            const uint32_t mt = (c >> 4) & 7u, dl = c & 7u;
-            uint32_t out = 0;
-            if (mt) out = TB_SRC_MATCH | ((31u - (uint32_t)__clz((int)mt)) << 8);
-            else if (c & TBR_INS) out = TB_SRC_INS;
-            else if (dl) out = TB_SRC_DEL | ((31u - (uint32_t)__clz((int)dl)) << 8);
-            return out | ((c >> 7) << 2);
-        }
         return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
     };
     auto cell = [&](const uint4& a, uint32_t s) -> uint32_t { return cell_dec(a, s, cell_raw(a, s)); };

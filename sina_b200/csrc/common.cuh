@@ -45,27 +45,37 @@ constexpr int DP_CTAS_PER_SM = 4;            // resident DP CTAs per SM the kern
 constexpr int DP_T = 224;                    // node rows per DP group (compute lanes, one row each)
 constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
 constexpr int DP_RING = 8;                   // ring depth (time slots) of the shared-memory row window
-constexpr int GHOST_LEAD = 6;                // a ghost trails its source row by >= this many column ranks (prefetch 4 + 2)
+constexpr int DP_MAXD = 4;                   // v2 kernel: largest column-rank distance of a predecessor served by the ring
+                                             // (the generic kernel serves DP_RING - 2); farther ones go through ghosts
+constexpr int GHOST_PF = 2;                  // steps a ghost requests its data ahead of publishing it
+constexpr int GHOST_LEAD = GHOST_PF + 2;     // a ghost trails a source row of its own group by >= this many column ranks
+static_assert(GHOST_LEAD <= DP_MAXD, "an in-group edge too long for the ring must be long enough for a ghost");
 constexpr uint32_t FARLIST_CAP = 1024;       // far edges per group the v2 plan can hold
 constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row lives in the global spill buffer
 
-// traceback cell layout (mesh.cu writes, backtrack.cu decodes); cells of two consecutive steps share one store:
-// tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells.
+// traceback cell layout (mesh.cu writes, backtrack.cu decodes).
+// generic kernel (hdr.mode 1): one query position per step, cells of two consecutive steps share one store:
+//   tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells.
+// v2 kernel (hdr.mode 2): two query positions per step, u8 cells, 8 steps (16 cells) per 16-byte store:
+//   tb128[group][t/8][thread], byte 2*(t&7) + (s&1), with s = 2*(t - (sigma - sigma_lo)) + (s&1).
 // Deletion candidates are computed once, by the row they leave from: a row publishes (value, dm) with
 //   dm(x,s) = min(value(x,s) + gap, gapm_val(x,s) + gapext)            (deletion(), src/mesh.h:305-330, seen from src)
 // and records in ITS OWN cell the bit ob(x,s) = value(x,s) + gap < gapm_val(x,s) + gapext ("a deletion leaving this
 // cell opens the gap"). The reference's per-edge facts follow from it: the deletion via predecessor p opened iff
 // ob(p,s); gapm_idx(x,s) = ob(lastpred(x), s) ? lastpred(x) : gapm_idx(lastpred(x), s).
 constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH = 3;
-// u8 : [1:0] src  [4:2] pred slot  [5] ob  [7] insertion opened
+// u8 : [1:0] src  [4:2] pred slot  [5] ob  [7] insertion opened (generic kernel only)
 // u16: [1:0] src  [2] ob  [4] ins-open  [15:8] pred slot
-// raw u8 (rows of v2 warps specialised on <= 3 predecessor slots, u8 cells): the comparison outcomes as they fall,
-// undecoded. The last winner in evaluation order (deletion slots, insertion, match slots) is the source; the
-// insertion-opened flag is not stored: it is "the source of (m, s-1) is not an insertion" (see backtrack.cu).
-//   [2:0] deletion via slot k won  [3] insertion won  [6:4] match via slot k won  [7] ob
+// raw u8 (rows of v2 warps specialised on <= 3 predecessor slots): which candidates EQUAL the cell's value. The
+// reference's source (the last update in its evaluation order: deletions with '<', insertion with '<=', matches
+// with '<') is the first set flag in the order insertion, deletion slots, match slots; the last match slot has no
+// flag (it is the source when no flag is set). A row without predecessor has no deletion / match source whatever
+// the flags say (its deletion candidate is the constant that stands for the initial value). The insertion-opened
+// flag is not stored: it is "the source of (m, s-1) is not an insertion" (see backtrack.cu).
+//   [2:0] deletion via slot k equals  [3] insertion equals  [5:4] match via slot k equals (k < slots-1)  [7] ob
 constexpr uint32_t TBR_DEL = 1, TBR_INS = 8, TBR_MATCH = 16, TBR_OB = 128;
 constexpr uint32_t TBR_FLAG = 0x80;          // in nshift[]: the row's cells are raw
-__host__ __device__ constexpr bool v2_raw_cells(int npw, bool wide) { return !wide && npw <= 3; }
+__host__ __device__ constexpr bool v2_raw_cells(int npw) { return npw <= 3; }
 
 // ------------------------------------------------------------------ index
 struct Index {
@@ -91,8 +101,8 @@ struct Index {
 struct GraphHdr {
     uint32_t V, E, n_cols, n_groups;
     uint32_t n_last, n_spill, max_indeg, wide;  // wide: traceback uses u16 cells
-    uint32_t mode;       // DP kernel: 2 / 3 = sorted rows + ghost columns (mesh_v2 with 8 / 16 query-table planes), 1 = generic fallback (mesh_v1)
-    uint32_t maskset;    // bit b set iff some node has IUPAC mask b (1..15); the v2 kernel keeps one query-table plane per mask
+    uint32_t mode;       // DP kernel: 2 = sorted rows + ghost columns (v2: two positions per step), 1 = generic fallback (v1)
+    uint32_t maskset;    // bit b set iff some node has IUPAC mask b (1..15); the v2 kernel keeps one query match-bit plane per mask
     uint64_t tb_off;     // offset (in 4-byte words) of this query's traceback in the arena
     uint64_t spill_off;  // offset (in float2) of this query's spill rows in the arena
     uint32_t status;     // 0 ok, else SG_Q_* / internal failure code (see GS_*)
@@ -223,7 +233,6 @@ struct Session {
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
-    int bankplan = 0;                // SG_BANKPLAN=1: bank-aware ring columns (bankplan_kernel). Measured on B200: shared-load bank conflicts 735M -> 395M per chunk, DP 80.2 -> 78.6 ms per 10k queries, but the plan costs 5.2 ms: off by default
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

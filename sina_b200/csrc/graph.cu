@@ -380,7 +380,8 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
             const uint32_t p = preds[e], d = sg_ - nsigma[p];
             if (p / T == g && d <= (uint32_t)DP_RING - 2) pdesc[e] = (d << 16) | (p - g * T);
-            else { pdesc[e] = FAR_BIT; spillrow[p] = 1; }
+            else pdesc[e] = FAR_BIT;
+            if (p / T != g || d > (uint32_t)DP_MAXD) spillrow[p] = 1;   // the v2 kernel's ring reaches DP_MAXD ranks
         }
     }
     __syncthreads();
@@ -430,14 +431,14 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             base += tot;
         }
         if (tid >= n && tid < T) order[(uint64_t)g * T + tid] = NONE;
-        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (uint8_t)tid;   // bankplan_kernel permutes these
+        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (uint8_t)tid;   // ring column of the thread's row
         if (tid == 0) { shv[2] = 0; shv[3] = 0; }  // far edges, ghosts
         __syncthreads();
         if (valid) {
             const uint32_t sg_ = nsigma[m];
             for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
                 const uint32_t p = preds[e], d = sg_ - nsigma[p];
-                if (p >= lo && d <= (uint32_t)DP_RING - 2) pdesc2[e] = (d << 16) | nthr[p];
+                if (p >= lo && d <= (uint32_t)DP_MAXD) pdesc2[e] = (d << 16) | nthr[p];
                 else {
                     const uint32_t i = atomicAdd(&shv[2], 1u);
                     if (i < FARLIST_CAP) far_e[i] = e; else shv[1] = 1;
@@ -447,11 +448,11 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         }
         __syncthreads();
         const uint32_t nfar = min(shv[2], FARLIST_CAP);
-        if (tid == 0) {  // ghosts = distinct (source row, 14-rank bucket of the consumer)
+        if (tid == 0) {  // ghosts = distinct (source row, DP_MAXD-rank bucket of the consumer)
             uint32_t ng = 0;
             for (uint32_t i = 0; i < nfar; i++) {
                 const uint32_t e = far_e[i], p = preds[e], mm = pdesc2[e];
-                const uint32_t bk = (nsigma[mm] - sigma_lo) / (DP_RING - 2);
+                const uint32_t bk = (nsigma[mm] - sigma_lo) / DP_MAXD;
                 uint32_t j = 0;
                 while (j < ng && !(gh_p[j] == p && gh_b[j] == bk)) j++;
                 if (j == ng) {
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         __syncthreads();
         const uint32_t ng = shv[3];
         auto ghost_sigma = [&](uint32_t j) -> int {  // column rank the ghost pretends to sit at
-            int sgm = (int)sigma_lo + (int)(gh_b[j] * (DP_RING - 2)) - 1;
+            int sgm = (int)sigma_lo + (int)(gh_b[j] * DP_MAXD) - 1;
             if (gh_p[j] >= lo) sgm = max(sgm, (int)nsigma[gh_p[j]] + GHOST_LEAD);  // source still being computed
             return sgm;
         };
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         }
         __syncthreads();
     }
+    const uint32_t mode = (shv[1] || A.force_generic || wide) ? 1u : 2u;   // v2 holds in-degree <= 8 and u8 cells
     if (tid == 0) {
         uint64_t words_total = 0;
         for (uint32_t g = 0; g < n_groups; g++) {
@@ -500,176 +502,28 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             groups[g].sigma_lo = lo;
             groups[g].depth = hi - lo + 1;
             groups[g].tb_off = words_total;
-            const uint32_t steps = (Lq + (hi - lo) + 3) & ~3u;  // the v2 kernel runs whole blocks of 4 steps
-            const uint32_t per_word = wide ? 2 : 4;
-            words_total += (uint64_t)(steps / per_word) * T;
+            if (mode == 2) {   // two positions per step, 16 bytes per thread and block of 8 steps (mesh.cu)
+                const uint32_t steps8 = (((Lq + 1u) >> 1) + (hi - lo) + 7u) & ~7u;
+                words_total += (uint64_t)(steps8 >> 3) * T * 4u;
+            } else {
+                const uint32_t steps = (Lq + (hi - lo) + 3) & ~3u;
+                const uint32_t per_word = wide ? 2 : 4;
+                words_total += (uint64_t)(steps / per_word) * T;
+            }
         }
-        const uint64_t spill_need = (uint64_t)n_spill * Lq;
+        const uint64_t spill_need = (uint64_t)n_spill * ((Lq + 1u) & ~1u);   // rows of an even number of positions (16-byte cells of the v2 kernel)
         const uint64_t tb_off = atomicAdd(&A.cursors[0], (unsigned long long)words_total);
         const uint64_t sp_off = atomicAdd(&A.cursors[1], (unsigned long long)spill_need);
         hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;
         hdr->n_last = n_last; hdr->n_spill = n_spill; hdr->max_indeg = max_indeg; hdr->wide = wide;
         hdr->maskset = shv[4];
-        hdr->mode = (shv[1] || A.force_generic) ? 1u : (__popc(shv[4]) > 8 ? 3u : 2u);
+        hdr->mode = mode;
         hdr->tb_off = tb_off; hdr->spill_off = sp_off;
         if (tb_off + words_total > A.tb_words || sp_off + spill_need > A.spill_elems) hdr->status = GS_ARENA_FULL;
         else atomicAdd(A.cells, (unsigned long long)V * Lq);
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------------
-// Ring-column plan of the v2 DP kernel, one warp per (query, group).
-// A row publishes its cells into one column of the shared-memory ring and every successor row reads them from
-// there with one LDS.64 per step. The 16 lanes of a half-warp are served in one wavefront only if their columns
-// fall into 16 different 8-byte bank pairs; with columns = thread ids the predecessor columns of a half-warp are
-// close to random and the loads cost 5.3 wavefronts instead of 2 (ncu: the LSU data pipe is what bounds the DP
-// kernel). Here every row gets its ring column: the column stays inside the row's 16-thread block (so a warp's
-// stores still cover whole 128-byte lines without conflict) and its bank is chosen greedily, block by block, as
-// the one that collides least with the predecessors already placed in the load instructions that will read it.
-// Bank pair of (column c, column-rank distance d) = (c + 3 * (8 - d)) mod 16: the ring's time-slot stride is
-// 3 cells more than a multiple of 16 (mesh.cu, RS).
-constexpr int BP_WARPS = 4;
-constexpr uint32_t BP_ENT = 640;        // near in-group edges per group the plan looks at
-constexpr uint32_t BP_INST = (DP_T / 16) * 8;   // load instructions per group: (half-warp, predecessor slot < 8)
-struct BankPlanArgs {
-    const GraphHdr* hdr; uint32_t q0, gcap, icap;
-    const uint32_t* order; const uint16_t* nthr; const uint32_t* pred_off; const uint32_t* preds; const uint32_t* nsigma;
-    uint32_t* pdesc2; uint8_t* rcol;
-};
-
-__global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A) {
-    __shared__ uint32_t occ_s[BP_WARPS][BP_INST * 16 / 4];   // u8 counters: addresses per (instruction, bank pair)
-    __shared__ uint32_t off_s[BP_WARPS][DP_T + 1];           // reads of the row at a position: CSR offsets
-    __shared__ uint32_t cur_s[BP_WARPS][DP_T];
-    __shared__ uint16_t ent_s[BP_WARPS][BP_ENT];             // instruction | distance << 7
-    __shared__ uint8_t np_s[BP_WARPS][DP_T];
-    __shared__ uint8_t rho_s[BP_WARPS][DP_T];
-    const uint32_t FULLM = 0xffffffffu;
-    const uint32_t w = warp_id(), lane = lane_id(), ql = blockIdx.x;
-    const GraphHdr h = A.hdr[A.q0 + ql];
-    if (h.status != GS_OK || h.mode < 2) return;
-    const uint32_t T = DP_T;
-    const uint64_t io = (uint64_t)ql * A.icap;
-    const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
-    const uint32_t* preds = A.preds + io;
-    const uint32_t* nsigma = A.nsigma + io;
-    const uint16_t* nthr = A.nthr + io;
-    uint32_t* pdesc2 = A.pdesc2 + io;
-    uint32_t* occ32 = occ_s[w];
-    const uint8_t* occ = reinterpret_cast<const uint8_t*>(occ32);
-    uint32_t* off = off_s[w];
-    uint32_t* cur = cur_s[w];
-    uint16_t* ent = ent_s[w];
-    uint8_t* npl = np_s[w];
-    uint8_t* rho = rho_s[w];
-    for (uint32_t g = w; g < h.n_groups; g += BP_WARPS) {
-        const uint32_t lo = g * T, n = min(T, h.V - lo);
-        const uint32_t* order = A.order + ((uint64_t)ql * A.gcap + g) * T;
-        uint8_t* rcol = A.rcol + ((uint64_t)ql * A.gcap + g) * T;
-        // in-degree of the row at every position; lane i keeps the specialisation width of DP warp i
-        uint32_t npw_mine = 1;
-        for (uint32_t wi = 0; wi < T / 32; wi++) {
-            const uint32_t pos = wi * 32 + lane;
-            uint32_t np = 0;
-            if (pos < n) { const uint32_t m = order[pos]; np = pred_off[m + 1] - pred_off[m]; }
-            npl[pos] = (uint8_t)min(np, 255u);
-            const uint32_t mx = max(1u, __reduce_max_sync(FULLM, np));
-            if (lane == wi) npw_mine = mx;
-        }
-        for (uint32_t i = lane; i <= T; i += 32) off[i] = 0;
-        for (uint32_t i = lane; i < BP_INST * 16 / 4; i += 32) occ32[i] = 0;
-        __syncwarp();
-        // reads of every producer position: pass 0 counts, pass 1 fills. Far predecessors sit in ghost columns that
-        // are already fixed: they go straight into the occupancy table.
-        uint32_t total = 0;
-        for (int pass = 0; pass < 2; pass++) {
-            for (uint32_t wi = 0; wi < T / 32; wi++) {
-                const uint32_t pos = wi * 32 + lane;
-                const uint32_t npw = __shfl_sync(FULLM, npw_mine, wi);
-                if (pos < n && npw <= 8) {
-                    const uint32_t m = order[pos], po = pred_off[m], np = npl[pos], shift = npw - np, sg_ = nsigma[m];
-                    for (uint32_t o = 0; o < np; o++) {
-                        const uint32_t p = preds[po + o], d = sg_ - nsigma[p];
-                        const uint32_t inst = (pos >> 4) * 8 + o + shift;
-                        if (p >= lo && d <= (uint32_t)DP_RING - 2) {
-                            const uint32_t pp = nthr[p];
-                            if (pass == 0) atomicAdd(&off[pp], 1u);
-                            else {
-                                const uint32_t at = atomicAdd(&cur[pp], 1u);
-                                if (at < BP_ENT) ent[at] = (uint16_t)(inst | (d << 7));
-                            }
-                        } else if (pass == 1) {
-                            const uint32_t dd = pdesc2[po + o];   // (distance << 16) | ghost column
-                            const uint32_t idx = inst * 16 + (((dd & 0xffffu) + 3u * (8u - (dd >> 16))) & 15u);
-                            atomicAdd(&occ32[idx >> 2], 1u << (8 * (idx & 3)));
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (pass == 0) {   // exclusive scan of the counts
-                uint32_t carry = 0;
-                for (uint32_t i0 = 0; i0 < T; i0 += 32) {
-                    const uint32_t v = off[i0 + lane];
-                    uint32_t x = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, x, o); if (lane >= (uint32_t)o) x += y; }
-                    off[i0 + lane] = carry + x - v;
-                    cur[i0 + lane] = carry + x - v;
-                    carry += __shfl_sync(FULLM, x, 31);
-                }
-                total = carry;
-                if (lane == 0) off[T] = total;
-                __syncwarp();
-            }
-        }
-        if (total > BP_ENT) continue;   // an unusually dense group keeps the identity columns written by graph_kernel
-        // greedy choice, position by position; lane b < 16 prices bank pair b, lane i < 14 keeps the free banks of block i
-        uint32_t fm = 0xffffu;
-        for (uint32_t pos = 0; pos < T; pos++) {
-            const uint32_t blk = pos >> 4;
-            const uint32_t fmask = __shfl_sync(FULLM, fm, blk);
-            uint32_t b;
-            const uint32_t a = off[pos], e = off[pos + 1];
-            if (pos < n && e > a) {
-                uint32_t key = 0xffffffffu;
-                if (lane < 16 && ((fmask >> lane) & 1u)) {
-                    uint32_t cost = 0;
-                    for (uint32_t j = a; j < e; j++) {
-                        const uint32_t en = ent[j];
-                        cost += occ[(en & 127u) * 16 + ((lane + 3u * (8u - (en >> 7))) & 15u)];
-                    }
-                    key = (cost << 4) | ((lane - pos) & 15u);   // ties: the bank nearest above the thread's own
-                }
-                key = __reduce_min_sync(FULLM, key);
-                b = ((key & 15u) + pos) & 15u;
-                for (uint32_t j = a + lane; j < e; j += 32) {
-                    const uint32_t en = ent[j];
-                    const uint32_t idx = (en & 127u) * 16 + ((b + 3u * (8u - (en >> 7))) & 15u);
-                    atomicAdd(&occ32[idx >> 2], 1u << (8 * (idx & 3)));
-                }
-            } else {
-                // nobody reads this position through the ring: the free bank nearest above the thread's own
-                const uint32_t rot = (fmask >> (pos & 15u)) | (fmask << (16u - (pos & 15u)));
-                b = ((uint32_t)__ffs((int)(rot & 0xffffu)) - 1u + pos) & 15u;
-            }
-            if (lane == blk) fm &= ~(1u << b);
-            if (lane == 0) rho[pos] = (uint8_t)(blk * 16 + b);
-            __syncwarp();
-        }
-        // publish: ring column per thread, and the column field of every near edge
-        for (uint32_t pos = lane; pos < T; pos += 32) rcol[pos] = rho[pos];
-        for (uint32_t pos = lane; pos < n; pos += 32) {
-            const uint32_t m = order[pos], po = pred_off[m], np = pred_off[m + 1] - po, sg_ = nsigma[m];
-            for (uint32_t o = 0; o < np; o++) {
-                const uint32_t p = preds[po + o], d = sg_ - nsigma[p];
-                if (p >= lo && d <= (uint32_t)DP_RING - 2) pdesc2[po + o] = (d << 16) | rho[nthr[p]];
-            }
-        }
-        __syncwarp();
-    }
-}
 
 int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
@@ -709,14 +563,6 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
     s->stats.kernel_launches += 1;
-    if (s->bankplan) {
-        BankPlanArgs B;
-        B.hdr = s->d_hdr; B.q0 = q0; B.gcap = s->gcap; B.icap = s->icap;
-        B.order = w->d_order; B.nthr = w->d_nthr; B.pred_off = w->d_pred_off; B.preds = w->d_preds; B.nsigma = w->d_nsigma;
-        B.pdesc2 = w->d_pdesc2; B.rcol = w->d_rcol;
-        bankplan_kernel<<<n, 32 * BP_WARPS, 0, w->stream>>>(B);
-        s->stats.kernel_launches += 1;
-    }
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
