@@ -25,7 +25,7 @@ namespace sg {
 
 struct __align__(16) NodeRec {
     uint32_t tbbase;    // generic kernel: index of the row's first cell pair inside the query's traceback block (u16 or u32
-                        // units); v2 kernel: byte offset of the row's first 16-byte record
+                        // units); v2 kernel: byte offset of the row's first word (4 cells)
     uint32_t meta;      // [15:0] sigma - sigma_lo(group)  [23:16] predecessor-slot shift  [31:24] in-degree
     uint32_t ncol;
     uint32_t pred_off;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
             const GroupInfo gi = groups[g];
             const uint32_t po = pred_off[m], np = pred_off[m + 1] - po;
             uint4 a, b;
-            a.x = v2 ? (uint32_t)(4 * gi.tb_off) + 16u * tid : (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
+            a.x = v2 ? (uint32_t)(4 * gi.tb_off) + 4u * tid : (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
             a.y = (nsigma[m] - gi.sigma_lo) | ((uint32_t)nshift[m] << 16) | (min(np, 255u) << 24);
             a.z = ncol[m];
             a.w = po;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     auto cell_raw = [&](const uint4& a, uint32_t s) -> uint32_t {
         if (v2) {
             const uint32_t t = (s >> 1) + (a.y & 0xffffu);
-            return (uint32_t)__ldcg(&tbq8[a.x + (t >> 3) * (T * 16u) + 2u * (t & 7u) + (s & 1u)]);
+            return (uint32_t)__ldcg(&tbq8[a.x + (t >> 1) * (T * 4u) + 2u * (t & 1u) + (s & 1u)]);
         }
         const uint32_t t = s + (a.y & 0xffffu);
         const uint32_t idx = a.x + (t >> 1) * T;

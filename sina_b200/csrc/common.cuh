@@ -56,8 +56,8 @@ constexpr uint32_t FAR_BIT = 0x80000000u;    // predecessor descriptor: row live
 // traceback cell layout (mesh.cu writes, backtrack.cu decodes).
 // generic kernel (hdr.mode 1): one query position per step, cells of two consecutive steps share one store:
 //   tb16[group][t/2][thread] (byte t&1) for u8 cells, tb32[group][t/2][thread] (half t&1) for u16 cells.
-// v2 kernel (hdr.mode 2): two query positions per step, u8 cells, 8 steps (16 cells) per 16-byte store:
-//   tb128[group][t/8][thread], byte 2*(t&7) + (s&1), with s = 2*(t - (sigma - sigma_lo)) + (s&1).
+// v2 kernel (hdr.mode 2): two query positions per step, u8 cells, 2 steps (4 cells) per 32-bit store:
+//   tb32[group][t/2][thread], byte 2*(t&1) + (s&1), with s = 2*(t - (sigma - sigma_lo)) + (s&1).
 // Deletion candidates are computed once, by the row they leave from: a row publishes (value, dm) with
 //   dm(x,s) = min(value(x,s) + gap, gapm_val(x,s) + gapext)            (deletion(), src/mesh.h:305-330, seen from src)
 // and records in ITS OWN cell the bit ob(x,s) = value(x,s) + gap < gapm_val(x,s) + gapext ("a deletion leaving this

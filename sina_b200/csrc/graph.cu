@@ -502,9 +502,9 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             groups[g].sigma_lo = lo;
             groups[g].depth = hi - lo + 1;
             groups[g].tb_off = words_total;
-            if (mode == 2) {   // two positions per step, 16 bytes per thread and block of 8 steps (mesh.cu)
+            if (mode == 2) {   // two positions per step, one word per thread and pair of steps (mesh.cu)
                 const uint32_t steps8 = (((Lq + 1u) >> 1) + (hi - lo) + 7u) & ~7u;
-                words_total += (uint64_t)(steps8 >> 3) * T * 4u;
+                words_total += (uint64_t)(steps8 >> 1) * T;
             } else {
                 const uint32_t steps = (Lq + (hi - lo) + 3) & ~3u;
                 const uint32_t per_word = wide ? 2 : 4;

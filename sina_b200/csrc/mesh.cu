@@ -66,15 +66,20 @@ constexpr int QB_PLANES = 19;
 static_assert(DP_T + DP_G - 2 <= (int)COL_PAD, "ghost columns must end below the constant columns");
 static_assert(2 * DP_T + 64 <= QB_PAD, "pre-start steps of a row must stay inside the padding");
 
-template <uint32_t OFF>
+template <int OFF>
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "n"(OFF) : "memory");
     return r;
 }
-template <uint32_t OFF>
+template <int OFF>
 __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0+%5], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "n"(OFF) : "memory");
+}
+// predicated store (no branch): executed iff flag != 0
+template <int OFF>
+__device__ __forceinline__ void sts_f4_if(uint32_t addr, float4 v, uint32_t flag) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.f32 [%0+%6], {%1, %2, %3, %4};\n\t}" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(flag), "n"(OFF) : "memory");
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t r;
@@ -112,7 +117,7 @@ struct V2Lane {
     float* lastcol_ptr;
 };
 
-// One step (two query positions) of a row, phase U of the ring.
+// Two steps (four query positions) of a row from step t0 (even).
 // A ring cell is (value, dm) per position: dm = min(value + gap, gapm_val + gapext) is the deletion candidate the
 // cell offers to every successor row (deletion(), mesh.h:305-330, evaluated once by the row it leaves from instead
 // of once per edge); the row's own gapm_val is the dm of its last predecessor ("last predecessor wins").
@@ -127,131 +132,139 @@ struct V2Lane {
 // (common.cuh), all flags against one final value so that the minimum itself is a chain of FMNMX3.
 // E carries gaps_val of the row's next cell: (m,s)'s insertion candidate is fixed when (m,s-1) is finished;
 // extension iff gaps_val == value (mesh.h:340-349).
-// EDGES: some lane of the warp may start (s == 0) or end (s == Lq-1) in this block of steps.
-template <int NPW, bool EDGES, int U>
-__device__ __forceinline__ void v2_step(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
-                                        const uint32_t qb, float (&pvp)[NPW], float& E, uint32_t& w16) {
+// qb: the row's match bits, bit i = comp(node, query position of cell i of these two steps); four are consumed.
+// EDGES: some lane of the warp may start (s == 0) or end (s == Lq-1) in these steps.
+// The loop over steps is kept this short on purpose: a body unrolled over the 8 ring phases (every offset an
+// immediate) measured 3x slower, the warps of a CTA run up to five differently specialised bodies and 5-13 KB
+// each do not fit the instruction caches (ncu: 15 % of the stall samples "no instruction", the rest waiting at
+// the barrier for the warp that had none).
+template <int NPW, bool EDGES>
+__device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
+                                              const uint32_t qb, float (&pvp)[NPW], float& E) {
     const float INF = __int_as_float(0x7f800000);
     constexpr bool RAW = v2_raw_cells(NPW);
-    float4 c[NPW];
+    uint32_t tbw = 0;
+    // ring phase of the first step: 0, 2, 4 or 6; the second step is one slot further (an immediate, no wrap)
+    const uint32_t x0 = (t0 & (R - 1)) * SLOT2;
+    uint32_t ak[NPW];
 #pragma unroll
-    for (int k = 0; k < NPW; k++) c[k] = lds_f4<U * SLOT2>(L.pk[k]);
-    if (EDGES) {
-        // s == 0 (mesh.h:294-301,469-473): value starts from 1, no insertion, no match. E = 1 supplies that 1 and
-        // makes the next insertion an extension exactly when value(m,0) == 1 (gaps_val == value)
-        if (t0 + U == L.tf) {
-            E = 1.0f;
+    for (int k = 0; k < NPW; k++) ak[k] = L.pk[k] + x0;
+    const uint32_t aw = L.wadr + x0;
+    // main copy (index u, read by consumers whose phase wrapped): phases LBASE..R-1; mirror (index u + R): phases 0..R-2
+    static_assert(LBASE == 4 && R == 8, "the store predicates below are written for 8 phases, main copy from phase 4 on");
+    const uint32_t p_main = t0 & 4u, p_mir1 = (t0 & 6u) ^ 6u;
 #pragma unroll
-            for (int k = 0; k < NPW; k++) pvp[k] = INF;
-        }
-    }
-    const float sc0 = (qb & (1u << (2 * U))) ? L.msw : L.mmsw;       // comp(): the IUPAC masks intersect
-    const float sc1 = (qb & (2u << (2 * U))) ? L.msw : L.mmsw;
-    float out[4];
-    float acc = 0.f;        // RAW: the two cells' flag bytes as a small integer held in a float
-    uint32_t code = 0;      // !RAW: the two cells' codes
+    for (int v = 0; v < 2; v++) {
+        const uint32_t t = t0 + v;
+        float4 c[NPW];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float del[NPW], mt[NPW];
+        for (int k = 0; k < NPW; k++) c[k] = v ? lds_f4<(int)SLOT2>(ak[k]) : lds_f4<0>(ak[k]);
+        if (EDGES) {
+            // s == 0 (mesh.h:294-301,469-473): value starts from 1, no insertion, no match. E = 1 supplies that 1 and
+            // makes the next insertion an extension exactly when value(m,0) == 1 (gaps_val == value)
+            if (t == L.tf) {
+                E = 1.0f;
 #pragma unroll
-        for (int k = 0; k < NPW; k++) {
-            del[k] = h ? c[k].w : c[k].y;                                  // deletion via slot k (mesh.h:305-330)
-            mt[k] = __fadd_rn(h ? c[k].x : pvp[k], h ? sc1 : sc0);         // match via slot k   (mesh.h:360-374)
-        }
-        const float gmin = del[NPW - 1];                                    // last predecessor wins
-        float value;
-        if (RAW) {
-            // minimum of all candidates, the insertion (latest operand to arrive) in the last FMNMX3
-            if (NPW == 1) value = fmin3(del[0], mt[0], E);
-            else if (NPW == 2) value = fmin3(fmin3(del[0], del[1], mt[0]), mt[1], E);
-            else value = fmin3(fmin3(fmin3(del[0], del[1], del[2]), mt[0], mt[1]), mt[2], E);
-            const float sh = h ? 256.f : 1.f;
-#pragma unroll
-            for (int k = 0; k < NPW; k++) acc = fmaf(fset_eq(del[k], value), (float)(TBR_DEL << k) * sh, acc);
-#pragma unroll
-            for (int k = 0; k + 1 < NPW; k++) acc = fmaf(fset_eq(mt[k], value), (float)(TBR_MATCH << k) * sh, acc);
-        } else {
-            // reference order with its strict / non-strict comparisons
-            value = del[0];
-            uint32_t cd = TB_SRC_DEL;
-#pragma unroll
-            for (int k = 1; k < NPW; k++) {
-                const bool win = del[k] < value;
-                value = fminf(value, del[k]);
-                cd = win ? (TB_SRC_DEL | (k << 2)) : cd;
+                for (int k = 0; k < NPW; k++) pvp[k] = INF;
             }
-            const bool iwin = E <= value;
-            value = fminf(value, E);
-            cd = iwin ? TB_SRC_INS : cd;
+        }
+        const float sc0 = (qb & (1u << (2 * v))) ? L.msw : L.mmsw;       // comp(): the IUPAC masks intersect
+        const float sc1 = (qb & (2u << (2 * v))) ? L.msw : L.mmsw;
+        float out[4];
+        float acc = 0.f;        // RAW: the two cells' flag bytes as a small integer held in a float
+        uint32_t code = 0;      // !RAW: the two cells' codes
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            float del[NPW], mt[NPW];
 #pragma unroll
             for (int k = 0; k < NPW; k++) {
-                const bool win = mt[k] < value;
-                value = fminf(value, mt[k]);
-                cd = win ? (TB_SRC_MATCH | (k << 2)) : cd;
+                del[k] = h ? c[k].w : c[k].y;                                  // deletion via slot k (mesh.h:305-330)
+                mt[k] = __fadd_rn(h ? c[k].x : pvp[k], h ? sc1 : sc0);         // match via slot k   (mesh.h:360-374)
             }
-            code |= cd << (8 * h);
+            const float gmin = del[NPW - 1];                                    // last predecessor wins
+            float value;
+            if (RAW) {
+                // minimum of all candidates, the insertion (latest operand to arrive) in the last FMNMX3
+                if (NPW == 1) value = fmin3(del[0], mt[0], E);
+                else if (NPW == 2) value = fmin3(fmin3(del[0], del[1], mt[0]), mt[1], E);
+                else value = fmin3(fmin3(fmin3(del[0], del[1], del[2]), mt[0], mt[1]), mt[2], E);
+                const float sh = h ? 256.f : 1.f;
+#pragma unroll
+                for (int k = 0; k < NPW; k++) acc = fmaf(fset_eq(del[k], value), (float)(TBR_DEL << k) * sh, acc);
+#pragma unroll
+                for (int k = 0; k + 1 < NPW; k++) acc = fmaf(fset_eq(mt[k], value), (float)(TBR_MATCH << k) * sh, acc);
+            } else {
+                // reference order with its strict / non-strict comparisons
+                value = del[0];
+                uint32_t cd = TB_SRC_DEL;
+#pragma unroll
+                for (int k = 1; k < NPW; k++) {
+                    const bool win = del[k] < value;
+                    value = fminf(value, del[k]);
+                    cd = win ? (TB_SRC_DEL | (k << 2)) : cd;
+                }
+                const bool iwin = E <= value;
+                value = fminf(value, E);
+                cd = iwin ? TB_SRC_INS : cd;
+#pragma unroll
+                for (int k = 0; k < NPW; k++) {
+                    const bool win = mt[k] < value;
+                    value = fminf(value, mt[k]);
+                    cd = win ? (TB_SRC_MATCH | (k << 2)) : cd;
+                }
+                code |= cd << (8 * h);
+            }
+            // ---- what this cell offers: the deletion candidate of its successors and the row's next insertion
+            const float vgp = __fadd_rn(value, gp);
+            const float ggpe = __fadd_rn(gmin, gpe);
+            const float egpe = __fadd_rn(E, gpe);
+            const bool ext = (E == value);                                      // gaps_val == value (mesh.h:340-349)
+            if (RAW) {
+                acc = fmaf(fset_lt(vgp, ggpe), (float)TBR_OB * (h ? 256.f : 1.f), acc);
+                acc = ext ? __fadd_rn(acc, (float)TBR_INS * (h ? 256.f : 1.f)) : acc;
+            } else {
+                code |= (vgp < ggpe) ? (32u << (8 * h)) : 0u;
+            }
+            E = ext ? egpe : vgp;
+            out[2 * h] = value;
+            out[2 * h + 1] = fminf(vgp, ggpe);
         }
-        // ---- what this cell offers: the deletion candidate of its successors and the row's next insertion
-        const float vgp = __fadd_rn(value, gp);
-        const float ggpe = __fadd_rn(gmin, gpe);
-        const float egpe = __fadd_rn(E, gpe);
-        const bool ext = (E == value);                                      // gaps_val == value (mesh.h:340-349)
-        if (RAW) {
-            acc = fmaf(fset_lt(vgp, ggpe), (float)TBR_OB * (h ? 256.f : 1.f), acc);
-            acc = ext ? __fadd_rn(acc, (float)TBR_INS * (h ? 256.f : 1.f)) : acc;
+#pragma unroll
+        for (int k = 0; k < NPW; k++) pvp[k] = c[k].z;
+        const float4 o4 = make_float4(out[0], out[1], out[2], out[3]);
+        if (v == 0) {
+            sts_f4_if<-(int)(LBASE * SLOT2)>(aw, o4, p_main);
+            sts_f4<(int)(DP_MAXD * SLOT2)>(aw, o4);
         } else {
-            code |= (vgp < ggpe) ? (32u << (8 * h)) : 0u;
+            sts_f4_if<(int)SLOT2 - (int)(LBASE * SLOT2)>(aw, o4, p_main);
+            sts_f4_if<(int)SLOT2 + (int)(DP_MAXD * SLOT2)>(aw, o4, p_mir1);
         }
-        E = ext ? egpe : vgp;
-        out[2 * h] = value;
-        out[2 * h + 1] = fminf(vgp, ggpe);
+        if (EDGES) {
+            if (t == L.tl) *L.lastcol_ptr = L.odd ? out[0] : out[2];
+        }
+        __syncthreads();
+        // the integer sits in the low mantissa bits of acc + 2^23 (acc < 2^16, exact)
+        const uint32_t w16 = RAW ? __float_as_uint(__fadd_rn(acc, 8388608.0f)) : code;
+        tbw = v ? __byte_perm(tbw, w16, 0x5410) : w16;
     }
-#pragma unroll
-    for (int k = 0; k < NPW; k++) pvp[k] = c[k].z;
-    const float4 o4 = make_float4(out[0], out[1], out[2], out[3]);
-    if (U >= LBASE) sts_f4<(uint32_t)(U >= LBASE ? U - LBASE : 0) * SLOT2>(L.wadr, o4);     // main copy (read by wrapping consumers)
-    if (U <= R - 2) sts_f4<(uint32_t)(U + DP_MAXD) * SLOT2>(L.wadr, o4);                    // mirror copy
-    if (EDGES) {
-        if (t0 + U == L.tl) *L.lastcol_ptr = L.odd ? out[0] : out[2];
-    }
-    __syncthreads();
-    // the integer sits in the low mantissa bits of acc + 2^23 (acc < 2^16, exact)
-    w16 = RAW ? __float_as_uint(__fadd_rn(acc, 8388608.0f)) : code;
+    return tbw;
 }
 
-// Eight steps (one turn of the ring) from step t0 (a multiple of 8); returns the 16 traceback bytes.
-template <int NPW, bool EDGES>
-__device__ __forceinline__ uint4 v2_block(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
-                                          float (&pvp)[NPW], float& E) {
-    // the row's match bits for the 16 positions of this block: bit i = comp(node, query[2*(t0 - soff) + i])
-    const int bp = 2 * ((int)t0 - L.soff) + QB_PAD;
+// the row's match bits from step t (any parity) on: bit i = comp(node, query[2 * (t - soff) + i]), 32 positions
+template <int NPW>
+__device__ __forceinline__ uint32_t v2_qbits(const V2Lane<NPW>& L, uint32_t t) {
+    const int bp = 2 * ((int)t - L.soff) + QB_PAD;
     const uint32_t wa = L.qaddr + ((uint32_t)bp >> 5) * 4u;
-    const uint32_t qb = __funnelshift_r(lds_u32(wa), lds_u32(wa + 4u), (uint32_t)bp & 31u);
-    uint32_t w[8];
-    v2_step<NPW, EDGES, 0>(L, gp, gpe, t0, qb, pvp, E, w[0]);
-    v2_step<NPW, EDGES, 1>(L, gp, gpe, t0, qb, pvp, E, w[1]);
-    v2_step<NPW, EDGES, 2>(L, gp, gpe, t0, qb, pvp, E, w[2]);
-    v2_step<NPW, EDGES, 3>(L, gp, gpe, t0, qb, pvp, E, w[3]);
-    v2_step<NPW, EDGES, 4>(L, gp, gpe, t0, qb, pvp, E, w[4]);
-    v2_step<NPW, EDGES, 5>(L, gp, gpe, t0, qb, pvp, E, w[5]);
-    v2_step<NPW, EDGES, 6>(L, gp, gpe, t0, qb, pvp, E, w[6]);
-    v2_step<NPW, EDGES, 7>(L, gp, gpe, t0, qb, pvp, E, w[7]);
-    return make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410),
-                      __byte_perm(w[4], w[5], 0x5410), __byte_perm(w[6], w[7], 0x5410));
-}
-
-__device__ __forceinline__ void v2_idle_block() {
-#pragma unroll
-    for (int u = 0; u < 8; u++) __syncthreads();
+    return __funnelshift_r(lds_u32(wa), lds_u32(wa + 4u), (uint32_t)bp & 31u);
 }
 
 // All steps of one group for a warp whose rows have <= NPW predecessors.
-// [e0, e1) = blocks in which some row of the warp is inside the query; outside of them the warp only keeps the
+// [e0, e1) = steps at which some row of the warp is inside the query; outside of them the warp only keeps the
 // barriers (nothing it would publish is read: a consumer's window starts after its predecessors' and ends after
-// theirs). [c0, c1) = blocks in which every row of the warp is strictly inside (no start, no end): no edge tests.
+// theirs). [c0, c1) = steps at which every row of the warp is strictly inside (no start, no end): no edge tests.
 template <int NPW>
 __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t steps8,
-                                         const bool valid, uint4* tbl) {
+                                         const bool valid, uint32_t* tbl) {
     float pvp[NPW];
 #pragma unroll
     for (int k = 0; k < NPW; k++) pvp[k] = 0.f;
@@ -260,24 +273,45 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
     const uint32_t w_last = __reduce_max_sync(0xffffffffu, valid ? L.tl : 0u);
     const uint32_t i_first = __reduce_max_sync(0xffffffffu, valid ? L.tf : 0u) + 1u;   // every row has started
     const uint32_t i_last = __reduce_min_sync(0xffffffffu, L.tl);                       // first step at which a row ends
-    const uint32_t e0 = min(w_first & ~7u, steps8);
-    const uint32_t e1 = min((w_last & ~7u) + 8u, steps8);
-    uint32_t c0 = (i_first + 7u) & ~7u, c1 = i_last & ~7u;      // blocks [t0, t0+8) with i_first <= t0 and t0 + 7 < i_last
+    const uint32_t e0 = min(w_first & ~1u, steps8);
+    const uint32_t e1 = min((w_last & ~1u) + 2u, steps8);
+    uint32_t c0 = (i_first + 1u) & ~1u, c1 = i_last & ~1u;      // pairs [t0, t0+2) with i_first <= t0 and t0 + 1 < i_last
     if (c0 >= c1 || c0 < e0 || c1 > e1) c0 = c1 = e1;
-    for (uint32_t t0 = 0; t0 < e0; t0 += 8) v2_idle_block();
+    for (uint32_t t0 = 0; t0 < e0; t0 += 2) { __syncthreads(); __syncthreads(); }
+    // three phases: edge steps [e0, c0), inner steps [c0, c1), edge steps [c1, e1); the match bits are fetched for 16
+    // steps at a time (32 query positions) and consumed from a register, four per pair of steps
+    uint32_t* tbp = tbl + (uint64_t)(e0 >> 1) * T;
 #pragma unroll 1
-    for (uint32_t t0 = e0; t0 < c0; t0 += 8) tbl[(uint64_t)(t0 >> 3) * T] = v2_block<NPW, true>(L, gp, gpe, t0, pvp, E);
+    for (int ph = 0; ph < 3; ph++) {
+        uint32_t t0 = ph == 0 ? e0 : (ph == 1 ? c0 : c1);
+        const uint32_t b = ph == 0 ? c0 : (ph == 1 ? c1 : e1);
+        while (t0 < b) {
+            const uint32_t stop = min(b, (t0 & ~15u) + 16u);
+            uint32_t qb = v2_qbits<NPW>(L, t0);
+            if (ph == 1) {
 #pragma unroll 1
-    for (uint32_t t0 = c0; t0 < c1; t0 += 8) tbl[(uint64_t)(t0 >> 3) * T] = v2_block<NPW, false>(L, gp, gpe, t0, pvp, E);
+                for (; t0 < stop; t0 += 2) {
+                    *tbp = v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E);
+                    tbp += T;
+                    qb >>= 4;
+                }
+            } else {
 #pragma unroll 1
-    for (uint32_t t0 = c1; t0 < e1; t0 += 8) tbl[(uint64_t)(t0 >> 3) * T] = v2_block<NPW, true>(L, gp, gpe, t0, pvp, E);
-    for (uint32_t t0 = e1; t0 < steps8; t0 += 8) v2_idle_block();
+                for (; t0 < stop; t0 += 2) {
+                    *tbp = v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E);
+                    tbp += T;
+                    qb >>= 4;
+                }
+            }
+        }
+    }
+    for (uint32_t t0 = e1; t0 < steps8; t0 += 2) { __syncthreads(); __syncthreads(); }
 }
 
 template <int NPW>
 __device__ __forceinline__ void v2_dispatch(const MeshArgs& A, uint32_t sring, uint32_t sqb, const uint32_t* ck, uint32_t rcol,
                                             bool valid, uint32_t np, int soff, uint32_t Lq, uint32_t plane, float w,
-                                            uint32_t steps8, float* lastcol_ptr, uint4* tbl) {
+                                            uint32_t steps8, float* lastcol_ptr, uint32_t* tbl) {
     V2Lane<NPW> L;
 #pragma unroll
     for (int k = 0; k < NPW; k++) L.pk[k] = sring + ck[k];
@@ -411,10 +445,10 @@ __device__ __forceinline__ void v2_query(const MeshArgs& A, const GraphHdr& h, u
             const uint32_t npw = max(1u, __reduce_max_sync(0xffffffffu, np));
             const bool warp_has_rows = __any_sync(0xffffffffu, valid);
             if (valid) A.nshift[io + m] = (uint8_t)((npw - np) | (v2_raw_cells((int)npw) ? TBR_FLAG : 0u));
-            uint4* tbl = reinterpret_cast<uint4*>(tbq + gi.tb_off) + tid;   // this lane's 16 bytes of block 0
+            uint32_t* tbl = tbq + gi.tb_off + tid;   // this lane's word of step pair 0
             __syncthreads();  // matches the loader's prologue barrier
             if (!warp_has_rows) {
-                for (uint32_t t0 = 0; t0 < steps8; t0 += 8) v2_idle_block();
+                for (uint32_t t = 0; t < steps8; t++) __syncthreads();   // a warp without rows only keeps the barriers
             } else {
                 // shared offset of predecessor slot k at phase 0: column * 16 + (DP_MAXD - distance) slots
                 uint32_t ck[NPF];
