@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsina_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("SINA_B200_LIB", "libsina_b200.so"))   # SINA_B200_LIB: an experimental build next to the product library (tools/)
 
 # every symbol include/sina_b200.h declares
 EXPORTS = [

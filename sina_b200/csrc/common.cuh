@@ -41,12 +41,17 @@ constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predec
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
 constexpr int DP_BLOCK = 256;                // threads per DP CTA = columns of the shared-memory ring
-constexpr int DP_CTAS_PER_SM = 4;            // resident DP CTAs per SM the kernels are compiled for (register cap)
+#ifndef DP_CTAS
+#define DP_CTAS 4
+#endif
+constexpr int DP_CTAS_PER_SM = DP_CTAS;            // resident DP CTAs per SM the kernels are compiled for (register cap)
 constexpr int DP_T = 224;                    // node rows per DP group (compute lanes, one row each)
 constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
 constexpr int DP_RING = 8;                   // ring depth (time slots) of the shared-memory row window
 constexpr int DP_MAXD = 4;                   // v2 kernel: largest column-rank distance of a predecessor served by the ring
                                              // (the generic kernel serves DP_RING - 2); farther ones go through ghosts
+constexpr int DP_RS2 = 257;                  // v2 kernel: 16-byte cells per time slot of the ring (one bank group more than a multiple of 8)
+constexpr uint32_t DP_COL_PAD = 254, DP_COL_EDGE = 255;   // v2 kernel: constant ring columns (mesh.cu)
 constexpr int GHOST_PF = 2;                  // steps a ghost requests its data ahead of publishing it
 constexpr int GHOST_LEAD = GHOST_PF + 2;     // a ghost trails a source row of its own group by >= this many column ranks
 static_assert(GHOST_LEAD <= DP_MAXD, "an in-group edge too long for the ring must be long enough for a ghost");
@@ -233,6 +238,7 @@ struct Session {
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
+    int bankplan = 1;                // SG_BANKPLAN=0: identity ring columns instead of the bank-aware plan (bankplan_kernel)
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

@@ -54,12 +54,12 @@ constexpr int QPAD = 256;      // v1: padding either side of the query bytes in 
 // never read and are not allocated: NSLOT2 = R + DP_MAXD - 1 slots. The slot stride is 257 cells, i.e. one 16-byte
 // bank group more than a multiple of eight, which rotates the bank groups between slots.
 // ====================================================================================================
-constexpr int RS2 = 257;
+constexpr int RS2 = DP_RS2;
 constexpr uint32_t SLOT2 = 16u * RS2;
 constexpr int NSLOT2 = R + DP_MAXD - 1;
 constexpr int LBASE = R - DP_MAXD;            // first linear slot index that exists
 constexpr uint32_t RING2_BYTES = SLOT2 * NSLOT2;
-constexpr uint32_t COL_PAD = 254, COL_EDGE = 255;
+constexpr uint32_t COL_PAD = DP_COL_PAD, COL_EDGE = DP_COL_EDGE;
 constexpr int QB_PAD = 512;                   // zero bits either side of the query in the match-bit planes
 constexpr int QB_BASE_PLANES = 15;            // planes 15..18: scratch (one plane per base bit A G C U)
 constexpr int QB_PLANES = 19;
@@ -334,7 +334,6 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
     const uint32_t j = threadIdx.x - T;
     const uint32_t Lq = h.qlen, npairs = (Lq + 1u) >> 1;
     const uint64_t io = (uint64_t)ql * A.icap;
-    float4* ring = reinterpret_cast<float4*>(smem);
     float4* spill = reinterpret_cast<float4*>(A.spill + h.spill_off);   // rows of npairs cells
     // ghost
     const bool is_ghost = j < gi.n_ghost;
@@ -359,53 +358,70 @@ __device__ __forceinline__ void v2_loader_group(const MeshArgs& A, unsigned char
     }
     float rmin = 0.f;
     uint32_t rarg = 0;
-    auto gload = [&](int t) -> float4 {  // what the ghost publishes at step t: query positions 2(t - gsoff), +1
-        const int jj = t - gsoff;
-        if (is_ghost && jj >= 0 && jj < (int)npairs) return __ldcg(&gsrc[jj]);
-        return make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    auto gstore = [&](uint32_t t, float4 c) {
-        const uint32_t u = t & (R - 1);
-        if (u >= (uint32_t)LBASE) ring[(u - LBASE) * RS2 + threadIdx.x] = c;
-        if (u <= (uint32_t)R - 2) ring[(u + DP_MAXD) * RS2 + threadIdx.x] = c;
-    };
-    // prologue = step -1 (a ghost with soff -1 must have its first cell in the ring before step 0); afterwards the
-    // data of step t + GHOST_PF is requested at step t, so the L2 latency never sits between two barriers
-    // (GHOST_LEAD = GHOST_PF + 2 keeps that request behind the source row's spill store).
+    const uint32_t sring = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t gaddr = sring + threadIdx.x * 16u;      // the ghost's ring column (= this thread's), linear slot LBASE
+    const uint32_t waddr = sring + wcol * 16u;             // the drained row's ring column
+    float4* const sdst = spill + (uint64_t)(wsr >= 0 ? wsr : 0) * npairs;
+    const bool wspill = is_writer && wsr >= 0;
+    const bool any_last = __any_sync(0xffffffffu, is_writer && wlast);   // uniform: groups without last nodes skip the minimum
+    // This warp is alone in its role and every row warp waits for it at each step's barrier: its step is kept
+    // straight-line and predicated (a first version with per-lane branches was the slowest warp of the CTA: ncu
+    // showed it busy 83 % of the time against 42 % for the row warps).
+    // A ghost publishes at step t the cell of the query positions 2(t - gsoff), +1 and asks for the cell of step
+    // t + GHOST_PF at step t, so the L2 latency never sits between two barriers (GHOST_LEAD = GHOST_PF + 2 keeps that
+    // request behind the source row's spill store). Cells outside the query are never read by a consumer.
     float4 pf[GHOST_PF];
-    {
-        const float4 c = gload(-1);
-        if (is_ghost) gstore((uint32_t)(-1), c);
-    }
 #pragma unroll
-    for (int k = 0; k < GHOST_PF; k++) pf[k] = gload(k);
+    for (int k = 0; k < GHOST_PF; k++) pf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    {   // prologue = step -1 (phase 7, main copy): a ghost with soff -1 must have its first cell in the ring before step 0
+        const int jj = -1 - gsoff;
+        if (is_ghost && jj >= 0 && jj < (int)npairs) sts_f4<(int)((R - 1 - LBASE) * SLOT2)>(gaddr, __ldcg(&gsrc[jj]));
+    }
+    int gj = -gsoff;                        // pair index of the ghost cell requested next
+#pragma unroll
+    for (int k = 0; k < GHOST_PF; k++, gj++)
+        if (is_ghost && (uint32_t)gj < npairs) pf[k] = __ldcg(&gsrc[gj]);
     __syncthreads();
-    auto drain = [&](uint32_t t) {  // what the writer's row published at step t-1
-        const int jw = (int)t - 1 - wsoff;
-        if (is_writer && jw >= 0 && jw < (int)npairs) {
-            const uint32_t u = (t - 1) & (R - 1);
-            const float4 c = ring[(u <= (uint32_t)R - 2 ? u + DP_MAXD : u - LBASE) * RS2 + wcol];
-            if (wsr >= 0) __stcg(&spill[(uint64_t)wsr * npairs + jw], c);
-            if (wlast) {
-                const uint32_t s0 = 2u * (uint32_t)jw;
-                if (s0 == 0 || c.x < rmin) { rmin = c.x; rarg = s0; }
-                if (s0 + 1 < Lq && c.z < rmin) { rmin = c.z; rarg = s0 + 1; }
-            }
+    int wj = -1 - wsoff;                    // pair index the drained row published at the previous step
+    // what the writer's row published at step t-1: spill it (rows with far successors), track the row minimum (last nodes)
+    auto drain = [&](uint32_t xd) {
+        const bool on = is_writer && (uint32_t)wj < npairs;
+        const float4 c = lds_f4<0>(waddr + xd);
+        if (on && wspill) __stcg(&sdst[wj], c);
+        if (any_last) {
+            const uint32_t s0 = 2u * (uint32_t)wj;
+            const bool l0 = on && wlast && (s0 == 0 || c.x < rmin);
+            rmin = l0 ? c.x : rmin; rarg = l0 ? s0 : rarg;
+            const bool l1 = on && wlast && s0 + 1 < Lq && c.z < rmin;
+            rmin = l1 ? c.z : rmin; rarg = l1 ? s0 + 1 : rarg;
         }
+        wj++;
     };
-    static_assert(8 % GHOST_PF == 0, "the prefetch queue is rotated by unrolling");
-    for (uint32_t t0 = 0; t0 < steps8; t0 += GHOST_PF) {
-#pragma unroll
-        for (int u = 0; u < GHOST_PF; u++) {
-            const uint32_t t = t0 + u;
-            const float4 c = pf[u];
-            pf[u] = gload((int)t + GHOST_PF);
-            if (is_ghost) gstore(t, c);
-            if (t >= 1) drain(t);
-            __syncthreads();
-        }
+    static_assert(GHOST_PF == 2, "the prefetch queue is rotated by the two-step unrolling below");
+#pragma unroll 1
+    for (uint32_t t0 = 0; t0 < steps8; t0 += 2) {
+        const uint32_t ph = t0 & (R - 1);                       // 0, 2, 4 or 6
+        const uint32_t x0 = ph * SLOT2;
+        const uint32_t gm = is_ghost ? 1u : 0u;
+        const uint32_t p_main = gm & (ph >> 2), p_mir1 = gm & (ph != 6u ? 1u : 0u);
+        // the cell of step t0 - 1: mirror copy of phase ph - 1, or the main copy of phase 7
+        const uint32_t xd0 = ph ? x0 + (uint32_t)(DP_MAXD - 1) * SLOT2 : (uint32_t)(R - 1 - LBASE) * SLOT2;
+        // ---- step t0
+        sts_f4_if<-(int)(LBASE * SLOT2)>(gaddr + x0, pf[0], p_main);
+        sts_f4_if<(int)(DP_MAXD * SLOT2)>(gaddr + x0, pf[0], gm);
+        if (is_ghost && (uint32_t)gj < npairs) pf[0] = __ldcg(&gsrc[gj]);
+        gj++;
+        drain(xd0);
+        __syncthreads();
+        // ---- step t0 + 1
+        sts_f4_if<(int)SLOT2 - (int)(LBASE * SLOT2)>(gaddr + x0, pf[1], p_main);
+        sts_f4_if<(int)SLOT2 + (int)(DP_MAXD * SLOT2)>(gaddr + x0, pf[1], p_mir1);
+        if (is_ghost && (uint32_t)gj < npairs) pf[1] = __ldcg(&gsrc[gj]);
+        gj++;
+        drain(x0 + (uint32_t)DP_MAXD * SLOT2);                  // the cell of step t0: mirror copy of phase ph
+        __syncthreads();
     }
-    drain(steps8);
+    drain((uint32_t)(R - 1 - LBASE) * SLOT2);                   // steps8 is a multiple of 8: the last step's phase is 7
     if (is_writer && wlast) { A.rowmin[io + wnode] = rmin; A.rowarg[io + wnode] = rarg; }
 }
 
