@@ -224,9 +224,14 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
                 else out = TB_SRC_MATCH | (((sh & 0x7fu) + np - 1u) << 8);
                 return out | ((c >> 7) << 2);
             }
-            uint32_t src = c & 3u;
-            if (np == 0 && src != TB_SRC_INS) src = TB_SRC_NONE;
-            return src | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
+            // index cell (common.cuh): 0 insertion, 1..slots deletion, slots+1.. match
+            const uint32_t idx = c & 31u, slots = (sh & 0x7fu) + np;
+            uint32_t out = 0;
+            if (idx == 0) out = TB_SRC_INS;
+            else if (np == 0) out = TB_SRC_NONE;
+            else if (idx <= slots) out = TB_SRC_DEL | ((idx - 1u) << 8);
+            else out = TB_SRC_MATCH | ((idx - 1u - slots) << 8);
+            return out | ((c >> 7) << 2);
         }
         const uint32_t t = s + (a.y & 0xffffu);
         if (wide) return (raw >> (16 * (t & 1))) & 0xffffu;

@@ -78,6 +78,8 @@ constexpr uint32_t TB_SRC_NONE = 0, TB_SRC_DEL = 1, TB_SRC_INS = 2, TB_SRC_MATCH
 // the flags say (its deletion candidate is the constant that stands for the initial value). The insertion-opened
 // flag is not stored: it is "the source of (m, s-1) is not an insertion" (see backtrack.cu).
 //   [2:0] deletion via slot k equals  [3] insertion equals  [5:4] match via slot k equals (k < slots-1)  [7] ob
+// index u8 (rows of v2 warps specialised on 4..8 slots): [4:0] index of the source = of the first candidate equal to the
+// value in the order insertion (0), deletion slots (1..slots), match slots (slots+1..2*slots)  [7] ob
 constexpr uint32_t TBR_DEL = 1, TBR_INS = 8, TBR_MATCH = 16, TBR_OB = 128;
 constexpr uint32_t TBR_FLAG = 0x80;          // in nshift[]: the row's cells are raw
 __host__ __device__ constexpr bool v2_raw_cells(int npw) { return npw <= 3; }
@@ -238,7 +240,7 @@ struct Session {
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
-    int bankplan = 1;                // SG_BANKPLAN=0: identity ring columns instead of the bank-aware plan (bankplan_kernel)
+    int bankplan = 0;                // SG_BANKPLAN=1 (+n: n swap sweeps): bank-aware ring columns (bankplan_kernel) instead of identity columns
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

@@ -104,6 +104,24 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return r;
 }
 
+// minimum of a[0..N) and e with FMNMX3s, e (the operand that arrives last) in the final one
+template <int N>
+__device__ __forceinline__ float min_with(const float (&a)[N], float e) {
+    if constexpr (N == 1) return fminf(a[0], e);
+    else if constexpr (N == 2) return fmin3(a[0], a[1], e);
+    else {
+        constexpr int M = (N + 2) / 3;
+        float b[M];
+#pragma unroll
+        for (int j = 0; j < M; j++) {
+            if (3 * j + 2 < N) b[j] = fmin3(a[3 * j], a[3 * j + 1], a[3 * j + 2]);
+            else if (3 * j + 1 < N) b[j] = fminf(a[3 * j], a[3 * j + 1]);
+            else b[j] = a[3 * j];
+        }
+        return min_with<M>(b, e);
+    }
+}
+
 // Per-lane constants of the specialised step.
 template <int NPW>
 struct V2Lane {
@@ -171,8 +189,7 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
         const float sc0 = (qb & (1u << (2 * v))) ? L.msw : L.mmsw;       // comp(): the IUPAC masks intersect
         const float sc1 = (qb & (2u << (2 * v))) ? L.msw : L.mmsw;
         float out[4];
-        float acc = 0.f;        // RAW: the two cells' flag bytes as a small integer held in a float
-        uint32_t code = 0;      // !RAW: the two cells' codes
+        float acc = 0.f;        // the two cells' traceback bytes as a small integer held in a float
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             float del[NPW], mt[NPW];
@@ -194,37 +211,27 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
 #pragma unroll
                 for (int k = 0; k + 1 < NPW; k++) acc = fmaf(fset_eq(mt[k], value), (float)(TBR_MATCH << k) * sh, acc);
             } else {
-                // reference order with its strict / non-strict comparisons
-                value = del[0];
-                uint32_t cd = TB_SRC_DEL;
+                // wider rows: the cell records the INDEX of the source, i.e. of the first candidate equal to the value
+                // in the order insertion (0), deletion slots (1..NPW), match slots (NPW+1..2 NPW). key = index if equal,
+                // 64 otherwise; the minimum of the keys is the index (shallow FMNMX3 trees instead of a chain of
+                // compare / select pairs: these warps are the slowest of the CTA and every other warp waits for them)
+                float cand[2 * NPW];
 #pragma unroll
-                for (int k = 1; k < NPW; k++) {
-                    const bool win = del[k] < value;
-                    value = fminf(value, del[k]);
-                    cd = win ? (TB_SRC_DEL | (k << 2)) : cd;
-                }
-                const bool iwin = E <= value;
-                value = fminf(value, E);
-                cd = iwin ? TB_SRC_INS : cd;
+                for (int k = 0; k < NPW; k++) { cand[k] = del[k]; cand[NPW + k] = mt[k]; }
+                value = min_with<2 * NPW>(cand, E);
+                float key[2 * NPW];
 #pragma unroll
-                for (int k = 0; k < NPW; k++) {
-                    const bool win = mt[k] < value;
-                    value = fminf(value, mt[k]);
-                    cd = win ? (TB_SRC_MATCH | (k << 2)) : cd;
-                }
-                code |= cd << (8 * h);
+                for (int k = 0; k < 2 * NPW; k++) key[k] = fmaf(fset_eq(cand[k], value), (float)(k + 1) - 64.f, 64.f);
+                const float idx = min_with<2 * NPW>(key, fmaf(fset_eq(E, value), -64.f, 64.f));
+                acc = fmaf(idx, h ? 256.f : 1.f, acc);
             }
             // ---- what this cell offers: the deletion candidate of its successors and the row's next insertion
             const float vgp = __fadd_rn(value, gp);
             const float ggpe = __fadd_rn(gmin, gpe);
             const float egpe = __fadd_rn(E, gpe);
             const bool ext = (E == value);                                      // gaps_val == value (mesh.h:340-349)
-            if (RAW) {
-                acc = fmaf(fset_lt(vgp, ggpe), (float)TBR_OB * (h ? 256.f : 1.f), acc);
-                acc = ext ? __fadd_rn(acc, (float)TBR_INS * (h ? 256.f : 1.f)) : acc;
-            } else {
-                code |= (vgp < ggpe) ? (32u << (8 * h)) : 0u;
-            }
+            acc = fmaf(fset_lt(vgp, ggpe), (float)TBR_OB * (h ? 256.f : 1.f), acc);
+            if (RAW) acc = ext ? __fadd_rn(acc, (float)TBR_INS * (h ? 256.f : 1.f)) : acc;
             E = ext ? egpe : vgp;
             out[2 * h] = value;
             out[2 * h + 1] = fminf(vgp, ggpe);
@@ -244,7 +251,7 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
         }
         __syncthreads();
         // the integer sits in the low mantissa bits of acc + 2^23 (acc < 2^16, exact)
-        const uint32_t w16 = RAW ? __float_as_uint(__fadd_rn(acc, 8388608.0f)) : code;
+        const uint32_t w16 = __float_as_uint(__fadd_rn(acc, 8388608.0f));
         tbw = v ? __byte_perm(tbw, w16, 0x5410) : w16;
     }
     return tbw;
@@ -291,14 +298,14 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
             if (ph == 1) {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    *tbp = v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E);
+                    __stcs(tbp, v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E));   // streaming: the traceback must not push the spill rows out of L2
                     tbp += T;
                     qb >>= 4;
                 }
             } else {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    *tbp = v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E);
+                    __stcs(tbp, v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E));
                     tbp += T;
                     qb >>= 4;
                 }
