@@ -3,6 +3,9 @@
 //   graph_kernel                         mseq::mseq column sweep + dag::link + sort + reduce_edges
 //                                        (src/mseq.cpp:47-118, src/graph.h:332-357,451-488, src/align.cpp:399-402)
 //                                        followed by the DP plan (groups, ring/spill classification, arenas)
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sg {
@@ -102,6 +105,7 @@ struct GraphArgs {
     uint32_t* order; uint8_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
     unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
+    uint32_t stab_bytes;   // shared-memory budget of the column table (fast path of steps 2-5)
 };
 
 // running-carry exclusive scan of arr[0..n) (u32, global or shared), in place -> exclusive; returns total
@@ -117,6 +121,66 @@ __device__ uint32_t scan_array_inplace(T* arr, uint32_t n, uint32_t* red) {
     }
     __syncthreads();
     return carry;
+}
+
+
+// ---- per-column helpers of the shared-memory path (one thread per column of the family's column table) ----
+constexpr int GK = 6;   // distinct (local node, predecessor) pairs of a column kept in registers; more take the local-memory path
+// predecessor node of row j's base in column c: the node of the row's previous base (NONE: c holds the row's first base)
+__device__ __forceinline__ uint32_t prev_node(const uint8_t* stab, const uint32_t* scolbase, uint32_t F, uint32_t c, uint32_t j) {
+    uint32_t r = c, pe = 0;
+    while (r > 0) { r--; pe = stab[r * F + j]; if (pe) break; }
+    return pe ? scolbase[r] + pe - 1u : NONE;
+}
+// the column's distinct keys (local node << 24 | predecessor), ascending, into k[GK]; returns their number, or GK + 1
+// if there are more than GK (k is then incomplete)
+__device__ __forceinline__ uint32_t column_keys(const uint8_t* stab, const uint32_t* scolbase, uint32_t F, uint32_t c, uint32_t (&k)[GK]) {
+#pragma unroll
+    for (int i = 0; i < GK; i++) k[i] = NONE;
+    uint32_t nu = 0, last = NONE;
+    const uint8_t* t = stab + c * F;
+    for (uint32_t j = 0; j < F; j++) {
+        const uint32_t e = t[j];
+        if (!e) continue;
+        const uint32_t p = prev_node(stab, scolbase, F, c, j);
+        if (p == NONE) continue;
+        const uint32_t key = ((e - 1u) << 24) | p;
+        if (key == last) continue;            // most rows of a family run through the same pair of nodes
+        last = key;
+        bool dup = false;
+#pragma unroll
+        for (int i = 0; i < GK; i++) dup |= k[i] == key;
+        if (dup) continue;
+        if (nu >= (uint32_t)GK) return GK + 1;
+#pragma unroll
+        for (int i = 0; i < GK; i++) if ((uint32_t)i == nu) k[i] = key;
+        nu++;
+    }
+    // sorting network for 6 keys (unused slots hold NONE = the largest value)
+    static_assert(GK == 6, "sorting network below");
+#define GK_CX(a, b) { const uint32_t lo_ = min(k[a], k[b]), hi_ = max(k[a], k[b]); k[a] = lo_; k[b] = hi_; }
+    GK_CX(0, 5) GK_CX(1, 3) GK_CX(2, 4) GK_CX(1, 2) GK_CX(3, 4) GK_CX(0, 3) GK_CX(2, 5) GK_CX(0, 1) GK_CX(2, 3) GK_CX(4, 5) GK_CX(1, 2) GK_CX(3, 4)
+#undef GK_CX
+    return nu;
+}
+// the same for a column with many distinct pairs: sorted list of distinct keys in local memory; returns their number
+__device__ __noinline__ uint32_t column_keys_many(const uint8_t* stab, const uint32_t* scolbase, uint32_t F, uint32_t c, uint32_t* u) {
+    uint32_t nu = 0;
+    const uint8_t* t = stab + c * F;
+    for (uint32_t j = 0; j < F; j++) {
+        const uint32_t e = t[j];
+        if (!e) continue;
+        const uint32_t p = prev_node(stab, scolbase, F, c, j);
+        if (p == NONE) continue;
+        const uint32_t key = ((e - 1u) << 24) | p;
+        uint32_t y = nu;
+        while (y > 0 && u[y - 1] > key) y--;
+        if (y > 0 && u[y - 1] == key) continue;
+        for (uint32_t z = nu; z > y; z--) u[z] = u[z - 1];
+        u[y] = key;
+        nu++;
+    }
+    return nu;
 }
 
 __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
@@ -198,166 +262,354 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     }
     auto colrank = [&](uint32_t c) -> uint32_t { return wrank[c >> 5] + __popc(bitmap[c >> 5] & ((1u << (c & 31)) - 1u)); };
 
-    // ---- 2. column table: tab[c][j] = base mask of family row j in column rank c
-    for (uint32_t i = tid; i < n_cols * A.fam_cap; i += nt) tab[i] = 0;
-    __syncthreads();
-    // (the column rank of every item is kept in item_node until the nodes exist)
-    for (uint32_t j = wid; j < F; j += nwarp) {
-        const uint64_t a = rowbase[j];
-        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
-        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
-            uint32_t c[4];
-            uint8_t mk[4];
+    uint32_t my_max = 0;
+    uint32_t E = 0, shv_V = 0;
+    // Steps 2-5 (column table, nodes, edges). Fast path: the column table of the family (n_cols x F bytes, ~64 KB for
+    // 40 full-length rows) lives in SHARED memory and the nodes, their per-row local indices and the de-duplicated,
+    // sorted predecessor lists are all derived from it, one thread per column; global memory only sees the item reads
+    // and the final node / edge arrays. (The generic path below keeps tab / tabli / item_node / slot in global
+    // scratch: 3.65 MB of DRAM traffic per query against ~0.4 MB algorithmic, 22 long-scoreboard stalls per issue.)
+    uint8_t* stab = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rowbase + A.fam_cap) + 15u) & ~(uintptr_t)15u);   // [n_cols][F] base masks, then local node index + 1
+    const bool fast = (uint64_t)n_cols * F <= A.stab_bytes && n_cols + 1 <= 2 * words && F <= FAM_CAP_MAX;
+    if (fast) {
+        uint32_t* scolbase = bitmap;   // [n_cols + 1], over the bitmap / rank arrays once the table is filled
+        // ---- 2. column table
+        {
+            uint4* z = reinterpret_cast<uint4*>(stab);
+            const uint32_t nz = (n_cols * F + 15) >> 4;
+            for (uint32_t i = tid; i < nz; i += nt) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        for (uint32_t j = wid; j < F; j += nwarp) {
+            const uint64_t a = rowbase[j];
+            const uint32_t len = famoff[j + 1] - famoff[j];
+            for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+                uint32_t c[4];
+                uint8_t mk[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                c[u] = NONE;
-                if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
+                for (int u = 0; u < 4; u++) {
+                    c[u] = NONE;
+                    if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (c[u] != NONE) stab[colrank(c[u]) * F + j] = mk[u] & 31u;
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (c[u] == NONE) continue;
-                const uint32_t r = colrank(c[u]);
-                tab[(uint64_t)r * A.fam_cap + j] = mk[u] & 31u;
-                item_node[fo + i0 + 32 * u] = r;
+        }
+        __syncthreads();   // bitmap / wrank are dead from here on
+        // ---- 3. nodes: one per (column, IUPAC char incl. case), local order = first family row bringing it
+        //         (mseq.cpp:88-98). Pass A counts per column, pass B writes node arrays and turns the table entries into
+        //         local node index + 1.
+        uint32_t cnt_mine[8];   // nodes of the (up to 8) columns this thread owns: columns tid, tid + nt, ...
+        {
+            uint32_t q8 = 0;
+            for (uint32_t c = tid; c < n_cols; c += nt, q8++) {
+                uint32_t seen = 0, nn = 0;
+                const uint8_t* t = stab + c * F;
+                for (uint32_t j = 0; j < F; j++) { const uint32_t bb = t[j]; if (bb && !((seen >> bb) & 1u)) { seen |= 1u << bb; nn++; } }
+                if (q8 < 8) cnt_mine[q8] = nn;
             }
         }
-    }
-    __syncthreads();
-
-    // ---- 3. nodes: one per (column, IUPAC char incl. case), local order = first family row bringing it
-    //         (mseq.cpp:88-98). Pass A counts per column, pass B writes node arrays.
-    for (uint32_t c = tid; c < n_cols; c += nt) {
-        uint32_t seen = 0, nn = 0;
-        const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
-        for (uint32_t j = 0; j < F; j++) { uint32_t b = t[j]; if (b && !((seen >> b) & 1u)) { seen |= 1u << b; nn++; } }
-        colbase[c] = nn;
-    }
-    __syncthreads();
-    const uint32_t V = scan_array_inplace(colbase, n_cols, red);
-    if (tid == 0) colbase[n_cols] = V;
-    if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
-    uint32_t my_masks = 0;   // IUPAC masks (case ignored) of the nodes this thread creates
-    if (tid == 0) shv[4] = 0;
-    for (uint32_t c = tid; c < n_cols; c += nt) {
-        uint32_t seen = 0, nn = 0;
-        uint8_t li_of[32];
-        uint16_t cnt[32];
-        uint8_t nm[32];
-        const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
-        uint8_t* tl = tabli + (uint64_t)c * A.fam_cap;
-        for (uint32_t j = 0; j < F; j++) {
-            uint32_t b = t[j];
-            if (!b) continue;
-            if (!((seen >> b) & 1u)) { seen |= 1u << b; li_of[b] = (uint8_t)nn; cnt[nn] = 1; nm[nn] = (uint8_t)b; nn++; }
-            else cnt[li_of[b]]++;
-            tl[j] = li_of[b];
+        __syncthreads();
+        {
+            uint32_t q8 = 0;
+            for (uint32_t c = tid; c < n_cols; c += nt, q8++) {
+                uint32_t nn;
+                if (q8 < 8) nn = cnt_mine[q8];
+                else {   // more than 8 columns per thread: count again
+                    uint32_t seen = 0; nn = 0;
+                    const uint8_t* t = stab + c * F;
+                    for (uint32_t j = 0; j < F; j++) { const uint32_t bb = t[j]; if (bb && !((seen >> bb) & 1u)) { seen |= 1u << bb; nn++; } }
+                }
+                scolbase[c] = nn;
+            }
         }
-        const uint32_t base = colbase[c], col = colof[c];
-        for (uint32_t k2 = 0; k2 < nn; k2++) {
-            const uint32_t m = base + k2;
-            my_masks |= 1u << (nm[k2] & 15u);
-            ncol[m] = col; nmask[m] = nm[k2]; ncount[m] = cnt[k2]; nsigma[m] = c;
-            // node->weight = 1.0/(weight+1) + weight * (node->weight/num_seqs)   (mseq.cpp:111-116)
-            float fr = __fdiv_rn((float)cnt[k2], (float)F);
-            float b2 = __fmul_rn(A.fs_weight, fr);
-            nweight[m] = (float)(1.0 / (double)__fadd_rn(A.fs_weight, 1.0f) + (double)b2);
-            cursor[m] = 0; nflags[m] = 0; spillrow[m] = 0;
-            slotbase[m] = cnt[k2];
+        __syncthreads();
+        const uint32_t V = scan_array_inplace(scolbase, n_cols, red);
+        if (tid == 0) scolbase[n_cols] = V;
+        if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+        __syncthreads();
+        uint32_t my_masks = 0;   // IUPAC masks (case ignored) of the nodes this thread creates
+        if (tid == 0) shv[4] = 0;
+        for (uint32_t c = tid; c < n_cols; c += nt) {
+            uint8_t* t = stab + c * F;
+            const uint32_t base = scolbase[c], nn = scolbase[c + 1] - base, col = colof[c];
+            colbase[c] = base;
+            auto emit = [&](uint32_t k2, uint32_t mask, uint32_t count) {
+                const uint32_t m = base + k2;
+                my_masks |= 1u << (mask & 15u);
+                ncol[m] = col; nmask[m] = (uint8_t)mask; ncount[m] = (uint16_t)count; nsigma[m] = c;
+                // node->weight = 1.0/(weight+1) + weight * (node->weight/num_seqs)   (mseq.cpp:111-116)
+                const float fr = __fdiv_rn((float)count, (float)F);
+                const float b2 = __fmul_rn(A.fs_weight, fr);
+                nweight[m] = (float)(1.0 / (double)__fadd_rn(A.fs_weight, 1.0f) + (double)b2);
+                nflags[m] = 0; spillrow[m] = 0;
+            };
+            if (nn <= 4) {   // the usual column: its (up to four) characters and their counts stay in registers
+                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, have = 0;
+                for (uint32_t j = 0; j < F; j++) {
+                    const uint32_t bb = t[j];
+                    if (!bb) continue;
+                    uint32_t li;
+                    if (have > 0 && bb == m0) { li = 0; c0++; }
+                    else if (have > 1 && bb == m1) { li = 1; c1++; }
+                    else if (have > 2 && bb == m2) { li = 2; c2++; }
+                    else if (have > 3 && bb == m3) { li = 3; c3++; }
+                    else {
+                        li = have;
+                        if (have == 0) { m0 = bb; c0 = 1; } else if (have == 1) { m1 = bb; c1 = 1; }
+                        else if (have == 2) { m2 = bb; c2 = 1; } else { m3 = bb; c3 = 1; }
+                        have++;
+                    }
+                    t[j] = (uint8_t)(li + 1);
+                }
+                if (nn > 0) emit(0, m0, c0);
+                if (nn > 1) emit(1, m1, c1);
+                if (nn > 2) emit(2, m2, c2);
+                if (nn > 3) emit(3, m3, c3);
+            } else {
+                uint32_t seen = 0, k3 = 0;
+                uint8_t li_of[32];
+                uint16_t cnt[32];
+                uint8_t nm[32];
+                for (uint32_t j = 0; j < F; j++) {
+                    const uint32_t bb = t[j];
+                    if (!bb) continue;
+                    if (!((seen >> bb) & 1u)) { seen |= 1u << bb; li_of[bb] = (uint8_t)k3; cnt[k3] = 1; nm[k3] = (uint8_t)bb; k3++; }
+                    else cnt[li_of[bb]]++;
+                    t[j] = li_of[bb] + 1;
+                }
+                for (uint32_t k2 = 0; k2 < nn; k2++) emit(k2, nm[k2], cnt[k2]);
+            }
         }
-    }
-    __syncthreads();
-    if (my_masks) atomicOr(&shv[4], my_masks);
-
-    // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
-    scan_array_inplace(slotbase, V, red);
-    if (tid == 0) slotbase[V] = I;
-    for (uint32_t j = wid; j < F; j += nwarp) {
-        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
-        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
-            uint32_t r[4], cb[4], li[4];
+        if (tid == 0) colbase[n_cols] = V;
+        __syncthreads();
+        if (my_masks) atomicOr(&shv[4], my_masks);
+        // ---- 4 + 5. edges: the predecessor of (column c, row j) is the node of row j's previous base (dag::link,
+        //         graph.h:332-340); per node the distinct predecessors in ascending id (reduce_edges, graph.h:466-488).
+        //         A thread collects its column's (local node, predecessor) pairs as a sorted list of distinct keys
+        //         (pass 0: in-degree per node; pass 1, after the scan: the predecessor ids)
+        for (int pass = 0; pass < 2; pass++) {
+            for (uint32_t c = tid; c < n_cols; c += nt) {
+                const uint32_t base = scolbase[c], nn = scolbase[c + 1] - base, cm = colof[c];
+                uint32_t k[GK];
+                uint32_t nu = column_keys(stab, scolbase, F, c, k);
+                // one run of equal local node per node with predecessors: in-degree = run length (pass 0), the ids (pass 1)
+                auto edge = [&](uint32_t key, uint32_t o) {   // pass 1: predecessor number o (global index) of its node
+                    const uint32_t p = key & 0xffffffu;
+                    preds[o] = p;
+                    nflags[p] = 1;  // has a successor (benign same-value race)
+                    if (A.forbid) atomicMin(&A.nmaxins[io + p], cm);
+                };
+                if (pass == 0) for (uint32_t k2 = 0; k2 < nn; k2++) pred_off[base + k2] = 0;
+                if (nu <= (uint32_t)GK) {
+                    uint32_t run = 0, o = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) r[u] = i0 + 32 * u < len ? item_node[fo + i0 + 32 * u] : NONE;
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (r[u] != NONE) { cb[u] = colbase[r[u]]; li[u] = tabli[(uint64_t)r[u] * A.fam_cap + j]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (r[u] != NONE) item_node[fo + i0 + 32 * u] = cb[u] + li[u];
-        }
-    }
-    __syncthreads();
-    for (uint32_t j = wid; j < F; j += nwarp) {
-        const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
-        for (uint32_t i0 = lane; i0 < len; i0 += 128) {
-            uint32_t node[4], from[4], pos[4], sb[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = i0 + 32 * u;
-                node[u] = NONE;
-                if (i < len) {
-                    node[u] = item_node[fo + i];
-                    from[u] = i ? item_node[fo + i - 1] : NONE;   // previous item of the same family row
+                    for (int x = 0; x < GK; x++) {
+                        if ((uint32_t)x < nu) {
+                            const uint32_t li = k[x] >> 24;
+                            const bool first = x == 0 || (k[x - (x > 0)] >> 24) != li;
+                            if (pass == 0) {
+                                run = first ? 1u : run + 1u;
+                                const bool lastofrun = (uint32_t)x + 1 == nu || (k[x + (x + 1 < GK)] >> 24) != li;
+                                if (lastofrun) { pred_off[base + li] = run; my_max = max(my_max, run); }
+                            } else {
+                                o = first ? pred_off[base + li] : o + 1u;
+                                edge(k[x], o);
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t u[FAM_CAP_MAX + 1];
+                    nu = column_keys_many(stab, scolbase, F, c, u);
+                    uint32_t x = 0;
+                    while (x < nu) {
+                        const uint32_t li = u[x] >> 24;
+                        uint32_t x2 = x;
+                        while (x2 < nu && (u[x2] >> 24) == li) x2++;
+                        if (pass == 0) { pred_off[base + li] = x2 - x; my_max = max(my_max, x2 - x); }
+                        else { const uint32_t o = pred_off[base + li]; for (uint32_t y = x; y < x2; y++) edge(u[y], o + (y - x)); }
+                        x = x2;
+                    }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (node[u] != NONE) { pos[u] = atomicAdd(&cursor[node[u]], 1u); sb[u] = slotbase[node[u]]; }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (node[u] == NONE) continue;
-                slot[sb[u] + pos[u]] = from[u];
-                if (from[u] != NONE) nflags[from[u]] = 1;  // has a successor (benign same-value race)
+            __syncthreads();
+            if (pass == 0) {
+                E = scan_array_inplace(pred_off, V, red);
+                if (tid == 0) pred_off[V] = E;
+                if (A.forbid) for (uint32_t m = tid; m < V; m += nt) A.nmaxins[io + m] = 1000000u;
+                __syncthreads();
             }
         }
-    }
-    __syncthreads();
+        if (A.forbid) {
+            // --insertion forbid: max_insert of a node = columns free before its nearest successor
+            // (compute_node_simple::calc, src/mesh.h:480-484: min over next nodes of their position, 1000000 without one)
+            uint32_t* nmaxins = A.nmaxins + io;
+            for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = nmaxins[m] - ncol[m] - 1u;
+        }
+        shv_V = V;
+    } else {
+        // ---- 2. column table: tab[c][j] = base mask of family row j in column rank c
+        for (uint32_t i = tid; i < n_cols * A.fam_cap; i += nt) tab[i] = 0;
+        __syncthreads();
+        // (the column rank of every item is kept in item_node until the nodes exist)
+        for (uint32_t j = wid; j < F; j += nwarp) {
+            const uint64_t a = rowbase[j];
+            const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+            for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+                uint32_t c[4];
+                uint8_t mk[4];
+    #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    c[u] = NONE;
+                    if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
+                }
+    #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (c[u] == NONE) continue;
+                    const uint32_t r = colrank(c[u]);
+                    tab[(uint64_t)r * A.fam_cap + j] = mk[u] & 31u;
+                    item_node[fo + i0 + 32 * u] = r;
+                }
+            }
+        }
+        __syncthreads();
 
-    // ---- 5. reduce_edges: sort predecessor ids, drop duplicates (graph.h:466-488); in-degree per node
-    uint32_t my_max = 0;
-    for (uint32_t m = tid; m < V; m += nt) {
-        uint32_t* sl = slot + slotbase[m];
-        const uint32_t n = slotbase[m + 1] - slotbase[m];
-        // sorted list of the distinct predecessors, built in thread-local memory (n <= family size, and most of the
-        // n candidates repeat one of a handful of nodes)
-        uint32_t u[FAM_CAP_MAX + 1];
-        uint32_t deg = 0;
-        for (uint32_t x0 = 0; x0 < n; x0 += 4) {
-            uint32_t key[4];
-#pragma unroll
-            for (int k2 = 0; k2 < 4; k2++) key[k2] = x0 + k2 < n ? sl[x0 + k2] : NONE;
-#pragma unroll
-            for (int k2 = 0; k2 < 4; k2++) {
-                if (key[k2] == NONE) continue;
-                uint32_t y = deg;
-                while (y > 0 && u[y - 1] > key[k2]) y--;
-                if (y > 0 && u[y - 1] == key[k2]) continue;
-                for (uint32_t z = deg; z > y; z--) u[z] = u[z - 1];
-                u[y] = key[k2];
-                deg++;
+        // ---- 3. nodes: one per (column, IUPAC char incl. case), local order = first family row bringing it
+        //         (mseq.cpp:88-98). Pass A counts per column, pass B writes node arrays.
+        for (uint32_t c = tid; c < n_cols; c += nt) {
+            uint32_t seen = 0, nn = 0;
+            const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
+            for (uint32_t j = 0; j < F; j++) { uint32_t b = t[j]; if (b && !((seen >> b) & 1u)) { seen |= 1u << b; nn++; } }
+            colbase[c] = nn;
+        }
+        __syncthreads();
+        const uint32_t V = scan_array_inplace(colbase, n_cols, red);
+        shv_V = V;
+        if (tid == 0) colbase[n_cols] = V;
+        if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
+        uint32_t my_masks = 0;   // IUPAC masks (case ignored) of the nodes this thread creates
+        if (tid == 0) shv[4] = 0;
+        for (uint32_t c = tid; c < n_cols; c += nt) {
+            uint32_t seen = 0, nn = 0;
+            uint8_t li_of[32];
+            uint16_t cnt[32];
+            uint8_t nm[32];
+            const uint8_t* t = tab + (uint64_t)c * A.fam_cap;
+            uint8_t* tl = tabli + (uint64_t)c * A.fam_cap;
+            for (uint32_t j = 0; j < F; j++) {
+                uint32_t b = t[j];
+                if (!b) continue;
+                if (!((seen >> b) & 1u)) { seen |= 1u << b; li_of[b] = (uint8_t)nn; cnt[nn] = 1; nm[nn] = (uint8_t)b; nn++; }
+                else cnt[li_of[b]]++;
+                tl[j] = li_of[b];
+            }
+            const uint32_t base = colbase[c], col = colof[c];
+            for (uint32_t k2 = 0; k2 < nn; k2++) {
+                const uint32_t m = base + k2;
+                my_masks |= 1u << (nm[k2] & 15u);
+                ncol[m] = col; nmask[m] = nm[k2]; ncount[m] = cnt[k2]; nsigma[m] = c;
+                // node->weight = 1.0/(weight+1) + weight * (node->weight/num_seqs)   (mseq.cpp:111-116)
+                float fr = __fdiv_rn((float)cnt[k2], (float)F);
+                float b2 = __fmul_rn(A.fs_weight, fr);
+                nweight[m] = (float)(1.0 / (double)__fadd_rn(A.fs_weight, 1.0f) + (double)b2);
+                cursor[m] = 0; nflags[m] = 0; spillrow[m] = 0;
+                slotbase[m] = cnt[k2];
             }
         }
-        for (uint32_t x = 0; x < deg; x++) sl[x] = u[x];
-        pred_off[m] = deg;
-        my_max = max(my_max, deg);
-    }
-    __syncthreads();
-    const uint32_t E = scan_array_inplace(pred_off, V, red);
-    if (tid == 0) pred_off[V] = E;
-    __syncthreads();
-    for (uint32_t m = tid; m < V; m += nt) {
-        const uint32_t deg = pred_off[m + 1] - pred_off[m];
-        for (uint32_t x = 0; x < deg; x++) preds[pred_off[m] + x] = slot[slotbase[m] + x];
-    }
-    if (A.forbid) {
-        // --insertion forbid: max_insert of a node = columns free before its nearest successor
-        // (compute_node_simple::calc, src/mesh.h:480-484: min over next nodes of their position, 1000000 without one)
-        uint32_t* nmaxins = A.nmaxins + io;
-        for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = 1000000u;
+        __syncthreads();
+        if (my_masks) atomicOr(&shv[4], my_masks);
+
+        // ---- 4. node of every item; predecessor candidates grouped per node (dag::link, graph.h:332-340)
+        scan_array_inplace(slotbase, V, red);
+        if (tid == 0) slotbase[V] = I;
+        for (uint32_t j = wid; j < F; j += nwarp) {
+            const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+            for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+                uint32_t r[4], cb[4], li[4];
+    #pragma unroll
+                for (int u = 0; u < 4; u++) r[u] = i0 + 32 * u < len ? item_node[fo + i0 + 32 * u] : NONE;
+    #pragma unroll
+                for (int u = 0; u < 4; u++) if (r[u] != NONE) { cb[u] = colbase[r[u]]; li[u] = tabli[(uint64_t)r[u] * A.fam_cap + j]; }
+    #pragma unroll
+                for (int u = 0; u < 4; u++) if (r[u] != NONE) item_node[fo + i0 + 32 * u] = cb[u] + li[u];
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = wid; j < F; j += nwarp) {
+            const uint32_t fo = famoff[j], len = famoff[j + 1] - fo;
+            for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+                uint32_t node[4], from[4], pos[4], sb[4];
+    #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32 * u;
+                    node[u] = NONE;
+                    if (i < len) {
+                        node[u] = item_node[fo + i];
+                        from[u] = i ? item_node[fo + i - 1] : NONE;   // previous item of the same family row
+                    }
+                }
+    #pragma unroll
+                for (int u = 0; u < 4; u++) if (node[u] != NONE) { pos[u] = atomicAdd(&cursor[node[u]], 1u); sb[u] = slotbase[node[u]]; }
+    #pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (node[u] == NONE) continue;
+                    slot[sb[u] + pos[u]] = from[u];
+                    if (from[u] != NONE) nflags[from[u]] = 1;  // has a successor (benign same-value race)
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 5. reduce_edges: sort predecessor ids, drop duplicates (graph.h:466-488); in-degree per node
+        for (uint32_t m = tid; m < V; m += nt) {
+            uint32_t* sl = slot + slotbase[m];
+            const uint32_t n = slotbase[m + 1] - slotbase[m];
+            // sorted list of the distinct predecessors, built in thread-local memory (n <= family size, and most of the
+            // n candidates repeat one of a handful of nodes)
+            uint32_t u[FAM_CAP_MAX + 1];
+            uint32_t deg = 0;
+            for (uint32_t x0 = 0; x0 < n; x0 += 4) {
+                uint32_t key[4];
+    #pragma unroll
+                for (int k2 = 0; k2 < 4; k2++) key[k2] = x0 + k2 < n ? sl[x0 + k2] : NONE;
+    #pragma unroll
+                for (int k2 = 0; k2 < 4; k2++) {
+                    if (key[k2] == NONE) continue;
+                    uint32_t y = deg;
+                    while (y > 0 && u[y - 1] > key[k2]) y--;
+                    if (y > 0 && u[y - 1] == key[k2]) continue;
+                    for (uint32_t z = deg; z > y; z--) u[z] = u[z - 1];
+                    u[y] = key[k2];
+                    deg++;
+                }
+            }
+            for (uint32_t x = 0; x < deg; x++) sl[x] = u[x];
+            pred_off[m] = deg;
+            my_max = max(my_max, deg);
+        }
+        __syncthreads();
+        E = scan_array_inplace(pred_off, V, red);
+        if (tid == 0) pred_off[V] = E;
         __syncthreads();
         for (uint32_t m = tid; m < V; m += nt) {
-            const uint32_t deg = pred_off[m + 1] - pred_off[m], cm = ncol[m];
-            for (uint32_t x = 0; x < deg; x++) atomicMin(&nmaxins[slot[slotbase[m] + x]], cm);
+            const uint32_t deg = pred_off[m + 1] - pred_off[m];
+            for (uint32_t x = 0; x < deg; x++) preds[pred_off[m] + x] = slot[slotbase[m] + x];
         }
-        __syncthreads();
-        for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = nmaxins[m] - ncol[m] - 1u;
+        if (A.forbid) {
+            // --insertion forbid: max_insert of a node = columns free before its nearest successor
+            // (compute_node_simple::calc, src/mesh.h:480-484: min over next nodes of their position, 1000000 without one)
+            uint32_t* nmaxins = A.nmaxins + io;
+            for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = 1000000u;
+            __syncthreads();
+            for (uint32_t m = tid; m < V; m += nt) {
+                const uint32_t deg = pred_off[m + 1] - pred_off[m], cm = ncol[m];
+                for (uint32_t x = 0; x < deg; x++) atomicMin(&nmaxins[slot[slotbase[m] + x]], cm);
+            }
+            __syncthreads();
+            for (uint32_t m = tid; m < V; m += nt) nmaxins[m] = nmaxins[m] - ncol[m] - 1u;
+        }
     }
+    const uint32_t V = shv_V;
     // block max of in-degree
     for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(0xffffffffu, my_max, o));
     __syncthreads();
@@ -755,6 +1007,11 @@ int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t
     return SG_OK;
 }
 
+static uint64_t env_kb(const char* name, uint64_t dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? strtoull(v, nullptr, 10) : dflt;
+}
+
 int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
     GraphArgs A;
@@ -772,7 +1029,13 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;
-    size_t smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + 1 + 2 * s->fam_cap) * 4;
+    const size_t base_smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + 1 + 2 * s->fam_cap) * 4;
+    // column table in shared memory: what the batch's families can need (columns <= items of the longest rows), capped so
+    // that two CTAs stay resident per SM; a family that needs more takes the global-scratch path
+    const uint64_t want = std::min<uint64_t>(s->ncap, (uint64_t)ix->max_row_len * 2) * s->fam_cap;
+    A.stab_bytes = s->graph_generic ? 0u : (uint32_t)((std::min<uint64_t>(want, env_kb("SG_STAB_KB", 80) * 1024) + 15u) & ~15ull);
+    size_t smem = base_smem + 16 + A.stab_bytes;
+    if (smem > 200 * 1024) { A.stab_bytes = 0; smem = base_smem + 16; }   // very wide alignments: the bitmap alone fills the SM
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
     s->stats.kernel_launches += 1;

@@ -63,7 +63,11 @@ def test_align_golden_cases():
             assert int(bits(r["score"])) == e["score_bits"], i
 
 
-def test_graph_matches_oracle(orc):
+@pytest.mark.parametrize("graph_path", ["shared", "generic"])
+def test_graph_matches_oracle(orc, graph_path, monkeypatch):
+    """family graph (nodes, weights, predecessor lists) through the shared-memory column table and through the
+    global-scratch fallback"""
+    monkeypatch.setenv("SG_GRAPH_GENERIC", "1" if graph_path == "generic" else "0")
     rng = np.random.default_rng(42)
     for it in range(25):
         rows, q = synth.random_case(rng, lowercase=0.05 if it % 2 else 0.0)
