@@ -39,6 +39,9 @@ extern "C" {
 #define SG_Q_SKIPPED 2  /* all relatives contained the query and --realign removed them (src/align.cpp:337-348) */
 #define SG_Q_NOSPACE 3  /* fix_duplicate_positions' runtime_error: more bases than columns (src/cseq.cpp:557-560) */
 #define SG_Q_NOFAMILY 4 /* fewer than fs_req relatives (src/famfinder.cpp:486-491) */
+#define SG_Q_LIMIT 5    /* this query's family graph exceeds a device capacity (nodes, columns, traceback arena): it is left
+                         * unaligned, the rest of the batch is not affected (per-query failure, as src/famfinder.cpp:486-491
+                         * and src/cseq.cpp:557-560 fail one sequence, not the run) */
 
 typedef struct sg_index sg_index;     /* reference MSA + k-mer posting lists, resident in one GPU's HBM */
 typedef struct sg_session sg_session; /* a batch of queries + all per-batch device workspace */

@@ -24,7 +24,7 @@ EXPORTS = [
     "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
 ]
 
-SG_Q_ALIGNED, SG_Q_COPIED, SG_Q_SKIPPED, SG_Q_NOSPACE, SG_Q_NOFAMILY = 0, 1, 2, 3, 4
+SG_Q_ALIGNED, SG_Q_COPIED, SG_Q_SKIPPED, SG_Q_NOSPACE, SG_Q_NOFAMILY, SG_Q_LIMIT = 0, 1, 2, 3, 4, 5
 TURN_MODES = {"none": 0, "revcomp": 1, "all": 2}
 
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")

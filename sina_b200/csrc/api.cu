@@ -38,6 +38,7 @@ static void free_workspace(Workspace* w) {
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->done) cudaEventDestroy(w->done);
     if (w->stream) cudaStreamDestroy(w->stream);
+    if (w->dp_stream) cudaStreamDestroy(w->dp_stream);
     *w = Workspace{};
 }
 
@@ -53,7 +54,14 @@ static void free_align(Session* s) {
 
 static int alloc_workspace(Session* s, Workspace* w) {
     const uint64_t C = s->chunk, I = s->icap;
-    SG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    if (env_mb("SG_PRIO", 0)) {
+        int lo = 0, hi = 0;
+        SG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (largest number)
+        SG_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, hi));
+        SG_CUDA(cudaStreamCreateWithPriority(&w->dp_stream, cudaStreamNonBlocking, lo));
+    } else {
+        SG_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    }
     for (auto& e : w->ev) SG_CUDA(cudaEventCreate(&e));
     SG_CUDA(cudaEventCreateWithFlags(&w->done, cudaEventDisableTiming));
     SG_CUDA(cudaHostAlloc((void**)&w->h_remaining, sizeof(uint32_t), cudaHostAllocDefault));
@@ -310,7 +318,7 @@ void sg_session_destroy(sg_session* h) {
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     free_align(s);
-    void* ptrs[] = {s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
+    void* ptrs[] = {s->d_full_scores, s->d_full_tmp, s->d_full_keys, s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results,
                     s->d_turn_scores, s->d_turn, s->d_turn_ops};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -398,23 +406,84 @@ int sg_session_turn(sg_session* h, int mode, int32_t* turn) {
     return SG_OK;
 }
 
-// Family finding for queries [q0, q0 + n) of the batch (n == 0: all of it): k-mer search + selection, the candidate
-// window widened x10 until no query of the range asks for more (famfinder.cpp:590-608).
+// Family finding for queries [q0, q0 + n) of the batch (n == 0: all of it): k-mer search + selection with the
+// reference's first window fs_max + 1; the queries whose quotas that window does not meet (famfinder.cpp:591-608 widens
+// it x10 until it covers the index) are re-ranked alone, run by run: with the next windows while the shared-memory
+// merge holds them, then over the whole index (rank_full_kernel). A wider window never changes the result of the
+// walk, so the outcome equals the reference's loop.
 static int family_range(Session* s, const sg_fam_params* fp, uint32_t q0, uint32_t n) {
+    Index* ix = s->ix;
+    if (n == 0) { q0 = 0; n = s->nq; }
     uint64_t window = (uint64_t)fp->fs_max + 1;  // famfinder.cpp:590
-    for (;;) {
-        const uint32_t w = (uint32_t)std::min<uint64_t>(window, s->ix->N);
+    auto fits_merge = [&](uint64_t w) {
+        uint64_t p2 = 1;
+        while (p2 < w * ix->n_tiles) p2 <<= 1;
+        return p2 <= FIND_MAX_SORT;
+    };
+    auto pass = [&](uint32_t w, uint32_t a, uint32_t cnt, uint32_t* retry) -> int {
         SG_TRY(stage_begin(s, 0));
-        SG_TRY(launch_find(s, w, q0, n));
+        SG_TRY(launch_find(s, w, a, cnt));
         SG_TRY(stage_end(s, &s->stats.ms_find));
         SG_TRY(stage_begin(s, 1));
-        SG_TRY(launch_family(s, *fp, s->find_max, q0, n));
+        SG_TRY(launch_family(s, *fp, s->find_max, a, cnt));
         SG_TRY(stage_end(s, &s->stats.ms_family));
-        uint32_t retry = 0;
-        SG_CUDA(cudaMemcpyAsync(&retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaMemcpyAsync(retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
         SG_CUDA(cudaStreamSynchronize(s->stream));
-        if (retry == 0 || w >= s->ix->N) break;
-        window *= 10;  // famfinder.cpp:607 (the whole range is re-ranked with the wider window)
+        return SG_OK;
+    };
+    uint32_t retry = 0;
+    const uint32_t w0 = (uint32_t)std::min<uint64_t>(window, ix->N);
+    if (!fits_merge(w0)) SG_FAIL(SG_ERR_LIMIT, "--fs-max too large for this reference size (first window exceeds the top-k merge)");
+    SG_TRY(pass(w0, q0, n, &retry));
+    if (retry == 0 || w0 >= ix->N) return SG_OK;
+    // runs of consecutive queries still asking for a wider window
+    std::vector<int32_t> fam_n(n);
+    auto flagged_runs = [&](std::vector<std::pair<uint32_t, uint32_t>>& runs) -> int {
+        SG_CUDA(cudaMemcpyAsync(fam_n.data(), s->d_fam_n + q0, (size_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+        SG_CUDA(cudaStreamSynchronize(s->stream));
+        runs.clear();
+        for (uint32_t i = 0; i < n;) {
+            if (fam_n[i] != -2) { i++; continue; }
+            uint32_t j = i;
+            while (j < n && fam_n[j] == -2) j++;
+            runs.emplace_back(q0 + i, j - i);
+            i = j;
+        }
+        return SG_OK;
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> runs;
+    for (;;) {
+        window *= 10;  // famfinder.cpp:607
+        const uint32_t w = (uint32_t)std::min<uint64_t>(window, ix->N);
+        if (!fits_merge(w)) break;
+        SG_TRY(flagged_runs(runs));
+        uint32_t left = 0;
+        for (auto& r : runs) { uint32_t rr = 0; SG_TRY(pass(w, r.first, r.second, &rr)); left += rr; }
+        if (left == 0 || w >= ix->N) return SG_OK;
+    }
+    // the rest walks the whole index
+    SG_TRY(flagged_runs(runs));
+    const uint64_t per_q = (uint64_t)ix->N * (2 + 8 + 8);
+    const uint32_t cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(256, (512ull << 20) / per_q));
+    if (cap > s->full_cap) {
+        if (s->d_full_scores) cudaFree(s->d_full_scores);
+        if (s->d_full_tmp) cudaFree(s->d_full_tmp);
+        if (s->d_full_keys) cudaFree(s->d_full_keys);
+        s->d_full_scores = nullptr; s->d_full_tmp = nullptr; s->d_full_keys = nullptr; s->full_cap = 0;
+        SG_TRY(dmalloc(&s->d_full_scores, (uint64_t)cap * ix->N)); SG_TRY(dmalloc(&s->d_full_tmp, (uint64_t)cap * ix->N));
+        SG_TRY(dmalloc(&s->d_full_keys, (uint64_t)cap * ix->N));
+        s->full_cap = cap;
+    }
+    for (auto& r : runs) {
+        for (uint32_t a = r.first; a < r.first + r.second; a += s->full_cap) {
+            const uint32_t cnt = std::min(s->full_cap, r.first + r.second - a);
+            SG_TRY(stage_begin(s, 0));
+            SG_TRY(launch_find_full(s, a, cnt));
+            SG_TRY(stage_end(s, &s->stats.ms_find));
+            SG_TRY(stage_begin(s, 1));
+            SG_TRY(launch_family(s, *fp, ix->N, a, cnt, s->d_full_keys));
+            SG_TRY(stage_end(s, &s->stats.ms_family));
+        }
     }
     return SG_OK;
 }
@@ -424,7 +493,9 @@ int sg_session_family(sg_session* h, const sg_fam_params* fp) {
     if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_family: no queries uploaded");
     SG_TRY(validate_fam_params(fp));
     SG_CUDA(cudaSetDevice(s->ix->device));
-    SG_TRY(ensure_family_capacity(s, fp->fs_max + fp->fs_req_full + 1));
+    // the quota only starts removing items once fs_min are kept (famfinder.cpp:558-586): with --fs-min > --fs-max the family
+    // grows to fs_min members
+    SG_TRY(ensure_family_capacity(s, std::max(fp->fs_min, fp->fs_max) + fp->fs_req_full + 1));
     SG_TRY(family_range(s, fp, 0, 0));
     s->have_find = true;
     s->have_family = true;
@@ -499,14 +570,16 @@ static int stage_chunk(Session* s, uint32_t q0, uint32_t n) {
 static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap);
 
 static int enqueue_chunk(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n) {
-    w->q0 = q0; w->n = n; w->busy = true;
+    w->q0 = q0; w->n = n; w->busy = true; w->last_q0 = q0; w->last_n = n;
     SG_CUDA(cudaMemsetAsync(w->d_cursors, 0, 16, w->stream));  // arena cursors
     SG_CUDA(cudaMemsetAsync(w->d_remaining, 0, 4, w->stream));
     SG_CUDA(cudaEventRecord(w->ev[0], w->stream));
     SG_TRY(launch_graph(s, w, ap, q0, n));
     SG_CUDA(cudaEventRecord(w->ev[1], w->stream));
+    if (w->dp_stream) SG_CUDA(cudaStreamWaitEvent(w->dp_stream, w->ev[1], 0));
     SG_TRY(launch_mesh(s, w, ap, q0, n));
-    SG_CUDA(cudaEventRecord(w->ev[2], w->stream));
+    SG_CUDA(cudaEventRecord(w->ev[2], w->dp_stream ? w->dp_stream : w->stream));
+    if (w->dp_stream) SG_CUDA(cudaStreamWaitEvent(w->stream, w->ev[2], 0));
     SG_TRY(launch_backtrack(s, w, ap, q0, n));
     SG_CUDA(cudaEventRecord(w->ev[3], w->stream));
     SG_CUDA(cudaMemcpyAsync(w->h_remaining, w->d_remaining, 4, cudaMemcpyDeviceToHost, w->stream));
@@ -525,7 +598,7 @@ static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
         const uint32_t remaining = *w->h_remaining;
         if (remaining == 0) { w->prev_remaining = 0xffffffffu; SG_TRY(stage_chunk(s, w->q0, w->n)); break; }
         if (remaining >= w->prev_remaining)
-            SG_FAIL(SG_ERR_LIMIT, "traceback/spill arena too small for a single query (raise SG_TB_ARENA_MB / SG_SPILL_ARENA_MB)");
+            SG_FAIL(SG_ERR_LIMIT, "align stage made no progress (internal error: every query left fits an empty arena)");
         w->prev_remaining = remaining;
         SG_TRY(enqueue_chunk(s, w, ap, w->q0, w->n));  // finished queries are skipped (GS_DONE), the rest redone
     }
@@ -560,16 +633,35 @@ static int align_chunks(Session* s, const sg_align_params* ap, uint32_t q_start,
     return SG_OK;
 }
 
+// Bring the chunk pipeline back to idle: after an error exit of the align stage some workspaces still carry a chunk
+// "in flight" (stale q0 / n) and kernels of the failed call may still run; the next call must not retire those chunks
+// into its own output buffers.
+static void reset_pipeline(Session* s) {
+    for (int i = 0; i < s->n_ws; i++) {
+        Workspace* w = &s->ws[i];
+        if (w->stream) cudaStreamSynchronize(w->stream);
+        if (w->dp_stream) cudaStreamSynchronize(w->dp_stream);
+        w->busy = false;
+        w->prev_remaining = 0xffffffffu;
+    }
+    if (s->cstream) cudaStreamSynchronize(s->cstream);
+    s->stage_info[0].pending = s->stage_info[1].pending = false;
+    cudaGetLastError();
+}
+
 int sg_session_align(sg_session* h, const sg_align_params* ap) {
     Session* s = (Session*)h;
     if (!s || s->nq == 0) SG_FAIL(SG_ERR_ARG, "sg_session_align: no queries uploaded");
     if (!s->have_family) SG_FAIL(SG_ERR_ARG, "sg_session_align: run sg_session_family or sg_session_set_family first");
     SG_TRY(validate_align_params(ap));
     SG_CUDA(cudaSetDevice(s->ix->device));
+    for (int i = 0; i < s->n_ws; i++) if (s->ws[i].busy) { reset_pipeline(s); break; }   // a previous call failed half way
     SG_TRY(stage_begin(s, 2));
     SG_TRY(launch_prealign(s, *ap));
     SG_TRY(stage_end(s, &s->stats.ms_graph));   // synchronises: the workspace streams may start
-    return align_chunks(s, ap, 0, 0);
+    const int rc = align_chunks(s, ap, 0, 0);
+    if (rc != SG_OK) { const std::string msg = g_err; reset_pipeline(s); set_error(msg); }
+    return rc;
 }
 
 // famfinder + aligner on the resident batch in one call (what sg_run_batch runs). The family finding of the whole batch
@@ -645,9 +737,7 @@ int sg_session_download_align(sg_session* h, uint32_t* out_cols, uint8_t* out_ma
     if (!r) { tmp.resize(s->nq); r = tmp.data(); }
     SG_CUDA(cudaMemcpyAsync(r, s->d_results, (uint64_t)s->nq * sizeof(sg_align_result), cudaMemcpyDeviceToHost, s->stream));
     SG_CUDA(cudaStreamSynchronize(s->stream));
-    for (uint32_t q = 0; q < s->nq; q++)
-        if (r[q].status >= 100) SG_FAIL(SG_ERR_LIMIT, "a query exceeded a device capacity limit (family graph too large)");
-    return SG_OK;
+    return SG_OK;   // per-query failures (SG_Q_LIMIT, SG_Q_NOSPACE, ...) are in results[].status
 }
 
 int sg_session_stats(sg_session* h, sg_stage_stats* st, int reset) {
@@ -692,11 +782,12 @@ int sg_session_dump_graph(sg_session* h, uint32_t q, uint32_t cap_nodes, uint32_
     if (V) *V = hd.V;
     if (E) *E = hd.E;
     if (hd.V > cap_nodes || hd.E > cap_edges) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: capacity too small");
-    // the workspace that handled q's chunk; its arrays are only still there if no later chunk reused it
-    const uint32_t c = q / s->chunk, n_chunks = (s->nq + s->chunk - 1) / s->chunk;
-    if (c + (uint32_t)s->n_ws < n_chunks) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: the query's workspace has been reused");
-    const Workspace* w = &s->ws[c % s->n_ws];
-    const uint64_t ql = q - c * s->chunk, io = ql * s->icap;
+    // the workspace that handled q's chunk last: its arrays are only still there if no later chunk reused it
+    const Workspace* w = nullptr;
+    for (int i = 0; i < s->n_ws; i++)
+        if (q >= s->ws[i].last_q0 && q < s->ws[i].last_q0 + s->ws[i].last_n) w = &s->ws[i];
+    if (!w) SG_FAIL(SG_ERR_ARG, "sg_session_dump_graph: the query's workspace has been reused");
+    const uint64_t ql = q - w->last_q0, io = ql * s->icap;
     if (col) SG_CUDA(cudaMemcpy(col, w->d_ncol + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));
     if (mask) SG_CUDA(cudaMemcpy(mask, w->d_nmask + io, hd.V, cudaMemcpyDeviceToHost));
     if (weight) SG_CUDA(cudaMemcpy(weight, w->d_nweight + io, (uint64_t)hd.V * 4, cudaMemcpyDeviceToHost));

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         return;
     }
     if (h.status != GS_OK) {
-        r.status = (int32_t)h.status;
+        r.status = h.status == GS_LIMIT ? (int32_t)SG_Q_LIMIT : (int32_t)h.status;
         if (lane == 0) { A.results[q] = r; A.hdr[q].status = GS_DONE; }
         return;
     }

@@ -133,11 +133,14 @@ struct GhostInfo {   // a ring column fed from a spilled row: far predecessors b
 // Per-query arrays use a uniform stride (icap items / ncap columns).
 constexpr int MAX_WS = 8;
 struct Workspace {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // graph, backtrack, bookkeeping (high priority when dp_stream is used)
+    cudaStream_t dp_stream = nullptr; // SG_PRIO=1: the DP kernel runs on its own low-priority stream, so that the latency-bound
+                                     // graph / backtrack kernels of other chunks get the SM slots a retiring DP CTA frees
     cudaEvent_t ev[4] = {};          // stage boundaries: graph | dp | backtrack | end
     cudaEvent_t done = nullptr;
     bool busy = false;               // a chunk is in flight (retire() has not run yet)
     uint32_t q0 = 0, n = 0;          // the chunk in flight
+    uint32_t last_q0 = 0, last_n = 0; // the chunk whose arrays the workspace holds (sg_session_dump_graph)
     uint32_t prev_remaining = 0xffffffffu;
     unsigned long long* d_cursors = nullptr;  // [0] traceback arena cursor, [1] spill arena cursor
     uint32_t* d_remaining = nullptr; // queries of the chunk that did not fit the arenas in this pass
@@ -199,6 +202,11 @@ struct Session {
     uint32_t* d_kmers = nullptr;   // [max_bases] valid (fast: A-prefixed) k-mers of query q at qoff[q].., duplicates kept
     uint32_t* d_nk = nullptr;      // [nq] how many
     unsigned long long* d_counters = nullptr;  // [8]: 0 postings, 1 cells
+    // full ranking (family walk over the whole index for the queries whose window the top-k merge cannot hold)
+    uint32_t full_cap = 0;           // queries the buffers below hold
+    uint16_t* d_full_scores = nullptr;   // [full_cap][N]
+    uint64_t* d_full_tmp = nullptr;      // [full_cap][N]
+    uint64_t* d_full_keys = nullptr;     // [full_cap][N] rank order
     // family
     uint32_t fam_cap = 0;
     uint32_t* d_fam_ids = nullptr;   // [nq][fam_cap] rank order
@@ -248,7 +256,9 @@ struct Session {
 int launch_index_build(Index* ix, cudaStream_t st);
 // q0 / n: query range of the batch (n == 0: all of it)
 int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0);
+// ranked: rank-ordered keys of the range (stride `window`); null = the session's d_ranked
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr);
+int launch_find_full(Session* s, uint32_t q0, uint32_t n);   // every reference in rank order for n <= full_cap queries
 int launch_turn(Session* s, int all);
 int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0 = 0, uint32_t n = 0);
 int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0, uint32_t n);

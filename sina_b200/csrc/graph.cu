@@ -764,6 +764,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             }
         }
         const uint64_t spill_need = (uint64_t)n_spill * ((Lq + 1u) & ~1u);   // rows of an even number of positions (16-byte cells of the v2 kernel)
+        if (words_total > A.tb_words || spill_need > A.spill_elems) { hdr->status = GS_LIMIT; return; }   // not even alone
         const uint64_t tb_off = atomicAdd(&A.cursors[0], (unsigned long long)words_total);
         const uint64_t sp_off = atomicAdd(&A.cursors[1], (unsigned long long)spill_need);
         hdr->V = V; hdr->E = E; hdr->n_cols = n_cols; hdr->n_groups = n_groups;

@@ -718,7 +718,7 @@ int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0
     const size_t smem = RING2_BYTES + 16 + (v2_bytes > v1_bytes ? v2_bytes : v1_bytes);  // ring + query table
     if (smem > 220 * 1024) SG_FAIL(SG_ERR_LIMIT, "query too long for the DP kernel's shared memory");
     SG_CUDA(cudaFuncSetAttribute(mesh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mesh_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
+    mesh_kernel<<<n, DP_BLOCK, smem, w->dp_stream ? w->dp_stream : w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

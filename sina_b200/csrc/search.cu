@@ -54,6 +54,7 @@ struct FindArgs {
     uint32_t N, sub_size, n_sub, tile_warps;
     const uint32_t* list_off; const uint16_t* postings;
     uint32_t max; uint64_t* cand; uint32_t* cand_n; unsigned long long* counters;
+    uint16_t* scores_out;   // non-null: write the tile's score counters to scores_out[q][N] instead of selecting (full ranking)
 };
 
 __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs A) {
@@ -122,6 +123,11 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
         if (lane == 0 && my_post) atomicAdd(&A.counters[0], my_post);
     }
     __syncthreads();
+    if (A.scores_out) {   // full ranking (rank_full_kernel): hand the whole score vector over
+        uint16_t* dst = A.scores_out + (uint64_t)q * A.N + tile_lo;
+        for (uint32_t i = tid; i < tile_n; i += nt) dst[i] = hist[i];
+        return;
+    }
 
     // ---- selection
     const uint32_t need = min(A.max, tile_n);
@@ -286,12 +292,103 @@ int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
                                                           s->d_kmers, s->d_nk + q0);
     FindArgs A;
     A.kmers = s->d_kmers; A.nk = s->d_nk + q0; A.qoff = s->d_qoff + q0; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
-    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max;
+    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max; A.scores_out = nullptr;
     A.cand = s->d_cand + (uint64_t)q0 * ix->n_tiles * max; A.cand_n = s->d_cand_n + (uint64_t)q0 * ix->n_tiles; A.counters = s->d_counters;
     dim3 grid(n, ix->n_tiles);
     find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
     find_merge_kernel<<<n, p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
         A.cand, A.cand_n, ix->n_tiles, max, ix->N, p2, s->d_ranked + (uint64_t)q0 * max, s->d_nres + q0);
+    SG_CUDA(cudaGetLastError());
+    s->stats.kernel_launches += 3;
+    return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Full ranking of one query's score vector: every reference in rank order (score desc, id desc), i.e. find() with
+// max = N. Used when the family walk needs a window the shared-memory merge cannot hold (the reference widens its
+// window x10 until it covers the index, src/famfinder.cpp:591-608; a wider window never changes the result, so the
+// walk goes straight to the whole index). One CTA per query: a stable LSD radix sort of the 16-bit scores (two 8-bit
+// passes, descending digits) over the ids taken in DESCENDING order, so that equal scores keep the higher id first.
+constexpr int RF_THREADS = 1024;
+__global__ void __launch_bounds__(RF_THREADS) rank_full_kernel(const uint16_t* __restrict__ scores, uint32_t N,
+                                                               uint64_t* __restrict__ tmp, uint64_t* __restrict__ out,
+                                                               uint32_t* __restrict__ nres) {
+    __shared__ uint32_t base[256];               // first output position of a digit
+    __shared__ uint32_t wcnt[RF_THREADS / 32][256];   // per chunk: elements of a digit per warp -> exclusive offsets
+    const uint32_t q = blockIdx.x, tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    const uint16_t* sc = scores + (uint64_t)q * N;
+    uint64_t* t0 = tmp + (uint64_t)q * N;
+    uint64_t* o0 = out + (uint64_t)q * N;
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t shift = 8 * pass;
+        auto load = [&](uint32_t i) -> uint64_t {   // element i of the pass's input sequence
+            if (pass == 0) { const uint32_t id = N - 1 - i; return ((uint64_t)sc[id] << 32) | id; }
+            return t0[i];
+        };
+        auto digit = [&](uint64_t key) -> uint32_t { return 255u - ((uint32_t)(key >> (32 + shift)) & 255u); };
+        if (tid < 256) base[tid] = 0;
+        __syncthreads();
+        for (uint32_t c0 = 0; c0 < N; c0 += RF_THREADS) {   // warp-aggregated: the scores crowd into a few digits
+            const uint32_t i = c0 + tid;
+            const uint32_t d = i < N ? digit(load(i)) : 0xffffffffu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (i < N && (uint32_t)__ffs((int)peers) - 1u == lane) atomicAdd(&base[d], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        if (w == 0) {   // exclusive prefix over the 256 digit counts
+            uint32_t carry = 0;
+            for (uint32_t d0 = 0; d0 < 256; d0 += 32) {
+                const uint32_t v = base[d0 + lane];
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+                base[d0 + lane] = carry + x - v;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+        }
+        __syncthreads();
+        uint64_t* dst = pass == 0 ? t0 : o0;
+        for (uint32_t c0 = 0; c0 < N; c0 += RF_THREADS) {
+            for (uint32_t i = tid; i < (RF_THREADS / 32) * 256; i += RF_THREADS) (&wcnt[0][0])[i] = 0;
+            __syncthreads();
+            const uint32_t i = c0 + tid;
+            const bool have = i < N;
+            uint64_t key = 0;
+            uint32_t d = 0xffffffffu, rank = 0;
+            if (have) { key = load(i); d = digit(key); }
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (have && rank == 0) wcnt[w][d] = __popc(peers);
+            __syncthreads();
+            if (tid < 256) {   // per digit: exclusive offsets of the warps inside this chunk, then the chunk's total
+                uint32_t run = 0;
+                for (uint32_t ww = 0; ww < RF_THREADS / 32; ww++) { const uint32_t c = wcnt[ww][tid]; wcnt[ww][tid] = run; run += c; }
+                const uint32_t b = base[tid];
+                base[tid] = b + run;
+                for (uint32_t ww = 0; ww < RF_THREADS / 32; ww++) wcnt[ww][tid] += b;
+            }
+            __syncthreads();
+            if (have) dst[wcnt[w][d] + rank] = key;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) nres[q] = N;
+}
+
+// full score vectors + full ranking of queries [q0, q0 + n) into s->d_full_keys (n <= s->full_cap)
+int launch_find_full(Session* s, uint32_t q0, uint32_t n) {
+    Index* ix = s->ix;
+    const size_t smem = (size_t)ix->tile_warps * ix->sub_size * 2;
+    SG_CUDA(cudaFuncSetAttribute(find_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    query_kmers_kernel<<<(n + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff + q0, n, ix->k, ix->nofast,
+                                                          s->d_kmers, s->d_nk + q0);
+    FindArgs A;
+    A.kmers = s->d_kmers; A.nk = s->d_nk + q0; A.qoff = s->d_qoff + q0; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
+    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = 1;
+    A.cand = nullptr; A.cand_n = nullptr; A.counters = s->d_counters; A.scores_out = s->d_full_scores;
+    dim3 grid(n, ix->n_tiles);
+    find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
+    rank_full_kernel<<<n, RF_THREADS, 0, s->stream>>>(s->d_full_scores, ix->N, s->d_full_tmp, s->d_full_keys, s->d_nres + q0);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 3;
     return SG_OK;
@@ -431,11 +528,11 @@ __global__ void family_kernel(const uint64_t* __restrict__ ranked, const uint32_
     fam_n[q] = n < p.fs_req ? -1 : (int32_t)n;  // :486-491
 }
 
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0, uint32_t n) {
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0, uint32_t n, const uint64_t* ranked) {
     Index* ix = s->ix;
     if (n == 0) { q0 = 0; n = s->nq; }
     SG_CUDA(cudaMemsetAsync(s->d_retry, 0, sizeof(uint32_t), s->stream));
-    family_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d_ranked + (uint64_t)q0 * window, s->d_nres + q0, n, window, ix->N,
+    family_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(ranked ? ranked : s->d_ranked + (uint64_t)q0 * window, s->d_nres + q0, n, window, ix->N,
                                                          ix->d_row_off, ix->d_cols, s->d_excl + q0, fp, s->fam_cap,
                                                          s->d_fam_ids + (uint64_t)q0 * s->fam_cap,
                                                          s->d_fam_scores + (uint64_t)q0 * s->fam_cap, s->d_fam_n + q0, s->d_retry);

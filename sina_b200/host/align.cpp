@@ -112,6 +112,10 @@ void aligner::run(std::vector<tray*>& trays, bool rethrow) {
             t.log << "ERROR: no space to left and right?? sequence longer than alignment?!;";
             continue;
         }
+        if (r.status == SG_Q_LIMIT) {  // this sequence only: its family graph exceeds a device capacity (include/sina_b200.h)
+            t.log << "family graph exceeds the GPU aligner's capacity; sequence not aligned;";
+            continue;
+        }
         cseq* c = new cseq(cseq::withoutBases(*t.input_sequence));  // working copy: name and attributes
         std::vector<aligned_base> v;
         v.reserve(r.n_out);

@@ -224,6 +224,38 @@ def test_family_retry_window_and_quotas(orc):
     ix.close()
 
 
+def test_family_window_beyond_merge_capacity(orc, monkeypatch):
+    """the retry loop reaches windows the shared-memory top-k merge cannot hold (max x tiles > 16384): those queries
+    are ranked over the whole index (rank_full_kernel), as the reference's loop ends at max_results >= index size
+    (famfinder.cpp:591-608). Mixed batch: some queries meet their quotas in the first window, some never do."""
+    monkeypatch.setenv("SG_SUBTILE", "32")          # 24 x 32 = 768 references per tile -> 8 tiles
+    tree, m, c, o = synth.synth_msa(6000, W=700, L=300, seed=33)
+    msa = O.MSA(m, c, o, 700)
+    oix = orc.index_build(msa, 6, 0)
+    ix = sina_b200.Index(m, c, o, 700, k=6)
+    assert ix.info()["n_tiles"] >= 8
+    qm, qo = synth.synth_queries(tree, 12, "full", seed=4)
+    lens = np.diff(o.astype(np.int64))
+    full = int(np.sort(lens)[-25])                   # only 25 references count as full length
+    for fp_kw in (dict(fs_min=40, fs_max=40, fs_min_len=10, fs_full_len=full, fs_req_full=2, fs_req_gaps=0),
+                  dict(fs_min=40, fs_max=40, fs_min_len=10, fs_full_len=10 ** 6, fs_req_gaps=0),       # quota never met
+                  dict(fs_min=10, fs_max=30, fs_min_len=int(lens.max()) + 1, fs_full_len=10, fs_req_gaps=0)):  # nothing long enough
+        fids, fsc, fn = ix.family(qm, qo, sina_b200.FamParams(**fp_kw))
+        for i in range(12):
+            n1, f1, s1 = orc.family(oix, msa, qm[int(qo[i]):int(qo[i + 1])], O.FamParams(**fp_kw))
+            assert fn[i] == n1, (fp_kw, i, fn[i], n1)
+            assert (fids[i, :max(n1, 0)] == f1).all() and (fsc[i, :max(n1, 0)] == s1).all(), (fp_kw, i)
+    # the whole pipeline still runs after such a batch (the session is reused by the host-buffer entry points)
+    oc, om, res = ix.run(qm, qo, sina_b200.FamParams(fs_min_len=10, fs_full_len=full, fs_req_full=2, fs_req_gaps=0), sina_b200.AlignParams())
+    ores, occ, omm, *_ = orc.run_batch(oix, msa, qm, qo, O.FamParams(fs_min_len=10, fs_full_len=full, fs_req_full=2, fs_req_gaps=0),
+                                       O.AlignParams(), nthreads=4)
+    for i in range(12):
+        a, n1 = int(qo[i]), ores[i].n_out
+        assert res[i]["status"] == ores[i].status and (oc[a:a + n1] == occ[a:a + n1]).all(), i
+    orc.index_free(oix)
+    ix.close()
+
+
 def test_pipeline_golden():
     case = load_golden("pipeline_case")
     tree, m, c, o = synth.synth_msa(case["N"], W=case["W"], L=case["L"], seed=case["seed"])
@@ -282,6 +314,35 @@ def test_chunk_pipeline_and_arena_retry(orc, monkeypatch):
             compare_result(res[i], oc[a:b], om[a:b], ores[i], occ[a:a + ores[i].n_out], omm[a:a + ores[i].n_out], 900,
                            (batch, streams, tb_mb, i))
         ix.close()
+    orc.index_free(oix)
+
+
+def test_oversized_query_fails_alone(orc, monkeypatch):
+    """per-query soft failure: a query whose traceback does not fit the arena even alone gets status SG_Q_LIMIT; the
+    rest of the batch is aligned as usual, and the session stays usable for the next call"""
+    tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
+    msa = O.MSA(m, c, o, 900)
+    oix = orc.index_build(msa, 6, 0)
+    qm, qo = synth.synth_queries(tree, 9, "full", seed=23)
+    rng = np.random.default_rng(3)
+    big = (1 << rng.integers(0, 4, 6000)).astype(np.uint8)          # 6000 random bases: ~25x the cells of the others
+    qs = [qm[int(qo[i]):int(qo[i + 1])] for i in range(9)]
+    qs.insert(4, big)
+    qm2, qo2 = pack_queries(qs)
+    fp_kw = dict(fs_min=20, fs_max=20, fs_min_len=100, fs_full_len=240, fs_req_gaps=5)
+    monkeypatch.setenv("SG_TB_ARENA_MB", "1")
+    monkeypatch.setenv("SG_BATCH", "4")
+    ix = sina_b200.Index(m, c, o, 900, k=6)
+    for rep in range(2):   # the second call reuses the cached session
+        oc, om, res = ix.run(qm2, qo2, sina_b200.FamParams(**fp_kw), sina_b200.AlignParams())
+        assert res[4]["status"] == sina_b200.SG_Q_LIMIT
+        ores, occ, omm, *_ = orc.run_batch(oix, msa, qm2, qo2, O.FamParams(**fp_kw), O.AlignParams(), nthreads=4)
+        for i in range(10):
+            if i == 4:
+                continue
+            a, b = int(qo2[i]), int(qo2[i + 1])
+            compare_result(res[i], oc[a:b], om[a:b], ores[i], occ[a:a + ores[i].n_out], omm[a:a + ores[i].n_out], 900, (rep, i))
+    ix.close()
     orc.index_free(oix)
 
 
