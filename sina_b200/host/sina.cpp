@@ -137,6 +137,16 @@ int real_main(int argc, const char* const* argv) {
 
     const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 6 * std::max(1u, ngpu);
     bounded_queue<batch_t> todo(inflight), torender(inflight), towrite(inflight);
+    // Batches alive between the reader and the last byte written (the reference's limiter node, src/sina.cpp:485-489):
+    // a rendered batch holds its FASTA records (4096 x 50 kB at 50 000 columns), so nothing but this bound keeps a slow
+    // output device from growing the `done` map until memory runs out. The reader takes a slot per batch, the slot comes
+    // back when the batch's trays are destroyed.
+    const size_t alive_cap = 3 * inflight + 8;
+    std::mutex alive_mu;
+    std::condition_variable alive_cv;
+    size_t alive = 0;
+    auto alive_acquire = [&] { std::unique_lock<std::mutex> l(alive_mu); alive_cv.wait(l, [&] { return alive < alive_cap; }); alive++; };
+    auto alive_release = [&] { { std::lock_guard<std::mutex> l(alive_mu); alive--; } alive_cv.notify_one(); };
     std::mutex done_mu;
     std::condition_variable done_cv;
     std::map<uint64_t, batch_t> done;
@@ -162,12 +172,13 @@ int real_main(int argc, const char* const* argv) {
                 b.trays.push_back(t);
                 if (b.trays.size() == opts.batch) {
                     b.no = n_batches++;
+                    alive_acquire();
                     todo.push(std::move(b));
                     b = batch_t();
                 }
                 if (failed) break;
             }
-            if (!b.trays.empty()) { b.no = n_batches++; todo.push(std::move(b)); }
+            if (!b.trays.empty()) { b.no = n_batches++; alive_acquire(); todo.push(std::move(b)); }
         } catch (std::exception& e) {
             std::lock_guard<std::mutex> l(done_mu);
             failure = e.what();
@@ -242,6 +253,7 @@ int real_main(int argc, const char* const* argv) {
                 failed = true;
             }
             us_pwrite += usec(t0);
+            alive_release();
         }
     };
     std::vector<std::thread> workers, renderers, writers;
@@ -293,6 +305,7 @@ int real_main(int argc, const char* const* argv) {
             t.destroy();  // src/sina.cpp:573-579
         }
         us_write += usec(t0w);
+        alive_release();
     }
     towrite.close();
     for (auto& w : writers) w.join();
