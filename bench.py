@@ -42,7 +42,19 @@ def parse():
     ap.add_argument("--kind", default="full", choices=["full", "v4"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --queries per step on every GPU; strong: --total-queries per step split over the GPUs")
+    ap.add_argument("--total-queries", type=int, default=0, help="strong scaling: queries per step over all GPUs")
+    ap.add_argument("--shares", action="store_true",
+                    help="also measure one GPU's share of BASELINE configs[2] (V4) and configs[3] (full-length) against a "
+                         "500k-row reference, each with its own parity / roofline / cpu_baseline (adds several minutes)")
+    a = ap.parse_args()
+    if a.scaling == "strong":
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        total = a.total_queries or a.queries
+        a.total_queries = total
+        a.queries = max(1, total // world)
+    return a
 
 
 class ClockSampler(threading.Thread):
@@ -84,6 +96,12 @@ def make_data(args, rank):
     tree, m, c, o = synth.synth_msa(args.refs, W=W_COLS, L=L_REF, seed=SEED)
     qm, qo = synth.synth_queries(tree, args.queries, args.kind, seed=1000 + rank)
     return tree, m, c, o, qm, qo
+
+
+class _NS:
+    """attribute bag (a variant of the command-line arguments for a share)"""
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
 
 
 class CpuPath:
@@ -136,10 +154,35 @@ class CpuPath:
                      "cores": 1, "sample": "%d queries, find(max=41) only" % nf}
         except Exception:
             pass
+        self.last = {"res": res, "cols": oc, "qoff": qoff if self.kind == "reference" else sub_off, "n": nsample}
         return {"kmer_search": kfind, "value": nsample / dt, "unit": "sequences/s", "cores": int(nt), "kind": self.kind,
                 "sample": "%d of the step's %s queries vs the same %d-row index, whole path, %.1f s on %d threads"
                           % (nsample, self.args.kind, self.args.refs, dt, int(nt)),
                 "mcells_per_s": cells / dt / 1e6, "seconds": dt}
+
+    def parity(self, qo, oc_gpu, res_gpu):
+        """the sample just run on the CPU against the GPU's output for the same queries: status, number of bases, every
+        alignment column, head / tail / quality, and the DP score bit for bit"""
+        L = self.last
+        mism, first = 0, None
+        for i in range(L["n"]):
+            r, g = L["res"][i], res_gpu[i]
+            ok = int(r.status) == int(g["status"])
+            if ok and int(r.status) in (0, 1):
+                a, b = int(L["qoff"][i]), int(qo[i] - qo[0])
+                n = int(g["n_out"])
+                ok = bool((L["cols"][a:a + n] == oc_gpu[b:b + n]).all())
+            if ok and int(r.status) == 0:
+                ok = (np.float32(r.score).view(np.uint32) == np.float32(g["score"]).view(np.uint32)
+                      and (int(r.head), int(r.tail), int(r.qual)) == (int(g["head"]), int(g["tail"]), int(g["qual"])))
+            if not ok:
+                mism += 1
+                first = i if first is None else first
+        out = {"checked": L["n"], "mismatches": mism, "against": self.kind,
+               "what": "status, aligned columns of every base, head/tail/quality, score bits"}
+        if first is not None:
+            out["first_mismatch_query"] = first
+        return out
 
     def close(self):
         if self.kind == "reference":
@@ -179,15 +222,15 @@ def run_reference(args):
     val = nsample / t
     line = {"impl": "reference", "metric": "sequences aligned/sec", "value": val, "unit": "sequences/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, nsample),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, nsample, sample_of=args.queries),
             "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
             "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args, queries_per_step):
+def workload_config(args, queries_per_step, sample_of=None):
     if args.refs == N_REFS and args.kind == "full":
         which = "BASELINE configs[1]"
     elif args.refs == 500000 and args.kind == "v4":
@@ -200,6 +243,9 @@ def workload_config(args, queries_per_step):
                         "k=%d fast, fs-max 40, reference defaults" % (which, queries_per_step, "full-length" if args.kind == "full" else "V4",
                                                                      1500 if args.kind == "full" else 280, args.refs, W_COLS, KMER),
             "queries_per_step_per_gpu": queries_per_step, "refs": args.refs, "columns": W_COLS, "k": KMER,
+            **({"bounded_sample": "each step of this arm is a bounded sample of %d of the workload's %d queries per step (same index, same "
+                                  "options): a rate on the same configuration, not a smaller configuration" % (queries_per_step, sample_of)} if sample_of else {}),
+            **({"strong_scaling_total_queries_per_step": args.total_queries} if getattr(args, "scaling", "weak") == "strong" else {}),
             "l2": "inputs larger than L2 (index 0.4 GB + >30 GB traceback written per step)",
             "timing": "value: CUDA events on the library's own stream around the K steps (sg_session_timer), max over "
                       "ranks; e2e: host clock between device-wide synchronisations (host copies are part of it); per-stage "
@@ -207,26 +253,12 @@ def workload_config(args, queries_per_step):
             "parallelism": "queries sharded over GPUs, index replicated, no collective"}
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-    import torch
-    import torch.distributed as dist
-    import sina_b200
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or sina_b200.device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: sina_b200 has no CPU path")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    tree, m, c, o, qm, qo = make_data(args, rank)
-    nq = args.queries
-    ix = sina_b200.Index(m, c, o, W_COLS, k=KMER, device=local)
+def measure(mods, ix, m, c, o, qm, qo, wargs, steps, warmup, rank, world, local, cpu=True):
+    """One workload on this rank's GPU: device-resident number (CUDA events on the library's stream), end-to-end number
+    through the host-buffer C-ABI call, kernel-only pass for the roofline, and on rank 0 of a 1-GPU run the CPU baseline
+    with the parity check of its sample against the GPU's output. Returns the JSON line (rank 0) or None."""
+    torch, dist, sina_b200 = mods
+    nq = wargs.queries
     fp, ap = sina_b200.FamParams(), sina_b200.AlignParams()
     sess = sina_b200.Session(ix, nq, int(qo[-1]))
     sess.upload(qm, qo)  # queries resident in HBM before the timed region
@@ -248,7 +280,7 @@ def main():
         return ix.run(qm, qo, fp, ap, out=e2e_out)
 
     # ---- device-resident number
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_device()
     sess.stats(reset=True)
     sampler = ClockSampler(local)
@@ -256,18 +288,18 @@ def main():
     barrier()
     t0 = time.perf_counter()
     sess.timer_start()          # CUDA event on the library's stream (torch.cuda.Event only sees torch's streams)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     dt = sess.timer_stop() / 1e3  # device clock between the two events: every kernel of the K steps lies inside
     barrier()
     dt_host = time.perf_counter() - t0
     st = sess.stats()
     # ---- end-to-end through the host-buffer C-ABI call
-    for _ in range(min(args.warmup, 1) or 1):
+    for _ in range(min(warmup, 1) or 1):
         oc, om, res = step_e2e()
     barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         oc, om, res = step_e2e()
     barrier()
     dt_e2e = time.perf_counter() - t1
@@ -276,7 +308,7 @@ def main():
     n_ok = int((res["status"] == 0).sum())
 
     # ---- kernel-only pass: one workspace / one stream, so that the CUDA events bracket every kernel alone
-    # (in the timed region above the chunks of two workspaces overlap and the per-stage event times include
+    # (in the timed region above the chunks of several workspaces overlap and the per-stage event times include
     # whatever ran beside them)
     sess.close()
     os.environ["SG_STREAMS"] = "1"
@@ -303,80 +335,122 @@ def main():
         tt = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt, dt_e2e = float(tt[0]), float(tt[1])
-        cnt = torch.tensor([float(st["cells"]), float(st["postings"]), float(st["ms_dp"]), float(st["ms_find"])],
-                           device="cuda", dtype=torch.float64)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        cells_all, posts_all = float(cnt[0]), float(cnt[1])
-    else:
-        cells_all, posts_all = float(st["cells"]), float(st["postings"])
+    if rank != 0:
+        return None
 
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        total_q = nq * args.steps * world
-        value = total_q / dt
-        # dominant kernel: mesh DP (mesh_v2_kernel). Algorithmic bytes = 1 B packed traceback per cell;
-        # duration = CUDA events around the kernel on its stream in the kernel-only pass, this rank.
-        dp_s = st_iso["ms_dp"] / 1e3
-        cells_iso = float(st_iso["cells"])
-        gcups = cells_iso / dp_s / 1e9 if dp_s > 0 else 0.0
-        dp_live_s = st["ms_dp"] / 1e3
-        cells = float(st["cells"])
-        sm_mhz = sampler.summary().get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-        ops_per_cell = 3 + 7 * 1.65
-        issue_ceiling = 148 * 128 * sm_mhz * 1e6 / ops_per_cell / 1e9  # GCUPS at the measured clock
-        find_s = st_iso["ms_find"] / 1e3
-        posts = float(st_iso["postings"])
-        kmer_bytes = 4.0 * posts + (2.0 * args.refs + 8.0 * 41) * nq_iso
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["mesh_v2_kernel"]
-            traffic = tj["dram_bytes_per_query"] * min(CHUNK_ISO, nq_iso) / 1e9   # GB per launch of one full chunk
-        except Exception:
-            pass
-        launches_iso = max(1, -(-nq_iso // CHUNK_ISO))
-        line = {
-            "metric": "sequences aligned/sec", "value": value, "unit": "sequences/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, nq),
-            "e2e": {"value": total_q / dt_e2e, "unit": "sequences/s", "h2d_bytes_per_step": int(len(qm) + qo.nbytes) * world,
-                    "d2h_bytes_per_step": int(oc.nbytes + om.nbytes + res.nbytes) * world},
-            "gpu_launches": int(st["kernel_launches"]),
-            "roofline": {"kernel": "mesh_v2_kernel", "bound": "hbm", "achieved": gcups * 1.0,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": gcups / hbm_peak,
-                         "traffic": traffic, "traffic_unit": "GB per launch (%d-query chunk), ncu dram read+write" % CHUNK_ISO,
-                         "kernel_only_pass": "%d queries in launches of %d on one stream (the timed region runs %d-query launches on 4 streams, where the kernel's events overlap other kernels)" % (nq_iso, CHUNK_ISO, CHUNK),
-                         "algorithmic_gb_per_launch": cells_iso / launches_iso / 1e9,
-                         "peak_source": peak_src,
-                         "note": "1 B of traceback per cell is the only mandatory HBM traffic, so the HBM fraction is low by "
-                                 "construction: the kernel is bound by the ALU pipe (fp32 compare/select) and barrier latency; "
-                                 "see gcups vs issue_ceiling_gcups and profiles/",
-                         "gcups": gcups, "gcups_in_pipeline": cells / dp_live_s / 1e9 if dp_live_s > 0 else 0.0,
-                         "issue_ceiling_gcups": issue_ceiling,
-                         "frac_issue": gcups / issue_ceiling if issue_ceiling else None,
-                         "duration_ms_per_launch": st_iso["ms_dp"] / launches_iso,
-                         "share_of_step": st["ms_dp"] / (dt * 1e3)},
-            "roofline_kmer": {"kernel": "find_tile_kernel", "bound": "hbm", "achieved": kmer_bytes / find_s / 1e9 if find_s > 0 else 0.0,
-                              "peak": hbm_peak, "unit": "GB/s", "frac": (kmer_bytes / find_s / 1e9 / hbm_peak) if find_s > 0 else 0.0,
-                              "bytes_per_query": "4*P + 2*N + 8*max", "postings_per_query": posts / nq_iso},
-            "stages_ms_per_step_isolated": {k: st_iso[k] * (nq / nq_iso) for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
-            "stages_ms_per_step": {k: st[k] / args.steps for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
-            "cells_per_query": cells / (nq * args.steps), "aligned_ok": n_ok, "ms_per_step_host_clock": dt_host / args.steps * 1e3,
-            "clocks": sampler.summary(),
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = CpuPath(args, m, c, o)
-            cb = cpu.run(qm, qo, cpu_sample_size(args))
-            cpu.close()
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s", "kmer_search")}
-        print(json.dumps(line))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    total_q = nq * steps * world
+    value = total_q / dt
+    # dominant kernel: mesh DP (mesh_kernel). Algorithmic bytes = 1 B packed traceback per cell;
+    # duration = CUDA events around the kernel on its stream in the kernel-only pass, this rank.
+    dp_s = st_iso["ms_dp"] / 1e3
+    cells_iso = float(st_iso["cells"])
+    gcups = cells_iso / dp_s / 1e9 if dp_s > 0 else 0.0
+    cells = float(st["cells"])
+    sm_mhz = sampler.summary().get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    ops_per_cell = 3 + 7 * 1.65
+    issue_ceiling = 148 * 128 * sm_mhz * 1e6 / ops_per_cell / 1e9  # GCUPS at the measured clock
+    find_s = st_iso["ms_find"] / 1e3
+    posts = float(st_iso["postings"])
+    kmer_bytes = 4.0 * posts + (2.0 * wargs.refs + 8.0 * 41) * nq_iso
+    traffic, kmer_traffic = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["mesh_kernel"]["dram_bytes_per_query"] * min(CHUNK_ISO, nq_iso) / 1e9   # GB per launch of one full chunk
+        kmer_traffic = tj.get("find_tile_kernel", {}).get("dram_bytes_per_query_by_refs", {}).get(str(wargs.refs))
+    except Exception:
+        pass
+    launches_iso = max(1, -(-nq_iso // CHUNK_ISO))
+    iso_sum = sum(st_iso[k] for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack"))
+    line = {
+        "metric": "sequences aligned/sec", "value": value, "unit": "sequences/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": wargs.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wargs, nq),
+        "e2e": {"value": total_q / dt_e2e, "unit": "sequences/s", "h2d_bytes_per_step": int(len(qm) + qo.nbytes) * world,
+                "d2h_bytes_per_step": int(oc.nbytes + om.nbytes + res.nbytes) * world},
+        "gpu_launches": int(st["kernel_launches"]),
+        "roofline": {"kernel": "mesh_kernel", "bound": "hbm", "achieved": gcups * 1.0,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": gcups / hbm_peak,
+                     "traffic": traffic, "traffic_unit": "GB per launch (%d-query chunk), ncu dram read+write" % CHUNK_ISO,
+                     "kernel_only_pass": "%d queries in launches of %d on one stream (the timed region runs %d-query launches on 4 streams, where the kernel's events overlap other kernels)" % (nq_iso, CHUNK_ISO, CHUNK),
+                     "algorithmic_gb_per_launch": cells_iso / launches_iso / 1e9,
+                     "peak_source": peak_src,
+                     "limiter": "not HBM: 1 B of traceback per cell is the only mandatory HBM traffic, so `frac` is low by construction "
+                                "(the contract's `bound` only knows hbm / tensor). The kernel is bound by instruction issue on the "
+                                "ALU pipe (fp32 min / compare / select) and the per-step barrier: judge it by frac_issue",
+                     "gcups": gcups, "issue_ceiling_gcups": issue_ceiling,
+                     "frac_issue": gcups / issue_ceiling if issue_ceiling else None,
+                     "duration_ms_per_launch": st_iso["ms_dp"] / launches_iso,
+                     "share_of_step_isolated": st_iso["ms_dp"] / iso_sum if iso_sum else None},
+        "roofline_kmer": {"kernel": "find_tile_kernel", "bound": "hbm", "achieved": kmer_bytes / find_s / 1e9 if find_s > 0 else 0.0,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": (kmer_bytes / find_s / 1e9 / hbm_peak) if find_s > 0 else 0.0,
+                          "bytes_per_query": "4*P + 2*N + 8*max (SURVEY §8d: u32 postings, one pass over the int16 score vector)",
+                          "postings_per_query": posts / nq_iso,
+                          "traffic": kmer_traffic, "traffic_unit": "bytes per query, ncu dram read+write (the index stores u16 postings and the counters live in shared memory)"},
+        "stages_ms_per_step_isolated": {k: st_iso[k] * (nq / nq_iso) for k in ("ms_find", "ms_family", "ms_graph", "ms_dp", "ms_backtrack")},
+        "cells_per_query": cells / (nq * steps), "aligned_ok": n_ok, "ms_per_step_host_clock": dt_host / steps * 1e3,
+        "clocks": sampler.summary(),
+    }
+    if world == 1 and cpu:
+        cpu_path = CpuPath(wargs, m, c, o)
+        cb = cpu_path.run(qm, qo, cpu_sample_size(wargs))
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mcells_per_s", "kmer_search")}
+        # parity of the timed configuration: the CPU sample's alignments against the GPU's for the same queries
+        line["parity"] = cpu_path.parity(qo, oc, res)
+        cpu_path.close()
+    return line
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import sina_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or sina_b200.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: sina_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mods = (torch, dist, sina_b200)
+
+    tree, m, c, o, qm, qo = make_data(args, rank)
+    ix = sina_b200.Index(m, c, o, W_COLS, k=KMER, device=local)
+    line = measure(mods, ix, m, c, o, qm, qo, args, args.steps, args.warmup, rank, world, local, cpu=not args.no_cpu_baseline)
     ix.close()
+
+    if args.shares and world == 1:
+        # one GPU's share of BASELINE configs[3] (100k full-length over 8 GPUs) and configs[2] (1M V4 over 8 GPUs), both
+        # against a 500k-row reference: own index, own parity / roofline / cpu_baseline
+        from sina_b200 import synth
+        del m, c, o, qm, qo
+        refs = 500000
+        tree, m, c, o = synth.synth_msa(refs, W=W_COLS, L=L_REF, seed=SEED)
+        ix = sina_b200.Index(m, c, o, W_COLS, k=KMER, device=local)
+        shares = {}
+        for name, kind, nq in (("configs[3]", "full", 12500), ("configs[2]", "v4", 125000)):
+            w = _NS(**vars(args))
+            w.refs, w.kind, w.queries, w.scaling = refs, kind, nq, "weak"
+            w.cpu_sample = args.cpu_sample or (256 if kind == "full" else 1024)
+            qm, qo = synth.synth_queries(tree, nq, kind, seed=1000)
+            shares[name] = measure(mods, ix, m, c, o, qm, qo, w, max(1, min(args.steps, 2)), 1, rank, world, local,
+                                   cpu=not args.no_cpu_baseline)
+        ix.close()
+        line["shares"] = shares
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

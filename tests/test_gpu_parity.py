@@ -529,3 +529,48 @@ def test_edge_case_queries_vs_oracle(orc):
         assert res[i]["status"] == ores[i].status, ("one", i)
         if ores[i].status in (0, 1):
             assert (oc[a:a + n] == occ[a:a + n]).all() and (om[a:a + n] == omm[a:a + n]).all(), ("one", i)
+
+
+def test_production_layout_300k_vs_reference():
+    """the configuration the numbers are quoted on: production search layout (sub-tiles of 4096 references, 24 per CTA
+    tile) over a 300 000-row reference (4 tiles), reference defaults, against the COMPILED REFERENCE (oracle/_ref):
+    find ranks, families and aligned columns / score bits of 64 full-length and 64 V4 queries"""
+    if not O.have_ref():
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    N = 300000
+    tree, m, c, o = synth.synth_msa(N, W=50000, L=1500, seed=20260117)
+    msa = O.MSA(m, c, o, 50000)
+    ref = O.Ref()
+    db = ref.db(msa)
+    rix = ref.kidx_build(db, 10, 0)
+    ix = sina_b200.Index(m, c, o, 50000, k=10)
+    info = ix.info()
+    assert info["n_tiles"] >= 4 and info["tile_size"] == 24 * 4096
+    fp, ap = sina_b200.FamParams(), sina_b200.AlignParams()
+    for kind, seed in (("full", 1000), ("v4", 1001)):
+        qm, qo = synth.synth_queries(tree, 64, kind, seed=seed)
+        queries = [O.decode(qm[int(qo[i]):int(qo[i + 1])]) for i in range(64)]
+        # find: rank order (score desc, id desc) of the first window
+        sc, ids, nres = ix.find(qm, qo, 41)
+        for i in range(0, 64, 8):
+            s1, i1, _ = ref.find(rix, queries[i], 41)
+            assert (ids[i, :41] == i1).all() and (sc[i, :41] == s1).all(), (kind, i)
+        # families
+        fids, fsc, fn = ix.family(qm, qo, fp)
+        for i in range(0, 64, 4):
+            n1, f1, s1 = ref.family(rix, queries[i], O.FamParams())
+            assert fn[i] == n1 and (fids[i, :n1] == f1).all() and (fsc[i, :n1] == s1).all(), (kind, i)
+        # whole path
+        oc, om, res = ix.run(qm, qo, fp, ap)
+        rres, roc, rqoff, *_ = ref.run_batch(rix, queries, O.FamParams(), O.AlignParams())
+        for i in range(64):
+            assert res[i]["status"] == rres[i].status, (kind, i)
+            if rres[i].status in (0, 1):
+                a, b, n = int(qo[i]), int(rqoff[i]), int(res[i]["n_out"])
+                assert (oc[a:a + n] == roc[b:b + n]).all(), (kind, i)
+            if rres[i].status == 0:
+                assert bits(res[i]["score"]) == bits(rres[i].score), (kind, i)
+                assert (res[i]["head"], res[i]["tail"], res[i]["qual"]) == (rres[i].head, rres[i].tail, rres[i].qual), (kind, i)
+    ref.kidx_free(rix)
+    ref.db_free(db)
+    ix.close()

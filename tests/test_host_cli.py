@@ -176,3 +176,33 @@ def test_cli_turn(orc, data, tmp_path):
     for i, w in enumerate(want):
         if w is not None:
             assert got["q%d" % i] == w, i
+
+
+def test_align_test_mimic_12x12_realign(orc, tmp_path):
+    """BASELINE configs[0], the reference's tests/align.test workload: every 1000th sequence of a database (12 of them)
+    is extracted and re-aligned against the extract itself with --realign (each query is contained in the database, so
+    its own row is dropped from the family, src/align.cpp:337-348); the test asserts 'align 12 sequences', exit 0 and that
+    writing to stdout gives the same bytes as writing to a file (tests/align.test:11-32). The ARB fixture cannot be read
+    here, so the database is synthetic; unlike the reference's test the aligned strings are pinned too."""
+    tree, m, c, o = synth.synth_msa(12000, W=5000, L=1500, seed=77)
+    big = O.MSA(m, c, o, 5000)
+    pick = list(range(0, 12000, 1000))
+    rows = [big.row_string(i) for i in pick]
+    names = ["seq%d" % i for i in pick]
+    write_fasta(tmp_path / "extracted.fasta", names, rows, width=80)
+    msa = O.MSA.from_rows(rows)
+    base = [os.path.join(BIN, "sina"), "-i", str(tmp_path / "extracted.fasta"), "--preserve-order", "--realign", "--db",
+            str(tmp_path / "extracted.fasta"), "--fs-engine", "internal", "--gpus", "1"]
+    r1 = subprocess.run(base + ["-o", str(tmp_path / "aligned.fasta")], capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stderr
+    assert "align 12 sequences" in r1.stderr
+    r2 = subprocess.run(base, capture_output=True, timeout=600)          # FASTA -> stdout
+    assert r2.returncode == 0 and b"align 12 sequences" in r2.stderr
+    assert r2.stdout == open(tmp_path / "aligned.fasta", "rb").read()     # cmp aligned.fasta aligned.2.fasta
+    got = read_fasta(tmp_path / "aligned.fasta")
+    qmasks = [msa.row(i)[0] & 15 for i in range(12)]
+    want, res = oracle_strings(orc, msa, qmasks, dict(realign=1), fp_kw={}, k=10)
+    assert list(got) == [names[i] for i in range(12) if want[i] is not None]
+    for i in range(12):
+        if want[i] is not None:
+            assert res[i].status == 0 and got[names[i]] == want[i], i
