@@ -45,9 +45,10 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --queries per step on every GPU; strong: --total-queries per step split over the GPUs")
     ap.add_argument("--total-queries", type=int, default=0, help="strong scaling: queries per step over all GPUs")
-    ap.add_argument("--shares", action="store_true",
-                    help="also measure one GPU's share of BASELINE configs[2] (V4) and configs[3] (full-length) against a "
-                         "500k-row reference, each with its own parity / roofline / cpu_baseline (adds several minutes)")
+    ap.add_argument("--no-shares", dest="shares", action="store_false",
+                    help="skip the sub-objects measured by default on one GPU: one GPU's share of BASELINE configs[2] (V4) and "
+                         "configs[3] (full-length) against a 500k-row reference, each with its own parity / roofline / "
+                         "cpu_baseline (they add 2-3 minutes)")
     a = ap.parse_args()
     if a.scaling == "strong":
         world = int(os.environ.get("WORLD_SIZE", "1"))
