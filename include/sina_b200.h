@@ -16,6 +16,8 @@
  *                                                                     src/mesh.h:453-739, src/cseq.cpp:456-594
  *   sg_run_batch         the famfinder -> aligner node pair           src/sina.cpp:511,516
  *   sg_turn_batch        famfinder::impl::turn_check (--turn)          src/famfinder.cpp:344-378
+ *   sg_index_set_column_weights   scoring_scheme_weighted + alignment_stats weights (--filter)
+ *                                                                     src/scoring_schemes.h:166-241, src/align.cpp:409-415
  *
  * Data layout: bases are SINA's IUPAC bit masks, one byte each (A=1 G=2 C=4 T/U=8, +16 lowercase;
  * src/aligned_base.h:38-52). A set of sequences is (masks[], off[n+1]); aligned rows add cols[] (alignment
@@ -99,6 +101,12 @@ int sg_device_count(void);
 int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* row_off, uint32_t N, uint32_t W,
                     int k, int nofast, int device, sg_index** out);
 void sg_index_destroy(sg_index* ix);
+/* Positional column weights of the alignment (alignment_stats::getWeights(), what --filter selects in the reference,
+ * src/alignment_stats.cpp:54-112): from then on the aligner scores with scoring_scheme_weighted
+ * (src/scoring_schemes.h:166-241, src/align.cpp:409-415) instead of scoring_scheme_simple. weights[W], one per column;
+ * n = 0 clears them. The reference reads weights[column + 1 + insertion length] without a bounds check; an index past
+ * W - 1 reads weights[W - 1] here. Not to be called while a batch is in flight on this index. */
+int sg_index_set_column_weights(sg_index* ix, const float* weights, uint32_t n);
 /* n_postings: total posting entries; n_tiles: reference-id tiles of the search histogram */
 int sg_index_info(const sg_index* ix, uint32_t* N, uint32_t* W, int* k, int* nofast, uint64_t* n_postings,
                   uint32_t* n_tiles, uint32_t* tile_size);

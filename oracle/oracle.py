@@ -207,6 +207,16 @@ class Oracle:
                                    u32p, u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.so_char_to_mask.restype = C.c_int
         L.so_mask_to_char.restype = C.c_int
+        L.so_set_column_weights.argtypes = [C.c_void_p, C.c_uint32]
+        self._colw = None
+
+    def set_column_weights(self, w):
+        """positional weights (scoring_scheme_weighted) for every later mesh / align / run_batch call; None = off"""
+        self._colw = None if w is None else np.ascontiguousarray(w, np.float32)
+        if self._colw is None:
+            self.L.so_set_column_weights(None, 0)
+        else:
+            self.L.so_set_column_weights(self._colw.ctypes.data_as(C.c_void_p), len(self._colw))
 
     def char_to_mask(self, c):
         return self.L.so_char_to_mask(C.c_int(ord(c)))
@@ -377,11 +387,20 @@ class Ref:
         L.ref_fix_duplicate_positions.restype = C.c_int
         L.ref_fix_duplicate_positions.argtypes = [C.c_uint32, u32p, u8p, C.c_uint32, C.c_int, u32p, u8p]
         L.ref_char_to_mask.restype = C.c_int
+        L.ref_set_column_weights.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.ref_cseq_roundtrip.restype = C.c_int
         L.ref_run_batch.restype = C.c_int
         L.ref_run_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(FamParams),
                                     C.POINTER(AlignParams), C.c_int, u64p, u32p, C.POINTER(RefResult),
                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+
+    def set_column_weights(self, w, pad=1 << 16):
+        """alignment_stats weights (--filter) for every later align / run_batch call; None = scoring_scheme_simple"""
+        if w is None:
+            self.L.ref_set_column_weights(None, 0, 0)
+        else:
+            w = np.ascontiguousarray(w, np.float32)
+            self.L.ref_set_column_weights(w.ctypes.data_as(C.c_void_p), len(w), pad)
 
     def char_to_mask(self, c):
         return self.L.ref_char_to_mask(C.c_ubyte(ord(c)))

@@ -414,11 +414,17 @@ static bool iequals(const std::string& a, const std::string& b) {
 
 struct align_item { float score; const cseq* sequence; };
 
+// per-column weights of the alignment (alignment_stats::getWeights(), what --filter selects; empty = no filter).
+// The reference indexes them up to position + 1 + insertion length without a bounds check (scoring_schemes.h:186-201):
+// the test harness pads the vector so that those reads are defined (the padding repeats the last weight, the rule
+// the oracle and the CUDA path use).
+static std::vector<float> g_col_weights;
+
 // do_align (align.cpp:475-521) for one transition type: transition_simple, or transition_aspace_aware for
 // --insertion forbid (choose_transition, align.cpp:462-473)
 extern "C++" {
-template <typename TR>
-static bool run_dp(mseq& m, cseq& c, const scoring_scheme_simple& s, const ref_align_params& P, ref_align_result& R,
+template <typename TR, typename SCHEME>
+static bool run_dp(mseq& m, cseq& c, const SCHEME& s, const ref_align_params& P, ref_align_result& R,
                    std::stringstream& log, std::string* logstr, uint32_t* cells, uint64_t cells_cap_words) {
     using cell_t = typename TR::data_type;
     TR tr(s);
@@ -501,10 +507,19 @@ static void align_one(ref_db* db, std::vector<align_item>& vc, const cseq& input
         m.sort();
         m.reduce_edges();
         R.n_nodes = m.size();
-        scoring_scheme_simple s(-P.match_score, -P.mismatch_score, P.gap_penalty, P.gap_ext_penalty);
-        const bool ok = P.insertion == INSERTION_FORBID
-            ? run_dp<transition_aspace_aware<scoring_scheme_simple, mseq, cseq>>(m, c, s, P, R, log, logstr, cells, cells_cap_words)
-            : run_dp<mesh_tr>(m, c, s, P, R, log, logstr, cells, cells_cap_words);
+        bool ok;
+        if (g_col_weights.empty()) {   // astats width 0: scoring_scheme_simple (align.cpp:405-408)
+            scoring_scheme_simple s(-P.match_score, -P.mismatch_score, P.gap_penalty, P.gap_ext_penalty);
+            ok = P.insertion == INSERTION_FORBID
+                ? run_dp<transition_aspace_aware<scoring_scheme_simple, mseq, cseq>>(m, c, s, P, R, log, logstr, cells, cells_cap_words)
+                : run_dp<mesh_tr>(m, c, s, P, R, log, logstr, cells, cells_cap_words);
+        } else {                       // positional weights (--filter): scoring_scheme_weighted (align.cpp:409-415)
+            std::vector<float> weights = g_col_weights;
+            scoring_scheme_weighted s(-P.match_score, -P.mismatch_score, P.gap_penalty, P.gap_ext_penalty, weights);
+            ok = P.insertion == INSERTION_FORBID
+                ? run_dp<transition_aspace_aware<scoring_scheme_weighted, mseq, cseq>>(m, c, s, P, R, log, logstr, cells, cells_cap_words)
+                : run_dp<transition_simple<scoring_scheme_weighted, mseq, cseq>>(m, c, s, P, R, log, logstr, cells, cells_cap_words);
+        }
         if (!ok) return;
     }
     aligned = c.getAligned(true, false);  // rw_fasta.cpp:520
@@ -513,6 +528,11 @@ static void align_one(ref_db* db, std::vector<align_item>& vc, const cseq& input
         for (const auto& ab : c.getAlignedBases()) out_cols->push_back(ab.getPosition());
     }
     if (logstr) *logstr = log.str();
+}
+
+void ref_set_column_weights(const float* w, uint32_t n, uint32_t pad) {
+    g_col_weights.assign(w, w + n);
+    if (n) g_col_weights.resize((size_t)n + pad, w[n - 1]);
 }
 
 // Align `query` against the given family (ids into db, family order as given).

@@ -448,6 +448,16 @@ void so_graph_free(so_graph* g) {
     free(g);
 }
 
+/* ------------------------------------------------------------------ positional weights */
+/* scoring_scheme_weighted (src/scoring_schemes.h:166-241, chosen when the alignment statistics have a width,
+ * src/align.cpp:409-415): gap costs and match scores are multiplied by the weight of an alignment column. The
+ * reference reads weights[position + 1 + insertion length] without a bounds check; here an index past the end reads
+ * the last weight (the only place where this restatement has to DEFINE something the reference leaves undefined). */
+static const float* g_colw = NULL;
+static uint32_t g_ncolw = 0;
+void so_set_column_weights(const float* w, uint32_t n) { g_colw = n ? w : NULL; g_ncolw = n; }
+static inline float colw(uint32_t i) { return g_colw[i < g_ncolw ? i : g_ncolw - 1]; }
+
 /* ------------------------------------------------------------------ mesh DP */
 /* compute() src/mesh.h:509-528 over compute_node_simple::calc :453-502 with transition_simple
  * :305-374 and scoring_scheme_simple src/scoring_schemes.h:102-164. Scores are minimised. */
@@ -476,6 +486,10 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
     for (uint32_t m = 0; m < g->V; m++) {
         uint32_t pb = g->pred_off[m], pe = g->pred_off[m + 1];
         float w = g->weight[m];
+        /* weighted scheme: deletions cost gap * weights[col(m)] (scoring_schemes.h:203-222), matches score
+         * (match * weights[col(m)]) * weight(m) (:224-232), all with the TARGET node's column */
+        const float wm = g_colw ? colw(g->col[m]) : 1.0f;
+        const float gpm = g_colw ? gp * wm : gp, gpem = g_colw ? gpe * wm : gpe;
         const uint32_t smax = forbid ? (uint32_t)(int)(min_mpos[m] - g->col[m] - 1) : 0;
         for (uint32_t s = 0; s < L; s++) {
             uint64_t o = (uint64_t)m * L + s;
@@ -486,8 +500,8 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
             for (uint32_t e = pb; e < pe; e++) { /* deletion :475-478 -> :305-330 */
                 uint32_t mi = g->preds[e];
                 uint64_t so = (uint64_t)mi * L + s;
-                float v = M->value[so] + gp;
-                float gv = M->gapm_val[so] + gpe;
+                float v = M->value[so] + gpm;
+                float gv = M->gapm_val[so] + gpem;
                 uint32_t midx = mi;
                 if (v < gv) { gapm_val = v; gapm_idx = mi; }
                 else { gapm_val = gv; gapm_idx = M->gapm_idx[so]; v = gv; midx = M->gapm_idx[so]; }
@@ -496,15 +510,19 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
             if (s > 0) { /* insertion :486-490 -> :332-358 */
                 uint64_t so = o - 1;
                 int evaluated = 1;
+                /* insertion costs: gap * weights[col(m) + 1] to open, gapext * weights[col(m) + 1 + run length] to
+                 * extend (scoring_schemes.h:178-201: the column the inserted base will be placed in) */
+                const float gpi = g_colw ? gp * colw(g->col[m] + 1) : gp;
+                const float gpei = g_colw ? gpe * colw(g->col[m] + 1 + ((s - 1) - M->gaps_idx[so])) : gpe;
                 if (!forbid) {
-                    if (M->gaps_val[so] != M->value[so]) { gaps_val = M->value[so] + gp; gaps_idx = s - 1; }
-                    else { gaps_val = M->gaps_val[so] + gpe; gaps_idx = M->gaps_idx[so]; }
+                    if (M->gaps_val[so] != M->value[so]) { gaps_val = M->value[so] + gpi; gaps_idx = s - 1; }
+                    else { gaps_val = M->gaps_val[so] + gpei; gaps_idx = M->gaps_idx[so]; }
                 } else if (smax < 1) {
                     evaluated = 0;                                        /* can't insert :412-414 */
                 } else if (M->gaps_val[so] != M->value[so]) {              /* opening gap :416-420 */
-                    gaps_val = M->value[so] + gp; gaps_idx = s - 1; gaps_max[o] = smax - 1;
+                    gaps_val = M->value[so] + gpi; gaps_idx = s - 1; gaps_max[o] = smax - 1;
                 } else if (gaps_max[so] > 0) {                             /* extending gap :421-426 */
-                    gaps_val = M->gaps_val[so] + gpe; gaps_idx = M->gaps_idx[so]; gaps_max[o] = gaps_max[so] - 1;
+                    gaps_val = M->gaps_val[so] + gpei; gaps_idx = M->gaps_idx[so]; gaps_max[o] = gaps_max[so] - 1;
                 } else {
                     evaluated = 0;                                        /* :427-429 */
                 }
@@ -512,7 +530,9 @@ so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t L, const 
                 for (uint32_t e = pb; e < pe; e++) { /* match :492-500 -> :360-374 */
                     uint32_t mi = g->preds[e];
                     uint64_t po = (uint64_t)mi * L + (s - 1);
-                    float sc = ((g->mask[m] & q[s] & 0xf) ? ms : mms) * w; /* scoring_schemes.h:150-156 */
+                    float sc = (g->mask[m] & q[s] & 0xf) ? ms : mms;
+                    if (g_colw) sc = sc * wm;                              /* scoring_schemes.h:224-232 */
+                    sc = sc * w;                                           /* scoring_schemes.h:150-156 */
                     float v = M->value[po] + sc;
                     if (v < value) { value = v; value_midx = mi; value_sidx = s - 1; }
                 }
@@ -639,7 +659,7 @@ int so_backtrack(const so_graph* g, const so_mesh* M, const uint8_t* q, uint32_t
     uint32_t pos = W - 1 - g->col[m];                  /* :620 */
     float sum_weight = 0;
     out_append(&o, pos, q[s]);                         /* :626-628 */
-    sum_weight = sum_weight + ms * g->weight[m];       /* :631-638: forced match */
+    sum_weight = sum_weight + (g_colw ? ms * colw(g->col[m]) : ms) * g->weight[m];   /* :631-638: forced match */
     while (s != 0 && !is_first[m]) {                   /* :642-685 */
         uint32_t snew = M->value_sidx[CELL(m, s)];
         m = M->value_midx[CELL(m, s)];
@@ -648,7 +668,7 @@ int so_backtrack(const so_graph* g, const so_mesh* M, const uint8_t* q, uint32_t
         while (s != snew) {
             --s;
             out_append(&o, pos, q[s]);
-            sum_weight = sum_weight + ms * g->weight[m];
+            sum_weight = sum_weight + (g_colw ? ms * colw(g->col[m]) : ms) * g->weight[m];
         }
     }
 #undef CELL

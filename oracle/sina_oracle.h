@@ -99,6 +99,9 @@ typedef struct so_mesh { /* full mesh in the reference's field set (src/mesh.h:2
     uint32_t *value_midx, *value_sidx, *gapm_idx, *gaps_idx;
     float *value, *gapm_val, *gaps_val;
 } so_mesh;
+/* positional column weights for every later so_mesh_compute / so_backtrack / so_align / so_run_batch (n = 0: none).
+ * The pointer is kept, not copied. src/scoring_schemes.h:166-241 */
+void so_set_column_weights(const float* w, uint32_t n);
 so_mesh* so_mesh_compute(const so_graph* g, const uint8_t* q, uint32_t qlen, const so_align_params* p);
 void so_mesh_free(so_mesh* m);
 

@@ -231,9 +231,24 @@ void sg_index_destroy(sg_index* h) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     if (ix->cached) { sg_session_destroy((sg_session*)ix->cached); ix->cached = nullptr; }
-    cudaFree(ix->d_masks); cudaFree(ix->d_cols); cudaFree(ix->d_row_off); cudaFree(ix->d_list_off);
+    cudaFree(ix->d_masks); cudaFree(ix->d_cols); cudaFree(ix->d_row_off); cudaFree(ix->d_list_off); cudaFree(ix->d_colw);
     cudaFree(ix->d_postings);
     delete ix;
+}
+
+int sg_index_set_column_weights(sg_index* h, const float* weights, uint32_t n) {
+    Index* ix = (Index*)h;
+    if (!ix) SG_FAIL(SG_ERR_ARG, "null index");
+    if (n != 0 && (n != ix->W || !weights)) SG_FAIL(SG_ERR_ARG, "sg_index_set_column_weights: one weight per alignment column (or n = 0 for none)");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    SG_CUDA(cudaSetDevice(ix->device));
+    SG_CUDA(cudaDeviceSynchronize());
+    if (ix->d_colw) { cudaFree(ix->d_colw); ix->d_colw = nullptr; }
+    if (n == 0) return SG_OK;
+    for (uint32_t i = 0; i < n; i++) if (!(weights[i] == weights[i])) SG_FAIL(SG_ERR_ARG, "sg_index_set_column_weights: NaN weight");
+    SG_TRY(dmalloc(&ix->d_colw, (uint64_t)n));
+    SG_CUDA(cudaMemcpy(ix->d_colw, weights, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return SG_OK;
 }
 
 int sg_index_info(const sg_index* h, uint32_t* N, uint32_t* W, int* k, int* nofast, uint64_t* n_postings,

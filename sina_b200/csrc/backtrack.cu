@@ -44,6 +44,7 @@ struct BtArgs {
     NodeRec* rec;
     uint32_t* out_cols; uint8_t* out_masks; sg_align_result* results;
     float ms; int overhang, lowercase;
+    const float* colw; uint32_t ncolw;   // positional weights (scoring_scheme_weighted, generic DP kernel), null = none
 };
 
 constexpr int BT_WARPS = 2;   // queries per CTA
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     const uint8_t* tbq8 = reinterpret_cast<const uint8_t*>(tbq);
     const bool wide = h.wide != 0;
     const bool v2 = h.mode == 2;   // cells written by the v2 DP kernel: two query positions per step (common.cuh)
+    const bool weighted = A.colw != nullptr;
     const uint32_t V = h.V, W = A.W;
     const uint32_t T = DP_T;
     NodeRec* rec = A.rec + io;
@@ -233,10 +235,12 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
             else out = TB_SRC_MATCH | ((idx - 1u - slots) << 8);
             return out | ((c >> 7) << 2);
         }
+        // generic kernel: bit 2 = ob (weighted scheme: the LAST predecessor's deletion opened), bit 3 (weighted scheme
+        // only) = the chosen deletion opened
         const uint32_t t = s + (a.y & 0xffffu);
         if (wide) return (raw >> (16 * (t & 1))) & 0xffffu;
         const uint32_t c = (raw >> (8 * (t & 1))) & 0xffu;
-        return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2);
+        return (c & 3u) | (((c >> 2) & 7u) << 8) | (((c >> 5) & 1u) << 2) | (((c >> 6) & 1u) << 3);
     };
     auto cell = [&](const uint4& a, uint32_t s) -> uint32_t { return cell_dec(a, s, cell_raw(a, s)); };
     auto np_of = [](const uint4& a) -> uint32_t { return a.y >> 24; };
@@ -270,7 +274,26 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         if (src == TB_SRC_NONE) { nm = 0; ns = 0; }
         else if (src == TB_SRC_MATCH) { nm = pred_of(a, b, ord); ns = s - 1; }
         else if (src == TB_SRC_INS) { nm = m; ns = gaps_idx(a, s); }
-        else {
+        else if (weighted) {
+            // weighted scheme: whether a deletion opens depends on the TARGET node's column weight, so the facts are in
+            // the target's cells: the chosen deletion via p opened (bit 3 of (m,s)) -> (p, s); else gapm_idx(p, s) with
+            // gapm_idx(x, s) = "last predecessor's deletion opened" (bit 2 of (x,s)) ? lastpred(x) : gapm_idx(lastpred(x), s),
+            // 0 for a row without predecessor (mesh.h:305-330)
+            uint32_t x = pred_of(a, b, ord);
+            if (!(c & 8u)) {
+                for (;;) {
+                    uint4 xa, xb;
+                    ldrec(x, xa, xb);
+                    const uint32_t np = np_of(xa);
+                    if (np == 0) { x = 0; break; }
+                    const bool opened = cell(xa, s) & 4u;
+                    x = pred_of(xa, xb, np - 1);
+                    if (opened) break;
+                }
+            }
+            nm = x;
+            ns = s;
+        } else {
             // deletion via predecessor p: (p, s) if it opened there, else gapm_idx(p, s): down the chain of last
             // predecessors to the first cell whose deletion opens; a row without predecessor ends it at node 0
             // (init_edge, mesh.h:294-297)
@@ -387,7 +410,12 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     for (uint32_t j0 = 0; j0 <= s_end - s_fin; j0 += 32) {
         const uint32_t j = j0 + lane;
         const bool in = j <= s_end - s_fin;
-        const float pw = in ? __fmul_rn(A.ms, nweight[ocols[s_end - j]]) : 0.f;
+        float pw = 0.f;
+        if (in) {   // match score of a forced match (mesh.h:631-638,683); weighted scheme: (match * weights[col]) * node weight
+            const uint32_t node = ocols[s_end - j];
+            pw = weighted ? __fmul_rn(__fmul_rn(A.ms, A.colw[min(A.ncol[io + node], A.ncolw - 1u)]), nweight[node])
+                          : __fmul_rn(A.ms, nweight[node]);
+        }
         const uint32_t cnt = min(32u, s_end - s_fin + 1 - j0);
         for (uint32_t l = 0; l < cnt; l++) sum_weight = __fadd_rn(sum_weight, __shfl_sync(FULL, pw, l));
     }
@@ -477,6 +505,7 @@ int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32
     A.rec = reinterpret_cast<NodeRec*>(w->d_rec);
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;
     A.ms = -ap.match_score; A.overhang = ap.overhang; A.lowercase = ap.lowercase;
+    A.colw = ix->d_colw; A.ncolw = ix->W;
     backtrack_kernel<<<(n + BT_WARPS - 1) / BT_WARPS, 32 * BT_WARPS, 0, w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;

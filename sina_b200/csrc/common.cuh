@@ -100,6 +100,7 @@ struct Index {
     uint32_t* d_list_off = nullptr; // [n_slots*n_sub + 1], k-mer-major: list (v, j) = postings[off[v*n_sub+j] .. off[v*n_sub+j+1])
     uint16_t* d_postings = nullptr; // reference id minus the sub-tile's first id, unordered inside a list
     uint64_t n_postings = 0;
+    float* d_colw = nullptr;        // [W] positional column weights (scoring_scheme_weighted), null = none
     void* cached = nullptr;  // Session reused by the host-buffer entry points
     std::mutex mu;           // serialises host-buffer calls on this index
 };

@@ -1025,7 +1025,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cursor = w->d_cursor; A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.pdesc = w->d_pdesc;
     A.spillrow = w->d_spillrow; A.nflags = w->d_nflags; A.lastnodes = w->d_lastnodes; A.groups = w->d_groups;
     A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
-    A.force_generic = s->force_generic || ap.insertion == 1;   // the aspace-aware transition lives in the generic kernel
+    A.force_generic = s->force_generic || ap.insertion == 1 || ix->d_colw != nullptr;   // the aspace-aware transition and the weighted scheme live in the generic kernel
     A.nmaxins = w->d_nmaxins; A.forbid = ap.insertion == 1;
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;

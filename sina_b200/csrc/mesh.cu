@@ -34,6 +34,7 @@ struct MeshArgs {
     float* lastcol; float* rowmin; uint32_t* rowarg;
     float ms, mms, gp, gpe;  // -match_score, -mismatch_score, gap_penalty, gap_ext_penalty (align.cpp:406-407)
     uint32_t nw;             // v2: 32-bit words per plane of the query match-bit table
+    const float* colw; uint32_t ncolw; const uint32_t* ncol;   // positional weights (scoring_scheme_weighted): generic kernel only
 };
 
 constexpr int T = DP_T;        // rows per group
@@ -531,7 +532,12 @@ __device__ __forceinline__ void v2_build_qbits(const GraphHdr& h, const uint8_t*
 // v1: generic fallback (hdr.mode == 1). Rows keep id order inside a group; far predecessors are read
 // straight from the spill buffer; every row tracks its own spill / row-minimum.
 // ====================================================================================================
-template <bool WIDE>
+// WEIGHTED: scoring_scheme_weighted (src/scoring_schemes.h:166-241, chosen when --filter supplies positional weights,
+// src/align.cpp:409-415): gap costs and match scores are multiplied by the weight of the TARGET node's column, so a
+// deletion candidate cannot be computed once by the row it leaves from: the ring / spill cells hold (value, gapm_val) and
+// every edge evaluates deletion() as the reference does; the traceback cell records whether the chosen deletion opened and
+// whether the last predecessor's did (the latter is what gapm_idx chains follow, see backtrack.cu).
+template <bool WIDE, bool WEIGHTED>
 __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, uint32_t ql, float2* ring,
                                          const uint8_t* qm) {
     const uint32_t tid = threadIdx.x;
@@ -550,7 +556,8 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
         const bool valid = tid < (uint32_t)T && m < V;
         uint32_t np = 0, pbase = 0, mask = 0;
         int soff = 0, sr = -1;
-        float msw = 0.f, mmsw = 0.f;
+        float msw = 0.f, mmsw = 0.f, gpm = gp, gpem = gpe;
+        uint32_t icol = 0, gidx_prev = 0;       // WEIGHTED: column after the node; gaps_idx of (m, s-1)
         bool is_last = false;
         uint32_t pd[NPR];
         float pv_prev[NPR];
@@ -561,8 +568,18 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
             np = pred_off[m + 1] - pbase;
             mask = A.nmask[io + m];
             const float w = A.nweight[io + m];
-            msw = __fmul_rn(A.ms, w);
-            mmsw = __fmul_rn(A.mms, w);
+            if (WEIGHTED) {
+                const uint32_t cm = A.ncol[io + m];
+                const float wm = A.colw[min(cm, A.ncolw - 1u)];
+                msw = __fmul_rn(__fmul_rn(A.ms, wm), w);      // (match * weights[col]) * node weight (scoring_schemes.h:224-232)
+                mmsw = __fmul_rn(__fmul_rn(A.mms, wm), w);
+                gpm = __fmul_rn(gp, wm);                      // deletions happen in the node's own column (:203-222)
+                gpem = __fmul_rn(gpe, wm);
+                icol = cm + 1u;                               // insertions go to the columns after it (:178-201)
+            } else {
+                msw = __fmul_rn(A.ms, w);
+                mmsw = __fmul_rn(A.mms, w);
+            }
             soff = (int)(A.nsigma[io + m] - gi.sigma_lo);
             sr = A.spillrow[io + m];
             is_last = A.nflags[io + m] == 0;
@@ -587,7 +604,19 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                 float value = edge ? 1.0f : 1000000.0f;
                 float gapm = value;
                 float pv_cur[NPR];
+                bool last_open = false;
                 auto del_step = [&](uint32_t i, float2 c) {              // mesh.h:305-330; c.y = the predecessor's dm
+                    if (WEIGHTED) {            // c.y = the predecessor's gapm_val: the edge is evaluated here
+                        const float v = __fadd_rn(c.x, gpm), gv = __fadd_rn(c.y, gpem);
+                        last_open = v < gv;
+                        const float cand = last_open ? v : gv;
+                        gapm = cand;           // last predecessor wins
+                        if (cand < value) {
+                            value = cand;
+                            code = (WIDE ? (TB_SRC_DEL | (i << 8)) : (TB_SRC_DEL | (i << 2))) | (last_open ? (WIDE ? 8u : 64u) : 0u);
+                        }
+                        return;
+                    }
                     gapm = c.y;                // last predecessor wins
                     if (c.y < value) {
                         value = c.y;
@@ -611,20 +640,28 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                     del_step(i, load_cell(d, s, t));
                 }
                 float E = edge ? 1.0f : 1000000.0f;                      // gaps_val as initialised (mesh.h:294-301)
-                uint32_t gmax = 0;
+                uint32_t gmax = 0, gidx = 0;
                 if (s > 0) {
                     bool evaluated = true;
+                    float gpi = gp, gpei = gpe;
+                    const bool opening = E_prev != H_prev;
+                    if (WEIGHTED) {   // the column the inserted base will be placed in (scoring_schemes.h:178-201)
+                        gpi = __fmul_rn(gp, A.colw[min(icol, A.ncolw - 1u)]);
+                        gpei = __fmul_rn(gpe, A.colw[min(icol + ((uint32_t)s - 1u - gidx_prev), A.ncolw - 1u)]);
+                        gidx = opening ? (uint32_t)s - 1u : gidx_prev;    // gaps_idx (mesh.h:343-348), kept as initialised (0) if not evaluated
+                    }
                     if (!A.forbid) {                                     // transition_simple::insertion, mesh.h:332-358
-                        E = (E_prev != H_prev) ? __fadd_rn(H_prev, gp) : __fadd_rn(E_prev, gpe);
+                        E = opening ? __fadd_rn(H_prev, gpi) : __fadd_rn(E_prev, gpei);
                     } else if (maxins < 1) {                             // transition_aspace_aware, mesh.h:403-438
                         evaluated = false;
-                    } else if (E_prev != H_prev) {
-                        E = __fadd_rn(H_prev, gp); gmax = maxins - 1;
+                    } else if (opening) {
+                        E = __fadd_rn(H_prev, gpi); gmax = maxins - 1;
                     } else if (gmax_prev > 0) {
-                        E = __fadd_rn(E_prev, gpe); gmax = gmax_prev - 1;
+                        E = __fadd_rn(E_prev, gpei); gmax = gmax_prev - 1;
                     } else {
                         evaluated = false;
                     }
+                    if (WEIGHTED && !evaluated) gidx = 0;
                     if (evaluated && E <= value) { value = E; code = TB_SRC_INS; }
                     const float sc = (mask & qm[s] & 15u) ? msw : mmsw;  // mesh.h:360-374
 #pragma unroll
@@ -641,11 +678,12 @@ __device__ __forceinline__ void v1_query(const MeshArgs& A, const GraphHdr& h, u
                     }
                 }
                 const float vgp = __fadd_rn(value, gp), ggpe = __fadd_rn(gapm, gpe);
-                if (vgp < ggpe) code |= WIDE ? 4u : 32u;                 // ob: a deletion leaving this cell opens
-                E_prev = E; H_prev = value; gmax_prev = gmax;
+                if (WEIGHTED) { if (last_open) code |= WIDE ? 4u : 32u; }   // the last predecessor's deletion opened (gapm_idx chains)
+                else if (vgp < ggpe) code |= WIDE ? 4u : 32u;            // ob: a deletion leaving this cell opens
+                E_prev = E; H_prev = value; gmax_prev = gmax; gidx_prev = gidx;
 #pragma unroll
                 for (int i = 0; i < NPR; i++) pv_prev[i] = pv_cur[i];
-                const float2 out = make_float2(value, fminf(vgp, ggpe));
+                const float2 out = WEIGHTED ? make_float2(value, gapm) : make_float2(value, fminf(vgp, ggpe));
                 ring[(t & (R - 1)) * S + tid] = out;
                 if (sr >= 0) __stcg(&spill_w[(uint64_t)sr * Lq2 + s], out);
                 if (s == (int)Lq - 1) A.lastcol[io + m] = value;
@@ -678,8 +716,11 @@ __global__ void __launch_bounds__(DP_BLOCK, DP_CTAS_PER_SM) mesh_kernel(MeshArgs
         uint8_t* qm = smem + RING2_BYTES + 16 + QPAD;
         for (uint32_t i = threadIdx.x; i < h.qlen; i += blockDim.x) qm[i] = src[i];
         __syncthreads();
-        if (h.wide) v1_query<true>(A, h, blockIdx.x, ring, qm);
-        else v1_query<false>(A, h, blockIdx.x, ring, qm);
+        if (A.colw) {
+            if (h.wide) v1_query<true, true>(A, h, blockIdx.x, ring, qm);
+            else v1_query<false, true>(A, h, blockIdx.x, ring, qm);
+        } else if (h.wide) v1_query<true, false>(A, h, blockIdx.x, ring, qm);
+        else v1_query<false, false>(A, h, blockIdx.x, ring, qm);
         return;
     }
     uint32_t* qbt = reinterpret_cast<uint32_t*>(smem + RING2_BYTES + 16);
@@ -708,6 +749,7 @@ int launch_mesh(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q0
     A.nmaxins = w->d_nmaxins; A.forbid = ap.insertion == 1;
     A.tb = w->d_tb; A.spill = w->d_spill; A.lastcol = w->d_lastcol; A.rowmin = w->d_rowmin; A.rowarg = w->d_rowarg;
     A.ms = -ap.match_score; A.mms = -ap.mismatch_score; A.gp = ap.gap_penalty; A.gpe = ap.gap_ext_penalty;
+    A.colw = s->ix->d_colw; A.ncolw = s->ix->W; A.ncol = w->d_ncol;
     uint32_t max_qlen = 0;
     for (uint32_t i = q0; i < q0 + n; i++) {
         uint32_t l = (uint32_t)(s->h_qoff[i + 1] - s->h_qoff[i]);

@@ -1,6 +1,7 @@
 #include "align.h"
 
 #include <ctime>
+#include <fstream>
 
 #include "../../include/sina_b200.h"
 #include "famfinder.h"
@@ -50,9 +51,26 @@ void aligner::get_options_description(po::options_description& /*main*/, po::opt
 
 void aligner::validate_vm(po::variables_map& /*vm*/, po::options_description& /*desc*/) {}
 
+// --filter-weights: the positional weights alignment_stats computes from an ARB SAI (src/alignment_stats.cpp:54-112),
+// given directly, one per alignment column
+static std::vector<float> load_weights(const std::string& path, unsigned int width) {
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("Unable to open column weights file '" + path + "'");
+    std::vector<float> w;
+    float x;
+    while (in >> x) w.push_back(x);
+    if (!in.eof()) throw std::runtime_error("column weights file '" + path + "': not a number after " + std::to_string(w.size()) + " values");
+    if (w.size() != width)
+        throw std::runtime_error("column weights file '" + path + "' holds " + std::to_string(w.size()) + " values, the alignment has " +
+                                 std::to_string(width) + " columns");
+    return w;
+}
+
 aligner::aligner(int device)
     : index(kmer_search::get_kmer_search(famfinder::opts.database, (int)famfinder::opts.fs_kmer_len, famfinder::opts.fs_no_fast, device)) {
     if (!opts) opts = new options();
+    if (!famfinder::opts.filter_weights.empty())
+        index->set_column_weights(load_weights(famfinder::opts.filter_weights, index->db().getAlignmentWidth()));
 }
 aligner::aligner(const aligner& rhs)
     : index(kmer_search::get_kmer_search(famfinder::opts.database, (int)famfinder::opts.fs_kmer_len, famfinder::opts.fs_no_fast, rhs.index->device())) {}
@@ -142,7 +160,7 @@ void aligner::run(std::vector<tray*>& trays, bool rethrow) {
             }
         }
         c->set_attr<std::string>(fn_date, now);
-        c->set_attr<std::string>(fn_filter, "");
+        c->set_attr<std::string>(fn_filter, famfinder::opts.filter_weights);   // astats->getName() in the reference (src/align.cpp:456)
         delete t.aligned_sequence;
         t.aligned_sequence = c;
     }

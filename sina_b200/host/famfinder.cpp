@@ -49,7 +49,9 @@ void famfinder::get_options_description(po::options_description& main, po::optio
     od.unsupported("gene-start", true, "gene range quotas need ARB field data");
     od.unsupported("gene-end", true, "gene range quotas need ARB field data");
     od.unsupported("fs-cover-gene", true, "gene range quotas need ARB field data");
-    od.unsupported("filter", true, "positional variability filters are ARB SAI data");
+    od.unsupported("filter", true, "positional variability filters are ARB SAI data; pass the column weights themselves with --filter-weights FILE");
+    od.value<std::string>("filter-weights", &opts.filter_weights, "", "[sina_b200] file with one positional weight per alignment column "
+                          "(whitespace separated; alignment_stats::getWeights(), src/alignment_stats.cpp:54-112): selects the weighted scoring scheme");
     od.unsupported("auto-filter-field", true, "positional variability filters are ARB SAI data");
     od.unsupported("auto-filter-threshold", true, "positional variability filters are ARB SAI data");
     od.unsupported("fs-oldmatch", false, "legacy PT-server family composition");

@@ -42,6 +42,7 @@ public:
         unsigned int fs_kmer_len = 10, fs_kmer_mm = 0;
         bool fs_kmer_norel = false;
         std::string database;
+        std::string filter_weights;   // [sina_b200] file with one positional weight per alignment column (what --filter computes from an ARB SAI)
     };
     static options opts;
 };

@@ -55,6 +55,10 @@ kmer_search* kmer_search::get_kmer_search(const std::string& database, int k, bo
     return new kmer_search(it->second);
 }
 
+void kmer_search::set_column_weights(const std::vector<float>& w) {
+    check_sg(sg_index_set_column_weights(pimpl->ix, w.empty() ? nullptr : w.data(), (uint32_t)w.size()), "setting the column weights");
+}
+
 void kmer_search::release_kmer_search(const std::string& database, int k, bool nofast, int device) {
     std::lock_guard<std::mutex> lock(g_mu);
     g_indices.erase(key_t(database, k, nofast, device));

@@ -27,6 +27,9 @@ public:
     unsigned int size() const override;
 
     sg_index* handle() const;
+    /// positional weights of the alignment's columns (alignment_stats::getWeights()): the aligner then scores with
+    /// scoring_scheme_weighted (src/align.cpp:409-415); an empty vector switches back to scoring_scheme_simple
+    void set_column_weights(const std::vector<float>& w);
     const reference_db& db() const;
     int device() const;
 

@@ -317,6 +317,51 @@ def test_chunk_pipeline_and_arena_retry(orc, monkeypatch):
     orc.index_free(oix)
 
 
+def test_weighted_scoring_vs_oracle(orc):
+    """positional column weights (--filter): scoring_scheme_weighted (src/scoring_schemes.h:166-241) through
+    sg_index_set_column_weights against the oracle (pinned to the compiled reference's weighted scheme in
+    tests/test_oracle_vs_ref.py): small random families incl. --insertion forbid, and a batch of full graphs"""
+    rng = np.random.default_rng(77)
+    try:
+        for it in range(30):
+            rows, q = synth.random_case(rng, lowercase=0.05 if it % 3 == 0 else 0.0)
+            msa = O.MSA.from_rows(rows)
+            w = np.where(rng.random(msa.W) < 0.3, 1.0, 0.5 - np.log(rng.uniform(1e-6, 0.95, msa.W))).astype(np.float32)
+            ap_kw = dict(overhang=it % 3, lowercase=[0, 2, 1][(it // 3) % 3], fs_weight=[1.0, 0.0, 2.5][it % 3], realign=1,
+                         insertion=1 if it % 4 == 3 else 0)
+            if it % 5 == 4:
+                ap_kw.update(match_score=1.7, mismatch_score=-0.9, gap_penalty=4.3, gap_ext_penalty=1.1)
+            qm = O.encode(q)
+            orc.set_column_weights(w)
+            r1, c1, m1, _ = orc.align(msa, np.arange(msa.N), qm, O.AlignParams(**ap_kw))
+            ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=4)
+            ix.set_column_weights(w)
+            fam = np.arange(msa.N, dtype=np.uint32)
+            oc, om, res = ix.align(qm, np.array([0, len(qm)], np.uint64), fam, np.array([0, msa.N], np.uint64), sina_b200.AlignParams(**ap_kw))
+            compare_result(res[0], oc, om, r1, c1, m1, msa.W, (it, ap_kw))
+            ix.close()
+        # whole pipeline on larger graphs; switching the weights off again restores the simple scheme
+        tree, m, c, o = synth.synth_msa(300, W=900, L=260, seed=5)
+        msa = O.MSA(m, c, o, 900)
+        oix = orc.index_build(msa, 6, 0)
+        qm, qo = synth.synth_queries(tree, 24, "full", seed=29)
+        fp_kw = dict(fs_min=20, fs_max=20, fs_min_len=100, fs_full_len=240, fs_req_gaps=5)
+        w = (0.5 - np.log(rng.uniform(1e-4, 0.95, 900))).astype(np.float32)
+        ix = sina_b200.Index(m, c, o, 900, k=6)
+        for weights in (w, None):
+            orc.set_column_weights(weights)
+            ix.set_column_weights(weights)
+            oc, om, res = ix.run(qm, qo, sina_b200.FamParams(**fp_kw), sina_b200.AlignParams())
+            ores, occ, omm, *_ = orc.run_batch(oix, msa, qm, qo, O.FamParams(**fp_kw), O.AlignParams(), nthreads=4)
+            for i in range(24):
+                a, b = int(qo[i]), int(qo[i + 1])
+                compare_result(res[i], oc[a:b], om[a:b], ores[i], occ[a:a + ores[i].n_out], omm[a:a + ores[i].n_out], 900, (weights is None, i))
+        ix.close()
+        orc.index_free(oix)
+    finally:
+        orc.set_column_weights(None)
+
+
 def test_oversized_query_fails_alone(orc, monkeypatch):
     """per-query soft failure: a query whose traceback does not fit the arena even alone gets status SG_Q_LIMIT; the
     rest of the batch is aligned as usual, and the session stays usable for the next call"""

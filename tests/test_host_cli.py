@@ -206,3 +206,30 @@ def test_align_test_mimic_12x12_realign(orc, tmp_path):
     for i in range(12):
         if want[i] is not None:
             assert res[i].status == 0 and got[names[i]] == want[i], i
+
+
+def test_cli_filter_weights(orc, data, tmp_path):
+    """--filter-weights FILE: positional column weights -> scoring_scheme_weighted (src/align.cpp:409-415)"""
+    d, msa, qmasks = data
+    rng = np.random.default_rng(5)
+    w = (0.5 - np.log(rng.uniform(1e-4, 0.95, msa.W))).astype(np.float32)
+    with open(tmp_path / "weights.txt", "w") as f:
+        f.write("\n".join("%.9g" % x for x in w) + "\n")
+    out = tmp_path / "out.fasta"
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
+                        "--filter-weights", str(tmp_path / "weights.txt")] + FAM_ARGS, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    orc.set_column_weights(w)
+    try:
+        want, res = oracle_strings(orc, msa, qmasks, {})
+    finally:
+        orc.set_column_weights(None)
+    got = read_fasta(out)
+    for i, s in enumerate(want):
+        if s is not None:
+            assert got["q%d" % i] == s, i
+    plain, _ = oracle_strings(orc, msa, qmasks, {})
+    assert any(a != b for a, b in zip(want, plain))   # the weights do change alignments
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
+                        "--filter", "pos_var"] + FAM_ARGS, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "filter-weights" in r.stderr

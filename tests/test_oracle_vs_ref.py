@@ -232,3 +232,44 @@ def test_insertion_forbid_random(orc, ref):
             differ += int(r0.status != 0 or len(c0) != len(c1) or (c0 != c1).any())
         ref.db_free(db)
     assert ncells > 300000 and differ >= 10, (ncells, differ)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_weighted_scheme_random(orc, ref, seed):
+    """positional weights (--filter): scoring_scheme_weighted compiled from the reference (src/scoring_schemes.h:166-241,
+    chosen in src/align.cpp:409-415) against the restatement: every mesh cell field, strings, head/tail, score bits;
+    with transition_simple and with transition_aspace_aware (--insertion forbid)."""
+    rng = np.random.default_rng(4000 + seed)
+    ncells = 0
+    try:
+        for it in range(50):
+            rows, q = synth.random_case(rng, lowercase=0.05 if it % 3 == 0 else 0.0)
+            msa = O.MSA.from_rows(rows)
+            # weights as alignment_stats makes them: 1 for sparse columns, 0.5 - log(rate) (0.5 .. 20) elsewhere
+            w = np.where(rng.random(msa.W) < 0.3, 1.0, 0.5 - np.log(rng.uniform(1e-6, 0.95, msa.W))).astype(np.float32)
+            orc.set_column_weights(w)
+            ref.set_column_weights(w)
+            db = ref.db(msa)
+            fam = np.arange(msa.N, dtype=np.uint32)
+            ap = params_for(it)
+            ap.insertion = 1 if it % 4 == 3 else 0
+            qm = O.encode(q)
+            rr, s2, c2, log, cells = ref.align(db, fam, q, msa.W, ap, want_cells=True)
+            r1, c1, m1, famp = orc.align(msa, fam, qm, ap)
+            assert rr.status == r1.status, it
+            if rr.status == 0:
+                mesh = orc.mesh(msa, famp[:r1.fam_used], (qm & 15) if ap.lowercase != 1 else qm, ap)
+                for k in mesh:
+                    a, b = mesh[k], cells[k]
+                    if a.dtype == np.float32:
+                        a, b = bits(a), bits(b)
+                    assert (a == b).all(), (it, k)
+                ncells += mesh["value"].size
+                assert O.render(m1, c1, msa.W) == s2 and (c1 == c2).all()
+                assert (r1.head, r1.tail, r1.qual) == (rr.head, rr.tail, rr.qual)
+                assert bits(r1.score) == bits(rr.score)
+            ref.db_free(db)
+    finally:
+        orc.set_column_weights(None)
+        ref.set_column_weights(None)
+    assert ncells > 200000

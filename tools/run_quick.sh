@@ -5,6 +5,6 @@ timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 
 tail -15 gpurun_out/${tag}_pytest.log
 timeout 600 python tools/dp_probe.py --refs 20000 --queries 1184 --reps 3 2>&1 | tee gpurun_out/${tag}_probe.log | tail -3
 if [ "$2" = "bench" ]; then
-  timeout 900 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
+  timeout 900 python bench.py --no-cpu-baseline --no-shares > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
   cat gpurun_out/${tag}_bench.json
 fi
