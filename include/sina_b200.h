@@ -110,6 +110,11 @@ int sg_index_set_column_weights(sg_index* ix, const float* weights, uint32_t n);
 /* n_postings: total posting entries; n_tiles: reference-id tiles of the search histogram */
 int sg_index_info(const sg_index* ix, uint32_t* N, uint32_t* W, int* k, int* nofast, uint64_t* n_postings,
                   uint32_t* n_tiles, uint32_t* tile_size);
+/* All posting lists at once, as the reference keeps them (kmer_idx[kmer] = ascending reference ids,
+ * src/kmer_search.cpp:152-211): list_off[n_slots + 1] with n_slots = 4^(k-1) in fast mode (k-mers starting with A; the
+ * k-mer value IS the slot) and 4^k otherwise; ids[n_postings] (may be null to get the offsets only). This is what the
+ * host writes into a .sidx index cache (src/kmer_search.cpp:278-303). */
+int sg_index_export_lists(const sg_index* ix, uint64_t* list_off, uint32_t* ids);
 /* test hook: list sizes (summed over tiles) for n k-mers */
 int sg_index_list_sizes(const sg_index* ix, const uint32_t* kmers, uint32_t n, uint64_t* sizes);
 /* test hook: copy the posting list of one k-mer (ids ascending) into ids[cap]; *n = list length */

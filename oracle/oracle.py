@@ -364,6 +364,14 @@ class Ref:
         L.ref_kidx_build.restype = C.c_void_p
         L.ref_kidx_build.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_kidx_free.argtypes = [C.c_void_p]
+        L.ref_kidx_store.restype = C.c_int
+        L.ref_kidx_store.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.ref_kidx_from_lists.restype = C.c_void_p
+        L.ref_kidx_from_lists.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_uint32, u32p, u64p, u32p]
+        L.ref_kidx_list_scores.restype = C.c_int
+        L.ref_kidx_list_scores.argtypes = [C.c_void_p, C.c_uint32, i16p]
+        L.ref_kidx_load.restype = C.c_void_p
+        L.ref_kidx_load.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.ref_kidx_list_size.restype = C.c_uint64
         L.ref_kidx_list_size.argtypes = [C.c_void_p, C.c_uint32]
         L.ref_kidx_find.restype = C.c_uint32
@@ -437,6 +445,28 @@ class Ref:
 
     def kidx_free(self, ix):
         self.L.ref_kidx_free(ix)
+
+    def kidx_from_lists(self, N, k, nofast, kmers, list_off, ids):
+        """index made of the given posting lists (reference vlimap objects, inverted when longer than N / 2)"""
+        kmers = np.ascontiguousarray(kmers, np.uint32)
+        ids = np.ascontiguousarray(ids if len(ids) else np.zeros(1), np.uint32)
+        return C.c_void_p(self.L.ref_kidx_from_lists(N, k, int(nofast), len(kmers), kmers, np.ascontiguousarray(list_off, np.uint64), ids))
+
+    def kidx_list_scores(self, ix, kmer, N):
+        """(scores[N], offset) of one list's vlimap::increment, offset added: 1 where the id is in the list"""
+        sc = np.zeros(max(1, N), np.int16)
+        off = self.L.ref_kidx_list_scores(ix, kmer, sc)
+        return sc[:N], off
+
+    def kidx_store(self, ix, names, path):
+        """kmer_search::impl::store: the reference's .sidx file for this index"""
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        assert self.L.ref_kidx_store(ix, C.cast(arr, C.c_void_p), str(path).encode()) == 0
+
+    def kidx_load(self, db, path, k=10, nofast=False):
+        """kmer_search::impl::try_load: index from a .sidx file (None on a header mismatch)"""
+        h = self.L.ref_kidx_load(db, str(path).encode(), k, int(nofast))
+        return C.c_void_p(h) if h else None
 
     def kidx_list_size(self, ix, kmer):
         return self.L.ref_kidx_list_size(ix, kmer)

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <fstream>
 #include <sstream>
 #include <thread>
 #include <atomic>
@@ -76,6 +77,8 @@ struct ref_kidx {
     bool nofast;
     uint32_t n_kmers;
     std::vector<vlimap*> lists;
+    uint32_t n_seqs = 0;   // index built from bare lists (ref_kidx_from_lists): number of sequences, else db->seqs.size()
+    uint32_t size() const { return db ? (uint32_t)db->seqs.size() : n_seqs; }
     ~ref_kidx() { for (auto* l : lists) delete l; }
 };
 
@@ -199,6 +202,79 @@ ref_kidx* ref_kidx_build(ref_db* db, int k, int nofast) {
     return ix;
 }
 void ref_kidx_free(ref_kidx* ix) { delete ix; }
+
+// kmer_search::impl::store (kmer_search.cpp:278-303) over the reference's own vlimap::write (idset.h:386-398)
+int ref_kidx_store(ref_kidx* ix, const char* const* names, const char* path) {
+    std::ofstream out(path, std::ofstream::binary);
+    if (!out) return -1;
+    struct idx_header { uint64_t magic{0x5844494b414e4953}; uint16_t vers{0}; uint32_t n_sequences{0}; uint16_t flags{0}; };  // kmer_search.cpp:66-88
+    idx_header header;
+    memset((void*)&header, 0, sizeof(header));
+    header.magic = 0x5844494b414e4953; header.vers = 0;
+    header.n_sequences = ix->size();
+    header.flags = (uint16_t)((ix->k & 0xff) | (ix->nofast ? 0x100 : 0));
+    out.write((char*)&header, sizeof(idx_header));
+    for (uint32_t i = 0; i < header.n_sequences; i++) out << names[i] << std::endl;
+    vlimap emptymap(header.n_sequences);
+    for (unsigned int i = 0; i < ix->n_kmers; i++)
+        if (ix->lists[i] != nullptr && ix->lists[i]->size() > 0) emptymap.push_back(i);
+    emptymap.write(out);
+    size_t idxno = 0;
+    for (auto inc : emptymap) { idxno += inc; ix->lists[idxno]->write(out); }
+    return out ? 0 : -1;
+}
+
+// index from bare posting lists (ascending ids), lists longer than N / 2 inverted as build() does (kmer_search.cpp:264-266)
+ref_kidx* ref_kidx_from_lists(uint32_t N, int k, int nofast, uint32_t n_lists, const uint32_t* kmers, const uint64_t* list_off,
+                              const uint32_t* ids) {
+    auto* ix = new ref_kidx;
+    ix->db = nullptr; ix->n_seqs = N; ix->k = k; ix->nofast = nofast != 0;
+    ix->n_kmers = 1u << (2 * k);
+    ix->lists.assign(ix->n_kmers, nullptr);
+    for (uint32_t i = 0; i < n_lists; i++) {
+        auto* l = new vlimap(N);
+        for (uint64_t e = list_off[i]; e < list_off[i + 1]; e++) l->push_back(ids[e]);
+        if (l->size() > N / 2) l->invert();
+        ix->lists[kmers[i]] = l;
+    }
+    return ix;
+}
+// scores[N] after incrementing with list `kmer` (+ the offset an inverted list asks for): what find() adds for one k-mer
+int ref_kidx_list_scores(ref_kidx* ix, uint32_t kmer, int16_t* scores) {
+    idset::inc_t sc(ix->size(), 0);
+    if (!ix->lists[kmer]) return -1;
+    const int off = ix->lists[kmer]->increment(sc);
+    for (uint32_t i = 0; i < ix->size(); i++) scores[i] = sc[i] + off;
+    return off;
+}
+
+// kmer_search::impl::try_load (kmer_search.cpp:305-351) over the reference's own vlimap::read (idset.h:400-409);
+// returns null on a header mismatch
+ref_kidx* ref_kidx_load(ref_db* db, const char* path, int k, int nofast) {
+    std::ifstream in(path, std::ifstream::binary);
+    if (!in) return nullptr;
+    struct idx_header { uint64_t magic; uint16_t vers; uint32_t n_sequences; uint16_t flags; };
+    idx_header header;
+    in.read((char*)&header, sizeof(idx_header));
+    if (header.magic != 0x5844494b414e4953 || header.vers != 0) return nullptr;
+    if ((header.flags & 0xff) != k || ((header.flags >> 8) & 1) != (nofast != 0)) return nullptr;
+    if (db && header.n_sequences != db->seqs.size()) return nullptr;
+    for (unsigned int i = 0; i < header.n_sequences; i++) { std::string name; getline(in, name); }
+    auto* ix = new ref_kidx;
+    ix->db = db; ix->n_seqs = header.n_sequences; ix->k = k; ix->nofast = nofast != 0;
+    ix->n_kmers = 1u << (2 * k);
+    ix->lists.assign(ix->n_kmers, nullptr);
+    vlimap emptymap(header.n_sequences);
+    emptymap.read(in);
+    size_t idxno = 0;
+    for (auto inc : emptymap) {
+        idxno += inc;
+        auto* idx = new vlimap(header.n_sequences);
+        idx->read(in);
+        ix->lists[idxno] = idx;
+    }
+    return ix;
+}
 
 // number of postings in list `kmer` (un-inverted size), and total
 uint64_t ref_kidx_list_size(ref_kidx* ix, uint32_t kmer) { return ix->lists[kmer] ? ix->lists[kmer]->size() : 0; }

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(HERE, os.environ.get("SINA_B200_LIB", "libsina_b200.so")
 # every symbol include/sina_b200.h declares
 EXPORTS = [
     "sg_default_fam_params", "sg_default_align_params", "sg_last_error", "sg_device_count",
-    "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list", "sg_index_set_column_weights",
+    "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list", "sg_index_set_column_weights", "sg_index_export_lists",
     "sg_find_batch", "sg_turn_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
     "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_turn", "sg_session_family",
     "sg_session_set_family", "sg_session_align", "sg_session_run", "sg_session_sync", "sg_session_download_find",
@@ -99,6 +99,7 @@ def lib():
     L.sg_index_destroy.restype = None
     L.sg_index_info.argtypes = [C.c_void_p] + [C.c_void_p] * 7
     L.sg_index_set_column_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.sg_index_export_lists.argtypes = [C.c_void_p, u64p, C.c_void_p]
     L.sg_index_list.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.sg_index_list_sizes.argtypes = [C.c_void_p, u32p, C.c_uint32, u64p]
     L.sg_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_uint32, i16p, u32p, u32p]
@@ -170,6 +171,15 @@ class Index:
             self.close()
         except Exception:
             pass
+
+    def export_lists(self):
+        """every posting list: (list_off[n_slots + 1], ids[n_postings]), ids ascending inside a list"""
+        inf = self.info()
+        n_slots = 4 ** (inf["k"] if inf["nofast"] else inf["k"] - 1)
+        off = np.zeros(n_slots + 1, np.uint64)
+        ids = np.zeros(max(1, inf["n_postings"]), np.uint32)
+        _check(lib().sg_index_export_lists(self.h, off, ids.ctypes.data_as(C.c_void_p)))
+        return off, ids[:inf["n_postings"]]
 
     def set_column_weights(self, w):
         """positional column weights (--filter / alignment_stats): scoring_scheme_weighted from now on; None = off"""

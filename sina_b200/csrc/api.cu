@@ -285,6 +285,29 @@ int sg_index_list(const sg_index* h, uint32_t kmer, uint32_t* ids, uint64_t cap,
     return SG_OK;
 }
 
+int sg_index_export_lists(const sg_index* h, uint64_t* list_off, uint32_t* ids) {
+    const Index* ix = (const Index*)h;
+    if (!ix || !list_off) SG_FAIL(SG_ERR_ARG, "sg_index_export_lists: null argument");
+    SG_CUDA(cudaSetDevice(ix->device));
+    const uint64_t n_off = ix->n_slots * ix->n_sub + 1;
+    std::vector<uint32_t> offs(n_off);
+    SG_CUDA(cudaMemcpy(offs.data(), ix->d_list_off, n_off * 4, cudaMemcpyDeviceToHost));
+    for (uint64_t v = 0; v <= ix->n_slots; v++) list_off[v] = offs[v * ix->n_sub];
+    if (!ids) return SG_OK;
+    std::vector<uint16_t> loc(ix->n_postings);
+    if (ix->n_postings) SG_CUDA(cudaMemcpy(loc.data(), ix->d_postings, ix->n_postings * 2, cudaMemcpyDeviceToHost));
+    // (k-mer, sub-tile) lists are stored k-mer-major with ids local to the sub-tile and unordered inside a list: global
+    // ids, ascending inside every k-mer's list
+    for (uint64_t v = 0; v < ix->n_slots; v++) {
+        for (uint32_t j = 0; j < ix->n_sub; j++) {
+            const uint32_t a = offs[v * ix->n_sub + j], b = offs[v * ix->n_sub + j + 1];
+            for (uint32_t e = a; e < b; e++) ids[e] = j * ix->sub_size + loc[e];
+            std::sort(ids + a, ids + b);
+        }
+    }
+    return SG_OK;
+}
+
 int sg_index_list_sizes(const sg_index* h, const uint32_t* kmers, uint32_t n, uint64_t* sizes) {
     const Index* ix = (const Index*)h;
     if (!ix || !kmers || !sizes) SG_FAIL(SG_ERR_ARG, "null argument");

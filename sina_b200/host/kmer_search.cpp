@@ -1,5 +1,11 @@
 #include "kmer_search.h"
 
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "sidx.h"
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -50,6 +56,28 @@ kmer_search* kmer_search::get_kmer_search(const std::string& database, int k, bo
         check_sg(sg_index_create(p->rdb->masks().data(), p->rdb->cols().data(), p->rdb->offsets().data(),
                                  p->rdb->getSeqCount(), p->rdb->getAlignmentWidth(), k, nofast ? 1 : 0, device, &p->ix),
                  "building the k-mer index");
+        // index cache next to the database, as kmer_search::impl::impl keeps one (src/kmer_search.cpp:213-242): written when
+        // there is none for this (k, fast) yet. The GPU rebuilds the index faster than the file is read, so the cache is never
+        // loaded for its lists: it records the index order (reference_db::getDB) and serves SINA itself.
+        if (!getenv("SINA_B200_NO_SIDX") && std::ifstream(database).good()) {   // only next to a database that is a file
+            try {
+                sidx::info have;
+                bool ok = false;
+                try { ok = sidx::read(database + ".sidx", have) && have.k == (unsigned)k && have.nofast == nofast &&
+                           have.n_sequences == p->rdb->getSeqCount(); } catch (std::exception&) { ok = false; }
+                if (!ok) {
+                    uint64_t n_post = 0;
+                    check_sg(sg_index_info(p->ix, nullptr, nullptr, nullptr, nullptr, &n_post, nullptr, nullptr), "index info");
+                    const uint64_t n_slots = 1ull << (2 * (nofast ? k : k - 1));
+                    std::vector<uint64_t> off(n_slots + 1);
+                    std::vector<uint32_t> ids(n_post ? n_post : 1);
+                    check_sg(sg_index_export_lists(p->ix, off.data(), ids.data()), "exporting the posting lists");
+                    sidx::write(database + ".sidx", (unsigned)k, nofast, p->rdb->getSequenceNames(), off.data(), ids.data(), n_slots);
+                }
+            } catch (std::exception& e) {
+                std::cerr << "warning: index cache not written: " << e.what() << std::endl;
+            }
+        }
         it = g_indices.emplace(key, std::move(p)).first;
     }
     return new kmer_search(it->second);

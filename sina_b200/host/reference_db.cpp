@@ -1,9 +1,12 @@
 #include "reference_db.h"
 
+#include "sidx.h"
+
 #include <fstream>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <unordered_map>
 
 namespace sina {
 
@@ -77,6 +80,31 @@ reference_db* reference_db::getDB(const std::string& path) {
         }
     }
     if (v.empty()) throw std::runtime_error("reference database '" + path + "' holds no sequences");
+    // Index order. In the reference the id of a sequence is its position in query_arb::getSequenceNames()
+    // (src/kmer_search.cpp:248-249), which a .sidx index cache records (:289-291). When `<db>.sidx` exists and lists
+    // exactly this database's sequences, its order is adopted, so that ids -- and with them the rank order of equal
+    // k-mer scores -- are those of the SINA run that built the cache. Otherwise: order of the file.
+    sidx::info cache;
+    bool have_cache = false;
+    try { have_cache = sidx::read(path + ".sidx", cache); } catch (std::exception&) { have_cache = false; }
+    if (have_cache && cache.names.size() == v.size()) {
+        std::unordered_map<std::string, size_t> at;
+        for (size_t i = 0; i < v.size(); i++) at.emplace(v[i].getName(), i);
+        std::vector<size_t> order;
+        std::vector<char> used(v.size(), 0);
+        for (const auto& n : cache.names) {
+            auto it = at.find(n);
+            if (it == at.end() || used[it->second]) break;
+            used[it->second] = 1;
+            order.push_back(it->second);
+        }
+        if (order.size() == v.size()) {
+            std::vector<cseq> r;
+            r.reserve(v.size());
+            for (size_t i : order) r.push_back(std::move(v[i]));
+            v.swap(r);
+        }
+    }
     return fromSequences(path, std::move(v));
 }
 

@@ -233,3 +233,48 @@ def test_cli_filter_weights(orc, data, tmp_path):
     r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
                         "--filter", "pos_var"] + FAM_ARGS, capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "filter-weights" in r.stderr
+
+
+def test_cli_sidx_cache_and_index_order(orc, data, tmp_path):
+    """like kmer_search::impl::impl (src/kmer_search.cpp:213-242) the command line leaves `<db>.sidx` next to the database:
+    the file equals the one the reference's own code writes for the same index; and a .sidx found next to a database
+    defines the index ORDER (ids = positions in its name list, :289-291), which decides ties between equal k-mer scores"""
+    if not O.have_ref():
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    d, msa, qmasks = data
+    import shutil
+    db = tmp_path / "ref.fasta"
+    shutil.copy(d / "ref.fasta", db)
+    names = ["ref%d" % i for i in range(msa.N)]
+    base = [os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(tmp_path / "out.fasta"), "--db", str(db)] + FAM_ARGS
+    r = subprocess.run(base, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(str(db) + ".sidx")
+    ref = O.Ref()
+    rdb = ref.db(msa)
+    rix = ref.kidx_build(rdb, 6, 0)
+    ref.kidx_store(rix, names, tmp_path / "want.sidx")
+    x, y = bytearray(open(str(db) + ".sidx", "rb").read()), bytearray(open(tmp_path / "want.sidx", "rb").read())
+    for sl in (slice(10, 12), slice(18, 24)):   # padding inside idx_header
+        x[sl] = y[sl] = b"\0" * (sl.stop - sl.start)
+    assert x == y
+    ref.kidx_free(rix)
+    ref.db_free(rdb)
+    first = read_fasta(tmp_path / "out.fasta")
+    # a cache that lists the sequences in another order: ids follow it
+    perm = np.random.default_rng(8).permutation(msa.N)
+    rows = [msa.row_string(int(i)) for i in perm]
+    pmsa = O.MSA.from_rows(rows)
+    pdb = ref.db(pmsa)
+    pix = ref.kidx_build(pdb, 6, 0)
+    ref.kidx_store(pix, [names[int(i)] for i in perm], str(db) + ".sidx")
+    ref.kidx_free(pix)
+    ref.db_free(pdb)
+    r = subprocess.run(base, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = read_fasta(tmp_path / "out.fasta")
+    want, res = oracle_strings(orc, pmsa, qmasks, {})
+    for i, w in enumerate(want):
+        if w is not None:
+            assert got["q%d" % i] == w, i
+    assert first.keys() == got.keys()
