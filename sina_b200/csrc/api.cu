@@ -79,7 +79,7 @@ static int alloc_workspace(Session* s, Workspace* w) {
     SG_TRY(dmalloc(&w->d_pdesc2, C * I)); SG_TRY(dmalloc(&w->d_order, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_rcol, C * s->gcap * DP_T)); SG_TRY(dmalloc(&w->d_nthr, C * I));
     SG_TRY(dmalloc(&w->d_nshift, C * I)); SG_TRY(dmalloc(&w->d_nmaxins, C * I)); SG_TRY(dmalloc(&w->d_ghosts, C * s->gcap * DP_G));
     SG_TRY(dmalloc(&w->d_writers, C * s->gcap * DP_G));
-    { uint8_t* p = nullptr; SG_TRY(dmalloc(&p, C * I * 32)); w->d_rec = p; }
+    { uint8_t* p = nullptr; SG_TRY(dmalloc(&p, C * I * 48)); w->d_rec = p; }
     SG_TRY(dmalloc(&w->d_tb, s->tb_words)); SG_TRY(dmalloc(&w->d_spill, s->spill_elems));
     return SG_OK;
 }

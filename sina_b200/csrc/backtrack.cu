@@ -30,8 +30,10 @@ struct __align__(16) NodeRec {
     uint32_t ncol;
     uint32_t pred_off;
     uint32_t pred[4];   // predecessors 0..3 (ascending id)
+    uint32_t ptb[3];    // tbbase of predecessors 0..2: their traceback cells can be requested as soon as THIS record is known,
+    uint32_t psoff;     // [7:0], [15:8], [23:16] their step offsets            without waiting for their own records
 };
-static_assert(sizeof(NodeRec) == 32, "NodeRec is read as two 16-byte loads");
+static_assert(sizeof(NodeRec) == 48, "NodeRec is read as three 16-byte loads");
 
 struct BtArgs {
     uint32_t nq, W, q0;  // nq queries of the chunk starting at q0
@@ -174,22 +176,31 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         const uint16_t* nthr = A.nthr + io;
         const uint8_t* nshift = A.nshift + io;
         const bool sorted = h.mode >= 2;  // v2 kernel: rows sorted inside the group, predecessor slots right-aligned
-        for (uint32_t m = lane; m < V; m += 32) {
-            const uint32_t g = m / T, tid = sorted ? (uint32_t)nthr[m] : m - g * T;
+        auto tb_of = [&](uint32_t x, uint32_t& soff) -> uint32_t {   // (tbbase, step offset) of node x
+            const uint32_t g = x / T, tid = sorted ? (uint32_t)nthr[x] : x - g * T;
             const GroupInfo gi = groups[g];
+            soff = nsigma[x] - gi.sigma_lo;
+            return v2 ? (uint32_t)(4 * gi.tb_off) + 4u * tid : (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
+        };
+        for (uint32_t m = lane; m < V; m += 32) {
             const uint32_t po = pred_off[m], np = pred_off[m + 1] - po;
-            uint4 a, b;
-            a.x = v2 ? (uint32_t)(4 * gi.tb_off) + 4u * tid : (uint32_t)(wide ? gi.tb_off : 2 * gi.tb_off) + tid;
-            a.y = (nsigma[m] - gi.sigma_lo) | ((uint32_t)nshift[m] << 16) | (min(np, 255u) << 24);
+            uint4 a, b, c = make_uint4(0, 0, 0, 0);
+            uint32_t soff;
+            a.x = tb_of(m, soff);
+            a.y = soff | ((uint32_t)nshift[m] << 16) | (min(np, 255u) << 24);
             a.z = ncol[m];
             a.w = po;
             b.x = np > 0 ? preds[po] : 0u;
             b.y = np > 1 ? preds[po + 1] : 0u;
             b.z = np > 2 ? preds[po + 2] : 0u;
             b.w = np > 3 ? preds[po + 3] : 0u;
+            if (np > 0) { c.x = tb_of(b.x, soff); c.w |= soff; }
+            if (np > 1) { c.y = tb_of(b.y, soff); c.w |= soff << 8; }
+            if (np > 2) { c.z = tb_of(b.z, soff); c.w |= soff << 16; }
             uint4* dst = reinterpret_cast<uint4*>(rec + m);
             __stcg(dst, a);
             __stcg(dst + 1, b);
+            __stcg(dst + 2, c);
         }
     }
     __syncwarp();
@@ -198,6 +209,12 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         const uint4* p = reinterpret_cast<const uint4*>(rec + x);
         a = __ldcg(p);
         b = __ldcg(p + 1);
+    };
+    auto ldrec3 = [&](uint32_t x, uint4& a, uint4& b, uint4& c) {
+        const uint4* p = reinterpret_cast<const uint4*>(rec + x);
+        a = __ldcg(p);
+        b = __ldcg(p + 1);
+        c = __ldcg(p + 2);
     };
     // traceback cell: the load (cell_raw) and its decoding (cell_dec) are separate so that a speculative load can stay
     // in flight; decoded = src | slot<<8 | ob<<2 (the wide layout; ob = a deletion leaving the cell opens, common.cuh)
@@ -339,25 +356,27 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     const uint32_t m_end = m, s_end = s;
 
     // ---- walk back (mesh.h:642-685): ocols[s] = node the query position s is aligned to
-    uint4 ra, rb;
-    ldrec(m, ra, rb);
+    uint4 ra, rb, rc;
+    ldrec3(m, ra, rb, rc);
     uint32_t c = cell(ra, s);
     if (lane == 0) ocols[s] = m;
     while (s != 0 && np_of(ra) != 0) {
-        // records of the inline predecessors, requested before the cell is looked at
+        // speculation: the most common step is a match through one of the first predecessors. Their cells (p_k, s-1) are
+        // requested by lane k straight from THIS node's record (it carries their traceback bases), together with their
+        // records: one memory latency per step of the walk instead of record -> cell
         const uint32_t np = np_of(ra);
-        uint4 qa0 = ra, qb0 = rb, qa1 = ra, qb1 = rb, qa2 = ra, qb2 = rb, qa3 = ra, qb3 = rb;
-        ldrec(rb.x, qa0, qb0);
-        if (np > 1) ldrec(rb.y, qa1, qb1);
-        if (np > 2) ldrec(rb.z, qa2, qb2);
-        if (np > 3) ldrec(rb.w, qa3, qb3);
-        // speculation: the most common step is a match through one of the inline predecessors; its cell (p_k, s-1) is
-        // requested by lane k as soon as p_k's record is there, i.e. while this node's own cell is still on its way
         uint32_t spec_raw = 0;
-        if (lane < min(np, 4u)) {
-            const uint4 pa = lane == 0 ? qa0 : (lane == 1 ? qa1 : (lane == 2 ? qa2 : qa3));
-            spec_raw = cell_raw(pa, s - 1);
+        if (lane < min(np, 3u)) {
+            uint4 fake = ra;
+            fake.x = lane == 0 ? rc.x : (lane == 1 ? rc.y : rc.z);
+            fake.y = (rc.w >> (8 * lane)) & 0xffu;
+            spec_raw = cell_raw(fake, s - 1);
         }
+        uint4 qa0 = ra, qb0 = rb, qc0 = rc, qa1 = ra, qb1 = rb, qc1 = rc, qa2 = ra, qb2 = rb, qc2 = rc, qa3 = ra, qb3 = rb, qc3 = rc;
+        ldrec3(rb.x, qa0, qb0, qc0);
+        if (np > 1) ldrec3(rb.y, qa1, qb1, qc1);
+        if (np > 2) ldrec3(rb.z, qa2, qb2, qc2);
+        if (np > 3) { ldrec3(rb.w, qa3, qb3, qc3); if (lane == 3) spec_raw = cell_raw(qa3, s - 1); }
         uint32_t spec_k = 4;   // inline predecessor the match goes through, if it does
         if ((c & 3u) == TB_SRC_MATCH) {
             const uint32_t sl = c >> 8, sh = (ra.y >> 16) & (wide ? 0xffu : 0x7fu);
@@ -365,14 +384,14 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
         }
         uint32_t nm, snew;
         follow(ra, rb, m, s, c, nm, snew);
-        uint4 na, nb;
-        if (nm == m) { na = ra; nb = rb; }
-        else if (nm == rb.x) { na = qa0; nb = qb0; }
-        else if (np > 1 && nm == rb.y) { na = qa1; nb = qb1; }
-        else if (np > 2 && nm == rb.z) { na = qa2; nb = qb2; }
-        else if (np > 3 && nm == rb.w) { na = qa3; nb = qb3; }
-        else ldrec(nm, na, nb);
-        m = nm; ra = na; rb = nb;
+        uint4 na, nb, nc;
+        if (nm == m) { na = ra; nb = rb; nc = rc; }
+        else if (nm == rb.x) { na = qa0; nb = qb0; nc = qc0; }
+        else if (np > 1 && nm == rb.y) { na = qa1; nb = qb1; nc = qc1; }
+        else if (np > 2 && nm == rb.z) { na = qa2; nb = qb2; nc = qc2; }
+        else if (np > 3 && nm == rb.w) { na = qa3; nb = qb3; nc = qc3; }
+        else ldrec3(nm, na, nb, nc);
+        m = nm; ra = na; rb = nb; rc = nc;
         uint32_t c2 = 0;
         if (snew != 0) {  // landing on a cell reached by deletion (its value_sidx == snew): skip it (mesh.h:653-655)
             if (spec_k < 4) c2 = cell_dec(ra, snew, __shfl_sync(FULL, spec_raw, spec_k));   // (p_k, s-1), already loaded
@@ -381,7 +400,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
                 uint32_t m2, s2;
                 follow(ra, rb, m, snew, c2, m2, s2);
                 m = m2;
-                ldrec(m, ra, rb);
+                ldrec3(m, ra, rb, rc);
                 c2 = cell(ra, snew);
             }
         }

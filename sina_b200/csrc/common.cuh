@@ -177,7 +177,7 @@ struct Workspace {
     float* d_lastcol = nullptr;      // [n][icap] value(m, Lq-1)
     float* d_rowmin = nullptr;       // [n][icap] min over s of value(m, s) (last nodes only)
     uint32_t* d_rowarg = nullptr;    // [n][icap] first s reaching it
-    void* d_rec = nullptr;           // [n][icap] 32-byte node records of the backtrack kernel
+    void* d_rec = nullptr;           // [n][icap] 48-byte node records of the backtrack kernel
     uint32_t* d_tb = nullptr;        // traceback arena (words)
     float2* d_spill = nullptr;       // spill arena
 };
