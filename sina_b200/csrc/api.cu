@@ -1,6 +1,7 @@
 // C-ABI of libsina_b200.so (see include/sina_b200.h): index / session lifetime, stage drivers, host-buffer
 // wrappers. No torch types, no exceptions across the boundary, no CPU fallback.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -39,6 +40,7 @@ static void free_workspace(Workspace* w) {
     if (w->done) cudaEventDestroy(w->done);
     if (w->stream) cudaStreamDestroy(w->stream);
     if (w->dp_stream) cudaStreamDestroy(w->dp_stream);
+    if (w->bt_stream) cudaStreamDestroy(w->bt_stream);
     *w = Workspace{};
 }
 
@@ -54,7 +56,12 @@ static void free_align(Session* s) {
 
 static int alloc_workspace(Session* s, Workspace* w) {
     const uint64_t C = s->chunk, I = s->icap;
-    if (env_mb("SG_PRIO", 0)) {
+    if (env_mb("SG_PRIO", 0) == 2) {
+        int lo = 0, hi = 0;
+        SG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SG_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, lo));
+        SG_CUDA(cudaStreamCreateWithPriority(&w->bt_stream, cudaStreamNonBlocking, hi));
+    } else if (env_mb("SG_PRIO", 0) == 1) {
         int lo = 0, hi = 0;
         SG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (largest number)
         SG_CUDA(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, hi));
@@ -618,10 +625,12 @@ static int enqueue_chunk(Session* s, Workspace* w, const sg_align_params& ap, ui
     SG_TRY(launch_mesh(s, w, ap, q0, n));
     SG_CUDA(cudaEventRecord(w->ev[2], w->dp_stream ? w->dp_stream : w->stream));
     if (w->dp_stream) SG_CUDA(cudaStreamWaitEvent(w->stream, w->ev[2], 0));
+    cudaStream_t bs = w->bt_stream ? w->bt_stream : w->stream;
+    if (w->bt_stream) SG_CUDA(cudaStreamWaitEvent(bs, w->ev[2], 0));
     SG_TRY(launch_backtrack(s, w, ap, q0, n));
-    SG_CUDA(cudaEventRecord(w->ev[3], w->stream));
-    SG_CUDA(cudaMemcpyAsync(w->h_remaining, w->d_remaining, 4, cudaMemcpyDeviceToHost, w->stream));
-    SG_CUDA(cudaEventRecord(w->done, w->stream));
+    SG_CUDA(cudaEventRecord(w->ev[3], bs));
+    SG_CUDA(cudaMemcpyAsync(w->h_remaining, w->d_remaining, 4, cudaMemcpyDeviceToHost, bs));
+    SG_CUDA(cudaEventRecord(w->done, bs));
     return SG_OK;
 }
 
@@ -632,6 +641,11 @@ static int retire_chunk(Session* s, Workspace* w, const sg_align_params& ap) {
         SG_CUDA(cudaEventElapsedTime(&ms, w->ev[0], w->ev[1])); s->stats.ms_graph += ms;
         SG_CUDA(cudaEventElapsedTime(&ms, w->ev[1], w->ev[2])); s->stats.ms_dp += ms;
         SG_CUDA(cudaEventElapsedTime(&ms, w->ev[2], w->ev[3])); s->stats.ms_backtrack += ms;
+        if (getenv("SG_TRACE")) {   // timeline of the chunk pipeline: stage boundaries of every chunk relative to the align call's start
+            float t[4];
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], s->ev[0], w->ev[i]);
+            fprintf(stderr, "chunk q0=%u n=%u ws=%d graph %.3f dp %.3f backtrack %.3f end %.3f ms\n", w->q0, w->n, (int)(w - s->ws), t[0], t[1], t[2], t[3]);
+        }
         w->busy = false;
         const uint32_t remaining = *w->h_remaining;
         if (remaining == 0) { w->prev_remaining = 0xffffffffu; SG_TRY(stage_chunk(s, w->q0, w->n)); break; }
@@ -679,6 +693,7 @@ static void reset_pipeline(Session* s) {
         Workspace* w = &s->ws[i];
         if (w->stream) cudaStreamSynchronize(w->stream);
         if (w->dp_stream) cudaStreamSynchronize(w->dp_stream);
+        if (w->bt_stream) cudaStreamSynchronize(w->bt_stream);
         w->busy = false;
         w->prev_remaining = 0xffffffffu;
     }

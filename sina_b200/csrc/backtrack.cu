@@ -360,51 +360,57 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
     ldrec3(m, ra, rb, rc);
     uint32_t c = cell(ra, s);
     if (lane == 0) ocols[s] = m;
+    auto bcast4 = [&](const uint4& v, uint32_t from) -> uint4 {
+        return make_uint4(__shfl_sync(FULL, v.x, from), __shfl_sync(FULL, v.y, from), __shfl_sync(FULL, v.z, from), __shfl_sync(FULL, v.w, from));
+    };
     while (s != 0 && np_of(ra) != 0) {
-        // speculation: the most common step is a match through one of the first predecessors. Their cells (p_k, s-1) are
-        // requested by lane k straight from THIS node's record (it carries their traceback bases), together with their
-        // records: one memory latency per step of the walk instead of record -> cell
         const uint32_t np = np_of(ra);
+        // Speculation: the most common step is a match through one of the first predecessors. Lane k < 4 fetches
+        // predecessor k: its record, and its cell (p_k, s-1) -- for k < 3 straight from THIS node's record, which carries
+        // their traceback bases, so that record and cell travel together: one memory latency per step. The winner's
+        // record and cell are then broadcast from its lane (a first version kept all four records in every lane and spent
+        // ~450 dependent instructions per step selecting among them: the walk was bound by issue latency, not memory).
+        uint4 qa = ra, qb = rb, qc = rc;
         uint32_t spec_raw = 0;
-        if (lane < min(np, 3u)) {
-            uint4 fake = ra;
-            fake.x = lane == 0 ? rc.x : (lane == 1 ? rc.y : rc.z);
-            fake.y = (rc.w >> (8 * lane)) & 0xffu;
-            spec_raw = cell_raw(fake, s - 1);
+        if (lane < min(np, 4u)) {
+            const uint32_t pk = lane == 0 ? rb.x : (lane == 1 ? rb.y : (lane == 2 ? rb.z : rb.w));
+            if (lane < 3) {
+                uint4 fake = ra;
+                fake.x = lane == 0 ? rc.x : (lane == 1 ? rc.y : rc.z);
+                fake.y = (rc.w >> (8 * lane)) & 0xffu;
+                spec_raw = cell_raw(fake, s - 1);
+            }
+            ldrec3(pk, qa, qb, qc);
+            if (lane == 3) spec_raw = cell_raw(qa, s - 1);
         }
-        uint4 qa0 = ra, qb0 = rb, qc0 = rc, qa1 = ra, qb1 = rb, qc1 = rc, qa2 = ra, qb2 = rb, qc2 = rc, qa3 = ra, qb3 = rb, qc3 = rc;
-        ldrec3(rb.x, qa0, qb0, qc0);
-        if (np > 1) ldrec3(rb.y, qa1, qb1, qc1);
-        if (np > 2) ldrec3(rb.z, qa2, qb2, qc2);
-        if (np > 3) { ldrec3(rb.w, qa3, qb3, qc3); if (lane == 3) spec_raw = cell_raw(qa3, s - 1); }
-        uint32_t spec_k = 4;   // inline predecessor the match goes through, if it does
+        uint32_t ord = 0xffffffffu;   // predecessor ordinal of a match step
         if ((c & 3u) == TB_SRC_MATCH) {
             const uint32_t sl = c >> 8, sh = (ra.y >> 16) & (wide ? 0xffu : 0x7fu);
-            spec_k = sl > sh ? sl - sh : 0u;
+            ord = sl > sh ? sl - sh : 0u;
         }
-        uint32_t nm, snew;
-        follow(ra, rb, m, s, c, nm, snew);
-        uint4 na, nb, nc;
-        if (nm == m) { na = ra; nb = rb; nc = rc; }
-        else if (nm == rb.x) { na = qa0; nb = qb0; nc = qc0; }
-        else if (np > 1 && nm == rb.y) { na = qa1; nb = qb1; nc = qc1; }
-        else if (np > 2 && nm == rb.z) { na = qa2; nb = qb2; nc = qc2; }
-        else if (np > 3 && nm == rb.w) { na = qa3; nb = qb3; nc = qc3; }
-        else ldrec3(nm, na, nb, nc);
-        m = nm; ra = na; rb = nb; rc = nc;
-        uint32_t c2 = 0;
-        if (snew != 0) {  // landing on a cell reached by deletion (its value_sidx == snew): skip it (mesh.h:653-655)
-            if (spec_k < 4) c2 = cell_dec(ra, snew, __shfl_sync(FULL, spec_raw, spec_k));   // (p_k, s-1), already loaded
-            else c2 = cell(ra, snew);
-            if ((c2 & 3u) == TB_SRC_DEL) {
-                uint32_t m2, s2;
-                follow(ra, rb, m, snew, c2, m2, s2);
-                m = m2;
-                ldrec3(m, ra, rb, rc);
-                c2 = cell(ra, snew);
-            }
+        uint32_t snew, c2 = 0;
+        if (ord < 4u) {
+            m = ord == 0 ? rb.x : (ord == 1 ? rb.y : (ord == 2 ? rb.z : rb.w));
+            snew = s - 1;
+            ra = bcast4(qa, ord); rb = bcast4(qb, ord); rc = bcast4(qc, ord);
+            const uint32_t raw = __shfl_sync(FULL, spec_raw, ord);
+            if (snew != 0) c2 = cell_dec(ra, snew, raw);
+        } else {
+            uint32_t nm;
+            follow(ra, rb, m, s, c, nm, snew);
+            if (nm != m) ldrec3(nm, ra, rb, rc);
+            m = nm;
+            if (snew != 0) c2 = cell(ra, snew);
         }
-        for (int ss = (int)s - 1 - (int)lane; ss >= (int)snew; ss -= 32) ocols[ss] = m;
+        if (snew != 0 && (c2 & 3u) == TB_SRC_DEL) {   // landing on a cell reached by deletion (its value_sidx == snew): skip it (mesh.h:653-655)
+            uint32_t m2, s2;
+            follow(ra, rb, m, snew, c2, m2, s2);
+            m = m2;
+            ldrec3(m, ra, rb, rc);
+            c2 = cell(ra, snew);
+        }
+        if (snew + 1 == s) { if (lane == 0) ocols[snew] = m; }   // one base per step, almost always
+        else for (int ss = (int)s - 1 - (int)lane; ss >= (int)snew; ss -= 32) ocols[ss] = m;
         s = snew;
         c = c2;
     }
@@ -525,7 +531,7 @@ int launch_backtrack(Session* s, Workspace* w, const sg_align_params& ap, uint32
     A.out_cols = s->d_out_cols; A.out_masks = s->d_out_masks; A.results = s->d_results;
     A.ms = -ap.match_score; A.overhang = ap.overhang; A.lowercase = ap.lowercase;
     A.colw = ix->d_colw; A.ncolw = ix->W;
-    backtrack_kernel<<<(n + BT_WARPS - 1) / BT_WARPS, 32 * BT_WARPS, 0, w->stream>>>(A);
+    backtrack_kernel<<<(n + BT_WARPS - 1) / BT_WARPS, 32 * BT_WARPS, 0, w->bt_stream ? w->bt_stream : w->stream>>>(A);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

@@ -137,6 +137,8 @@ struct Workspace {
     cudaStream_t stream = nullptr;   // graph, backtrack, bookkeeping (high priority when dp_stream is used)
     cudaStream_t dp_stream = nullptr; // SG_PRIO=1: the DP kernel runs on its own low-priority stream, so that the latency-bound
                                      // graph / backtrack kernels of other chunks get the SM slots a retiring DP CTA frees
+    cudaStream_t bt_stream = nullptr; // SG_PRIO=2: the backtrack kernel runs on its own HIGH-priority stream: its small CTAs take the
+                                     // slots retiring DP CTAs free instead of queueing behind the DP grids of the other chunks
     cudaEvent_t ev[4] = {};          // stage boundaries: graph | dp | backtrack | end
     cudaEvent_t done = nullptr;
     bool busy = false;               // a chunk is in flight (retire() has not run yet)
