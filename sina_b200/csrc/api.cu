@@ -75,7 +75,7 @@ static int alloc_workspace(Session* s, Workspace* w) {
     SG_TRY(dmalloc(&w->d_cursors, 2)); SG_TRY(dmalloc(&w->d_remaining, 1));
     SG_TRY(dmalloc(&w->d_tab, C * s->ncap * s->fam_cap)); SG_TRY(dmalloc(&w->d_tabli, C * s->ncap * s->fam_cap));
     SG_TRY(dmalloc(&w->d_colof, C * s->ncap)); SG_TRY(dmalloc(&w->d_colbase, C * (s->ncap + 1)));
-    SG_TRY(dmalloc(&w->d_item_node, C * I)); SG_TRY(dmalloc(&w->d_slot, C * I));
+    SG_TRY(dmalloc(&w->d_item_node, C * s->itemcap)); SG_TRY(dmalloc(&w->d_slot, C * s->itemcap));
     SG_TRY(dmalloc(&w->d_ncol, C * I)); SG_TRY(dmalloc(&w->d_nmask, C * I)); SG_TRY(dmalloc(&w->d_ncount, C * I));
     SG_TRY(dmalloc(&w->d_nweight, C * I)); SG_TRY(dmalloc(&w->d_nsigma, C * I));
     SG_TRY(dmalloc(&w->d_slotbase, C * (I + 1))); SG_TRY(dmalloc(&w->d_cursor, C * I));
@@ -100,7 +100,14 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     const uint64_t Q = s->max_q;   // per-query results of the whole batch
     const uint64_t C = s->chunk;   // graph/DP workspace: one align pass handles `chunk` queries
     s->fam_cap = fam_cap;
-    s->icap = fam_cap * ix->max_row_len;
+    // capacities per query. Items (bases of the family rows) are bounded by fam_cap x longest row, but only the
+    // global-scratch graph path stores anything per item. Nodes and edges of a family graph are far fewer (a node per
+    // column and character: ~1.6 per column for 40 relatives): their arrays, with one stride for all of them, are sized for
+    // 8 x the longest row (SG_NODE_CAP overrides); a query whose graph needs more gets SG_Q_LIMIT. (Sizing them by the
+    // item bound, 28 x more than a full-length graph uses, left no room for chunks large enough to amortise the
+    // latency-bound kernels.)
+    s->itemcap = (uint32_t)std::min<uint64_t>((uint64_t)fam_cap * ix->max_row_len, 0xffffff);
+    s->icap = (uint32_t)std::min<uint64_t>(s->itemcap, env_mb("SG_NODE_CAP", std::max<uint64_t>(4096, 8ull * ix->max_row_len)));
     s->ncap = ix->W < s->icap ? ix->W : s->icap;
     s->gcap = s->icap / DP_T + 1;
     SG_TRY(dmalloc(&s->d_fam_ids, Q * fam_cap)); SG_TRY(dmalloc(&s->d_fam_scores, Q * fam_cap));
@@ -109,13 +116,13 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     // arenas per workspace: traceback (1-2 B per DP cell) and spill rows; SG_TB_ARENA_MB / SG_SPILL_ARENA_MB override
     const uint64_t max_qlen_guess = std::max<uint64_t>(ix->max_row_len, s->max_bases / std::max<uint64_t>(1, Q));
     uint64_t tb_mb = env_mb("SG_TB_ARENA_MB", std::min<uint64_t>(32768, std::max<uint64_t>(64, C * (2 * ix->max_row_len * (max_qlen_guess + 512) / 1000000 + 1))));   // V <= ~1.5 row lengths in practice; a chunk that does not fit is re-run (retire_chunk)
-    uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (256 * max_qlen_guess * 8 / 1000000 + 1))));
+    uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (128 * max_qlen_guess * 8 / 1000000 + 1))));   // ~100 spilled rows per query (group boundaries); a chunk that does not fit is re-run
     s->tb_words = tb_mb * 1024 * 1024 / 4;
     s->spill_elems = sp_mb * 1024 * 1024 / 8;
     // one workspace when the batch is a single chunk, else SG_STREAMS (default 4) so that chunks overlap: measured on
     // B200 (10k full-length queries): 1184 x 2: 91.3k seq/s, 1184 x 3: 99.7k, 888 x 3: 97.3k, 888 x 4: 99.8k, 592 x 4: 98.7k
     const uint64_t n_chunks = (Q + C - 1) / C;
-    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 4)), MAX_WS);
+    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 2)), MAX_WS);
     if ((uint64_t)want > n_chunks) want = (int)n_chunks;
     for (int i = 0; i < want; i++) {
         SG_TRY(alloc_workspace(s, &s->ws[i]));
@@ -337,7 +344,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     SG_CUDA(cudaSetDevice(ix->device));
     Session* s = new Session;
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
-    s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 888)));
+    s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 2368)));
     s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
     s->bankplan = (int)env_mb("SG_BANKPLAN", 0);
     s->graph_generic = (int)env_mb("SG_GRAPH_GENERIC", 0);

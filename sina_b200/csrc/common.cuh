@@ -221,7 +221,8 @@ struct Session {
     int32_t* d_turn = nullptr;        // [nq] chosen orientation 0..3
     uint8_t* d_turn_ops = nullptr;    // [nq]
     // align (whole batch)
-    uint32_t icap = 0, ncap = 0, gcap = 0;  // per-query capacities: items (= nodes = edges), column ranks, DP groups
+    uint32_t icap = 0, ncap = 0, gcap = 0;  // per-query capacities: nodes (= edges; the stride of all per-node arrays), column ranks, DP groups
+    uint32_t itemcap = 0;                   // items (bases of the family rows): item_node / slot of the global-scratch graph path
     uint32_t* d_afam = nullptr;      // [nq][fam_cap] family after the contains-query partition
     uint32_t* d_afam_n = nullptr;    // [nq]
     uint32_t* d_contains = nullptr;  // [nq][fam_cap] 1 + first offset of the query inside the relative, 0 = none

@@ -96,6 +96,7 @@ struct GraphArgs {
     const uint8_t* masks; const uint32_t* cols; const uint64_t* row_off; uint32_t W;
     const uint32_t* afam; const uint32_t* afam_n; uint32_t fam_cap;
     uint32_t icap, ncap, gcap, q0;  // q0: first query of the chunk (workspace arrays are chunk-local)
+    uint32_t itemcap;               // stride of the per-item arrays (generic path)
     GraphHdr* hdr;
     uint8_t *tab, *tabli; uint32_t *colof, *colbase, *item_node, *slot;
     uint32_t* ncol; uint8_t* nmask; uint16_t* ncount; float* nweight; uint32_t* nsigma;
@@ -127,9 +128,12 @@ __device__ uint32_t scan_array_inplace(T* arr, uint32_t n, uint32_t* red) {
 // ---- per-column helpers of the shared-memory path (one thread per column of the family's column table) ----
 constexpr int GK = 6;   // distinct (local node, predecessor) pairs of a column kept in registers; more take the local-memory path
 // predecessor node of row j's base in column c: the node of the row's previous base (NONE: c holds the row's first base)
-__device__ __forceinline__ uint32_t prev_node(const uint8_t* stab, const uint32_t* scolbase, uint32_t F, uint32_t c, uint32_t j) {
+// (the table holds one NIBBLE per (column, family row): Fh = (F + 1) / 2 bytes per column, row j in the low (even j) or
+// high (odd j) half of byte j / 2)
+__device__ __forceinline__ uint32_t prev_node(const uint8_t* stab, const uint32_t* scolbase, uint32_t Fh, uint32_t c, uint32_t j) {
     uint32_t r = c, pe = 0;
-    while (r > 0) { r--; pe = stab[r * F + j]; if (pe) break; }
+    const uint32_t jb = j >> 1, sh = (j & 1u) * 4u;
+    while (r > 0) { r--; pe = (stab[r * Fh + jb] >> sh) & 15u; if (pe) break; }
     return pe ? scolbase[r] + pe - 1u : NONE;
 }
 // the column's distinct keys (local node << 24 | predecessor), ascending, into k[GK]; returns their number, or GK + 1
@@ -138,11 +142,12 @@ __device__ __forceinline__ uint32_t column_keys(const uint8_t* stab, const uint3
 #pragma unroll
     for (int i = 0; i < GK; i++) k[i] = NONE;
     uint32_t nu = 0, last = NONE;
-    const uint8_t* t = stab + c * F;
+    const uint32_t Fh = (F + 1u) >> 1;
+    const uint8_t* t = stab + c * Fh;
     for (uint32_t j = 0; j < F; j++) {
-        const uint32_t e = t[j];
+        const uint32_t e = (t[j >> 1] >> ((j & 1u) * 4u)) & 15u;
         if (!e) continue;
-        const uint32_t p = prev_node(stab, scolbase, F, c, j);
+        const uint32_t p = prev_node(stab, scolbase, Fh, c, j);
         if (p == NONE) continue;
         const uint32_t key = ((e - 1u) << 24) | p;
         if (key == last) continue;            // most rows of a family run through the same pair of nodes
@@ -166,11 +171,12 @@ __device__ __forceinline__ uint32_t column_keys(const uint8_t* stab, const uint3
 // the same for a column with many distinct pairs: sorted list of distinct keys in local memory; returns their number
 __device__ __noinline__ uint32_t column_keys_many(const uint8_t* stab, const uint32_t* scolbase, uint32_t F, uint32_t c, uint32_t* u) {
     uint32_t nu = 0;
-    const uint8_t* t = stab + c * F;
+    const uint32_t Fh = (F + 1u) >> 1;
+    const uint8_t* t = stab + c * Fh;
     for (uint32_t j = 0; j < F; j++) {
-        const uint32_t e = t[j];
+        const uint32_t e = (t[j >> 1] >> ((j & 1u) * 4u)) & 15u;
         if (!e) continue;
-        const uint32_t p = prev_node(stab, scolbase, F, c, j);
+        const uint32_t p = prev_node(stab, scolbase, Fh, c, j);
         if (p == NONE) continue;
         const uint32_t key = ((e - 1u) << 24) | p;
         uint32_t y = nu;
@@ -208,8 +214,8 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     uint32_t* colof = A.colof + (uint64_t)ql * A.ncap;
     uint32_t* colbase = A.colbase + (uint64_t)ql * (A.ncap + 1);
     const uint64_t io = (uint64_t)ql * A.icap;
-    uint32_t* item_node = A.item_node + io;
-    uint32_t* slot = A.slot + io;
+    uint32_t* item_node = A.item_node + (uint64_t)ql * A.itemcap;
+    uint32_t* slot = A.slot + (uint64_t)ql * A.itemcap;
     uint32_t* ncol = A.ncol + io; uint8_t* nmask = A.nmask + io; uint16_t* ncount = A.ncount + io;
     float* nweight = A.nweight + io; uint32_t* nsigma = A.nsigma + io;
     uint32_t* slotbase = A.slotbase + (uint64_t)ql * (A.icap + 1);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     const uint32_t I = scan_array_inplace(famoff, F, red);
     if (tid == 0) famoff[F] = I;
     __syncthreads();
-    if (I > A.icap || F == 0) { if (tid == 0) hdr->status = F == 0 ? (uint32_t)SG_Q_SKIPPED : GS_LIMIT; return; }
+    if (I > A.itemcap || F == 0) { if (tid == 0) hdr->status = F == 0 ? (uint32_t)SG_Q_SKIPPED : GS_LIMIT; return; }
     // item passes: one warp per family row at a time, 4 items per lane and round so that the global loads of a
     // round are all in flight together. ROW_ITEMS(body) runs body(x, at, u) for item x (flat index over the family),
     // `at` = its position in the index arrays.
@@ -269,69 +275,82 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     // sorted predecessor lists are all derived from it, one thread per column; global memory only sees the item reads
     // and the final node / edge arrays. (The generic path below keeps tab / tabli / item_node / slot in global
     // scratch: 3.65 MB of DRAM traffic per query against ~0.4 MB algorithmic, 22 long-scoreboard stalls per issue.)
-    uint8_t* stab = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rowbase + A.fam_cap) + 15u) & ~(uintptr_t)15u);   // [n_cols][F] base masks, then local node index + 1
-    const bool fast = (uint64_t)n_cols * F <= A.stab_bytes && n_cols + 1 <= 2 * words && F <= FAM_CAP_MAX;
+    uint8_t* stab = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(rowbase + A.fam_cap) + 15u) & ~(uintptr_t)15u);   // [n_cols][Fh] nibbles: base masks, then local node index + 1
+    const uint32_t Fh = (F + 1u) >> 1;
+    bool fast = (uint64_t)n_cols * Fh <= A.stab_bytes && n_cols + 1 <= 2 * words && F <= FAM_CAP_MAX;
     if (fast) {
-        uint32_t* scolbase = bitmap;   // [n_cols + 1], over the bitmap / rank arrays once the table is filled
-        // ---- 2. column table
+        // ---- 2. column table (one nibble per entry: a family with lower-case bases, whose nodes differ by case, takes
+        //         the generic path). A warp fills the two rows sharing the table's bytes one after the other.
         {
             uint4* z = reinterpret_cast<uint4*>(stab);
-            const uint32_t nz = (n_cols * F + 15) >> 4;
+            const uint32_t nz = (n_cols * Fh + 15) >> 4;
             for (uint32_t i = tid; i < nz; i += nt) z[i] = make_uint4(0, 0, 0, 0);
+            if (tid == 0) shv[5] = 0;
         }
         __syncthreads();
-        for (uint32_t j = wid; j < F; j += nwarp) {
-            const uint64_t a = rowbase[j];
-            const uint32_t len = famoff[j + 1] - famoff[j];
-            for (uint32_t i0 = lane; i0 < len; i0 += 128) {
-                uint32_t c[4];
-                uint8_t mk[4];
+        uint32_t lower = 0;
+        for (uint32_t jp = wid; jp < Fh; jp += nwarp) {
+            for (uint32_t half = 0; half < 2; half++) {
+                const uint32_t j = 2 * jp + half;
+                if (j >= F) break;
+                const uint64_t a = rowbase[j];
+                const uint32_t len = famoff[j + 1] - famoff[j];
+                for (uint32_t i0 = lane; i0 < len; i0 += 128) {
+                    uint32_t c[4];
+                    uint8_t mk[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    c[u] = NONE;
-                    if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
+                    for (int u = 0; u < 4; u++) {
+                        c[u] = NONE;
+                        if (i0 + 32 * u < len) { c[u] = A.cols[a + i0 + 32 * u]; mk[u] = A.masks[a + i0 + 32 * u]; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (c[u] == NONE) continue;
+                        lower |= mk[u] & 16u;
+                        uint8_t* e = stab + colrank(c[u]) * Fh + jp;
+                        *e = (uint8_t)(*e | ((mk[u] & 15u) << (4 * half)));
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) if (c[u] != NONE) stab[colrank(c[u]) * F + j] = mk[u] & 31u;
+                __syncwarp();
             }
         }
+        if (lower) shv[5] = 1;
         __syncthreads();   // bitmap / wrank are dead from here on
-        // ---- 3. nodes: one per (column, IUPAC char incl. case), local order = first family row bringing it
-        //         (mseq.cpp:88-98). Pass A counts per column, pass B writes node arrays and turns the table entries into
-        //         local node index + 1.
+        if (shv[5]) fast = false;
+    }
+    if (fast) {
+        uint32_t* scolbase = bitmap;   // [n_cols + 1], over the bitmap / rank arrays once the table is filled
+        // ---- 3. nodes: one per (column, IUPAC char), local order = first family row bringing it (mseq.cpp:88-98).
+        //         Pass A counts per column, pass B writes node arrays and turns the table entries into local node index + 1.
+        auto count_column = [&](uint32_t c) -> uint32_t {
+            uint32_t seen = 0, nn = 0;
+            const uint8_t* t = stab + c * Fh;
+            for (uint32_t jb = 0; jb < Fh; jb++) {
+                const uint32_t byte = t[jb], lo = byte & 15u, hi = byte >> 4;
+                if (lo && !((seen >> lo) & 1u)) { seen |= 1u << lo; nn++; }
+                if (hi && !((seen >> hi) & 1u)) { seen |= 1u << hi; nn++; }
+            }
+            return nn;
+        };
         uint32_t cnt_mine[8];   // nodes of the (up to 8) columns this thread owns: columns tid, tid + nt, ...
         {
             uint32_t q8 = 0;
-            for (uint32_t c = tid; c < n_cols; c += nt, q8++) {
-                uint32_t seen = 0, nn = 0;
-                const uint8_t* t = stab + c * F;
-                for (uint32_t j = 0; j < F; j++) { const uint32_t bb = t[j]; if (bb && !((seen >> bb) & 1u)) { seen |= 1u << bb; nn++; } }
-                if (q8 < 8) cnt_mine[q8] = nn;
-            }
+            for (uint32_t c = tid; c < n_cols; c += nt, q8++) { const uint32_t nn = count_column(c); if (q8 < 8) cnt_mine[q8] = nn; }
         }
         __syncthreads();
         {
             uint32_t q8 = 0;
-            for (uint32_t c = tid; c < n_cols; c += nt, q8++) {
-                uint32_t nn;
-                if (q8 < 8) nn = cnt_mine[q8];
-                else {   // more than 8 columns per thread: count again
-                    uint32_t seen = 0; nn = 0;
-                    const uint8_t* t = stab + c * F;
-                    for (uint32_t j = 0; j < F; j++) { const uint32_t bb = t[j]; if (bb && !((seen >> bb) & 1u)) { seen |= 1u << bb; nn++; } }
-                }
-                scolbase[c] = nn;
-            }
+            for (uint32_t c = tid; c < n_cols; c += nt, q8++) scolbase[c] = q8 < 8 ? cnt_mine[q8] : count_column(c);
         }
         __syncthreads();
         const uint32_t V = scan_array_inplace(scolbase, n_cols, red);
         if (tid == 0) scolbase[n_cols] = V;
         if (V > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
         __syncthreads();
-        uint32_t my_masks = 0;   // IUPAC masks (case ignored) of the nodes this thread creates
+        uint32_t my_masks = 0;   // IUPAC masks of the nodes this thread creates
         if (tid == 0) shv[4] = 0;
         for (uint32_t c = tid; c < n_cols; c += nt) {
-            uint8_t* t = stab + c * F;
+            uint8_t* t = stab + c * Fh;
             const uint32_t base = scolbase[c], nn = scolbase[c + 1] - base, col = colof[c];
             colbase[c] = base;
             auto emit = [&](uint32_t k2, uint32_t mask, uint32_t count) {
@@ -346,21 +365,21 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             };
             if (nn <= 4) {   // the usual column: its (up to four) characters and their counts stay in registers
                 uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, have = 0;
-                for (uint32_t j = 0; j < F; j++) {
-                    const uint32_t bb = t[j];
-                    if (!bb) continue;
-                    uint32_t li;
-                    if (have > 0 && bb == m0) { li = 0; c0++; }
-                    else if (have > 1 && bb == m1) { li = 1; c1++; }
-                    else if (have > 2 && bb == m2) { li = 2; c2++; }
-                    else if (have > 3 && bb == m3) { li = 3; c3++; }
-                    else {
-                        li = have;
-                        if (have == 0) { m0 = bb; c0 = 1; } else if (have == 1) { m1 = bb; c1 = 1; }
-                        else if (have == 2) { m2 = bb; c2 = 1; } else { m3 = bb; c3 = 1; }
-                        have++;
-                    }
-                    t[j] = (uint8_t)(li + 1);
+                auto place = [&](uint32_t bb) -> uint32_t {   // local node index + 1 of a base, 0 for none
+                    if (!bb) return 0u;
+                    if (have > 0 && bb == m0) { c0++; return 1u; }
+                    if (have > 1 && bb == m1) { c1++; return 2u; }
+                    if (have > 2 && bb == m2) { c2++; return 3u; }
+                    if (have > 3 && bb == m3) { c3++; return 4u; }
+                    if (have == 0) { m0 = bb; c0 = 1; } else if (have == 1) { m1 = bb; c1 = 1; }
+                    else if (have == 2) { m2 = bb; c2 = 1; } else { m3 = bb; c3 = 1; }
+                    return ++have;
+                };
+                for (uint32_t jb = 0; jb < Fh; jb++) {
+                    const uint32_t byte = t[jb];
+                    if (!byte) continue;
+                    const uint32_t lo = place(byte & 15u), hi = place(byte >> 4);
+                    t[jb] = (uint8_t)(lo | (hi << 4));
                 }
                 if (nn > 0) emit(0, m0, c0);
                 if (nn > 1) emit(1, m1, c1);
@@ -368,15 +387,20 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
                 if (nn > 3) emit(3, m3, c3);
             } else {
                 uint32_t seen = 0, k3 = 0;
-                uint8_t li_of[32];
-                uint16_t cnt[32];
-                uint8_t nm[32];
-                for (uint32_t j = 0; j < F; j++) {
-                    const uint32_t bb = t[j];
-                    if (!bb) continue;
+                uint8_t li_of[16];
+                uint16_t cnt[16];
+                uint8_t nm[16];
+                auto place = [&](uint32_t bb) -> uint32_t {
+                    if (!bb) return 0u;
                     if (!((seen >> bb) & 1u)) { seen |= 1u << bb; li_of[bb] = (uint8_t)k3; cnt[k3] = 1; nm[k3] = (uint8_t)bb; k3++; }
                     else cnt[li_of[bb]]++;
-                    t[j] = li_of[bb] + 1;
+                    return li_of[bb] + 1u;
+                };
+                for (uint32_t jb = 0; jb < Fh; jb++) {
+                    const uint32_t byte = t[jb];
+                    if (!byte) continue;
+                    const uint32_t lo = place(byte & 15u), hi = place(byte >> 4);
+                    t[jb] = (uint8_t)(lo | (hi << 4));
                 }
                 for (uint32_t k2 = 0; k2 < nn; k2++) emit(k2, nm[k2], cnt[k2]);
             }
@@ -435,6 +459,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             __syncthreads();
             if (pass == 0) {
                 E = scan_array_inplace(pred_off, V, red);
+                if (E > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
                 if (tid == 0) pred_off[V] = E;
                 if (A.forbid) for (uint32_t m = tid; m < V; m += nt) A.nmaxins[io + m] = 1000000u;
                 __syncthreads();
@@ -589,6 +614,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
         }
         __syncthreads();
         E = scan_array_inplace(pred_off, V, red);
+        if (E > A.icap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
         if (tid == 0) pred_off[V] = E;
         __syncthreads();
         for (uint32_t m = tid; m < V; m += nt) {
@@ -1018,7 +1044,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     GraphArgs A;
     A.masks = ix->d_masks; A.cols = ix->d_cols; A.row_off = ix->d_row_off; A.W = ix->W;
     A.afam = s->d_afam; A.afam_n = s->d_afam_n; A.fam_cap = s->fam_cap;
-    A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap; A.q0 = q0;
+    A.icap = s->icap; A.ncap = s->ncap; A.gcap = s->gcap; A.q0 = q0; A.itemcap = s->itemcap;
     A.hdr = s->d_hdr; A.tab = w->d_tab; A.tabli = w->d_tabli; A.colof = w->d_colof; A.colbase = w->d_colbase;
     A.item_node = w->d_item_node; A.slot = w->d_slot; A.ncol = w->d_ncol; A.nmask = w->d_nmask;
     A.ncount = w->d_ncount; A.nweight = w->d_nweight; A.nsigma = w->d_nsigma; A.slotbase = w->d_slotbase;
@@ -1034,7 +1060,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     // column table in shared memory: what the batch's families can need (columns <= items of the longest rows), capped so
     // that two CTAs stay resident per SM; a family that needs more takes the global-scratch path
     const uint64_t want = std::min<uint64_t>(s->ncap, (uint64_t)ix->max_row_len * 2) * s->fam_cap;
-    A.stab_bytes = s->graph_generic ? 0u : (uint32_t)((std::min<uint64_t>(want, env_kb("SG_STAB_KB", 80) * 1024) + 15u) & ~15ull);
+    A.stab_bytes = s->graph_generic ? 0u : (uint32_t)((std::min<uint64_t>((want + 1) / 2, env_kb("SG_STAB_KB", 40) * 1024) + 15u) & ~15ull);   // a nibble per entry
     size_t smem = base_smem + 16 + A.stab_bytes;
     if (smem > 200 * 1024) { A.stab_bytes = 0; smem = base_smem + 16; }   // very wide alignments: the bitmap alone fills the SM
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
