@@ -31,9 +31,10 @@ struct __align__(16) NodeRec {
     uint32_t pred_off;
     uint32_t pred[4];   // predecessors 0..3 (ascending id)
     uint32_t ptb[3];    // tbbase of predecessors 0..2: their traceback cells can be requested as soon as THIS record is known,
-    uint32_t psoff;     // [7:0], [15:8], [23:16] their step offsets            without waiting for their own records
+    uint32_t psoff;     // [9:0], [19:10], [29:20] their step offsets           without waiting for their own records
 };
 static_assert(sizeof(NodeRec) == 48, "NodeRec is read as three 16-byte loads");
+static_assert(DP_T <= 1024, "step offsets inside a group are packed into 10 bits");
 
 struct BtArgs {
     uint32_t nq, W, q0;  // nq queries of the chunk starting at q0
@@ -195,8 +196,8 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
             b.z = np > 2 ? preds[po + 2] : 0u;
             b.w = np > 3 ? preds[po + 3] : 0u;
             if (np > 0) { c.x = tb_of(b.x, soff); c.w |= soff; }
-            if (np > 1) { c.y = tb_of(b.y, soff); c.w |= soff << 8; }
-            if (np > 2) { c.z = tb_of(b.z, soff); c.w |= soff << 16; }
+            if (np > 1) { c.y = tb_of(b.y, soff); c.w |= soff << 10; }
+            if (np > 2) { c.z = tb_of(b.z, soff); c.w |= soff << 20; }
             uint4* dst = reinterpret_cast<uint4*>(rec + m);
             __stcg(dst, a);
             __stcg(dst + 1, b);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(32 * BT_WARPS) backtrack_kernel(BtArgs A) {
             if (lane < 3) {
                 uint4 fake = ra;
                 fake.x = lane == 0 ? rc.x : (lane == 1 ? rc.y : rc.z);
-                fake.y = (rc.w >> (8 * lane)) & 0xffu;
+                fake.y = (rc.w >> (10 * lane)) & 0x3ffu;
                 spec_raw = cell_raw(fake, s - 1);
             }
             ldrec3(pk, qa, qb, qc);

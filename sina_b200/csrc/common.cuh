@@ -40,18 +40,39 @@ constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts
 constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
+typedef uint16_t rcol_t;                     // ring column index
+#ifdef DP_LARGE   // experiment: double-size DP CTAs (480 rows + 32 loader lanes), two per SM
+constexpr int DP_BLOCK = 512;
+#ifndef DP_CTAS
+#define DP_CTAS 2
+#endif
+constexpr int DP_CTAS_PER_SM = DP_CTAS;
+constexpr int DP_T = 480;
+#elif defined(DP_SMALL)   // experiment: half-size DP CTAs (96 rows + 32 loader lanes), twice as many per SM: smaller barrier domains
+constexpr int DP_BLOCK = 128;
+#ifndef DP_CTAS
+#define DP_CTAS 7
+#endif
+constexpr int DP_CTAS_PER_SM = DP_CTAS;
+constexpr int DP_T = 96;
+#else
 constexpr int DP_BLOCK = 256;                // threads per DP CTA = columns of the shared-memory ring
 #ifndef DP_CTAS
 #define DP_CTAS 4
 #endif
 constexpr int DP_CTAS_PER_SM = DP_CTAS;            // resident DP CTAs per SM the kernels are compiled for (register cap)
 constexpr int DP_T = 224;                    // node rows per DP group (compute lanes, one row each)
+#endif
+#ifndef GRAPH_THREADS
+#define GRAPH_THREADS 384
+#endif
+constexpr int GRAPH_BLOCK = DP_BLOCK > GRAPH_THREADS ? DP_BLOCK : GRAPH_THREADS;             // threads of the graph kernel's CTA
 constexpr int DP_G = DP_BLOCK - DP_T;        // loader lanes: ghost columns (far predecessors) + spill writers
 constexpr int DP_RING = 8;                   // ring depth (time slots) of the shared-memory row window
 constexpr int DP_MAXD = 4;                   // v2 kernel: largest column-rank distance of a predecessor served by the ring
                                              // (the generic kernel serves DP_RING - 2); farther ones go through ghosts
-constexpr int DP_RS2 = 257;                  // v2 kernel: 16-byte cells per time slot of the ring (one bank group more than a multiple of 8)
-constexpr uint32_t DP_COL_PAD = 254, DP_COL_EDGE = 255;   // v2 kernel: constant ring columns (mesh.cu)
+constexpr int DP_RS2 = DP_BLOCK + 1;         // v2 kernel: 16-byte cells per time slot of the ring (one bank group more than a multiple of 8)
+constexpr uint32_t DP_COL_PAD = DP_BLOCK - 2, DP_COL_EDGE = DP_BLOCK - 1;   // v2 kernel: constant ring columns (mesh.cu)
 constexpr int GHOST_PF = 2;                  // steps a ghost requests its data ahead of publishing it
 constexpr int GHOST_LEAD = GHOST_PF + 2;     // a ghost trails a source row of its own group by >= this many column ranks
 static_assert(GHOST_LEAD <= DP_MAXD, "an in-group edge too long for the ring must be long enough for a ghost");
@@ -166,7 +187,7 @@ struct Workspace {
     uint32_t* d_pdesc = nullptr;     // [n][icap] near/far descriptor per edge (generic kernel)
     uint32_t* d_pdesc2 = nullptr;    // [n][icap] (delta<<16 | ring column) per edge (v2 kernel)
     uint32_t* d_order = nullptr;     // [n][gcap*DP_T] node handled by (group, thread) in the v2 kernel
-    uint8_t* d_rcol = nullptr;       // [n][gcap*DP_T] ring column (group, thread) publishes to: a permutation inside every 16-thread block
+    rcol_t* d_rcol = nullptr;       // [n][gcap*DP_T] ring column (group, thread) publishes to: a permutation inside every 16-thread block
     uint16_t* d_nthr = nullptr;      // [n][icap] thread (ring column) of a node inside its group
     uint8_t* d_nshift = nullptr;     // [n][icap] predecessor-slot shift of a node (v2: slot = ordinal + shift)
     uint32_t* d_nmaxins = nullptr;   // [n][icap] --insertion forbid: free columns between a node and its nearest successor

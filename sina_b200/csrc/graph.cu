@@ -103,7 +103,7 @@ struct GraphArgs {
     uint32_t *slotbase, *cursor, *pred_off, *preds, *pdesc; int32_t* spillrow; uint8_t* nflags;
     uint32_t* lastnodes; GroupInfo* groups;
     uint32_t* nmaxins; int forbid;   // --insertion forbid
-    uint32_t* order; uint8_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
+    uint32_t* order; rcol_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
     unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
     uint32_t stab_bytes;   // shared-memory budget of the column table (fast path of steps 2-5)
@@ -189,7 +189,7 @@ __device__ __noinline__ uint32_t column_keys_many(const uint8_t* stab, const uin
     return nu;
 }
 
-__global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
+__global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
     extern __shared__ uint32_t sm[];
     const uint32_t q = A.q0 + blockIdx.x;  // global query index (hdr, family); workspace uses the local index
     const uint32_t ql = blockIdx.x;
@@ -651,6 +651,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
     // ends are in the same group and at most DP_RING-2 column ranks apart; otherwise the predecessor row
     // is spilled to global memory ("far").
     const uint32_t T = DP_T;
+    static_assert(GRAPH_BLOCK >= DP_T, "the v2 plan below gives every row of a group its own thread");
     const uint32_t n_groups = (V + T - 1) / T;
     if (n_groups > A.gcap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
     for (uint32_t m = tid; m < V; m += nt) {
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(DP_BLOCK) graph_kernel(GraphArgs A) {
             base += tot;
         }
         if (tid >= n && tid < T) order[(uint64_t)g * T + tid] = NONE;
-        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (uint8_t)tid;   // ring column of the thread's row
+        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (rcol_t)tid;   // ring column of the thread's row
         if (tid == 0) { shv[2] = 0; shv[3] = 0; }  // far edges, ghosts
         __syncthreads();
         if (valid) {
@@ -824,7 +825,7 @@ static_assert(DP_RS2 % 8 == 1, "bank group formula of the plan");
 struct BankPlanArgs {
     const GraphHdr* hdr; uint32_t q0, gcap, icap;
     const uint32_t* order; const uint16_t* nthr; const uint32_t* pred_off; const uint32_t* preds; const uint32_t* nsigma;
-    uint32_t* pdesc2; uint8_t* rcol; int sweeps;
+    uint32_t* pdesc2; rcol_t* rcol; int sweeps;
 };
 
 __global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A) {
@@ -856,7 +857,7 @@ __global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A)
     for (uint32_t g = w; g < h.n_groups; g += BP_WARPS) {
         const uint32_t lo = g * T, n = min(T, h.V - lo);
         const uint32_t* order = A.order + ((uint64_t)ql * A.gcap + g) * T;
-        uint8_t* rcol = A.rcol + ((uint64_t)ql * A.gcap + g) * T;
+        rcol_t* rcol = A.rcol + ((uint64_t)ql * A.gcap + g) * T;
         // in-degree of the row at every position; lane i keeps the specialisation width of DP warp i
         uint32_t npw_mine = 1;
         for (uint32_t wi = 0; wi < T / 32; wi++) {
@@ -1064,7 +1065,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     size_t smem = base_smem + 16 + A.stab_bytes;
     if (smem > 200 * 1024) { A.stab_bytes = 0; smem = base_smem + 16; }   // very wide alignments: the bitmap alone fills the SM
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_kernel<<<n, DP_BLOCK, smem, w->stream>>>(A);
+    graph_kernel<<<n, GRAPH_BLOCK, smem, w->stream>>>(A);
     s->stats.kernel_launches += 1;
     if (s->bankplan) {
         BankPlanArgs B;

@@ -27,7 +27,7 @@ struct MeshArgs {
     const GraphHdr* hdr; const GroupInfo* groups; uint32_t gcap, icap, q0;
     const uint8_t* nmask; const float* nweight; const uint32_t* nsigma;
     const uint32_t* pred_off; const uint32_t* pdesc; const int32_t* spillrow; const uint8_t* nflags;
-    const uint32_t* pdesc2; const uint32_t* order; const uint8_t* rcol; const uint16_t* nthr; uint8_t* nshift;
+    const uint32_t* pdesc2; const uint32_t* order; const rcol_t* rcol; const uint16_t* nthr; uint8_t* nshift;
     const GhostInfo* ghosts; const uint32_t* writers;
     const uint32_t* nmaxins; int forbid;   // --insertion forbid (generic kernel only): free columns after each node
     uint32_t* tb; float2* spill;
@@ -61,7 +61,7 @@ constexpr int NSLOT2 = R + DP_MAXD - 1;
 constexpr int LBASE = R - DP_MAXD;            // first linear slot index that exists
 constexpr uint32_t RING2_BYTES = SLOT2 * NSLOT2;
 constexpr uint32_t COL_PAD = DP_COL_PAD, COL_EDGE = DP_COL_EDGE;
-constexpr int QB_PAD = 512;                   // zero bits either side of the query in the match-bit planes
+constexpr int QB_PAD = 2 * DP_T + 64 <= 512 ? 512 : 1024;                   // zero bits either side of the query in the match-bit planes
 constexpr int QB_BASE_PLANES = 15;            // planes 15..18: scratch (one plane per base bit A G C U)
 constexpr int QB_PLANES = 19;
 static_assert(DP_T + DP_G - 2 <= (int)COL_PAD, "ghost columns must end below the constant columns");
