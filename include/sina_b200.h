@@ -146,6 +146,37 @@ int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint
                  const sg_fam_params* fp, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
                  sg_align_result* results);
 
+/* ---- --search stage and the sequence comparator ------------------------------------------------------ */
+/* search_filter options, defaults = reference defaults (src/search_filter.cpp:96-133, src/cseq_comparator.cpp:432-462) */
+typedef struct sg_search_params {
+    uint32_t kmer_candidates;  /* --search-kmer-candidates 1000 */
+    uint32_t max_result;       /* --search-max-result 10 */
+    float min_sim;             /* --search-min-sim 0.7 */
+    int32_t ignore_super;      /* --search-ignore-super (the reference's partition + erase KEEPS the candidates that contain
+                                * the query, src/search_filter.cpp:313-316: reproduced) */
+    int32_t iupac;             /* --search-iupac: 0 optimistic, 1 pessimistic, 2 exact */
+    int32_t correction;        /* --search-correction: 0 none, 1 jc */
+    int32_t cover;             /* --search-cover: 0 abs, 1 query, 2 target, 3 overlap, 4 all, 5 average, 6 min, 7 max, 8 nogap */
+    int32_t filter_lowercase;  /* --search-filter-lowercase */
+} sg_search_params;
+void sg_default_search_params(sg_search_params* p);
+/* rank[i] = position of reference i's name in ascending lexicographic order: search::result_item orders equal scores by
+ * name (src/search.h:56-68). n = 0 clears them (ties then go by reference id). */
+int sg_index_set_name_ranks(sg_index* ix, const uint32_t* rank, uint32_t n);
+/* cseq_comparator::operator() (src/cseq_comparator.cpp:209-293) of aligned sequence q (bases amasks, strictly increasing
+ * alignment columns acols, rows aoff[q]..aoff[q+1]) against the reference rows ref_ids[ref_off[q]..ref_off[q+1]).
+ * out[ref_off[nq]]: match count / cover-rule base as float; 0/0 (nothing to compare) is NaN as in the reference. */
+int sg_identity_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t nq,
+                      const uint32_t* ref_ids, const uint64_t* ref_off, int iupac, int correction, int cover,
+                      int filter_lowercase, float* out);
+/* search_filter::operator() (src/search_filter.cpp:244-330, the k-mer branch: --search-all is not offered) for a batch of
+ * ALIGNED sequences: k-mer search for kmer_candidates references, identity of every candidate, the max_result best by
+ * (score, name) descending with score > min_sim. out_ids / out_scores [nq * max_result], out_n [nq] (0 for sequences
+ * shorter than 20 bases). kmer_candidates * (index tiles) must not exceed 16384. With correction = jc the logarithm and
+ * the final selection run on the host (the reference's double log), everything before it on the device. */
+int sg_search_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t nq,
+                    const sg_search_params* sp, uint32_t* out_ids, float* out_scores, uint32_t* out_n);
+
 /* ---- session: the same stages with the batch resident in HBM (used by bench.py for the device-only
  * number and by the host-buffer calls above internally) ------------------------------------------- */
 int sg_session_create(sg_index* ix, uint32_t max_queries, uint64_t max_bases, sg_session** out);

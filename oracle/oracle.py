@@ -165,6 +165,48 @@ def render(masks, cols, W):
     return s.tobytes().decode()
 
 
+def compare_np(amasks, acols, bmasks, bcols, iupac=0, dist=0, cover=1, filter_lc=False):
+    """numpy restatement of cseq_comparator::operator() (src/cseq_comparator.cpp:57-118,209-293): the merge loop's
+    counters in closed form (this is the derivation the CUDA kernel uses; pinned against the compiled reference in
+    tests/test_search.py). Rows are (masks, strictly increasing columns). Returns float32 (NaN for 0/0)."""
+    am, ac = np.asarray(amasks, np.uint8), np.asarray(acols, np.int64)
+    bm, bc = np.asarray(bmasks, np.uint8), np.asarray(bcols, np.int64)
+    af = (am & 16) != 0 if filter_lc else np.zeros(len(am), bool)
+    bf = (bm & 16) != 0 if filter_lc else np.zeros(len(bm), bool)
+    ai, bi = np.nonzero(~af)[0], np.nonzero(~bf)[0]
+    if len(ai) == 0 or len(bi) == 0:
+        return np.float32(np.nan)      # the reference dereferences end() here
+    ta0, ta1, tb0, tb1 = ai[0], ai[-1] + 1, bi[0], bi[-1] + 1   # filtered bases trimmed at both ends (:65-79)
+    am, ac, af = am[ta0:ta1], ac[ta0:ta1], af[ta0:ta1]
+    bm, bc, bf = bm[tb0:tb1], bc[tb0:tb1], bf[tb0:tb1]
+    lo, hi = max(ac[0], bc[0]), min(ac[-1], bc[-1])             # columns both sequences span (:81-117)
+    a_in, b_in = (ac >= lo) & (ac <= hi), (bc >= lo) & (bc <= hi)
+    ovh_a, ovh_b = int((~a_in & ~af).sum()), int((~b_in & ~bf).sum())
+    pos = np.searchsorted(ac, bc)
+    has = (pos < len(ac)) & (ac[np.minimum(pos, len(ac) - 1)] == bc) & b_in
+    pa = np.minimum(pos, len(ac) - 1)
+    both_unf = has & ~bf & ~af[pa]
+    x, y = am[pa] & 15, bm & 15
+    if iupac == 0:
+        eq = (x & y) != 0
+    elif iupac == 1:
+        eq = (np.array([bin(v).count("1") for v in x]) <= 1) & (x == y)
+    else:
+        eq = x == y
+    match, mismatch = int((both_unf & eq).sum()), int((both_unf & ~eq).sum())
+    only_a = int((a_in & ~af).sum()) - match - mismatch
+    only_b = int((b_in & ~bf).sum()) - match - mismatch
+    base = [1, match + mismatch + only_a + ovh_a, match + mismatch + only_b + ovh_b, match + mismatch + only_a + only_b,
+            match + mismatch + only_a + only_b + ovh_a + ovh_b, match + mismatch + (only_a + only_b + ovh_a + ovh_b) // 2,
+            match + mismatch + min(only_a + ovh_a, only_b + ovh_b), match + mismatch + max(only_a + ovh_a, only_b + ovh_b),
+            match + mismatch][cover]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d = np.float32(match) / np.float32(base)
+        if dist == 1:
+            d = np.float32(-3.0 / 4 * np.log(1.0 - 4.0 / 3 * np.float64(d)))
+    return np.float32(d)
+
+
 class Oracle:
     """Plain-C restatement (sina_oracle.c)."""
 
@@ -390,6 +432,11 @@ class Ref:
                                 C.c_uint32, C.c_void_p, C.c_uint64]
         L.ref_kmers.restype = C.c_int
         L.ref_kmers.argtypes = [C.c_char_p, C.c_int, C.c_int, u32p, C.c_int]
+        L.ref_compare.restype = C.c_float
+        L.ref_compare.argtypes = [C.c_uint32, u8p, u32p, C.c_uint32, u8p, u32p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.ref_search.restype = C.c_int
+        L.ref_search.argtypes = [C.c_void_p, C.c_uint32, u8p, u32p, C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, u32p, f32p]
         L.ref_vlimap_increment.restype = C.c_int
         L.ref_vlimap_increment.argtypes = [C.c_uint32, u32p, C.c_uint32, C.c_int, i16p]
         L.ref_fix_duplicate_positions.restype = C.c_int
@@ -477,6 +524,21 @@ class Ref:
         P = C.c_uint64()
         n = self.L.ref_kidx_find(ix, query.encode(), max_results, sc, ids, C.byref(P))
         return sc[:n].copy(), ids[:n].copy(), P.value
+
+    def compare(self, amasks, acols, bmasks, bcols, iupac=0, dist=0, cover=1, filter_lc=False):
+        """cseq_comparator::operator() (src/cseq_comparator.cpp:209-293) on two aligned rows given as (masks, columns)"""
+        ac, bc = MASK2RNA[np.asarray(amasks, np.uint8) & 31].copy(), MASK2RNA[np.asarray(bmasks, np.uint8) & 31].copy()
+        return float(self.L.ref_compare(len(ac), ac, np.ascontiguousarray(acols, np.uint32), len(bc), bc,
+                                        np.ascontiguousarray(bcols, np.uint32), iupac, dist, cover, int(filter_lc)))
+
+    def search(self, ix, masks, cols, kmer_candidates=1000, max_result=10, min_sim=0.7, ignore_super=False, iupac=0,
+               dist=0, cover=1, filter_lc=False):
+        """search_filter::operator() (src/search_filter.cpp:244-330, k-mer branch) for one aligned query"""
+        ch = MASK2RNA[np.asarray(masks, np.uint8) & 31].copy()
+        ids, sc = np.zeros(max(1, max_result), np.uint32), np.zeros(max(1, max_result), np.float32)
+        n = self.L.ref_search(ix, len(ch), ch, np.ascontiguousarray(cols, np.uint32), kmer_candidates, max_result,
+                              min_sim, int(ignore_super), iupac, dist, cover, int(filter_lc), ids, sc)
+        return ids[:n].copy(), sc[:n].copy()
 
     def turn_check(self, ix, query, all_frames=True):
         sc = np.zeros(4, np.int32)

@@ -8,7 +8,9 @@
 // What is the reference's own code here:      mseq ctor, dag::sort/reduce_edges, compute(),
 //   backtrack(), cseq::append/reverse/setWidth/fix_duplicate_positions/getAligned,
 //   kmer generators (all_/prefix_/unique_ kmers), vlimap (push_back/invert/increment).
+//   cseq_comparator::operator() (cseq_comparator.cpp, compiled whole; its option parsing only has to compile).
 // What is restated (needs ARB/boost/TBB in the reference, so cannot be compiled):
+//   search_filter::operator(), k-mer branch (src/search_filter.cpp:244-330)
 //   kmer_search::impl::build/find  (src/kmer_search.cpp:152-276, 365-420)
 //   famfinder::impl::match + gap filter + fs_req (src/famfinder.cpp:497-612, 474-491)
 //   aligner::operator() pre-steps and do_align glue (src/align.cpp:320-460, 475-521)
@@ -38,6 +40,7 @@ std::shared_ptr<spdlog::logger> Log::create_logger(std::string name) {
 #include "cseq.h"
 #include "kmer.h"
 #include "idset.h"
+#include "cseq_comparator.h"
 
 using namespace sina;
 
@@ -416,6 +419,73 @@ int ref_family(ref_kidx* ix, const char* qname, const char* query, const ref_fam
     for (uint32_t i = 0; i < n && i < cap; i++) { ids[i] = fam[i].id; scores[i] = fam[i].score; }
     if (n < p->fs_req) return -1;
     return (int)n;
+}
+
+// ---------------------------------------------------------------- identity / --search
+static cseq packed_cseq(const char* name, uint32_t n, const uint8_t* chars, const uint32_t* cols) {
+    cseq c(name, nullptr);
+    for (uint32_t j = 0; j < n; j++) c.append(aligned_base(cols[j], chars[j]));
+    return c;
+}
+
+// cseq_comparator::operator() (src/cseq_comparator.cpp:209-293), the reference's own code.
+// iupac: 0 optimistic 1 pessimistic 2 exact; dist: 0 none 1 jc; cover: CMP_COVER_TYPE order (abs, query, target, overlap,
+// all, average, min, max, nogap)
+float ref_compare(uint32_t na, const uint8_t* achars, const uint32_t* acols, uint32_t nb, const uint8_t* bchars,
+                  const uint32_t* bcols, int iupac, int dist, int cover, int filter_lc) {
+    cseq a = packed_cseq("a", na, achars, acols), b = packed_cseq("b", nb, bchars, bcols);
+    cseq_comparator cmp((CMP_IUPAC_TYPE)iupac, (CMP_DIST_TYPE)dist, (CMP_COVER_TYPE)cover, filter_lc != 0);
+    return cmp(a, b);
+}
+
+// search_filter::operator() (src/search_filter.cpp:244-330), the branch without --search-all: find(kmer_candidates),
+// --search-ignore-super's partition + erase (which KEEPS the candidates containing the query, :313-316), comparator
+// score of every candidate (:318-320), partial_sort by greater<result_item> = (score, name) descending (:322-330),
+// cut at the first score <= min_sim. Returns the number of results, 0 for queries shorter than 20 bases (:253-256).
+int ref_search(ref_kidx* ix, uint32_t n, const uint8_t* chars, const uint32_t* cols, uint32_t kmer_candidates,
+               uint32_t max_result, float min_sim, int ignore_super, int iupac, int dist, int cover, int filter_lc,
+               uint32_t* ids, float* scores) {
+    cseq c = packed_cseq("query", n, chars, cols);
+    if (c.size() < 20) return 0;
+    struct item {
+        float score;
+        const cseq* sequence;
+        bool operator<(const item& o) const {   // search::result_item (src/search.h:56-68)
+            if (score < o.score) return true;
+            if (score > o.score) return false;
+            return *sequence < *o.sequence;
+        }
+        bool operator>(const item& o) const { return !operator<(o); }
+    };
+    std::vector<item> vc;
+    {   // index->find(*c, vc, kmer_candidates) (src/kmer_search.cpp:365-420)
+        uint32_t max = std::min<uint32_t>(kmer_candidates, ix->db->seqs.size());
+        std::vector<rank_pair> ranks;
+        kidx_rank(ix, c, ranks, nullptr);
+        std::partial_sort(ranks.begin(), ranks.begin() + max, ranks.end(), std::greater<rank_pair>());
+        for (uint32_t i = 0; i < max; i++) vc.push_back({(float)ranks[i].first, &ix->db->seqs[ranks[i].second]});
+    }
+    auto iupac_compare = [](const aligned_base& a, const aligned_base& b) { return a.comp(b); };
+    auto contains_query = [&](item& it) {
+        const auto& hay = it.sequence->getAlignedBases();
+        const auto& needle = c.getAlignedBases();
+        return std::search(hay.begin(), hay.end(), needle.begin(), needle.end(), iupac_compare) != hay.end();   // boost::algorithm::contains
+    };
+    if (ignore_super) {
+        auto it = std::partition(vc.begin(), vc.end(), contains_query);
+        vc.erase(it, vc.end());
+    }
+    cseq_comparator cmp((CMP_IUPAC_TYPE)iupac, (CMP_DIST_TYPE)dist, (CMP_COVER_TYPE)cover, filter_lc != 0);
+    for (auto& r : vc) r.score = cmp(c, *r.sequence);
+    auto it = vc.begin();
+    auto middle = vc.begin() + max_result;
+    auto end = vc.end();
+    if (middle > end) middle = end;
+    std::partial_sort(it, middle, end, std::greater<item>());
+    while (it != middle && it->score > min_sim) ++it;
+    vc.erase(it, vc.end());
+    for (size_t i = 0; i < vc.size(); i++) { ids[i] = (uint32_t)(vc[i].sequence - ix->db->seqs.data()); scores[i] = vc[i].score; }
+    return (int)vc.size();
 }
 
 // ---------------------------------------------------------------- graph dump

@@ -19,6 +19,7 @@ EXPORTS = [
     "sg_default_fam_params", "sg_default_align_params", "sg_last_error", "sg_device_count",
     "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list", "sg_index_set_column_weights", "sg_index_export_lists",
     "sg_find_batch", "sg_turn_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
+    "sg_default_search_params", "sg_index_set_name_ranks", "sg_identity_batch", "sg_search_batch",
     "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_turn", "sg_session_family",
     "sg_session_set_family", "sg_session_align", "sg_session_run", "sg_session_sync", "sg_session_download_find",
     "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
@@ -57,6 +58,22 @@ class AlignParams(C.Structure):
                  overhang=0, lowercase=0, insertion=0, realign=0):
         super().__init__(match_score, mismatch_score, gap_penalty, gap_ext_penalty, fs_weight, overhang, lowercase,
                          insertion, realign)
+
+
+IUPAC_RULES = {"optimistic": 0, "pessimistic": 1, "exact": 2}
+CORRECTIONS = {"none": 0, "jc": 1}
+COVER_RULES = {"abs": 0, "query": 1, "target": 2, "overlap": 3, "all": 4, "average": 5, "min": 6, "max": 7, "nogap": 8}
+
+
+class SearchParams(C.Structure):
+    """sg_search_params; defaults are SINA's (src/search_filter.cpp:96-133, src/cseq_comparator.cpp:432-462)."""
+    _fields_ = [("kmer_candidates", C.c_uint32), ("max_result", C.c_uint32), ("min_sim", C.c_float),
+                ("ignore_super", C.c_int32), ("iupac", C.c_int32), ("correction", C.c_int32), ("cover", C.c_int32),
+                ("filter_lowercase", C.c_int32)]
+
+    def __init__(self, kmer_candidates=1000, max_result=10, min_sim=0.7, ignore_super=0, iupac=0, correction=0, cover=1,
+                 filter_lowercase=0):
+        super().__init__(kmer_candidates, max_result, min_sim, ignore_super, iupac, correction, cover, filter_lowercase)
 
 
 class AlignResult(C.Structure):
@@ -110,6 +127,12 @@ def lib():
                                  C.c_void_p]
     L.sg_run_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_void_p, C.POINTER(FamParams),
                                C.POINTER(AlignParams), u32p, u8p, C.c_void_p]
+    L.sg_default_search_params.argtypes = [C.POINTER(SearchParams)]
+    L.sg_default_search_params.restype = None
+    L.sg_index_set_name_ranks.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.sg_identity_batch.argtypes = [C.c_void_p, u8p, u32p, u64p, C.c_uint32, u32p, u64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    f32p]
+    L.sg_search_batch.argtypes = [C.c_void_p, u8p, u32p, u64p, C.c_uint32, C.POINTER(SearchParams), u32p, f32p, u32p]
     L.sg_session_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p)]
     L.sg_session_destroy.argtypes = [C.c_void_p]
     L.sg_session_destroy.restype = None
@@ -188,6 +211,38 @@ class Index:
         else:
             w = np.ascontiguousarray(w, np.float32)
             _check(lib().sg_index_set_column_weights(self.h, w.ctypes.data_as(C.c_void_p), len(w)))
+
+    def set_name_ranks(self, names):
+        """order of the references' names: search::result_item breaks score ties by name (src/search.h:56-68). `names` =
+        list of N strings (or None: ties go by reference id)"""
+        if names is None:
+            _check(lib().sg_index_set_name_ranks(self.h, None, 0))
+            return
+        order = sorted(range(len(names)), key=lambda i: (names[i], i))
+        rank = np.zeros(len(names), np.uint32)
+        rank[np.asarray(order)] = np.arange(len(names), dtype=np.uint32)
+        _check(lib().sg_index_set_name_ranks(self.h, rank.ctypes.data_as(C.c_void_p), len(rank)))
+
+    def identity(self, amasks, acols, aoff, ref_ids, ref_off, iupac=0, correction=0, cover=1, filter_lowercase=0):
+        """cseq_comparator::operator() of aligned sequences against reference rows (flat pair list per query)"""
+        amasks, acols = np.ascontiguousarray(amasks, np.uint8), np.ascontiguousarray(acols, np.uint32)
+        aoff, ref_off = np.ascontiguousarray(aoff, np.uint64), np.ascontiguousarray(ref_off, np.uint64)
+        ref_ids = np.ascontiguousarray(ref_ids, np.uint32)
+        out = np.zeros(max(1, len(ref_ids)), np.float32)
+        _check(lib().sg_identity_batch(self.h, amasks, acols, aoff, len(aoff) - 1, ref_ids if len(ref_ids) else np.zeros(1, np.uint32),
+                                       ref_off, iupac, correction, cover, filter_lowercase, out))
+        return out[:len(ref_ids)]
+
+    def search(self, amasks, acols, aoff, sp=None):
+        """--search stage (search_filter::operator()) for a batch of aligned sequences: (ids[nq,max_result],
+        scores[nq,max_result], n[nq])"""
+        sp = sp or SearchParams()
+        amasks, acols = np.ascontiguousarray(amasks, np.uint8), np.ascontiguousarray(acols, np.uint32)
+        aoff = np.ascontiguousarray(aoff, np.uint64)
+        nq = len(aoff) - 1
+        ids, sc, n = np.zeros((nq, sp.max_result), np.uint32), np.zeros((nq, sp.max_result), np.float32), np.zeros(nq, np.uint32)
+        _check(lib().sg_search_batch(self.h, amasks, acols, aoff, nq, C.byref(sp), ids, sc, n))
+        return ids, sc, n
 
     def info(self):
         N, W, nt, ts = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()

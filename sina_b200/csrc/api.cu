@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -167,6 +168,12 @@ int sg_device_count(void) {
     return n;
 }
 
+void sg_default_search_params(sg_search_params* p) {
+    if (!p) return;
+    p->kmer_candidates = 1000; p->max_result = 10; p->min_sim = 0.7f; p->ignore_super = 0;
+    p->iupac = 0; p->correction = 0; p->cover = 1; p->filter_lowercase = 0;
+}
+
 void sg_default_fam_params(sg_fam_params* p) {
     p->fs_min = 40; p->fs_max = 40; p->fs_msc = 0.7f; p->fs_msc_max = 2.0f; p->fs_min_len = 150; p->fs_req_full = 1;
     p->fs_full_len = 1400; p->fs_req_gaps = 10; p->fs_req = 1; p->leave_query_out = 0;
@@ -246,7 +253,7 @@ void sg_index_destroy(sg_index* h) {
     cudaSetDevice(ix->device);
     if (ix->cached) { sg_session_destroy((sg_session*)ix->cached); ix->cached = nullptr; }
     cudaFree(ix->d_masks); cudaFree(ix->d_cols); cudaFree(ix->d_row_off); cudaFree(ix->d_list_off); cudaFree(ix->d_colw);
-    cudaFree(ix->d_postings);
+    cudaFree(ix->d_postings); cudaFree(ix->d_name_rank);
     delete ix;
 }
 
@@ -262,6 +269,20 @@ int sg_index_set_column_weights(sg_index* h, const float* weights, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) if (!(weights[i] == weights[i])) SG_FAIL(SG_ERR_ARG, "sg_index_set_column_weights: NaN weight");
     SG_TRY(dmalloc(&ix->d_colw, (uint64_t)n));
     SG_CUDA(cudaMemcpy(ix->d_colw, weights, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return SG_OK;
+}
+
+int sg_index_set_name_ranks(sg_index* h, const uint32_t* rank, uint32_t n) {
+    Index* ix = (Index*)h;
+    if (!ix) SG_FAIL(SG_ERR_ARG, "null index");
+    if (n != 0 && (n != ix->N || !rank)) SG_FAIL(SG_ERR_ARG, "sg_index_set_name_ranks: one rank per reference (or n = 0 for none)");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    SG_CUDA(cudaSetDevice(ix->device));
+    SG_CUDA(cudaDeviceSynchronize());
+    if (ix->d_name_rank) { cudaFree(ix->d_name_rank); ix->d_name_rank = nullptr; }
+    if (n == 0) return SG_OK;
+    SG_TRY(dmalloc(&ix->d_name_rank, (uint64_t)n));
+    SG_CUDA(cudaMemcpy(ix->d_name_rank, rank, (size_t)n * 4, cudaMemcpyHostToDevice));
     return SG_OK;
 }
 
@@ -372,7 +393,7 @@ void sg_session_destroy(sg_session* h) {
     free_align(s);
     void* ptrs[] = {s->d_full_scores, s->d_full_tmp, s->d_full_keys, s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results,
-                    s->d_turn_scores, s->d_turn, s->d_turn_ops};
+                    s->d_turn_scores, s->d_turn, s->d_turn_ops, s->d_acols, s->d_pair, s->d_sids, s->d_sscores, s->d_sn};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->cev) if (e) cudaEventDestroy(e);
@@ -972,6 +993,134 @@ int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
         SG_TRY(align_streaming(L.s, fp, ap, out_cols ? out_cols + qoff[a] : nullptr, out_masks ? out_masks + qoff[a] : nullptr));
         SG_TRY(sg_session_download_align(s, nullptr, nullptr, results ? results + a : nullptr));
+    }
+    return SG_OK;
+}
+
+// ---- --search stage and the sequence comparator ------------------------------------------------------
+namespace {
+int validate_cmp(int iupac, int correction, int cover, const char* who) {
+    if (iupac < 0 || iupac > 2 || correction < 0 || correction > 1 || cover < 0 || cover > 8) SG_FAIL(SG_ERR_ARG, std::string(who) + ": comparator rule out of range");
+    if (cover == 0 && correction != 0) SG_FAIL(SG_ERR_ARG, std::string(who) + ": only fractional identity can be distance corrected");   // src/cseq_comparator.cpp:478-481
+    return SG_OK;
+}
+// jukes_cantor() of the reference (src/cseq_comparator.cpp:42-44): host double log, as the reference computes it
+float jukes_cantor(float in) { return (float)(-3.0 / 4 * std::log(1.0 - 4.0 / 3 * in)); }
+
+int upload_aligned(Session* s, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t n) {
+    SG_TRY(sg_session_upload((sg_session*)s, amasks, aoff, n, nullptr));
+    if (!s->d_acols) SG_TRY(dmalloc(&s->d_acols, s->max_bases));
+    const uint64_t base = aoff[0], total = aoff[n] - base;
+    for (uint32_t q = 0; q < n; q++)
+        for (uint64_t j = aoff[q] + 1; j < aoff[q + 1]; j++)
+            if (acols[j] <= acols[j - 1]) SG_FAIL(SG_ERR_ARG, "aligned sequence: columns must be strictly increasing");
+    SG_CUDA(cudaMemcpyAsync(s->d_acols, acols + base, total * 4, cudaMemcpyHostToDevice, s->stream));
+    return SG_OK;
+}
+}  // namespace
+
+int sg_identity_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t nq,
+                      const uint32_t* ref_ids, const uint64_t* ref_off, int iupac, int correction, int cover,
+                      int filter_lowercase, float* out) {
+    if (!ix || !amasks || !acols || !aoff || !ref_ids || !ref_off || !out || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_identity_batch: bad argument");
+    SG_TRY(validate_cmp(iupac, correction, cover, "sg_identity_batch"));
+    Index* X = (Index*)ix;
+    for (uint64_t i = ref_off[0]; i < ref_off[nq]; i++) if (ref_ids[i] >= X->N) SG_FAIL(SG_ERR_ARG, "sg_identity_batch: reference id out of range");
+    SessionLease L(ix, aoff, nq);
+    if (L.rc) return L.rc;
+    Session* s = L.s;
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(upload_aligned(s, amasks, acols, aoff + a, n));
+        const uint64_t p0 = ref_off[a], np = ref_off[a + n] - p0;
+        if (np == 0) continue;
+        uint32_t* d_ids = nullptr; uint64_t* d_off = nullptr; float* d_sc = nullptr;
+        std::vector<uint64_t> off(n + 1);
+        for (uint32_t i = 0; i <= n; i++) off[i] = ref_off[a + i] - p0;
+        int rc = dmalloc(&d_ids, np);
+        if (rc == SG_OK) rc = dmalloc(&d_off, (uint64_t)n + 1);
+        if (rc == SG_OK) rc = dmalloc(&d_sc, np);
+        if (rc == SG_OK && cudaMemcpyAsync(d_ids, ref_ids + p0, np * 4, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) rc = SG_ERR_CUDA;
+        if (rc == SG_OK && cudaMemcpyAsync(d_off, off.data(), ((uint64_t)n + 1) * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) rc = SG_ERR_CUDA;
+        if (rc == SG_OK) rc = launch_identity(s, s->d_qmasks, s->d_acols, s->d_qoff, n, nullptr, nullptr, 0, d_ids, d_off, iupac, cover, filter_lowercase, 0, d_sc);
+        if (rc == SG_OK && cudaMemcpyAsync(out + p0, d_sc, np * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) rc = SG_ERR_CUDA;
+        if (rc == SG_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = SG_ERR_CUDA;
+        cudaFree(d_ids); cudaFree(d_off); cudaFree(d_sc);
+        if (rc != SG_OK) { if (rc == SG_ERR_CUDA) set_error("sg_identity_batch: CUDA failure"); return rc; }
+        if (correction == 1) for (uint64_t i = p0; i < p0 + np; i++) out[i] = jukes_cantor(out[i]);
+    }
+    return SG_OK;
+}
+
+int sg_search_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t nq,
+                    const sg_search_params* sp, uint32_t* out_ids, float* out_scores, uint32_t* out_n) {
+    if (!ix || !amasks || !acols || !aoff || !sp || !out_ids || !out_scores || !out_n || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_search_batch: bad argument");
+    SG_TRY(validate_cmp(sp->iupac, sp->correction, sp->cover, "sg_search_batch"));
+    if (sp->kmer_candidates == 0 || sp->max_result == 0) SG_FAIL(SG_ERR_ARG, "sg_search_batch: kmer_candidates and max_result must be > 0");
+    Index* X = (Index*)ix;
+    SessionLease L(ix, aoff, nq);
+    if (L.rc) return L.rc;
+    Session* s = L.s;
+    const uint32_t cand = std::min(sp->kmer_candidates, X->N), mr = sp->max_result;
+    if (cand > s->pair_cap) {
+        if (s->d_pair) { cudaFree(s->d_pair); s->d_pair = nullptr; s->pair_cap = 0; }
+        SG_TRY(dmalloc(&s->d_pair, (uint64_t)s->max_q * cand));
+        s->pair_cap = cand;
+    }
+    if (mr > s->sres_cap) {
+        cudaFree(s->d_sids); cudaFree(s->d_sscores); s->d_sids = nullptr; s->d_sscores = nullptr; s->sres_cap = 0;
+        SG_TRY(dmalloc(&s->d_sids, (uint64_t)s->max_q * mr));
+        SG_TRY(dmalloc(&s->d_sscores, (uint64_t)s->max_q * mr));
+        s->sres_cap = mr;
+    }
+    if (!s->d_sn) SG_TRY(dmalloc(&s->d_sn, (uint64_t)s->max_q));
+    for (uint32_t a = 0; a < nq; a += L.step()) {
+        const uint32_t n = std::min(L.step(), nq - a);
+        SG_TRY(upload_aligned(s, amasks, acols, aoff + a, n));
+        SG_TRY(sg_session_find((sg_session*)s, cand));   // index->find(*c, vc, kmer_candidates) (src/search_filter.cpp:303)
+        SG_TRY(launch_identity(s, s->d_qmasks, s->d_acols, s->d_qoff, n, s->d_ranked, s->d_nres, s->find_max, nullptr, nullptr,
+                               sp->iupac, sp->cover, sp->filter_lowercase, sp->ignore_super, s->d_pair));
+        if (sp->correction == 0) {
+            SG_TRY(launch_search_select(s, s->d_pair, s->d_ranked, s->d_nres, s->find_max, n, mr, sp->min_sim, s->d_sids, s->d_sscores, s->d_sn));
+            SG_CUDA(cudaMemcpyAsync(out_ids + (uint64_t)a * mr, s->d_sids, (uint64_t)n * mr * 4, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaMemcpyAsync(out_scores + (uint64_t)a * mr, s->d_sscores, (uint64_t)n * mr * 4, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaMemcpyAsync(out_n + a, s->d_sn, (uint64_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaStreamSynchronize(s->stream));
+        } else {
+            // --search-correction jc: the reference corrects with the host's double log before it sorts; the identities
+            // come from the device, the logarithm and the (score, name) selection of max_result items run here
+            const uint32_t st = s->find_max;
+            std::vector<float> pair((uint64_t)n * st);
+            std::vector<uint64_t> keys((uint64_t)n * st);
+            std::vector<uint32_t> nr(n), rank;
+            SG_CUDA(cudaMemcpyAsync(pair.data(), s->d_pair, pair.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaMemcpyAsync(keys.data(), s->d_ranked, keys.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+            SG_CUDA(cudaMemcpyAsync(nr.data(), s->d_nres, (uint64_t)n * 4, cudaMemcpyDeviceToHost, s->stream));
+            if (X->d_name_rank) { rank.resize(X->N); SG_CUDA(cudaMemcpyAsync(rank.data(), X->d_name_rank, (uint64_t)X->N * 4, cudaMemcpyDeviceToHost, s->stream)); }
+            SG_CUDA(cudaStreamSynchronize(s->stream));
+            struct item { float score; uint32_t rk, id; };
+            std::vector<item> v;
+            for (uint32_t q = 0; q < n; q++) {
+                v.clear();
+                for (uint32_t i = 0; i < nr[q]; i++) {
+                    uint32_t bits; const float raw = pair[(uint64_t)q * st + i];
+                    memcpy(&bits, &raw, 4);
+                    if (bits >= 0x7f800000u) continue;
+                    const float jc = jukes_cantor(raw);
+                    if (!(jc == jc)) continue;
+                    const uint32_t id = (uint32_t)keys[(uint64_t)q * st + i];
+                    v.push_back({jc, rank.empty() ? id : rank[id], id});
+                }
+                auto gt = [](const item& x, const item& y) { return x.score > y.score || (x.score == y.score && x.rk > y.rk); };
+                const size_t m = std::min<size_t>(mr, v.size());
+                std::partial_sort(v.begin(), v.begin() + m, v.end(), gt);
+                uint32_t e = 0;
+                while (e < m && v[e].score > sp->min_sim) { out_ids[(uint64_t)(a + q) * mr + e] = v[e].id; out_scores[(uint64_t)(a + q) * mr + e] = v[e].score; e++; }
+                out_n[a + q] = e;
+            }
+        }
+        // search_filter skips sequences shorter than 20 bases (src/search_filter.cpp:253-256)
+        for (uint32_t q = 0; q < n; q++) if (aoff[a + q + 1] - aoff[a + q] < 20) out_n[a + q] = 0;
     }
     return SG_OK;
 }

@@ -41,28 +41,18 @@ constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predec
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
 typedef uint16_t rcol_t;                     // ring column index
-#ifdef DP_LARGE   // experiment: double-size DP CTAs (480 rows + 32 loader lanes), two per SM
-constexpr int DP_BLOCK = 512;
-#ifndef DP_CTAS
-#define DP_CTAS 2
+// DP CTA shape: DP_THREADS threads = DP_THREADS - 32 row lanes + one loader warp; DP_CTAS resident CTAs per SM (the
+// register cap the kernels are compiled for). Measured on B200 (full-length 16S queries, GCUPS of the DP kernel):
+// 128 threads x 7 CTAs 481, 192 x 5 560, 224 x 5 552, 256 x 4 604, 512 x 2 537.
+#ifndef DP_THREADS
+#define DP_THREADS 256
 #endif
+#ifndef DP_CTAS
+#define DP_CTAS (DP_THREADS >= 512 ? 2 : DP_THREADS >= 256 ? 4 : DP_THREADS >= 192 ? 5 : 7)
+#endif
+constexpr int DP_BLOCK = DP_THREADS;         // threads per DP CTA = columns of the shared-memory ring
 constexpr int DP_CTAS_PER_SM = DP_CTAS;
-constexpr int DP_T = 480;
-#elif defined(DP_SMALL)   // experiment: half-size DP CTAs (96 rows + 32 loader lanes), twice as many per SM: smaller barrier domains
-constexpr int DP_BLOCK = 128;
-#ifndef DP_CTAS
-#define DP_CTAS 7
-#endif
-constexpr int DP_CTAS_PER_SM = DP_CTAS;
-constexpr int DP_T = 96;
-#else
-constexpr int DP_BLOCK = 256;                // threads per DP CTA = columns of the shared-memory ring
-#ifndef DP_CTAS
-#define DP_CTAS 4
-#endif
-constexpr int DP_CTAS_PER_SM = DP_CTAS;            // resident DP CTAs per SM the kernels are compiled for (register cap)
-constexpr int DP_T = 224;                    // node rows per DP group (compute lanes, one row each)
-#endif
+constexpr int DP_T = DP_BLOCK - 32;          // node rows per DP group (compute lanes, one row each)
 #ifndef GRAPH_THREADS
 #define GRAPH_THREADS 384
 #endif
@@ -122,6 +112,7 @@ struct Index {
     uint16_t* d_postings = nullptr; // reference id minus the sub-tile's first id, unordered inside a list
     uint64_t n_postings = 0;
     float* d_colw = nullptr;        // [W] positional column weights (scoring_scheme_weighted), null = none
+    uint32_t* d_name_rank = nullptr; // [N] rank of the reference's name in ascending order (ties of the --search stage), null = id
     void* cached = nullptr;  // Session reused by the host-buffer entry points
     std::mutex mu;           // serialises host-buffer calls on this index
 };
@@ -237,6 +228,14 @@ struct Session {
     float* d_fam_scores = nullptr;   // [nq][fam_cap]
     int32_t* d_fam_n = nullptr;      // [nq] (-1: too few, -2: window too small)
     uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window
+    // --search stage (lazily allocated)
+    uint32_t* d_acols = nullptr;     // [max_bases] alignment columns of the aligned queries
+    float* d_pair = nullptr;         // [max_q][pair_cap] identity of (query, candidate)
+    uint32_t pair_cap = 0;
+    uint32_t* d_sids = nullptr;      // [max_q][sres_cap] results
+    float* d_sscores = nullptr;
+    uint32_t* d_sn = nullptr;        // [max_q]
+    uint32_t sres_cap = 0;
     // orientation check (--turn)
     int32_t* d_turn_scores = nullptr; // [4][nq] top k-mer score of the query as is / reversed / complemented / both
     int32_t* d_turn = nullptr;        // [nq] chosen orientation 0..3
@@ -283,6 +282,11 @@ int launch_index_build(Index* ix, cudaStream_t st);
 int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
 // ranked: rank-ordered keys of the range (stride `window`); null = the session's d_ranked
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr);
+int launch_identity(Session* s, const uint8_t* d_amasks, const uint32_t* d_acols, const uint64_t* d_aoff, uint32_t nq,
+                    const uint64_t* ranked, const uint32_t* nres, uint32_t stride, const uint32_t* pair_ids,
+                    const uint64_t* pair_off, int iupac, int cover, int filter_lc, int ignore_super, float* d_scores);
+int launch_search_select(Session* s, const float* d_scores, const uint64_t* ranked, const uint32_t* nres, uint32_t stride,
+                         uint32_t nq, uint32_t max_result, float min_sim, uint32_t* d_ids, float* d_out, uint32_t* d_n);
 int launch_find_full(Session* s, uint32_t q0, uint32_t n);   // every reference in rank order for n <= full_cap queries
 int launch_turn(Session* s, int all);
 int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0 = 0, uint32_t n = 0);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
 
     // ---- 0. item offsets of the family rows
     for (uint32_t i = tid; i < words; i += nt) bitmap[i] = 0;
-    uint32_t* rb32 = shv + 8 + 2 * FARLIST_CAP + 2 * DP_G;
+    uint32_t* rb32 = shv + 8 + 2 * FARLIST_CAP + 2 * DP_G + DP_T;
     if (reinterpret_cast<uintptr_t>(rb32) & 7u) rb32++;
     uint64_t* rowbase = reinterpret_cast<uint64_t*>(rb32);  // [fam_cap] first item of family row j in the index
     for (uint32_t j = tid; j < F; j += nt) {
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
     // ends are in the same group and at most DP_RING-2 column ranks apart; otherwise the predecessor row
     // is spilled to global memory ("far").
     const uint32_t T = DP_T;
-    static_assert(GRAPH_BLOCK >= DP_T, "the v2 plan below gives every row of a group its own thread");
+    static_assert(DP_T % 8 == 0 && GRAPH_BLOCK >= DP_T, "the v2 plan below gives every row of a group its own thread");
     const uint32_t n_groups = (V + T - 1) / T;
     if (n_groups > A.gcap) { if (tid == 0) hdr->status = GS_LIMIT; return; }
     for (uint32_t m = tid; m < V; m += nt) {
@@ -692,6 +692,7 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
     uint32_t* far_gi = far_e + FARLIST_CAP;      // [FARLIST_CAP] ghost index of the edge
     uint32_t* gh_p = far_gi + FARLIST_CAP;       // [DP_G] ghost source node
     uint32_t* gh_b = gh_p + DP_G;                // [DP_G] ghost bucket
+    uint32_t* rwant = gh_b + DP_G;               // [DP_T] ring column wish, then ring column, of the row at a thread
     if (tid == 0) shv[1] = 0;                    // overflow flag
     __syncthreads();
     for (uint32_t g = 0; g < n_groups; g++) {
@@ -710,19 +711,51 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
             base += tot;
         }
         if (tid >= n && tid < T) order[(uint64_t)g * T + tid] = NONE;
-        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (rcol_t)tid;   // ring column of the thread's row
+        if (tid < T) rwant[tid] = NONE;
         if (tid == 0) { shv[2] = 0; shv[3] = 0; }  // far edges, ghosts
         __syncthreads();
+        // Ring column of every row. A row publishes its cells into one column of the DP's shared-memory ring and
+        // its successors read them with LDS.128; the 8 lanes of a quarter-warp are served in one wavefront only if
+        // their cells lie in 8 different 16-byte bank groups. Bank group of (column c, distance d) = (c - d) mod 8
+        // (the ring's slot stride is one cell more than a multiple of eight, mesh.cu). So a row asks for the column
+        // whose bank group equals the LANE (mod 8) of the successor that will read it, preferring the successor with
+        // the fewest predecessors: if every lane of a quarter-warp gets its wish the load is conflict free. The
+        // column stays inside the row's own block of 8 threads (the stores of a warp keep covering whole lines),
+        // wishes that collide inside a block are granted in thread order, the others take what is left.
         if (valid) {
-            const uint32_t sg_ = nsigma[m];
+            const uint32_t sg_ = nsigma[m], me = nthr[m];
             for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
                 const uint32_t p = preds[e], d = sg_ - nsigma[p];
-                if (p >= lo && d <= (uint32_t)DP_MAXD) pdesc2[e] = (d << 16) | nthr[p];
+                if (p >= lo && d <= (uint32_t)DP_MAXD) atomicMin(&rwant[nthr[p]], (min(np, 15u) << 3) | ((me + d) & 7u));
                 else {
                     const uint32_t i = atomicAdd(&shv[2], 1u);
                     if (i < FARLIST_CAP) far_e[i] = e; else shv[1] = 1;
                     pdesc2[e] = m;  // remember the consumer until the ghost is known
                 }
+            }
+        }
+        __syncthreads();
+        if (tid < T / 8) {
+            uint32_t used = 0, w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                w[i] = rwant[tid * 8 + i];
+                const uint32_t b = w[i] & 7u;
+                if (w[i] != NONE && !((used >> b) & 1u)) { used |= 1u << b; w[i] = b; } else w[i] = NONE;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (w[i] == NONE) { w[i] = (uint32_t)__ffs((int)~used) - 1u; used |= 1u << w[i]; }
+                rwant[tid * 8 + i] = tid * 8 + w[i];
+            }
+        }
+        __syncthreads();
+        if (tid < T) A.rcol[((uint64_t)ql * A.gcap + g) * T + tid] = (rcol_t)rwant[tid];
+        if (valid) {
+            const uint32_t sg_ = nsigma[m];
+            for (uint32_t e = pred_off[m]; e < pred_off[m + 1]; e++) {
+                const uint32_t p = preds[e], d = sg_ - nsigma[p];
+                if (p >= lo && d <= (uint32_t)DP_MAXD) pdesc2[e] = (d << 16) | rwant[nthr[p]];
             }
         }
         __syncthreads();
@@ -1057,7 +1090,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
     A.fs_weight = ap.fs_weight;
     const uint32_t words = (ix->W + 31) >> 5;
-    const size_t base_smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + 1 + 2 * s->fam_cap) * 4;
+    const size_t base_smem = (size_t)(2 * words + s->fam_cap + 1 + 33 + 8 + 2 * FARLIST_CAP + 2 * DP_G + DP_T + 1 + 2 * s->fam_cap) * 4;
     // column table in shared memory: what the batch's families can need (columns <= items of the longest rows), capped so
     // that two CTAs stay resident per SM; a family that needs more takes the global-scratch path
     const uint64_t want = std::min<uint64_t>(s->ncap, (uint64_t)ix->max_row_len * 2) * s->fam_cap;

@@ -136,6 +136,12 @@ struct V2Lane {
     float* lastcol_ptr;
 };
 
+template <int NPW>
+struct V2Addr {
+    uint32_t ak[NPW];        // shared addresses of the predecessor cells read by the next pair of steps
+    uint32_t aw;             // ... and of the row's own cell
+};
+
 // Two steps (four query positions) of a row from step t0 (even).
 // A ring cell is (value, dm) per position: dm = min(value + gap, gapm_val + gapext) is the deletion candidate the
 // cell offers to every successor row (deletion(), mesh.h:305-330, evaluated once by the row it leaves from instead
@@ -159,16 +165,18 @@ struct V2Lane {
 // the barrier for the warp that had none).
 template <int NPW, bool EDGES>
 __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
-                                              const uint32_t qb, float (&pvp)[NPW], float& E) {
+                                              const uint32_t qb, float (&pvp)[NPW], float& E, V2Addr<NPW>& AD,
+                                              uint32_t* const prev_p, const uint32_t prev_w) {
     const float INF = __int_as_float(0x7f800000);
     constexpr bool RAW = v2_raw_cells(NPW);
     uint32_t tbw = 0;
-    // ring phase of the first step: 0, 2, 4 or 6; the second step is one slot further (an immediate, no wrap)
-    const uint32_t x0 = (t0 & (R - 1)) * SLOT2;
+    // ring phase of the first step: 0, 2, 4 or 6; the second step is one slot further (an immediate, no wrap).
+    // The addresses were computed during the previous pair of steps: the loads are the first instructions behind
+    // the barrier, nothing else sits between the release and their issue.
     uint32_t ak[NPW];
 #pragma unroll
-    for (int k = 0; k < NPW; k++) ak[k] = L.pk[k] + x0;
-    const uint32_t aw = L.wadr + x0;
+    for (int k = 0; k < NPW; k++) ak[k] = AD.ak[k];
+    const uint32_t aw = AD.aw;
     // main copy (index u, read by consumers whose phase wrapped): phases LBASE..R-1; mirror (index u + R): phases 0..R-2
     static_assert(LBASE == 4 && R == 8, "the store predicates below are written for 8 phases, main copy from phase 4 on");
     const uint32_t p_main = t0 & 4u, p_mir1 = (t0 & 6u) ^ 6u;
@@ -178,6 +186,15 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
         float4 c[NPW];
 #pragma unroll
         for (int k = 0; k < NPW; k++) c[k] = v ? lds_f4<(int)SLOT2>(ak[k]) : lds_f4<0>(ak[k]);
+        if (v == 0) {
+            __stcs(prev_p, prev_w);   // the previous pair's traceback word leaves in the shadow of the loads (streaming:
+                                      // the traceback must not push the spill rows out of L2)
+        } else {
+            const uint32_t xn = ((t0 + 2u) & (R - 1)) * SLOT2;
+#pragma unroll
+            for (int k = 0; k < NPW; k++) AD.ak[k] = L.pk[k] + xn;
+            AD.aw = L.wadr + xn;
+        }
         if (EDGES) {
             // s == 0 (mesh.h:294-301,469-473): value starts from 1, no insertion, no match. E = 1 supplies that 1 and
             // makes the next insertion an extension exactly when value(m,0) == 1 (gaps_val == value)
@@ -289,6 +306,17 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
     // three phases: edge steps [e0, c0), inner steps [c0, c1), edge steps [c1, e1); the match bits are fetched for 16
     // steps at a time (32 query positions) and consumed from a register, four per pair of steps
     uint32_t* tbp = tbl + (uint64_t)(e0 >> 1) * T;
+    // a pair's traceback word is stored during the next pair (the first store writes 0 to the word the first pair
+    // then overwrites)
+    uint32_t* prev_p = tbp;
+    uint32_t prev_w = 0;
+    V2Addr<NPW> AD;
+    {
+        const uint32_t xn = (e0 & (R - 1)) * SLOT2;
+#pragma unroll
+        for (int k = 0; k < NPW; k++) AD.ak[k] = L.pk[k] + xn;
+        AD.aw = L.wadr + xn;
+    }
 #pragma unroll 1
     for (int ph = 0; ph < 3; ph++) {
         uint32_t t0 = ph == 0 ? e0 : (ph == 1 ? c0 : c1);
@@ -299,20 +327,23 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
             if (ph == 1) {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    __stcs(tbp, v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E));   // streaming: the traceback must not push the spill rows out of L2
+                    prev_w = v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E, AD, prev_p, prev_w);
+                    prev_p = tbp;
                     tbp += T;
                     qb >>= 4;
                 }
             } else {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    __stcs(tbp, v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E));
+                    prev_w = v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E, AD, prev_p, prev_w);
+                    prev_p = tbp;
                     tbp += T;
                     qb >>= 4;
                 }
             }
         }
     }
+    __stcs(prev_p, prev_w);
     for (uint32_t t0 = e1; t0 < steps8; t0 += 2) { __syncthreads(); __syncthreads(); }
 }
 
