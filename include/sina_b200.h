@@ -53,7 +53,9 @@ typedef struct sg_fam_params {
     uint32_t fs_min;       /* --fs-min 40 */
     uint32_t fs_max;       /* --fs-max 40 */
     float fs_msc;          /* --fs-msc 0.7 */
-    float fs_msc_max;      /* --fs-msc-max 2 (values < 1 need the identity filter: unsupported, SG_ERR_ARG) */
+    float fs_msc_max;      /* --fs-msc-max 2: candidates more identical to the query than this are dropped (remove_similar,
+                            * src/famfinder.cpp:553-556). Identities are <= 1; values < 1 need the queries' own positions
+                            * (sg_family_batch_aligned / sg_session_set_query_columns) */
     uint32_t fs_min_len;   /* --fs-min-len 150 */
     uint32_t fs_req_full;  /* --fs-req-full 1 */
     uint32_t fs_full_len;  /* --fs-full-len 1400 */
@@ -141,6 +143,11 @@ int sg_family_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, u
 int sg_align_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const uint32_t* fam_ids,
                    const uint64_t* fam_off, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
                    sg_align_result* results);
+/* sg_family_batch for queries that carry positions (a pre-aligned input, as the reference's evaluation runs with
+ * --fs-msc-max < 1 use): qcols[j] = position of base j, strictly increasing inside a query; null = sg_family_batch. */
+int sg_family_batch_aligned(sg_index* ix, const uint8_t* qmasks, const uint32_t* qcols, const uint64_t* qoff, uint32_t nq,
+                            const int64_t* exclude_ids, const sg_fam_params* fp, uint32_t fam_stride, uint32_t* fam_ids,
+                            float* fam_scores, int32_t* fam_n);
 /* famfinder + aligner for a batch: host in, host out. */
 int sg_run_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq, const int64_t* exclude_ids,
                  const sg_fam_params* fp, const sg_align_params* ap, uint32_t* out_cols, uint8_t* out_masks,
@@ -183,6 +190,9 @@ int sg_session_create(sg_index* ix, uint32_t max_queries, uint64_t max_bases, sg
 void sg_session_destroy(sg_session* s);
 int sg_session_upload(sg_session* s, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
                       const int64_t* exclude_ids);
+/* positions of the uploaded batch's bases (same layout as qmasks, starting at the batch's first base): needed by
+ * --fs-msc-max < 1 only; forgotten at the next upload */
+int sg_session_set_query_columns(sg_session* s, const uint32_t* qcols);
 int sg_session_find(sg_session* s, uint32_t max);
 /* orientation check on the resident batch; the queries are left in the chosen orientation (turn may be null) */
 int sg_session_turn(sg_session* s, int mode, int32_t* turn);

@@ -359,7 +359,7 @@ int ref_turn_check(ref_kidx* ix, const char* query, int all, int32_t* scores4) {
 // ---------------------------------------------------------------- family selection (restated)
 struct fam_item { float score; uint32_t id; };
 
-// famfinder::impl::match (famfinder.cpp:497-612) + gap filter (:474-480). fs_msc_max must be > 2
+// famfinder::impl::match (famfinder.cpp:497-612) + gap filter (:474-480); remove_similar with the reference's comparator
 // (identity filter needs cseq_comparator; off at default). returns family size.
 static uint32_t select_family(const ref_kidx* ix, const cseq& query, const ref_fam_params& p,
                               std::vector<fam_item>& fam, uint64_t* postings) {
@@ -369,9 +369,11 @@ static uint32_t select_family(const ref_kidx* ix, const cseq& query, const ref_f
     kidx_rank(ix, query, ranks, postings);
     size_t have = 0, have_full = 0;
     auto is_full = [&](const fam_item& r) { return seqs[r.id].size() >= p.fs_full_len; };
+    cseq_comparator similar(CMP_IUPAC_OPTIMISTIC, CMP_DIST_NONE, CMP_COVER_QUERY, false);   // famfinder.cpp:554
     auto remove = [&](const fam_item& r) {
         bool rm = seqs[r.id].size() < p.fs_min_len ||
                   (p.leave_query_out && query.getName() == seqs[r.id].getName()) ||
+                  (p.fs_msc_max <= 2 && similar(query, seqs[r.id]) > p.fs_msc_max) ||   // remove_similar (:553-556)
                   (have >= p.fs_min && (have >= p.fs_max || !(r.score < p.fs_msc)) &&
                    !(p.fs_req_full && have_full < p.fs_req_full && is_full(r)));
         if (rm) return true;

@@ -20,6 +20,7 @@ EXPORTS = [
     "sg_index_create", "sg_index_destroy", "sg_index_info", "sg_index_list_sizes", "sg_index_list", "sg_index_set_column_weights", "sg_index_export_lists",
     "sg_find_batch", "sg_turn_batch", "sg_family_batch", "sg_align_batch", "sg_run_batch",
     "sg_default_search_params", "sg_index_set_name_ranks", "sg_identity_batch", "sg_search_batch",
+    "sg_family_batch_aligned", "sg_session_set_query_columns",
     "sg_session_create", "sg_session_destroy", "sg_session_upload", "sg_session_find", "sg_session_turn", "sg_session_family",
     "sg_session_set_family", "sg_session_align", "sg_session_run", "sg_session_sync", "sg_session_download_find",
     "sg_session_download_family", "sg_session_download_align", "sg_session_stats", "sg_session_timer", "sg_session_dump_graph",
@@ -123,6 +124,9 @@ def lib():
     L.sg_turn_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_int, i32p]
     L.sg_family_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_void_p, C.POINTER(FamParams), C.c_uint32,
                                   u32p, f32p, i32p]
+    L.sg_family_batch_aligned.argtypes = [C.c_void_p, u8p, C.c_void_p, u64p, C.c_uint32, C.c_void_p, C.POINTER(FamParams),
+                                          C.c_uint32, u32p, f32p, i32p]
+    L.sg_session_set_query_columns.argtypes = [C.c_void_p, u32p]
     L.sg_align_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, u32p, u64p, C.POINTER(AlignParams), u32p, u8p,
                                  C.c_void_p]
     L.sg_run_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint32, C.c_void_p, C.POINTER(FamParams),
@@ -283,13 +287,16 @@ class Index:
         _check(lib().sg_turn_batch(self.h, qmasks, qoff, nq, TURN_MODES[mode], out))
         return out
 
-    def family(self, qmasks, qoff, fp=None, exclude_ids=None):
+    def family(self, qmasks, qoff, fp=None, exclude_ids=None, qcols=None):
+        """famfinder stage; `qcols` = positions of the query bases (pre-aligned input), needed by fs_msc_max < 1"""
         fp = fp or FamParams()
         qmasks, qoff = np.ascontiguousarray(qmasks, np.uint8), np.ascontiguousarray(qoff, np.uint64)
-        nq, stride = len(qoff) - 1, fp.fs_max + fp.fs_req_full + 1
+        nq, stride = len(qoff) - 1, max(fp.fs_min, fp.fs_max) + fp.fs_req_full + 1
         ids, sc, n = np.zeros((nq, stride), np.uint32), np.zeros((nq, stride), np.float32), np.zeros(nq, np.int32)
         keep, ex = _excl_ptr(exclude_ids)
-        _check(lib().sg_family_batch(self.h, qmasks, qoff, nq, ex, C.byref(fp), stride, ids, sc, n))
+        qc = None if qcols is None else np.ascontiguousarray(qcols, np.uint32)
+        _check(lib().sg_family_batch_aligned(self.h, qmasks, None if qc is None else qc.ctypes.data_as(C.c_void_p), qoff, nq, ex,
+                                             C.byref(fp), stride, ids, sc, n))
         return ids, sc, n
 
     def align(self, qmasks, qoff, fam_ids, fam_off, ap=None):

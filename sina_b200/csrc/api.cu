@@ -150,7 +150,6 @@ static int validate_align_params(const sg_align_params* ap) {
 }
 static int validate_fam_params(const sg_fam_params* fp) {
     if (!fp) SG_FAIL(SG_ERR_ARG, "family params missing");
-    if (fp->fs_msc_max < 1.0f) SG_FAIL(SG_ERR_ARG, "--fs-msc-max < 1 needs the identity filter: not supported");
     if (fp->fs_max == 0) SG_FAIL(SG_ERR_ARG, "--fs-max must be > 0");
     return SG_OK;
 }
@@ -393,7 +392,7 @@ void sg_session_destroy(sg_session* h) {
     free_align(s);
     void* ptrs[] = {s->d_full_scores, s->d_full_tmp, s->d_full_keys, s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results,
-                    s->d_turn_scores, s->d_turn, s->d_turn_ops, s->d_acols, s->d_pair, s->d_sids, s->d_sscores, s->d_sn};
+                    s->d_turn_scores, s->d_turn, s->d_turn_ops, s->d_qcols, s->d_fpair, s->d_acols, s->d_pair, s->d_sids, s->d_sscores, s->d_sn};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->cev) if (e) cudaEventDestroy(e);
@@ -445,6 +444,22 @@ int sg_session_upload(sg_session* h, const uint8_t* qmasks, const uint64_t* qoff
     if (exclude_ids) SG_CUDA(cudaMemcpyAsync(s->d_excl, exclude_ids, (uint64_t)nq * 8, cudaMemcpyHostToDevice, s->stream));
     else SG_CUDA(cudaMemsetAsync(s->d_excl, 0xff, (uint64_t)nq * 8, s->stream));
     s->have_find = s->have_family = s->have_align = false;
+    s->have_qcols = false;
+    return SG_OK;
+}
+
+int sg_session_set_query_columns(sg_session* h, const uint32_t* qcols) {
+    Session* s = (Session*)h;
+    if (!s || s->nq == 0 || !qcols) SG_FAIL(SG_ERR_ARG, "sg_session_set_query_columns: no queries uploaded");
+    SG_CUDA(cudaSetDevice(s->ix->device));
+    const uint64_t total = s->h_qoff[s->nq];
+    for (uint32_t q = 0; q < s->nq; q++)
+        for (uint64_t j = s->h_qoff[q] + 1; j < s->h_qoff[q + 1]; j++)
+            if (qcols[j] <= qcols[j - 1]) SG_FAIL(SG_ERR_ARG, "query positions must be strictly increasing");
+    if (!s->d_qcols) SG_TRY(dmalloc(&s->d_qcols, s->max_bases));
+    SG_CUDA(cudaMemcpyAsync(s->d_qcols, qcols, total * 4, cudaMemcpyHostToDevice, s->stream));
+    SG_CUDA(cudaStreamSynchronize(s->stream));
+    s->have_qcols = true;
     return SG_OK;
 }
 
@@ -493,12 +508,30 @@ static int family_range(Session* s, const sg_fam_params* fp, uint32_t q0, uint32
         while (p2 < w * ix->n_tiles) p2 <<= 1;
         return p2 <= FIND_MAX_SORT;
     };
+    // remove_similar (famfinder.cpp:553-556): cseq_comparator(optimistic, none, query cover, no filter) of the query at its
+    // own input positions against the candidate; identities are <= 1, so the test only bites below 1
+    const bool similar = fp->fs_msc_max < 1.0f;
+    if (similar && !s->have_qcols) SG_FAIL(SG_ERR_ARG, "--fs-msc-max < 1 compares positions: give the queries' columns (sg_session_set_query_columns / sg_family_batch_aligned)");
+    auto ident_buffer = [&](uint64_t need) -> int {
+        if (need <= s->fpair_cap) return SG_OK;
+        if (s->d_fpair) { cudaFree(s->d_fpair); s->d_fpair = nullptr; s->fpair_cap = 0; }
+        SG_TRY(dmalloc(&s->d_fpair, need));
+        s->fpair_cap = need;
+        return SG_OK;
+    };
     auto pass = [&](uint32_t w, uint32_t a, uint32_t cnt, uint32_t* retry) -> int {
         SG_TRY(stage_begin(s, 0));
         SG_TRY(launch_find(s, w, a, cnt));
         SG_TRY(stage_end(s, &s->stats.ms_find));
         SG_TRY(stage_begin(s, 1));
-        SG_TRY(launch_family(s, *fp, s->find_max, a, cnt));
+        const float* ident = nullptr;
+        if (similar) {
+            SG_TRY(ident_buffer((uint64_t)cnt * s->find_max));
+            SG_TRY(launch_identity(s, s->d_qmasks, s->d_qcols, s->d_qoff + a, cnt, s->d_ranked + (uint64_t)a * s->find_max, s->d_nres + a,
+                                   s->find_max, nullptr, nullptr, 0, 1, 0, 0, s->d_fpair));
+            ident = s->d_fpair;
+        }
+        SG_TRY(launch_family(s, *fp, s->find_max, a, cnt, nullptr, ident));
         SG_TRY(stage_end(s, &s->stats.ms_family));
         SG_CUDA(cudaMemcpyAsync(retry, s->d_retry, 4, cudaMemcpyDeviceToHost, s->stream));
         SG_CUDA(cudaStreamSynchronize(s->stream));
@@ -554,7 +587,14 @@ static int family_range(Session* s, const sg_fam_params* fp, uint32_t q0, uint32
             SG_TRY(launch_find_full(s, a, cnt));
             SG_TRY(stage_end(s, &s->stats.ms_find));
             SG_TRY(stage_begin(s, 1));
-            SG_TRY(launch_family(s, *fp, ix->N, a, cnt, s->d_full_keys));
+            const float* ident = nullptr;
+            if (similar) {
+                SG_TRY(ident_buffer((uint64_t)cnt * ix->N));
+                SG_TRY(launch_identity(s, s->d_qmasks, s->d_qcols, s->d_qoff + a, cnt, s->d_full_keys, s->d_nres + a, ix->N, nullptr, nullptr,
+                                       0, 1, 0, 0, s->d_fpair));
+                ident = s->d_fpair;
+            }
+            SG_TRY(launch_family(s, *fp, ix->N, a, cnt, s->d_full_keys, ident));
             SG_TRY(stage_end(s, &s->stats.ms_family));
         }
     }
@@ -949,6 +989,12 @@ int sg_turn_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uin
 int sg_family_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, uint32_t nq,
                     const int64_t* exclude_ids, const sg_fam_params* fp, uint32_t fam_stride, uint32_t* fam_ids,
                     float* fam_scores, int32_t* fam_n) {
+    return sg_family_batch_aligned(ix, qmasks, nullptr, qoff, nq, exclude_ids, fp, fam_stride, fam_ids, fam_scores, fam_n);
+}
+
+int sg_family_batch_aligned(sg_index* ix, const uint8_t* qmasks, const uint32_t* qcols, const uint64_t* qoff, uint32_t nq,
+                            const int64_t* exclude_ids, const sg_fam_params* fp, uint32_t fam_stride, uint32_t* fam_ids,
+                            float* fam_scores, int32_t* fam_n) {
     if (!ix || !qmasks || !qoff || nq == 0) SG_FAIL(SG_ERR_ARG, "sg_family_batch: bad argument");
     SessionLease L(ix, qoff, nq);
     if (L.rc) return L.rc;
@@ -956,6 +1002,7 @@ int sg_family_batch(sg_index* ix, const uint8_t* qmasks, const uint64_t* qoff, u
     for (uint32_t a = 0; a < nq; a += L.step()) {
         const uint32_t n = std::min(L.step(), nq - a);
         SG_TRY(sg_session_upload(s, qmasks, qoff + a, n, exclude_ids ? exclude_ids + a : nullptr));
+        if (qcols) SG_TRY(sg_session_set_query_columns(s, qcols + qoff[a]));
         SG_TRY(sg_session_family(s, fp));
         SG_TRY(sg_session_download_family(s, fam_stride, fam_ids ? fam_ids + (uint64_t)a * fam_stride : nullptr,
                                           fam_scores ? fam_scores + (uint64_t)a * fam_stride : nullptr,

@@ -228,6 +228,11 @@ struct Session {
     float* d_fam_scores = nullptr;   // [nq][fam_cap]
     int32_t* d_fam_n = nullptr;      // [nq] (-1: too few, -2: window too small)
     uint32_t* d_retry = nullptr;     // [0] queries needing a larger candidate window
+    // --fs-msc-max < 1: identity of the query (at its own input positions) with every candidate of the ranked window
+    uint32_t* d_qcols = nullptr;     // [max_bases] positions of the query bases (sg_session_set_query_columns)
+    bool have_qcols = false;
+    float* d_fpair = nullptr;        // [queries of the pass][window]
+    uint64_t fpair_cap = 0;
     // --search stage (lazily allocated)
     uint32_t* d_acols = nullptr;     // [max_bases] alignment columns of the aligned queries
     float* d_pair = nullptr;         // [max_q][pair_cap] identity of (query, candidate)
@@ -281,7 +286,8 @@ int launch_index_build(Index* ix, cudaStream_t st);
 // q0 / n: query range of the batch (n == 0: all of it)
 int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
 // ranked: rank-ordered keys of the range (stride `window`); null = the session's d_ranked
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr);
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr,
+                  const float* ident = nullptr);
 int launch_identity(Session* s, const uint8_t* d_amasks, const uint32_t* d_acols, const uint64_t* d_aoff, uint32_t nq,
                     const uint64_t* ranked, const uint32_t* nres, uint32_t stride, const uint32_t* pair_ids,
                     const uint64_t* pair_off, int iupac, int cover, int filter_lc, int ignore_super, float* d_scores);

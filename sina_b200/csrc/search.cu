@@ -485,7 +485,7 @@ __global__ void family_kernel(const uint64_t* __restrict__ ranked, const uint32_
                               uint32_t window, uint32_t N, const uint64_t* __restrict__ row_off,
                               const uint32_t* __restrict__ cols, const int64_t* __restrict__ excl, sg_fam_params p,
                               uint32_t fam_cap, uint32_t* __restrict__ fam_ids, float* __restrict__ fam_scores,
-                              int32_t* __restrict__ fam_n, uint32_t* __restrict__ retry) {
+                              int32_t* __restrict__ fam_n, uint32_t* __restrict__ retry, const float* __restrict__ ident) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const uint64_t* r = ranked + (uint64_t)q * window;
@@ -501,6 +501,7 @@ __global__ void family_kernel(const uint64_t* __restrict__ ranked, const uint32_
         const bool is_full = len >= p.fs_full_len;
         bool rm = len < p.fs_min_len;                                             // remove_short :537-539
         rm = rm || (p.leave_query_out && ex == (int64_t)id);                     // remove_query :542-544
+        rm = rm || (ident && ident[(uint64_t)q * window + i] > p.fs_msc_max);     // remove_similar :553-556 (identity_kernel)
         rm = rm || (have >= p.fs_min && (have >= p.fs_max || !(score < p.fs_msc)) &&   // quota :558-586
                     !(p.fs_req_full && have_full < p.fs_req_full && is_full));
         if (rm) continue;
@@ -528,14 +529,14 @@ __global__ void family_kernel(const uint64_t* __restrict__ ranked, const uint32_
     fam_n[q] = n < p.fs_req ? -1 : (int32_t)n;  // :486-491
 }
 
-int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0, uint32_t n, const uint64_t* ranked) {
+int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0, uint32_t n, const uint64_t* ranked, const float* ident) {
     Index* ix = s->ix;
     if (n == 0) { q0 = 0; n = s->nq; }
     SG_CUDA(cudaMemsetAsync(s->d_retry, 0, sizeof(uint32_t), s->stream));
     family_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(ranked ? ranked : s->d_ranked + (uint64_t)q0 * window, s->d_nres + q0, n, window, ix->N,
                                                          ix->d_row_off, ix->d_cols, s->d_excl + q0, fp, s->fam_cap,
                                                          s->d_fam_ids + (uint64_t)q0 * s->fam_cap,
-                                                         s->d_fam_scores + (uint64_t)q0 * s->fam_cap, s->d_fam_n + q0, s->d_retry);
+                                                         s->d_fam_scores + (uint64_t)q0 * s->fam_cap, s->d_fam_n + q0, s->d_retry, ident);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 1;
     return SG_OK;

@@ -1,5 +1,7 @@
 #include "famfinder.h"
 
+#include <algorithm>
+
 #include <cstdio>
 
 #include "../../include/sina_b200.h"
@@ -61,8 +63,6 @@ void famfinder::get_options_description(po::options_description& main, po::optio
 void famfinder::validate_vm(po::variables_map& vm, po::options_description& /*desc*/) {
     if (vm.count("db") == 0) throw std::logic_error("Family Finder: Must have reference database (--db/-r)");  // famfinder.cpp:218-220
     if (opts.fs_kmer_len < 1 || opts.fs_kmer_len > 16) throw std::logic_error("Family Finder: K must be in 1..16");
-    if (opts.fs_msc_max < 1.0f)
-        throw std::logic_error("--fs-msc-max below 1 needs the identity filter (cseq_comparator), which sina_b200 does not implement");
     if (opts.fs_max == 0) throw std::logic_error("Family Finder: --fs-max must be > 0");
 }
 
@@ -143,13 +143,20 @@ void famfinder::impl::run(std::vector<tray*>& trays) {
         excl.reserve(qs.size());
         for (const cseq* q : qs) excl.push_back(db.indexOf(q->getName()));
     }
-    const uint32_t stride = fp.fs_max + fp.fs_req_full + 1;
+    // remove_similar (src/famfinder.cpp:553-556) compares the query at the positions it came with: only a pre-aligned
+    // input makes that meaningful, and only a threshold below 1 can remove anything
+    std::vector<uint32_t> qcols;
+    if (opts.fs_msc_max < 1.0f) {
+        qcols.reserve(masks.size());
+        for (const cseq* q : qs) for (const aligned_base& b : q->getAlignedBases()) qcols.push_back(b.getPosition());
+    }
+    const uint32_t stride = std::max(fp.fs_min, fp.fs_max) + fp.fs_req_full + 1;
     const uint32_t nq = (uint32_t)qs.size();
     std::vector<uint32_t> ids((size_t)nq * stride);
     std::vector<float> scores((size_t)nq * stride);
     std::vector<int32_t> fam_n(nq);
-    check_sg(sg_family_batch(index->handle(), masks.data(), off.data(), nq, excl.empty() ? nullptr : excl.data(), &fp, stride,
-                             ids.data(), scores.data(), fam_n.data()),
+    check_sg(sg_family_batch_aligned(index->handle(), masks.data(), qcols.empty() ? nullptr : qcols.data(), off.data(), nq,
+                                     excl.empty() ? nullptr : excl.data(), &fp, stride, ids.data(), scores.data(), fam_n.data()),
              "family selection");
     for (uint32_t q = 0; q < nq; q++) {
         tray& t = *live[q];

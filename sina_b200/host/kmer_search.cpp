@@ -1,5 +1,7 @@
 #include "kmer_search.h"
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -56,6 +58,14 @@ kmer_search* kmer_search::get_kmer_search(const std::string& database, int k, bo
         check_sg(sg_index_create(p->rdb->masks().data(), p->rdb->cols().data(), p->rdb->offsets().data(),
                                  p->rdb->getSeqCount(), p->rdb->getAlignmentWidth(), k, nofast ? 1 : 0, device, &p->ix),
                  "building the k-mer index");
+        {   // order of the names: search::result_item breaks score ties by name (src/search.h:56-68)
+            const std::vector<std::string> names = p->rdb->getSequenceNames();
+            std::vector<uint32_t> order(names.size()), rank(names.size());
+            for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] != names[b] ? names[a] < names[b] : a < b; });
+            for (uint32_t i = 0; i < order.size(); i++) rank[order[i]] = i;
+            check_sg(sg_index_set_name_ranks(p->ix, rank.data(), (uint32_t)rank.size()), "setting the name order");
+        }
         // index cache next to the database, as kmer_search::impl::impl keeps one (src/kmer_search.cpp:213-242): written when
         // there is none for this (k, fast) yet. The GPU rebuilds the index faster than the file is read, so the cache is never
         // loaded for its lists: it records the index order (reference_db::getDB) and serves SINA itself.

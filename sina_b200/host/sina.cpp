@@ -18,6 +18,7 @@
 #include "../../include/sina_b200.h"
 #include "align.h"
 #include "famfinder.h"
+#include "search_filter.h"
 #include "kmer_search.h"
 #include "rw_fasta.h"
 
@@ -28,7 +29,7 @@ namespace {
 struct cli_options {
     std::string in = "-", out = "-";
     unsigned int threads = 0, batch = 4096, gpus = 0, max_trays = 0;
-    bool inorder = false, noalign = false, skip_align = false, show_log = false;
+    bool inorder = false, noalign = false, skip_align = false, show_log = false, do_search = false;
 };
 cli_options opts;
 
@@ -80,7 +81,7 @@ int real_main(int argc, const char* const* argv) {
     main_od.value<std::string>("in,i", &opts.in, "-", "input file (fasta)");
     main_od.value<std::string>("out,o", &opts.out, "-", "output file (fasta)");
     main_od.unsupported("add-relatives", true, "writing relatives next to the query");
-    main_od.unsupported("search,S", false, "the search/classification stage is outside the accelerated path");
+    main_od.flag("search,S", &opts.do_search, "enable search stage");
     main_od.flag("prealigned,P", &opts.skip_align, "skip alignment stage");
     main_od.value<unsigned int>("threads,p", &opts.threads, 0u, "accepted for compatibility (the GPU path batches instead)");
     main_od.unsupported("num-pts", true, "PT servers");
@@ -97,6 +98,7 @@ int real_main(int argc, const char* const* argv) {
     rw_fasta::get_options_description(main_od, adv);
     famfinder::get_options_description(main_od, adv);
     aligner::get_options_description(main_od, adv);
+    search_filter::get_options_description(main_od, adv);
     po::options_description all("");
     all.add(main_od).add(adv);
     po::variables_map vm;
@@ -112,11 +114,12 @@ int real_main(int argc, const char* const* argv) {
         famfinder::validate_vm(vm, all);
         aligner::validate_vm(vm, all);
     }
+    if (opts.do_search) search_filter::validate_vm(vm, all);
     rw_fasta::validate_vm(vm, all);
     if (opts.batch == 0) throw std::logic_error("--batch-size must be > 0");
 
     unsigned int ngpu = 0;
-    if (do_align) {
+    if (do_align || opts.do_search) {
         const int have = sg_device_count();
         if (have < 1) throw std::runtime_error("no CUDA device: sina_b200 has no CPU path");
         ngpu = opts.gpus == 0 ? (unsigned)have : std::min<unsigned>(opts.gpus, (unsigned)have);
@@ -128,9 +131,13 @@ int real_main(int argc, const char* const* argv) {
     // stage instances, one pair per GPU (each builds / shares the device's replica of the index)
     std::vector<std::unique_ptr<famfinder>> ff;
     std::vector<std::unique_ptr<aligner>> al;
+    std::vector<std::unique_ptr<search_filter>> sf;
     for (unsigned int d = 0; d < ngpu; d++) {
-        ff.emplace_back(new famfinder((int)d));
-        al.emplace_back(new aligner((int)d));
+        if (do_align) {
+            ff.emplace_back(new famfinder((int)d));
+            al.emplace_back(new aligner((int)d));
+        }
+        if (opts.do_search) sf.emplace_back(new search_filter((int)d));   // src/sina.cpp:519-527
     }
     std::cerr << "Aligner ready. Processing sequences" << std::endl;  // src/sina.cpp:581
     const auto before = std::chrono::steady_clock::now();
@@ -202,6 +209,11 @@ int real_main(int argc, const char* const* argv) {
                     al[d]->run(b.trays);
                     us_align += usec(t0);
                 }
+                if (opts.do_search && !failed) {
+                    if (!do_align)   // --prealigned: the input alignment is what gets searched (src/sina.cpp:505-509)
+                        for (tray& t : b.trays) if (t.input_sequence && !t.aligned_sequence) t.aligned_sequence = new cseq(*t.input_sequence);
+                    sf[d]->run(b.trays);
+                }
             } catch (std::exception& e) {
                 std::lock_guard<std::mutex> l(done_mu);
                 if (!failed) failure = e.what();
@@ -220,7 +232,7 @@ int real_main(int argc, const char* const* argv) {
                 if (!failed) {
                     for (size_t i = 0; i < b.trays.size(); i++) {
                         tray& t = b.trays[i];
-                        if (!do_align && t.input_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
+                        if (!do_align && t.input_sequence && !t.aligned_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
                         if (t.input_sequence == nullptr) throw std::runtime_error("Received broken tray in rw_fasta writer");
                         if (t.aligned_sequence) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
                     }
@@ -260,7 +272,7 @@ int real_main(int argc, const char* const* argv) {
     for (unsigned int r = 0; r < 4; r++) writers.emplace_back(write_pool);
     // several host threads per GPU: the library serialises the device calls of one index, so while one thread's batch
     // is on the GPU the others pack queries / build the result sequences of theirs
-    unsigned int wpg = do_align ? (ngpu <= 2 ? 6u : 3u) : 1u;   // B200 box, 1 GPU, 160k queries: 3 threads 44.8k seq/s, 6 threads 49.1k
+    unsigned int wpg = (do_align || opts.do_search) ? (ngpu <= 2 ? 6u : 3u) : 1u;   // B200 box, 1 GPU, 160k queries: 3 threads 44.8k seq/s, 6 threads 49.1k
     if (do_align && getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
     for (unsigned int d = 0; d < std::max(1u, ngpu); d++)
         for (unsigned int k = 0; k < wpg; k++) workers.emplace_back(work, d);

@@ -278,3 +278,46 @@ def test_cli_sidx_cache_and_index_order(orc, data, tmp_path):
         if w is not None:
             assert got["q%d" % i] == w, i
     assert first.keys() == got.keys()
+
+
+def test_cli_search_stage(data, tmp_path):
+    """--search: search_filter after the aligner (src/sina.cpp:519-527, src/search_filter.cpp:244-330); `nearest_slv` lists
+    the max_result nearest references by identity (name~score, score with three decimals as in the reference)"""
+    if not O.have_ref():
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    d, msa, qmasks = data
+    out = tmp_path / "out.fasta"
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
+                        "--search", "--search-kmer-len", "6", "--search-max-result", "5", "--search-min-sim", "0.5",
+                        "--search-kmer-candidates", "50", "--meta-fmt", "comment"] + FAM_ARGS,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    # the aligned sequences and their nearest_slv comment lines
+    recs, name = {}, None
+    for line in open(out):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            recs[name] = {"seq": "", "nearest": None}
+        elif line.startswith(";"):
+            k, _, v = line[1:].strip().partition("=")
+            if k == "nearest_slv":
+                recs[name]["nearest"] = v
+        elif name:
+            recs[name]["seq"] += line
+    ref = O.Ref()
+    names = ["ref%d" % i for i in range(msa.N)]
+    rdb = ref.db(O.MSA(msa.masks, msa.cols, msa.off, msa.W, names=names))
+    rix = ref.kidx_build(rdb, 6, 0)
+    checked = 0
+    for qn, rec in recs.items():
+        a = O._CHAR2MASK[np.frombuffer(rec["seq"].encode(), np.uint8)]
+        cols = np.nonzero(a > 0)[0].astype(np.uint32)
+        masks = a[cols].astype(np.uint8)
+        ids, sc = ref.search(rix, masks, cols, 50, 5, 0.5)
+        want = "".join("%s~%.3f " % (names[i], s) for i, s in zip(ids, sc))
+        assert (rec["nearest"] or "") == want.strip() or (rec["nearest"] or "") == want, (qn, rec["nearest"], want)
+        checked += len(ids) > 0
+    assert checked >= 30
+    ref.kidx_free(rix)
+    ref.db_free(rdb)

@@ -53,8 +53,10 @@ def test_cli_help_and_version():
     (["--db", "x", "--filter", "f"], "not supported"),
     (["--db", "x", "--insertion", "sideways"], "insertion type must be one of"),
     (["--db", "x", "--turn", "sideways"], "Turn type must be one of"),
-    (["--db", "x", "--search"], "not supported"),
-    (["--db", "x", "--fs-msc-max", "0.9"], "identity filter"),
+    (["--db", "x", "--search", "--search-all"], "not supported"),
+    (["--db", "x", "--search", "--lca-fields", "tax_slv"], "not supported"),
+    (["--db", "x", "--search", "--search-cover", "abs", "--search-correction", "jc"], "only fractional identity"),
+    (["--db", "x", "--search", "--search-iupac", "sometimes"], "iupac matching must be"),
     (["--db", "x", "--bogus"], "unrecognised option"),
     (["-i", "q"], "Must have reference database"),
 ])

@@ -179,3 +179,43 @@ def test_search_jukes_cantor_unrelated_rows(ref):
     ref.kidx_free(rix)
     ref.db_free(db)
     ix.close()
+
+
+@pytest.mark.gpu
+def test_family_identity_filter_vs_reference(ref):
+    """--fs-msc-max < 1 (remove_similar, src/famfinder.cpp:553-556): pre-aligned queries, candidates more identical than the
+    threshold are skipped. Queries: references themselves with a few columns changed, and aligned outputs."""
+    rng = np.random.default_rng(17)
+    tree, msa = small_db(rng, N=400)
+    names = msa.names
+    ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=8)
+    qm, qc, qo, strings = [], [], [0], []
+    for r in rng.choice(msa.N, 30, replace=False):
+        m_, c_ = msa.row(int(r))
+        m_ = m_.copy()
+        flip = rng.choice(len(m_), size=len(m_) // 15, replace=False)
+        m_[flip] = rng.choice(np.array([1, 2, 4, 8], np.uint8), size=len(flip))
+        keep = np.sort(rng.choice(len(m_), size=len(m_) - 10, replace=False))
+        qm.append(m_[keep]); qc.append(c_[keep]); qo.append(qo[-1] + len(keep))
+        s = np.full(msa.W, ord("-"), np.uint8)
+        s[c_[keep]] = O.MASK2RNA[m_[keep] & 31]
+        strings.append(s.tobytes().decode())
+    qm, qc, qo = np.concatenate(qm), np.concatenate(qc), np.array(qo, np.uint64)
+    db = ref.db(msa)
+    rix = ref.kidx_build(db, 8)
+    differs = 0
+    for thr in (0.97, 0.9, 0.8):
+        kw = dict(fs_min=8, fs_max=8, fs_min_len=50, fs_full_len=250, fs_req_gaps=0, fs_msc_max=thr)
+        ids, sc, n = ix.family(qm, qo, sina_b200.FamParams(**kw), qcols=qc)
+        ids0, _, n0 = ix.family(qm, qo, sina_b200.FamParams(**dict(kw, fs_msc_max=2.0)))
+        for q in range(len(qo) - 1):
+            rn, rid, rsc = ref.family(rix, strings[q], O.FamParams(**kw))
+            assert n[q] == rn, (thr, q, n[q], rn)
+            assert (ids[q, :rn] == rid).all() and (sc[q, :rn] == rsc).all(), (thr, q)
+            differs += n0[q] != n[q] or (ids0[q, :n0[q]] != ids[q, :n[q]]).any()
+    assert differs > 20     # the filter does remove candidates
+    with pytest.raises(sina_b200.SinaB200Error):
+        ix.family(qm, qo, sina_b200.FamParams(fs_msc_max=0.9))    # positions are required
+    ref.kidx_free(rix)
+    ref.db_free(db)
+    ix.close()
