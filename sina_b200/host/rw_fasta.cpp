@@ -145,22 +145,19 @@ rw_fasta::writer::~writer() = default;
 unsigned int rw_fasta::writer::written() const { return data->count; }
 unsigned int rw_fasta::writer::excluded() const { return data->excluded; }
 
-std::string rw_fasta::writer::format(const cseq& c) {  // src/rw_fasta.cpp:438-528
-    if (!opts) opts = new options();
-    std::string o;
-    const std::string seq = c.getAligned(!opts->out_dots, opts->out_dna);
-    o.reserve(seq.size() + seq.size() / (opts->line_length ? opts->line_length : seq.size() + 1) + 256);
+// header line (+ comment lines) of a record, src/rw_fasta.cpp:438-500
+static void append_header(const cseq& c, std::string& o) {
     o += ">";
     o += c.getName();
     const std::string fname = c.get_attr_string(fn_fullname);
     if (!fname.empty()) { o += " "; o += fname; }
-    if (opts->fastameta == FASTA_META_HEADER) {
+    if (rw_fasta::opts->fastameta == FASTA_META_HEADER) {
         for (const auto& ap : c.get_attrs()) {
             if (ap.first == fn_family || ap.first == fn_fullname || ap.second.empty()) continue;
             o += " ["; o += ap.first; o += "="; o += ap.second; o += "]";
         }
         o += "\n";
-    } else if (opts->fastameta == FASTA_META_COMMENT) {
+    } else if (rw_fasta::opts->fastameta == FASTA_META_COMMENT) {
         o += "\n";
         for (const auto& ap : c.get_attrs()) {
             if (ap.first == fn_family || ap.first == fn_fullname) continue;
@@ -169,12 +166,61 @@ std::string rw_fasta::writer::format(const cseq& c) {  // src/rw_fasta.cpp:438-5
     } else {
         o += "\n";
     }
-    if (opts->line_length > 0) {
-        for (size_t i = 0; i < seq.size(); i += opts->line_length) { o.append(seq, i, opts->line_length); o += "\n"; }
-    } else {
-        o += seq;
-        o += "\n";
+}
+
+// length of cseq::getAligned(): the alignment width, or one past the last base where the gap placement pushed bases
+// beyond it (src/cseq.cpp:135-174)
+static size_t aligned_length(const cseq& c) {
+    const auto& b = c.getAlignedBases();
+    size_t n = c.getWidth();
+    if (!b.empty()) n = std::max<size_t>(n, (size_t)b.back().getPosition() + 1);
+    return n;
+}
+
+size_t rw_fasta::writer::record_size(const cseq& c) {
+    if (!opts) opts = new options();
+    std::string h;
+    append_header(c, h);
+    const size_t n = aligned_length(c);
+    return h.size() + n + (opts->line_length > 0 ? (n + opts->line_length - 1) / opts->line_length : 1);
+}
+
+void rw_fasta::writer::format_into(const cseq& c, std::string& o) {  // src/rw_fasta.cpp:438-528
+    if (!opts) opts = new options();
+    o.clear();
+    append_header(c, o);
+    const auto& bases = c.getAlignedBases();
+    bool sorted = true;
+    for (size_t i = 1; i < bases.size() && sorted; i++) sorted = bases[i].getPosition() > bases[i - 1].getPosition();
+    if (opts->line_length > 0 || !sorted) {   // wrapped lines (or an unplaced sequence): render, then cut
+        const std::string seq = c.getAligned(!opts->out_dots, opts->out_dna);
+        if (opts->line_length > 0) {
+            for (size_t i = 0; i < seq.size(); i += opts->line_length) { o.append(seq, i, opts->line_length); o += "\n"; }
+        } else {
+            o += seq;
+            o += "\n";
+        }
+        return;
     }
+    // one line: fill with gap characters and drop the bases in place (what getAligned produces, without the second copy)
+    const size_t h = o.size(), n = aligned_length(c);
+    o.resize(h + n + 1);
+    char* p = &o[h];
+    memset(p, '-', n);
+    if (opts->out_dots) {   // dots before the first and after the last base (cseq::getAligned(nodots = false))
+        const size_t first = bases.empty() ? n : bases.front().getPosition();
+        memset(p, '.', first);
+        const size_t last = bases.empty() ? 0 : (size_t)bases.back().getPosition() + 1;
+        if (!bases.empty() && last < n) memset(p + last, '.', n - last);
+    }
+    if (opts->out_dna) for (const auto& b : bases) p[b.getPosition()] = base_iupac::iupac_dna(b.getBase());
+    else for (const auto& b : bases) p[b.getPosition()] = base_iupac::iupac_rna(b.getBase());
+    p[n] = '\n';
+}
+
+std::string rw_fasta::writer::format(const cseq& c) {
+    std::string o;
+    format_into(c, o);
     return o;
 }
 

@@ -42,6 +42,9 @@ public:
         // the record operator() would write for this sequence (header + sequence lines), so that the rendering of the
         // alignment_width-long lines can run on several threads; write_formatted() then emits it (null: sequence excluded)
         static std::string format(const cseq& c);
+        // the same into a caller-owned buffer (reused from record to record), and the size it will have
+        static void format_into(const cseq& c, std::string& record);
+        static size_t record_size(const cseq& c);
         void write_formatted(const std::string* record);
         // positional output (regular files): the caller reserves byte ranges in record order and any thread fills them
         // with pwrite, so that writing 50 kB records is not bound to one thread. Not available on stdout.

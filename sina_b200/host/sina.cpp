@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -39,6 +40,15 @@ struct batch_t {
     std::vector<std::string> records;   // FASTA record of every tray, rendered off the writer thread
     std::vector<char> has_record;
     uint64_t file_offset = 0;           // where the batch's records start in the output file (positional writer)
+};
+
+// A run of consecutive trays of one batch whose records go to consecutive bytes of the output file: rendered and
+// written by one thread of the output pool, record by record through a buffer that stays in that core's cache.
+struct slice_t {
+    std::shared_ptr<batch_t> batch;
+    std::shared_ptr<std::atomic<int>> left;   // slices of the batch still to be written
+    size_t begin = 0, end = 0;
+    uint64_t file_offset = 0;
 };
 
 template <typename T>
@@ -127,6 +137,7 @@ int real_main(int argc, const char* const* argv) {
 
     rw_fasta::reader reader(opts.in);
     rw_fasta::writer writer(opts.out);
+    const bool direct = writer.positional();   // a regular file: records are written at reserved offsets by a pool
 
     // stage instances, one pair per GPU (each builds / shares the device's replica of the index)
     std::vector<std::unique_ptr<famfinder>> ff;
@@ -143,7 +154,7 @@ int real_main(int argc, const char* const* argv) {
     const auto before = std::chrono::steady_clock::now();
 
     const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 6 * std::max(1u, ngpu);
-    bounded_queue<batch_t> todo(inflight), torender(inflight), towrite(inflight);
+    bounded_queue<batch_t> todo(inflight), torender(inflight);
     // Batches alive between the reader and the last byte written (the reference's limiter node, src/sina.cpp:485-489):
     // a rendered batch holds its FASTA records (4096 x 50 kB at 50 000 columns), so nothing but this bound keeps a slow
     // output device from growing the `done` map until memory runs out. The reader takes a slot per batch, the slot comes
@@ -219,7 +230,13 @@ int real_main(int argc, const char* const* argv) {
                 if (!failed) failure = e.what();
                 failed = true;
             }
-            torender.push(std::move(b));
+            if (direct) {   // positional output: records are rendered by the output pool, straight into the write
+                std::lock_guard<std::mutex> l(done_mu);
+                done.emplace(b.no, std::move(b));
+                done_cv.notify_all();
+            } else {
+                torender.push(std::move(b));
+            }
         }
     };
     auto render = [&] {
@@ -249,15 +266,22 @@ int real_main(int argc, const char* const* argv) {
         }
     };
     std::atomic<uint64_t> us_pwrite(0);
+    bounded_queue<slice_t> towrite(16 * inflight);
     auto write_pool = [&] {
-        batch_t b;
-        while (towrite.pop(b)) {
+        slice_t sl;
+        std::string rec;
+        while (towrite.pop(sl)) {
             const auto t0 = std::chrono::steady_clock::now();
             try {
-                uint64_t at = b.file_offset;
-                for (size_t i = 0; i < b.trays.size(); i++) {
-                    if (b.has_record[i] && !failed) { writer.write_at(at, b.records[i].data(), b.records[i].size()); at += b.records[i].size(); }
-                    b.trays[i].destroy();  // src/sina.cpp:573-579
+                uint64_t at = sl.file_offset;
+                for (size_t i = sl.begin; i < sl.end; i++) {
+                    tray& t = sl.batch->trays[i];
+                    if (sl.batch->has_record[i] && !failed) {
+                        rw_fasta::writer::format_into(*t.aligned_sequence, rec);
+                        writer.write_at(at, rec.data(), rec.size());
+                        at += rec.size();
+                    }
+                    t.destroy();  // src/sina.cpp:573-579
                 }
             } catch (std::exception& e) {
                 std::lock_guard<std::mutex> l(done_mu);
@@ -265,18 +289,29 @@ int real_main(int argc, const char* const* argv) {
                 failed = true;
             }
             us_pwrite += usec(t0);
-            alive_release();
+            if (sl.left->fetch_sub(1) == 1) alive_release();
         }
     };
     std::vector<std::thread> workers, renderers, writers;
-    for (unsigned int r = 0; r < 4; r++) writers.emplace_back(write_pool);
+    const unsigned int hw = std::max(1u, std::thread::hardware_concurrency());
+    // render + pwrite, one record at a time. A tmpfs / page-cache file takes about 2.5 GB/s (50 k records of 50 kB per
+    // second) however many threads write to it (B200 box: 4 threads 2.2 GB/s, 8 threads 2.5 GB/s, 12 threads and twice the
+    // workers 1.6 GB/s), so the pool stays small and the rest of the cores go to the per-GPU workers
+    unsigned int n_write = direct ? std::max(4u, std::min(8u, hw / 3)) : 0u;
+    if (direct && getenv("SINA_B200_WRITERS")) n_write = std::max(1, atoi(getenv("SINA_B200_WRITERS")));
+    for (unsigned int r = 0; r < n_write; r++) writers.emplace_back(write_pool);
     // several host threads per GPU: the library serialises the device calls of one index, so while one thread's batch
-    // is on the GPU the others pack queries / build the result sequences of theirs
-    unsigned int wpg = (do_align || opts.do_search) ? (ngpu <= 2 ? 6u : 3u) : 1u;   // B200 box, 1 GPU, 160k queries: 3 threads 44.8k seq/s, 6 threads 49.1k
-    if (do_align && getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
+    // is on the GPU the others pack queries / build the result sequences of theirs (B200 box, 1 GPU, 160k queries:
+    // 3 threads 44.8k seq/s, 6 threads 49.1k); never more threads than the cores left beside the output pool
+    unsigned int wpg = 1u;
+    if (do_align || opts.do_search) {
+        const unsigned int spare = hw > n_write + 2 ? hw - n_write - 2 : 2;
+        wpg = std::max(2u, std::min(6u, spare / std::max(1u, ngpu)));
+    }
+    if ((do_align || opts.do_search) && getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
     for (unsigned int d = 0; d < std::max(1u, ngpu); d++)
         for (unsigned int k = 0; k < wpg; k++) workers.emplace_back(work, d);
-    const unsigned int n_render = std::max(2u, std::min(16u, std::max(1u, std::thread::hardware_concurrency()) / 2));
+    const unsigned int n_render = direct ? 0u : std::max(2u, std::min(16u, hw / 2));
     for (unsigned int r = 0; r < n_render; r++) renderers.emplace_back(render);
 
     uint64_t count = 0, next = 0;
@@ -291,18 +326,34 @@ int real_main(int argc, const char* const* argv) {
         }
         next++;
         const auto t0w = std::chrono::steady_clock::now();
-        if (writer.positional() && !failed) {
-            // byte ranges are handed out here, in input order; the write pool fills them and frees the trays
+        if (direct) {
+            // byte ranges are handed out here, in input order (the size of a record follows from its header and the
+            // alignment width); the output pool renders and writes them, slice by slice, and frees the trays
+            auto sb = std::make_shared<batch_t>(std::move(b));
+            batch_t& B = *sb;
+            const size_t n = B.trays.size(), per = 256;
+            B.has_record.assign(n, 0);
+            std::vector<uint64_t> size(n, 0);
             uint64_t total = 0;
             unsigned int nrec = 0, nexc = 0;
-            for (size_t i = 0; i < b.trays.size(); i++) {
-                if (b.has_record[i]) { total += b.records[i].size(); nrec++; } else nexc++;
-                if (opts.show_log) std::cerr << "sequence_number: " << b.trays[i].seqno << " sequence_identifier: "
-                                             << b.trays[i].input_sequence->getName() << " " << b.trays[i].log.str() << std::endl;
+            for (size_t i = 0; i < n; i++) {
+                tray& t = B.trays[i];
+                if (!do_align && t.input_sequence && !t.aligned_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
+                if (t.input_sequence == nullptr) { if (!failed) failure = "Received broken tray in rw_fasta writer"; failed = true; }
+                if (t.aligned_sequence && !failed) { size[i] = rw_fasta::writer::record_size(*t.aligned_sequence); B.has_record[i] = 1; total += size[i]; nrec++; } else nexc++;
+                if (opts.show_log && t.input_sequence) std::cerr << "sequence_number: " << t.seqno << " sequence_identifier: "
+                                                                 << t.input_sequence->getName() << " " << t.log.str() << std::endl;
             }
-            count += b.trays.size();
-            b.file_offset = writer.reserve(total, nrec, nexc);
-            towrite.push(std::move(b));
+            count += n;
+            uint64_t at = writer.reserve(total, nrec, nexc);
+            auto left = std::make_shared<std::atomic<int>>((int)((n + per - 1) / per));
+            for (size_t i0 = 0; i0 < n; i0 += per) {
+                slice_t sl;
+                sl.batch = sb; sl.left = left; sl.begin = i0; sl.end = std::min(n, i0 + per); sl.file_offset = at;
+                for (size_t i = sl.begin; i < sl.end; i++) at += size[i];
+                towrite.push(std::move(sl));
+            }
+            if (n == 0) alive_release();
             us_write += usec(t0w);
             continue;
         }
@@ -332,8 +383,8 @@ int real_main(int argc, const char* const* argv) {
              secs > 0 ? count / secs : 0.0);  // src/sina.cpp:588-589
     std::cerr << buf << std::endl;
     if (getenv("SINA_B200_TIMING")) {
-        snprintf(buf, sizeof(buf), "busy seconds: read %.3f | family %.3f + align %.3f over %u worker threads | render %.3f over %u threads | sink %.3f | pwrite %.3f over 4 threads",
-                 us_read / 1e6, us_family / 1e6, us_align / 1e6, wpg * std::max(1u, ngpu), us_render / 1e6, n_render, us_write / 1e6, us_pwrite / 1e6);
+        snprintf(buf, sizeof(buf), "busy seconds: read %.3f | family %.3f + align %.3f over %u worker threads | render %.3f over %u threads | sink %.3f | render+pwrite %.3f over %u threads",
+                 us_read / 1e6, us_family / 1e6, us_align / 1e6, wpg * std::max(1u, ngpu), us_render / 1e6, n_render, us_write / 1e6, us_pwrite / 1e6, n_write);
         std::cerr << buf << std::endl;
     }
     if (writer.excluded()) std::cerr << writer.excluded() << " sequences were not aligned and not written" << std::endl;

@@ -15,6 +15,7 @@ ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--dir", default="/dev/shm/sina_cli")
 ap.add_argument("--batch-size", type=int, default=0)
 ap.add_argument("--keep-inputs", action="store_true")
+ap.add_argument("--out", default="", help="output file (default: out.fasta in --dir); /dev/null measures the pipeline without the file system")
 a = ap.parse_args()
 os.makedirs(a.dir, exist_ok=True)
 W = 50000
@@ -35,11 +36,12 @@ with open(os.path.join(a.dir, "q.fasta"), "wb") as f:
 print("wrote inputs in %.1f s" % (time.time() - t0), flush=True)
 exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sina_b200", "bin", "sina")
 t0 = time.time()
-r = subprocess.run([exe, "-i", os.path.join(a.dir, "q.fasta"), "-o", os.path.join(a.dir, "out.fasta"), "--db",
+outp = a.out or os.path.join(a.dir, "out.fasta")
+r = subprocess.run([exe, "-i", os.path.join(a.dir, "q.fasta"), "-o", outp, "--db",
                     os.path.join(a.dir, "ref.fasta"), "--fs-engine", "internal", "--gpus", str(a.gpus)] + (["--batch-size", str(a.batch_size)] if a.batch_size else []), capture_output=True, text=True, env=dict(os.environ, SINA_B200_TIMING="1"))
 print("rc", r.returncode, "wall %.1f s (includes loading the reference and building the index)" % (time.time() - t0))
 print("\n".join(r.stderr.strip().splitlines()[-5:]))
-print("output bytes", os.path.getsize(os.path.join(a.dir, "out.fasta")) if os.path.exists(os.path.join(a.dir, "out.fasta")) else None)
+print("output", outp, "bytes", os.path.getsize(outp) if os.path.exists(outp) else None)
 for fn in ("ref.fasta", "q.fasta", "out.fasta"):
     try: os.remove(os.path.join(a.dir, fn))
     except OSError: pass
