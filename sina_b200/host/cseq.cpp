@@ -61,6 +61,17 @@ cseq& cseq::append(const char* str) {
     return *this;
 }
 
+cseq& cseq::append(const char* str, size_t n) {
+    bases.reserve(bases.size() + n);
+    for (size_t i = 0; i < n; i++) {
+        const char c = str[i];
+        if (c == ' ' || c == '\t' || c == '\n' || c == '\r') continue;
+        if (c != '-' && c != '.') bases.emplace_back(alignment_width, base_iupac::from_char((unsigned char)c));
+        alignment_width++;
+    }
+    return *this;
+}
+
 cseq& cseq::append(const aligned_base& ab) {
     if (ab.getPosition() >= alignment_width) {
         bases.push_back(ab);

@@ -48,6 +48,7 @@ public:
     void setName(const std::string& n) { name = n; }
     // src/cseq.cpp:63-77: blanks ignored, '-' and '.' advance the column, anything else must be IUPAC
     cseq& append(const char* str);
+    cseq& append(const char* str, size_t n);              // n characters (the FASTA reader hands whole records)
     cseq& append(const std::string& s) { return append(s.c_str()); }
     // src/cseq.cpp:79-95: positions must not decrease; a base placed before the previous one is forced onto it
     cseq& append(const aligned_base& ab);

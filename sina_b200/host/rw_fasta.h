@@ -29,6 +29,12 @@ public:
         explicit reader(const std::string& infile);  // "-" = stdin; throws std::runtime_error if unreadable
         ~reader();
         bool operator()(tray& t);                    // false at end of input; bad sequences are skipped with a message
+        // the two halves of operator(): the text of the next record (one thread), and its parsing (any thread). parse_record
+        // returns false for a record with an illegal character (message printed, t.input_sequence left null)
+        bool next_record(std::string& record, unsigned int& seqno, unsigned int& lineno);
+        static bool parse_record(const std::string& record, unsigned int seqno, unsigned int lineno, const std::string& filename, tray& t);
+        const std::string& filename() const;
+        void count_skipped();
         unsigned int skipped() const;
     private:
         struct priv_data;

@@ -29,7 +29,7 @@ namespace {
 
 struct cli_options {
     std::string in = "-", out = "-";
-    unsigned int threads = 0, batch = 4096, gpus = 0, max_trays = 0;
+    unsigned int threads = 0, batch = 9472, gpus = 0, max_trays = 0;
     bool inorder = false, noalign = false, skip_align = false, show_log = false, do_search = false;
 };
 cli_options opts;
@@ -37,6 +37,8 @@ cli_options opts;
 struct batch_t {
     uint64_t no = 0;
     std::vector<tray> trays;
+    std::vector<std::string> raw;       // text of the input records, parsed into trays by the worker that takes the batch
+    std::vector<unsigned int> raw_seqno, raw_lineno;
     std::vector<std::string> records;   // FASTA record of every tray, rendered off the writer thread
     std::vector<char> has_record;
     uint64_t file_offset = 0;           // where the batch's records start in the output file (positional writer)
@@ -103,7 +105,7 @@ int real_main(int argc, const char* const* argv) {
     adv.unsupported("outtype", true, "only FASTA output");
     adv.unsupported("fields,f", true, "field selection");
     adv.value<unsigned int>("gpus", &opts.gpus, 0u, "[sina_b200] number of GPUs to shard the queries over (0: all visible)");
-    adv.value<unsigned int>("batch-size", &opts.batch, 4096u, "[sina_b200] queries per device batch");
+    adv.value<unsigned int>("batch-size", &opts.batch, 9472u, "[sina_b200] queries per device batch");
     adv.flag("show-log", &opts.show_log, "[sina_b200] print each query's log line to stderr");
     rw_fasta::get_options_description(main_od, adv);
     famfinder::get_options_description(main_od, adv);
@@ -174,7 +176,8 @@ int real_main(int argc, const char* const* argv) {
     bool reading_done = false;
 
     // busy seconds of every pipeline role, printed with SINA_B200_TIMING=1 (where does a file-to-file run spend its time)
-    std::atomic<uint64_t> us_read(0), us_family(0), us_align(0), us_render(0), us_write(0);
+    std::atomic<uint64_t> us_read(0), us_parse(0), us_family(0), us_align(0), us_render(0), us_write(0);
+    std::atomic<unsigned int> n_skipped(0);
     auto usec = [](std::chrono::steady_clock::time_point a) {
         return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - a).count();
     };
@@ -182,13 +185,16 @@ int real_main(int argc, const char* const* argv) {
         try {
             batch_t b;
             for (;;) {
-                tray t;
+                std::string rec;
+                unsigned int seqno = 0, lineno = 0;
                 const auto t0 = std::chrono::steady_clock::now();
-                const bool more = reader(t);
+                const bool more = reader.next_record(rec, seqno, lineno);
                 us_read += usec(t0);
                 if (!more) break;
-                b.trays.push_back(t);
-                if (b.trays.size() == opts.batch) {
+                b.raw.push_back(std::move(rec));
+                b.raw_seqno.push_back(seqno);
+                b.raw_lineno.push_back(lineno);
+                if (b.raw.size() == opts.batch) {
                     b.no = n_batches++;
                     alive_acquire();
                     todo.push(std::move(b));
@@ -196,7 +202,7 @@ int real_main(int argc, const char* const* argv) {
                 }
                 if (failed) break;
             }
-            if (!b.trays.empty()) { b.no = n_batches++; alive_acquire(); todo.push(std::move(b)); }
+            if (!b.raw.empty()) { b.no = n_batches++; alive_acquire(); todo.push(std::move(b)); }
         } catch (std::exception& e) {
             std::lock_guard<std::mutex> l(done_mu);
             failure = e.what();
@@ -212,6 +218,17 @@ int real_main(int argc, const char* const* argv) {
         batch_t b;
         while (todo.pop(b)) {
             try {
+                {   // the records of the batch become trays here, on the worker (rw_fasta::reader::parse_record)
+                    const auto t0 = std::chrono::steady_clock::now();
+                    b.trays.reserve(b.raw.size());
+                    for (size_t i = 0; i < b.raw.size(); i++) {
+                        tray t;
+                        if (rw_fasta::reader::parse_record(b.raw[i], b.raw_seqno[i], b.raw_lineno[i], reader.filename(), t)) b.trays.push_back(t);
+                        else n_skipped++;
+                    }
+                    b.raw.clear(); b.raw.shrink_to_fit();
+                    us_parse += usec(t0);
+                }
                 if (do_align && !failed) {
                     auto t0 = std::chrono::steady_clock::now();
                     ff[d]->run(b.trays);
@@ -383,8 +400,8 @@ int real_main(int argc, const char* const* argv) {
              secs > 0 ? count / secs : 0.0);  // src/sina.cpp:588-589
     std::cerr << buf << std::endl;
     if (getenv("SINA_B200_TIMING")) {
-        snprintf(buf, sizeof(buf), "busy seconds: read %.3f | family %.3f + align %.3f over %u worker threads | render %.3f over %u threads | sink %.3f | render+pwrite %.3f over %u threads",
-                 us_read / 1e6, us_family / 1e6, us_align / 1e6, wpg * std::max(1u, ngpu), us_render / 1e6, n_render, us_write / 1e6, us_pwrite / 1e6, n_write);
+        snprintf(buf, sizeof(buf), "busy seconds: read %.3f | parse %.3f + family %.3f + align %.3f over %u worker threads | render %.3f over %u threads | sink %.3f | render+pwrite %.3f over %u threads",
+                 us_read / 1e6, us_parse / 1e6, us_family / 1e6, us_align / 1e6, wpg * std::max(1u, ngpu), us_render / 1e6, n_render, us_write / 1e6, us_pwrite / 1e6, n_write);
         std::cerr << buf << std::endl;
     }
     if (writer.excluded()) std::cerr << writer.excluded() << " sequences were not aligned and not written" << std::endl;
