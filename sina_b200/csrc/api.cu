@@ -366,7 +366,6 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
     s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 2368)));
     s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
-    s->bankplan = (int)env_mb("SG_BANKPLAN", 0);
     s->graph_generic = (int)env_mb("SG_GRAPH_GENERIC", 0);
     *out = (sg_session*)s;
     SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));

@@ -278,7 +278,6 @@ struct Session {
     bool have_family = false, have_find = false, have_align = false;
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
     int graph_generic = 0;           // SG_GRAPH_GENERIC=1: family graph through the global-scratch path (testing)
-    int bankplan = 0;                // SG_BANKPLAN=1 (+n: n swap sweeps): bank-aware ring columns (bankplan_kernel) instead of identity columns
 };
 
 // ------------------------------------------------------------------ kernel launchers (one per .cu)

@@ -104,6 +104,7 @@ struct GraphArgs {
     uint32_t* lastnodes; GroupInfo* groups;
     uint32_t* nmaxins; int forbid;   // --insertion forbid
     uint32_t* order; rcol_t* rcol; uint16_t* nthr; uint32_t* pdesc2; GhostInfo* ghosts; uint32_t* writers; int force_generic;
+    float pen_max, pen_min;   // larger / smaller of the gap open and gap extension penalties
     unsigned long long* cells; unsigned long long* cursors; uint64_t tb_words, spill_elems;
     float fs_weight;
     uint32_t stab_bytes;   // shared-memory budget of the column table (fast path of steps 2-5)
@@ -805,7 +806,11 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
         }
         __syncthreads();
     }
-    const uint32_t mode = (shv[1] || A.force_generic || wide) ? 1u : 2u;   // v2 holds in-degree <= 8 and u8 cells
+    // The v2 kernel never materialises the reference's initial cell value 1000000 (mesh.cu): it relies on every cell having
+    // a candidate below it, value(m, s) <= 1 + (column rank + s) * max(gap, gapext) by a chain of gap steps. Penalties that
+    // could break that bound (or negative ones) send the query through the generic kernel, which keeps the initial value.
+    const bool bound_ok = A.pen_min >= 0.f && 1.f + (float)(n_cols + Lq) * A.pen_max < 900000.f;
+    const uint32_t mode = (shv[1] || A.force_generic || wide || !bound_ok) ? 1u : 2u;   // v2 holds in-degree <= 8 and u8 cells
     if (tid == 0) {
         uint64_t words_total = 0;
         for (uint32_t g = 0; g < n_groups; g++) {
@@ -837,219 +842,6 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------------
-// Ring-column plan of the v2 DP kernel, one warp per (query, group).
-// A row publishes its cells into one column of the shared-memory ring and every successor row reads them from
-// there with one LDS.128 per step. The 8 lanes of a quarter-warp are served in one wavefront only if their cells
-// fall into 8 different 16-byte bank groups; with columns = thread ids the predecessor columns of a quarter-warp
-// are close to random and a load costs 9 wavefronts instead of 4 (ncu: the LSU data pipe is what bounds the DP
-// kernel). Here every row gets its ring column: the column stays inside the row's 8-thread block (so a warp's
-// stores still cover whole 128-byte lines without conflict) and its bank group is chosen greedily, block by block,
-// as the one that collides least with the cells already placed in the load instructions that will read it; a
-// second pass swaps two rows of a block whenever that lowers the count further.
-// Bank group of (column c, column-rank distance d) = (c - d) mod 8: the ring's slot stride is one cell more than
-// a multiple of eight (DP_RS2) and a reader at distance d looks d slots back (mesh.cu).
-constexpr int BP_WARPS = 4;
-constexpr uint32_t BP_ENT = 768;                 // near in-group edges per group the plan looks at
-constexpr uint32_t BP_INST = (DP_T / 8) * 8;     // load instructions per group: (quarter-warp, predecessor slot < 8)
-constexpr uint16_t BP_DUP = 0xFFFFu;             // entry repeating another one of the same row (same address: a broadcast)
-static_assert(DP_RS2 % 8 == 1, "bank group formula of the plan");
-struct BankPlanArgs {
-    const GraphHdr* hdr; uint32_t q0, gcap, icap;
-    const uint32_t* order; const uint16_t* nthr; const uint32_t* pred_off; const uint32_t* preds; const uint32_t* nsigma;
-    uint32_t* pdesc2; rcol_t* rcol; int sweeps;
-};
-
-__global__ void __launch_bounds__(32 * BP_WARPS) bankplan_kernel(BankPlanArgs A) {
-    __shared__ uint32_t occ_s[BP_WARPS][BP_INST * 8 / 4];   // u8 counters: cells per (instruction, bank group)
-    __shared__ __align__(4) uint16_t off_s[BP_WARPS][DP_T + 2];           // reads of the row at a position: CSR offsets
-    __shared__ __align__(4) uint16_t cur_s[BP_WARPS][DP_T];
-    __shared__ uint16_t ent_s[BP_WARPS][BP_ENT];             // instruction | distance << 8
-    __shared__ uint8_t np_s[BP_WARPS][DP_T];
-    __shared__ uint8_t rho_s[BP_WARPS][DP_T];
-    const uint32_t FULLM = 0xffffffffu;
-    const uint32_t w = warp_id(), lane = lane_id(), ql = blockIdx.x;
-    const GraphHdr h = A.hdr[A.q0 + ql];
-    if (h.status != GS_OK || h.mode != 2) return;
-    const uint32_t T = DP_T;
-    const uint64_t io = (uint64_t)ql * A.icap;
-    const uint32_t* pred_off = A.pred_off + (uint64_t)ql * (A.icap + 1);
-    const uint32_t* preds = A.preds + io;
-    const uint32_t* nsigma = A.nsigma + io;
-    const uint16_t* nthr = A.nthr + io;
-    uint32_t* pdesc2 = A.pdesc2 + io;
-    uint32_t* occ32 = occ_s[w];
-    uint8_t* occ = reinterpret_cast<uint8_t*>(occ32);
-    uint16_t* off = off_s[w];
-    uint16_t* cur = cur_s[w];
-    uint16_t* ent = ent_s[w];
-    uint8_t* npl = np_s[w];
-    uint8_t* rho = rho_s[w];
-    auto occ_add = [&](uint32_t idx, int v) { atomicAdd(&occ32[idx >> 2], (uint32_t)v << (8 * (idx & 3))); };
-    for (uint32_t g = w; g < h.n_groups; g += BP_WARPS) {
-        const uint32_t lo = g * T, n = min(T, h.V - lo);
-        const uint32_t* order = A.order + ((uint64_t)ql * A.gcap + g) * T;
-        rcol_t* rcol = A.rcol + ((uint64_t)ql * A.gcap + g) * T;
-        // in-degree of the row at every position; lane i keeps the specialisation width of DP warp i
-        uint32_t npw_mine = 1;
-        for (uint32_t wi = 0; wi < T / 32; wi++) {
-            const uint32_t pos = wi * 32 + lane;
-            uint32_t np = 0;
-            if (pos < n) { const uint32_t m = order[pos]; np = pred_off[m + 1] - pred_off[m]; }
-            npl[pos] = (uint8_t)min(np, 255u);
-            const uint32_t mx = max(1u, __reduce_max_sync(FULLM, np));
-            if (lane == wi) npw_mine = mx;
-        }
-        for (uint32_t i = lane; i < T + 2; i += 32) off[i] = 0;
-        for (uint32_t i = lane; i < BP_INST * 8 / 4; i += 32) occ32[i] = 0;
-        __syncwarp();
-        // reads of every producer position: pass 0 counts, pass 1 fills. Cells whose columns are fixed go straight
-        // into the occupancy table: ghost columns (far predecessors) and the two constant columns, the latter once per
-        // instruction however many lanes read them (one address).
-        uint32_t total = 0;
-        for (int pass = 0; pass < 2; pass++) {
-            for (uint32_t wi = 0; wi < T / 32; wi++) {
-                const uint32_t pos = wi * 32 + lane;
-                const uint32_t npw = __shfl_sync(FULLM, npw_mine, wi);
-                if (npw > 8) continue;
-                const bool have = pos < n;
-                uint32_t m = 0, po = 0, np = 0, sg_ = 0;
-                if (have) { m = order[pos]; po = pred_off[m]; np = npl[pos]; sg_ = nsigma[m]; }
-                const uint32_t shift = npw - np;
-                for (uint32_t k = 0; k < npw; k++) {
-                    const uint32_t inst = (pos >> 3) * 8 + k;
-                    const bool edge = np == 0;                       // lanes without a row read the edge column too
-                    const bool pad = !edge && k < shift;
-                    if (pass == 1) {
-                        const uint32_t oct = 0xffu << (lane & 24u);
-                        const uint32_t pm = __ballot_sync(FULLM, pad) & oct, em = __ballot_sync(FULLM, edge) & oct;
-                        if (pad && (uint32_t)__ffs((int)pm) - 1u == lane) occ_add(inst * 8 + ((DP_COL_PAD - DP_MAXD) & 7u), 1);
-                        if (edge && (uint32_t)__ffs((int)em) - 1u == lane) occ_add(inst * 8 + ((DP_COL_EDGE - DP_MAXD) & 7u), 1);
-                    }
-                    if (!have || edge || pad) continue;
-                    const uint32_t e = po + k - shift;
-                    const uint32_t p = preds[e], d = sg_ - nsigma[p];
-                    if (p >= lo && d <= (uint32_t)DP_MAXD) {
-                        const uint32_t pp = nthr[p];
-                        if (pass == 0) atomicAdd(reinterpret_cast<uint32_t*>(off) + ((pp + 1) >> 1), (pp + 1) & 1 ? 0x10000u : 1u);
-                        else {
-                            const uint32_t at = atomicAdd(reinterpret_cast<uint32_t*>(cur) + (pp >> 1), pp & 1 ? 0x10000u : 1u);
-                            const uint32_t idx = (pp & 1 ? at >> 16 : at) & 0xffffu;
-                            if (idx < BP_ENT) ent[idx] = (uint16_t)(inst | (d << 8));
-                        }
-                    } else if (pass == 1) {
-                        const uint32_t dd = pdesc2[e];   // (distance << 16) | ghost column
-                        occ_add(inst * 8 + (((dd & 0xffffu) - (dd >> 16)) & 7u), 1);
-                    }
-                }
-            }
-            __syncwarp();
-            if (pass == 0) {   // off[i + 1] holds the count of position i: inclusive scan -> off[i] = first entry of position i
-                uint32_t carry = 0;
-                for (uint32_t i0 = 0; i0 < T; i0 += 32) {
-                    const uint32_t v = off[i0 + lane + 1];
-                    uint32_t x = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLM, x, o); if (lane >= (uint32_t)o) x += y; }
-                    __syncwarp();
-                    off[i0 + lane + 1] = (uint16_t)(carry + x);
-                    cur[i0 + lane] = (uint16_t)(carry + x - v);
-                    carry += __shfl_sync(FULLM, x, 31);
-                }
-                total = carry;
-                __syncwarp();
-            }
-        }
-        if (total > BP_ENT) continue;   // an unusually dense group keeps the identity columns written by graph_kernel
-        // several lanes of a quarter-warp reading one cell (same row, same distance) are one address: keep one entry
-        for (uint32_t pos = lane; pos < n; pos += 32) {
-            const uint32_t a = off[pos], e = off[pos + 1];
-            for (uint32_t j = a + 1; j < e; j++)
-                for (uint32_t j2 = a; j2 < j; j2++) if (ent[j] == ent[j2]) { ent[j] = BP_DUP; break; }
-        }
-        __syncwarp();
-        // cost of putting the row at `pos` into bank group b: cells already placed in the instructions that read it
-        auto price = [&](uint32_t pos, uint32_t b) -> uint32_t {
-            uint32_t cost = 0;
-            for (uint32_t j = off[pos]; j < off[pos + 1]; j++) {
-                const uint32_t en = ent[j];
-                if (en != BP_DUP) cost += occ[(en & 255u) * 8 + ((b - (en >> 8)) & 7u)];
-            }
-            return cost;
-        };
-        auto place = [&](uint32_t pos, uint32_t b, int v) {   // all lanes: add (v = 1) or remove (v = -1) the row's cells
-            for (uint32_t j = off[pos] + lane; j < off[pos + 1]; j += 32) {
-                const uint32_t en = ent[j];
-                if (en != BP_DUP) occ_add((en & 255u) * 8 + ((b - (en >> 8)) & 7u), v);
-            }
-            __syncwarp();
-        };
-        // greedy choice, position by position; lane b < 8 prices bank group b, lane i < 28 keeps the free groups of block i
-        uint32_t fm = 0xffu;
-        for (uint32_t pos = 0; pos < T; pos++) {
-            const uint32_t blk = pos >> 3;
-            const uint32_t fmask = __shfl_sync(FULLM, fm, blk);
-            uint32_t b;
-            if (pos < n && off[pos + 1] > off[pos]) {
-                uint32_t key = 0xffffffffu;
-                if (lane < 8 && ((fmask >> lane) & 1u)) key = (price(pos, lane) << 3) | ((lane - pos) & 7u);   // ties: nearest above the thread's own
-                key = __reduce_min_sync(FULLM, key);
-                b = ((key & 7u) + pos) & 7u;
-                place(pos, b, 1);
-            } else {
-                // nobody reads this position through the ring: the free group nearest above the thread's own
-                const uint32_t rot = (fmask >> (pos & 7u)) | (fmask << (8u - (pos & 7u)));
-                b = ((uint32_t)__ffs((int)(rot & 0xffu)) - 1u + pos) & 7u;
-            }
-            if (lane == blk) fm &= ~(1u << b);
-            if (lane == 0) rho[pos] = (uint8_t)(blk * 8 + b);
-            __syncwarp();
-        }
-        // improvement sweeps: swap the bank groups of two rows of a block when that lowers the number of cells they
-        // share a bank group with (lane y < 8 prices the swap with the block's y-th row)
-        for (int sw = 0; sw < A.sweeps; sw++) {
-            for (uint32_t pos = 0; pos < n; pos++) {
-                if (off[pos + 1] == off[pos]) continue;    // uniform: shared data
-                const uint32_t bx = rho[pos] & 7u, blk8 = pos & ~7u;
-                place(pos, bx, -1);
-                const uint32_t cx_here = price(pos, bx);
-                uint32_t key = 0xffffffffu;
-                if (lane < 8 && blk8 + lane != pos) {
-                    const uint32_t y = blk8 + lane, by = rho[y] & 7u;
-                    // the y row's own cells are in the table: they count once in its current price
-                    const uint32_t ny = y < n ? (uint32_t)(off[y + 1] - off[y]) : 0u;
-                    uint32_t dups = 0;
-                    for (uint32_t j = off[y]; j < off[y] + ny; j++) dups += ent[j] == BP_DUP;
-                    const int now = (int)cx_here + (int)price(y, by) - (int)(ny - dups);
-                    const int then = (int)price(pos, by) + (int)price(y, bx);
-                    if (then < now) key = ((uint32_t)(then - now + 4096) << 3) | lane;
-                }
-                key = __reduce_min_sync(FULLM, key);
-                if (key != 0xffffffffu) {
-                    const uint32_t y = blk8 + (key & 7u), by = rho[y] & 7u;
-                    place(y, by, -1);
-                    place(y, bx, 1);
-                    place(pos, by, 1);
-                    if (lane == 0) { rho[pos] = (uint8_t)(blk8 + by); rho[y] = (uint8_t)(blk8 + bx); }
-                } else {
-                    place(pos, bx, 1);
-                }
-                __syncwarp();
-            }
-        }
-        // publish: ring column per thread, and the column field of every near edge
-        for (uint32_t pos = lane; pos < T; pos += 32) rcol[pos] = rho[pos];
-        for (uint32_t pos = lane; pos < n; pos += 32) {
-            const uint32_t m = order[pos], po = pred_off[m], np = pred_off[m + 1] - po, sg_ = nsigma[m];
-            for (uint32_t o = 0; o < np; o++) {
-                const uint32_t p = preds[po + o], d = sg_ - nsigma[p];
-                if (p >= lo && d <= (uint32_t)DP_MAXD) pdesc2[po + o] = (d << 16) | rho[nthr[p]];
-            }
-        }
-        __syncwarp();
-    }
-}
 
 int launch_prealign(Session* s, const sg_align_params& ap, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
@@ -1085,6 +877,7 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     A.cursor = w->d_cursor; A.pred_off = w->d_pred_off; A.preds = w->d_preds; A.pdesc = w->d_pdesc;
     A.spillrow = w->d_spillrow; A.nflags = w->d_nflags; A.lastnodes = w->d_lastnodes; A.groups = w->d_groups;
     A.order = w->d_order; A.rcol = w->d_rcol; A.nthr = w->d_nthr; A.pdesc2 = w->d_pdesc2; A.ghosts = w->d_ghosts; A.writers = w->d_writers;
+    A.pen_max = fmaxf(ap.gap_penalty, ap.gap_ext_penalty); A.pen_min = fminf(ap.gap_penalty, ap.gap_ext_penalty);
     A.force_generic = s->force_generic || ap.insertion == 1 || ix->d_colw != nullptr;   // the aspace-aware transition and the weighted scheme live in the generic kernel
     A.nmaxins = w->d_nmaxins; A.forbid = ap.insertion == 1;
     A.cells = s->d_counters + 1; A.cursors = w->d_cursors; A.tb_words = s->tb_words; A.spill_elems = s->spill_elems;
@@ -1100,14 +893,6 @@ int launch_graph(Session* s, Workspace* w, const sg_align_params& ap, uint32_t q
     SG_CUDA(cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_kernel<<<n, GRAPH_BLOCK, smem, w->stream>>>(A);
     s->stats.kernel_launches += 1;
-    if (s->bankplan) {
-        BankPlanArgs B;
-        B.hdr = s->d_hdr; B.q0 = q0; B.gcap = s->gcap; B.icap = s->icap;
-        B.order = w->d_order; B.nthr = w->d_nthr; B.pred_off = w->d_pred_off; B.preds = w->d_preds; B.nsigma = w->d_nsigma;
-        B.pdesc2 = w->d_pdesc2; B.rcol = w->d_rcol; B.sweeps = s->bankplan - 1;
-        bankplan_kernel<<<n, 32 * BP_WARPS, 0, w->stream>>>(B);
-        s->stats.kernel_launches += 1;
-    }
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }

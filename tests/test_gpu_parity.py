@@ -120,6 +120,30 @@ def test_align_batch_random_vs_oracle(orc, dp_mode):
     ix.close()
 
 
+def test_penalties_beyond_the_value_bound(orc):
+    """gap penalties so large that a cell's best candidate can exceed the reference's initial cell value 1000000
+    (src/mesh.h:469-473), negative penalties, zero penalties: such batches leave the specialised kernel (which never
+    materialises that initial value) for the generic one and still equal the oracle bit for bit"""
+    rng = np.random.default_rng(19)
+    tree, m, c, o = synth.synth_msa(200, W=900, L=260, seed=6)
+    msa = O.MSA(m, c, o, 900)
+    qm, qo = synth.synth_queries(tree, 24, "full", seed=4)
+    ix = sina_b200.Index(msa.masks, msa.cols, msa.off, msa.W, k=6)
+    fams, foff = [], [0]
+    for i in range(24):
+        F = int(rng.integers(2, 30))
+        fams.append(rng.choice(200, F, replace=False).astype(np.uint32))
+        foff.append(foff[-1] + F)
+    for ap_kw in (dict(gap_penalty=3000.0, gap_ext_penalty=2500.0), dict(gap_penalty=5.0, gap_ext_penalty=1200.0),
+                  dict(gap_penalty=-1.0, gap_ext_penalty=2.0), dict(gap_penalty=0.0, gap_ext_penalty=0.0)):
+        oc, om, res = ix.align(qm, qo, np.concatenate(fams), np.array(foff, np.uint64), sina_b200.AlignParams(**ap_kw))
+        for i in range(24):
+            a, b = int(qo[i]), int(qo[i + 1])
+            r1, c1, m1, _ = orc.align(msa, fams[i], qm[a:b], O.AlignParams(**ap_kw))
+            compare_result(res[i], oc[a:b], om[a:b], r1, c1, m1, msa.W, (ap_kw, i))
+    ix.close()
+
+
 def test_wide_indegree_and_far_edges(orc, dp_mode):
     """in-degree > 8 switches the traceback to 16-bit cells; long gaps force predecessor rows through the
     global spill path (column-rank distance > ring depth); Lq > W hits the reference's runtime_error."""
