@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 N_REFS, W_COLS, L_REF, KMER = 50000, 50000, 1500, 10
 CHUNK = int(os.environ.get("SG_BATCH", "2368"))   # queries per graph/DP/backtrack launch (the library's default)
-CHUNK_ISO = 1184                                 # launch size of the kernel-only pass behind `roofline`
+CHUNK_ISO = 2368                                 # launch size of the kernel-only pass behind `roofline`: the production chunk (SG_BATCH)
 SEED = 20260117
 
 
@@ -314,7 +314,8 @@ def measure(mods, ix, m, c, o, qm, qo, wargs, steps, warmup, rank, world, local,
     sess.close()
     os.environ["SG_STREAMS"] = "1"
     user_batch = os.environ.get("SG_BATCH")
-    os.environ["SG_BATCH"] = str(CHUNK_ISO)   # whole waves: 1184 = 2 x (148 SMs x 4 resident CTAs), no ragged last launch
+    os.environ["SG_BATCH"] = str(CHUNK_ISO)   # whole waves: 2368 = 4 x (148 SMs x 4 resident CTAs), the production chunk
+    os.environ["SG_FIRST_DIV"] = "1"          # ... and no short first launch
     nq_iso = min(nq, 3 * CHUNK_ISO)
     iso = sina_b200.Session(ix, nq_iso, int(qo[nq_iso]))
     iso.upload(qm[:int(qo[nq_iso])], qo[:nq_iso + 1])
@@ -329,6 +330,7 @@ def measure(mods, ix, m, c, o, qm, qo, wargs, steps, warmup, rank, world, local,
     iso.close()
     os.environ.pop("SG_STREAMS", None)
     os.environ.pop("SG_BATCH", None)
+    os.environ.pop("SG_FIRST_DIV", None)
     if user_batch is not None:
         os.environ["SG_BATCH"] = user_batch
 

@@ -43,7 +43,7 @@ constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
 typedef uint16_t rcol_t;                     // ring column index
 // DP CTA shape: DP_THREADS threads = DP_THREADS - 32 row lanes + one loader warp; DP_CTAS resident CTAs per SM (the
 // register cap the kernels are compiled for). Measured on B200 (full-length 16S queries, GCUPS of the DP kernel):
-// 128 threads x 7 CTAs 481, 192 x 5 560, 224 x 5 552, 256 x 4 604, 512 x 2 537.
+// 128 threads x 7 CTAs 481, 192 x 5 560, 224 x 5 552, 256 x 4 604, 288 x 3 574, 320 x 3 539, 512 x 2 537.
 #ifndef DP_THREADS
 #define DP_THREADS 256
 #endif
