@@ -145,22 +145,33 @@ __device__ __forceinline__ uint32_t column_keys(const uint8_t* stab, const uint3
     uint32_t nu = 0, last = NONE;
     const uint32_t Fh = (F + 1u) >> 1;
     const uint8_t* t = stab + c * Fh;
-    for (uint32_t j = 0; j < F; j++) {
-        const uint32_t e = (t[j >> 1] >> ((j & 1u) * 4u)) & 15u;
-        if (!e) continue;
-        const uint32_t p = prev_node(stab, scolbase, Fh, c, j);
-        if (p == NONE) continue;
-        const uint32_t key = ((e - 1u) << 24) | p;
-        if (key == last) continue;            // most rows of a family run through the same pair of nodes
-        last = key;
-        bool dup = false;
+    // the previous base of a row nearly always sits in the previous column: its byte is fetched together with the
+    // column's own, the walk back through the table (prev_node) is left to the rows with a gap there
+    const uint8_t* tp = c ? t - Fh : t;
+    const uint32_t pbase = c ? scolbase[c - 1] : 0u;
+    for (uint32_t jb = 0; jb < Fh; jb++) {
+        const uint32_t cur = t[jb];
+        if (!cur) continue;
+        const uint32_t prv = c ? tp[jb] : 0u;
 #pragma unroll
-        for (int i = 0; i < GK; i++) dup |= k[i] == key;
-        if (dup) continue;
-        if (nu >= (uint32_t)GK) return GK + 1;
+        for (uint32_t half = 0; half < 2; half++) {
+            const uint32_t e = (cur >> (4u * half)) & 15u;
+            if (!e) continue;
+            const uint32_t pe = (prv >> (4u * half)) & 15u;
+            const uint32_t p = pe ? pbase + pe - 1u : (c ? prev_node(stab, scolbase, Fh, c - 1u, 2u * jb + half) : NONE);
+            if (p == NONE) continue;
+            const uint32_t key = ((e - 1u) << 24) | p;
+            if (key == last) continue;            // most rows of a family run through the same pair of nodes
+            last = key;
+            bool dup = false;
 #pragma unroll
-        for (int i = 0; i < GK; i++) if ((uint32_t)i == nu) k[i] = key;
-        nu++;
+            for (int i = 0; i < GK; i++) dup |= k[i] == key;
+            if (dup) continue;
+            if (nu >= (uint32_t)GK) return GK + 1;
+#pragma unroll
+            for (int i = 0; i < GK; i++) if ((uint32_t)i == nu) k[i] = key;
+            nu++;
+        }
     }
     // sorting network for 6 keys (unused slots hold NONE = the largest value)
     static_assert(GK == 6, "sorting network below");
@@ -413,11 +424,24 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
         //         graph.h:332-340); per node the distinct predecessors in ascending id (reduce_edges, graph.h:466-488).
         //         A thread collects its column's (local node, predecessor) pairs as a sorted list of distinct keys
         //         (pass 0: in-degree per node; pass 1, after the scan: the predecessor ids)
+        const bool keep_keys = (uint64_t)n_cols * GK <= A.itemcap;   // `slot` (global scratch of the generic path) is free here
         for (int pass = 0; pass < 2; pass++) {
             for (uint32_t c = tid; c < n_cols; c += nt) {
                 const uint32_t base = scolbase[c], nn = scolbase[c + 1] - base, cm = colof[c];
                 uint32_t k[GK];
-                uint32_t nu = column_keys(stab, scolbase, F, c, k);
+                uint32_t nu;
+                if (pass == 0 || !keep_keys) {
+                    nu = column_keys(stab, scolbase, F, c, k);
+                    if (pass == 0 && keep_keys) {   // pass 1 reads the column's keys back instead of deriving them again
+#pragma unroll
+                        for (int x = 0; x < GK; x++) slot[(uint64_t)c * GK + x] = nu <= (uint32_t)GK ? k[x] : 0xFFFFFFFEu;
+                    }
+                } else {
+                    nu = 0;
+#pragma unroll
+                    for (int x = 0; x < GK; x++) { k[x] = slot[(uint64_t)c * GK + x]; nu += k[x] != NONE ? 1u : 0u; }
+                    if (k[0] == 0xFFFFFFFEu) nu = GK + 1;
+                }
                 // one run of equal local node per node with predecessors: in-degree = run length (pass 0), the ids (pass 1)
                 auto edge = [&](uint32_t key, uint32_t o) {   // pass 1: predecessor number o (global index) of its node
                     const uint32_t p = key & 0xffffffu;
