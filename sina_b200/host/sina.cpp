@@ -155,13 +155,13 @@ int real_main(int argc, const char* const* argv) {
     std::cerr << "Aligner ready. Processing sequences" << std::endl;  // src/sina.cpp:581
     const auto before = std::chrono::steady_clock::now();
 
-    const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 6 * std::max(1u, ngpu);
+    const size_t inflight = opts.max_trays ? std::max<size_t>(1, opts.max_trays / opts.batch) : 3 * std::max(1u, ngpu) + 1;
     bounded_queue<batch_t> todo(inflight), torender(inflight);
     // Batches alive between the reader and the last byte written (the reference's limiter node, src/sina.cpp:485-489):
     // a rendered batch holds its FASTA records (4096 x 50 kB at 50 000 columns), so nothing but this bound keeps a slow
     // output device from growing the `done` map until memory runs out. The reader takes a slot per batch, the slot comes
     // back when the batch's trays are destroyed.
-    const size_t alive_cap = 3 * inflight + 8;
+    const size_t alive_cap = 2 * inflight + 4;   // x 9472 trays of ~26 kB (input + aligned sequence): 0.25 GB per batch
     std::mutex alive_mu;
     std::condition_variable alive_cv;
     size_t alive = 0;

@@ -18,13 +18,14 @@ ap.add_argument("--refs", type=int, default=5000)
 ap.add_argument("--queries", type=int, default=1024)
 ap.add_argument("--kind", default="full")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--fs-max", type=int, default=40, help="family size (1: a chain graph, every node has one predecessor)")
 a = ap.parse_args()
 tree, m, c, o = synth.synth_msa(a.refs, W=50000, L=1500, seed=20260117)
 qm, qo = synth.synth_queries(tree, a.queries, a.kind, seed=1000)
 ix = sina_b200.Index(m, c, o, 50000, k=10)
 s = sina_b200.Session(ix, a.queries, int(qo[-1]))
 s.upload(qm, qo)
-fp, al = sina_b200.FamParams(), sina_b200.AlignParams()
+fp, al = sina_b200.FamParams(fs_min=a.fs_max, fs_max=a.fs_max, fs_req_full=min(1, a.fs_max - 1) if a.fs_max < 40 else 1), sina_b200.AlignParams(realign=1)
 s.family(fp)
 s.align(al)
 s.sync()
