@@ -382,7 +382,7 @@ def measure(mods, ix, m, c, o, qm, qo, wargs, steps, warmup, rank, world, local,
         "roofline": {"kernel": "mesh_kernel", "bound": "hbm", "achieved": gcups * 1.0,
                      "peak": hbm_peak, "unit": "GB/s", "frac": gcups / hbm_peak,
                      "traffic": traffic, "traffic_unit": "GB per launch (%d-query chunk), ncu dram read+write" % CHUNK_ISO,
-                     "kernel_only_pass": "%d queries in launches of %d on one stream (the timed region runs %d-query launches on %s streams, where the kernel's events overlap other kernels)" % (nq_iso, CHUNK_ISO, CHUNK, os.environ.get("SG_STREAMS", "2")),
+                     "kernel_only_pass": "%d queries in launches of %d on one stream (the timed region runs %d-query launches on %s streams, where the kernel's events overlap other kernels)" % (nq_iso, CHUNK_ISO, CHUNK, os.environ.get("SG_STREAMS", "3")),
                      "algorithmic_gb_per_launch": cells_iso / launches_iso / 1e9,
                      "peak_source": peak_src,
                      "limiter": "not HBM: 1 B of traceback per cell is the only mandatory HBM traffic, so `frac` is low by construction "

@@ -120,13 +120,22 @@ static int ensure_family_capacity(Session* s, uint32_t fam_cap) {
     uint64_t sp_mb = env_mb("SG_SPILL_ARENA_MB", std::min<uint64_t>(16384, std::max<uint64_t>(64, C * (128 * max_qlen_guess * 8 / 1000000 + 1))));   // ~100 spilled rows per query (group boundaries); a chunk that does not fit is re-run
     s->tb_words = tb_mb * 1024 * 1024 / 4;
     s->spill_elems = sp_mb * 1024 * 1024 / 8;
-    // one workspace when the batch is a single chunk, else SG_STREAMS (default 4) so that chunks overlap: measured on
-    // B200 (10k full-length queries): 1184 x 2: 91.3k seq/s, 1184 x 3: 99.7k, 888 x 3: 97.3k, 888 x 4: 99.8k, 592 x 4: 98.7k
+    // one workspace when the batch is a single chunk, else SG_STREAMS (default 3) so that chunks overlap: measured on
+    // B200 (10k full-length queries, chunks of 2368): 2 workspaces 127.4k seq/s, 3 workspaces 130.4k
     const uint64_t n_chunks = (Q + C - 1) / C;
-    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 2)), MAX_WS);
+    int want = (int)std::min<uint64_t>(std::max<uint64_t>(1, env_mb("SG_STREAMS", 3)), MAX_WS);
     if ((uint64_t)want > n_chunks) want = (int)n_chunks;
     for (int i = 0; i < want; i++) {
-        SG_TRY(alloc_workspace(s, &s->ws[i]));
+        const int rc = alloc_workspace(s, &s->ws[i]);
+        if (rc != SG_OK) {
+            // out of device memory for another workspace (two sessions of 10 k full-length queries with three workspaces
+            // each fill most of 180 GB): run with the workspaces there are; without any the call fails
+            free_workspace(&s->ws[i]);
+            s->ws[i] = Workspace();
+            cudaGetLastError();
+            if (i == 0) return rc;
+            break;
+        }
         s->n_ws = i + 1;
     }
     return SG_OK;
@@ -366,6 +375,7 @@ int sg_session_create(sg_index* h, uint32_t max_queries, uint64_t max_bases, sg_
     s->ix = ix; s->max_q = max_queries; s->max_bases = max_bases ? max_bases : 1;
     s->chunk = std::min<uint32_t>(max_queries, (uint32_t)std::max<uint64_t>(1, env_mb("SG_BATCH", 2368)));
     s->force_generic = (int)env_mb("SG_DP_GENERIC", 0);
+    s->pair = (int)env_mb("SG_PAIR", 0);
     s->graph_generic = (int)env_mb("SG_GRAPH_GENERIC", 0);
     *out = (sg_session*)s;
     SG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -685,12 +695,17 @@ static int enqueue_chunk(Session* s, Workspace* w, const sg_align_params& ap, ui
     w->q0 = q0; w->n = n; w->busy = true; w->last_q0 = q0; w->last_n = n;
     SG_CUDA(cudaMemsetAsync(w->d_cursors, 0, 16, w->stream));  // arena cursors
     SG_CUDA(cudaMemsetAsync(w->d_remaining, 0, 4, w->stream));
+    // SG_PAIR=1: the graph kernel of this chunk starts when the DP kernel of the previous chunk (other workspace) ends,
+    // i.e. together with that chunk's backtrack kernel: the two latency-bound kernels share the GPU between two DP kernels
+    // instead of each trickling in beside one
+    if (s->pair && s->last_dp) SG_CUDA(cudaStreamWaitEvent(w->stream, s->last_dp, 0));
     SG_CUDA(cudaEventRecord(w->ev[0], w->stream));
     SG_TRY(launch_graph(s, w, ap, q0, n));
     SG_CUDA(cudaEventRecord(w->ev[1], w->stream));
     if (w->dp_stream) SG_CUDA(cudaStreamWaitEvent(w->dp_stream, w->ev[1], 0));
     SG_TRY(launch_mesh(s, w, ap, q0, n));
     SG_CUDA(cudaEventRecord(w->ev[2], w->dp_stream ? w->dp_stream : w->stream));
+    s->last_dp = w->ev[2];
     if (w->dp_stream) SG_CUDA(cudaStreamWaitEvent(w->stream, w->ev[2], 0));
     cudaStream_t bs = w->bt_stream ? w->bt_stream : w->stream;
     if (w->bt_stream) SG_CUDA(cudaStreamWaitEvent(bs, w->ev[2], 0));

@@ -276,6 +276,8 @@ struct Session {
     cudaEvent_t ev[8] = {};
     sg_stage_stats stats = {};
     bool have_family = false, have_find = false, have_align = false;
+    int pair = 0;                    // SG_PAIR=1: see enqueue_chunk
+    cudaEvent_t last_dp = nullptr;   // end of the DP kernel queued last
     int force_generic = 0;           // SG_DP_GENERIC=1: run every query through the generic DP kernel (testing)
     int graph_generic = 0;           // SG_GRAPH_GENERIC=1: family graph through the global-scratch path (testing)
 };
