@@ -1,5 +1,7 @@
 #include "align.h"
 
+#include <algorithm>
+#include <cstdio>
 #include <ctime>
 #include <fstream>
 
@@ -45,7 +47,7 @@ void aligner::get_options_description(po::options_description& /*main*/, po::opt
     od.unsupported("debug-graph", false, "graphviz dumps");
     od.unsupported("use-subst-matrix", false, "experimental scoring system of the reference");
     od.flag("write-used-rels", &opts->write_used_rels, "write used reference sequences to field 'used_rels'");
-    od.unsupported("calc-idty", false, "identity computation (cseq_comparator)");
+    od.flag("calc-idty", &opts->calc_idty, "calculate highest identity of aligned sequence with any reference");
     adv.add(od);
 }
 
@@ -163,6 +165,47 @@ void aligner::run(std::vector<tray*>& trays, bool rethrow) {
         c->set_attr<std::string>(fn_filter, famfinder::opts.filter_weights);   // astats->getName() in the reference (src/align.cpp:456)
         delete t.aligned_sequence;
         t.aligned_sequence = c;
+    }
+    if (opts->calc_idty) {
+        // --calc-idty (src/align.cpp:443-453): highest identity (optimistic, no correction, relative to the overlap) of the
+        // aligned sequence with any relative it was aligned against; 100 for a copied alignment (:380-382)
+        std::vector<uint8_t> am;
+        std::vector<uint32_t> ac, ids;
+        std::vector<uint64_t> aoff(1, 0), roff(1, 0);
+        std::vector<tray*> who;
+        for (size_t q = 0; q < live.size(); q++) {
+            tray& t = *live[q];
+            if (res[q].status == SG_Q_COPIED && t.aligned_sequence) { t.aligned_sequence->set_attr<std::string>(fn_idty, "100"); continue; }
+            if (res[q].status != SG_Q_ALIGNED || !t.aligned_sequence || t.aligned_sequence->size() < 2) continue;
+            std::string qb;
+            if (opts->realign) { qb = t.input_sequence->getBases(); for (char& ch : qb) ch = (char)toupper((unsigned char)ch); }
+            for (const auto& r : *t.alignment_reference) {
+                if (opts->realign) {   // the relatives containing the query were removed from the family (src/align.cpp:337-343)
+                    std::string rb = r.sequence->getBases();
+                    for (char& ch : rb) ch = (char)toupper((unsigned char)ch);
+                    if (rb.find(qb) != std::string::npos) continue;
+                }
+                ids.push_back(db.indexOf(r.sequence));
+            }
+            roff.push_back(ids.size());
+            for (const aligned_base& b : t.aligned_sequence->getAlignedBases()) { am.push_back(b.getBase()); ac.push_back(b.getPosition()); }
+            aoff.push_back(am.size());
+            who.push_back(&t);
+        }
+        if (!who.empty()) {
+            std::vector<float> idty(ids.size() + 1);
+            if (ids.empty()) ids.push_back(0);
+            check_sg(sg_identity_batch(index->handle(), am.data(), ac.data(), aoff.data(), (uint32_t)who.size(), ids.data(), roff.data(),
+                                       0, 0, 3, 0, idty.data()),
+                     "identity");
+            for (size_t i = 0; i < who.size(); i++) {
+                float best = 0;
+                for (uint64_t j = roff[i]; j < roff[i + 1]; j++) best = std::max(best, idty[j]);   // NaN never wins, as in std::max(idty, x)
+                char buf[32];
+                snprintf(buf, sizeof(buf), "%.9g", 100.f * best);
+                who[i]->aligned_sequence->set_attr<std::string>(fn_idty, buf);
+            }
+        }
     }
 }
 

@@ -22,7 +22,7 @@ public:
         LOWERCASE_TYPE lowercase = LOWERCASE_NONE;
         INSERTION_TYPE insertion = INSERTION_SHIFT;
         float fs_weight = 1.f, match_score = 2.f, mismatch_score = -1.f, gap_penalty = 5.f, gap_ext_penalty = 2.f;
-        bool write_used_rels = false;
+        bool write_used_rels = false, calc_idty = false;
     };
     static options* opts;
 

@@ -10,6 +10,7 @@ const char* const fn_acc = "acc";
 const char* const fn_start = "start";
 const char* const fn_fullname = "full_name";
 const char* const fn_qual = "align_quality_slv";
+const char* const fn_idty = "align_ident_slv";
 const char* const fn_head = "align_cutoff_head_slv";
 const char* const fn_tail = "align_cutoff_tail_slv";
 const char* const fn_date = "aligned_slv";

@@ -107,6 +107,7 @@ extern const char* const fn_acc;
 extern const char* const fn_start;
 extern const char* const fn_fullname;
 extern const char* const fn_qual;
+extern const char* const fn_idty;
 extern const char* const fn_head;
 extern const char* const fn_tail;
 extern const char* const fn_date;

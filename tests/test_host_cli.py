@@ -321,3 +321,51 @@ def test_cli_search_stage(data, tmp_path):
     assert checked >= 30
     ref.kidx_free(rix)
     ref.db_free(rdb)
+
+
+def test_cli_calc_idty(data, tmp_path):
+    """--calc-idty (src/align.cpp:443-453): align_ident_slv = 100 x the highest identity (optimistic, relative to the
+    overlap) of the aligned sequence with any relative of its family; 100 for a copied alignment"""
+    if not O.have_ref():
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    d, msa, qmasks = data
+    out = tmp_path / "out.fasta"
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out), "--db", str(d / "ref.fasta"),
+                        "--calc-idty", "--meta-fmt", "comment"] + FAM_ARGS, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    recs, name = {}, None
+    for line in open(out):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            recs[name] = {"seq": "", "idty": None}
+        elif line.startswith(";"):
+            k, _, v = line[1:].strip().partition("=")
+            if k == "align_ident_slv":
+                recs[name]["idty"] = v
+        elif name:
+            recs[name]["seq"] += line
+    ref = O.Ref()
+    rdb = ref.db(msa)
+    rix = ref.kidx_build(rdb, 6, 0)
+    checked = 0
+    for i, qm in enumerate(qmasks):
+        rec = recs.get("q%d" % i)
+        if rec is None:
+            continue
+        n, ids, _ = ref.family(rix, O.decode(qm), O.FamParams(**FAM))
+        a = O._CHAR2MASK[np.frombuffer(rec["seq"].encode(), np.uint8)]
+        cols = np.nonzero(a > 0)[0].astype(np.uint32)
+        masks = a[cols].astype(np.uint8)
+        best = np.float32(0)
+        for rid in ids:
+            bm, bc = msa.row(int(rid))
+            v = np.float32(ref.compare(masks, cols, bm, bc, 0, 0, 3, False))
+            if v > best:
+                best = v
+        want = "%.9g" % float(np.float32(100) * best)
+        assert rec["idty"] == want, (i, rec["idty"], want)
+        checked += 1
+    assert checked >= 30
+    ref.kidx_free(rix)
+    ref.db_free(rdb)
