@@ -23,11 +23,11 @@ void rw_fasta::get_options_description(po::options_description& main, po::option
     });
     po::options_description od("FASTA I/O");
     od.value<int>("line-length", &opts->line_length, 0, "wrap output sequence (unlimited)");
-    od.unsupported("min-idty", true, "identity computation (cseq_comparator)");
+    od.value<float>("min-idty", &opts->min_idty, 0.f, "only write sequences with align_idty_slv > X, implies calc-idty");
     od.flag("fasta-write-dna", &opts->out_dna, "Write DNA sequences (default: RNA)");
     od.flag("fasta-write-dots", &opts->out_dots, "Use dots instead of dashes to distinguish unknown sequence data from indels");
-    od.unsupported("fasta-idx", true, "block-wise input");
-    od.unsupported("fasta-block", true, "block-wise input");
+    od.value<long>("fasta-idx", &opts->fasta_idx, 0L, "process only sequences beginning in block <arg>");
+    od.value<long>("fasta-block", &opts->fasta_block, 0L, "length of blocks");
     adv.add(od);
 }
 void rw_fasta::validate_vm(po::variables_map&, po::options_description&) {}
@@ -42,11 +42,13 @@ struct rw_fasta::reader::priv_data {
     std::string filename;
     std::string buf;
     size_t pos = 0;
+    uint64_t base = 0;           // file offset of buf[0]
     bool eof = false;
     unsigned int seqno = 0, lineno = 1, skipped = 0;
     bool refill() {   // drop the consumed part, read another block; false when nothing was added
         if (eof) return false;
         buf.erase(0, pos);
+        base += pos;
         pos = 0;
         const size_t old = buf.size(), block = 4u << 20;
         buf.resize(old + block);
@@ -67,6 +69,12 @@ rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
         if (!data->file) throw std::runtime_error("Unable to open file " + infile + " for reading.");
         data->in = &data->file;
     }
+    // --fasta-block / --fasta-idx (src/rw_fasta.cpp:209-216,237-242): start at byte block * idx, at the next title line
+    if (opts->fasta_block > 0) {
+        if (infile == "-") throw std::logic_error("Cannot use --fasta-idx when input is piped");
+        data->file.seekg((std::streamoff)(opts->fasta_block * opts->fasta_idx));
+        data->base = (uint64_t)(opts->fasta_block * opts->fasta_idx);
+    }
 }
 rw_fasta::reader::~reader() = default;
 unsigned int rw_fasta::reader::skipped() const { return data->skipped; }
@@ -75,6 +83,8 @@ void rw_fasta::reader::count_skipped() { data->skipped++; }
 
 bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, unsigned int& lineno) {
     priv_data& d = *data;
+    // block-wise input: stop once the previous sequence ended past the block (the reference tests tellg() here)
+    if (opts->fasta_block > 0 && d.base + d.pos > (uint64_t)(opts->fasta_block * (opts->fasta_idx + 1))) return false;
     // skip to the next title line
     for (;;) {
         if (d.pos >= d.buf.size() && !d.refill()) return false;
@@ -285,6 +295,12 @@ void rw_fasta::writer::format_into(const cseq& c, std::string& o) {  // src/rw_f
     p[n] = '\n';
 }
 
+bool rw_fasta::writer::passes_min_idty(const cseq& c) {
+    if (!opts) opts = new options();
+    if (!(opts->min_idty > 0)) return true;
+    return !(opts->min_idty > c.get_attr<float>(fn_idty, 0.f));
+}
+
 std::string rw_fasta::writer::format(const cseq& c) {
     std::string o;
     format_into(c, o);
@@ -306,6 +322,10 @@ void rw_fasta::writer::write_formatted(const std::string* record) {
 tray rw_fasta::writer::operator()(tray t) {
     if (t.input_sequence == nullptr) throw std::runtime_error("Received broken tray in rw_fasta writer");
     if (t.aligned_sequence == nullptr) {  // src/rw_fasta.cpp:399-404
+        ++data->excluded;
+        return t;
+    }
+    if (!passes_min_idty(*t.aligned_sequence)) {  // src/rw_fasta.cpp:405-414
         ++data->excluded;
         return t;
     }

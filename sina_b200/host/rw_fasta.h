@@ -18,6 +18,8 @@ public:
     struct options {
         FASTA_META_TYPE fastameta = FASTA_META_NONE;
         int line_length = 0;
+        float min_idty = 0.f;              // --min-idty: only sequences with align_ident_slv above it are written
+        long fasta_block = 0, fasta_idx = 0;   // --fasta-block B --fasta-idx i: the records starting in bytes (B*i, B*(i+1)] of the input
         bool out_dots = false, out_dna = false;
     };
     static options* opts;
@@ -51,6 +53,8 @@ public:
         // the same into a caller-owned buffer (reused from record to record), and the size it will have
         static void format_into(const cseq& c, std::string& record);
         static size_t record_size(const cseq& c);
+        // --min-idty (src/rw_fasta.cpp:405-414): false for a sequence whose align_ident_slv is below the threshold
+        static bool passes_min_idty(const cseq& c);
         void write_formatted(const std::string* record);
         // positional output (regular files): the caller reserves byte ranges in record order and any thread fills them
         // with pwrite, so that writing 50 kB records is not bound to one thread. Not available on stdout.

@@ -268,7 +268,7 @@ int real_main(int argc, const char* const* argv) {
                         tray& t = b.trays[i];
                         if (!do_align && t.input_sequence && !t.aligned_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
                         if (t.input_sequence == nullptr) throw std::runtime_error("Received broken tray in rw_fasta writer");
-                        if (t.aligned_sequence) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
+                        if (t.aligned_sequence && rw_fasta::writer::passes_min_idty(*t.aligned_sequence)) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
                     }
                 }
             } catch (std::exception& e) {
@@ -357,7 +357,7 @@ int real_main(int argc, const char* const* argv) {
                 tray& t = B.trays[i];
                 if (!do_align && t.input_sequence && !t.aligned_sequence) t.aligned_sequence = new cseq(*t.input_sequence);  // --prealigned: pass through
                 if (t.input_sequence == nullptr) { if (!failed) failure = "Received broken tray in rw_fasta writer"; failed = true; }
-                if (t.aligned_sequence && !failed) { size[i] = rw_fasta::writer::record_size(*t.aligned_sequence); B.has_record[i] = 1; total += size[i]; nrec++; } else nexc++;
+                if (t.aligned_sequence && !failed && rw_fasta::writer::passes_min_idty(*t.aligned_sequence)) { size[i] = rw_fasta::writer::record_size(*t.aligned_sequence); B.has_record[i] = 1; total += size[i]; nrec++; } else nexc++;
                 if (opts.show_log && t.input_sequence) std::cerr << "sequence_number: " << t.seqno << " sequence_identifier: "
                                                                  << t.input_sequence->getName() << " " << t.log.str() << std::endl;
             }

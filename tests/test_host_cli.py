@@ -369,3 +369,13 @@ def test_cli_calc_idty(data, tmp_path):
     assert checked >= 30
     ref.kidx_free(rix)
     ref.db_free(rdb)
+    # --min-idty (src/rw_fasta.cpp:405-414): sequences below the threshold are not written
+    vals = sorted(float(rec["idty"]) for rec in recs.values())
+    thr = vals[len(vals) // 2]
+    out2 = tmp_path / "out2.fasta"
+    r = subprocess.run([os.path.join(BIN, "sina"), "-i", str(d / "q.fasta"), "-o", str(out2), "--db", str(d / "ref.fasta"),
+                        "--calc-idty", "--min-idty", "%.9g" % thr] + FAM_ARGS, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    got = set(read_fasta(out2))
+    assert got == {n for n, rec in recs.items() if not (np.float32(thr) > np.float32(float(rec["idty"])))}
+    assert 0 < len(got) < len(recs)

@@ -3,6 +3,7 @@ cseq vectors, the option surface, and the loud failure without a GPU. No device 
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -105,3 +106,39 @@ def test_cli_prealigned_passthrough_keeps_order(tmp_path):
     for n, row in zip(names, rows):
         assert all(len(x) <= 70 for x in got[n])
         assert "".join(got[n]) == row
+
+
+def test_cli_fasta_block_and_idx(tmp_path):
+    """--fasta-block B --fasta-idx i (src/rw_fasta.cpp:209-216,237-242): seek to byte B*i, skip to the next title line, read
+    records until the previous one ended past byte B*(i+1). No GPU needed: --prealigned passes the sequences through."""
+    rng = np.random.default_rng(3)
+    names, seqs, starts, text = [], [], [], ""
+    for i in range(40):
+        n = int(rng.integers(30, 400))
+        s = "".join(rng.choice(list("ACGU-"), size=n))
+        names.append("s%d" % i)
+        starts.append(len(text))
+        text += ">s%d\n" % i
+        for j in range(0, n, 60):
+            text += s[j:j + 60] + "\n"
+    (tmp_path / "in.fasta").write_text(text)
+    B = 700
+    seen = []
+    for idx in range(len(text) // B + 1):
+        out = tmp_path / ("out%d.fasta" % idx)
+        r = run(["sina", "-i", str(tmp_path / "in.fasta"), "-o", str(out), "--prealigned", "--fasta-block", str(B), "--fasta-idx", str(idx)])
+        assert r.returncode == 0, r.stderr
+        got = [l[1:].split()[0] for l in open(out) if l.startswith(">")]
+        # the reference's rule: first record = first title line at or after byte B*idx; it keeps reading while the position
+        # after the previous record is <= B*(idx+1)
+        want, pos = [], B * idx
+        first = next((k for k, st in enumerate(starts) if st >= pos), None)
+        k = first
+        while k is not None and k < len(starts):
+            if (k > first and starts[k] > B * (idx + 1)) or (k == first and pos > B * (idx + 1)):
+                break
+            want.append(names[k])
+            k += 1
+        assert got == want, (idx, got, want)
+        seen += got
+    assert set(seen) == set(names)
