@@ -843,9 +843,11 @@ __global__ void __launch_bounds__(GRAPH_BLOCK) graph_kernel(GraphArgs A) {
             groups[g].sigma_lo = lo;
             groups[g].depth = hi - lo + 1;
             groups[g].tb_off = words_total;
-            if (mode == 2) {   // two positions per step, one word per thread and pair of steps (mesh.cu)
+            if (mode == 2) {   // two positions per step, one word per thread and pair of steps (mesh.cu), behind one pad
+                               // row: the DP kernel stores a pair's word one row back while it computes the next pair
                 const uint32_t steps8 = (((Lq + 1u) >> 1) + (hi - lo) + 7u) & ~7u;
-                words_total += (uint64_t)(steps8 >> 1) * T;
+                groups[g].tb_off = words_total + T;
+                words_total += (uint64_t)((steps8 >> 1) + 1u) * T;
             } else {
                 const uint32_t steps = (Lq + (hi - lo) + 3) & ~3u;
                 const uint32_t per_word = wide ? 2 : 4;

@@ -166,7 +166,7 @@ struct V2Addr {
 template <int NPW, bool EDGES>
 __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float gp, const float gpe, const uint32_t t0,
                                               const uint32_t qb, float (&pvp)[NPW], float& E, V2Addr<NPW>& AD,
-                                              uint32_t* const prev_p, const uint32_t prev_w) {
+                                              uint32_t* const tbp, const uint32_t prev_w) {
     const float INF = __int_as_float(0x7f800000);
     constexpr bool RAW = v2_raw_cells(NPW);
     uint32_t tbw = 0;
@@ -187,7 +187,7 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
 #pragma unroll
         for (int k = 0; k < NPW; k++) c[k] = v ? lds_f4<(int)SLOT2>(ak[k]) : lds_f4<0>(ak[k]);
         if (v == 0) {
-            __stcs(prev_p, prev_w);   // the previous pair's traceback word leaves in the shadow of the loads (streaming:
+            __stcs(tbp - T, prev_w);  // the previous pair's traceback word leaves in the shadow of the loads (streaming:
                                       // the traceback must not push the spill rows out of L2)
         } else {
             const uint32_t xn = ((t0 + 2u) & (R - 1)) * SLOT2;
@@ -207,7 +207,9 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
         const float sc0 = (qb & (1u << (2 * v))) ? L.msw : L.mmsw;       // comp(): the IUPAC masks intersect
         const float sc1 = (qb & (2u << (2 * v))) ? L.msw : L.mmsw;
         float out[4];
-        float acc = 0.f;        // the two cells' traceback bytes as a small integer held in a float
+        // the two cells' traceback bytes as a small integer held in the low mantissa bits of a float: the sum starts at
+        // 2^23 (every partial sum is an integer below 2^24, exact), so the first flag needs no separate addition
+        float acc = 8388608.0f;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             float del[NPW], mt[NPW];
@@ -268,8 +270,7 @@ __device__ __forceinline__ uint32_t v2_steps2(const V2Lane<NPW>& L, const float 
             if (t == L.tl) *L.lastcol_ptr = L.odd ? out[0] : out[2];
         }
         __syncthreads();
-        // the integer sits in the low mantissa bits of acc + 2^23 (acc < 2^16, exact)
-        const uint32_t w16 = __float_as_uint(__fadd_rn(acc, 8388608.0f));
+        const uint32_t w16 = __float_as_uint(acc);
         tbw = v ? __byte_perm(tbw, w16, 0x5410) : w16;
     }
     return tbw;
@@ -306,9 +307,9 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
     // three phases: edge steps [e0, c0), inner steps [c0, c1), edge steps [c1, e1); the match bits are fetched for 16
     // steps at a time (32 query positions) and consumed from a register, four per pair of steps
     uint32_t* tbp = tbl + (uint64_t)(e0 >> 1) * T;
-    // a pair's traceback word is stored during the next pair (the first store writes 0 to the word the first pair
-    // then overwrites)
-    uint32_t* prev_p = tbp;
+    // a pair's traceback word is stored during the next pair, one row of words back (tbp - T); the first store writes 0
+    // to the word before the warp's first one: a cell before the row's first step, never read, or the pad row every
+    // group's block starts with (graph.cu)
     uint32_t prev_w = 0;
     V2Addr<NPW> AD;
     {
@@ -327,23 +328,21 @@ __device__ __forceinline__ void v2_group(const V2Lane<NPW>& L, const float gp, c
             if (ph == 1) {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    prev_w = v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E, AD, prev_p, prev_w);
-                    prev_p = tbp;
+                    prev_w = v2_steps2<NPW, false>(L, gp, gpe, t0, qb, pvp, E, AD, tbp, prev_w);
                     tbp += T;
                     qb >>= 4;
                 }
             } else {
 #pragma unroll 1
                 for (; t0 < stop; t0 += 2) {
-                    prev_w = v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E, AD, prev_p, prev_w);
-                    prev_p = tbp;
+                    prev_w = v2_steps2<NPW, true>(L, gp, gpe, t0, qb, pvp, E, AD, tbp, prev_w);
                     tbp += T;
                     qb >>= 4;
                 }
             }
         }
     }
-    __stcs(prev_p, prev_w);
+    __stcs(tbp - T, prev_w);
     for (uint32_t t0 = e1; t0 < steps8; t0 += 2) { __syncthreads(); __syncthreads(); }
 }
 
