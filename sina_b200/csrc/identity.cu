@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(ID_THREADS) identity_kernel(IdentArgs A) {
         if (ta0 >= ta1 || tb0 >= tb1) { if (lane == 0) out[pi] = qnan; continue; }   // the reference dereferences end() here
         const uint32_t fa = ac[ta0], la = ac[ta1 - 1], fb = bc[tb0], lb = bc[tb1 - 1];
         const uint32_t lo = max(fa, fb), hi = min(la, lb);
-        uint32_t match = 0, mismatch = 0, only_b = 0, ovh_b = 0, only_a_both = 0;
+        uint32_t match = 0, mismatch = 0, only_b = 0, ovh_b = 0;
         for (uint32_t j = tb0 + lane; j < tb1; j += 32) {
             const uint32_t col = bc[j], b = bm[j];
             const bool bf = A.filter_lc && (b & 16u);
@@ -117,11 +117,9 @@ __global__ void __launch_bounds__(ID_THREADS) identity_kernel(IdentArgs A) {
             if (!a) { only_b += !bf; continue; }
             const bool af = A.filter_lc && (a & 16u);
             if (!af && !bf) { if (base_match(a, b, A.iupac)) match++; else mismatch++; }   // both() (src/cseq_comparator.cpp:190-204)
-            else if (!af) only_a_both++;
-            else if (!bf) only_b++;
+            else if (af && !bf) only_b++;                                                   // (a alone: counted on the query side below)
         }
         match = warp_sum(match); mismatch = warp_sum(mismatch); only_b = warp_sum(only_b); ovh_b = warp_sum(ovh_b);
-        only_a_both = warp_sum(only_a_both);
         // query side: unfiltered bases inside the overlap are matched, mismatched or alone
         uint32_t a_unf_region;
         if (!A.filter_lc) a_unf_region = lo <= hi ? lower_bound_u32(ac, na, hi + 1u) - lower_bound_u32(ac, na, lo) : 0u;
@@ -130,7 +128,6 @@ __global__ void __launch_bounds__(ID_THREADS) identity_kernel(IdentArgs A) {
             for (uint32_t i = ta0 + lane; i < ta1; i += 32) c += (!(am[i] & 16u) && ac[i] >= lo && ac[i] <= hi) ? 1u : 0u;
             a_unf_region = warp_sum(c);
         }
-        (void)only_a_both;
         const int only_a = (int)a_unf_region - (int)match - (int)mismatch;
         const int ovh_a = (int)a_unf_total - (int)a_unf_region;
         int base;

@@ -175,6 +175,66 @@ static void test_fasta(const std::string& tmpdir) {
     EQUAL(ss.str(), std::string(">seq1 first sequence\n--AG-CU\n"));
     t1.destroy(); t2.destroy();
     remove(in.c_str()); remove(out.c_str());
+
+    // record_size / format_into against format() over the writer's options and awkward sequences (bases pushed past
+    // the alignment width, an empty sequence, lower case, attributes)
+    {
+        std::vector<cseq> cs;
+        cs.emplace_back("plain", "--AG-CU--ACGUACGU-------");
+        cs.emplace_back("lower", "acgu--ACGU");
+        cs.emplace_back("empty", "-------");
+        { cseq c("past", "AC"); c.append(aligned_base(40, 1)); c.setWidth(30); cs.push_back(c); }   // last base beyond the width
+        { cseq c("attrs", "--ACGU--"); c.set_attr<std::string>(fn_fullname, "a full name"); c.set_attr(fn_qual, 97); c.set_attr<std::string>("turn", "none"); cs.push_back(c); }
+        const FASTA_META_TYPE metas[] = {FASTA_META_NONE, FASTA_META_HEADER, FASTA_META_COMMENT};
+        for (FASTA_META_TYPE meta : metas) for (int ll : {0, 7, 60}) for (int dots = 0; dots < 2; dots++) for (int dna = 0; dna < 2; dna++) {
+            rw_fasta::opts->fastameta = meta; rw_fasta::opts->line_length = ll; rw_fasta::opts->out_dots = dots; rw_fasta::opts->out_dna = dna;
+            std::string rec;
+            for (const cseq& c : cs) {
+                const std::string want = rw_fasta::writer::format(c);
+                rw_fasta::writer::format_into(c, rec);
+                EQUAL(rec, want);
+                EQUAL(rw_fasta::writer::record_size(c), want.size());
+                const std::string seq = c.getAligned(!dots, dna);   // the sequence lines are getAligned(), wrapped
+                std::string body = want.substr(want.find('\n') + 1), joined;
+                if (meta == FASTA_META_COMMENT) while (!body.empty() && body[0] == ';') body = body.substr(body.find('\n') + 1);
+                for (char ch : body) if (ch != '\n') joined.push_back(ch);
+                EQUAL(joined, seq);
+            }
+        }
+        rw_fasta::opts->fastameta = FASTA_META_NONE; rw_fasta::opts->line_length = 0; rw_fasta::opts->out_dots = false; rw_fasta::opts->out_dna = false;
+    }
+    // the block reader: records cut at any buffer boundary, parsing as a separate step
+    {
+        const std::string big = tmpdir + "/host_unit_big.fasta";
+        std::vector<std::string> names, seqs;
+        {
+            std::ofstream f(big);
+            for (int i = 0; i < 3000; i++) {
+                std::string s2;
+                for (int j = 0; j < 1000 + (i * 37) % 900; j++) s2.push_back("ACGU-"[(i * 7 + j * 13) % 5]);
+                names.push_back("r" + std::to_string(i));
+                seqs.push_back(s2);
+                f << ">" << names.back() << " desc " << i << "\n";
+                for (size_t j = 0; j < s2.size(); j += 70) f << s2.substr(j, 70) << (i % 3 == 0 ? "\r\n" : "\n");
+            }
+        }
+        rw_fasta::reader r2(big);
+        std::string rec;
+        unsigned int seqno = 0, lineno = 0, n = 0;
+        while (r2.next_record(rec, seqno, lineno)) {
+            tray t;
+            CHECK(rw_fasta::reader::parse_record(rec, seqno, lineno, big, t));
+            EQUAL(seqno, n + 1);
+            if (n < names.size()) {
+                EQUAL(t.input_sequence->getName(), names[n]);
+                EQUAL(t.input_sequence->getAligned(true), seqs[n]);
+            }
+            t.destroy();
+            n++;
+        }
+        EQUAL(n, 3000u);
+        remove(big.c_str());
+    }
 }
 
 int main(int argc, char** argv) {
