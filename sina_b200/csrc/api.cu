@@ -229,7 +229,12 @@ int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* 
         delete ix;
         SG_FAIL(SG_ERR_LIMIT, "k-mer table too large for this k and reference size");
     }
-    uint64_t tw = env_mb("SG_TILE_WARPS", TILE_WARPS_MAX);
+    // sub-tiles per search CTA: up to 14 in one tile; beyond that tiles of at most 12, balanced, so that two CTAs
+    // share an SM (one CTA's selection phase and barriers hide behind the other's counting; 500 k references:
+    // 11 tiles of 12 instead of 6 of 24). SG_TILE_WARPS overrides (<= 24).
+    uint64_t tw_auto = ix->n_sub;
+    if (tw_auto > 14) { const uint64_t nt12 = (ix->n_sub + 11) / 12; tw_auto = (ix->n_sub + nt12 - 1) / nt12; }
+    uint64_t tw = env_mb("SG_TILE_WARPS", tw_auto);
     tw = std::max<uint64_t>(1, std::min<uint64_t>(tw, std::min<uint64_t>(TILE_WARPS_MAX, (uint64_t)TILE_WARPS_MAX * SUB_DEFAULT / sub)));
     ix->tile_warps = (uint32_t)std::min<uint64_t>(tw, ix->n_sub);
     ix->tile_size = ix->tile_warps * ix->sub_size;
@@ -399,7 +404,7 @@ void sg_session_destroy(sg_session* h) {
     cudaSetDevice(s->ix->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     free_align(s);
-    void* ptrs[] = {s->d_full_scores, s->d_full_tmp, s->d_full_keys, s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_ranked, s->d_nres, s->d_counters,
+    void* ptrs[] = {s->d_full_scores, s->d_full_tmp, s->d_full_keys, s->d_qmasks, s->d_qoff, s->d_excl, s->d_kmers, s->d_nk, s->d_cand, s->d_cand_n, s->d_cand2, s->d_cand2_n, s->d_ranked, s->d_nres, s->d_counters,
                     s->d_fam_n, s->d_retry, s->d_hdr, s->d_out_cols, s->d_out_masks, s->d_results,
                     s->d_turn_scores, s->d_turn, s->d_turn_ops, s->d_qcols, s->d_fpair, s->d_acols, s->d_pair, s->d_sids, s->d_sscores, s->d_sn};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -512,11 +517,7 @@ static int family_range(Session* s, const sg_fam_params* fp, uint32_t q0, uint32
     Index* ix = s->ix;
     if (n == 0) { q0 = 0; n = s->nq; }
     uint64_t window = (uint64_t)fp->fs_max + 1;  // famfinder.cpp:590
-    auto fits_merge = [&](uint64_t w) {
-        uint64_t p2 = 1;
-        while (p2 < w * ix->n_tiles) p2 <<= 1;
-        return p2 <= FIND_MAX_SORT;
-    };
+    auto fits_merge = [&](uint64_t w) { return find_merge_plan(w, ix->n_tiles, nullptr, nullptr); };
     // remove_similar (famfinder.cpp:553-556): cseq_comparator(optimistic, none, query cover, no filter) of the query at its
     // own input positions against the candidate; identities are <= 1, so the test only bites below 1
     const bool similar = fp->fs_msc_max < 1.0f;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -212,6 +213,9 @@ struct Session {
     uint32_t find_max = 0, find_cap = 0;
     uint64_t* d_cand = nullptr;    // [nq][n_tiles][find_max] keys (score<<32 | id), unordered
     uint32_t* d_cand_n = nullptr;  // [nq][n_tiles]
+    uint64_t* d_cand2 = nullptr;   // two-level merge: [nq][groups][find_max] keys of the tile groups
+    uint32_t* d_cand2_n = nullptr; // [nq][groups]
+    uint64_t cand2_cap = 0;        // keys d_cand2 holds
     uint64_t* d_ranked = nullptr;  // [nq][find_max] keys in rank order
     uint32_t* d_nres = nullptr;    // [nq]
     uint32_t* d_kmers = nullptr;   // [max_bases] valid (fast: A-prefixed) k-mers of query q at qoff[q].., duplicates kept
@@ -286,6 +290,18 @@ struct Session {
 int launch_index_build(Index* ix, cudaStream_t st);
 // q0 / n: query range of the batch (n == 0: all of it)
 int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
+// Top-k merge plan for a window of `max` candidates per tile: the merge sorts up to FIND_MAX_SORT keys per CTA in
+// shared memory, so it takes the tiles in groups of *group tiles (one level when a single group holds them all) and
+// merges the groups' winners in a second level. false: the window does not fit two levels either.
+inline bool find_merge_plan(uint64_t max, uint32_t n_tiles, uint32_t* group, uint32_t* n_groups) {
+    if (max == 0 || max > FIND_MAX_SORT) return false;
+    const uint32_t gs = (uint32_t)std::min<uint64_t>(n_tiles, FIND_MAX_SORT / max);
+    const uint32_t ng = (n_tiles + gs - 1) / gs;
+    if (ng > 1 && (gs < 2 || (uint64_t)ng * max > FIND_MAX_SORT)) return false;
+    if (group) *group = gs;
+    if (n_groups) *n_groups = ng;
+    return true;
+}
 // ranked: rank-ordered keys of the range (stride `window`); null = the session's d_ranked
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr,
                   const float* ident = nullptr);

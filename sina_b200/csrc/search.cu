@@ -3,6 +3,7 @@
 //   find_merge_kernel  partial_sort by greater<pair<int16,int>> (:412): score desc, then id desc
 //   family_kernel      famfinder::impl::match + gap filter + fs_req (src/famfinder.cpp:497-612, 474-491)
 #include "common.cuh"
+#include <algorithm>
 
 namespace sg {
 
@@ -41,13 +42,64 @@ __global__ void __launch_bounds__(128) query_kmers_kernel(const uint8_t* __restr
 // the k-mer's posting list for its own sub-tile: ids inside one list are distinct, so the 32 lanes of one load
 // update 32 different counters with a plain LDS / add / STS and no atomic is needed (shared-memory atomics run
 // at 2 cycles per lane and were the bound of the first version); lists are applied one after the other, in
-// program order. The first 32 postings of FIND_G lists are requested before any of them is applied.
+// program order.
+// A (k-mer, sub-tile) list holds ~9 postings at 500 k references, so the kernel lives or dies by the instructions
+// and the latency it spends per LIST, not by bytes (ncu, profiles/r02x: issue slots 49 % busy at 28 instructions
+// per list, stalls on the LDS -> add -> STS chain and at the barriers):
+// (1) the CTA stages the list offsets of `kc` k-mers x (tile_warps + 1) sub-tile boundaries in shared memory with
+//     coalesced loads (a k-mer's offsets for the tile are contiguous), transposed to off[boundary][k-mer] so that a
+//     warp reads the starts and ends of four of its lists with two LDS.128; the next chunk's offsets travel in
+//     registers while the current chunk is counted;
+// (2) a warp requests the first 32 postings of G lists before it applies the previous G (double buffered in
+//     registers); lanes without a posting increment a dummy counter of their own, so the apply loop has no branch;
+//     lists longer than 32 (rare) get their rest applied in a pass of their own before the loop.
+// Two CTAs per SM where the counters allow it (tiles of <= 14 sub-tiles): one CTA's selection and barriers hide
+// behind the other's counting.
 // Selection: the tile's top-`need` in rank order (score desc, id desc) are those above a threshold score T plus
-// the highest ids among the ties at T. T is found on a histogram of the high scores only ((M/2, M], then
-// (M/4, M/2], ... below the tile's maximum M), so the many low counters cost one compare each.
-constexpr int FIND_G = 8;
+// the highest ids among the ties at T. T is found on a histogram of a window of high scores; the first window
+// starts at the `need`-th largest of the threads' own maxima (a lower bound of T that is almost always within a few
+// ties of it), later ones halve downwards. The passes over the counters read eight at a time (LDS.128) and reject a
+// pair of low counters with one packed u16x2 maximum.
+// x = postings[a + lane] if lane < len (x keeps its value otherwise); base = &postings[lane]
+__device__ __forceinline__ void ldg_u16_if(uint32_t& x, uint64_t base, uint32_t a, uint32_t lane, uint32_t len) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 ad;\n\tsetp.lt.u32 p, %3, %4;\n\tmad.wide.u32 ad, %2, 2, %1;\n\t@p ld.global.nc.u16 %0, [ad];\n\t}"
+                 : "+r"(x) : "l"(base), "r"(a), "r"(lane), "r"(len));
+}
+constexpr int FIND_KC = 192;           // k-mers whose offsets are staged at a time (at most)
+constexpr int FIND_PRE = 8;            // staged offsets a thread carries in registers
 constexpr uint32_t SEL_BINS = 1024;    // widest score window histogrammed at once
 constexpr uint32_t TIE_CAP = 1024;     // ties at the threshold ranked in shared memory (more: id-ordered walk)
+// kernel variants by tile size: lists in flight per request (registers) / threads / CTAs per SM
+struct FindVariant { int g; uint32_t max_warps, ctas; };
+constexpr FindVariant FIND_VARIANTS[3] = {{16, 12, 2}, {8, 14, 2}, {16, TILE_WARPS_MAX, 1}};
+// scratch behind the counters: while counting, the staged offsets off[tile_warps + 1][ks] (ks = kc + 2 G + 4: the
+// columns past kc stay zero, requests past the chunk see empty lists; + 4 rotates the banks between rows) and one dummy
+// counter per thread; while selecting, hist2 + tie
+struct FindLayout {
+    int variant;
+    uint32_t kc;                // k-mers staged at a time: a multiple of 2 G, kc * (tile_warps + 1) <= FIND_PRE * threads
+    uint32_t ks;                // row stride of the staged offsets in words (a multiple of 4)
+    uint32_t scratch_words;
+    size_t smem;
+};
+static FindLayout find_layout(const Index* ix) {
+    const uint32_t tw = ix->tile_warps, ow = tw + 1, nt = 32 * tw;
+    FindLayout L;
+    L.variant = tw <= FIND_VARIANTS[0].max_warps ? 0 : tw <= FIND_VARIANTS[1].max_warps ? 1 : 2;
+    const FindVariant& V = FIND_VARIANTS[L.variant];
+    const uint32_t g2 = 2u * (uint32_t)V.g;
+    const size_t counters = (size_t)tw * ix->sub_size * 2;
+    // what a CTA may use if V.ctas of them are to share an SM (228 KB, 1 KB reserved per CTA, ~200 B static)
+    const size_t per_cta = std::min<size_t>(227 * 1024, 228 * 1024 / V.ctas) - 1280;
+    const size_t room = std::max<size_t>(per_cta > counters ? per_cta - counters : 0, (SEL_BINS + TIE_CAP) * 4) / 4;   // words
+    uint32_t kc = std::min<uint32_t>(FIND_KC, FIND_PRE * nt / ow) & ~(g2 - 1u);
+    while (kc > g2 && (size_t)ow * (kc + g2 + 4) + nt > room) kc -= g2;
+    L.kc = kc;
+    L.ks = kc + g2 + 4;
+    L.scratch_words = std::max<uint32_t>(ow * L.ks + nt, SEL_BINS + TIE_CAP);
+    L.smem = counters + (size_t)L.scratch_words * 4;
+    return L;
+}
 
 struct FindArgs {
     const uint32_t* kmers; const uint32_t* nk; const uint64_t* qoff;
@@ -55,74 +107,128 @@ struct FindArgs {
     const uint32_t* list_off; const uint16_t* postings;
     uint32_t max; uint64_t* cand; uint32_t* cand_n; unsigned long long* counters;
     uint16_t* scores_out;   // non-null: write the tile's score counters to scores_out[q][N] instead of selecting (full ranking)
+    uint32_t kc, ks, scratch_words;   // FindLayout
 };
 
-__global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs A) {
-    extern __shared__ uint32_t hist32[];  // tile_warps * sub_size u16 counters
-    __shared__ uint32_t hist2[SEL_BINS];
-    __shared__ uint32_t tie[TIE_CAP];
+template <int FIND_G, int MAX_THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindArgs A) {
+    extern __shared__ __align__(16) uint32_t hist32[];  // tile_warps * sub_size u16 counters, then the scratch words
     __shared__ uint32_t red[33];
-    __shared__ uint32_t sh_sel[8];      // 0: T, 1: count_gt, 2: need_eq, 3: emitted, 4: found, 5: ties gathered, 6: count_eq
+    __shared__ uint32_t sh_sel[8];      // 0: T, 1: count_gt, 2: need_eq, 3: emitted, 4: found, 5: ties gathered, 6: count_eq, 7: postings
     uint16_t* hist = reinterpret_cast<uint16_t*>(hist32);
     const uint32_t q = blockIdx.x, tile = blockIdx.y, n_tiles = gridDim.y;
-    const uint32_t B = A.sub_size;
-    const uint32_t tile_lo = tile * A.tile_warps * B;
-    const uint32_t tile_n = min(A.tile_warps * B, A.N - tile_lo);
-    const uint32_t words = (tile_n + 1) >> 1;
+    const uint32_t B = A.sub_size, tw = A.tile_warps;
+    uint32_t* scratch = hist32 + ((size_t)tw * B >> 1);
+    uint32_t* hist2 = scratch;             // [SEL_BINS]
+    uint32_t* tie = scratch + SEL_BINS;    // [TIE_CAP]
+    const uint32_t tile_lo = tile * tw * B;
+    const uint32_t tile_n = min(tw * B, A.N - tile_lo);
+    const uint32_t quads = (tw * B) >> 3;              // all counters of the CTA, eight per 16 bytes (B is a power of two >= 32)
     const uint32_t tid = threadIdx.x, nt = blockDim.x, lane = lane_id(), w = warp_id();
-    for (uint32_t i = tid; i < words; i += nt) hist32[i] = 0;
-    __syncthreads();
+    uint4* hist128 = reinterpret_cast<uint4*>(hist32);
+    for (uint32_t i = tid; i < quads; i += nt) hist128[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < A.scratch_words; i += nt) scratch[i] = 0;   // zero columns, dummy counters
+    if (tid == 0) sh_sel[7] = 0;
 
     // ---- counting
-    const uint32_t sub = tile * A.tile_warps + w;
-    uint32_t lmax = 0;   // highest counter value this lane wrote: the tile maximum needs no pass of its own
-    if (sub < A.n_sub) {
-        uint16_t* hw = hist + (size_t)w * B;
-        const uint32_t* kl = A.kmers + A.qoff[q];
-        const uint32_t nk = A.nk[q];
-        const uint16_t* __restrict__ post = A.postings;
-        unsigned long long my_post = 0;
-        for (uint32_t base = 0; base < nk; base += 32) {
-            uint32_t a = 0, len = 0;
-            if (base + lane < nk) {
-                const uint32_t* o = A.list_off + (uint64_t)kl[base + lane] * A.n_sub + sub;
-                a = __ldg(o);
-                len = __ldg(o + 1) - a;
+    const uint32_t sub0 = tile * tw, sub = sub0 + w;
+    const uint32_t ow = tw + 1;                                   // staged offsets per k-mer
+    const uint32_t ow_inv = ((1u << 20) + ow - 1u) / ow;
+    const uint32_t kc = A.kc, ks = A.ks;
+    const uint32_t* kl = A.kmers + A.qoff[q];
+    const uint32_t nk = A.nk[q];
+    uint32_t my_post = 0;                                         // postings of the tile's lists (mod 2^32 per thread, summed per CTA)
+    uint32_t pre[FIND_PRE];
+    auto fetch = [&](uint32_t c0) {   // offsets of the k-mers [c0, c0 + kc) x this tile's sub-tile boundaries
+#pragma unroll
+        for (int i = 0; i < FIND_PRE; i++) {
+            const uint32_t idx = tid + (uint32_t)i * nt;
+            const uint32_t k = (idx * ow_inv) >> 20, j = idx - k * ow;   // idx / ow, exact for idx < 2^20 / ow
+            pre[i] = 0;
+            if (k < kc && c0 + k < nk)
+                pre[i] = __ldg(A.list_off + (uint64_t)__ldg(kl + c0 + k) * A.n_sub + min(sub0 + j, A.n_sub));
+        }
+    };
+    if (nk) fetch(0);
+    uint16_t* hw = hist + (size_t)w * B;
+    // a lane without a posting increments hw[dummy]: a word of its own behind the offsets
+    const uint32_t dummy = (uint32_t)(reinterpret_cast<uint16_t*>(scratch + ow * ks + tid) - hw);
+    const uint32_t* row_a = scratch + w * ks;                     // row_a[k], row_a[ks + k]: this warp's list of k-mer k
+    const uint16_t* __restrict__ post = A.postings;
+    uint64_t pl;                                                  // this lane's view of the postings, kept in registers
+    asm volatile("mov.u64 %0, %1;" : "=l"(pl) : "l"(post + lane));
+    for (uint32_t c0 = 0; c0 < nk; c0 += kc) {
+        __syncthreads();              // counters zeroed / the previous chunk's offsets are no longer read
+#pragma unroll
+        for (int i = 0; i < FIND_PRE; i++) {
+            const uint32_t idx = tid + (uint32_t)i * nt;
+            const uint32_t k = (idx * ow_inv) >> 20, j = idx - k * ow;
+            if (k < kc) {
+                scratch[j * ks + k] = pre[i];
+                // boundaries past the index are clamped to its end: last boundary minus first = the tile's postings
+                my_post += j == tw ? pre[i] : j == 0 ? 0u - pre[i] : 0u;
             }
-            my_post += len;
-            if (!__any_sync(0xffffffffu, len != 0)) continue;
-            for (uint32_t i0 = 0; i0 < 32; i0 += FIND_G) {
-                uint32_t al[FIND_G], ll[FIND_G], x[FIND_G];
+        }
+        __syncthreads();
+        if (c0 + kc < nk) fetch(c0 + kc);
+        if (sub >= A.n_sub) continue;
+        const uint32_t cn = min(kc, nk - c0);
+        // lists longer than 32: everything behind the first 32 postings, four loads at a time (adds commute: done first)
+        for (uint32_t kb = 0; kb < cn; kb += 32) {
+            const uint32_t kk = kb + lane;                        // columns up to ks are readable and zero past the chunk
+            uint32_t m = __ballot_sync(0xffffffffu, kk < cn && row_a[ks + kk] - row_a[kk] > 32u);
+            for (; m; m &= m - 1u) {                              // warp-uniform
+                const uint32_t k = kb + (uint32_t)__ffs((int)m) - 1u;
+                const uint32_t a = row_a[k], len = row_a[ks + k] - a;
+                for (uint32_t e0 = 32; e0 < len; e0 += 128) {
+                    uint32_t y[4];
 #pragma unroll
-                for (int g = 0; g < FIND_G; g++) {
-                    al[g] = __shfl_sync(0xffffffffu, a, i0 + g);
-                    ll[g] = __shfl_sync(0xffffffffu, len, i0 + g);
-                    x[g] = lane < ll[g] ? (uint32_t)__ldg(post + al[g] + lane) : 0u;
-                }
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t e = e0 + 32 * u + lane;
+                        y[u] = e < len ? (uint32_t)__ldg(post + a + e) : dummy;
+                    }
 #pragma unroll
-                for (int g = 0; g < FIND_G; g++) {
-                    if (ll[g] == 0) continue;                       // warp-uniform
-                    if (lane < ll[g]) { const uint32_t nv = hw[x[g]] + 1u; hw[x[g]] = (uint16_t)nv; lmax = max(lmax, nv); }
-                    __syncwarp();
-                    for (uint32_t e0 = 32; e0 < ll[g]; e0 += 128) {  // long lists: four more loads at a time
-                        uint32_t y[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint32_t e = e0 + 32 * u + lane;
-                            y[u] = e < ll[g] ? (uint32_t)__ldg(post + al[g] + e) : 0xffffffffu;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (y[u] != 0xffffffffu) { const uint32_t nv = hw[y[u]] + 1u; hw[y[u]] = (uint16_t)nv; lmax = max(lmax, nv); }
+                    for (int u = 0; u < 4; u++) {
+                        hw[y[u]] = (uint16_t)(hw[y[u]] + 1u);
                         __syncwarp();
                     }
                 }
             }
         }
-        for (int o = 16; o > 0; o >>= 1) my_post += __shfl_xor_sync(0xffffffffu, my_post, o);
-        if (lane == 0 && my_post) atomicAdd(&A.counters[0], my_post);
+        // first 32 postings of the lists [k0, k0 + FIND_G) as counter indices (lanes without one: the dummy)
+        auto request = [&](uint32_t k0, uint32_t (&x)[FIND_G]) {
+#pragma unroll
+            for (int g = 0; g < FIND_G; g += 4) {
+                const uint4 a4 = *reinterpret_cast<const uint4*>(row_a + k0 + g);
+                const uint4 e4 = *reinterpret_cast<const uint4*>(row_a + ks + k0 + g);
+                x[g] = x[g + 1] = x[g + 2] = x[g + 3] = dummy;
+                ldg_u16_if(x[g], pl, a4.x, lane, e4.x - a4.x);
+                ldg_u16_if(x[g + 1], pl, a4.y, lane, e4.y - a4.y);
+                ldg_u16_if(x[g + 2], pl, a4.z, lane, e4.z - a4.z);
+                ldg_u16_if(x[g + 3], pl, a4.w, lane, e4.w - a4.w);
+            }
+        };
+        auto apply = [&](const uint32_t (&x)[FIND_G]) {
+#pragma unroll
+            for (int g = 0; g < FIND_G; g++) {
+                hw[x[g]] = (uint16_t)(hw[x[g]] + 1u);
+                __syncwarp();
+            }
+        };
+        uint32_t xa[FIND_G], xb[FIND_G];
+        request(0, xa);
+#pragma unroll 1
+        for (uint32_t k0 = 0; k0 < cn; k0 += 2 * FIND_G) {         // the next lists are on their way while these are applied
+            request(k0 + FIND_G, xb);
+            apply(xa);
+            request(k0 + 2 * FIND_G, xa);
+            apply(xb);
+        }
     }
+    for (int o = 16; o > 0; o >>= 1) my_post += __shfl_xor_sync(0xffffffffu, my_post, o);
+    if (lane == 0 && my_post) atomicAdd(&sh_sel[7], my_post);
     __syncthreads();
+    if (tid == 0 && sh_sel[7]) atomicAdd(&A.counters[0], (unsigned long long)sh_sel[7]);
     if (A.scores_out) {   // full ranking (rank_full_kernel): hand the whole score vector over
         uint16_t* dst = A.scores_out + (uint64_t)q * A.N + tile_lo;
         for (uint32_t i = tid; i < tile_n; i += nt) dst[i] = hist[i];
@@ -133,8 +239,14 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
     const uint32_t need = min(A.max, tile_n);
     uint64_t* out = A.cand + ((uint64_t)q * n_tiles + tile) * A.max;
     auto score_of = [&](uint32_t i) -> uint32_t { return hist[i]; };
-    // tile maximum
-    uint32_t mx = lmax;   // tracked while counting (a counter's last write is its final value)
+    // tile maximum, and the thread's own maxima (even / odd counters): packed u16x2 maxima over the counters
+    uint32_t mx2 = 0;
+    for (uint32_t i = tid; i < quads; i += nt) {
+        const uint4 v4 = hist128[i];
+        mx2 = __vmaxu2(__vmaxu2(mx2, v4.x), __vmaxu2(v4.y, __vmaxu2(v4.z, v4.w)));
+    }
+    const uint32_t own0 = mx2 & 0xffffu, own1 = mx2 >> 16;
+    uint32_t mx = max(own0, own1);
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (lane == 0) red[w] = mx;
     if (tid == 0) { sh_sel[3] = 0; sh_sel[4] = 0; sh_sel[5] = 0; }
@@ -142,50 +254,78 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
     if (tid == 0) { uint32_t m2 = 0; for (uint32_t i = 0; i < (nt >> 5); i++) m2 = max(m2, red[i]); red[32] = m2; }
     __syncthreads();
     const uint32_t M = red[32];
+    // warp 0: the highest bin of hist2 (scores lo + 1 ...) at which `cum` + the entries in the bins above reach `need`;
+    // sets sh_sel[0] = its score, [1] = entries above it, [2] = entries still needed at it, [6] = entries in it, [4] = 1;
+    // if the window does not reach that far: [1] = cum + the window's entries
+    auto scan_window = [&](uint32_t lo, uint32_t cum) {
+        uint32_t part = 0;
+        for (uint32_t b = 0; b < 32; b++) part += hist2[32 * lane + b];   // lane L owns bins [32L, 32L+32)
+        // above = entries in the bins of higher lanes, suffix = entries in the whole window
+        uint32_t above = 0, suffix = 0;
+        for (int l = 31; l >= 0; l--) {
+            const uint32_t pl2 = __shfl_sync(0xffffffffu, part, l);
+            if ((int)lane == l) above = suffix;
+            suffix += pl2;
+        }
+        const bool mine = cum + above < need && cum + above + part >= need;
+        const uint32_t who = __ballot_sync(0xffffffffu, mine);
+        if (who) {
+            if (mine) {
+                uint32_t c2 = cum + above;
+                for (int b = 31; b >= 0; b--) {
+                    const uint32_t hb = hist2[32 * lane + b];
+                    if (c2 + hb >= need) { sh_sel[0] = lo + 1 + 32 * lane + b; sh_sel[1] = c2; sh_sel[2] = need - c2; sh_sel[6] = hb; break; }
+                    c2 += hb;
+                }
+                sh_sel[4] = 1;
+            }
+        } else if (lane == 0) {
+            sh_sel[1] = cum + suffix;   // everything in this window ranks above the threshold
+        }
+    };
+    // seed: the need-th largest of the threads' own maxima (2 per thread, distinct counters) is a lower bound of T
+    uint32_t seed_lo = 0xffffffffu;
+    if (M > 0) {
+        const uint32_t lo0 = M > SEL_BINS ? M - SEL_BINS : 0u;
+        for (uint32_t i = tid; i < SEL_BINS; i += nt) hist2[i] = 0;
+        __syncthreads();
+        if (own0 > lo0) atomicAdd(&hist2[own0 - lo0 - 1], 1u);
+        if (own1 > lo0) atomicAdd(&hist2[own1 - lo0 - 1], 1u);
+        __syncthreads();
+        if (w == 0) scan_window(lo0, 0u);
+        __syncthreads();
+        if (sh_sel[4]) seed_lo = sh_sel[0] - 1u;
+        __syncthreads();
+        if (tid == 0) sh_sel[4] = 0;
+    }
     uint32_t T = 0, count_gt = 0, need_eq = 0, count_eq = 0;
     {
-        // windows (lo, hi] of scores, highest first; entries above the current window are already counted in cum
+        // windows (lo, hi] of scores, highest first; entries above the current window are already counted in cum.
+        // Counters past tile_n are zero and a window's lower bound is >= 0: they never fall into one.
         uint32_t hi = M, cum = 0;
         for (;;) {
             uint32_t lo = hi / 2;
+            if (seed_lo < hi) { lo = seed_lo; seed_lo = 0xffffffffu; }   // first window only
             if (hi - lo > SEL_BINS) lo = hi - SEL_BINS;
             for (uint32_t i = tid; i < SEL_BINS; i += nt) hist2[i] = 0;
             __syncthreads();
             if (hi > 0) {
-                for (uint32_t i = tid; i < words; i += nt) {
-                    const uint32_t v = hist32[i];
-                    const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
-                    if (s0 > lo && s0 <= hi) atomicAdd(&hist2[s0 - lo - 1], 1u);
-                    if (s1 > lo && s1 <= hi && 2 * i + 1 < tile_n) atomicAdd(&hist2[s1 - lo - 1], 1u);
+                const uint32_t lo2 = lo | (lo << 16);
+                for (uint32_t i = tid; i < quads; i += nt) {
+                    const uint4 v4 = hist128[i];
+                    const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t v = vv[c];
+                        if (__vmaxu2(v, lo2) == lo2) continue;          // both counters <= lo
+                        const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
+                        if (s0 > lo && s0 <= hi) atomicAdd(&hist2[s0 - lo - 1], 1u);
+                        if (s1 > lo && s1 <= hi) atomicAdd(&hist2[s1 - lo - 1], 1u);
+                    }
                 }
             }
             __syncthreads();
-            if (w == 0) {   // lane L owns bins [32L, 32L+32); find the highest bin where cum + suffix count >= need
-                uint32_t part = 0;
-                for (uint32_t b = 0; b < 32; b++) part += hist2[32 * lane + b];
-                // above = entries in the bins of higher lanes, suffix = entries in the whole window
-                uint32_t above = 0, suffix = 0;
-                for (int l = 31; l >= 0; l--) {
-                    const uint32_t pl = __shfl_sync(0xffffffffu, part, l);
-                    if ((int)lane == l) above = suffix;
-                    suffix += pl;
-                }
-                const bool mine = cum + above < need && cum + above + part >= need;
-                const uint32_t who = __ballot_sync(0xffffffffu, mine);
-                if (who) {
-                    if (mine) {
-                        uint32_t c2 = cum + above;
-                        for (int b = 31; b >= 0; b--) {
-                            const uint32_t hb = hist2[32 * lane + b];
-                            if (c2 + hb >= need) { sh_sel[0] = lo + 1 + 32 * lane + b; sh_sel[1] = c2; sh_sel[2] = need - c2; sh_sel[6] = hb; break; }
-                            c2 += hb;
-                        }
-                        sh_sel[4] = 1;
-                    }
-                } else if (lane == 0) {
-                    sh_sel[1] = cum + suffix;   // everything in this window ranks above the threshold
-                }
-            }
+            if (w == 0) scan_window(lo, cum);
             __syncthreads();
             if (sh_sel[4]) { T = sh_sel[0]; count_gt = sh_sel[1]; need_eq = sh_sel[2]; count_eq = sh_sel[6]; break; }
             cum = sh_sel[1];
@@ -196,14 +336,24 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
     }
     // entries above the threshold, and the ties at it
     const bool rank_ties = T > 0 && count_eq <= TIE_CAP;
-    for (uint32_t i = tid; i < words; i += nt) {
-        const uint32_t v = hist32[i];
-        const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
-        if (s0 > T) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s0 << 32) | (tile_lo + 2 * i);
-        if (s1 > T && 2 * i + 1 < tile_n) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s1 << 32) | (tile_lo + 2 * i + 1);
-        if (rank_ties) {
-            if (s0 == T) tie[atomicAdd(&sh_sel[5], 1u)] = 2 * i;
-            if (s1 == T && 2 * i + 1 < tile_n) tie[atomicAdd(&sh_sel[5], 1u)] = 2 * i + 1;
+    {
+        const uint32_t below = T ? (T - 1u) | ((T - 1u) << 16) : 0u;    // T > 0: a pair of counters both < T holds nothing
+        for (uint32_t i = tid; i < quads; i += nt) {
+            const uint4 v4 = hist128[i];
+            const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint32_t v = vv[c];
+                if (T && __vmaxu2(v, below) == below) continue;
+                const uint32_t i0 = 8 * i + 2 * c;
+                const uint32_t s0 = v & 0xffffu, s1 = v >> 16;
+                if (s0 > T) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s0 << 32) | (tile_lo + i0);
+                if (s1 > T) out[atomicAdd(&sh_sel[3], 1u)] = ((uint64_t)s1 << 32) | (tile_lo + i0 + 1);
+                if (rank_ties) {
+                    if (s0 == T) tie[atomicAdd(&sh_sel[5], 1u)] = i0;
+                    if (s1 == T) tie[atomicAdd(&sh_sel[5], 1u)] = i0 + 1;
+                }
+            }
         }
     }
     __syncthreads();
@@ -232,21 +382,37 @@ __global__ void __launch_bounds__(32 * TILE_WARPS_MAX) find_tile_kernel(FindArgs
     if (tid == 0) A.cand_n[q * n_tiles + tile] = need;
 }
 
-// One CTA per query: gather the tiles' candidates, bitonic-sort the 64-bit keys descending in shared
-// memory, keep the first `max`.
+static int launch_find_tile(const Index* ix, FindArgs& A, dim3 grid, cudaStream_t st) {
+    const FindLayout L = find_layout(ix);
+    A.kc = L.kc; A.ks = L.ks; A.scratch_words = L.scratch_words;
+#define FIND_LAUNCH(V)                                                                                              \
+    {                                                                                                               \
+        auto kern = find_tile_kernel<FIND_VARIANTS[V].g, 32 * FIND_VARIANTS[V].max_warps, FIND_VARIANTS[V].ctas>;   \
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));              \
+        kern<<<grid, 32 * ix->tile_warps, L.smem, st>>>(A);                                                         \
+    }
+    if (L.variant == 0) FIND_LAUNCH(0) else if (L.variant == 1) FIND_LAUNCH(1) else FIND_LAUNCH(2)
+#undef FIND_LAUNCH
+    return SG_OK;
+}
+
+// One CTA per (query, group of candidate lists): gather the lists [g * gs, (g + 1) * gs) of the query (lists_per_q of
+// up to `max` keys each), bitonic-sort the 64-bit keys descending in shared memory, keep the first `max`.
+// One level: a single group of all the tiles' lists. Two levels (max * tiles beyond the sort capacity): groups of
+// tiles first, then the groups' winners.
 __global__ void __launch_bounds__(1024) find_merge_kernel(const uint64_t* __restrict__ cand,
-                                                           const uint32_t* __restrict__ cand_n, uint32_t n_tiles,
-                                                           uint32_t max, uint32_t N, uint32_t p2,
-                                                           uint64_t* __restrict__ ranked, uint32_t* __restrict__ nres) {
+                                                           const uint32_t* __restrict__ cand_n, uint32_t lists_per_q,
+                                                           uint32_t gs, uint32_t max, uint32_t p2,
+                                                           uint64_t* __restrict__ out, uint32_t* __restrict__ out_n) {
     extern __shared__ uint64_t keys[];
-    const uint32_t q = blockIdx.x;
+    const uint32_t q = blockIdx.x, g = blockIdx.y, ng = gridDim.y;
     for (uint32_t i = threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0;
     __syncthreads();
-    // compact tile lists back to back (deterministic positions: prefix over cand_n, which is tiny)
+    // compact the lists back to back (deterministic positions: prefix over cand_n, which is tiny)
     uint32_t base = 0;
-    for (uint32_t t = 0; t < n_tiles; t++) {
-        uint32_t c = cand_n[q * n_tiles + t];
-        const uint64_t* src = cand + ((uint64_t)q * n_tiles + t) * max;
+    for (uint32_t t = g * gs; t < min((g + 1) * gs, lists_per_q); t++) {
+        uint32_t c = cand_n[q * lists_per_q + t];
+        const uint64_t* src = cand + ((uint64_t)q * lists_per_q + t) * max;
         for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) keys[base + i] = src[i] + 1;  // +1: real keys > padding
         base += c;
     }
@@ -263,9 +429,21 @@ __global__ void __launch_bounds__(1024) find_merge_kernel(const uint64_t* __rest
             __syncthreads();
         }
     }
-    const uint32_t r = min(max, N);
-    for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) ranked[(uint64_t)q * max + i] = keys[i] - 1;
-    if (threadIdx.x == 0) nres[q] = r;
+    const uint32_t r = min(max, base);   // all tiles: sum of min(max, tile size) >= min(max, N)
+    uint64_t* dst = out + ((uint64_t)q * ng + g) * max;
+    for (uint32_t i = threadIdx.x; i < r; i += blockDim.x) dst[i] = keys[i] - 1;
+    if (threadIdx.x == 0) out_n[q * ng + g] = r;
+}
+
+static int launch_merge(Session* s, const uint64_t* cand, const uint32_t* cand_n, uint32_t lists_per_q, uint32_t gs, uint32_t ng,
+                        uint32_t max, uint32_t n, uint64_t* out, uint32_t* out_n) {
+    uint32_t p2 = 1;
+    while (p2 < (uint64_t)max * std::min(gs, lists_per_q)) p2 <<= 1;
+    SG_CUDA(cudaFuncSetAttribute(find_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p2 * 8)));
+    find_merge_kernel<<<dim3(n, ng), p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
+        cand, cand_n, lists_per_q, gs, max, p2, out, out_n);
+    s->stats.kernel_launches += 1;
+    return SG_OK;
 }
 
 int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
@@ -273,9 +451,8 @@ int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
     if (n == 0) { q0 = 0; n = s->nq; }
     if (max == 0) SG_FAIL(SG_ERR_ARG, "find: max must be > 0");
     if (max > ix->N) max = ix->N;
-    uint32_t p2 = 1;
-    while (p2 < (uint64_t)max * ix->n_tiles) p2 <<= 1;
-    if (p2 > FIND_MAX_SORT) SG_FAIL(SG_ERR_LIMIT, "find: max * tiles exceeds the top-k merge capacity (16384)");
+    uint32_t gs = 0, ng = 0;
+    if (!find_merge_plan(max, ix->n_tiles, &gs, &ng)) SG_FAIL(SG_ERR_LIMIT, "find: max * tiles exceeds the two-level top-k merge capacity");
     if (max > s->find_cap) {
         if (s->d_cand) cudaFree(s->d_cand);
         if (s->d_ranked) cudaFree(s->d_ranked);
@@ -284,10 +461,15 @@ int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
         SG_CUDA(cudaMalloc(&s->d_ranked, (uint64_t)s->max_q * max * sizeof(uint64_t)));
         s->find_cap = max;
     }
+    if (ng > 1 && (uint64_t)s->max_q * ng * max > s->cand2_cap) {
+        if (s->d_cand2) cudaFree(s->d_cand2);
+        if (s->d_cand2_n) cudaFree(s->d_cand2_n);
+        s->d_cand2 = nullptr; s->d_cand2_n = nullptr; s->cand2_cap = 0;
+        SG_CUDA(cudaMalloc(&s->d_cand2, (uint64_t)s->max_q * ng * max * sizeof(uint64_t)));
+        SG_CUDA(cudaMalloc(&s->d_cand2_n, (uint64_t)s->max_q * ix->n_tiles * sizeof(uint32_t)));
+        s->cand2_cap = (uint64_t)s->max_q * ng * max;
+    }
     s->find_max = max;
-    const size_t smem = (size_t)ix->tile_warps * ix->sub_size * 2;
-    SG_CUDA(cudaFuncSetAttribute(find_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SG_CUDA(cudaFuncSetAttribute(find_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(p2 * 8)));
     query_kmers_kernel<<<(n + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff + q0, n, ix->k, ix->nofast,
                                                           s->d_kmers, s->d_nk + q0);
     FindArgs A;
@@ -295,11 +477,16 @@ int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
     A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max; A.scores_out = nullptr;
     A.cand = s->d_cand + (uint64_t)q0 * ix->n_tiles * max; A.cand_n = s->d_cand_n + (uint64_t)q0 * ix->n_tiles; A.counters = s->d_counters;
     dim3 grid(n, ix->n_tiles);
-    find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
-    find_merge_kernel<<<n, p2 / 2 < 1024 ? (p2 / 2 < 32 ? 32 : p2 / 2) : 1024, p2 * 8, s->stream>>>(
-        A.cand, A.cand_n, ix->n_tiles, max, ix->N, p2, s->d_ranked + (uint64_t)q0 * max, s->d_nres + q0);
+    SG_TRY(launch_find_tile(ix, A, grid, s->stream));
+    uint64_t* ranked = s->d_ranked + (uint64_t)q0 * max;
+    if (ng == 1) {
+        SG_TRY(launch_merge(s, A.cand, A.cand_n, ix->n_tiles, ix->n_tiles, 1, max, n, ranked, s->d_nres + q0));
+    } else {   // queries [q0, q0 + n) use the first n slots of the group buffers
+        SG_TRY(launch_merge(s, A.cand, A.cand_n, ix->n_tiles, gs, ng, max, n, s->d_cand2, s->d_cand2_n));
+        SG_TRY(launch_merge(s, s->d_cand2, s->d_cand2_n, ng, ng, 1, max, n, ranked, s->d_nres + q0));
+    }
     SG_CUDA(cudaGetLastError());
-    s->stats.kernel_launches += 3;
+    s->stats.kernel_launches += 2;
     return SG_OK;
 }
 
@@ -378,8 +565,6 @@ __global__ void __launch_bounds__(RF_THREADS) rank_full_kernel(const uint16_t* _
 // full score vectors + full ranking of queries [q0, q0 + n) into s->d_full_keys (n <= s->full_cap)
 int launch_find_full(Session* s, uint32_t q0, uint32_t n) {
     Index* ix = s->ix;
-    const size_t smem = (size_t)ix->tile_warps * ix->sub_size * 2;
-    SG_CUDA(cudaFuncSetAttribute(find_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     query_kmers_kernel<<<(n + 3) / 4, 128, 0, s->stream>>>(s->d_qmasks, s->d_qoff + q0, n, ix->k, ix->nofast,
                                                           s->d_kmers, s->d_nk + q0);
     FindArgs A;
@@ -387,7 +572,7 @@ int launch_find_full(Session* s, uint32_t q0, uint32_t n) {
     A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = 1;
     A.cand = nullptr; A.cand_n = nullptr; A.counters = s->d_counters; A.scores_out = s->d_full_scores;
     dim3 grid(n, ix->n_tiles);
-    find_tile_kernel<<<grid, 32 * ix->tile_warps, smem, s->stream>>>(A);
+    SG_TRY(launch_find_tile(ix, A, grid, s->stream));
     rank_full_kernel<<<n, RF_THREADS, 0, s->stream>>>(s->d_full_scores, ix->N, s->d_full_tmp, s->d_full_keys, s->d_nres + q0);
     SG_CUDA(cudaGetLastError());
     s->stats.kernel_launches += 3;
