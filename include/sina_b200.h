@@ -179,7 +179,8 @@ int sg_identity_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols
 /* search_filter::operator() (src/search_filter.cpp:244-330, the k-mer branch: --search-all is not offered) for a batch of
  * ALIGNED sequences: k-mer search for kmer_candidates references, identity of every candidate, the max_result best by
  * (score, name) descending with score > min_sim. out_ids / out_scores [nq * max_result], out_n [nq] (0 for sequences
- * shorter than 20 bases). kmer_candidates * (index tiles) must not exceed 16384. With correction = jc the logarithm and
+ * shorter than 20 bases). kmer_candidates must fit the two-level top-k merge (at the default 1000: up to 256 index tiles of
+ * 49152 references). With correction = jc the logarithm and
  * the final selection run on the host (the reference's double log), everything before it on the device. */
 int sg_search_batch(sg_index* ix, const uint8_t* amasks, const uint32_t* acols, const uint64_t* aoff, uint32_t nq,
                     const sg_search_params* sp, uint32_t* out_ids, float* out_scores, uint32_t* out_n);

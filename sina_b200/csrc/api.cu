@@ -218,11 +218,12 @@ int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* 
     ix->device = device; ix->N = N; ix->W = W; ix->k = k; ix->nofast = nofast ? 1 : 0;
     ix->max_row_len = max_len ? max_len : 1; ix->total_bases = total;
     ix->n_slots = 1ull << (2 * (nofast ? k : k - 1));
-    // sub-tile size: SG_SUBTILE (power of two, 32..65536; tests use small ones to reach the multi-tile paths),
+    // sub-tile size: SG_SUBTILE (power of two, 32..32768: the u16 value 0xffff is the search kernel's "no posting";
+    // tests use small ones to reach the multi-tile paths),
     // doubled until the (k-mer, sub-tile) offset table stays below 2^32 entries
     uint64_t sub = env_mb("SG_SUBTILE", SUB_DEFAULT);
-    if (sub < 32 || sub > 65536 || (sub & (sub - 1))) { delete ix; SG_FAIL(SG_ERR_ARG, "SG_SUBTILE must be a power of two in 32..65536"); }
-    while (sub < 65536 && ix->n_slots * (((uint64_t)N + sub - 1) / sub) >= (1ull << 32)) sub <<= 1;
+    if (sub < 32 || sub > 32768 || (sub & (sub - 1))) { delete ix; SG_FAIL(SG_ERR_ARG, "SG_SUBTILE must be a power of two in 32..32768"); }
+    while (sub < 32768 && ix->n_slots * (((uint64_t)N + sub - 1) / sub) >= (1ull << 32)) sub <<= 1;
     ix->sub_size = (uint32_t)sub;
     ix->n_sub = (uint32_t)(((uint64_t)N + sub - 1) / sub);
     if (ix->n_slots * ix->n_sub >= (1ull << 32)) {

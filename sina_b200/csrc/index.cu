@@ -153,6 +153,9 @@ int launch_index_build(Index* ix, cudaStream_t st) {
     const uint32_t total32 = (uint32_t)h_total;
     SG_CUDA(cudaMemcpyAsync(ix->d_list_off + n, &total32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SG_CUDA(cudaMalloc(&ix->d_postings, (ix->n_postings + 64) * sizeof(uint16_t)));
+    // postings[n_postings ...] = 0xffff: what the search kernel's lanes without a posting load (never a local id: sub-tiles
+    // hold at most 32768 references)
+    SG_CUDA(cudaMemsetAsync(ix->d_postings + ix->n_postings, 0xff, 64 * sizeof(uint16_t), st));
     idx_rows_kernel<<<grid, 128, smem, st>>>(ix->d_masks, ix->d_row_off, ix->N, ix->k, ix->nofast, ix->sub_size,
                                             ix->n_sub, hash_size, counts, ix->d_list_off, ix->d_postings, 1);
     SG_CUDA(cudaStreamSynchronize(st));

@@ -48,11 +48,10 @@ __global__ void __launch_bounds__(128) query_kmers_kernel(const uint8_t* __restr
 // per list, stalls on the LDS -> add -> STS chain and at the barriers):
 // (1) the CTA stages the list offsets of `kc` k-mers x (tile_warps + 1) sub-tile boundaries in shared memory with
 //     coalesced loads (a k-mer's offsets for the tile are contiguous), transposed to off[boundary][k-mer] so that a
-//     warp reads the starts and ends of four of its lists with two LDS.128; the next chunk's offsets travel in
-//     registers while the current chunk is counted;
-// (2) a warp requests the first 32 postings of G lists before it applies the previous G (double buffered in
-//     registers); lanes without a posting increment a dummy counter of their own, so the apply loop has no branch;
-//     lists longer than 32 (rare) get their rest applied in a pass of their own before the loop.
+//     warp reads the starts and ends of four of its lists with two LDS.128;
+// (2) a warp requests the first 32 postings of G = 8 lists before it applies the previous G (double buffered in
+//     registers; 8, 12 and 16 measure the same: the loads in flight are not what bounds it); lanes without a posting load a sentinel and their update is predicated off, so the apply loop has
+//     no branch; lists longer than 32 (rare) get their rest applied in a pass of their own before the loop.
 // Two CTAs per SM where the counters allow it (tiles of <= 14 sub-tiles): one CTA's selection and barriers hide
 // behind the other's counting.
 // Selection: the tile's top-`need` in rank order (score desc, id desc) are those above a threshold score T plus
@@ -60,10 +59,23 @@ __global__ void __launch_bounds__(128) query_kmers_kernel(const uint8_t* __restr
 // starts at the `need`-th largest of the threads' own maxima (a lower bound of T that is almost always within a few
 // ties of it), later ones halve downwards. The passes over the counters read eight at a time (LDS.128) and reject a
 // pair of low counters with one packed u16x2 maximum.
-// x = postings[a + lane] if lane < len (x keeps its value otherwise); base = &postings[lane]
-__device__ __forceinline__ void ldg_u16_if(uint32_t& x, uint64_t base, uint32_t a, uint32_t lane, uint32_t len) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 ad;\n\tsetp.lt.u32 p, %3, %4;\n\tmad.wide.u32 ad, %2, 2, %1;\n\t@p ld.global.nc.u16 %0, [ad];\n\t}"
-                 : "+r"(x) : "l"(base), "r"(a), "r"(lane), "r"(len));
+// x = postings[a + lane] if lane < len, else the sentinel 0xffff stored behind the last posting (launch_index_build):
+// an unconditional load from a selected address. (A predicated load into a preset register made ptxas put the preset
+// BEHIND the load under register pressure: a write to a register with a load in flight, i.e. a stall on every list.)
+__device__ __forceinline__ uint32_t ldg_posting(uint64_t post, uint32_t a, uint32_t lane, uint32_t len, uint32_t sentinel_at,
+                                                uint32_t& off) {
+    uint32_t x;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 ad;\n\tsetp.lt.u32 p, %4, %5;\n\tadd.u32 %1, %3, %4;\n\t"
+                 "selp.u32 %1, %1, %6, p;\n\tmad.wide.u32 ad, %1, 2, %2;\n\tld.global.nc.u16 %0, [ad];\n\t}"
+                 : "=r"(x), "=r"(off) : "l"(post), "r"(a), "r"(lane), "r"(len), "r"(sentinel_at));
+    return x;
+}
+// counter x of the warp's sub-tile (shared byte address hb) += 1, unless x is the sentinel: no branch. The load is
+// unconditional (sentinel lanes read counter 0), only the store is predicated: a predicated load left ptxas with a
+// partially defined register per list, which it kept alive (16 registers) and spilled.
+__device__ __forceinline__ void bump_posting(uint32_t hb, uint32_t x) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t.reg .u32 ad;\n\tsetp.ne.u32 p, %1, 0xffff;\n\tmad.lo.u32 ad, %1, 2, %0;\n\t"
+                 "selp.u32 ad, ad, %0, p;\n\tld.shared.u16 c, [ad];\n\tadd.u32 c, c, 1;\n\t@p st.shared.u16 [ad], c;\n\t}" ::"r"(hb), "r"(x) : "memory");
 }
 constexpr int FIND_KC = 192;           // k-mers whose offsets are staged at a time (at most)
 constexpr int FIND_PRE = 8;            // staged offsets a thread carries in registers
@@ -71,10 +83,10 @@ constexpr uint32_t SEL_BINS = 1024;    // widest score window histogrammed at on
 constexpr uint32_t TIE_CAP = 1024;     // ties at the threshold ranked in shared memory (more: id-ordered walk)
 // kernel variants by tile size: lists in flight per request (registers) / threads / CTAs per SM
 struct FindVariant { int g; uint32_t max_warps, ctas; };
-constexpr FindVariant FIND_VARIANTS[3] = {{16, 12, 2}, {8, 14, 2}, {16, TILE_WARPS_MAX, 1}};
+constexpr FindVariant FIND_VARIANTS[3] = {{8, 12, 2}, {8, 14, 2}, {16, TILE_WARPS_MAX, 1}};
 // scratch behind the counters: while counting, the staged offsets off[tile_warps + 1][ks] (ks = kc + 2 G + 4: the
-// columns past kc stay zero, requests past the chunk see empty lists; + 4 rotates the banks between rows) and one dummy
-// counter per thread; while selecting, hist2 + tie
+// columns past kc stay zero, requests past the chunk see empty lists; + 4 rotates the banks between rows); while
+// selecting, hist2 + tie
 struct FindLayout {
     int variant;
     uint32_t kc;                // k-mers staged at a time: a multiple of 2 G, kc * (tile_warps + 1) <= FIND_PRE * threads
@@ -93,10 +105,10 @@ static FindLayout find_layout(const Index* ix) {
     const size_t per_cta = std::min<size_t>(227 * 1024, 228 * 1024 / V.ctas) - 1280;
     const size_t room = std::max<size_t>(per_cta > counters ? per_cta - counters : 0, (SEL_BINS + TIE_CAP) * 4) / 4;   // words
     uint32_t kc = std::min<uint32_t>(FIND_KC, FIND_PRE * nt / ow) & ~(g2 - 1u);
-    while (kc > g2 && (size_t)ow * (kc + g2 + 4) + nt > room) kc -= g2;
+    while (kc > g2 && (size_t)ow * (kc + g2 + 4) > room) kc -= g2;
     L.kc = kc;
     L.ks = kc + g2 + 4;
-    L.scratch_words = std::max<uint32_t>(ow * L.ks + nt, SEL_BINS + TIE_CAP);
+    L.scratch_words = std::max<uint32_t>(ow * L.ks, SEL_BINS + TIE_CAP);
     L.smem = counters + (size_t)L.scratch_words * 4;
     return L;
 }
@@ -105,6 +117,8 @@ struct FindArgs {
     const uint32_t* kmers; const uint32_t* nk; const uint64_t* qoff;
     uint32_t N, sub_size, n_sub, tile_warps;
     const uint32_t* list_off; const uint16_t* postings;
+    uint32_t sentinel_at;   // postings[sentinel_at] = 0xffff
+    uint32_t zero;          // 0 (see request())
     uint32_t max; uint64_t* cand; uint32_t* cand_n; unsigned long long* counters;
     uint16_t* scores_out;   // non-null: write the tile's score counters to scores_out[q][N] instead of selecting (full ranking)
     uint32_t kc, ks, scratch_words;   // FindLayout
@@ -127,7 +141,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
     const uint32_t tid = threadIdx.x, nt = blockDim.x, lane = lane_id(), w = warp_id();
     uint4* hist128 = reinterpret_cast<uint4*>(hist32);
     for (uint32_t i = tid; i < quads; i += nt) hist128[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t i = tid; i < A.scratch_words; i += nt) scratch[i] = 0;   // zero columns, dummy counters
+    for (uint32_t i = tid; i < A.scratch_words; i += nt) scratch[i] = 0;   // zero columns
     if (tid == 0) sh_sel[7] = 0;
 
     // ---- counting
@@ -149,16 +163,15 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
                 pre[i] = __ldg(A.list_off + (uint64_t)__ldg(kl + c0 + k) * A.n_sub + min(sub0 + j, A.n_sub));
         }
     };
-    if (nk) fetch(0);
-    uint16_t* hw = hist + (size_t)w * B;
-    // a lane without a posting increments hw[dummy]: a word of its own behind the offsets
-    const uint32_t dummy = (uint32_t)(reinterpret_cast<uint16_t*>(scratch + ow * ks + tid) - hw);
+    const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist + (size_t)w * B);   // this warp's counters
     const uint32_t* row_a = scratch + w * ks;                     // row_a[k], row_a[ks + k]: this warp's list of k-mer k
-    const uint16_t* __restrict__ post = A.postings;
-    uint64_t pl;                                                  // this lane's view of the postings, kept in registers
-    asm volatile("mov.u64 %0, %1;" : "=l"(pl) : "l"(post + lane));
+    uint64_t post;                                                // kept in registers (not re-read from the constant bank per list)
+    asm volatile("mov.u64 %0, %1;" : "=l"(post) : "l"(A.postings));
+    const uint32_t sent = A.sentinel_at;
     for (uint32_t c0 = 0; c0 < nk; c0 += kc) {
         __syncthreads();              // counters zeroed / the previous chunk's offsets are no longer read
+        fetch(c0);                    // (not prefetched during the previous chunk: the registers are worth more to the
+                                      // lists in flight, and the SM's other CTA fills the gap)
 #pragma unroll
         for (int i = 0; i < FIND_PRE; i++) {
             const uint32_t idx = tid + (uint32_t)i * nt;
@@ -170,7 +183,6 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
             }
         }
         __syncthreads();
-        if (c0 + kc < nk) fetch(c0 + kc);
         if (sub >= A.n_sub) continue;
         const uint32_t cn = min(kc, nk - c0);
         // lists longer than 32: everything behind the first 32 postings, four loads at a time (adds commute: done first)
@@ -183,35 +195,38 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
                 for (uint32_t e0 = 32; e0 < len; e0 += 128) {
                     uint32_t y[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t e = e0 + 32 * u + lane;
-                        y[u] = e < len ? (uint32_t)__ldg(post + a + e) : dummy;
-                    }
+                    for (int u = 0; u < 4; u++) { uint32_t o; y[u] = ldg_posting(post, a + e0 + 32 * u, lane, len - min(len, e0 + 32 * u), sent, o); }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        hw[y[u]] = (uint16_t)(hw[y[u]] + 1u);
+                        bump_posting(hb, y[u]);
                         __syncwarp();
                     }
                 }
             }
         }
-        // first 32 postings of the lists [k0, k0 + FIND_G) as counter indices (lanes without one: the dummy)
+        // first 32 postings of the lists [k0, k0 + FIND_G) (lanes without one: the sentinel)
+        // (`chain` is always 0, which ptxas cannot know: each group of four lists takes its offsets from an address that
+        // depends on the previous group's, or ptxas hoists all the offset loads and address arithmetic of a request ahead
+        // of its first LDG -- 168 registers uncapped, spills of in-flight postings at the cap)
         auto request = [&](uint32_t k0, uint32_t (&x)[FIND_G]) {
+            uint32_t chain = 0;
 #pragma unroll
             for (int g = 0; g < FIND_G; g += 4) {
-                const uint4 a4 = *reinterpret_cast<const uint4*>(row_a + k0 + g);
-                const uint4 e4 = *reinterpret_cast<const uint4*>(row_a + ks + k0 + g);
-                x[g] = x[g + 1] = x[g + 2] = x[g + 3] = dummy;
-                ldg_u16_if(x[g], pl, a4.x, lane, e4.x - a4.x);
-                ldg_u16_if(x[g + 1], pl, a4.y, lane, e4.y - a4.y);
-                ldg_u16_if(x[g + 2], pl, a4.z, lane, e4.z - a4.z);
-                ldg_u16_if(x[g + 3], pl, a4.w, lane, e4.w - a4.w);
+                const uint32_t* ra = row_a + k0 + g + chain;
+                const uint4 a4 = *reinterpret_cast<const uint4*>(ra);
+                const uint4 e4 = *reinterpret_cast<const uint4*>(ra + ks);
+                uint32_t o0, o1, o2, o3;
+                x[g] = ldg_posting(post, a4.x, lane, e4.x - a4.x, sent, o0);
+                x[g + 1] = ldg_posting(post, a4.y, lane, e4.y - a4.y, sent, o1);
+                x[g + 2] = ldg_posting(post, a4.z, lane, e4.z - a4.z, sent, o2);
+                x[g + 3] = ldg_posting(post, a4.w, lane, e4.w - a4.w, sent, o3);
+                chain = o3 & A.zero;
             }
         };
         auto apply = [&](const uint32_t (&x)[FIND_G]) {
 #pragma unroll
             for (int g = 0; g < FIND_G; g++) {
-                hw[x[g]] = (uint16_t)(hw[x[g]] + 1u);
+                bump_posting(hb, x[g]);
                 __syncwarp();
             }
         };
@@ -474,7 +489,7 @@ int launch_find(Session* s, uint32_t max, uint32_t q0, uint32_t n) {
                                                           s->d_kmers, s->d_nk + q0);
     FindArgs A;
     A.kmers = s->d_kmers; A.nk = s->d_nk + q0; A.qoff = s->d_qoff + q0; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
-    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = max; A.scores_out = nullptr;
+    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.sentinel_at = (uint32_t)ix->n_postings; A.zero = 0; A.max = max; A.scores_out = nullptr;
     A.cand = s->d_cand + (uint64_t)q0 * ix->n_tiles * max; A.cand_n = s->d_cand_n + (uint64_t)q0 * ix->n_tiles; A.counters = s->d_counters;
     dim3 grid(n, ix->n_tiles);
     SG_TRY(launch_find_tile(ix, A, grid, s->stream));
@@ -569,7 +584,7 @@ int launch_find_full(Session* s, uint32_t q0, uint32_t n) {
                                                           s->d_kmers, s->d_nk + q0);
     FindArgs A;
     A.kmers = s->d_kmers; A.nk = s->d_nk + q0; A.qoff = s->d_qoff + q0; A.N = ix->N; A.sub_size = ix->sub_size; A.n_sub = ix->n_sub;
-    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.max = 1;
+    A.tile_warps = ix->tile_warps; A.list_off = ix->d_list_off; A.postings = ix->d_postings; A.sentinel_at = (uint32_t)ix->n_postings; A.zero = 0; A.max = 1;
     A.cand = nullptr; A.cand_n = nullptr; A.counters = s->d_counters; A.scores_out = s->d_full_scores;
     dim3 grid(n, ix->n_tiles);
     SG_TRY(launch_find_tile(ix, A, grid, s->stream));

@@ -2,7 +2,7 @@
 # usage: [REFS="50000 500000"] [FIND_AB_ENV="SG_TILE_WARPS=24"] bash tools/run_find_ab.sh <tag> <lib> [<lib> ...]
 tag=${1:-findab}; shift
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "find or family or turn or search or pipeline_golden or production" > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "${PYTEST_K:-find or family or turn or search or pipeline_golden or production}" > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 for refs in ${REFS:-50000 500000}; do
   timeout 600 python tools/find_ab.py --refs $refs --queries 4096 --libs "$@" 2>&1 | tee gpurun_out/${tag}_${refs}.log | grep -v "^$" | tail -12
