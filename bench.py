@@ -426,6 +426,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: sina_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION (set on some boxes) makes NCCL print a banner to stdout, in front of the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mods = (torch, dist, sina_b200)
 
