@@ -71,11 +71,11 @@ __device__ __forceinline__ uint32_t ldg_posting(uint64_t post, uint32_t a, uint3
     return x;
 }
 // counter x of the warp's sub-tile (shared byte address hb) += 1, unless x is the sentinel: no branch. The load is
-// unconditional (sentinel lanes read counter 0), only the store is predicated: a predicated load left ptxas with a
-// partially defined register per list, which it kept alive (16 registers) and spilled.
-__device__ __forceinline__ void bump_posting(uint32_t hb, uint32_t x) {
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t.reg .u32 ad;\n\tsetp.ne.u32 p, %1, 0xffff;\n\tmad.lo.u32 ad, %1, 2, %0;\n\t"
-                 "selp.u32 ad, ad, %0, p;\n\tld.shared.u16 c, [ad];\n\tadd.u32 c, c, 1;\n\t@p st.shared.u16 [ad], c;\n\t}" ::"r"(hb), "r"(x) : "memory");
+// unconditional (sentinel lanes read the never-written zero word at dz), only the store is predicated: a predicated
+// load left ptxas with a partially defined register per list, which it kept alive (16 registers) and spilled.
+__device__ __forceinline__ void bump_posting(uint32_t hb, uint32_t dz, uint32_t x) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t.reg .u32 ad;\n\tsetp.ne.u32 p, %2, 0xffff;\n\tmad.lo.u32 ad, %2, 2, %0;\n\t"
+                 "selp.u32 ad, ad, %1, p;\n\tld.shared.u16 c, [ad];\n\tadd.u32 c, c, 1;\n\t@p st.shared.u16 [ad], c;\n\t}" ::"r"(hb), "r"(dz), "r"(x) : "memory");
 }
 constexpr int FIND_KC = 192;           // k-mers whose offsets are staged at a time (at most)
 constexpr int FIND_PRE = 8;            // staged offsets a thread carries in registers
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
         }
     };
     const uint32_t hb = (uint32_t)__cvta_generic_to_shared(hist + (size_t)w * B);   // this warp's counters
+    const uint32_t dz = (uint32_t)__cvta_generic_to_shared(scratch + A.kc);        // a zero column of the staged offsets: never written
     const uint32_t* row_a = scratch + w * ks;                     // row_a[k], row_a[ks + k]: this warp's list of k-mer k
     uint64_t post;                                                // kept in registers (not re-read from the constant bank per list)
     asm volatile("mov.u64 %0, %1;" : "=l"(post) : "l"(A.postings));
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
                     for (int u = 0; u < 4; u++) { uint32_t o; y[u] = ldg_posting(post, a + e0 + 32 * u, lane, len - min(len, e0 + 32 * u), sent, o); }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        bump_posting(hb, y[u]);
+                        bump_posting(hb, dz, y[u]);
                         __syncwarp();
                     }
                 }
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
         auto apply = [&](const uint32_t (&x)[FIND_G]) {
 #pragma unroll
             for (int g = 0; g < FIND_G; g++) {
-                bump_posting(hb, x[g]);
+                bump_posting(hb, dz, x[g]);
                 __syncwarp();
             }
         };
