@@ -222,19 +222,16 @@ int sg_index_create(const uint8_t* masks, const uint32_t* cols, const uint64_t* 
     // tests use small ones to reach the multi-tile paths),
     // doubled until the (k-mer, sub-tile) offset table stays below 2^32 entries
     uint64_t sub = env_mb("SG_SUBTILE", SUB_DEFAULT);
-    if (sub < 32 || sub > 32768 || (sub & (sub - 1))) { delete ix; SG_FAIL(SG_ERR_ARG, "SG_SUBTILE must be a power of two in 32..32768"); }
-    while (sub < 32768 && ix->n_slots * (((uint64_t)N + sub - 1) / sub) >= (1ull << 32)) sub <<= 1;
+    if (sub < 32 || sub > SUB_MAX || (sub & (sub - 1))) { delete ix; SG_FAIL(SG_ERR_ARG, "SG_SUBTILE must be a power of two in 32..32768"); }
+    while (sub < SUB_MAX && ix->n_slots * (((uint64_t)N + sub - 1) / sub) >= (1ull << 32)) sub <<= 1;
     ix->sub_size = (uint32_t)sub;
     ix->n_sub = (uint32_t)(((uint64_t)N + sub - 1) / sub);
     if (ix->n_slots * ix->n_sub >= (1ull << 32)) {
         delete ix;
         SG_FAIL(SG_ERR_LIMIT, "k-mer table too large for this k and reference size");
     }
-    // sub-tiles per search CTA: up to 14 in one tile; beyond that tiles of at most 12, balanced, so that two CTAs
-    // share an SM (one CTA's selection phase and barriers hide behind the other's counting; 500 k references:
-    // 11 tiles of 12 instead of 6 of 24). SG_TILE_WARPS overrides (<= 24).
-    uint64_t tw_auto = ix->n_sub;
-    if (tw_auto > 14) { const uint64_t nt12 = (ix->n_sub + 11) / 12; tw_auto = (ix->n_sub + nt12 - 1) / nt12; }
+    // sub-tiles per search CTA (find_layout.h); SG_TILE_WARPS overrides (<= 24)
+    const uint64_t tw_auto = find_auto_tile_warps(ix->n_sub);
     uint64_t tw = env_mb("SG_TILE_WARPS", tw_auto);
     tw = std::max<uint64_t>(1, std::min<uint64_t>(tw, std::min<uint64_t>(TILE_WARPS_MAX, (uint64_t)TILE_WARPS_MAX * SUB_DEFAULT / sub)));
     ix->tile_warps = (uint32_t)std::min<uint64_t>(tw, ix->n_sub);

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "../../include/sina_b200.h"
+#include "find_layout.h"
 
 namespace sg {
 
@@ -35,9 +36,6 @@ void set_error(const std::string& msg);
 
 // ------------------------------------------------------------------ constants
 constexpr int MAX_K = 16;
-constexpr uint32_t SUB_DEFAULT = 4096;       // references per search sub-tile: one warp owns its u16 score counters (8 KB)
-constexpr uint32_t TILE_WARPS_MAX = 24;      // sub-tiles (= warps) per search CTA: 24 x 8 KB = 192 KB of counters
-constexpr uint32_t FIND_MAX_SORT = 16384;    // candidates the top-k merge sorts in shared memory
 constexpr uint32_t FAM_CAP_MAX = 255;        // family members per query (predecessor ordinal fits 8 bits)
 constexpr uint32_t W_MAX = 1u << 20;         // alignment columns (used-column bitmap lives in shared memory)
 constexpr uint32_t QLEN_MAX = 1u << 16;      // bases per query
@@ -290,18 +288,6 @@ struct Session {
 int launch_index_build(Index* ix, cudaStream_t st);
 // q0 / n: query range of the batch (n == 0: all of it)
 int launch_find(Session* s, uint32_t max, uint32_t q0 = 0, uint32_t n = 0);
-// Top-k merge plan for a window of `max` candidates per tile: the merge sorts up to FIND_MAX_SORT keys per CTA in
-// shared memory, so it takes the tiles in groups of *group tiles (one level when a single group holds them all) and
-// merges the groups' winners in a second level. false: the window does not fit two levels either.
-inline bool find_merge_plan(uint64_t max, uint32_t n_tiles, uint32_t* group, uint32_t* n_groups) {
-    if (max == 0 || max > FIND_MAX_SORT) return false;
-    const uint32_t gs = (uint32_t)std::min<uint64_t>(n_tiles, FIND_MAX_SORT / max);
-    const uint32_t ng = (n_tiles + gs - 1) / gs;
-    if (ng > 1 && (gs < 2 || (uint64_t)ng * max > FIND_MAX_SORT)) return false;
-    if (group) *group = gs;
-    if (n_groups) *n_groups = ng;
-    return true;
-}
 // ranked: rank-ordered keys of the range (stride `window`); null = the session's d_ranked
 int launch_family(Session* s, const sg_fam_params& fp, uint32_t window, uint32_t q0 = 0, uint32_t n = 0, const uint64_t* ranked = nullptr,
                   const float* ident = nullptr);

@@ -77,41 +77,7 @@ __device__ __forceinline__ void bump_posting(uint32_t hb, uint32_t dz, uint32_t 
     asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t.reg .u32 ad;\n\tsetp.ne.u32 p, %2, 0xffff;\n\tmad.lo.u32 ad, %2, 2, %0;\n\t"
                  "selp.u32 ad, ad, %1, p;\n\tld.shared.u16 c, [ad];\n\tadd.u32 c, c, 1;\n\t@p st.shared.u16 [ad], c;\n\t}" ::"r"(hb), "r"(dz), "r"(x) : "memory");
 }
-constexpr int FIND_KC = 192;           // k-mers whose offsets are staged at a time (at most)
-constexpr int FIND_PRE = 8;            // staged offsets a thread carries in registers
-constexpr uint32_t SEL_BINS = 1024;    // widest score window histogrammed at once
-constexpr uint32_t TIE_CAP = 1024;     // ties at the threshold ranked in shared memory (more: id-ordered walk)
-// kernel variants by tile size: lists in flight per request (registers) / threads / CTAs per SM
-struct FindVariant { int g; uint32_t max_warps, ctas; };
-constexpr FindVariant FIND_VARIANTS[3] = {{8, 12, 2}, {8, 14, 2}, {16, TILE_WARPS_MAX, 1}};
-// scratch behind the counters: while counting, the staged offsets off[tile_warps + 1][ks] (ks = kc + 2 G + 4: the
-// columns past kc stay zero, requests past the chunk see empty lists; + 4 rotates the banks between rows); while
-// selecting, hist2 + tie
-struct FindLayout {
-    int variant;
-    uint32_t kc;                // k-mers staged at a time: a multiple of 2 G, kc * (tile_warps + 1) <= FIND_PRE * threads
-    uint32_t ks;                // row stride of the staged offsets in words (a multiple of 4)
-    uint32_t scratch_words;
-    size_t smem;
-};
-static FindLayout find_layout(const Index* ix) {
-    const uint32_t tw = ix->tile_warps, ow = tw + 1, nt = 32 * tw;
-    FindLayout L;
-    L.variant = tw <= FIND_VARIANTS[0].max_warps ? 0 : tw <= FIND_VARIANTS[1].max_warps ? 1 : 2;
-    const FindVariant& V = FIND_VARIANTS[L.variant];
-    const uint32_t g2 = 2u * (uint32_t)V.g;
-    const size_t counters = (size_t)tw * ix->sub_size * 2;
-    // what a CTA may use if V.ctas of them are to share an SM (228 KB, 1 KB reserved per CTA, ~200 B static)
-    const size_t per_cta = std::min<size_t>(227 * 1024, 228 * 1024 / V.ctas) - 1280;
-    const size_t room = std::max<size_t>(per_cta > counters ? per_cta - counters : 0, (SEL_BINS + TIE_CAP) * 4) / 4;   // words
-    uint32_t kc = std::min<uint32_t>(FIND_KC, FIND_PRE * nt / ow) & ~(g2 - 1u);
-    while (kc > g2 && (size_t)ow * (kc + g2 + 4) > room) kc -= g2;
-    L.kc = kc;
-    L.ks = kc + g2 + 4;
-    L.scratch_words = std::max<uint32_t>(ow * L.ks, SEL_BINS + TIE_CAP);
-    L.smem = counters + (size_t)L.scratch_words * 4;
-    return L;
-}
+static FindLayout find_layout(const Index* ix) { return find_layout(ix->tile_warps, ix->sub_size); }
 
 struct FindArgs {
     const uint32_t* kmers; const uint32_t* nk; const uint64_t* qoff;

@@ -7,6 +7,7 @@
 #include <iostream>
 #include <sstream>
 
+#include "../csrc/find_layout.h"
 #include "align.h"
 #include "famfinder.h"
 #include "rw_fasta.h"
@@ -237,7 +238,59 @@ static void test_fasta(const std::string& tmpdir) {
     }
 }
 
+// Launch geometry of the k-mer search kernels (csrc/find_layout.h) over every layout an index can have: sub-tiles of
+// 32..32768 references, 1..24 warps per tile (api.cu clamps warps x sub-tile to 24 x 4096 counters).
+static void test_find_layout() {
+    using namespace sg;
+    for (uint32_t sub = 32; sub <= SUB_MAX; sub <<= 1) {
+        const uint32_t tw_max = std::max<uint32_t>(1, std::min<uint32_t>(TILE_WARPS_MAX, TILE_WARPS_MAX * SUB_DEFAULT / sub));
+        for (uint32_t tw = 1; tw <= tw_max; tw++) {
+            const FindLayout L = find_layout(tw, sub);
+            const FindVariant& V = FIND_VARIANTS[L.variant];
+            const uint32_t g2 = 2u * (uint32_t)V.g, ow = tw + 1, nt = 32 * tw;
+            CHECK(tw <= V.max_warps && (L.variant == 0 || tw > FIND_VARIANTS[L.variant - 1].max_warps));
+            CHECK(L.kc >= g2 && L.kc % g2 == 0 && L.kc <= (uint32_t)FIND_KC);   // requests read whole groups of G lists
+            CHECK(L.kc * ow <= (uint32_t)FIND_PRE * nt);                          // every staged offset has a thread
+            CHECK(L.ks % 4 == 0 && L.ks >= L.kc + g2);                            // LDS.128 rows, zero columns past the chunk
+            CHECK(L.scratch_words >= ow * L.ks && L.scratch_words >= SEL_BINS + TIE_CAP);
+            CHECK(L.smem == (size_t)tw * sub * 2 + (size_t)L.scratch_words * 4);
+            CHECK(L.smem + FIND_SMEM_FIXED <= FIND_SMEM_CTA);                      // the launch fits one CTA's shared memory
+            CHECK((size_t)tw * sub * 2 % 16 == 0);                                // the scratch starts 16-byte aligned
+            // the production tiles keep their two CTAs per SM
+            if (sub == SUB_DEFAULT && tw <= FIND_VARIANTS[0].max_warps) CHECK(2 * (L.smem + FIND_SMEM_FIXED) <= FIND_SMEM_SM);
+            if (sub == SUB_DEFAULT && tw == 13) CHECK(2 * (L.smem + FIND_SMEM_FIXED) <= FIND_SMEM_SM);   // 50 k references: one tile
+        }
+    }
+    // tiles of an index: one tile up to 14 sub-tiles, then balanced tiles of at most 12
+    for (uint32_t n_sub = 1; n_sub <= 2000; n_sub++) {
+        const uint32_t tw = find_auto_tile_warps(n_sub), n_tiles = (n_sub + tw - 1) / tw;
+        CHECK(tw >= 1 && tw <= 14 && (n_sub <= 14 ? tw == n_sub : tw <= 12));
+        CHECK((uint64_t)n_tiles * tw >= n_sub && (uint64_t)(n_tiles - 1) * tw < n_sub);
+        if (n_sub > 14) CHECK(tw >= 8);                                           // no sliver tiles
+    }
+    EQUAL(find_auto_tile_warps(13), 13u);     // 50 000 references
+    EQUAL(find_auto_tile_warps(123), 12u);    // 500 000 references: 11 tiles
+    // top-k merge: one level while max x tiles fits the sort, two levels of groups beyond, failure past that
+    for (uint32_t n_tiles : {1u, 2u, 6u, 11u, 16u, 21u, 41u, 256u, 257u, 1000u})
+        for (uint64_t mx : {1ull, 41ull, 410ull, 1000ull, 4100ull, 8192ull, 8193ull, 16384ull, 16385ull}) {
+            uint32_t gs = 0, ng = 0;
+            const bool ok = find_merge_plan(mx, n_tiles, &gs, &ng);
+            if (ok) {
+                CHECK(gs >= 1 && (uint64_t)gs * mx <= FIND_MAX_SORT);             // a group's keys fit one sort
+                CHECK((uint64_t)ng * gs >= n_tiles && (uint64_t)(ng - 1) * gs < n_tiles);
+                CHECK(ng == 1 || (uint64_t)ng * mx <= FIND_MAX_SORT);             // and so do the groups' winners
+            } else {
+                CHECK(mx * n_tiles > FIND_MAX_SORT);                              // never refuses what one level holds
+            }
+        }
+    uint32_t gs = 0, ng = 0;
+    CHECK(find_merge_plan(41, 11, &gs, &ng) && ng == 1);            // family window at 500 000 references
+    CHECK(find_merge_plan(1000, 41, &gs, &ng) && ng == 3);          // --search candidates at 2 M references: two levels
+    CHECK(!find_merge_plan(4100, 41, &gs, &ng));                    // third family window there: full ranking instead
+}
+
 int main(int argc, char** argv) {
+    test_find_layout();
     test_cseq();
     test_options();
     test_fasta(argc > 1 ? argv[1] : "/tmp");
