@@ -173,8 +173,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MIN_CTAS) find_tile_kernel(FindAr
         }
         // first 32 postings of the lists [k0, k0 + FIND_G) (lanes without one: the sentinel)
         // (`chain` is always 0, which ptxas cannot know: each group of four lists takes its offsets from an address that
-        // depends on the previous group's, or ptxas hoists all the offset loads and address arithmetic of a request ahead
-        // of its first LDG -- 168 registers uncapped, spills of in-flight postings at the cap)
+        // depends on the previous group's, so the groups' offset loads and address arithmetic stay in program order
+        // instead of being hoisted ahead of the request's first LDG. It was put in while hunting register spills whose
+        // cause turned out to be bump_posting's predicated load; it costs two instructions per four lists and stayed
+        // because this is the build the parity runs and the sanitizer saw.)
         auto request = [&](uint32_t k0, uint32_t (&x)[FIND_G]) {
             uint32_t chain = 0;
 #pragma unroll
