@@ -10,6 +10,7 @@
 #include "../csrc/find_layout.h"
 #include "align.h"
 #include "famfinder.h"
+#include "reference_db.h"
 #include "rw_fasta.h"
 
 using namespace sina;
@@ -235,6 +236,59 @@ static void test_fasta(const std::string& tmpdir) {
         }
         EQUAL(n, 3000u);
         remove(big.c_str());
+    }
+    // ".gz" on both sides (src/rw_fasta.cpp:200-202,358-360): the writer functor emits gzip members, the reader takes the
+    // concatenated stream back
+    {
+        const std::string gz = tmpdir + "/host_unit_rt.fasta.gz";
+        std::vector<std::string> rows;
+        {
+            rw_fasta::writer wr(gz);
+            CHECK(wr.compressed() && !wr.positional());
+            for (int i = 0; i < 40; i++) {
+                std::string row(500, '-');
+                for (int j = 0; j < 120; j++) row[(size_t)((i * 31 + j * 17) % 500)] = "ACGU"[(i + j) % 4];
+                rows.push_back(row);
+                tray t;
+                t.input_sequence = new cseq(("z" + std::to_string(i)).c_str(), row.c_str());
+                t.aligned_sequence = new cseq(*t.input_sequence);
+                wr(t);
+                t.destroy();
+            }
+            EQUAL(wr.written(), 40u);
+        }
+        rw_fasta::reader rd2(gz);
+        for (int i = 0; i < 40; i++) {
+            tray t;
+            CHECK(rd2(t));
+            if (t.input_sequence) { EQUAL(t.input_sequence->getName(), "z" + std::to_string(i)); EQUAL(t.input_sequence->getAligned(true), rows[(size_t)i]); }
+            t.destroy();
+        }
+        tray tend;
+        CHECK(!rd2(tend));
+        remove(gz.c_str());
+        // a reference database may be compressed too (SILVA ships .fasta.gz): same rows, same packed form
+        {
+            const std::string db = tmpdir + "/host_unit_db.fasta", dbz = db + ".gz";
+            std::string text;
+            for (int i = 0; i < 25; i++) {
+                std::string row(70000, '-');   // lines longer than the gz line buffer
+                for (int j = 0; j < 900; j++) row[(size_t)((i * 131 + j * 77) % 70000)] = "ACGUN"[(i + j) % 5];
+                text += ">ref" + std::to_string(i) + " full name " + std::to_string(i) + "\n" + row + (i % 2 ? "\r\n" : "\n");
+            }
+            { std::ofstream f(db, std::ios::binary); f << text; }
+            { const std::string m = rw_fasta::writer::gzip_member(text.data(), text.size()); std::ofstream f(dbz, std::ios::binary); f.write(m.data(), (std::streamsize)m.size()); }
+            reference_db* a = reference_db::getDB(db);
+            reference_db* b = reference_db::getDB(dbz);
+            EQUAL(a->getSeqCount(), 25u); EQUAL(b->getSeqCount(), 25u);
+            EQUAL(a->getAlignmentWidth(), b->getAlignmentWidth());
+            CHECK(a->getSequenceNames() == b->getSequenceNames());
+            CHECK(a->masks() == b->masks() && a->cols() == b->cols() && a->offsets() == b->offsets());
+            EQUAL(b->getCseq(7).get_attr_string(fn_fullname), std::string("full name 7"));
+            remove(db.c_str()); remove(dbz.c_str());
+        }
+        const std::string one = rw_fasta::writer::gzip_member("", 0);   // an empty member is a valid stream
+        CHECK(one.size() >= 18 && (unsigned char)one[0] == 0x1f && (unsigned char)one[1] == 0x8b);
     }
 }
 

@@ -1,5 +1,7 @@
 #include "reference_db.h"
 
+#include <zlib.h>
+
 #include "sidx.h"
 
 #include <fstream>
@@ -55,13 +57,38 @@ reference_db* reference_db::getDB(const std::string& path) {
         auto it = g_dbs.find(path);
         if (it != g_dbs.end()) return it->second.get();
     }
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("Unable to open reference database '" + path + "'");
+    // plain or gzip-compressed aligned FASTA (SILVA ships its alignments as .fasta.gz)
+    const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
+    std::ifstream in;
+    gzFile zin = nullptr;
+    if (gz) {
+        zin = gzopen(path.c_str(), "rb");
+        if (zin) gzbuffer(zin, 1u << 20);
+    } else {
+        in.open(path);
+    }
+    if (gz ? zin == nullptr : !in) throw std::runtime_error("Unable to open reference database '" + path + "'");
+    struct zcloser { gzFile f; ~zcloser() { if (f) gzclose(f); } } zguard{zin};
+    std::vector<char> zbuf(gz ? 1u << 16 : 0);
+    auto next_line = [&](std::string& line) -> bool {
+        if (!gz) return (bool)std::getline(in, line);
+        line.clear();
+        for (;;) {   // gzgets stops at the buffer's end or behind a newline
+            if (!gzgets(zin, zbuf.data(), (int)zbuf.size())) {
+                int err = 0;
+                gzerror(zin, &err);
+                if (err != Z_OK && err != Z_STREAM_END) throw std::runtime_error("Error reading compressed reference database '" + path + "'");
+                return !line.empty();
+            }
+            line += zbuf.data();
+            if (!line.empty() && line.back() == '\n') { line.pop_back(); return true; }
+        }
+    };
     std::vector<cseq> v;
     std::string line;
     cseq* cur = nullptr;
     size_t lineno = 0;
-    while (std::getline(in, line)) {
+    while (next_line(line)) {
         lineno++;
         if (!line.empty() && line.back() == '\r') line.pop_back();
         if (line.empty() || line[0] == ';') continue;

@@ -2,15 +2,21 @@
 
 #include <fcntl.h>
 #include <unistd.h>
+#include <zlib.h>
 #include <cerrno>
+#include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
 #include <fstream>
 #include <iostream>
 
 namespace sina {
 
 rw_fasta::options* rw_fasta::opts = nullptr;
+
+// file names ending in ".gz" are gzip streams, on both sides (src/rw_fasta.cpp:200-202,358-360)
+static bool is_gz(const std::string& name) { return name.size() > 3 && name.compare(name.size() - 3, 3, ".gz") == 0; }
 
 void rw_fasta::get_options_description(po::options_description& main, po::options_description& adv) {
     if (!opts) opts = new options();
@@ -39,6 +45,8 @@ void rw_fasta::validate_vm(po::variables_map&, po::options_description&) {}
 struct rw_fasta::reader::priv_data {
     std::ifstream file;
     std::istream* in = nullptr;
+    gzFile gz = nullptr;         // ".gz" input
+    ~priv_data() { if (gz) gzclose(gz); }
     std::string filename;
     std::string buf;
     size_t pos = 0;
@@ -52,8 +60,15 @@ struct rw_fasta::reader::priv_data {
         pos = 0;
         const size_t old = buf.size(), block = 4u << 20;
         buf.resize(old + block);
-        in->read(&buf[old], (std::streamsize)block);
-        const size_t got = (size_t)in->gcount();
+        size_t got = 0;
+        if (gz) {
+            const int n = gzread(gz, &buf[old], (unsigned)block);
+            if (n < 0) throw std::runtime_error("Error reading compressed file " + filename);
+            got = (size_t)n;
+        } else {
+            in->read(&buf[old], (std::streamsize)block);
+            got = (size_t)in->gcount();
+        }
         buf.resize(old + got);
         if (got < block) eof = true;
         return got > 0;
@@ -64,13 +79,19 @@ rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
     if (!opts) opts = new options();
     data->filename = infile;
     if (infile == "-") data->in = &std::cin;
-    else {
+    else if (is_gz(infile)) {
+        data->gz = gzopen(infile.c_str(), "rb");
+        if (!data->gz) throw std::runtime_error("Unable to open file " + infile + " for reading.");
+        gzbuffer(data->gz, 1u << 20);
+        // (the reference seeks its filter chain here, which a gzip stream cannot do)
+        if (opts->fasta_block > 0) throw std::logic_error("Cannot use --fasta-idx on compressed input");
+    } else {
         data->file.open(infile, std::ios::binary);
         if (!data->file) throw std::runtime_error("Unable to open file " + infile + " for reading.");
         data->in = &data->file;
     }
     // --fasta-block / --fasta-idx (src/rw_fasta.cpp:209-216,237-242): start at byte block * idx, at the next title line
-    if (opts->fasta_block > 0) {
+    if (opts->fasta_block > 0 && !data->gz) {
         if (infile == "-") throw std::logic_error("Cannot use --fasta-idx when input is piped");
         data->file.seekg((std::streamoff)(opts->fasta_block * opts->fasta_idx));
         data->base = (uint64_t)(opts->fasta_block * opts->fasta_idx);
@@ -179,10 +200,12 @@ struct rw_fasta::writer::priv_data {
     int fd = -1;                 // regular file: positional writes
     uint64_t offset = 0;         // next free byte of the file
     std::ostream* out = nullptr; // stdout
+    bool gz = false;             // ".gz" output: every put() becomes a gzip member (members concatenate to one stream)
     unsigned int count = 0, excluded = 0;
     void write(const cseq& c);
     void put(const char* p, size_t n);
-    ~priv_data() { if (fd >= 0) ::close(fd); }
+    void put_raw(const char* p, size_t n);
+    ~priv_data();
 };
 
 static void pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
@@ -196,9 +219,55 @@ static void pwrite_all(int fd, const char* p, size_t n, uint64_t off) {
     }
 }
 
-void rw_fasta::writer::priv_data::put(const char* p, size_t n) {
+rw_fasta::writer::priv_data::~priv_data() {
+    if (fd < 0) return;
+    if (gz && offset == 0) {   // nothing was written: still a valid (empty) gzip stream
+        try { const std::string m = rw_fasta::writer::gzip_member("", 0); pwrite_all(fd, m.data(), m.size(), 0); } catch (...) {}
+    }
+    ::close(fd);
+}
+void rw_fasta::writer::priv_data::put_raw(const char* p, size_t n) {
     if (fd >= 0) { pwrite_all(fd, p, n, offset); offset += n; }
     else out->write(p, (std::streamsize)n);
+}
+void rw_fasta::writer::priv_data::put(const char* p, size_t n) {
+    if (!gz) { put_raw(p, n); return; }
+    const std::string m = rw_fasta::writer::gzip_member(p, n);
+    put_raw(m.data(), m.size());
+}
+
+// One complete gzip member holding p[0..n). A gzip file is any number of members back to back, so the command line
+// compresses the records of a batch on its render threads and the sink only appends the members in input order (the
+// reference pushes a single-threaded gzip_compressor in front of its file). Level: zlib's fastest unless
+// SINA_B200_GZIP_LEVEL says otherwise -- 50 kB alignment rows compress 12:1 at 180 MB/s per thread at level 1, 18:1 at
+// 37 MB/s at the default level 6.
+std::string rw_fasta::writer::gzip_member(const char* p, size_t n) {
+    static const int level = [] { const char* e = getenv("SINA_B200_GZIP_LEVEL"); const int l = e ? atoi(e) : 1; return l < 0 || l > 9 ? 1 : l; }();
+    z_stream z;
+    memset(&z, 0, sizeof(z));
+    if (deflateInit2(&z, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
+    std::string out;
+    out.resize(deflateBound(&z, (uLong)n) + 32);
+    size_t done = 0, produced = 0;
+    int rc = Z_OK;
+    do {   // avail_in is 32 bit: feed the input in pieces below 1 GiB
+        const size_t piece = std::min<size_t>(n - done, (size_t)1 << 30);
+        z.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(p + done));
+        z.avail_in = (uInt)piece;
+        done += piece;
+        do {
+            if (produced == out.size()) out.resize(out.size() * 2);
+            z.next_out = reinterpret_cast<Bytef*>(&out[produced]);
+            z.avail_out = (uInt)std::min<size_t>(out.size() - produced, (size_t)1 << 30);
+            const size_t before = z.avail_out;
+            rc = deflate(&z, done == n ? Z_FINISH : Z_NO_FLUSH);
+            produced += before - z.avail_out;
+            if (rc == Z_STREAM_ERROR) { deflateEnd(&z); throw std::runtime_error("deflate failed"); }
+        } while (z.avail_out == 0 || (done == n && rc != Z_STREAM_END));
+    } while (done < n);
+    deflateEnd(&z);
+    out.resize(produced);
+    return out;
 }
 
 rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
@@ -207,9 +276,16 @@ rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
     else {
         data->fd = ::open(outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (data->fd < 0) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
+        data->gz = is_gz(outfile);
     }
 }
-bool rw_fasta::writer::positional() const { return data->fd >= 0; }
+bool rw_fasta::writer::positional() const { return data->fd >= 0 && !data->gz; }   // compressed sizes are not known up front
+bool rw_fasta::writer::compressed() const { return data->gz; }
+void rw_fasta::writer::write_members(const std::string& members, unsigned int n_records, unsigned int n_excluded) {
+    data->put_raw(members.data(), members.size());
+    data->count += n_records;
+    data->excluded += n_excluded;
+}
 uint64_t rw_fasta::writer::reserve(uint64_t nbytes, unsigned int n_records, unsigned int n_excluded) {
     const uint64_t at = data->offset;
     data->offset += nbytes;

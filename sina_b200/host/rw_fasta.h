@@ -56,6 +56,11 @@ public:
         // --min-idty (src/rw_fasta.cpp:405-414): false for a sequence whose align_ident_slv is below the threshold
         static bool passes_min_idty(const cseq& c);
         void write_formatted(const std::string* record);
+        // ".gz" output (src/rw_fasta.cpp:358-360): records go out as gzip members. gzip_member() compresses any number of
+        // formatted records into one member (any thread), write_members() appends finished members in output order.
+        bool compressed() const;
+        static std::string gzip_member(const char* p, size_t n);
+        void write_members(const std::string& members, unsigned int n_records, unsigned int n_excluded);
         // positional output (regular files): the caller reserves byte ranges in record order and any thread fills them
         // with pwrite, so that writing 50 kB records is not bound to one thread. Not available on stdout.
         bool positional() const;

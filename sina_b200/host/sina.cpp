@@ -41,6 +41,8 @@ struct batch_t {
     std::vector<unsigned int> raw_seqno, raw_lineno;
     std::vector<std::string> records;   // FASTA record of every tray, rendered off the writer thread
     std::vector<char> has_record;
+    std::string members;                // ".gz" output: the batch's records as gzip members, compressed by the render pool
+    unsigned int n_rec = 0, n_exc = 0;
     uint64_t file_offset = 0;           // where the batch's records start in the output file (positional writer)
 };
 
@@ -271,6 +273,17 @@ int real_main(int argc, const char* const* argv) {
                         if (t.aligned_sequence && rw_fasta::writer::passes_min_idty(*t.aligned_sequence)) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
                     }
                 }
+                if (!failed && writer.compressed()) {   // one gzip member per 256 records, the records freed as they are packed
+                    std::string plain;
+                    for (size_t i0 = 0; i0 < b.trays.size(); i0 += 256) {
+                        plain.clear();
+                        for (size_t i = i0; i < std::min(b.trays.size(), i0 + 256); i++) {
+                            if (b.has_record[i]) { plain += b.records[i]; b.n_rec++; } else b.n_exc++;
+                            std::string().swap(b.records[i]);
+                        }
+                        if (!plain.empty()) b.members += rw_fasta::writer::gzip_member(plain.data(), plain.size());
+                    }
+                }
             } catch (std::exception& e) {
                 std::lock_guard<std::mutex> l(done_mu);
                 if (!failed) failure = e.what();
@@ -374,10 +387,11 @@ int real_main(int argc, const char* const* argv) {
             us_write += usec(t0w);
             continue;
         }
+        if (writer.compressed() && !failed) writer.write_members(b.members, b.n_rec, b.n_exc);
         for (size_t i = 0; i < b.trays.size(); i++) {
             tray& t = b.trays[i];
             if (!failed) {
-                writer.write_formatted(b.has_record[i] ? &b.records[i] : nullptr);
+                if (!writer.compressed()) writer.write_formatted(b.has_record[i] ? &b.records[i] : nullptr);
                 if (opts.show_log) std::cerr << "sequence_number: " << t.seqno << " sequence_identifier: "
                                              << t.input_sequence->getName() << " " << t.log.str() << std::endl;
             }

@@ -108,6 +108,37 @@ def test_cli_prealigned_passthrough_keeps_order(tmp_path):
         assert "".join(got[n]) == row
 
 
+def test_cli_gzip_in_and_out(tmp_path):
+    """file names ending in .gz are gzip streams on both sides (src/rw_fasta.cpp:200-202,358-360). --prealigned needs no
+    device: compressed input, compressed output (one gzip member per 256 records, written in input order), and the
+    same bytes as the uncompressed run once decompressed"""
+    import gzip, random
+    rnd = random.Random(9)
+    text = ""
+    for i in range(700):   # three members per batch of 600, two batches
+        text += ">g%04d some description\n%s\n" % (i, "".join(rnd.choice("ACGU------") for _ in range(300)))
+    with open(tmp_path / "in.fasta", "w") as f:
+        f.write(text)
+    with gzip.open(tmp_path / "in.fasta.gz", "wt") as f:
+        f.write(text)
+    plain, packed = tmp_path / "out.fasta", tmp_path / "out.fasta.gz"
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "in.fasta"), "-o", str(plain), "--batch-size", "600", "--line-length", "80"])
+    assert r.returncode == 0, r.stderr
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "in.fasta.gz"), "-o", str(packed), "--batch-size", "600", "--line-length", "80"])
+    assert r.returncode == 0, r.stderr
+    raw = open(packed, "rb").read()
+    assert raw[:2] == b"\x1f\x8b" and len(raw) < os.path.getsize(plain)
+    assert gzip.decompress(raw) == open(plain, "rb").read()
+    assert raw.count(b"\x1f\x8b\x08") >= 4                      # several members
+    # an empty input still gives a valid (empty) stream, and block-wise input refuses compressed files
+    open(tmp_path / "empty.fasta", "w").close()
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "empty.fasta"), "-o", str(tmp_path / "e.fasta.gz")])
+    assert r.returncode == 0, r.stderr
+    assert gzip.decompress(open(tmp_path / "e.fasta.gz", "rb").read()) == b""
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "in.fasta.gz"), "-o", "/dev/null", "--fasta-block", "1000", "--fasta-idx", "1"])
+    assert r.returncode != 0 and "compressed" in r.stderr
+
+
 def test_cli_fasta_block_and_idx(tmp_path):
     """--fasta-block B --fasta-idx i (src/rw_fasta.cpp:209-216,237-242): seek to byte B*i, skip to the next title line, read
     records until the previous one ended past byte B*(i+1). No GPU needed: --prealigned passes the sequences through."""
