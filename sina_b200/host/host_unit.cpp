@@ -287,6 +287,32 @@ static void test_fasta(const std::string& tmpdir) {
             EQUAL(b->getCseq(7).get_attr_string(fn_fullname), std::string("full name 7"));
             remove(db.c_str()); remove(dbz.c_str());
         }
+        // --add-relatives (src/rw_fasta.cpp:419-433) with --meta-fmt csv: the first N relatives not written before follow the
+        // sequence's record, the search result taking precedence over the alignment family
+        {
+            const std::string outp = tmpdir + "/host_unit_rel.fasta", csvp = tmpdir + "/host_unit_rel.csv";
+            cseq r1("ref1", "AC--GU"), r2("ref2", "A-C-GU"), r3("ref3", "ACG--U");
+            r2.set_attr<std::string>(fn_fullname, "second, reference");
+            rw_fasta::opts->copy_relatives = 2; rw_fasta::opts->fastameta = FASTA_META_CSV;
+            {
+                rw_fasta::writer wr(outp);
+                CHECK(!wr.positional());
+                tray a, b;
+                a.input_sequence = new cseq("qa", "ACGU"); a.aligned_sequence = new cseq("qa", "AC-G-U");
+                a.alignment_reference = new search::result_vector{{3.f, &r1}, {2.f, &r2}, {1.f, &r3}};
+                b.input_sequence = new cseq("qb", "ACGU"); b.aligned_sequence = new cseq("qb", "A-CG-U");
+                b.alignment_reference = new search::result_vector{{3.f, &r1}};
+                b.search_result = new search::result_vector{{0.9f, &r2}, {0.8f, &r3}, {0.7f, &r1}};
+                wr(a); wr(b);
+                a.destroy(); b.destroy();
+            }
+            rw_fasta::opts->copy_relatives = 0; rw_fasta::opts->fastameta = FASTA_META_NONE;
+            std::ifstream f1(outp); std::stringstream s1; s1 << f1.rdbuf();
+            EQUAL(s1.str(), std::string(">qa\nAC-G-U\n>ref1\nAC--GU\n>ref2 second, reference\nA-C-GU\n>qb\nA-CG-U\n>ref3\nACG--U\n"));
+            std::ifstream f2(csvp, std::ios::binary); std::stringstream s2; s2 << f2.rdbuf();
+            EQUAL(s2.str(), std::string("name\r\nqa\r\nref1\r\nref2,\"second, reference\"\r\nqb\r\nref3\r\n"));
+            remove(outp.c_str()); remove(csvp.c_str());
+        }
         const std::string one = rw_fasta::writer::gzip_member("", 0);   // an empty member is a valid stream
         CHECK(one.size() >= 18 && (unsigned char)one[0] == 0x1f && (unsigned char)one[1] == 0x8b);
     }

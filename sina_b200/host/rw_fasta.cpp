@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <fstream>
 #include <iostream>
+#include <unordered_set>
 
 namespace sina {
 
@@ -24,9 +25,10 @@ void rw_fasta::get_options_description(po::options_description& main, po::option
         if (v == "none") opts->fastameta = FASTA_META_NONE;
         else if (v == "header") opts->fastameta = FASTA_META_HEADER;
         else if (v == "comment") opts->fastameta = FASTA_META_COMMENT;
-        else if (v == "csv") throw std::logic_error("--meta-fmt csv is not supported by sina_b200");
+        else if (v == "csv") opts->fastameta = FASTA_META_CSV;
         else throw std::logic_error("Illegal value for meta-fmt");
     });
+    main.value<unsigned int>("add-relatives", &opts->copy_relatives, 0u, "add the ARG nearest relatives for each sequence to output");
     po::options_description od("FASTA I/O");
     od.value<int>("line-length", &opts->line_length, 0, "wrap output sequence (unlimited)");
     od.value<float>("min-idty", &opts->min_idty, 0.f, "only write sequences with align_idty_slv > X, implies calc-idty");
@@ -201,6 +203,9 @@ struct rw_fasta::writer::priv_data {
     uint64_t offset = 0;         // next free byte of the file
     std::ostream* out = nullptr; // stdout
     bool gz = false;             // ".gz" output: every put() becomes a gzip member (members concatenate to one stream)
+    std::ofstream out_csv;       // --meta-fmt csv
+    std::unordered_set<std::string> relatives_written;   // --add-relatives
+    bool csv_started = false;
     unsigned int count = 0, excluded = 0;
     void write(const cseq& c);
     void put(const char* p, size_t n);
@@ -278,8 +283,41 @@ rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
         if (data->fd < 0) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
         data->gz = is_gz(outfile);
     }
+    if (opts->fastameta == FASTA_META_CSV) {   // the output name with its extension replaced (src/rw_fasta.cpp:362-372)
+        std::string csv = outfile;
+        const size_t slash = csv.find_last_of('/'), dot = csv.find_last_of('.');
+        if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) csv.erase(dot);
+        csv += ".csv";
+        data->out_csv.open(csv, std::ios::binary);
+        if (!data->out_csv) throw std::runtime_error("Unable to open file \"" + csv + "\" for writing.");
+    }
 }
-bool rw_fasta::writer::positional() const { return data->fd >= 0 && !data->gz; }   // compressed sizes are not known up front
+
+// src/rw_fasta.cpp:379-392
+static std::string escape_string(const std::string& in) {
+    if (in.find_first_of("\",\r\n") == std::string::npos) return in;
+    std::string o = "\"";
+    for (const char ch : in) { if (ch == '"') o += "\"\""; else o.push_back(ch); }
+    o += "\"";
+    return o;
+}
+void rw_fasta::writer::write_csv(const cseq& c) {
+    if (opts->fastameta != FASTA_META_CSV) return;
+    std::string o;
+    if (!data->csv_started) {   // column names from the first record written
+        data->csv_started = true;
+        o = "name";
+        for (const auto& ap : c.get_attrs()) if (ap.first != fn_family) { o += ","; o += escape_string(ap.first); }
+        o += "\r\n";
+    }
+    o += c.getName();
+    for (const auto& ap : c.get_attrs()) if (ap.first != fn_family) { o += ","; o += escape_string(ap.second); }
+    o += "\r\n";
+    data->out_csv.write(o.data(), (std::streamsize)o.size());
+}
+bool rw_fasta::writer::positional() const {   // compressed sizes are not known up front; the csv lines go out in order
+    return data->fd >= 0 && !data->gz && opts->fastameta != FASTA_META_CSV && opts->copy_relatives == 0;   // ... and so do the relatives
+}
 bool rw_fasta::writer::compressed() const { return data->gz; }
 void rw_fasta::writer::write_members(const std::string& members, unsigned int n_records, unsigned int n_excluded) {
     data->put_raw(members.data(), members.size());
@@ -405,8 +443,24 @@ tray rw_fasta::writer::operator()(tray t) {
         ++data->excluded;
         return t;
     }
+    write_csv(*t.aligned_sequence);
     data->write(*t.aligned_sequence);
+    write_relatives(t);
     return t;
+}
+
+void rw_fasta::writer::write_relatives(const tray& t) {
+    if (opts->copy_relatives == 0) return;
+    const search::result_vector* relatives = t.search_result != nullptr ? t.search_result : t.alignment_reference;
+    if (relatives == nullptr) return;
+    int i = (int)opts->copy_relatives;
+    for (const auto& item : *relatives) {
+        if (data->relatives_written.insert(item.sequence->getName()).second) {
+            write_csv(*item.sequence);
+            data->write(*item.sequence);
+        }
+        if (--i == 0) break;
+    }
 }
 
 }  // namespace sina

@@ -11,7 +11,7 @@
 
 namespace sina {
 
-enum FASTA_META_TYPE { FASTA_META_NONE = 0, FASTA_META_HEADER = 1, FASTA_META_COMMENT = 2 };
+enum FASTA_META_TYPE { FASTA_META_NONE = 0, FASTA_META_HEADER = 1, FASTA_META_COMMENT = 2, FASTA_META_CSV = 3 };
 
 class rw_fasta {
 public:
@@ -21,6 +21,7 @@ public:
         float min_idty = 0.f;              // --min-idty: only sequences with align_ident_slv above it are written
         long fasta_block = 0, fasta_idx = 0;   // --fasta-block B --fasta-idx i: the records starting in bytes (B*i, B*(i+1)] of the input
         bool out_dots = false, out_dna = false;
+        unsigned int copy_relatives = 0;   // --add-relatives N: the N nearest relatives of every sequence are written too
     };
     static options* opts;
     static void get_options_description(po::options_description& main, po::options_description& adv);
@@ -61,6 +62,12 @@ public:
         bool compressed() const;
         static std::string gzip_member(const char* p, size_t n);
         void write_members(const std::string& members, unsigned int n_records, unsigned int n_excluded);
+        // --meta-fmt csv (src/rw_fasta.cpp:362-372,484-515): the attributes of every written record as a line of
+        // <outfile>.csv, the column names from the first record; to be called in output order for the records written
+        void write_csv(const cseq& c);
+        // --add-relatives (src/rw_fasta.cpp:419-433): the first N of the tray's search result (or, without one, of its
+        // alignment family) that have not been written yet, behind the sequence's own record; in output order
+        void write_relatives(const tray& t);
         // positional output (regular files): the caller reserves byte ranges in record order and any thread fills them
         // with pwrite, so that writing 50 kB records is not bound to one thread. Not available on stdout.
         bool positional() const;

@@ -94,7 +94,6 @@ int real_main(int argc, const char* const* argv) {
     main_od.flag("help-all,H", &help_all, "show full help (long)");
     main_od.value<std::string>("in,i", &opts.in, "-", "input file (fasta)");
     main_od.value<std::string>("out,o", &opts.out, "-", "output file (fasta)");
-    main_od.unsupported("add-relatives", true, "writing relatives next to the query");
     main_od.flag("search,S", &opts.do_search, "enable search stage");
     main_od.flag("prealigned,P", &opts.skip_align, "skip alignment stage");
     main_od.value<unsigned int>("threads,p", &opts.threads, 0u, "accepted for compatibility (the GPU path batches instead)");
@@ -142,6 +141,8 @@ int real_main(int argc, const char* const* argv) {
     rw_fasta::reader reader(opts.in);
     rw_fasta::writer writer(opts.out);
     const bool direct = writer.positional();   // a regular file: records are written at reserved offsets by a pool
+    // ".gz": the render pool compresses whole runs of records (relatives are interleaved by the sink, one member each)
+    const bool packed_members = writer.compressed() && rw_fasta::opts->copy_relatives == 0;
 
     // stage instances, one pair per GPU (each builds / shares the device's replica of the index)
     std::vector<std::unique_ptr<famfinder>> ff;
@@ -273,7 +274,7 @@ int real_main(int argc, const char* const* argv) {
                         if (t.aligned_sequence && rw_fasta::writer::passes_min_idty(*t.aligned_sequence)) { b.records[i] = rw_fasta::writer::format(*t.aligned_sequence); b.has_record[i] = 1; }
                     }
                 }
-                if (!failed && writer.compressed()) {   // one gzip member per 256 records, the records freed as they are packed
+                if (!failed && packed_members) {   // one gzip member per 256 records, the records freed as they are packed
                     std::string plain;
                     for (size_t i0 = 0; i0 < b.trays.size(); i0 += 256) {
                         plain.clear();
@@ -387,11 +388,13 @@ int real_main(int argc, const char* const* argv) {
             us_write += usec(t0w);
             continue;
         }
-        if (writer.compressed() && !failed) writer.write_members(b.members, b.n_rec, b.n_exc);
+        if (packed_members && !failed) writer.write_members(b.members, b.n_rec, b.n_exc);
         for (size_t i = 0; i < b.trays.size(); i++) {
             tray& t = b.trays[i];
             if (!failed) {
-                if (!writer.compressed()) writer.write_formatted(b.has_record[i] ? &b.records[i] : nullptr);
+                if (!packed_members) writer.write_formatted(b.has_record[i] ? &b.records[i] : nullptr);
+                if (b.has_record[i]) writer.write_csv(*t.aligned_sequence);   // --meta-fmt csv
+                if (b.has_record[i]) writer.write_relatives(t);                // --add-relatives
                 if (opts.show_log) std::cerr << "sequence_number: " << t.seqno << " sequence_identifier: "
                                              << t.input_sequence->getName() << " " << t.log.str() << std::endl;
             }

@@ -139,6 +139,21 @@ def test_cli_gzip_in_and_out(tmp_path):
     assert r.returncode != 0 and "compressed" in r.stderr
 
 
+def test_cli_meta_fmt_csv(tmp_path):
+    """--meta-fmt csv (src/rw_fasta.cpp:362-372,484-515): plain FASTA headers, the attributes in <out>.csv with CRLF lines,
+    the column names taken from the first record written, values with commas / quotes escaped (:379-392)"""
+    with open(tmp_path / "in.fasta", "w") as f:
+        f.write(">a desc A\n; turn = none\n; align_quality_slv = 97\nAC--GU\n>b with, comma\n--ACGU\n>c say \"hi\"\n; turn = all\nAC-G-U\n")
+    out = tmp_path / "res.fasta"
+    r = run(["sina", "--prealigned", "--meta-fmt", "csv", "-i", str(tmp_path / "in.fasta"), "-o", str(out), "--batch-size", "2"])
+    assert r.returncode == 0, r.stderr
+    assert open(out).read() == ">a desc A\nAC--GU\n>b with, comma\n--ACGU\n>c say \"hi\"\nAC-G-U\n"
+    assert open(tmp_path / "res.csv", "rb").read() == (b"name,align_quality_slv,full_name,turn\r\n"
+                                                       b"a,97,desc A,none\r\n"
+                                                       b"b,\"with, comma\"\r\n"
+                                                       b"c,\"say \"\"hi\"\"\",all\r\n")
+
+
 def test_cli_fasta_block_and_idx(tmp_path):
     """--fasta-block B --fasta-idx i (src/rw_fasta.cpp:209-216,237-242): seek to byte B*i, skip to the next title line, read
     records until the previous one ended past byte B*(i+1). No GPU needed: --prealigned passes the sequences through."""
