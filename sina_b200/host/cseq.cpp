@@ -52,22 +52,32 @@ cseq::cseq(const char* n, const char* data) : name(n ? n : "") {
     if (data) append(data);
 }
 
-cseq& cseq::append(const char* str) {
-    for (; *str; ++str) {
-        const char c = *str;
-        if (c == ' ' || c == '\t' || c == '\n' || c == '\r') continue;
-        if (c != '-' && c != '.') bases.emplace_back(alignment_width, base_iupac::from_char((unsigned char)c));
-        alignment_width++;
-    }
-    return *this;
-}
+cseq& cseq::append(const char* str) { return append(str, strlen(str)); }
 
+// src/cseq.cpp:63-77: blanks are skipped, '-' and '.' advance the column, anything else is a base (bad characters throw).
+// Runs of '-' are skipped eight at a time: an aligned row is 97 % gaps, and reference databases and --prealigned input
+// come as such rows.
 cseq& cseq::append(const char* str, size_t n) {
-    bases.reserve(bases.size() + n);
-    for (size_t i = 0; i < n; i++) {
+    bases.reserve(bases.size() + std::min<size_t>(n, 2048));
+    size_t i = 0;
+    while (i < n) {
         const char c = str[i];
+        if (c == '-') {
+            size_t j = i + 1;
+            while (j + 8 <= n) {
+                uint64_t w;
+                memcpy(&w, str + j, 8);
+                if (w != 0x2d2d2d2d2d2d2d2dULL) break;
+                j += 8;
+            }
+            while (j < n && str[j] == '-') j++;
+            alignment_width += (uint32_t)(j - i);
+            i = j;
+            continue;
+        }
+        i++;
         if (c == ' ' || c == '\t' || c == '\n' || c == '\r') continue;
-        if (c != '-' && c != '.') bases.emplace_back(alignment_width, base_iupac::from_char((unsigned char)c));
+        if (c != '.') bases.emplace_back(alignment_width, base_iupac::from_char((unsigned char)c));
         alignment_width++;
     }
     return *this;

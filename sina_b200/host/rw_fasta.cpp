@@ -11,6 +11,7 @@
 #include <fstream>
 #include <iostream>
 #include <unordered_set>
+#include <vector>
 
 namespace sina {
 
@@ -45,34 +46,35 @@ void rw_fasta::validate_vm(po::variables_map&, po::options_description&) {}
 // into a cseq is a separate, thread-safe step (parse_record), so that the command line can leave it to its worker
 // threads: one thread parsing 1.5 kB records reaches about 130 k sequences/s, eight GPUs take five times that.
 struct rw_fasta::reader::priv_data {
-    std::ifstream file;
-    std::istream* in = nullptr;
+    int fd = -1;                 // file or stdin (0): read() into buf, no stream layer in between
+    bool own_fd = false;
     gzFile gz = nullptr;         // ".gz" input
-    ~priv_data() { if (gz) gzclose(gz); }
     std::string filename;
-    std::string buf;
-    size_t pos = 0;
+    std::vector<char> buf;       // [pos, size) = bytes not yet handed out
+    size_t pos = 0, size = 0;
     uint64_t base = 0;           // file offset of buf[0]
     bool eof = false;
     unsigned int seqno = 0, lineno = 1, skipped = 0;
+    ~priv_data() { if (gz) gzclose(gz); if (own_fd && fd >= 0) ::close(fd); }
     bool refill() {   // drop the consumed part, read another block; false when nothing was added
         if (eof) return false;
-        buf.erase(0, pos);
-        base += pos;
-        pos = 0;
-        const size_t old = buf.size(), block = 4u << 20;
-        buf.resize(old + block);
+        const size_t block = 4u << 20;
+        if (pos > 0) { memmove(buf.data(), buf.data() + pos, size - pos); base += pos; size -= pos; pos = 0; }
+        if (buf.size() < size + block) buf.resize(std::max(buf.size() * 2, size + block));   // a record longer than the buffer
         size_t got = 0;
-        if (gz) {
-            const int n = gzread(gz, &buf[old], (unsigned)block);
-            if (n < 0) throw std::runtime_error("Error reading compressed file " + filename);
-            got = (size_t)n;
-        } else {
-            in->read(&buf[old], (std::streamsize)block);
-            got = (size_t)in->gcount();
+        while (got < block) {   // a pipe hands out less than asked for: keep the blocks large
+            long n;
+            if (gz) {
+                n = gzread(gz, buf.data() + size + got, (unsigned)(block - got));
+                if (n < 0) throw std::runtime_error("Error reading compressed file " + filename);
+            } else {
+                n = ::read(fd, buf.data() + size + got, block - got);
+                if (n < 0) { if (errno == EINTR) continue; throw std::runtime_error("Error reading file " + filename + ": " + strerror(errno)); }
+            }
+            if (n == 0) { eof = true; break; }
+            got += (size_t)n;
         }
-        buf.resize(old + got);
-        if (got < block) eof = true;
+        size += got;
         return got > 0;
     }
 };
@@ -80,7 +82,7 @@ struct rw_fasta::reader::priv_data {
 rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
     if (!opts) opts = new options();
     data->filename = infile;
-    if (infile == "-") data->in = &std::cin;
+    if (infile == "-") data->fd = 0;
     else if (is_gz(infile)) {
         data->gz = gzopen(infile.c_str(), "rb");
         if (!data->gz) throw std::runtime_error("Unable to open file " + infile + " for reading.");
@@ -88,14 +90,15 @@ rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
         // (the reference seeks its filter chain here, which a gzip stream cannot do)
         if (opts->fasta_block > 0) throw std::logic_error("Cannot use --fasta-idx on compressed input");
     } else {
-        data->file.open(infile, std::ios::binary);
-        if (!data->file) throw std::runtime_error("Unable to open file " + infile + " for reading.");
-        data->in = &data->file;
+        data->fd = ::open(infile.c_str(), O_RDONLY);
+        if (data->fd < 0) throw std::runtime_error("Unable to open file " + infile + " for reading.");
+        data->own_fd = true;
     }
     // --fasta-block / --fasta-idx (src/rw_fasta.cpp:209-216,237-242): start at byte block * idx, at the next title line
     if (opts->fasta_block > 0 && !data->gz) {
         if (infile == "-") throw std::logic_error("Cannot use --fasta-idx when input is piped");
-        data->file.seekg((std::streamoff)(opts->fasta_block * opts->fasta_idx));
+        if (::lseek(data->fd, (off_t)(opts->fasta_block * opts->fasta_idx), SEEK_SET) < 0)
+            throw std::runtime_error("Unable to seek in file " + infile);
         data->base = (uint64_t)(opts->fasta_block * opts->fasta_idx);
     }
 }
@@ -110,35 +113,41 @@ bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, uns
     if (opts->fasta_block > 0 && d.base + d.pos > (uint64_t)(opts->fasta_block * (opts->fasta_idx + 1))) return false;
     // skip to the next title line
     for (;;) {
-        if (d.pos >= d.buf.size() && !d.refill()) return false;
+        if (d.pos >= d.size && !d.refill()) return false;
         if (d.buf[d.pos] == '>') break;
-        const void* nl = memchr(d.buf.data() + d.pos, '\n', d.buf.size() - d.pos);
+        const void* nl = memchr(d.buf.data() + d.pos, '\n', d.size - d.pos);
         if (nl) { d.pos = (size_t)((const char*)nl - d.buf.data()) + 1; d.lineno++; }
-        else d.pos = d.buf.size();
+        else d.pos = d.size;
     }
-    // the record ends before the next "\n>"
-    size_t from = d.pos + 1;
+    // the record ends behind the newline that a '>' follows, or with the input: one memchr per line, which also
+    // counts the lines (the scan position is kept relative to the record's start: a refill moves that to 0)
+    size_t scan = 1, end = 0;
+    unsigned int lines = 0;
     for (;;) {
-        const char* base = d.buf.data();
-        const void* hit = from < d.buf.size() ? memmem(base + from - 1, d.buf.size() - from + 1, "\n>", 2) : nullptr;
-        if (hit) {
-            const size_t end = (size_t)((const char*)hit - base) + 1;   // keeps the newline
-            record.assign(base + d.pos, end - d.pos);
-            d.pos = end;
-            break;
+        const char* rec = d.buf.data() + d.pos;
+        const size_t avail = d.size - d.pos;
+        const void* nl = scan < avail ? memchr(rec + scan, '\n', avail - scan) : nullptr;
+        if (nl) {
+            const size_t at = (size_t)((const char*)nl - rec);
+            if (at + 1 < avail) {
+                lines++;
+                scan = at + 1;
+                if (rec[at + 1] == '>') { end = at + 1; break; }
+                continue;
+            }
+            if (d.eof) { lines++; end = avail; break; }
+            scan = at;                 // the byte behind this newline is not here yet: look at it again after the refill
+        } else {
+            if (d.eof) { end = avail; break; }
+            scan = avail;
         }
-        if (d.eof) {
-            record.assign(base + d.pos, d.buf.size() - d.pos);
-            d.pos = d.buf.size();
-            break;
-        }
-        const size_t keep = d.buf.size() - d.pos;   // refill moves the record's start to 0
         d.refill();
-        from = keep > 0 ? keep : 1;
     }
+    record.assign(d.buf.data() + d.pos, end);
+    d.pos += end;
     seqno = ++d.seqno;
     lineno = d.lineno;
-    for (const char c : record) d.lineno += c == '\n';
+    d.lineno += lines;
     return true;
 }
 

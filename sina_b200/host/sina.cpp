@@ -335,11 +335,12 @@ int real_main(int argc, const char* const* argv) {
     // is on the GPU the others pack queries / build the result sequences of theirs (B200 box, 1 GPU, 160k queries:
     // 3 threads 44.8k seq/s, 6 threads 49.1k); never more threads than the cores left beside the output pool
     unsigned int wpg = 1u;
-    if (do_align || opts.do_search) {
+    {
         const unsigned int spare = hw > n_write + 2 ? hw - n_write - 2 : 2;
-        wpg = std::max(2u, std::min(6u, spare / std::max(1u, ngpu)));
+        if (do_align || opts.do_search) wpg = std::max(2u, std::min(6u, spare / std::max(1u, ngpu)));
+        else wpg = std::max(1u, std::min(4u, spare));   // --prealigned without --search: the workers only parse
     }
-    if ((do_align || opts.do_search) && getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
+    if (getenv("SINA_B200_WORKERS")) wpg = std::max(1, atoi(getenv("SINA_B200_WORKERS")));
     for (unsigned int d = 0; d < std::max(1u, ngpu); d++)
         for (unsigned int k = 0; k < wpg; k++) workers.emplace_back(work, d);
     const unsigned int n_render = direct ? 0u : std::max(2u, std::min(16u, hw / 2));
