@@ -287,6 +287,43 @@ static void test_fasta(const std::string& tmpdir) {
             EQUAL(b->getCseq(7).get_attr_string(fn_fullname), std::string("full name 7"));
             remove(db.c_str()); remove(dbz.c_str());
         }
+        // the loader cuts the file into chunks of 64 records parsed on several threads: order and content survive, comment
+        // lines are skipped wherever they stand, a bad character fails the load with its line number, an empty file too
+        {
+            const std::string db = tmpdir + "/host_unit_db2.fasta", bad = tmpdir + "/host_unit_db3.fasta", none = tmpdir + "/host_unit_db4.fasta";
+            std::vector<std::string> rows;
+            {
+                std::ofstream f(db, std::ios::binary);
+                f << "text before the first record\n";
+                for (int i = 0; i < 1500; i++) {
+                    std::string row(300 + (size_t)(i % 50), '-');
+                    for (size_t j = 0; j < row.size(); j += 3 + (size_t)(i % 4)) row[j] = "ACGUacguN"[(i + (int)j) % 9];
+                    rows.push_back(row);
+                    f << ">d" << i << (i % 5 ? " described" : "") << (i % 2 ? "\r\n" : "\n");
+                    if (i % 7 == 0) f << "; a comment\n";
+                    f << row.substr(0, 100) << "\n" << (i % 11 == 0 ? "; another one\n" : "") << row.substr(100) << (i % 2 ? "\r\n" : "\n") << (i % 13 == 0 ? "\n" : "");
+                }
+            }
+            reference_db* d = reference_db::getDB(db);
+            EQUAL(d->getSeqCount(), 1500u);
+            bool same = true;
+            for (uint32_t i = 0; i < 1500 && same; i++) {
+                const cseq& c = d->getCseq(i);
+                std::string want = rows[i];
+                want.resize(d->getAlignmentWidth(), '-');   // rows are padded to the database's width
+                same = c.getName() == "d" + std::to_string(i) && c.getAligned(true) == want &&
+                       c.get_attr_string(fn_fullname) == (i % 5 ? "described" : "");
+            }
+            CHECK(same);
+            { std::ofstream f(bad); f << ">ok\nACGU\n>broken\nAC\nGXU\n"; }
+            bool threw = false;
+            try { reference_db::getDB(bad); } catch (std::runtime_error& e) { threw = std::string(e.what()).find("line 5") != std::string::npos && std::string(e.what()).find("'X'") != std::string::npos; }
+            CHECK(threw);
+            { std::ofstream f(none); f << "no records here\n"; }
+            THROWS(reference_db::getDB(none), std::runtime_error);
+            THROWS(reference_db::getDB(tmpdir + "/host_unit_does_not_exist.fasta"), std::runtime_error);
+            remove(db.c_str()); remove(bad.c_str()); remove(none.c_str());
+        }
         // --add-relatives (src/rw_fasta.cpp:419-433) with --meta-fmt csv: the first N relatives not written before follow the
         // sequence's record, the search result taking precedence over the alignment family
         {

@@ -1,13 +1,15 @@
 #include "reference_db.h"
 
-#include <zlib.h>
-
+#include "rw_fasta.h"
 #include "sidx.h"
 
-#include <fstream>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace sina {
@@ -57,55 +59,108 @@ reference_db* reference_db::getDB(const std::string& path) {
         auto it = g_dbs.find(path);
         if (it != g_dbs.end()) return it->second.get();
     }
-    // plain or gzip-compressed aligned FASTA (SILVA ships its alignments as .fasta.gz)
-    const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
-    std::ifstream in;
-    gzFile zin = nullptr;
-    if (gz) {
-        zin = gzopen(path.c_str(), "rb");
-        if (zin) gzbuffer(zin, 1u << 20);
-    } else {
-        in.open(path);
-    }
-    if (gz ? zin == nullptr : !in) throw std::runtime_error("Unable to open reference database '" + path + "'");
-    struct zcloser { gzFile f; ~zcloser() { if (f) gzclose(f); } } zguard{zin};
-    std::vector<char> zbuf(gz ? 1u << 16 : 0);
-    auto next_line = [&](std::string& line) -> bool {
-        if (!gz) return (bool)std::getline(in, line);
-        line.clear();
-        for (;;) {   // gzgets stops at the buffer's end or behind a newline
-            if (!gzgets(zin, zbuf.data(), (int)zbuf.size())) {
-                int err = 0;
-                gzerror(zin, &err);
-                if (err != Z_OK && err != Z_STREAM_END) throw std::runtime_error("Error reading compressed reference database '" + path + "'");
-                return !line.empty();
+    // plain or gzip-compressed aligned FASTA (SILVA ships its alignments as .fasta.gz). One thread cuts the file into
+    // records (rw_fasta's block reader), a few threads turn them into sequences: a 50 000-column row is 50 kB of text
+    // and a 500 000-row database 25 GB of it.
+    // a chunk = the text of up to per_chunk records back to back; chunks are recycled, so the reader copies into warm
+    // pages instead of faulting in 25 GB of fresh ones
+    struct chunk_t { size_t first = 0; std::string text; std::vector<size_t> end; std::vector<unsigned int> lineno; };
+    std::vector<chunk_t> spare;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_room;
+    std::deque<chunk_t> todo;
+    bool closed = false;
+    std::string failure;
+    std::vector<std::vector<cseq>> parts;   // by chunk number
+    const size_t per_chunk = 64;
+    auto parse = [&](const std::string& rec, size_t at, const size_t stop, unsigned int lineno, cseq& c) {   // one record: title, sequence lines
+        bool title = true;
+        while (at < stop) {
+            const void* nl = memchr(rec.data() + at, '\n', stop - at);
+            size_t e = nl ? (size_t)((const char*)nl - rec.data()) : stop;
+            const size_t next = e + 1;
+            if (e > at && rec[e - 1] == '\r') e--;
+            if (title) {
+                const std::string line(rec, at, e - at);
+                const auto blank = line.find_first_of(" \t");
+                c.setName(line.substr(1, blank == std::string::npos ? std::string::npos : blank - 1));
+                if (blank != std::string::npos) c.set_attr<std::string>(fn_fullname, line.substr(blank + 1));
+                title = false;
+            } else if (e > at && rec[at] != ';') {
+                try {
+                    c.append(rec.data() + at, e - at);
+                } catch (base_iupac::bad_character_exception& ex) {
+                    throw std::runtime_error("reference database '" + path + "' line " + std::to_string(lineno) +
+                                             ": character '" + std::string(1, (char)ex.character) + "' is not IUPAC");
+                }
             }
-            line += zbuf.data();
-            if (!line.empty() && line.back() == '\n') { line.pop_back(); return true; }
+            at = next;
+            lineno++;
         }
     };
-    std::vector<cseq> v;
-    std::string line;
-    cseq* cur = nullptr;
-    size_t lineno = 0;
-    while (next_line(line)) {
-        lineno++;
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty() || line[0] == ';') continue;
-        if (line[0] == '>') {
-            const auto blank = line.find_first_of(" \t");
-            v.emplace_back(line.substr(1, blank == std::string::npos ? std::string::npos : blank - 1).c_str());
-            cur = &v.back();
-            if (blank != std::string::npos) cur->set_attr<std::string>(fn_fullname, line.substr(blank + 1));
-        } else if (cur) {
-            try {
-                cur->append(line);
-            } catch (base_iupac::bad_character_exception& e) {
-                throw std::runtime_error("reference database '" + path + "' line " + std::to_string(lineno) +
-                                         ": character '" + std::string(1, (char)e.character) + "' is not IUPAC");
+    auto worker = [&] {
+        for (;;) {
+            chunk_t ch;
+            {
+                std::unique_lock<std::mutex> l(mu);
+                cv_work.wait(l, [&] { return !todo.empty() || closed; });
+                if (todo.empty()) return;
+                ch = std::move(todo.front());
+                todo.pop_front();
+                cv_room.notify_one();
             }
+            std::vector<cseq> out(ch.end.size());
+            try {
+                for (size_t i = 0; i < ch.end.size(); i++) parse(ch.text, i ? ch.end[i - 1] : 0, ch.end[i], ch.lineno[i], out[i]);
+            } catch (std::exception& e) {
+                std::lock_guard<std::mutex> l(mu);
+                if (failure.empty()) failure = e.what();
+            }
+            std::lock_guard<std::mutex> l(mu);
+            const size_t no = ch.first / per_chunk;
+            if (parts.size() <= no) parts.resize(no + 1);
+            parts[no] = std::move(out);
+            ch.text.clear(); ch.end.clear(); ch.lineno.clear();   // capacity kept
+            spare.push_back(std::move(ch));
         }
+    };
+    std::vector<std::thread> pool;
+    const unsigned int n_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    for (unsigned int i = 0; i < n_threads; i++) pool.emplace_back(worker);
+    size_t n_records = 0;
+    try {
+        rw_fasta::reader rd(path, true);   // whole file, whatever --fasta-block says about the query file
+        chunk_t ch;
+        unsigned int seqno = 0, lineno = 0;
+        auto push = [&] {
+            std::unique_lock<std::mutex> l(mu);
+            cv_room.wait(l, [&] { return todo.size() < 2 * n_threads; });
+            todo.push_back(std::move(ch));
+            cv_work.notify_one();
+            if (spare.empty()) ch = chunk_t();
+            else { ch = std::move(spare.back()); spare.pop_back(); }
+        };
+        for (;;) {
+            const bool more = rd.next_record(ch.text, seqno, lineno, true);
+            if (!more) break;
+            if (ch.end.empty()) ch.first = n_records;
+            ch.end.push_back(ch.text.size());
+            ch.lineno.push_back(lineno);
+            n_records++;
+            if (ch.end.size() == per_chunk) push();
+        }
+        if (!ch.end.empty()) push();
+    } catch (std::exception& e) {
+        std::lock_guard<std::mutex> l(mu);
+        if (failure.empty()) failure = std::string(e.what()).find("Unable to open") == 0 ? "Unable to open reference database '" + path + "'" : e.what();
     }
+    { std::lock_guard<std::mutex> l(mu); closed = true; }
+    cv_work.notify_all();
+    for (auto& t : pool) t.join();
+    if (!failure.empty()) throw std::runtime_error(failure);
+    std::vector<cseq> v;
+    v.reserve(n_records);
+    for (auto& part : parts) for (auto& c : part) v.push_back(std::move(c));
     if (v.empty()) throw std::runtime_error("reference database '" + path + "' holds no sequences");
     // Index order. In the reference the id of a sequence is its position in query_arb::getSequenceNames()
     // (src/kmer_search.cpp:248-249), which a .sidx index cache records (:289-291). When `<db>.sidx` exists and lists

@@ -54,6 +54,7 @@ struct rw_fasta::reader::priv_data {
     size_t pos = 0, size = 0;
     uint64_t base = 0;           // file offset of buf[0]
     bool eof = false;
+    long block = 0, block_idx = 0;   // --fasta-block / --fasta-idx as they apply to this file
     unsigned int seqno = 0, lineno = 1, skipped = 0;
     ~priv_data() { if (gz) gzclose(gz); if (own_fd && fd >= 0) ::close(fd); }
     bool refill() {   // drop the consumed part, read another block; false when nothing was added
@@ -79,27 +80,28 @@ struct rw_fasta::reader::priv_data {
     }
 };
 
-rw_fasta::reader::reader(const std::string& infile) : data(new priv_data) {
+rw_fasta::reader::reader(const std::string& infile, bool whole_file) : data(new priv_data) {
     if (!opts) opts = new options();
     data->filename = infile;
+    if (!whole_file) { data->block = opts->fasta_block; data->block_idx = opts->fasta_idx; }
     if (infile == "-") data->fd = 0;
     else if (is_gz(infile)) {
         data->gz = gzopen(infile.c_str(), "rb");
         if (!data->gz) throw std::runtime_error("Unable to open file " + infile + " for reading.");
         gzbuffer(data->gz, 1u << 20);
         // (the reference seeks its filter chain here, which a gzip stream cannot do)
-        if (opts->fasta_block > 0) throw std::logic_error("Cannot use --fasta-idx on compressed input");
+        if (data->block > 0) throw std::logic_error("Cannot use --fasta-idx on compressed input");
     } else {
         data->fd = ::open(infile.c_str(), O_RDONLY);
         if (data->fd < 0) throw std::runtime_error("Unable to open file " + infile + " for reading.");
         data->own_fd = true;
     }
     // --fasta-block / --fasta-idx (src/rw_fasta.cpp:209-216,237-242): start at byte block * idx, at the next title line
-    if (opts->fasta_block > 0 && !data->gz) {
+    if (data->block > 0 && !data->gz) {
         if (infile == "-") throw std::logic_error("Cannot use --fasta-idx when input is piped");
-        if (::lseek(data->fd, (off_t)(opts->fasta_block * opts->fasta_idx), SEEK_SET) < 0)
+        if (::lseek(data->fd, (off_t)(data->block * data->block_idx), SEEK_SET) < 0)
             throw std::runtime_error("Unable to seek in file " + infile);
-        data->base = (uint64_t)(opts->fasta_block * opts->fasta_idx);
+        data->base = (uint64_t)(data->block * data->block_idx);
     }
 }
 rw_fasta::reader::~reader() = default;
@@ -107,10 +109,10 @@ unsigned int rw_fasta::reader::skipped() const { return data->skipped; }
 const std::string& rw_fasta::reader::filename() const { return data->filename; }
 void rw_fasta::reader::count_skipped() { data->skipped++; }
 
-bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, unsigned int& lineno) {
+bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, unsigned int& lineno, bool append) {
     priv_data& d = *data;
     // block-wise input: stop once the previous sequence ended past the block (the reference tests tellg() here)
-    if (opts->fasta_block > 0 && d.base + d.pos > (uint64_t)(opts->fasta_block * (opts->fasta_idx + 1))) return false;
+    if (d.block > 0 && d.base + d.pos > (uint64_t)(d.block * (d.block_idx + 1))) return false;
     // skip to the next title line
     for (;;) {
         if (d.pos >= d.size && !d.refill()) return false;
@@ -143,7 +145,8 @@ bool rw_fasta::reader::next_record(std::string& record, unsigned int& seqno, uns
         }
         d.refill();
     }
-    record.assign(d.buf.data() + d.pos, end);
+    if (append) record.append(d.buf.data() + d.pos, end);
+    else record.assign(d.buf.data() + d.pos, end);
     d.pos += end;
     seqno = ++d.seqno;
     lineno = d.lineno;

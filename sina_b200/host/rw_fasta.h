@@ -29,12 +29,15 @@ public:
 
     class reader {
     public:
-        explicit reader(const std::string& infile);  // "-" = stdin; throws std::runtime_error if unreadable
+        // "-" = stdin; throws std::runtime_error if unreadable. whole_file: ignore --fasta-block / --fasta-idx (they select
+        // a part of the QUERY file; a reference database read through this class is read whole)
+        explicit reader(const std::string& infile, bool whole_file = false);
         ~reader();
         bool operator()(tray& t);                    // false at end of input; bad sequences are skipped with a message
         // the two halves of operator(): the text of the next record (one thread), and its parsing (any thread). parse_record
         // returns false for a record with an illegal character (message printed, t.input_sequence left null)
-        bool next_record(std::string& record, unsigned int& seqno, unsigned int& lineno);
+        // (append: the record's text is appended to `record` instead of replacing it)
+        bool next_record(std::string& record, unsigned int& seqno, unsigned int& lineno, bool append = false);
         static bool parse_record(const std::string& record, unsigned int seqno, unsigned int lineno, const std::string& filename, tray& t);
         const std::string& filename() const;
         void count_skipped();
