@@ -1,6 +1,8 @@
 #include "rw_fasta.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 #include <cerrno>
@@ -215,6 +217,7 @@ struct rw_fasta::writer::priv_data {
     uint64_t offset = 0;         // next free byte of the file
     std::ostream* out = nullptr; // stdout
     bool gz = false;             // ".gz" output: every put() becomes a gzip member (members concatenate to one stream)
+    bool map = false;            // SINA_B200_MMAP_OUT=1 on a regular, uncompressed file
     std::ofstream out_csv;       // --meta-fmt csv
     std::unordered_set<std::string> relatives_written;   // --add-relatives
     bool csv_started = false;
@@ -294,6 +297,14 @@ rw_fasta::writer::writer(const std::string& outfile) : data(new priv_data) {
         data->fd = ::open(outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (data->fd < 0) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
         data->gz = is_gz(outfile);
+        struct stat st;
+        const char* e = getenv("SINA_B200_MMAP_OUT");
+        data->map = e && atoi(e) > 0 && !data->gz && fstat(data->fd, &st) == 0 && S_ISREG(st.st_mode);
+        if (data->map) {   // the mappings need read access to the file
+            ::close(data->fd);
+            data->fd = ::open(outfile.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+            if (data->fd < 0) throw std::runtime_error("Unable to open file " + outfile + " for writing.");
+        }
     }
     if (opts->fastameta == FASTA_META_CSV) {   // the output name with its extension replaced (src/rw_fasta.cpp:362-372)
         std::string csv = outfile;
@@ -336,8 +347,21 @@ void rw_fasta::writer::write_members(const std::string& members, unsigned int n_
     data->count += n_records;
     data->excluded += n_excluded;
 }
+bool rw_fasta::writer::mapped() const { return data->map; }
+char* rw_fasta::writer::map_range(uint64_t offset, size_t n) const {
+    const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE), lo = offset / page * page;
+    void* p = mmap(nullptr, (size_t)(offset - lo) + n, PROT_READ | PROT_WRITE, MAP_SHARED, data->fd, (off_t)lo);
+    if (p == MAP_FAILED) throw std::runtime_error(std::string("mmap of the output file failed: ") + strerror(errno));
+    return static_cast<char*>(p) + (offset - lo);
+}
+void rw_fasta::writer::unmap_range(char* p, uint64_t offset, size_t n) const {
+    const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE), lo = offset / page * page;
+    munmap(p - (offset - lo), (size_t)(offset - lo) + n);
+}
 uint64_t rw_fasta::writer::reserve(uint64_t nbytes, unsigned int n_records, unsigned int n_excluded) {
     const uint64_t at = data->offset;
+    if (data->map && nbytes > 0 && ftruncate(data->fd, (off_t)(at + nbytes)) != 0)
+        throw std::runtime_error(std::string("growing the output file failed: ") + strerror(errno));
     data->offset += nbytes;
     data->count += n_records;
     data->excluded += n_excluded;

@@ -76,6 +76,12 @@ public:
         bool positional() const;
         uint64_t reserve(uint64_t nbytes, unsigned int n_records, unsigned int n_excluded);
         void write_at(uint64_t offset, const char* p, size_t n) const;
+        // SINA_B200_MMAP_OUT=1: reserve() grows the file and the pool fills mappings of the reserved ranges instead of
+        // calling pwrite (buffered writes to one file serialise on its inode lock, page faults of a mapping do not).
+        // map_range() returns the address of file byte `offset`; unmap_range() takes the same arguments back.
+        bool mapped() const;
+        char* map_range(uint64_t offset, size_t n) const;
+        void unmap_range(char* p, uint64_t offset, size_t n) const;
         unsigned int written() const;
         unsigned int excluded() const;
     private:

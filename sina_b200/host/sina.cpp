@@ -10,6 +10,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -52,7 +53,7 @@ struct slice_t {
     std::shared_ptr<batch_t> batch;
     std::shared_ptr<std::atomic<int>> left;   // slices of the batch still to be written
     size_t begin = 0, end = 0;
-    uint64_t file_offset = 0;
+    uint64_t file_offset = 0, bytes = 0;      // the slice's byte range of the output file
 };
 
 template <typename T>
@@ -305,15 +306,18 @@ int real_main(int argc, const char* const* argv) {
             const auto t0 = std::chrono::steady_clock::now();
             try {
                 uint64_t at = sl.file_offset;
+                char* map = writer.mapped() && sl.bytes > 0 && !failed ? writer.map_range(sl.file_offset, sl.bytes) : nullptr;
                 for (size_t i = sl.begin; i < sl.end; i++) {
                     tray& t = sl.batch->trays[i];
                     if (sl.batch->has_record[i] && !failed) {
                         rw_fasta::writer::format_into(*t.aligned_sequence, rec);
-                        writer.write_at(at, rec.data(), rec.size());
+                        if (map) memcpy(map + (at - sl.file_offset), rec.data(), rec.size());
+                        else writer.write_at(at, rec.data(), rec.size());
                         at += rec.size();
                     }
                     t.destroy();  // src/sina.cpp:573-579
                 }
+                if (map) writer.unmap_range(map, sl.file_offset, sl.bytes);
             } catch (std::exception& e) {
                 std::lock_guard<std::mutex> l(done_mu);
                 if (!failed) failure = e.what();
@@ -383,6 +387,7 @@ int real_main(int argc, const char* const* argv) {
                 slice_t sl;
                 sl.batch = sb; sl.left = left; sl.begin = i0; sl.end = std::min(n, i0 + per); sl.file_offset = at;
                 for (size_t i = sl.begin; i < sl.end; i++) at += size[i];
+                sl.bytes = at - sl.file_offset;
                 towrite.push(std::move(sl));
             }
             if (n == 0) alive_release();

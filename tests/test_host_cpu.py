@@ -154,6 +154,27 @@ def test_cli_meta_fmt_csv(tmp_path):
                                                        b"c,\"say \"\"hi\"\"\",all\r\n")
 
 
+def test_cli_mmap_output_matches_pwrite(tmp_path):
+    """SINA_B200_MMAP_OUT=1: the output pool fills mappings of the reserved byte ranges instead of calling pwrite; same
+    bytes, over slices that start and end anywhere inside a page, and an empty result is an empty file"""
+    import random
+    rnd = random.Random(11)
+    with open(tmp_path / "in.fasta", "w") as f:
+        for i in range(1500):
+            f.write(">m%04d d\n%s\n" % (i, "".join(rnd.choice("ACGU-------") for _ in range(rnd.randint(50, 6000)))))
+    outs = []
+    for mode in ("0", "1"):
+        out = tmp_path / ("out%s.fasta" % mode)
+        r = run(["sina", "--prealigned", "-i", str(tmp_path / "in.fasta"), "-o", str(out), "--batch-size", "700", "--line-length", "77"],
+                env=dict(os.environ, SINA_B200_MMAP_OUT=mode))
+        assert r.returncode == 0, r.stderr
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1] and len(outs[0]) > 1500 * 50
+    open(tmp_path / "empty.fasta", "w").close()
+    r = run(["sina", "--prealigned", "-i", str(tmp_path / "empty.fasta"), "-o", str(tmp_path / "e.fasta")], env=dict(os.environ, SINA_B200_MMAP_OUT="1"))
+    assert r.returncode == 0 and os.path.getsize(tmp_path / "e.fasta") == 0
+
+
 def test_cli_fasta_block_and_idx(tmp_path):
     """--fasta-block B --fasta-idx i (src/rw_fasta.cpp:209-216,237-242): seek to byte B*i, skip to the next title line, read
     records until the previous one ended past byte B*(i+1). No GPU needed: --prealigned passes the sequences through."""
